@@ -1,0 +1,147 @@
+/* b200inr.h -- C ABI of the B200-native INR fit/query hot path.
+ *
+ * The reference (MRIRC/MRI-super-resolution) has no FFI of its own: its hot path is PyTorch calls made from
+ * Python.  Each entry point below names the reference expression it replaces
+ * (paths relative to the reference checkout, INR/ = implicit-neural-representations/).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns every buffer,
+ *     including workspaces; the library allocates nothing and keeps no state between calls.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is stream-ordered; no call synchronises the host.
+ *   - Return value: 0 on success, a negative B200INR_ERR_* otherwise.  Nothing throws across the ABI.
+ *   - Row order everywhere is the reference's: C-order flatten, last axis fastest (INR/SRDWI.py:12-18),
+ *     tensors are [rows, features] row-major fp32.
+ *   - The library targets sm_100a only.  There is no CPU fallback.
+ */
+#ifndef B200INR_H_
+#define B200INR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200INR_OK 0
+#define B200INR_ERR_BAD_SHAPE (-1)
+#define B200INR_ERR_BAD_ALIGN (-2)
+#define B200INR_ERR_UNSUPPORTED_ARCH (-3)
+#define B200INR_ERR_CUDA (-4)
+#define B200INR_ERR_NULL (-5)
+
+#define B200INR_ACT_SINE 0
+
+/* Network description == ctor arguments of Siren (INR/SRDWI.py:68-71, INR/INRmodel.py:123-125). */
+typedef struct b200inr_net {
+  int32_t in_features;     /* d, raw coordinate dimension, 1..4                                 */
+  int32_t hidden_features; /* H, currently 256 (the width of every BASELINE SIREN config)        */
+  int32_t hidden_layers;   /* L, hidden->hidden sine layers; there are L+1 sine layers + 1 linear */
+  int32_t out_features;    /* C, 1..32                                                           */
+  float first_omega_0;     /* omega of the first SineLayer (INR/SRDWI.py:78)                      */
+  float hidden_omega_0;    /* omega of the hidden SineLayers (INR/SRDWI.py:81)                    */
+  int32_t activation;      /* B200INR_ACT_SINE                                                   */
+  int32_t reserved;
+} b200inr_net;
+
+/* Dense coordinate grid == get_mgrid(shape) (INR/SRDWI.py:12-18) restricted to linear rows
+ * [row_begin, row_begin + rows).  Coordinates are never materialised; kernels derive them from the index. */
+typedef struct b200inr_grid {
+  int32_t ndim;      /* must equal net.in_features */
+  int32_t shape[4];  /* global grid shape; unused trailing entries = 1 */
+  int64_t row_begin; /* first global linear index covered by this call (rank shard offset) */
+} b200inr_grid;
+
+/* Per-axis sparse operator of the separable LR degradation (2x average pooling, optionally preceded by the
+ * 5-tap Gaussian sigma=0.5 blur with mirror boundary).  Built on the host by
+ * b200inr_degrade_build_axis_host and uploaded by the caller. */
+#define B200INR_DEGRADE_MAX_TAPS 8
+typedef struct b200inr_axis_taps {
+  int32_t idx[B200INR_DEGRADE_MAX_TAPS];
+  float w[B200INR_DEGRADE_MAX_TAPS];
+} b200inr_axis_taps;
+
+const char* b200inr_version(void);
+const char* b200inr_error_string(int code);
+
+/* ---- parameter layout -------------------------------------------------------------------------------
+ * Flat fp32 parameter vector in reference units (W, not omega*W), canonical order
+ *   W0[H,d] b0[H]  W1[H,H] b1[H] ... WL[H,H] bL[H]  Wf[C,H] bf[C]
+ * each segment starting at a multiple of 4 floats.  offsets[2*i], offsets[2*i+1] = start of W_i, b_i;
+ * offsets has 2*(L+2) entries.  (nn.Linear weight layout [out,in], INR/SRDWI.py:47.) */
+int b200inr_param_count(const b200inr_net* net, int64_t* n_floats);
+int b200inr_param_offsets(const b200inr_net* net, int64_t* offsets);
+
+/* bf16 tensor-core staging of the weights (omega folded in, UMMA shared-memory layout, both orientations).
+ * Replaces nothing in the reference; it is the operand format of the fused kernels. */
+int b200inr_packed_bytes(const b200inr_net* net, size_t* bytes);
+int b200inr_pack_weights(const b200inr_net* net, const float* params, void* packed, void* stream);
+
+/* Activation stash written by a training forward and consumed by backward (bf16 sin outputs in UMMA tile
+ * layout, 16-bit phases, bf16 pre-activation gradients). */
+int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes);
+
+/* ---- fused MLP ---------------------------------------------------------------------------------------
+ * Siren.forward (INR/SRDWI.py:87-91 == nn.Sequential of SineLayer.forward :58-59 and the final nn.Linear).
+ * Exactly one of coords ([rows,d] fp32) / grid must be non-NULL.
+ * out: [rows,C] fp32.  clamp != 0 applies torch.clamp(min=clamp_min) (INR/superresDWI.py:161).
+ * stash == NULL: inference/query; otherwise the stash is filled for b200inr_siren_backward. */
+int b200inr_siren_forward(const b200inr_net* net, const void* packed, const float* coords,
+                          const b200inr_grid* grid, int64_t rows, float* out, int clamp, float clamp_min,
+                          void* stash, void* stream);
+
+/* loss.backward() through Siren (autograd of INR/SRDWI.py:58-59,87-91): given dL/dout [rows,C] fp32,
+ * ACCUMULATES dL/dparams into grad_params (flat layout above, reference units).  No input gradient
+ * (SRDWI.Siren detaches its coords, INR/SRDWI.py:88). */
+int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* stash, const float* coords,
+                           const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
+                           void* stream);
+
+/* ---- loss and LR degradation -------------------------------------------------------------------------
+ * ((out - gt)**2).mean() and its gradient (INR/superresDWI.py:135; weighted form INR/INR_ERD.py:265).
+ * loss_accum[0] += sum(w*(pred-target)^2)/count ; grad = 2*w*(pred-target)/count.  weight may be NULL. */
+int b200inr_mse_loss(const float* pred, const float* target, const float* weight, int64_t n, double count,
+                     float* grad, float* loss_accum, void* stream);
+
+/* Host helper: per-axis taps of D (LR row i <- HR columns) and of its transpose (HR column x <- LR rows).
+ * n_hr must be even; blur = 0 -> 2-tap box mean; blur = 1 -> Gaussian sigma 0.5 (5 taps, mirror) then box. */
+int b200inr_degrade_build_axis_host(int32_t n_hr, int blur, b200inr_axis_taps* fwd_host /*[n_hr/2]*/,
+                                    b200inr_axis_taps* adj_host /*[n_hr]*/);
+
+/* D: hr [X,Y,ZC] -> lr [X/2,Y/2,ZC] (in-plane only, mirrors the reference's [::2, ::2] decimation axes,
+ * INR/superresDWI.py:94).  tx/ty: device copies of the fwd taps of the x/y axes. */
+int b200inr_degrade_forward(const float* hr, float* lr, int32_t X, int32_t Y, int64_t ZC,
+                            const b200inr_axis_taps* tx, const b200inr_axis_taps* ty, void* stream);
+/* D^T: lr [X/2,Y/2,ZC] -> hr [X,Y,ZC] (adjoint taps). */
+int b200inr_degrade_adjoint(const float* lr, float* hr, int32_t X, int32_t Y, int64_t ZC,
+                            const b200inr_axis_taps* ax, const b200inr_axis_taps* ay, void* stream);
+/* Fused 2x2x1 average-pool consistency loss: loss_accum[0] += sum((pool(pred)-target_lr)^2)/count and
+ * grad_hr = pool^T(2*(pool(pred)-target_lr)/count), one pass (the fast path of BASELINE config 2). */
+int b200inr_pool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC,
+                     double count, float* grad_hr, float* loss_accum, void* stream);
+
+/* ---- optimiser ----------------------------------------------------------------------------------------
+ * torch.optim.Adam.step with defaults amsgrad=False, weight_decay=0 (INR/superresDWI.py:115-116,138).
+ * state: 4 floats on device {step, bias_correction1, bias_correction2, unused}; zero-initialised by the
+ * caller, advanced by the kernel (so the call can be captured in a CUDA graph). */
+int b200inr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float* state, void* stream);
+
+/* ---- coordinate helpers (API parity; the fused kernels do not need them) ------------------------------ */
+/* get_mgrid (INR/SRDWI.py:12-18): coords [rows, ndim] fp32. */
+int b200inr_get_mgrid(const b200inr_grid* grid, int64_t rows, float* coords, void* stream);
+/* input_mapping (INR/SRDWI.py:111-116): out [rows, 2m] = cat(sin(2*pi*x@B.T), cos(2*pi*x@B.T)). */
+int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t d, int32_t m, float* out,
+                          void* stream);
+
+/* ---- self test of the tensor-core plumbing ------------------------------------------------------------
+ * One CTA computes D[128,N] = A * B^T with tcgen05.mma from swizzled shared memory.
+ * mode 0: K-major operands, a[128,K], b[N,K] row-major bf16.  mode 1: MN-major operands, a[K,128], b[K,N].
+ * lbo/sbo < 0 select the library's own descriptor strides (the values used by the production kernels). */
+int b200inr_selftest_umma(int mode, const void* a_bf16, const void* b_bf16, float* d, int32_t N, int32_t K,
+                          int32_t lbo_a, int32_t sbo_a, int32_t lbo_b, int32_t sbo_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200INR_H_ */

@@ -1,0 +1,309 @@
+// capi.cu -- the extern "C" boundary declared in include/b200inr.h: argument checks, launch, error codes.
+// No state is kept between calls except the cached SM count of the current device.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200inr {
+int launch_selftest_umma(int mode, const void* a, const void* b, float* d, int N, int K, int lbo_a, int sbo_a,
+                         int lbo_b, int sbo_b, cudaStream_t stream);
+int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream);
+int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                     cudaStream_t stream);
+int launch_siren_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                     int num_sms, cudaStream_t stream);
+int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords, const b200inr_grid* grid,
+                       int64_t rows, float* grad_params, int num_sms, cudaStream_t stream);
+int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
+               float* loss_accum, cudaStream_t stream);
+int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
+                    float* loss_accum, cudaStream_t stream);
+int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int64_t ZC, const b200inr_axis_taps* tx,
+                const b200inr_axis_taps* ty, cudaStream_t stream);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float* state, cudaStream_t stream);
+int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
+int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
+
+static int check_net(const b200inr_net* net) {
+  if (!net) return B200INR_ERR_NULL;
+  if (net->hidden_features != 256) return B200INR_ERR_BAD_SHAPE;
+  if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
+  if (net->hidden_layers < 0 || net->hidden_layers + 1 > kMaxSineLayers) return B200INR_ERR_BAD_SHAPE;
+  if (net->out_features < 1 || net->out_features > kOutPad) return B200INR_ERR_BAD_SHAPE;
+  if (net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
+  return B200INR_OK;
+}
+
+static int check_grid(const b200inr_net* net, const b200inr_grid* grid, int64_t rows) {
+  if (grid->ndim != net->in_features) return B200INR_ERR_BAD_SHAPE;
+  long long tot = 1;
+  for (int j = 0; j < grid->ndim; ++j) {
+    if (grid->shape[j] < 1) return B200INR_ERR_BAD_SHAPE;
+    tot *= grid->shape[j];
+  }
+  if (grid->row_begin < 0 || grid->row_begin + rows > tot) return B200INR_ERR_BAD_SHAPE;
+  return B200INR_OK;
+}
+
+// sm_100 only; SM count of the current device (cached per device ordinal).
+static int device_sms(int* sms) {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200INR_ERR_CUDA;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) {
+    *sms = cached[dev];
+    return B200INR_OK;
+  }
+  int major = 0, n = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return B200INR_ERR_CUDA;
+  if (major != 10) return B200INR_ERR_UNSUPPORTED_ARCH;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200INR_ERR_CUDA;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  *sms = n;
+  return B200INR_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace b200inr
+
+using namespace b200inr;
+
+extern "C" {
+
+const char* b200inr_version(void) { return "b200inr 0.1 (sm_100a)"; }
+
+const char* b200inr_error_string(int code) {
+  switch (code) {
+    case B200INR_OK: return "ok";
+    case B200INR_ERR_BAD_SHAPE: return "unsupported or inconsistent shape";
+    case B200INR_ERR_BAD_ALIGN: return "pointer not 16-byte aligned";
+    case B200INR_ERR_UNSUPPORTED_ARCH: return "device is not sm_100 (B200)";
+    case B200INR_ERR_CUDA: return "CUDA runtime error";
+    case B200INR_ERR_NULL: return "null pointer argument";
+    default: return "unknown error";
+  }
+}
+
+int b200inr_param_count(const b200inr_net* net, int64_t* n_floats) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!n_floats) return B200INR_ERR_NULL;
+  *n_floats = param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, nullptr);
+  return B200INR_OK;
+}
+
+int b200inr_param_offsets(const b200inr_net* net, int64_t* offsets) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!offsets) return B200INR_ERR_NULL;
+  param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, offsets);
+  return B200INR_OK;
+}
+
+int b200inr_packed_bytes(const b200inr_net* net, size_t* bytes) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!bytes) return B200INR_ERR_NULL;
+  *bytes = make_pack_layout(net->hidden_features, net->hidden_layers).total;
+  return B200INR_OK;
+}
+
+int b200inr_pack_weights(const b200inr_net* net, const float* params, void* packed, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!params || !packed) return B200INR_ERR_NULL;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(packed) & 1023)) return B200INR_ERR_BAD_ALIGN;
+  return launch_pack(net, params, packed, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!bytes) return B200INR_ERR_NULL;
+  if (rows < 0) return B200INR_ERR_BAD_SHAPE;
+  *bytes = make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
+  return B200INR_OK;
+}
+
+int b200inr_siren_forward(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                          int64_t rows, float* out, int clamp, float clamp_min, void* stash, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !out) return B200INR_ERR_NULL;
+  if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if (grid && (e = check_grid(net, grid, rows))) return e;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (stash && (reinterpret_cast<uintptr_t>(stash) & 1023)))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  return launch_siren_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* stash, const float* coords,
+                           const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
+                           void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !stash || !grad_out || !grad_params) return B200INR_ERR_NULL;
+  if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if (grid && (e = check_grid(net, grid, rows))) return e;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023) ||
+      !aligned16(grad_params))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((e = launch_siren_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
+  return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, s);
+}
+
+int b200inr_mse_loss(const float* pred, const float* target, const float* weight, int64_t n, double count,
+                     float* grad, float* loss_accum, void* stream) {
+  if (!pred || !target) return B200INR_ERR_NULL;
+  if (n < 0 || !(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  if (n == 0) return B200INR_OK;
+  return launch_mse(pred, target, weight, n, count, grad, loss_accum, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_degrade_build_axis_host(int32_t n_hr, int blur, b200inr_axis_taps* fwd_host, b200inr_axis_taps* adj_host) {
+  if (!fwd_host || !adj_host) return B200INR_ERR_NULL;
+  if (n_hr < 2 || (n_hr & 1)) return B200INR_ERR_BAD_SHAPE;
+  const int n_lr = n_hr / 2;
+  // Gaussian sigma = 0.5, truncate 4.0 -> radius 2 (scipy.ndimage.gaussian_filter), normalised in double.
+  double g[5];
+  double gs = 0.0;
+  for (int t = -2; t <= 2; ++t) {
+    g[t + 2] = exp(-0.5 * double(t * t) / 0.25);
+    gs += g[t + 2];
+  }
+  for (int t = 0; t < 5; ++t) g[t] /= gs;
+  auto mirror = [n_hr](int i) {  // scipy 'mirror' == numpy 'reflect': d c b | a b c d | c b a
+    if (n_hr == 1) return 0;
+    const int period = 2 * (n_hr - 1);
+    i %= period;
+    if (i < 0) i += period;
+    return i < n_hr ? i : period - i;
+  };
+  memset(fwd_host, 0, sizeof(b200inr_axis_taps) * size_t(n_lr));
+  memset(adj_host, 0, sizeof(b200inr_axis_taps) * size_t(n_hr));
+  for (int i = 0; i < n_lr; ++i) {
+    double acc_w[B200INR_DEGRADE_MAX_TAPS];
+    int acc_i[B200INR_DEGRADE_MAX_TAPS];
+    int cnt = 0;
+    auto push = [&](int idx, double w) {
+      for (int k = 0; k < cnt; ++k)
+        if (acc_i[k] == idx) {
+          acc_w[k] += w;
+          return true;
+        }
+      if (cnt == B200INR_DEGRADE_MAX_TAPS) return false;
+      acc_i[cnt] = idx;
+      acc_w[cnt] = w;
+      ++cnt;
+      return true;
+    };
+    for (int s = 0; s < 2; ++s) {
+      const int x = 2 * i + s;
+      if (blur) {
+        for (int t = -2; t <= 2; ++t)
+          if (!push(mirror(x + t), 0.5 * g[t + 2])) return B200INR_ERR_BAD_SHAPE;
+      } else {
+        if (!push(x, 0.5)) return B200INR_ERR_BAD_SHAPE;
+      }
+    }
+    for (int k = 0; k < cnt; ++k) {
+      fwd_host[i].idx[k] = acc_i[k];
+      fwd_host[i].w[k] = float(acc_w[k]);
+      // transpose entry
+      b200inr_axis_taps& a = adj_host[acc_i[k]];
+      int slot = -1;
+      for (int q = 0; q < B200INR_DEGRADE_MAX_TAPS; ++q)
+        if (a.w[q] == 0.f) {
+          slot = q;
+          break;
+        }
+      if (slot < 0) return B200INR_ERR_BAD_SHAPE;
+      a.idx[slot] = i;
+      a.w[slot] = float(acc_w[k]);
+    }
+  }
+  return B200INR_OK;
+}
+
+int b200inr_degrade_forward(const float* hr, float* lr, int32_t X, int32_t Y, int64_t ZC, const b200inr_axis_taps* tx,
+                            const b200inr_axis_taps* ty, void* stream) {
+  if (!hr || !lr || !tx || !ty) return B200INR_ERR_NULL;
+  if (X < 2 || Y < 2 || (X & 1) || (Y & 1) || ZC < 1) return B200INR_ERR_BAD_SHAPE;
+  return launch_taps(hr, lr, Y, X / 2, Y / 2, ZC, tx, ty, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_degrade_adjoint(const float* lr, float* hr, int32_t X, int32_t Y, int64_t ZC, const b200inr_axis_taps* ax,
+                            const b200inr_axis_taps* ay, void* stream) {
+  if (!hr || !lr || !ax || !ay) return B200INR_ERR_NULL;
+  if (X < 2 || Y < 2 || (X & 1) || (Y & 1) || ZC < 1) return B200INR_ERR_BAD_SHAPE;
+  return launch_taps(lr, hr, Y / 2, X, Y, ZC, ax, ay, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_pool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC, double count,
+                     float* grad_hr, float* loss_accum, void* stream) {
+  if (!pred_hr || !target_lr) return B200INR_ERR_NULL;
+  if (!(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  return launch_pool_mse(pred_hr, target_lr, X, Y, ZC, count, grad_hr, loss_accum, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float* state, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return B200INR_ERR_NULL;
+  if (n < 0) return B200INR_ERR_BAD_SHAPE;
+  if (n == 0) return B200INR_OK;
+  return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_get_mgrid(const b200inr_grid* grid, int64_t rows, float* coords, void* stream) {
+  if (!grid || !coords) return B200INR_ERR_NULL;
+  if (grid->ndim < 1 || grid->ndim > 4 || rows < 0) return B200INR_ERR_BAD_SHAPE;
+  GridDesc g{};
+  g.ndim = grid->ndim;
+  long long tot = 1;
+  for (int j = 0; j < 4; ++j) {
+    g.shape[j] = (j < grid->ndim) ? grid->shape[j] : 1;
+    if (g.shape[j] < 1) return B200INR_ERR_BAD_SHAPE;
+    tot *= g.shape[j];
+  }
+  g.row_begin = grid->row_begin;
+  g.total = tot;
+  if (grid->row_begin < 0 || grid->row_begin + rows > tot) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  return launch_mgrid(g, rows, coords, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t d, int32_t m, float* out,
+                          void* stream) {
+  if (!x || !B || !out) return B200INR_ERR_NULL;
+  if (rows < 0 || d < 1 || m < 1) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  return launch_ffm(x, B, rows, d, m, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_selftest_umma(int mode, const void* a_bf16, const void* b_bf16, float* d, int32_t N, int32_t K,
+                          int32_t lbo_a, int32_t sbo_a, int32_t lbo_b, int32_t sbo_b, void* stream) {
+  if (!a_bf16 || !b_bf16 || !d) return B200INR_ERR_NULL;
+  if (mode != 0 && mode != 1) return B200INR_ERR_BAD_SHAPE;
+  int sms = 0;
+  int e = device_sms(&sms);
+  if (e) return e;
+  return launch_selftest_umma(mode, a_bf16, b_bf16, d, N, K, lbo_a, sbo_a, lbo_b, sbo_b,
+                              static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

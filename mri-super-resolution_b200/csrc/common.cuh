@@ -1,0 +1,140 @@
+// common.cuh -- byte layouts shared by the kernels and the C-ABI launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200inr.h"
+
+namespace b200inr {
+
+constexpr int kTileRows = 128;     // coordinate rows per tile == UMMA M
+constexpr int kMaxSineLayers = 8;  // L + 1 <= 8
+constexpr int kOutPad = 32;        // final layer N (C <= 32)
+constexpr int kDzoPad = 64;        // dL/dout tile width (one 128-byte swizzle row)
+
+// Byte offsets inside the packed (bf16, omega-folded) weight buffer of a width-H SIREN.
+struct PackLayout {
+  size_t w0;     // float4[H]            omega0 * W0 rows, zero padded to 4 inputs
+  size_t bias;   // float[(L+1)*H + 32]  omega * b of the sine layers, then the final bias (padded to 32)
+  size_t wh;     // L x [H/64][H][64]    forward B operand of hidden layer l (N = out, K = in), omega_h * W_l
+  size_t wht;    // L x [H/64][H][64]    dgrad   B operand of hidden layer l (N = in, K = out), omega_h * W_l^T
+  size_t wf;     // [H/64][32][64]       forward B operand of the final linear (N = c, K = in)
+  size_t wft;    // [1][H][64]           dgrad   B operand of the final linear (N = in, K = c padded to 64)
+  size_t total;
+};
+
+__host__ __device__ inline PackLayout make_pack_layout(int H, int L) {
+  PackLayout p;
+  size_t o = 0;
+  p.w0 = o;
+  o += size_t(H) * 16;
+  p.bias = o;
+  o += (size_t(L + 1) * H + 32) * 4;
+  o = (o + 1023) & ~size_t(1023);
+  p.wh = o;
+  o += size_t(L) * H * H * 2;
+  p.wht = o;
+  o += size_t(L) * H * H * 2;
+  p.wf = o;
+  o += size_t(H / 64) * kOutPad * 128;
+  p.wft = o;
+  o += size_t(H) * 128;
+  p.total = o;
+  return p;
+}
+
+// Activation stash for `rows` coordinates (T = ceil(rows/128) tiles), width-H SIREN with L+1 sine layers.
+struct StashLayout {
+  size_t y;             // (L+1) x T x [H/64][128][64] bf16   sin outputs, UMMA tile layout
+  size_t ph;            // (L+1) x T x [H/8][128][8]   u16    phase = round(theta * 65536 / 2pi) mod 65536
+  size_t dz;            // (L+1) x T x [H/64][128][64] bf16   dL/dtheta, UMMA tile layout
+  size_t dzo;           // T x [128][64] bf16                  dL/dout, one block per tile
+  size_t layer_stride;  // bytes per layer inside y / ph / dz
+  size_t tile_bytes;    // 128 * H * 2
+  size_t total;
+  int64_t tiles;
+};
+
+__host__ __device__ inline StashLayout make_stash_layout(int H, int L, int64_t rows) {
+  StashLayout s;
+  s.tiles = (rows + kTileRows - 1) / kTileRows;
+  s.tile_bytes = size_t(kTileRows) * H * 2;
+  s.layer_stride = size_t(s.tiles) * s.tile_bytes;
+  size_t o = 0;
+  s.y = o;
+  o += size_t(L + 1) * s.layer_stride;
+  s.ph = o;
+  o += size_t(L + 1) * s.layer_stride;
+  s.dz = o;
+  o += size_t(L + 1) * s.layer_stride;
+  s.dzo = o;
+  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.total = o;
+  return s;
+}
+
+// Flat fp32 parameter offsets (in floats): W_i at off[2i], b_i at off[2i+1], i = 0..L+1.
+__host__ __device__ inline int64_t param_offsets(int d, int H, int L, int C, int64_t* off) {
+  int64_t o = 0;
+  auto seg = [&](int64_t n) {
+    int64_t at = o;
+    o += (n + 3) & ~int64_t(3);
+    return at;
+  };
+  int64_t w, b;
+  w = seg(int64_t(H) * d);
+  b = seg(H);
+  if (off) { off[0] = w; off[1] = b; }
+  for (int l = 1; l <= L; ++l) {
+    w = seg(int64_t(H) * H);
+    b = seg(H);
+    if (off) { off[2 * l] = w; off[2 * l + 1] = b; }
+  }
+  w = seg(int64_t(C) * H);
+  b = seg(C);
+  if (off) { off[2 * (L + 1)] = w; off[2 * (L + 1) + 1] = b; }
+  return o;
+}
+
+struct GridDesc {
+  int ndim;
+  int shape[4];
+  long long row_begin;
+  long long total;  // product of shape
+};
+
+// torch.linspace(-1, 1, n)[i] in fp32, bit-for-bit (ATen RangeFactories: symmetric two-sided evaluation,
+// step = (end - start) / (n - 1), multiply and add rounded separately).
+__host__ __device__ inline float linspace_m1p1(int i, int n) {
+  if (n <= 1) return -1.0f;
+  const float step = 2.0f / float(n - 1);
+#ifdef __CUDA_ARCH__
+  if (i < n / 2) return __fadd_rn(-1.0f, __fmul_rn(step, float(i)));
+  return __fsub_rn(1.0f, __fmul_rn(step, float(n - 1 - i)));
+#else
+  volatile float prod;
+  if (i < n / 2) {
+    prod = step * float(i);
+    return -1.0f + prod;
+  }
+  prod = step * float(n - 1 - i);
+  return 1.0f - prod;
+#endif
+}
+
+__device__ inline void grid_coords(const GridDesc& g, long long row, float (&x)[4]) {
+  long long idx = g.row_begin + row;
+  if (idx >= g.total) idx = g.total - 1;
+  x[0] = x[1] = x[2] = x[3] = 0.0f;
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {
+    if (j < g.ndim) {
+      const int n = g.shape[j];
+      const int i = int(idx % n);
+      idx /= n;
+      x[j] = linspace_m1p1(i, n);
+    }
+  }
+}
+
+}  // namespace b200inr

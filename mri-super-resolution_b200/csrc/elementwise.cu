@@ -1,0 +1,254 @@
+// elementwise.cu -- the HBM-bound kernels of the fit step: MSE loss, LR degradation (forward / adjoint / fused
+// 2x2x1 pooling loss), Adam, plus get_mgrid / input_mapping for API parity.  All are coalesced along the fastest
+// axis, 128-bit vectorised where the extent allows, and launched on grids that are multiples of the SM count.
+#include "common.cuh"
+
+namespace b200inr {
+
+constexpr int kEwThreads = 256;
+constexpr int kSmCount = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One atomicAdd per block.
+__device__ __forceinline__ void block_accumulate(float v, float* dst) {
+  __shared__ float part[kEwThreads / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = (threadIdx.x < kEwThreads / 32) ? part[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(dst, s);
+  }
+}
+
+// ------------------------------------------------------------------ ((out - gt)**2).mean()   INR/superresDWI.py:135
+__global__ void __launch_bounds__(kEwThreads) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                         const float* __restrict__ weight, long long n, float inv_count,
+                                                         float* __restrict__ grad, float* loss_accum) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float r = pred[i] - target[i];
+    const float w = weight ? weight[i] : 1.f;
+    acc = fmaf(w * r, r, acc);
+    if (grad) grad[i] = 2.f * w * r * inv_count;
+  }
+  if (loss_accum) block_accumulate(acc * inv_count, loss_accum);
+}
+
+int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
+               float* loss_accum, cudaStream_t stream) {
+  long long blocks = (n + kEwThreads * 4 - 1) / (kEwThreads * 4);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kSmCount * 8) blocks = kSmCount * 8;
+  mse_kernel<<<int(blocks), kEwThreads, 0, stream>>>(pred, target, weight, n, float(1.0 / count), grad, loss_accum);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ fused 2x2x1 average-pool consistency loss
+// pred [X][Y][ZC], target [X/2][Y/2][ZC].  One thread handles 4 consecutive zc of one LR voxel column:
+// 4 x 16 B loads of pred, 1 x 16 B load of target, 4 x 16 B stores of grad.  
+template <int V>
+__global__ void __launch_bounds__(kEwThreads) pool_mse_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ target, int X, int Y,
+                                                              long long ZC, float inv_count, float* __restrict__ grad,
+                                                              float* loss_accum) {
+  const long long zcv = ZC / V;
+  const long long total = (long long)(X / 2) * (Y / 2) * zcv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long zc = (i % zcv) * V;
+    const long long xy = i / zcv;
+    const int yl = int(xy % (Y / 2));
+    const int xl = int(xy / (Y / 2));
+    const long long h00 = ((long long)(2 * xl) * Y + 2 * yl) * ZC + zc;
+    const long long h01 = h00 + ZC;
+    const long long h10 = h00 + (long long)Y * ZC;
+    const long long h11 = h10 + ZC;
+    const long long lo = ((long long)xl * (Y / 2) + yl) * ZC + zc;
+    float a[V], b[V], c[V], d[V], t[V], g[V];
+    if (V == 4) {
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(pred + h00);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(pred + h01);
+      *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(pred + h10);
+      *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(pred + h11);
+      *reinterpret_cast<float4*>(t) = *reinterpret_cast<const float4*>(target + lo);
+    } else {
+      a[0] = pred[h00]; b[0] = pred[h01]; c[0] = pred[h10]; d[0] = pred[h11]; t[0] = target[lo];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float r = 0.25f * ((a[j] + b[j]) + (c[j] + d[j])) - t[j];
+      acc = fmaf(r, r, acc);
+      g[j] = 0.5f * r * inv_count;  // 2 * r / count * 1/4
+    }
+    if (grad) {
+      if (V == 4) {
+        const float4 gv = *reinterpret_cast<float4*>(g);
+        *reinterpret_cast<float4*>(grad + h00) = gv;
+        *reinterpret_cast<float4*>(grad + h01) = gv;
+        *reinterpret_cast<float4*>(grad + h10) = gv;
+        *reinterpret_cast<float4*>(grad + h11) = gv;
+      } else {
+        grad[h00] = g[0]; grad[h01] = g[0]; grad[h10] = g[0]; grad[h11] = g[0];
+      }
+    }
+  }
+  if (loss_accum) block_accumulate(acc * inv_count, loss_accum);
+}
+
+int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
+                    float* loss_accum, cudaStream_t stream) {
+  if ((X & 1) || (Y & 1) || X < 2 || Y < 2 || ZC < 1) return B200INR_ERR_BAD_SHAPE;
+  const bool vec = (ZC % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
+                                      reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
+  const long long total = (long long)(X / 2) * (Y / 2) * (vec ? ZC / 4 : ZC);
+  long long blocks = (total + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  if (vec)
+    pool_mse_kernel<4><<<int(blocks), kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, float(1.0 / count), grad,
+                                                               loss_accum);
+  else
+    pool_mse_kernel<1><<<int(blocks), kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, float(1.0 / count), grad,
+                                                               loss_accum);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ separable in-plane degradation with taps
+// out[o_x][o_y][zc] = sum_a sum_b tx[o_x].w[a] * ty[o_y].w[b] * in[tx[o_x].idx[a]][ty[o_y].idx[b]][zc]
+// Serves D (in = HR, out = LR, forward taps) and D^T (in = LR, out = HR, adjoint taps).  Taps with w == 0 are
+// skipped; the tap tables sit in shared memory.
+__global__ void __launch_bounds__(kEwThreads) taps_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          int in_y, int out_x, int out_y, long long ZC,
+                                                          const b200inr_axis_taps* __restrict__ tx,
+                                                          const b200inr_axis_taps* __restrict__ ty) {
+  const long long total = (long long)out_x * out_y * ZC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long zc = i % ZC;
+    const long long xy = i / ZC;
+    const int oy = int(xy % out_y);
+    const int ox = int(xy / out_y);
+    const b200inr_axis_taps ax = tx[ox];
+    const b200inr_axis_taps ay = ty[oy];
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < B200INR_DEGRADE_MAX_TAPS; ++a) {
+      if (ax.w[a] == 0.f) continue;
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < B200INR_DEGRADE_MAX_TAPS; ++b) {
+        if (ay.w[b] == 0.f) continue;
+        row = fmaf(ay.w[b], in[((long long)ax.idx[a] * in_y + ay.idx[b]) * ZC + zc], row);
+      }
+      acc = fmaf(ax.w[a], row, acc);
+    }
+    out[i] = acc;
+  }
+}
+
+int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int64_t ZC, const b200inr_axis_taps* tx,
+                const b200inr_axis_taps* ty, cudaStream_t stream) {
+  const long long total = (long long)out_x * out_y * ZC;
+  long long blocks = (total + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  taps_kernel<<<int(blocks), kEwThreads, 0, stream>>>(in, out, in_y, out_x, out_y, ZC, tx, ty);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ torch.optim.Adam.step   INR/superresDWI.py:115-116,138
+// Arithmetic follows torch's single-tensor formulation (bias corrections in double on the step count, everything
+// else fp32): m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).
+__global__ void __launch_bounds__(kEwThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v, long long n,
+                                                          float lr, float beta1, float beta2, float eps,
+                                                          const float* __restrict__ state) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double step = double(state[0]) + 1.0;
+    const double bc1 = 1.0 - pow(double(beta1), step);
+    const double bc2 = 1.0 - pow(double(beta2), step);
+    s_step_size = float(double(lr) / bc1);
+    s_bc2_sqrt = float(sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    float mi = m[i], vi = v[i];
+    mi = fmaf(gi - mi, omb1, mi);
+    vi = fmaf(omb2 * gi, gi, beta2 * vi);
+    const float denom = __fsqrt_rn(vi) / bc2_sqrt + eps;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+__global__ void adam_tick_kernel(float* state) { state[0] += 1.f; }
+
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float* state, cudaStream_t stream) {
+  long long blocks = (n + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 8) blocks = kSmCount * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<int(blocks), kEwThreads, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, state);
+  adam_tick_kernel<<<1, 1, 0, stream>>>(state);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ get_mgrid   INR/SRDWI.py:12-18
+__global__ void __launch_bounds__(kEwThreads) mgrid_kernel(GridDesc g, long long rows, float* __restrict__ coords) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += stride) {
+    float x[4];
+    grid_coords(g, r, x);
+    for (int j = 0; j < g.ndim; ++j) coords[r * g.ndim + j] = x[j];
+  }
+}
+
+int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream) {
+  long long blocks = (rows + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 8) blocks = kSmCount * 8;
+  if (blocks < 1) blocks = 1;
+  mgrid_kernel<<<int(blocks), kEwThreads, 0, stream>>>(g, rows, coords);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ input_mapping   INR/SRDWI.py:111-116
+// out[r, k] = sin(p), out[r, m + k] = cos(p), p = sum_j (2*pi*x[r, j]) * B[k, j]   (sin block first).
+__global__ void __launch_bounds__(kEwThreads) ffm_kernel(const float* __restrict__ x, const float* __restrict__ B,
+                                                         long long rows, int d, int m, float* __restrict__ out) {
+  const long long total = rows * m;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / m;
+    const int k = int(i % m);
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) acc = fmaf(__fmul_rn(6.283185307179586f, x[r * d + j]), B[(long long)k * d + j], acc);
+    float s, c;
+    sincosf(acc, &s, &c);
+    out[r * 2 * m + k] = s;
+    out[r * 2 * m + m + k] = c;
+  }
+}
+
+int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream) {
+  long long blocks = (rows * m + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  ffm_kernel<<<int(blocks), kEwThreads, 0, stream>>>(x, B, rows, d, m, out);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+}  // namespace b200inr

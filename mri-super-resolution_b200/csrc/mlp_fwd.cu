@@ -1,0 +1,363 @@
+// mlp_fwd.cu -- fused SIREN forward (query and training forward) for sm_100a.
+//
+// Replaces Siren.forward = nn.Sequential(SineLayer x (L+1), nn.Linear)  (reference INR/SRDWI.py:58-59,87-91).
+//
+// One persistent CTA per SM walks 128-row coordinate tiles.  Per tile every layer stays on chip:
+//   layer 0      : fp32 FMA on CUDA cores straight from the voxel index (get_mgrid never materialised),
+//   layers 1..L  : tcgen05.mma 128x256x256 (bf16 in, fp32 accumulate in TMEM), weights streamed from L2 by the
+//                  bulk-copy (TMA) engine into a 4-slot ring of 64-wide K chunks,
+//   epilogue     : tcgen05.ld -> +bias -> sin -> bf16 -> swizzled shared memory (the next layer's A operand),
+//   final linear : tcgen05.mma 128x32x256, +bias, optional clamp, coalesced fp32 store.
+// In training mode the epilogue also stashes sin outputs (bulk store of the finished A tile) and 16-bit phases.
+//
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200inr {
+
+constexpr int kFwdThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kEpiBarId = 1;
+
+struct FwdParams {
+  const uint8_t* packed;
+  PackLayout pl;
+  const float* coords;  // [rows, d] or nullptr
+  GridDesc grid;        // used when coords == nullptr
+  long long rows;
+  int num_tiles;
+  int d, L, C;
+  float* out;
+  int clamp;
+  float clamp_min;
+  uint8_t* stash_y;   // nullptr => inference
+  uint8_t* stash_ph;
+  size_t stash_layer_stride;
+};
+
+template <int H>
+struct FwdSmem {
+  static constexpr int kKB = H / 64;                 // 64-wide K blocks
+  static constexpr int kABlock = kTileRows * 128;    // bytes of one [128][64] bf16 block
+  static constexpr int kABytes = kKB * kABlock;      // 64 KB for H = 256
+  static constexpr int kSlotBytes = H * 128;         // one K chunk of a hidden layer: [H rows][64]
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = kABytes;
+  static constexpr int kOffW0 = kOffW + kKB * kSlotBytes;
+  static constexpr int kOffBias = kOffW0 + H * 16;
+  static constexpr int kOffBar = kOffBias + (kMaxSineLayers * H + 32) * 4;
+  static constexpr int kBytes = kOffBar + 128;
+};
+
+constexpr float kPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
+constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
+
+// Activation + stores for 8 consecutive columns [col, col+8) of row r.
+template <bool kStash>
+__device__ __forceinline__ void emit_sine_chunk(const float (&th)[8], uint8_t* a_smem, int r, int col,
+                                                uint8_t* ph_tile) {
+  uint32_t yb[4];
+  uint32_t ph[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float s0 = __sinf(th[2 * j]);
+    const float s1 = __sinf(th[2 * j + 1]);
+    yb[j] = pack_bf16x2(s0, s1);
+    if (kStash) {
+      const uint32_t p0 = __float_as_uint(fmaf(th[2 * j], kPhaseScale, kPhaseMagic));
+      const uint32_t p1 = __float_as_uint(fmaf(th[2 * j + 1], kPhaseScale, kPhaseMagic));
+      ph[j] = __byte_perm(p0, p1, 0x5410);
+    }
+  }
+  const int kb = col >> 6;
+  const int ch = (col & 63) >> 3;
+  *reinterpret_cast<uint4*>(a_smem + kb * (kTileRows * 128) + sw128_chunk_off(r, ch)) =
+      make_uint4(yb[0], yb[1], yb[2], yb[3]);
+  if (kStash) {
+    *reinterpret_cast<uint4*>(ph_tile + (size_t(col >> 3) * kTileRows + r) * 16) =
+        make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  }
+}
+
+template <int H, bool kStash>
+__global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
+  using S = FwdSmem<H>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic shared memory is only guaranteed 16-byte aligned: align to the 1024 B the swizzle atoms need
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem + S::kOffA;
+  uint8_t* w_smem = smem + S::kOffW;
+  float4* w0_smem = reinterpret_cast<float4*>(smem + S::kOffW0);
+  float* bias_smem = reinterpret_cast<float*>(smem + S::kOffBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* w_full = bars;       // [4]
+  uint64_t* w_empty = bars + 4;  // [4]
+  uint64_t* a_ready = bars + 8;
+  uint64_t* d_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int L = p.L;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    w0_smem[i] = reinterpret_cast<const float4*>(p.packed + p.pl.w0)[i];
+  for (int i = threadIdx.x; i < (L + 1) * H + 32; i += blockDim.x)
+    bias_smem[i] = reinterpret_cast<const float*>(p.packed + p.pl.bias)[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::kKB; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(a_ready, kEpiThreads);
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      uint32_t use = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 1; l <= L + 1; ++l) {
+          const bool hidden = (l <= L);
+          const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
+          const uint32_t bytes = hidden ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            if (use > 0) mbar_wait(&w_empty[kb], (use - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[kb], bytes);
+            bulk_g2s(w_smem + kb * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[kb]);
+          }
+          ++use;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint64_t hi = smem_desc_hi_sw128(0, 1024);
+      const uint32_t a_base = smem_u32(a_smem);
+      const uint32_t w_base = smem_u32(w_smem);
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 1; l <= L + 1; ++l) {
+          const uint32_t idesc = (l <= L) ? idesc_bf16(128, H, false, false) : idesc_bf16(128, kOutPad, false, false);
+          mbar_wait(a_ready, n & 1);
+          tc_fence_after();
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            mbar_wait(&w_full[kb], n & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
+              const uint64_t db = smem_desc(w_base + kb * S::kSlotBytes + k4 * 32, hi);
+              umma_bf16_ss(tmem_d, da, db, idesc, (kb | k4) != 0);
+            }
+            umma_commit(&w_empty[kb]);
+          }
+          umma_commit(d_full);
+          ++n;
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int et = threadIdx.x - 64;  // 0..255
+    const int q = warp & 3;           // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;    // column half
+    const int r = q * 32 + lane;      // row inside the tile
+    const uint32_t t_lane = uint32_t(q * 32) << 16;
+    uint32_t n = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const long long row0 = (long long)tile * kTileRows;
+      uint8_t* ph_tile = kStash ? p.stash_ph + size_t(tile) * S::kABytes : nullptr;
+      uint8_t* y_tile = kStash ? p.stash_y + size_t(tile) * S::kABytes : nullptr;
+
+      // ---- layer 0 on CUDA cores
+      {
+        float x[4];
+        if (p.coords != nullptr) {
+          long long row = row0 + r;
+          if (row >= p.rows) row = p.rows - 1;
+          x[0] = x[1] = x[2] = x[3] = 0.0f;
+          for (int j = 0; j < p.d; ++j) x[j] = p.coords[row * p.d + j];
+        } else {
+          grid_coords(p.grid, row0 + r, x);
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = h * 128 + cc * 32 + g * 8;
+            float th[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w = w0_smem[col + j];
+              float acc = bias_smem[col + j];
+              acc = fmaf(x[0], w.x, acc);
+              acc = fmaf(x[1], w.y, acc);
+              acc = fmaf(x[2], w.z, acc);
+              acc = fmaf(x[3], w.w, acc);
+              th[j] = acc;
+            }
+            emit_sine_chunk<kStash>(th, a_smem, r, col, ph_tile);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        if (kStash) {
+          named_bar_sync(kEpiBarId, kEpiThreads);
+          if (et == 0) {
+            bulk_s2g(y_tile, a_smem, S::kABytes);
+            bulk_commit();
+          }
+        }
+        mbar_arrive(a_ready);
+      }
+
+      // ---- hidden layers
+      for (int l = 1; l <= L; ++l) {
+        mbar_wait(d_full, n & 1);
+        ++n;
+        tc_fence_after();
+        if (kStash) {
+          if (et == 0) bulk_wait_read0();
+          named_bar_sync(kEpiBarId, kEpiThreads);
+        }
+        const float* bl = bias_smem + l * H;
+        uint8_t* ph_l = kStash ? ph_tile + size_t(l) * p.stash_layer_stride : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = h * 128 + cc * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_d + t_lane + col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float th[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bl + col0 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4);
+            th[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+            th[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+            th[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+            th[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+            th[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+            th[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+            th[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+            th[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+            emit_sine_chunk<kStash>(th, a_smem, r, col0 + g * 8, ph_l);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        if (kStash) {
+          named_bar_sync(kEpiBarId, kEpiThreads);
+          if (et == 0) {
+            bulk_s2g(y_tile + size_t(l) * p.stash_layer_stride, a_smem, S::kABytes);
+            bulk_commit();
+          }
+        }
+        mbar_arrive(a_ready);
+      }
+
+      // ---- final linear: D[:, 0:32) + bias -> out
+      {
+        mbar_wait(d_full, n & 1);
+        ++n;
+        tc_fence_after();
+        if (kStash && et == 0) bulk_wait_read0();
+        named_bar_sync(kEpiBarId, kEpiThreads);  // A tile is free: reuse it as the fp32 output staging area
+        float* stage = reinterpret_cast<float*>(a_smem);
+        const int C = p.C;
+        if (h == 0) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + t_lane, v);
+          tmem_ld_wait();
+          const float* bf = bias_smem + (L + 1) * H;
+#pragma unroll
+          for (int c = 0; c < kOutPad; ++c) {
+            if (c < C) {
+              float o = __uint_as_float(v[c]) + bf[c];
+              if (p.clamp) o = fmaxf(o, p.clamp_min);
+              stage[r * C + c] = o;
+            }
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(kEpiBarId, kEpiThreads);
+        long long valid = p.rows - row0;
+        if (valid > kTileRows) valid = kTileRows;
+        const int nout = int(valid) * C;
+        float* dst = p.out + row0 * C;
+        for (int i = et; i < nout; i += kEpiThreads) dst[i] = stage[i];
+        named_bar_sync(kEpiBarId, kEpiThreads);  // staging consumed before the next tile overwrites A
+      }
+    }
+    if (kStash && et == 0) bulk_wait0();
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_d);
+}
+
+// ------------------------------------------------------------------ launcher
+int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                     cudaStream_t stream) {
+  constexpr int H = 256;
+  FwdParams p{};
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.pl = make_pack_layout(H, net->hidden_layers);
+  p.coords = coords;
+  if (grid) {
+    p.grid.ndim = grid->ndim;
+    long long tot = 1;
+    for (int j = 0; j < 4; ++j) {
+      p.grid.shape[j] = (j < grid->ndim) ? grid->shape[j] : 1;
+      tot *= p.grid.shape[j];
+    }
+    p.grid.row_begin = grid->row_begin;
+    p.grid.total = tot;
+  }
+  p.rows = rows;
+  p.num_tiles = int((rows + kTileRows - 1) / kTileRows);
+  p.d = net->in_features;
+  p.L = net->hidden_layers;
+  p.C = net->out_features;
+  p.out = out;
+  p.clamp = clamp;
+  p.clamp_min = clamp_min;
+  if (stash) {
+    StashLayout sl = make_stash_layout(H, net->hidden_layers, rows);
+    p.stash_y = reinterpret_cast<uint8_t*>(stash) + sl.y;
+    p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
+    p.stash_layer_stride = sl.layer_stride;
+  }
+  const int smem = FwdSmem<H>::kBytes + 1024;
+  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  cudaError_t e;
+  if (stash) {
+    e = cudaFuncSetAttribute(siren_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return B200INR_ERR_CUDA;
+    siren_fwd_kernel<H, true><<<grid_x, kFwdThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(siren_fwd_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return B200INR_ERR_CUDA;
+    siren_fwd_kernel<H, false><<<grid_x, kFwdThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+}  // namespace b200inr

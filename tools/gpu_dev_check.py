@@ -1,0 +1,184 @@
+"""Development check run on the GPU box: prints diagnostics for every kernel (does not assert), so that one
+gpurun call tells as much as possible.  The formal parity tests live in tests/."""
+import ctypes
+import importlib
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+L = importlib.import_module("mri-super-resolution_b200._lib")
+lib = L.load()
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def relerr(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def selftest():
+    for mode in (0, 1):
+        for (N, K) in ((256, 256), (32, 256), (256, 64)) if mode == 0 else ((256, 32), (64, 128), (256, 128)):
+            if mode == 0:
+                a = torch.randn(128, K, device=dev).bfloat16()
+                b = torch.randn(N, K, device=dev).bfloat16()
+                ref = a.float() @ b.float().T
+            else:
+                a = torch.randn(K, 128, device=dev).bfloat16()
+                b = torch.randn(K, N, device=dev).bfloat16()
+                ref = a.float().T @ b.float()
+            d = torch.zeros(128, N, device=dev)
+            rc = lib.b200inr_selftest_umma(mode, ptr(a), ptr(b), ptr(d), N, K, -1, -1, -1, -1, stream())
+            torch.cuda.synchronize()
+            print(f"selftest mode={mode} N={N} K={K} rc={rc} relerr={relerr(d, ref):.3e}", flush=True)
+
+
+class RefSiren(torch.nn.Module):
+    def __init__(self, d, H, Lh, C, w0=30.0, wh=30.0):
+        super().__init__()
+        self.lin = torch.nn.ModuleList([torch.nn.Linear(d, H)] + [torch.nn.Linear(H, H) for _ in range(Lh)])
+        self.final = torch.nn.Linear(H, C)
+        self.w0, self.wh = w0, wh
+        with torch.no_grad():
+            self.lin[0].weight.uniform_(-1 / d, 1 / d)
+            for l in self.lin[1:]:
+                l.weight.uniform_(-math.sqrt(6 / H) / wh, math.sqrt(6 / H) / wh)
+            self.final.weight.uniform_(-math.sqrt(6 / H) / wh, math.sqrt(6 / H) / wh)
+
+    def forward(self, x):
+        h = torch.sin(self.w0 * self.lin[0](x))
+        for l in self.lin[1:]:
+            h = torch.sin(self.wh * l(h))
+        return self.final(h)
+
+
+def flat_params(net, m):
+    off = L.param_offsets(net)
+    n = L.param_count(net)
+    flat = torch.zeros(n, device=dev)
+    mods = list(m.lin) + [m.final]
+    for i, mod in enumerate(mods):
+        w, b = mod.weight.detach(), mod.bias.detach()
+        flat[off[2 * i]:off[2 * i] + w.numel()] = w.reshape(-1)
+        flat[off[2 * i + 1]:off[2 * i + 1] + b.numel()] = b
+    return flat, off
+
+
+def mlp(d, Lh, C, shape, use_grid, rows=None):
+    H = 256
+    net = L.make_net(d, H, Lh, C)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    total = 1
+    for s in shape:
+        total *= s
+    rows = total if rows is None else rows
+    coords = torch.zeros(rows, d, device=dev)
+    L.check(lib.b200inr_get_mgrid(ctypes.byref(grid), rows, ptr(coords), stream()), "mgrid")
+    ref_c = torch.stack(torch.meshgrid(*[torch.linspace(-1, 1, s) for s in shape], indexing="ij"), -1).reshape(-1, d)
+    print(f"  mgrid max|diff| = {(coords.cpu() - ref_c[:rows]).abs().max().item():.3e}")
+    out = torch.full((rows, C), float("nan"), device=dev)
+    st_bytes = L.stash_bytes(net, rows)
+    stash = torch.zeros(st_bytes + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:]
+    # inference
+    L.check(lib.b200inr_siren_forward(ctypes.byref(net), ptr(pk), None if use_grid else ptr(coords),
+                                      ctypes.byref(grid) if use_grid else None, rows, ptr(out), 0, 0.0, None,
+                                      stream()), "fwd")
+    torch.cuda.synchronize()
+    ref = m(coords)
+    print(f"  fwd(infer) d={d} L={Lh} C={C} rows={rows} grid={use_grid}: relerr={relerr(out, ref.detach()):.3e} "
+          f"max|diff|={(out - ref).abs().max().item():.3e} ref_rms={ref.pow(2).mean().sqrt().item():.3e}", flush=True)
+    # training forward + backward
+    out2 = torch.full((rows, C), float("nan"), device=dev)
+    L.check(lib.b200inr_siren_forward(ctypes.byref(net), ptr(pk), None if use_grid else ptr(coords),
+                                      ctypes.byref(grid) if use_grid else None, rows, ptr(out2), 0, 0.0, ptr(st),
+                                      stream()), "fwd-train")
+    torch.cuda.synchronize()
+    print(f"  fwd(train) vs infer max|diff| = {(out2 - out).abs().max().item():.3e}")
+    target = torch.rand(rows, C, device=dev)
+    loss = ((ref - target) ** 2).mean()
+    loss.backward()
+    gout = (2.0 * (out2 - target) / (rows * C)).contiguous()
+    gflat = torch.zeros_like(flat)
+    L.check(lib.b200inr_siren_backward(ctypes.byref(net), ptr(pk), ptr(st), None if use_grid else ptr(coords),
+                                       ctypes.byref(grid) if use_grid else None, rows, ptr(gout), ptr(gflat),
+                                       stream()), "bwd")
+    torch.cuda.synchronize()
+    mods = list(m.lin) + [m.final]
+    for i, mod in enumerate(mods):
+        gw = gflat[off[2 * i]:off[2 * i] + mod.weight.numel()].reshape(mod.weight.shape)
+        gb = gflat[off[2 * i + 1]:off[2 * i + 1] + mod.bias.numel()]
+        print(f"    layer {i}: dW relerr={relerr(gw, mod.weight.grad):.3e}  db relerr={relerr(gb, mod.bias.grad):.3e} "
+              f"|dW|={mod.weight.grad.norm().item():.3e}", flush=True)
+    return net, pk, st, grid, out, gout, gflat
+
+
+def timing():
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    net = L.make_net(d, H, Lh, C)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    gout = torch.randn(rows, C, device=dev) * 1e-6
+    gflat = torch.zeros_like(flat)
+    stash = torch.zeros(L.stash_bytes(net, rows) + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:]
+
+    def t(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    g = ctypes.byref(grid)
+    nb = ctypes.byref(net)
+    ms = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 1, 0.0, None, stream()))
+    print(f"timing: query fwd {ms:.3f} ms  -> {rows / ms / 1e3:.1f} M vox/s, {rows * 541696 / ms / 1e9:.1f} TFLOP/s")
+    ms_f = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()))
+    print(f"timing: train fwd {ms_f:.3f} ms")
+    ms_b = t(lambda: lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()))
+    print(f"timing: bwd+wgrad {ms_b:.3f} ms  -> step ~{ms_f + ms_b:.3f} ms, "
+          f"{rows * 1623552 / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic")
+
+
+if __name__ == "__main__":
+    print(lib.b200inr_version().decode(), torch.cuda.get_device_name(0), flush=True)
+    which = sys.argv[1:] or ["selftest", "mlp", "timing"]
+    if "selftest" in which:
+        selftest()
+    if "mlp" in which:
+        print("mlp 2D"); mlp(2, 2, 1, (64, 48), True)
+        print("mlp 3D coords"); mlp(3, 4, 31, (16, 16, 9), False)
+        print("mlp 3D grid ragged"); mlp(3, 4, 31, (32, 32, 16), True, rows=32 * 32 * 16 - 77)
+        print("mlp 3D bigger"); mlp(3, 4, 31, (64, 64, 32), True)
+    if "timing" in which:
+        timing()
