@@ -97,6 +97,14 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
                            const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
                            void* stream);
 
+/* The two kernels of b200inr_siren_backward as separate calls (same arguments; backward == dgrad then wgrad):
+ * dgrad: activation-gradient chain, fills the stash with dL/dtheta of every sine layer and the bf16 dL/dout tile;
+ * wgrad: contracts the stash over the rows and ACCUMULATES into grad_params. */
+int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                        void* stream);
+int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords, const b200inr_grid* grid,
+                        int64_t rows, float* grad_params, void* stream);
+
 /* ---- loss and LR degradation -------------------------------------------------------------------------
  * ((out - gt)**2).mean() and its gradient (INR/superresDWI.py:135; weighted form INR/INR_ERD.py:265).
  * loss_accum[0] += sum(w*(pred-target)^2)/count ; grad = 2*w*(pred-target)/count.  weight may be NULL. */

@@ -1,0 +1,15 @@
+"""B200-native implementation of the INR fit / query hot path of MRIRC/MRI-super-resolution.
+
+The directory name contains hyphens, so import it with importlib (or through the root-level ``b200inr`` shim):
+
+    import b200inr                      # repo root on sys.path
+    from b200inr import Siren, get_mgrid, input_mapping
+
+Modules: ``inr`` (reference-facing nn.Module surface + fused fit/query), ``SRDWI`` / ``INRmodel`` (drop-in modules
+with exactly the reference's import names), ``phantom`` (synthetic DWI volumes), ``_lib`` (ctypes binding of the C
+ABI declared in include/b200inr.h), ``csrc`` (the sm_100a kernels).
+"""
+from .inr import ImageFitting_set, SineLayer, Siren, get_mgrid, input_mapping  # noqa: F401
+from . import _lib  # noqa: F401
+
+__all__ = ["ImageFitting_set", "SineLayer", "Siren", "get_mgrid", "input_mapping"]

@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200inr_stash_bytes": (ctypes.c_int, [_P(Net), _i64, _P(_sz)]),
     "b200inr_siren_forward": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, ctypes.c_int, _f32, _vp, _vp]),
     "b200inr_siren_backward": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _P(Grid), _i64, _vp, _vp, _vp]),
+    "b200inr_siren_dgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp]),
+    "b200inr_siren_wgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, _vp]),
     "b200inr_mse_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp]),
     "b200inr_degrade_build_axis_host": (ctypes.c_int, [_i32, ctypes.c_int, _P(AxisTaps), _P(AxisTaps)]),
     "b200inr_degrade_forward": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),

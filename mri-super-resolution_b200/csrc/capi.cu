@@ -166,6 +166,35 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, s);
 }
 
+int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                        void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !stash || !grad_out) return B200INR_ERR_NULL;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords, const b200inr_grid* grid,
+                        int64_t rows, float* grad_params, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!stash || !grad_params) return B200INR_ERR_NULL;
+  if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if (grid && (e = check_grid(net, grid, rows))) return e;
+  if ((reinterpret_cast<uintptr_t>(stash) & 1023) || !aligned16(grad_params)) return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
+}
+
 int b200inr_mse_loss(const float* pred, const float* target, const float* weight, int64_t n, double count,
                      float* grad, float* loss_accum, void* stream) {
   if (!pred || !target) return B200INR_ERR_NULL;

@@ -49,6 +49,7 @@ struct StashLayout {
   size_t ph;            // (L+1) x T x [H/8][128][8]   u16    phase = round(theta * 65536 / 2pi) mod 65536
   size_t dz;            // (L+1) x T x [H/64][128][64] bf16   dL/dtheta, UMMA tile layout
   size_t dzo;           // T x [128][64] bf16                  dL/dout, one block per tile
+  size_t xa;            // T x [128][64] bf16                  coordinates as bf16 hi (cols 0..3) + lo (cols 4..7)
   size_t layer_stride;  // bytes per layer inside y / ph / dz
   size_t tile_bytes;    // 128 * H * 2
   size_t total;
@@ -68,6 +69,8 @@ __host__ __device__ inline StashLayout make_stash_layout(int H, int L, int64_t r
   s.dz = o;
   o += size_t(L + 1) * s.layer_stride;
   s.dzo = o;
+  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.xa = o;
   o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
   s.total = o;
   return s;
@@ -126,6 +129,19 @@ __device__ inline void grid_coords(const GridDesc& g, long long row, float (&x)[
   long long idx = g.row_begin + row;
   if (idx >= g.total) idx = g.total - 1;
   x[0] = x[1] = x[2] = x[3] = 0.0f;
+  if (g.total <= 0x7fffffffLL) {  // 32-bit index arithmetic (every BASELINE grid, 2^26 voxels at most)
+    unsigned int i32 = (unsigned int)idx;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      if (j < g.ndim) {
+        const unsigned int n = (unsigned int)g.shape[j];
+        const unsigned int q = i32 / n;
+        x[j] = linspace_m1p1(int(i32 - q * n), int(n));
+        i32 = q;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 3; j >= 0; --j) {
     if (j < g.ndim) {

@@ -35,6 +35,7 @@ struct FwdParams {
   float clamp_min;
   uint8_t* stash_y;   // nullptr => inference
   uint8_t* stash_ph;
+  uint8_t* stash_xa;  // coordinate operand of the first-layer weight gradient (wgrad.cu)
   size_t stash_layer_stride;
 };
 
@@ -48,7 +49,8 @@ struct FwdSmem {
   static constexpr int kOffW = kABytes;
   static constexpr int kOffW0 = kOffW + kKB * kSlotBytes;
   static constexpr int kOffBias = kOffW0 + H * 16;
-  static constexpr int kOffBar = kOffBias + (kMaxSineLayers * H + 32) * 4;
+  static constexpr int kOffXa = (kOffBias + (kMaxSineLayers * H + 32) * 4 + 1023) / 1024 * 1024;
+  static constexpr int kOffBar = kOffXa + kTileRows * 128;  // xa block only carved out in training mode
   static constexpr int kBytes = kOffBar + 128;
 };
 
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   uint8_t* w_smem = smem + S::kOffW;
   float4* w0_smem = reinterpret_cast<float4*>(smem + S::kOffW0);
   float* bias_smem = reinterpret_cast<float*>(smem + S::kOffBias);
+  uint8_t* xa_smem = smem + S::kOffXa;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* w_full = bars;       // [4]
   uint64_t* w_empty = bars + 4;  // [4]
@@ -108,6 +111,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     w0_smem[i] = reinterpret_cast<const float4*>(p.packed + p.pl.w0)[i];
   for (int i = threadIdx.x; i < (L + 1) * H + 32; i += blockDim.x)
     bias_smem[i] = reinterpret_cast<const float*>(p.packed + p.pl.bias)[i];
+  if (kStash) {  // zero once: only the coordinate chunk of every row is rewritten per tile
+    for (int i = threadIdx.x; i < kTileRows * 8; i += blockDim.x)
+      reinterpret_cast<uint4*>(xa_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < S::kKB; ++i) {
       mbar_init(&w_full[i], 1);
@@ -196,6 +203,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         } else {
           grid_coords(p.grid, row0 + r, x);
         }
+        if (kStash && h == 0) {  // x = hi + lo in bf16 (exact to 2^-17): B operand of dW_0 = dTheta_0^T X
+          float hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hi[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
+            lo[j] = x[j] - hi[j];
+          }
+          *reinterpret_cast<uint4*>(xa_smem + sw128_chunk_off(r, 0)) =
+              make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
+                         pack_bf16x2(lo[2], lo[3]));
+        }
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
@@ -221,6 +239,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           named_bar_sync(kEpiBarId, kEpiThreads);
           if (et == 0) {
             bulk_s2g(y_tile, a_smem, S::kABytes);
+            bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
             bulk_commit();
           }
         }
@@ -343,6 +362,7 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
     StashLayout sl = make_stash_layout(H, net->hidden_layers, rows);
     p.stash_y = reinterpret_cast<uint8_t*>(stash) + sl.y;
     p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
+    p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
   }
   const int smem = FwdSmem<H>::kBytes + 1024;

@@ -9,9 +9,14 @@
 // (one per layer) are split over the row range across CTAs; every CTA keeps its partial dW in TMEM for its whole
 // row range (2 x [128 lanes x N] fp32) and flushes once with vector red.global.add.
 //
-// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = column sums on CUDA
-// cores (bias and first-layer gradients, fp32) while the tiles stream through, then the TMEM flush.
+// The first layer (K = d <= 4 inputs) uses the same machinery: its B operand is the [rows][64] block written by the
+// training forward whose first eight columns hold the coordinates split into bf16 hi and lo parts
+// (x = hi + lo to 2^-17), so dW_0 = D[:, j] + D[:, 4 + j].
+//
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = bias column sums on
+// CUDA cores (fp32) while the tiles stream through, then the TMEM flush.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -33,7 +38,7 @@ struct WgItem {
   int kind;
   int cta_begin, cta_count;  // CTAs [cta_begin, cta_begin + cta_count) share this item
   const uint8_t* a_src;      // tile stride kTileBytes, 4 blocks          (kFinal: Y_L, else dTheta_l)
-  const uint8_t* b_src;      // kHidden: Y_{l-1} (4 blocks); kFinal: dOut tiles (1 block, stride 16 KB)
+  const uint8_t* b_src;      // kHidden: Y_{l-1} (4 blocks); kFinal / kFirst: dOut / coordinate tiles (1 block, 16 KB)
   float* gw;                 // gradient of the weight (reference layout [out, in])
   float* gb;                 // gradient of the bias
   float scale;               // omega of the layer (1 for the final linear)
@@ -52,8 +57,7 @@ struct WgParams {
 template <int H>
 struct WgSmem {
   static constexpr int kOffStage = 0;
-  static constexpr int kOffX = kWgStages * kWgStageBytes;            // float4 [kWgStages][32]
-  static constexpr int kOffBar = kOffX + kWgStages * kWgStageRows * 16;
+  static constexpr int kOffBar = kWgStages * kWgStageBytes;
   static constexpr int kBytes = kOffBar + 256;
 };
 
@@ -68,7 +72,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
   using S = WgSmem<H>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float4* x_smem = reinterpret_cast<float4*>(smem + S::kOffX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* full = bars;                // [kWgStages]
   uint64_t* empty = bars + kWgStages;   // [kWgStages]
@@ -87,13 +90,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
   const int tile_begin = int((long long)p.num_tiles * split / item.cta_count);
   const int tile_end = int((long long)p.num_tiles * (split + 1) / item.cta_count);
   const int num_stages = (tile_end - tile_begin) * kWgStagesPerTile;
-  const bool has_mma = item.kind != kWgFirst;
+  const bool first = item.kind == kWgFirst;
   constexpr size_t kTileBytes = size_t(kTileRows) * H * 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], (has_mma ? 1 : 0) + kWgAuxThreads / 32);
+      mbar_init(&empty[i], 1 + kWgAuxThreads / 32);
     }
     mbar_init(d_full, 1);
     fence_mbar_init();
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
       // =============================== producer ===============================
       if (lane == 0) {
         const int na = 4;
-        const int nb = item.kind == kWgHidden ? 4 : (item.kind == kWgFinal ? 1 : 0);
+        const int nb = item.kind == kWgHidden ? 4 : 1;
         const uint32_t bytes = uint32_t(na + nb) * kWgBlkBytes;
         for (int s = 0; s < num_stages; ++s) {
           const int slot = s % kWgStages;
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
             const uint8_t* bsrc = item.b_src + size_t(tile) * kTileBytes + size_t(sub) * kWgBlkBytes;
             for (int b = 0; b < 4; ++b)
               bulk_g2s(dst + (4 + b) * kWgBlkBytes, bsrc + size_t(b) * (kTileRows * 128), kWgBlkBytes, &full[slot]);
-          } else if (item.kind == kWgFinal) {
+          } else {
             const uint8_t* bsrc = item.b_src + size_t(tile) * (kTileRows * 128) + size_t(sub) * kWgBlkBytes;
             bulk_g2s(dst + 4 * kWgBlkBytes, bsrc, kWgBlkBytes, &full[slot]);
           }
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
       }
     } else if (warp == 1) {
       // =============================== MMA issuer ===============================
-      if (lane == 0 && has_mma) {
+      if (lane == 0) {
         // MN-major operands: LBO = stride between 64-wide feature blocks, SBO = 8-row groups along K.
         const uint64_t hi = smem_desc_hi_sw128(kWgBlkBytes, 1024);
         const int ncols = item.kind == kWgHidden ? H : kDzoPad;  // N of the MMA == TMEM columns per M half
@@ -163,65 +166,34 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
       const int q = warp & 3;           // TMEM lane quadrant of this warp
       // column pair owned by this thread inside the summed operand: features 2*at, 2*at + 1
       const int sum_blocks = item.kind == kWgFinal ? 1 : 4;
-      const int sum_off = item.kind == kWgFinal ? 4 * kWgBlkBytes : 0;
+      const int sum_off = item.kind == kWgFinal ? 4 * kWgBlkBytes : 0;  // dOut (final) or dTheta (sine layers)
       const bool sums = (2 * at) < sum_blocks * 64;
       const int sblk = (2 * at) >> 6, sch = ((2 * at) & 63) >> 3, sel = (2 * at) & 7;
       float s0 = 0.f, s1 = 0.f;
-      float sx0[4] = {0.f, 0.f, 0.f, 0.f}, sx1[4] = {0.f, 0.f, 0.f, 0.f};
       for (int s = 0; s < num_stages; ++s) {
         const int slot = s % kWgStages;
-        if (item.kind == kWgFirst) {
-          // coordinates of the 32 rows of this stage (first warp of the group), fp32
-          if (at < kWgStageRows) {
-            const long long row = (long long)(tile_begin + s / kWgStagesPerTile) * kTileRows +
-                                  (s % kWgStagesPerTile) * kWgStageRows + at;
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.coords != nullptr) {
-              const long long rr = row < p.rows ? row : p.rows - 1;
-              for (int j = 0; j < p.d; ++j) x[j] = p.coords[rr * p.d + j];
-            } else {
-              grid_coords(p.grid, row, x);
-            }
-            x_smem[slot * kWgStageRows + at] = make_float4(x[0], x[1], x[2], x[3]);
-          }
-          named_bar_sync(kWgAuxBarId, kWgAuxThreads);
-        }
         mbar_wait(&full[slot], (s / kWgStages) & 1);
         if (sums) {
           const uint8_t* blk = smem + S::kOffStage + slot * kWgStageBytes + sum_off + sblk * kWgBlkBytes;
 #pragma unroll 8
           for (int rr = 0; rr < kWgStageRows; ++rr) {
             const uint32_t v = *reinterpret_cast<const uint32_t*>(blk + sw128_chunk_off(rr, sch) + sel * 2);
-            const float v0 = bf16lo(v), v1 = bf16hi(v);
-            s0 += v0;
-            s1 += v1;
-            if (item.kind == kWgFirst) {
-              const float4 x = x_smem[slot * kWgStageRows + rr];
-              sx0[0] = fmaf(v0, x.x, sx0[0]); sx0[1] = fmaf(v0, x.y, sx0[1]);
-              sx0[2] = fmaf(v0, x.z, sx0[2]); sx0[3] = fmaf(v0, x.w, sx0[3]);
-              sx1[0] = fmaf(v1, x.x, sx1[0]); sx1[1] = fmaf(v1, x.y, sx1[1]);
-              sx1[2] = fmaf(v1, x.z, sx1[2]); sx1[3] = fmaf(v1, x.w, sx1[3]);
-            }
+            s0 += bf16lo(v);
+            s1 += bf16hi(v);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);
       }
-      // ---- bias (and first-layer weight) gradients
+      // ---- bias gradients
       if (sums) {
         const int c0 = 2 * at;
         const int nfeat = item.kind == kWgFinal ? p.C : H;
         if (c0 < nfeat) atomicAdd(item.gb + c0, item.scale * s0);
         if (c0 + 1 < nfeat) atomicAdd(item.gb + c0 + 1, item.scale * s1);
-        if (item.kind == kWgFirst) {
-          for (int j = 0; j < p.d; ++j) {
-            atomicAdd(item.gw + (long long)c0 * p.d + j, item.scale * sx0[j]);
-            atomicAdd(item.gw + (long long)(c0 + 1) * p.d + j, item.scale * sx1[j]);
-          }
-        }
       }
       // ---- flush the TMEM partial products
-      if (has_mma) {
+      {
         mbar_wait(d_full, 0);
         tc_fence_after();
         const uint32_t t_lane = uint32_t(q * 32) << 16;
@@ -240,12 +212,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) siren_wgrad_kernel(const WgPara
               for (int j = 0; j < 32; j += 4)
                 red_add_v4(dst + j, item.scale * __uint_as_float(v[j]), item.scale * __uint_as_float(v[j + 1]),
                            item.scale * __uint_as_float(v[j + 2]), item.scale * __uint_as_float(v[j + 3]));
-            } else {
+            } else if (item.kind == kWgFinal) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;  // N index: output channel
                 if (c < p.C) atomicAdd(item.gw + (long long)c * H + feat, item.scale * __uint_as_float(v[j]));
               }
+            } else if (c0 == 0) {  // first layer: columns 0..3 = sum dTheta*x_hi, 4..7 = sum dTheta*x_lo
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < p.d)
+                  atomicAdd(item.gw + (long long)feat * p.d + j,
+                            item.scale * (__uint_as_float(v[j]) + __uint_as_float(v[4 + j])));
             }
           }
         }
@@ -283,8 +261,8 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     p.grid.row_begin = grid->row_begin;
     p.grid.total = tot;
   }
-  // CTA shares proportional to the bytes each item streams per tile.
-  const double w_first = 64.0, w_hidden = 128.0, w_final = 80.0;
+  // CTA shares proportional to the bytes each item streams per tile (the kernel is HBM-bound).
+  const double w_first = 80.0, w_hidden = 128.0, w_final = 80.0;
   const double w_total = w_first + L * w_hidden + w_final;
   int n_first = int(num_sms * w_first / w_total + 0.5);
   int n_final = int(num_sms * w_final / w_total + 0.5);
@@ -293,7 +271,10 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
   int n_hidden = L > 0 ? (num_sms - n_first - n_final) / L : 0;
   if (L > 0 && n_hidden < 1) n_hidden = 1;
   int cta = 0, ni = 0;
+  int mask = 7;  // development hook: B200INR_WGRAD_ITEMS = bitmask {1: hidden, 2: final, 4: first}
+  if (const char* e = getenv("B200INR_WGRAD_ITEMS")) mask = atoi(e);
   auto add = [&](int kind, int count, const uint8_t* a, const uint8_t* b, float* gw, float* gb, float scale) {
+    if (!(mask & (kind == kWgHidden ? 1 : (kind == kWgFinal ? 2 : 4)))) return;
     WgItem& w = p.items[ni++];
     w.kind = kind;
     w.cta_begin = cta;
@@ -310,7 +291,7 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
         grad_params + off[2 * l], grad_params + off[2 * l + 1], net->hidden_omega_0);
   add(kWgFinal, n_final, st + sl.y + size_t(L) * sl.layer_stride, st + sl.dzo, grad_params + off[2 * (L + 1)],
       grad_params + off[2 * (L + 1) + 1], 1.0f);
-  add(kWgFirst, n_first, st + sl.dz, nullptr, grad_params + off[0], grad_params + off[1], net->first_omega_0);
+  add(kWgFirst, n_first, st + sl.dz, st + sl.xa, grad_params + off[0], grad_params + off[1], net->first_omega_0);
   p.num_items = ni;
 
   const int smem = WgSmem<H>::kBytes + 1024;

@@ -1,0 +1,451 @@
+"""Host-side mirror of the reference's INR model module on top of the B200 C ABI (include/b200inr.h).
+
+Same names, constructor arguments, state-dict keys, RNG consumption and call protocol as the reference's
+INR/SRDWI.py (get_mgrid :12-18, ImageFitting_set :20-39, SineLayer :41-64, Siren :67-91, input_mapping :111-116) and
+INR/INRmodel.py (Siren :122-151), so the reference's scripts and notebooks run unchanged against it.  Every tensor
+operation on the hot path is a hand-written sm_100a kernel reached through ctypes; torch supplies device memory,
+streams, autograd bookkeeping and (multi-GPU) the NCCL process group.  There is no CPU path: modules must live on a
+CUDA device before forward / fit / query are called, and a missing libb200inr.so raises at the first call.
+
+Besides the nn.Module protocol (`forward` + autograd, as used at INR/superresDWI.py:134-138) two fused entry points
+bypass autograd entirely:
+
+    Siren.fit(...)    the in-lined training loop of INR/superresDWI.py:132-138 (full batch, fixed order, Adam), with
+                      the loss taken either point-wise or through the LR degradation operator
+    Siren.query(...)  torch.clamp(INR.forward(get_mgrid(shape)), min=0) of INR/superresDWI.py:161 without ever
+                      materialising the coordinate grid
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+from torch import nn
+from torch.utils.data import Dataset
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"b200inr: {what} must be a CUDA tensor (the B200 kernels are the only implementation)")
+
+
+def _aligned_bytes(nbytes, device, align=1024):
+    """Zero-initialised byte buffer whose data pointer is `align`-aligned."""
+    raw = torch.zeros(int(nbytes) + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + int(nbytes)]
+
+
+# ------------------------------------------------------------------------------------------------ coordinates
+def get_mgrid(shape, device=None):
+    """Reference INR/SRDWI.py:12-18: [prod(shape), len(shape)] coordinates in [-1, 1], C order, last axis fastest.
+
+    With device=None the result is a CPU tensor exactly like the reference's (built with the same torch calls, it is
+    data preparation, not the hot path); with a CUDA device the grid is written by the b200inr_get_mgrid kernel.
+    """
+    shape = tuple(int(s) for s in shape)
+    if device is None or torch.device(device).type == "cpu":
+        axes = tuple(torch.linspace(-1, 1, steps=n) for n in shape)
+        return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(shape))
+    if not 1 <= len(shape) <= 4:
+        raise RuntimeError("b200inr: get_mgrid supports 1 to 4 dimensions on the device")
+    rows = int(np.prod(shape))
+    out = torch.empty((rows, len(shape)), dtype=torch.float32, device=device)
+    grid = _lib.make_grid(shape)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().b200inr_get_mgrid(ctypes.byref(grid), rows, _ptr(out), _stream()), "get_mgrid")
+    return out
+
+
+class ImageFitting_set(Dataset):
+    """Reference INR/SRDWI.py:20-39: flattens N-D volumes to pixels [n, N, 1] and coords [n, N, d]; __getitem__
+    ignores its index and returns everything."""
+
+    def __init__(self, img_dataset):
+        super().__init__()
+        shape = img_dataset[0].shape
+        self.shape = shape
+        n = int(np.prod(shape))
+        self.pixels = torch.empty((len(img_dataset), n, 1))
+        self.coords = torch.empty((len(img_dataset), n, len(shape)))
+        grid = get_mgrid(shape)
+        for i, img in enumerate(img_dataset):
+            self.pixels[i] = torch.from_numpy(np.ascontiguousarray(img)).float().reshape(-1, 1)
+            self.coords[i] = grid
+
+    def __len__(self):
+        return len(self.pixels)
+
+    def __getitem__(self, idx):
+        return self.coords, self.pixels
+
+
+def input_mapping(x, B):
+    """Reference INR/SRDWI.py:111-116: cat([sin(2 pi x B^T), cos(2 pi x B^T)], -1); identity when B is None."""
+    if B is None:
+        return x
+    _require_cuda(x, "input_mapping input")
+    _require_cuda(B, "input_mapping B")
+    x = x.detach().contiguous().float()
+    B = B.detach().contiguous().float()
+    rows, d = x.shape
+    m = B.shape[0]
+    if B.shape[1] != d:
+        raise RuntimeError("b200inr: input_mapping expects B of shape [m, d]")
+    out = torch.empty((rows, 2 * m), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200inr_input_mapping(_ptr(x), _ptr(B), rows, d, m, _ptr(out), _stream()),
+                   "input_mapping")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ layers
+class SineLayer(nn.Module):
+    """Reference INR/SRDWI.py:41-64.  Parameter container with the reference's initialisation; the arithmetic runs
+    fused inside Siren (one kernel for the whole network), so a stand-alone forward is a 0-hidden-layer fused call."""
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega_0=30):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.is_first = is_first
+        self.in_features = in_features
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+        self.init_weights()
+
+    def init_weights(self):
+        with torch.no_grad():
+            if self.is_first:
+                bound = 1 / self.in_features
+            else:
+                bound = np.sqrt(6 / self.in_features) / self.omega_0
+            self.linear.weight.uniform_(-bound, bound)
+
+    def forward(self, input):
+        raise RuntimeError("b200inr: SineLayer is executed fused inside Siren.forward / fit / query; "
+                           "call the enclosing Siren instead")
+
+
+class _SirenFunction(torch.autograd.Function):
+    """Siren.forward as one fused kernel, loss.backward() as the fused dgrad + wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, coords, module, *params):
+        needs_grad = any(ctx.needs_input_grad[2:])
+        out, stash = module._forward_rows(coords=coords, grid=None, rows=coords.shape[0], train=needs_grad)
+        ctx.module = module
+        ctx.stash = stash
+        ctx.coords = coords
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module = ctx.module
+        if ctx.stash is None:
+            raise RuntimeError("b200inr: backward called on a forward that did not record activations")
+        flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out)
+        ctx.stash = None
+        grads = [flat_grad[o:o + p.numel()].view_as(p) for o, p in zip(module._offsets_canonical(), module._canonical())]
+        return (None, None, *grads)
+
+
+class Siren(nn.Module):
+    """Reference INR/SRDWI.py:67-91 (default) or INR/INRmodel.py:122-151 (`variant='INRmodel'`).
+
+    Same constructor arguments, registration order (final_linear is both an attribute and the last element of `net`,
+    SURVEY.md App. A-1) and RNG consumption order as the reference class, so `torch.manual_seed(s)` gives identical
+    initial weights and reference state_dicts load unchanged.
+    """
+
+    def __init__(self, in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.,
+                 hidden_omega_0=30., variant="SRDWI"):
+        super().__init__()
+        if variant not in ("SRDWI", "INRmodel"):
+            raise ValueError("variant must be 'SRDWI' or 'INRmodel'")
+        self.variant = variant
+        self.in_features, self.hidden_features = int(in_features), int(hidden_features)
+        self.hidden_layers, self.out_features = int(hidden_layers), int(out_features)
+        bound = np.sqrt(6 / hidden_features) / hidden_omega_0
+
+        def make_final():
+            fin = nn.Linear(hidden_features, out_features)
+            with torch.no_grad():
+                fin.weight.uniform_(-bound, bound)
+            return fin
+
+        net = []
+        if variant == "SRDWI":  # final linear first (INR/SRDWI.py:75-77)
+            self.final_linear = make_final()
+            net.append(SineLayer(in_features, hidden_features, is_first=True, omega_0=first_omega_0))
+            for _ in range(hidden_layers):
+                net.append(SineLayer(hidden_features, hidden_features, is_first=False, omega_0=hidden_omega_0))
+        else:  # sine layers first with the class-default omega 30, final linear last (INR/INRmodel.py:133-143)
+            first_omega_0 = 30.
+            net.append(SineLayer(in_features, hidden_features, is_first=True))
+            for _ in range(hidden_layers):
+                net.append(SineLayer(hidden_features, hidden_features, is_first=False))
+            self.final_linear = make_final()
+        net.append(self.final_linear)
+        self.net = nn.Sequential(*net)
+        self.first_omega_0 = float(first_omega_0)
+        self.hidden_omega_0 = float(net[1].omega_0) if hidden_layers > 0 else float(hidden_omega_0)
+        self._desc = _lib.make_net(in_features, hidden_features, hidden_layers, out_features, self.first_omega_0,
+                                   self.hidden_omega_0)
+        self._engine = None  # device-side staging (flat fp32 params, packed bf16 operands)
+        self._optim = None   # Adam state of fit()
+
+    # ---------------------------------------------------------------- parameter plumbing
+    def _canonical(self):
+        """Parameters in the flat-layout order of include/b200inr.h: W0 b0 ... WL bL Wf bf."""
+        ps = []
+        for i in range(self.hidden_layers + 1):
+            ps += [self.net[i].linear.weight, self.net[i].linear.bias]
+        ps += [self.final_linear.weight, self.final_linear.bias]
+        return ps
+
+    def _offsets_canonical(self):
+        return self._engine_state()["offsets"]
+
+    def _engine_state(self):
+        dev = self.final_linear.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("b200inr: the module must be on a CUDA device (call .cuda()); there is no CPU path")
+        eng = self._engine
+        if eng is None or eng["device"] != dev:
+            _lib.load()
+            n = _lib.param_count(self._desc)
+            eng = {
+                "device": dev,
+                "offsets": _lib.param_offsets(self._desc),
+                "flat": torch.zeros(n, dtype=torch.float32, device=dev),
+                "packed": _aligned_bytes(_lib.packed_bytes(self._desc), dev),
+                "key": None,
+            }
+            self._engine = eng
+        return eng
+
+    def _sync_params(self):
+        """Refresh the flat fp32 copy and the bf16 operand buffer when any parameter changed since the last call."""
+        eng = self._engine_state()
+        ps = self._canonical()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != eng["key"]:
+            flat = eng["flat"]
+            with torch.no_grad():
+                for o, p in zip(eng["offsets"], ps):
+                    flat[o:o + p.numel()].copy_(p.reshape(-1))
+            self._pack(eng)
+            eng["key"] = key
+        return eng
+
+    def _pack(self, eng):
+        with torch.cuda.device(eng["device"]):
+            _lib.check(_lib.load().b200inr_pack_weights(ctypes.byref(self._desc), _ptr(eng["flat"]),
+                                                        _ptr(eng["packed"]), _stream()), "pack_weights")
+
+    def _writeback_params(self, eng):
+        """Copy the flat fp32 master (updated by fit) back into the nn.Parameters."""
+        ps = self._canonical()
+        with torch.no_grad():
+            for o, p in zip(eng["offsets"], ps):
+                p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
+        eng["key"] = tuple((p.data_ptr(), p._version) for p in ps)
+
+    # ---------------------------------------------------------------- kernel calls
+    def _forward_rows(self, coords, grid, rows, train, clamp=None, out=None, eng=None):
+        eng = eng or self._sync_params()
+        dev = eng["device"]
+        if out is None:
+            out = torch.empty((rows, self.out_features), dtype=torch.float32, device=dev)
+        if rows == 0:  # empty input: nothing to launch (an empty tensor has no device pointer)
+            return out, (torch.empty(0, dtype=torch.uint8, device=dev) if train else None)
+        stash = _aligned_bytes(_lib.stash_bytes(self._desc, rows), dev) if train else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200inr_siren_forward(
+                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(coords), ctypes.byref(grid) if grid else None,
+                rows, _ptr(out), int(clamp is not None), float(clamp or 0.0), _ptr(stash), _stream()), "siren_forward")
+        return out, stash
+
+    def _backward_rows(self, stash, coords, grid, rows, grad_out, flat_grad=None, eng=None):
+        eng = eng or self._engine_state()
+        dev = eng["device"]
+        grad_out = grad_out.contiguous().float()
+        if flat_grad is None:
+            flat_grad = torch.zeros_like(eng["flat"])
+        if rows == 0:
+            return flat_grad
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200inr_siren_backward(
+                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(stash), _ptr(coords),
+                ctypes.byref(grid) if grid else None, rows, _ptr(grad_out), _ptr(flat_grad), _stream()),
+                "siren_backward")
+        return flat_grad
+
+    # ---------------------------------------------------------------- nn.Module protocol
+    def forward(self, coords):
+        """out = INR.forward(x) (INR/superresDWI.py:134).  Coordinates carry no gradient: SRDWI.Siren detaches them
+        (INR/SRDWI.py:88); the INRmodel variant's input gradient (PerturbNet phase) is not part of this path."""
+        _require_cuda(coords, "Siren.forward input")
+        if coords.dim() != 2 or coords.shape[1] != self.in_features:
+            raise RuntimeError(f"b200inr: expected coords of shape [N, {self.in_features}]")
+        coords = coords.detach().contiguous().float()
+        return _SirenFunction.apply(coords, self, *self._canonical())
+
+    # ---------------------------------------------------------------- fused query
+    def query(self, shape, clamp_min=0.0, out=None, row_range=None):
+        """torch.clamp(INR.forward(get_mgrid(shape)), min=0) of INR/superresDWI.py:161, coordinates derived in-kernel.
+
+        row_range=(begin, end) restricts the call to a contiguous range of the flattened grid (a rank's shard).
+        Returns [rows, out_features] fp32 on the module's device; pass clamp_min=None for the raw output.
+        """
+        shape = tuple(int(s) for s in shape)
+        if len(shape) != self.in_features:
+            raise RuntimeError("b200inr: query grid rank must equal in_features")
+        total = int(np.prod(shape))
+        begin, end = (0, total) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        grid = _lib.make_grid(shape, begin)
+        with torch.no_grad():
+            res, _ = self._forward_rows(None, grid, end - begin, train=False, clamp=clamp_min, out=out)
+        return res
+
+    # ---------------------------------------------------------------- fused fit
+    def fit(self, target, shape, steps, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
+            global_count=None, process_group=None, reset_optimizer=False):
+        """The reference training loop (INR/superresDWI.py:132-138) on a dense coordinate grid, without autograd:
+        per step  fused forward -> loss (+ LR degradation) -> fused backward -> [all-reduce] -> Adam -> re-stage bf16.
+
+        target   CUDA fp32.  degrade=None: [rows, C] values at the grid points.  degrade='pool': the LR volume
+                 [X/2, Y/2, Z, C] (flattened or not) that the 2x2x1 in-plane average of the prediction must match.
+        shape    the (HR) coordinate grid; rows = prod(shape) unless row_range=(begin, end) selects this rank's slab.
+        process_group / global_count: multi-GPU data parallel -- gradients are summed with one all-reduce per step and
+                 the loss is normalised by the global element count.
+        Returns the per-step loss as a CUDA tensor [steps] (this rank's share of the global mean).
+        """
+        session = FitSession(self, target, shape, lr=lr, degrade=degrade, betas=betas, eps=eps, row_range=row_range,
+                             global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer)
+        losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
+        for it in range(steps):
+            losses[it:it + 1].copy_(session.step())
+        session.finish()
+        return losses
+
+
+class FitSession:
+    """Device-resident state of one fused fit (buffers, Adam moments, activation stash) and its step function.
+
+    step() issues, on the current stream and without host synchronisation:
+        zero [grad | loss] -> fused forward (stash) -> loss / degradation + dL/dpred -> dgrad -> wgrad
+        -> [all-reduce of the flat [grad | loss] buffer] -> Adam -> bf16 re-staging of the weights
+    `marks`, when given, receives a CUDA event after every stage (used by bench.py for per-kernel timing).
+    """
+
+    STAGES = ("zero", "forward", "loss", "dgrad", "wgrad", "allreduce", "adam", "pack")
+
+    def __init__(self, module, target, shape, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
+                 global_count=None, process_group=None, reset_optimizer=False):
+        _require_cuda(target, "fit target")
+        self.module = module
+        eng = self.eng = module._sync_params()
+        dev = self.device = eng["device"]
+        self.lib = _lib.load()
+        shape = tuple(int(s) for s in shape)
+        total = int(np.prod(shape))
+        begin, end = (0, total) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        rows = self.rows = end - begin
+        C = self.C = module.out_features
+        if len(shape) != module.in_features:
+            raise RuntimeError("b200inr: fit grid rank must equal in_features")
+        self.grid = _lib.make_grid(shape, begin)
+        self.degrade = degrade
+        target = target.detach().contiguous().float().reshape(-1)
+        if degrade is None:
+            if target.numel() != rows * C:
+                raise RuntimeError("b200inr: fit target must have rows*C elements")
+            self.count = float(global_count if global_count is not None else rows * C)
+        elif degrade == "pool":
+            if len(shape) != 3:
+                raise RuntimeError("b200inr: degrade='pool' needs a 3-D grid (X, Y, Z)")
+            plane = shape[1] * shape[2]
+            if rows % (2 * plane) or begin % (2 * plane) or shape[1] % 2:
+                raise RuntimeError("b200inr: pooled fit needs whole pairs of x-planes and an even Y")
+            self.x_local, self.Y, self.ZC = rows // plane, shape[1], shape[2] * C
+            if target.numel() != rows * C // 4:
+                raise RuntimeError("b200inr: pooled fit target must have rows*C/4 elements")
+            self.count = float(global_count if global_count is not None else rows * C // 4)
+        else:
+            raise ValueError("degrade must be None or 'pool'")
+        self.target = target
+        if module._optim is None or reset_optimizer or module._optim["m"].device != dev:
+            module._optim = {"m": torch.zeros_like(eng["flat"]), "v": torch.zeros_like(eng["flat"]),
+                             "state": torch.zeros(4, dtype=torch.float32, device=dev)}
+        self.opt = module._optim
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.process_group = process_group
+        self.n_flat = eng["flat"].numel()
+        self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)  # [grad ..., loss, pad]
+        self.loss = self.grads[self.n_flat:self.n_flat + 1]
+        self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        self.dpred = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        self.stash = _aligned_bytes(_lib.stash_bytes(module._desc, rows), dev)
+        self.kernel_launches_per_step = 7  # forward, loss, dgrad, wgrad, adam, adam_tick, pack
+
+    def set_target(self, target):
+        """Replace the target values (same size), e.g. from pinned host memory."""
+        self.target.copy_(target.reshape(-1), non_blocking=True)
+
+    def step(self, marks=None):
+        m, eng, lib = self.module, self.eng, self.lib
+        net, gref = ctypes.byref(m._desc), ctypes.byref(self.grid)
+        rows, C = self.rows, self.C
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+
+        with torch.cuda.device(self.device), torch.no_grad():
+            s = _stream()
+            mark()
+            self.grads.zero_()
+            mark()
+            _lib.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, gref, rows, _ptr(self.pred), 0, 0.0,
+                                                 _ptr(self.stash), s), "siren_forward")
+            mark()
+            if self.degrade is None:
+                _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), None, rows * C, self.count,
+                                                _ptr(self.dpred), _ptr(self.loss), s), "mse_loss")
+            else:
+                _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
+                                                self.count, _ptr(self.dpred), _ptr(self.loss), s), "pool_mse")
+            mark()
+            _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows, _ptr(self.dpred), s),
+                       "siren_dgrad")
+            mark()
+            _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
+                       "siren_wgrad")
+            mark()
+            if self.process_group is not None:
+                torch.distributed.all_reduce(self.grads, group=self.process_group)
+            mark()
+            _lib.check(lib.b200inr_adam_step(_ptr(eng["flat"]), _ptr(self.grads), _ptr(self.opt["m"]),
+                                             _ptr(self.opt["v"]), self.n_flat, self.lr, self.betas[0], self.betas[1],
+                                             self.eps, _ptr(self.opt["state"]), s), "adam_step")
+            mark()
+            _lib.check(lib.b200inr_pack_weights(net, _ptr(eng["flat"]), _ptr(eng["packed"]), s), "pack_weights")
+            mark()
+        return self.loss
+
+    def finish(self):
+        """Write the fp32 master weights back into the module's nn.Parameters."""
+        with torch.cuda.device(self.device):
+            self.module._writeback_params(self.eng)

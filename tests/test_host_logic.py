@@ -1,0 +1,210 @@
+"""Host-side logic that needs no GPU: the C ABI loads and exports what include/b200inr.h declares, shapes/offsets,
+tap tables, module construction parity with the reference (state-dict keys, RNG order), sharding (gloo, world 2)."""
+import ctypes
+import importlib
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import b200inr
+from oracle import inr_oracle as O
+
+L = b200inr._lib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200inr.h")).read()
+    declared = set(re.findall(r"\b(b200inr_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in b200inr.h but not exported"
+    assert declared == set(L.SIGNATURES), "ctypes prototypes and header disagree"
+    assert lib.b200inr_version().startswith(b"b200inr")
+
+
+def test_param_layout_and_sizes():
+    net = L.make_net(3, 256, 4, 31)
+    off = L.param_offsets(net)
+    assert off[0] == 0 and all(o % 4 == 0 for o in off)
+    n = L.param_count(net)
+    assert n >= 272159 and n - 272159 < 4 * len(off)
+    assert L.packed_bytes(net) % 1024 == 0 or L.packed_bytes(net) > 0
+    # 3 x (bf16/u16) x 256 features x 5 sine layers per row, in whole 128-row tiles
+    assert L.stash_bytes(net, 128) == 3 * 5 * 128 * 256 * 2 + 2 * 128 * 64 * 2
+    assert L.stash_bytes(net, 129) == 2 * L.stash_bytes(net, 128)
+    assert L.stash_bytes(net, 0) == 0
+
+
+def test_error_codes_without_gpu():
+    lib = L.load()
+    n = ctypes.c_int64(0)
+    bad = L.make_net(3, 128, 4, 31)  # only H = 256 is implemented
+    assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    bad = L.make_net(5, 256, 4, 31)
+    assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    bad = L.make_net(3, 256, 4, 33)
+    assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    assert lib.b200inr_param_count(None, ctypes.byref(n)) == -5
+    assert b"shape" in lib.b200inr_error_string(-1)
+    with pytest.raises(RuntimeError):
+        L.check(-3, "x")
+    fwd = (L.AxisTaps * 4)()
+    adj = (L.AxisTaps * 8)()
+    assert lib.b200inr_degrade_build_axis_host(7, 0, fwd, adj) == -1
+
+
+@pytest.mark.parametrize("n_hr,blur", [(8, 0), (8, 1), (2, 1), (4, 1), (50, 1), (128, 0)])
+def test_degrade_taps_match_oracle_matrix(n_hr, blur):
+    fwd, adj = L.build_axis_taps(n_hr, blur)
+    D = O.degrade_axis_matrix(n_hr, bool(blur))
+    F = np.zeros_like(D)
+    for i, t in enumerate(fwd):
+        for k in range(L.MAX_TAPS):
+            F[i, t.idx[k]] += t.w[k]
+    np.testing.assert_allclose(F, D, atol=1e-7)
+    A = np.zeros((n_hr, n_hr // 2))
+    for x, t in enumerate(adj):
+        for k in range(L.MAX_TAPS):
+            A[x, t.idx[k]] += t.w[k]
+    np.testing.assert_allclose(A, D.T, atol=1e-7)
+
+
+def _cs(t):
+    t = t.detach().double().reshape(-1)
+    return np.array([t.sum().item(), (t * t).sum().item(), t[0].item(), t[-1].item(), t[t.numel() // 2].item()])
+
+
+@pytest.mark.parametrize("name", ["siren_cfg1.npz", "siren_cfg2.npz"])
+def test_module_construction_matches_reference(golden_dir, name):
+    """torch.manual_seed(s); Siren(...) gives the reference's initial weights and state-dict keys (App. A-1, A-2)."""
+    g = np.load(os.path.join(golden_dir, name))
+    c = g["ctor"]
+    torch.manual_seed(int(g["seed"]))
+    m = b200inr.Siren(int(c[0]), int(c[1]), int(c[2]), int(c[3]))
+    sd = m.state_dict()
+    ref_keys = [k[4:] for k in g.files if k.startswith("cs0/")]
+    assert sorted(sd.keys()) == sorted(ref_keys)
+    for k in ref_keys:
+        np.testing.assert_allclose(_cs(sd[k]), g["cs0/" + k], rtol=1e-12, atol=0)
+    # parameters(): final_linear first, duplicates removed
+    names = [n for n, _ in m.named_parameters()]
+    assert names[0] == "final_linear.weight" and len(names) == 2 * (int(c[2]) + 2)
+
+
+def test_inrmodel_variant_construction(golden_dir):
+    g = np.load(os.path.join(golden_dir, "inrmodel_siren.npz"))
+    torch.manual_seed(13)
+    m = b200inr.INRmodel.Siren(3, 256, 2, 4)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    for k in sd:
+        np.testing.assert_allclose(_cs(sd[k]), g["cs/" + k], rtol=1e-12, atol=0)
+
+
+def test_cpu_calls_fail_loudly():
+    m = b200inr.Siren(2, 256, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(4, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.query((4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b200inr.input_mapping(torch.zeros(4, 2), torch.zeros(3, 2))
+
+
+def test_get_mgrid_cpu_is_reference_expression():
+    for shape in [(4, 3, 2), (7, 6), (128,)]:
+        ref = torch.stack(torch.meshgrid(*[torch.linspace(-1, 1, steps=n) for n in shape], indexing="ij"), -1)
+        assert torch.equal(b200inr.get_mgrid(shape), ref.reshape(-1, len(shape)))
+    ds = b200inr.ImageFitting_set([np.arange(24, dtype=np.float64).reshape(4, 3, 2)])
+    assert ds.pixels.shape == (1, 24, 1) and ds.coords.shape == (1, 24, 3)
+    assert ds.pixels[0, 5, 0] == 5.0
+
+
+def test_shard_rows_cover_grid():
+    P = importlib.import_module("mri-super-resolution_b200.parallel")
+    for shape, pooled in [((128, 128, 64), True), ((512, 512, 256), False), ((6, 5), False), ((10, 4, 3), True)]:
+        for world in (1, 2, 3, 4, 8):
+            ranges = [P.shard_rows(shape, world, r, pooled) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == int(np.prod(shape))
+            for a, b in zip(ranges[:-1], ranges[1:]):
+                assert a[1] == b[0]
+            if pooled:
+                plane2 = 2 * int(np.prod(shape[1:]))
+                assert all(r0 % plane2 == 0 and r1 % plane2 == 0 for r0, r1 in ranges)
+
+
+def test_phantom_deterministic_and_slab_consistent():
+    ph = b200inr.phantom
+    a = ph.dwi_phantom((16, 12, 6), n_dirs=5, noise=0.0)
+    b = ph.dwi_phantom((16, 12, 6), n_dirs=5, noise=0.0, x_range=(4, 10))
+    assert a.shape == (16, 12, 6, 6) and a.dtype == np.float32
+    np.testing.assert_array_equal(a[4:10], b)
+    assert 0.0 <= a.min() and a.max() <= 1.0 + 1e-6
+    lr = ph.avg_pool_inplane(a)
+    np.testing.assert_allclose(lr, O.degrade_forward(a), atol=1e-6)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = importlib.import_module("mri-super-resolution_b200.parallel")
+    shape, C = (8, 6, 4), 3
+    torch.manual_seed(5)
+    m = O.torch_siren(3, 32, 1, C)
+    coords = torch.from_numpy(O.get_mgrid(shape))
+    hr = torch.rand(8 * 6 * 4, C, generator=torch.Generator().manual_seed(6))
+    lr_t = torch.from_numpy(O.degrade_forward(hr.numpy().reshape(8, 6, 4, C))) * 0.5
+    # full-batch reference gradient
+    full = O.torch_fit  # noqa: F841  (same loop; here one explicit step)
+    out = m(coords)
+    pooled = torch.nn.functional.avg_pool3d(out.reshape(8, 6, 4, C).permute(3, 0, 1, 2).unsqueeze(0), (2, 2, 1),
+                                            (2, 2, 1)).squeeze(0).permute(1, 2, 3, 0)
+    loss = ((pooled - lr_t) ** 2).mean()
+    gref = torch.autograd.grad(loss, list(m.parameters()))
+    # sharded: each rank its x-slab, loss normalised by the GLOBAL element count, one all-reduce of [grads, loss]
+    r0, r1 = P.shard_rows(shape, world, rank, pooled=True)
+    xs = (r1 - r0) // (6 * 4)
+    out_s = m(coords[r0:r1])
+    pooled_s = torch.nn.functional.avg_pool3d(out_s.reshape(xs, 6, 4, C).permute(3, 0, 1, 2).unsqueeze(0), (2, 2, 1),
+                                              (2, 2, 1)).squeeze(0).permute(1, 2, 3, 0)
+    lr_s = P.lr_slab(lr_t, shape, (r0, r1))
+    loss_s = ((pooled_s - lr_s) ** 2).sum() / lr_t.numel()
+    gs = torch.autograd.grad(loss_s, list(m.parameters()))
+    msg = torch.cat([g.reshape(-1) for g in gs] + [loss_s.detach().reshape(1)])
+    dist.all_reduce(msg)
+    ref = torch.cat([g.reshape(-1) for g in gref] + [loss.detach().reshape(1)])
+    q.put((rank, float((msg - ref).abs().max()), float(ref.abs().max())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_sum_matches_full_batch():
+    """world_size 2 over gloo: slab-sharded loss/gradient + one all-reduce == the single-process full-batch step."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, err, scale in res:
+        assert err <= 1e-5 * max(scale, 1.0)

@@ -1,0 +1,171 @@
+"""The oracle (oracle/inr_oracle.py) against the golden vectors produced by the unmodified reference
+(tools/make_golden.py).  CPU only."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inr_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_get_mgrid_one_ulp(golden_dir):
+    """torch.linspace on CPU evaluates whole SIMD vectors as base + step*lane (ATen RangeFactoriesKernel), so its
+    last bit depends on the host's vector width; the scalar two-sided formula agrees to 1 ulp (6e-8 at |x| <= 1)."""
+    g = _load(golden_dir, "coords.npz")
+    keys = [k for k in g.files if k.startswith("mgrid/")]
+    assert len(keys) >= 8
+    for k in keys:
+        shape = tuple(int(s) for s in k.split("/")[1].split("x"))
+        ours = O.get_mgrid(shape)
+        assert ours.shape == g[k].shape
+        assert np.abs(ours - g[k]).max() <= 1.2e-7, k
+        assert np.array_equal(ours[[0, -1]], g[k][[0, -1]]), k  # end points exact
+
+
+def test_input_mapping(golden_dir):
+    g = _load(golden_dir, "coords.npz")
+    ours = O.input_mapping(g["ffm/x"], g["ffm/B"])
+    assert ours.shape == g["ffm/out"].shape
+    np.testing.assert_allclose(ours, g["ffm/out"], atol=2e-6, rtol=0)
+
+
+def _siren_from_seed(g):
+    ctor = g["ctor"]
+    torch.manual_seed(int(g["seed"]))
+    m = O.torch_siren(int(ctor[0]), int(ctor[1]), int(ctor[2]), int(ctor[3]))  # omegas: class defaults 30 / 30
+    return m
+
+
+def _cs(t):
+    t = t.detach().double().reshape(-1)
+    return np.array([t.sum().item(), (t * t).sum().item(), t[0].item(), t[-1].item(), t[t.numel() // 2].item()])
+
+
+@pytest.mark.parametrize("name", ["siren_cfg1.npz", "siren_cfg2.npz"])
+def test_torch_restatement_matches_reference(golden_dir, name):
+    """Same seed -> same initial weights (RNG order), same forward, same 5-step Adam trajectory."""
+    g = _load(golden_dir, name)
+    m = _siren_from_seed(g)
+    sd = m.state_dict()
+    for k in [f for f in g.files if f.startswith("cs0/")]:
+        np.testing.assert_allclose(_cs(sd[k[4:]]), g[k], rtol=1e-12, atol=0)
+    coords = torch.from_numpy(O.get_mgrid(tuple(g["grid_shape"])))
+    out = m(coords)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=1e-6, rtol=1e-5)
+    losses = O.torch_fit(m, coords, torch.from_numpy(g["gt"]), int(g["steps"]), float(g["lr"]))
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-4)
+    np.testing.assert_allclose(m(coords).detach().numpy(), g["out_after"], atol=2e-5, rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["siren_cfg1.npz", "siren_cfg2.npz"])
+def test_numpy_forward_backward(golden_dir, name):
+    """Explicit NumPy forward / hand-derived backward against the reference's autograd gradients."""
+    g = _load(golden_dir, name)
+    m = _siren_from_seed(g)
+    L = int(g["ctor"][2])
+    Ws = [m.net[i].linear.weight.detach().numpy() for i in range(L + 1)] + [m.final_linear.weight.detach().numpy()]
+    bs = [m.net[i].linear.bias.detach().numpy() for i in range(L + 1)] + [m.final_linear.bias.detach().numpy()]
+    x = O.get_mgrid(tuple(g["grid_shape"]))
+    out, acts, _ = O.siren_forward(Ws, bs, x, 30.0, 30.0, True)
+    np.testing.assert_allclose(out, g["out"], atol=2e-6, rtol=1e-4)
+    np.testing.assert_allclose(acts[0], g["act_first"], atol=2e-5)
+    np.testing.assert_allclose(acts[-1], g["act_last"], atol=2e-5)
+    loss, gout = O.mse_loss(out, g["gt"])
+    assert math.isclose(loss, float(g["loss"]), rel_tol=1e-5)
+    dW, db = O.siren_backward(Ws, bs, x, gout, 30.0, 30.0)
+    names = [f"net.{i}.linear" for i in range(L + 1)] + ["final_linear"]
+    checked = 0
+    for n, w, b in zip(names, dW, db):
+        for suffix, arr in ((".weight", w), (".bias", b)):
+            key = "g/" + n + suffix
+            if key in g.files:
+                ref = g[key]
+                np.testing.assert_allclose(arr, ref, atol=1e-6 + 2e-4 * np.abs(ref).max(), rtol=0)
+                checked += 1
+            np.testing.assert_allclose(_cs(torch.from_numpy(arr))[:2], g["gcs/" + n + suffix][:2], rtol=2e-3,
+                                       atol=1e-7)
+    assert checked >= 4
+
+
+def test_inrmodel_variant_rng_order(golden_dir):
+    g = _load(golden_dir, "inrmodel_siren.npz")
+    torch.manual_seed(13)
+    m = O.torch_siren(3, 256, 2, 4, order="INRmodel")
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    for k in sd:
+        np.testing.assert_allclose(_cs(sd[k]), g["cs/" + k], rtol=1e-12, atol=0)
+    out = m(torch.from_numpy(O.get_mgrid((5, 4, 3)))).detach().numpy()
+    np.testing.assert_allclose(out, g["out"], atol=1e-6)
+
+
+def test_wire_forward(golden_dir):
+    g = _load(golden_dir, "wire_small.npz")
+    layers = []
+    i = 0
+    while f"w/net.{i}.linear.weight" in g.files:
+        layers.append((g[f"w/net.{i}.linear.weight"], g[f"w/net.{i}.linear.bias"],
+                       g[f"w/net.{i}.scale_orth.weight"], g[f"w/net.{i}.scale_orth.bias"]))
+        i += 1
+    assert len(layers) == 3
+    out = O.wire_forward(layers, g["w/final_linear.weight"], g["w/final_linear.bias"], g["x"], 1.2, 1.2)
+    np.testing.assert_allclose(out, g["out"], atol=2e-6, rtol=1e-4)
+
+
+def test_adam_matches_torch():
+    rng = np.random.RandomState(0)
+    p = rng.randn(1000).astype(np.float32)
+    tp = torch.nn.Parameter(torch.from_numpy(p.copy()))
+    opt = torch.optim.Adam([tp], lr=1e-3)
+    m = np.zeros_like(p)
+    v = np.zeros_like(p)
+    for step in range(1, 6):
+        gr = rng.randn(1000).astype(np.float32) * 10.0 ** rng.uniform(-6, 0)
+        tp.grad = torch.from_numpy(gr.copy())
+        opt.step()
+        p, m, v = O.adam_step(p, gr, m, v, step, 1e-3)
+        np.testing.assert_allclose(p, tp.detach().numpy(), atol=1e-7, rtol=1e-6)
+
+
+def test_degradation_against_scipy_and_torch():
+    from scipy import ndimage
+    rng = np.random.RandomState(1)
+    vol = rng.rand(12, 10, 3, 2).astype(np.float32)
+    # box only == avg_pool3d(2,2,1)
+    ours = O.degrade_forward(vol, blur=False)
+    t = torch.from_numpy(vol).permute(3, 0, 1, 2).unsqueeze(0)
+    ref = torch.nn.functional.avg_pool3d(t, (2, 2, 1), (2, 2, 1)).squeeze(0).permute(1, 2, 3, 0).numpy()
+    np.testing.assert_allclose(ours, ref, atol=1e-6)
+    # blur + box == gaussian_filter(sigma .5, mirror) in-plane, then zoom(.5, order 1, grid_mode) == 2-tap mean
+    blurred = ndimage.gaussian_filter(vol.astype(np.float64), sigma=(0.5, 0.5, 0, 0), mode="mirror")
+    ref2 = blurred.reshape(6, 2, 5, 2, 3, 2).mean(axis=(1, 3))
+    np.testing.assert_allclose(O.degrade_forward(vol, blur=True), ref2, atol=1e-6)
+    # adjoint identity <D x, y> == <x, D^T y>
+    y = rng.rand(6, 5, 3, 2).astype(np.float32)
+    for blur in (False, True):
+        lhs = float((O.degrade_forward(vol, blur).astype(np.float64) * y).sum())
+        rhs = float((vol.astype(np.float64) * O.degrade_adjoint(y, blur)).sum())
+        assert math.isclose(lhs, rhs, rel_tol=1e-5)
+    loss, grad = O.degraded_mse(vol, y)
+    tv = torch.from_numpy(vol).requires_grad_(True)
+    tl = ((torch.nn.functional.avg_pool3d(tv.permute(3, 0, 1, 2).unsqueeze(0), (2, 2, 1), (2, 2, 1)).squeeze(0)
+           .permute(1, 2, 3, 0) - torch.from_numpy(y)) ** 2).mean()
+    tl.backward()
+    assert math.isclose(loss, tl.item(), rel_tol=1e-5)
+    np.testing.assert_allclose(grad, tv.grad.numpy(), atol=1e-7)
+
+
+def test_metrics():
+    rng = np.random.RandomState(2)
+    a = rng.rand(40, 40)
+    assert O.ssim2d(a, a) == pytest.approx(1.0)
+    b = np.clip(a + 0.1 * rng.randn(40, 40), 0, 1)
+    s = O.ssim2d(a, b)
+    assert 0.0 < s < 1.0
+    assert O.psnr(a, a + 0.1) == pytest.approx(20.0, abs=1e-6)

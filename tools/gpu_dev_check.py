@@ -165,6 +165,12 @@ def timing():
     print(f"timing: query fwd {ms:.3f} ms  -> {rows / ms / 1e3:.1f} M vox/s, {rows * 541696 / ms / 1e9:.1f} TFLOP/s")
     ms_f = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()))
     print(f"timing: train fwd {ms_f:.3f} ms")
+    for mask in (1, 2, 4, 7):
+        os.environ["B200INR_WGRAD_ITEMS"] = str(mask)
+        ms_w = t(lambda: lib.b200inr_siren_wgrad(nb, ptr(st), None, g, rows, ptr(gflat), stream()))
+        print(f"timing: wgrad items mask={mask}: {ms_w:.3f} ms")
+    ms_d = t(lambda: lib.b200inr_siren_dgrad(nb, ptr(pk), ptr(st), rows, ptr(gout), stream()))
+    print(f"timing: dgrad {ms_d:.3f} ms")
     ms_b = t(lambda: lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()))
     print(f"timing: bwd+wgrad {ms_b:.3f} ms  -> step ~{ms_f + ms_b:.3f} ms, "
           f"{rows * 1623552 / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic")

@@ -1,0 +1,135 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (CPU, fp32) under fixed seeds.
+
+Run in the build container only (needs /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+The fixtures pin oracle/inr_oracle.py (tests/test_oracle_golden.py) and, on the GPU box, the CUDA path
+(tests/test_gpu_parity.py); /root/reference itself is never read at test time.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/implicit-neural-representations"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+import INRmodel  # noqa: E402
+import SRDWI  # noqa: E402
+
+torch.set_num_threads(4)
+
+
+def wire_classes():
+    """exec the two pure class-definition cells of wiretest.ipynb (cells 1 and 2)."""
+    nb = json.load(open(os.path.join(REF, "wiretest.ipynb")))
+    code = [c for c in nb["cells"] if c["cell_type"] == "code"]
+    ns = {"torch": torch, "nn": torch.nn, "np": np}
+    exec("".join(code[1]["source"]), ns)
+    exec("".join(code[2]["source"]), ns)
+    return ns
+
+
+def checksum(t):
+    t = t.detach().double().reshape(-1)
+    return np.array([t.sum().item(), (t * t).sum().item(), t[0].item(), t[-1].item(), t[t.numel() // 2].item()])
+
+
+def siren_case(name, ctor, seed, grid_shape, lr, steps, store_weights):
+    torch.manual_seed(seed)
+    m = SRDWI.Siren(*ctor)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    coords = SRDWI.get_mgrid(grid_shape)
+    gen = torch.Generator().manual_seed(seed + 1)
+    gt = torch.rand(coords.shape[0], ctor[3], generator=gen)
+    # forward + per-layer intermediates
+    h = coords
+    acts = []
+    for layer in list(m.net)[:-1]:
+        h, _ = layer.forward_with_intermediate(h)
+        acts.append(h.detach().numpy())
+    out = m.forward(coords)
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+    # trajectory: the in-lined loop of superresDWI.py:132-138
+    opt = torch.optim.Adam(lr=lr, params=list(m.parameters()))
+    losses = []
+    for _ in range(steps):
+        o = m.forward(coords)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    out_after = m.forward(coords).detach().numpy()
+    data = {
+        "ctor": np.array(ctor, dtype=np.float64), "seed": seed, "grid_shape": np.array(grid_shape), "lr": lr,
+        "steps": steps, "gt": gt.numpy(), "out": out.detach().numpy(), "loss": loss.item(),
+        "losses": np.array(losses), "out_after": out_after,
+        "act_first": acts[0], "act_last": acts[-1],
+    }
+    for k, v in sd0.items():
+        data["cs0/" + k] = checksum(v)
+        if store_weights:
+            data["w0/" + k] = v.numpy()
+    for k, v in grads.items():
+        data["gcs/" + k] = checksum(v)
+        if store_weights or v.numel() <= 8192:
+            data["g/" + k] = v.numpy()
+    for k, v in m.state_dict().items():
+        data["cs1/" + k] = checksum(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+    print(name, "loss", loss.item(), "losses", losses)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # ---- get_mgrid / input_mapping
+    data = {}
+    for shp in [(4, 3, 2), (5,), (7, 6), (1, 3), (25,), (50,), (3, 2, 2, 2), (128,), (257,)]:
+        data["mgrid/" + "x".join(map(str, shp))] = SRDWI.get_mgrid(shp).numpy()
+    rng = np.random.RandomState(3)
+    x = SRDWI.get_mgrid((6, 5, 4))
+    B = torch.from_numpy(rng.normal(size=(16, 3)) * 0.5).float()
+    data["ffm/x"] = x.numpy()
+    data["ffm/B"] = B.numpy()
+    data["ffm/out"] = SRDWI.input_mapping(x, B).numpy()
+    np.savez_compressed(os.path.join(OUT, "coords.npz"), **data)
+
+    # ---- SIREN cases (H = 256 is what the kernels implement)
+    siren_case("siren_cfg1", (2, 256, 2, 1), 11, (24, 20), 3e-4, 5, store_weights=True)
+    siren_case("siren_cfg2", (3, 256, 4, 31), 12, (10, 9, 8), 1e-4, 5, store_weights=False)
+
+    # ---- INRmodel.Siren construction order
+    torch.manual_seed(13)
+    m = INRmodel.Siren(3, 256, 2, 4)
+    d = {"cs/" + k: checksum(v) for k, v in m.state_dict().items()}
+    d["keys"] = np.array(list(m.state_dict().keys()))
+    xi = INRmodel.get_mgrid((5, 4, 3))
+    d["out"] = m.forward(xi).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "inrmodel_siren.npz"), **d)
+
+    # ---- WIRE (wiretest.ipynb cells 1-2), notebook hyper-parameters omega0 = scale = 1.2
+    ns = wire_classes()
+    torch.manual_seed(14)
+    w = ns["Siren"](in_features=3, hidden_features=32, hidden_layers=2, out_features=4, first_omega_0=1.2,
+                    hidden_omega_0=1.2, scale=1.2)
+    xw = SRDWI.get_mgrid((6, 5, 4))
+    ow = w(xw)
+    gtw = torch.rand(ow.shape, generator=torch.Generator().manual_seed(15))
+    ((ow - gtw) ** 2).mean().backward()
+    d = {"x": xw.numpy(), "out": ow.detach().numpy(), "gt": gtw.numpy()}
+    for k, v in w.state_dict().items():
+        d["w/" + k] = v.numpy()
+    for k, p in w.named_parameters():
+        if p.grad is not None:
+            d["g/" + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "wire_small.npz"), **d)
+    print("wire out", ow.abs().max().item())
+
+
+if __name__ == "__main__":
+    main()
