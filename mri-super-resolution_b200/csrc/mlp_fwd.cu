@@ -8,9 +8,14 @@
 //                  bulk-copy (TMA) engine into a 4-slot ring of 64-wide K chunks,
 //   epilogue     : tcgen05.ld -> +bias -> sin -> bf16 -> swizzled shared memory (the next layer's A operand),
 //   final linear : tcgen05.mma 128x32x256, +bias, optional clamp, coalesced fp32 store.
-// In training mode the epilogue also stashes sin outputs (bulk store of the finished A tile) and 16-bit phases.
+// The epilogue produces the next layer's A operand one 64-wide K block at a time and signals each block on its own
+// mbarrier, and the accumulator is double buffered in TMEM (2 x 256 columns), so the MMAs of layer l+1 run underneath
+// the epilogue of layer l: per layer the tensor pipe is exposed only for its last K block.
+// In training mode the finished A blocks (sin outputs) are bulk-stored to the stash by a dedicated thread, 16-bit
+// phases are stored straight from registers, and layer 0 also emits the coordinate operand used by wgrad.cu.
 //
-// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
+//             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
 #include <stdio.h>
 
 #include "common.cuh"
@@ -18,9 +23,12 @@
 
 namespace b200inr {
 
-constexpr int kFwdThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kFwdEpiWarps = 16;
+constexpr int kFwdFirstEpiWarp = 3;
+constexpr int kFwdThreads = (kFwdFirstEpiWarp + kFwdEpiWarps) * 32;  // 608
+constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;                   // 512
 constexpr uint32_t kEpiBarId = 1;
+constexpr int kFwdSlots = 4;
 
 struct FwdParams {
   const uint8_t* packed;
@@ -47,48 +55,44 @@ struct FwdSmem {
   static constexpr int kSlotBytes = H * 128;         // one K chunk of a hidden layer: [H rows][64]
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kABytes;
-  static constexpr int kOffW0 = kOffW + kKB * kSlotBytes;
+  static constexpr int kOffW0 = kOffW + kFwdSlots * kSlotBytes;
   static constexpr int kOffBias = kOffW0 + H * 16;
   static constexpr int kOffXa = (kOffBias + (kMaxSineLayers * H + 32) * 4 + 1023) / 1024 * 1024;
-  static constexpr int kOffBar = kOffXa + kTileRows * 128;  // xa block only carved out in training mode
-  static constexpr int kBytes = kOffBar + 128;
+  static constexpr int kOffBar = kOffXa + kTileRows * 128;
+  static constexpr int kBytes = kOffBar + 256;
 };
 
 constexpr float kPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
 constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 
-// Activation + stores for 8 consecutive columns [col, col+8) of row r.
+// sin + stores for the 16 consecutive columns [kb*64 + s*16, +16) of row r.
 template <bool kStash>
-__device__ __forceinline__ void emit_sine_chunk(const float (&th)[8], uint8_t* a_smem, int r, int col,
-                                                uint8_t* ph_tile) {
-  uint32_t yb[4];
-  uint32_t ph[4];
+__device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_block_addr, int r, int s,
+                                            uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float s0 = __sinf(th[2 * j]);
-    const float s1 = __sinf(th[2 * j + 1]);
-    yb[j] = pack_bf16x2(s0, s1);
-    if (kStash) {
-      const uint32_t p0 = __float_as_uint(fmaf(th[2 * j], kPhaseScale, kPhaseMagic));
-      const uint32_t p1 = __float_as_uint(fmaf(th[2 * j + 1], kPhaseScale, kPhaseMagic));
-      ph[j] = __byte_perm(p0, p1, 0x5410);
+  for (int c = 0; c < 2; ++c) {
+    uint32_t yb[4], ph[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
+      yb[j] = pack_bf16x2(__sinf(t0), __sinf(t1));
+      if (kStash) {
+        const uint32_t p0 = __float_as_uint(fmaf(t0, kPhaseScale, kPhaseMagic));
+        const uint32_t p1 = __float_as_uint(fmaf(t1, kPhaseScale, kPhaseMagic));
+        ph[j] = __byte_perm(p0, p1, 0x5410);
+      }
     }
-  }
-  const int kb = col >> 6;
-  const int ch = (col & 63) >> 3;
-  *reinterpret_cast<uint4*>(a_smem + kb * (kTileRows * 128) + sw128_chunk_off(r, ch)) =
-      make_uint4(yb[0], yb[1], yb[2], yb[3]);
-  if (kStash) {
-    *reinterpret_cast<uint4*>(ph_tile + (size_t(col >> 3) * kTileRows + r) * 16) =
-        make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
+    if (kStash)
+      *reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * (kTileRows * 16)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
   }
 }
 
 template <int H, bool kStash>
 __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
   using S = FwdSmem<H>;
+  static_assert(S::kKB == 4, "epilogue slicing assumes 4 K blocks");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic shared memory is only guaranteed 16-byte aligned: align to the 1024 B the swizzle atoms need
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem + S::kOffA;
   uint8_t* w_smem = smem + S::kOffW;
@@ -96,11 +100,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   float* bias_smem = reinterpret_cast<float*>(smem + S::kOffBias);
   uint8_t* xa_smem = smem + S::kOffXa;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;       // [4]
-  uint64_t* w_empty = bars + 4;  // [4]
-  uint64_t* a_ready = bars + 8;
-  uint64_t* d_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* w_full = bars;                     // [kFwdSlots]
+  uint64_t* w_empty = bars + kFwdSlots;        // [kFwdSlots]
+  uint64_t* a_ready = bars + 2 * kFwdSlots;    // [4]  K block kb of the next A operand is in shared memory
+  uint64_t* d_full = bars + 2 * kFwdSlots + 4;
+  uint64_t* a_free = bars + 2 * kFwdSlots + 5;  // stash stores of the A tile have been read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,15 +121,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       reinterpret_cast<uint4*>(xa_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S::kKB; ++i) {
+    for (int i = 0; i < kFwdSlots; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(a_ready, kEpiThreads);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kFwdEpiWarps);
     mbar_init(d_full, 1);
+    mbar_init(a_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -135,18 +141,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
-      uint32_t use = 0;
+      uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 1; l <= L + 1; ++l) {
           const bool hidden = (l <= L);
           const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
           const uint32_t bytes = hidden ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
-          for (int kb = 0; kb < S::kKB; ++kb) {
-            if (use > 0) mbar_wait(&w_empty[kb], (use - 1) & 1);
-            mbar_arrive_expect_tx(&w_full[kb], bytes);
-            bulk_g2s(w_smem + kb * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[kb]);
+          for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+            const uint32_t slot = c % kFwdSlots, round = c / kFwdSlots;
+            if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[slot], bytes);
+            bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[slot]);
           }
-          ++use;
         }
       }
     }
@@ -156,41 +162,62 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      uint32_t n = 0;
+      uint32_t c = 0, n = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        for (int l = 1; l <= L + 1; ++l) {
+        for (int l = 1; l <= L + 1; ++l, ++n) {
           const uint32_t idesc = (l <= L) ? idesc_bf16(128, H, false, false) : idesc_bf16(128, kOutPad, false, false);
-          mbar_wait(a_ready, n & 1);
-          tc_fence_after();
-          for (int kb = 0; kb < S::kKB; ++kb) {
-            mbar_wait(&w_full[kb], n & 1);
+          const uint32_t d_addr = tmem_d + uint32_t(l & 1) * 256;
+          for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+            const uint32_t slot = c % kFwdSlots;
+            mbar_wait(&a_ready[kb], n & 1);
+            mbar_wait(&w_full[slot], (c / kFwdSlots) & 1);
             tc_fence_after();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
-              const uint64_t db = smem_desc(w_base + kb * S::kSlotBytes + k4 * 32, hi);
-              umma_bf16_ss(tmem_d, da, db, idesc, (kb | k4) != 0);
+              const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+              umma_bf16_ss(d_addr, da, db, idesc, (kb | k4) != 0);
             }
-            umma_commit(&w_empty[kb]);
+            umma_commit(&w_empty[slot]);
           }
           umma_commit(d_full);
-          ++n;
         }
       }
     }
-  } else {
+  } else if (warp == 2) {
+    // =============================== stash store (training) ===============================
+    if (kStash && lane == 0) {
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        uint8_t* y_tile = p.stash_y + size_t(tile) * S::kABytes;
+        for (int l = 0; l <= L; ++l, ++n) {
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            mbar_wait(&a_ready[kb], n & 1);
+            bulk_s2g(y_tile + size_t(l) * p.stash_layer_stride + size_t(kb) * S::kABlock, a_smem + kb * S::kABlock,
+                     S::kABlock);
+          }
+          if (l == 0) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(a_free);
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= kFwdFirstEpiWarp) {
     // =============================== epilogue warps ===============================
-    const int et = threadIdx.x - 64;  // 0..255
-    const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int h = (warp - 2) >> 2;    // column half
-    const int r = q * 32 + lane;      // row inside the tile
+    const int et = threadIdx.x - kFwdFirstEpiWarp * 32;  // 0..511
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may access
+    const int s = (warp - kFwdFirstEpiWarp) >> 2;        // 16-column slice inside every 64-wide K block
+    const int r = q * 32 + lane;                         // row inside the tile
     const uint32_t t_lane = uint32_t(q * 32) << 16;
-    uint32_t n = 0;
+    const uint32_t a_addr = smem_u32(a_smem);
+    uint32_t n = 0, nf = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = int(blockIdx.x) + t * int(gridDim.x);
       const long long row0 = (long long)tile * kTileRows;
-      uint8_t* ph_tile = kStash ? p.stash_ph + size_t(tile) * S::kABytes : nullptr;
-      uint8_t* y_tile = kStash ? p.stash_y + size_t(tile) * S::kABytes : nullptr;
+      uint8_t* ph_row = kStash ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
 
       // ---- layer 0 on CUDA cores
       {
@@ -203,106 +230,93 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         } else {
           grid_coords(p.grid, row0 + r, x);
         }
-        if (kStash && h == 0) {  // x = hi + lo in bf16 (exact to 2^-17): B operand of dW_0 = dTheta_0^T X
+        if (kStash && s == 0) {  // x = hi + lo in bf16 (exact to 2^-17): B operand of dW_0 = dTheta_0^T X
           float hi[4], lo[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             hi[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
             lo[j] = x[j] - hi[j];
           }
-          *reinterpret_cast<uint4*>(xa_smem + sw128_chunk_off(r, 0)) =
-              make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
-                         pack_bf16x2(lo[2], lo[3]));
+          sts128(smem_u32(xa_smem) + sw128_chunk_off(r, 0),
+                 make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
+                            pack_bf16x2(lo[2], lo[3])));
         }
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int kb = 0; kb < S::kKB; ++kb) {
+          const int col0 = kb * 64 + s * 16;
+          float th[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = h * 128 + cc * 32 + g * 8;
-            float th[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w = w0_smem[col + j];
-              float acc = bias_smem[col + j];
-              acc = fmaf(x[0], w.x, acc);
-              acc = fmaf(x[1], w.y, acc);
-              acc = fmaf(x[2], w.z, acc);
-              acc = fmaf(x[3], w.w, acc);
-              th[j] = acc;
-            }
-            emit_sine_chunk<kStash>(th, a_smem, r, col, ph_tile);
+          for (int j = 0; j < 16; ++j) {
+            const float4 w = w0_smem[col0 + j];
+            float acc = bias_smem[col0 + j];
+            acc = fmaf(x[0], w.x, acc);
+            acc = fmaf(x[1], w.y, acc);
+            acc = fmaf(x[2], w.z, acc);
+            acc = fmaf(x[3], w.w, acc);
+            th[j] = acc;
           }
+          emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
+                              kStash ? ph_row + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[kb]);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        if (kStash) {
-          named_bar_sync(kEpiBarId, kEpiThreads);
-          if (et == 0) {
-            bulk_s2g(y_tile, a_smem, S::kABytes);
-            bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
-            bulk_commit();
-          }
-        }
-        mbar_arrive(a_ready);
       }
 
       // ---- hidden layers
       for (int l = 1; l <= L; ++l) {
         mbar_wait(d_full, n & 1);
         ++n;
-        tc_fence_after();
         if (kStash) {
-          if (et == 0) bulk_wait_read0();
-          named_bar_sync(kEpiBarId, kEpiThreads);
+          mbar_wait(a_free, nf & 1);
+          ++nf;
         }
+        tc_fence_after();
         const float* bl = bias_smem + l * H;
-        uint8_t* ph_l = kStash ? ph_tile + size_t(l) * p.stash_layer_stride : nullptr;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col0 = h * 128 + cc * 32;
-          uint32_t v[32];
-          tmem_ld32(tmem_d + t_lane + col0, v);
+        const uint32_t d_addr = tmem_d + t_lane + uint32_t(l & 1) * 256 + s * 16;
+        uint8_t* ph_l = kStash ? ph_row + size_t(l) * p.stash_layer_stride : nullptr;
+        uint32_t v[16], vn[16];
+        tmem_ld16(d_addr, vn);
+#pragma unroll
+        for (int kb = 0; kb < S::kKB; ++kb) {
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float th[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bl + col0 + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4);
-            th[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-            th[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-            th[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-            th[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-            th[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-            th[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-            th[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-            th[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-            emit_sine_chunk<kStash>(th, a_smem, r, col0 + g * 8, ph_l);
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
+          const int col0 = kb * 64 + s * 16;
+          float th[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bl + col0 + j4 * 4);
+            th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b.x;
+            th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b.y;
+            th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b.z;
+            th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b.w;
           }
+          emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
+                              kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[kb]);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        if (kStash) {
-          named_bar_sync(kEpiBarId, kEpiThreads);
-          if (et == 0) {
-            bulk_s2g(y_tile + size_t(l) * p.stash_layer_stride, a_smem, S::kABytes);
-            bulk_commit();
-          }
-        }
-        mbar_arrive(a_ready);
       }
 
       // ---- final linear: D[:, 0:32) + bias -> out
       {
         mbar_wait(d_full, n & 1);
         ++n;
+        if (kStash) {
+          mbar_wait(a_free, nf & 1);
+          ++nf;
+        }
         tc_fence_after();
-        if (kStash && et == 0) bulk_wait_read0();
-        named_bar_sync(kEpiBarId, kEpiThreads);  // A tile is free: reuse it as the fp32 output staging area
-        float* stage = reinterpret_cast<float*>(a_smem);
+        // the A tile is free (its MMAs and stash stores are done): reuse it as the fp32 output staging area
         const int C = p.C;
-        if (h == 0) {
+        if (s == 0) {
           uint32_t v[32];
-          tmem_ld32(tmem_d + t_lane, v);
+          tmem_ld32(tmem_d + t_lane + uint32_t((L + 1) & 1) * 256, v);
           tmem_ld_wait();
           const float* bf = bias_smem + (L + 1) * H;
 #pragma unroll
@@ -310,25 +324,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             if (c < C) {
               float o = __uint_as_float(v[c]) + bf[c];
               if (p.clamp) o = fmaxf(o, p.clamp_min);
-              stage[r * C + c] = o;
+              sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
             }
           }
         }
         tc_fence_before();
-        named_bar_sync(kEpiBarId, kEpiThreads);
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);
         long long valid = p.rows - row0;
         if (valid > kTileRows) valid = kTileRows;
         const int nout = int(valid) * C;
         float* dst = p.out + row0 * C;
-        for (int i = et; i < nout; i += kEpiThreads) dst[i] = stage[i];
-        named_bar_sync(kEpiBarId, kEpiThreads);  // staging consumed before the next tile overwrites A
+        for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);  // staging consumed before the next tile overwrites A
       }
     }
-    if (kStash && et == 0) bulk_wait0();
   }
 
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem_d);
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
 }
 
 // ------------------------------------------------------------------ launcher
