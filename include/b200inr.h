@@ -30,17 +30,26 @@ extern "C" {
 #define B200INR_ERR_CUDA (-4)
 #define B200INR_ERR_NULL (-5)
 
-#define B200INR_ACT_SINE 0
+#define B200INR_ACT_SINE 0 /* sin(omega * z)   (SineLayer, INR/SRDWI.py:59)                                  */
+#define B200INR_ACT_RELU 1 /* max(z, 0)         (Fourier-feature ReLU MLP of BASELINE config 4; omegas ignored) */
+
+#define B200INR_IN_COORDS 0   /* network input = the d <= 4 raw coordinates; first layer on CUDA cores (H = 256)   */
+#define B200INR_IN_FOURIER 1  /* network input = input_mapping(coords, B) (INR/SRDWI.py:111-116) computed in-kernel
+                                 from the d raw coordinates; in_features = d, first layer K = 2 * mapping_size      */
+#define B200INR_IN_FEATURES 2 /* network input = explicit fp32 feature rows [rows, in_features] (what the reference
+                                 scripts feed: pre-computed Fourier features, INR/superresDWI.py:121-122)          */
 
 /* Network description == ctor arguments of Siren (INR/SRDWI.py:68-71, INR/INRmodel.py:123-125). */
 typedef struct b200inr_net {
-  int32_t in_features;     /* d, raw coordinate dimension, 1..4                                 */
-  int32_t hidden_features; /* H, currently 256 (the width of every BASELINE SIREN config)        */
-  int32_t hidden_layers;   /* L, hidden->hidden sine layers; there are L+1 sine layers + 1 linear */
-  int32_t out_features;    /* C, 1..32                                                           */
-  float first_omega_0;     /* omega of the first SineLayer (INR/SRDWI.py:78)                      */
-  float hidden_omega_0;    /* omega of the hidden SineLayers (INR/SRDWI.py:81)                    */
-  int32_t activation;      /* B200INR_ACT_SINE                                                   */
+  int32_t in_features;     /* IN_COORDS / IN_FOURIER: d = 1..4; IN_FEATURES: K0, a multiple of 64, <= H        */
+  int32_t hidden_features; /* H: 256 (all modes) or 512 (IN_FOURIER / IN_FEATURES)                           */
+  int32_t hidden_layers;   /* L, hidden->hidden layers; there are L+1 activated layers + 1 final linear      */
+  int32_t out_features;    /* C, 1..32                                                                       */
+  float first_omega_0;     /* omega of the first SineLayer (INR/SRDWI.py:78)                                  */
+  float hidden_omega_0;    /* omega of the hidden SineLayers (INR/SRDWI.py:81)                                */
+  int32_t activation;      /* B200INR_ACT_*                                                                  */
+  int32_t input_mode;      /* B200INR_IN_*                                                                   */
+  int32_t mapping_size;    /* m of input_mapping (IN_FOURIER only; 2m a multiple of 64, <= H), else 0         */
   int32_t reserved;
 } b200inr_net;
 

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200inr.so")
 
 MAX_TAPS = 8
-ACT_SINE = 0
+ACT_SINE, ACT_RELU = 0, 1
+IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
 
 
 class Net(ctypes.Structure):
@@ -26,6 +27,8 @@ class Net(ctypes.Structure):
         ("first_omega_0", ctypes.c_float),
         ("hidden_omega_0", ctypes.c_float),
         ("activation", ctypes.c_int32),
+        ("input_mode", ctypes.c_int32),
+        ("mapping_size", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
     ]
 
@@ -95,9 +98,9 @@ def check(code, what):
 
 
 def make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.0, hidden_omega_0=30.0,
-             activation=ACT_SINE):
+             activation=ACT_SINE, input_mode=IN_COORDS, mapping_size=0):
     return Net(int(in_features), int(hidden_features), int(hidden_layers), int(out_features), float(first_omega_0),
-               float(hidden_omega_0), int(activation), 0)
+               float(hidden_omega_0), int(activation), int(input_mode), int(mapping_size), 0)
 
 
 def make_grid(shape, row_begin=0):
@@ -116,7 +119,7 @@ def param_count(net):
 
 
 def param_offsets(net):
-    n = 2 * (net.hidden_layers + 2)
+    n = 2 * (net.hidden_layers + 2) + (1 if net.input_mode == IN_FOURIER else 0)
     off = (_i64 * n)()
     check(load().b200inr_param_offsets(ctypes.byref(net), off), "param_offsets")
     return list(off)

@@ -16,6 +16,13 @@ int launch_siren_bwd(const b200inr_net* net, const void* packed, void* stash, in
                      int num_sms, cudaStream_t stream);
 int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords, const b200inr_grid* grid,
                        int64_t rows, float* grad_params, int num_sms, cudaStream_t stream);
+int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                   int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                   cudaStream_t stream);
+int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                   int num_sms, cudaStream_t stream);
+int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, int num_sms,
+                     cudaStream_t stream);
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
                float* loss_accum, cudaStream_t stream);
 int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
@@ -27,17 +34,38 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
 
+static bool is_gen(const b200inr_net* net) { return net->input_mode != B200INR_IN_COORDS; }
+
 static int check_net(const b200inr_net* net) {
   if (!net) return B200INR_ERR_NULL;
-  if (net->hidden_features != 256) return B200INR_ERR_BAD_SHAPE;
-  if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
   if (net->hidden_layers < 0 || net->hidden_layers + 1 > kMaxSineLayers) return B200INR_ERR_BAD_SHAPE;
   if (net->out_features < 1 || net->out_features > kOutPad) return B200INR_ERR_BAD_SHAPE;
-  if (net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
-  return B200INR_OK;
+  if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
+  const int H = net->hidden_features;
+  switch (net->input_mode) {
+    case B200INR_IN_COORDS:  // SIREN on raw coordinates: first layer on CUDA cores, H = 256
+      if (H != 256 || net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
+      if (net->in_features < 1 || net->in_features > 4 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
+      return B200INR_OK;
+    case B200INR_IN_FOURIER: {
+      if (H != 256 && H != 512) return B200INR_ERR_BAD_SHAPE;
+      if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
+      const int k0 = 2 * net->mapping_size;
+      if (net->mapping_size < 32 || k0 % 64 != 0 || k0 > H) return B200INR_ERR_BAD_SHAPE;
+      return B200INR_OK;
+    }
+    case B200INR_IN_FEATURES:
+      if (H != 256 && H != 512) return B200INR_ERR_BAD_SHAPE;
+      if (net->in_features < 64 || net->in_features % 64 != 0 || net->in_features > H || net->mapping_size != 0)
+        return B200INR_ERR_BAD_SHAPE;
+      return B200INR_OK;
+    default:
+      return B200INR_ERR_BAD_SHAPE;
+  }
 }
 
 static int check_grid(const b200inr_net* net, const b200inr_grid* grid, int64_t rows) {
+  if (net->input_mode == B200INR_IN_FEATURES) return B200INR_ERR_BAD_SHAPE;  // explicit features have no grid form
   if (grid->ndim != net->in_features) return B200INR_ERR_BAD_SHAPE;
   long long tot = 1;
   for (int j = 0; j < grid->ndim; ++j) {
@@ -92,7 +120,10 @@ int b200inr_param_count(const b200inr_net* net, int64_t* n_floats) {
   int e = check_net(net);
   if (e) return e;
   if (!n_floats) return B200INR_ERR_NULL;
-  *n_floats = param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, nullptr);
+  if (is_gen(net))
+    *n_floats = gen_param_offsets(make_gen_dims(net), nullptr);
+  else
+    *n_floats = param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, nullptr);
   return B200INR_OK;
 }
 
@@ -100,7 +131,10 @@ int b200inr_param_offsets(const b200inr_net* net, int64_t* offsets) {
   int e = check_net(net);
   if (e) return e;
   if (!offsets) return B200INR_ERR_NULL;
-  param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, offsets);
+  if (is_gen(net))
+    gen_param_offsets(make_gen_dims(net), offsets);
+  else
+    param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, offsets);
   return B200INR_OK;
 }
 
@@ -108,7 +142,8 @@ int b200inr_packed_bytes(const b200inr_net* net, size_t* bytes) {
   int e = check_net(net);
   if (e) return e;
   if (!bytes) return B200INR_ERR_NULL;
-  *bytes = make_pack_layout(net->hidden_features, net->hidden_layers).total;
+  *bytes = is_gen(net) ? make_gen_pack_layout(make_gen_dims(net)).total
+                       : make_pack_layout(net->hidden_features, net->hidden_layers).total;
   return B200INR_OK;
 }
 
@@ -125,7 +160,8 @@ int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes) {
   if (e) return e;
   if (!bytes) return B200INR_ERR_NULL;
   if (rows < 0) return B200INR_ERR_BAD_SHAPE;
-  *bytes = make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
+  *bytes = is_gen(net) ? make_gen_stash_layout(make_gen_dims(net), rows).total
+                       : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
   return B200INR_OK;
 }
 
@@ -142,6 +178,9 @@ int b200inr_siren_forward(const b200inr_net* net, const void* packed, const floa
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_gen(net))
+    return launch_gen_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
+                          static_cast<cudaStream_t>(stream));
   return launch_siren_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
                           static_cast<cudaStream_t>(stream));
 }
@@ -162,6 +201,10 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_gen(net)) {
+    if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
+    return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
+  }
   if ((e = launch_siren_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, s);
 }
@@ -177,6 +220,7 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_gen(net)) return launch_gen_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
 }
 
@@ -192,6 +236,7 @@ int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords
   if ((reinterpret_cast<uintptr_t>(stash) & 1023) || !aligned16(grad_params)) return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_gen(net)) return launch_gen_wgrad(net, stash, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
 }
 

@@ -99,6 +99,134 @@ __host__ __device__ inline int64_t param_offsets(int d, int H, int L, int C, int
   return o;
 }
 
+// ------------------------------------------------------------------ generic family (gen_*.cu)
+// Networks whose first layer is already a tensor-core layer: input = Fourier features computed in-kernel
+// (B200INR_IN_FOURIER) or explicit feature rows (B200INR_IN_FEATURES); H = 256 or 512; sine or ReLU.
+struct GenDims {
+  int d;    // raw coordinate dimension (IN_FOURIER) or 0
+  int m;    // mapping size (IN_FOURIER) or 0
+  int K0;   // width of the network input (2m or in_features), multiple of 64, <= H
+  int H, L, C;
+  int act, in_mode;
+  float omega0, omegah;
+  __host__ __device__ int kb0() const { return K0 / 64; }
+  __host__ __device__ int kbh() const { return H / 64; }
+  __host__ __device__ int nh() const { return H / 256; }
+};
+
+__host__ inline GenDims make_gen_dims(const b200inr_net* n) {
+  GenDims g{};
+  g.in_mode = n->input_mode;
+  g.d = n->input_mode == B200INR_IN_FOURIER ? n->in_features : 0;
+  g.m = n->input_mode == B200INR_IN_FOURIER ? n->mapping_size : 0;
+  g.K0 = n->input_mode == B200INR_IN_FOURIER ? 2 * n->mapping_size : n->in_features;
+  g.H = n->hidden_features;
+  g.L = n->hidden_layers;
+  g.C = n->out_features;
+  g.act = n->activation;
+  g.omega0 = n->activation == B200INR_ACT_SINE ? n->first_omega_0 : 1.0f;
+  g.omegah = n->activation == B200INR_ACT_SINE ? n->hidden_omega_0 : 1.0f;
+  return g;
+}
+
+// Flat fp32 parameter offsets of the generic family: W_i at off[2i], b_i at off[2i+1] (i = 0..L+1), B at off[2(L+2)].
+__host__ __device__ inline int64_t gen_param_offsets(const GenDims& g, int64_t* off) {
+  int64_t o = 0;
+  auto seg = [&](int64_t n) {
+    int64_t at = o;
+    o += (n + 3) & ~int64_t(3);
+    return at;
+  };
+  for (int l = 0; l <= g.L; ++l) {
+    const int64_t w = seg(int64_t(g.H) * (l == 0 ? g.K0 : g.H));
+    const int64_t b = seg(g.H);
+    if (off) { off[2 * l] = w; off[2 * l + 1] = b; }
+  }
+  const int64_t w = seg(int64_t(g.C) * g.H);
+  const int64_t b = seg(g.C);
+  if (off) { off[2 * (g.L + 1)] = w; off[2 * (g.L + 1) + 1] = b; }
+  if (g.in_mode == B200INR_IN_FOURIER) {
+    const int64_t bm = seg(int64_t(g.m) * g.d);
+    if (off) off[2 * (g.L + 2)] = bm;
+  }
+  return o;
+}
+
+constexpr int kGenChunkBytes = 256 * 128;  // weight chunk: [256 rows (N)][64 (K)] bf16, SWIZZLE_128B
+
+// Packed operand buffer of the generic family.  Forward chunks of layer l are ordered (n-half, k-block);
+// dgrad chunks of layer l >= 1 are ordered (n-half over inputs, k-block over outputs).
+struct GenPackLayout {
+  size_t bias;   // float [(L+1)*H + 32]  omega-folded biases, then the final bias padded to 32
+  size_t bmat;   // float4 [m]            frequency matrix rows (zero padded to 4 coordinates)
+  size_t w;      // layer 0: nh*kb0 chunks; layers 1..L: nh*kbh chunks each
+  size_t wt;     // layers 1..L: nh*kbh chunks each
+  size_t wf;     // [kbh][32][64]
+  size_t wft;    // nh chunks [256][64]
+  size_t total;
+  __host__ __device__ size_t w_layer(const GenDims& g, int l) const {
+    return l == 0 ? w : w + size_t(g.nh()) * g.kb0() * kGenChunkBytes +
+                            size_t(l - 1) * g.nh() * g.kbh() * kGenChunkBytes;
+  }
+  __host__ __device__ size_t wt_layer(const GenDims& g, int l) const {  // l >= 1
+    return wt + size_t(l - 1) * g.nh() * g.kbh() * kGenChunkBytes;
+  }
+};
+
+__host__ __device__ inline GenPackLayout make_gen_pack_layout(const GenDims& g) {
+  GenPackLayout p;
+  size_t o = 0;
+  p.bias = o;
+  o += (size_t(g.L + 1) * g.H + 32) * 4;
+  o = (o + 15) & ~size_t(15);
+  p.bmat = o;
+  o += size_t(g.m) * 16;
+  o = (o + 1023) & ~size_t(1023);
+  p.w = o;
+  o += (size_t(g.nh()) * g.kb0() + size_t(g.L) * g.nh() * g.kbh()) * kGenChunkBytes;
+  p.wt = o;
+  o += size_t(g.L) * g.nh() * g.kbh() * kGenChunkBytes;
+  p.wf = o;
+  o += size_t(g.kbh()) * kOutPad * 128;
+  p.wft = o;
+  o += size_t(g.nh()) * kGenChunkBytes;
+  p.total = o;
+  return p;
+}
+
+// Activation stash of the generic family (T = ceil(rows/128) tiles).
+struct GenStashLayout {
+  size_t ain;  // T x [K0/64][128][64] bf16          network input (A operand of layer 0, B operand of dW_0)
+  size_t y;    // (L+1) x T x [H/64][128][64] bf16   layer outputs
+  size_t ph;   // (L+1) x T x [H/8][128][8] u16      phases (sine only, else empty)
+  size_t dz;   // (L+1) x T x [H/64][128][64] bf16   dL/dtheta
+  size_t dzo;  // T x [128][64] bf16                  dL/dout
+  size_t tile_in, tile_h, layer_stride;
+  size_t total;
+  int64_t tiles;
+};
+
+__host__ __device__ inline GenStashLayout make_gen_stash_layout(const GenDims& g, int64_t rows) {
+  GenStashLayout s;
+  s.tiles = (rows + kTileRows - 1) / kTileRows;
+  s.tile_in = size_t(kTileRows) * g.K0 * 2;
+  s.tile_h = size_t(kTileRows) * g.H * 2;
+  s.layer_stride = size_t(s.tiles) * s.tile_h;
+  size_t o = 0;
+  s.ain = o;
+  o += size_t(s.tiles) * s.tile_in;
+  s.y = o;
+  o += size_t(g.L + 1) * s.layer_stride;
+  s.ph = o;
+  if (g.act == B200INR_ACT_SINE) o += size_t(g.L + 1) * s.layer_stride;
+  s.dz = o;
+  o += size_t(g.L + 1) * s.layer_stride;
+  s.dzo = o;
+  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.total = o;
+  return s;
+}
+
 struct GridDesc {
   int ndim;
   int shape[4];

@@ -1,0 +1,316 @@
+// gen_bwd.cu -- activation-gradient chain (dgrad) of the generic coordinate-MLP family (see gen_fwd.cu) for sm_100a.
+//
+// Replaces loss.backward() through the activated layers (autograd of INR/SRDWI.py:58-59 for sine; of nn.ReLU for the
+// Fourier-feature MLP of BASELINE config 4):
+//     dTheta_L   = (dOut  W_f ) .* act'(theta_L)
+//     dTheta_l-1 = (dTheta_l W'_l) .* act'(theta_l-1)          l = L .. 1
+// act' = cos(theta) from the stashed 16-bit phase (sine) or 1[y > 0] from the stashed bf16 output (ReLU).  The chain
+// stops at layer 0: the network input (Fourier features / explicit features) carries no gradient on this path.
+// Every dTheta_l tile and the bf16 dOut tile go to the stash for wgrad.cu.
+//
+// Warp roles as in gen_fwd.cu.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200inr {
+
+constexpr int kGenBwdEpiWarps = 16;
+constexpr int kGenBwdFirstEpiWarp = 3;
+constexpr int kGenBwdThreads = (kGenBwdFirstEpiWarp + kGenBwdEpiWarps) * 32;
+
+struct GenBwdParams {
+  const uint8_t* packed;
+  GenDims g;
+  GenPackLayout pl;
+  long long rows;
+  int num_tiles;
+  const float* grad_out;  // [rows, C]
+  const uint8_t* stash_y;
+  const uint8_t* stash_ph;
+  uint8_t* stash_dz;
+  uint8_t* stash_dzo;
+  size_t layer_stride;
+};
+
+template <int H>
+struct GenBwdSmem {
+  static constexpr int kKB = H / 64;
+  static constexpr int kABlock = kTileRows * 128;
+  static constexpr int kABytes = kKB * kABlock;
+  static constexpr int kSlots = (H == 512) ? 2 : 4;  // 128 KB A + 16 KB dOut block leave room for two chunks at H = 512
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = kABytes;
+  static constexpr int kOffDzo = kOffW + kSlots * kGenChunkBytes;
+  static constexpr int kOffBar = kOffDzo + kTileRows * 128;
+  static constexpr int kBytes = kOffBar + 256;
+};
+
+constexpr float kGenPhaseToRad = 9.587379924285257e-05f;  // 2*pi / 65536
+
+__device__ __forceinline__ float gen_cos_from_phase(uint32_t ph16) {
+  const float f = __uint_as_float(0x4B000000u | ph16) - 8388608.0f;
+  return __cosf(f * kGenPhaseToRad);
+}
+
+template <int H, int ACT>
+__global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwdParams p) {
+  using S = GenBwdSmem<H>;
+  constexpr int NH = H / 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem + S::kOffA;
+  uint8_t* w_smem = smem + S::kOffW;
+  uint8_t* dzo_smem = smem + S::kOffDzo;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + S::kSlots;
+  uint64_t* a_ready = bars + 2 * S::kSlots;
+  uint64_t* dzo_ready = bars + 2 * S::kSlots + 1;
+  uint64_t* d_full = bars + 2 * S::kSlots + 2;
+  uint64_t* a_free = bars + 2 * S::kSlots + 3;
+  uint64_t* dzo_free = bars + 2 * S::kSlots + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const GenDims g = p.g;
+  const int L = g.L;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::kSlots; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(a_ready, kGenBwdEpiWarps);
+    mbar_init(dzo_ready, kGenBwdEpiWarps);
+    mbar_init(d_full, 1);
+    mbar_init(a_free, 1);
+    mbar_init(dzo_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int u = 0; u <= L; ++u) {  // u = 0: W_f^T (NH chunks); u >= 1: W'^T of layer L - u + 1 (NH * kKB chunks)
+          const int nchunks = (u == 0) ? NH : NH * S::kKB;
+          const uint8_t* src = (u == 0) ? p.packed + p.pl.wft : p.packed + p.pl.wt_layer(g, L - u + 1);
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
+            if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[slot], kGenChunkBytes);
+            bulk_g2s(w_smem + slot * kGenChunkBytes, src + size_t(j) * kGenChunkBytes, kGenChunkBytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint64_t hi = smem_desc_hi_sw128(0, 1024);
+      const uint32_t a_base = smem_u32(a_smem);
+      const uint32_t w_base = smem_u32(w_smem);
+      const uint32_t dzo_base = smem_u32(dzo_smem);
+      const uint32_t idesc = idesc_bf16(128, 256, false, false);
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);  // a_ready completes L + 1 times per tile
+        for (int u = 0; u <= L; ++u) {
+          if (u == 0)
+            mbar_wait(dzo_ready, t & 1);
+          else
+            mbar_wait(a_ready, (inst0 + u - 1) & 1);
+          tc_fence_after();
+          const int kbn = (u == 0) ? 1 : S::kKB;
+          for (int nh = 0; nh < NH; ++nh) {
+            for (int kb = 0; kb < kbn; ++kb, ++c) {
+              const uint32_t slot = c % S::kSlots;
+              mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
+              tc_fence_after();
+              const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * S::kABlock;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16_ss(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
+                             smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+              }
+              umma_commit(&w_empty[slot]);
+            }
+          }
+          umma_commit(d_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =============================== stash store ===============================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        mbar_wait(dzo_ready, t & 1);
+        bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(dzo_free);
+        for (int l = L; l >= 0; --l, ++n) {
+          mbar_wait(a_ready, n & 1);
+          bulk_s2g(p.stash_dz + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(a_free);
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= kGenBwdFirstEpiWarp) {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;
+    const int s = (warp - kGenBwdFirstEpiWarp) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = uint32_t(q * 32) << 16;
+    const uint32_t a_addr = smem_u32(a_smem);
+    const uint32_t dzo_addr = smem_u32(dzo_smem);
+    const int C = g.C;
+    uint32_t n = 0, nf = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const long long row0 = (long long)tile * kTileRows;
+
+      // ---- dOut tile -> bf16 [128][64] block
+      if (t > 0) mbar_wait(dzo_free, (t - 1) & 1);
+      {
+        const bool valid = (row0 + r) < p.rows;
+        const float* gp = p.grad_out + (row0 + r) * C;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * s + cc;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = ch * 8 + j;
+            v[j] = (valid && col < C) ? gp[col] : 0.f;
+          }
+          sts128(dzo_addr + sw128_chunk_off(r, ch),
+                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7])));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dzo_ready);
+      }
+
+      // ---- dTheta_l = dY_l .* act'(theta_l), l = L .. 0
+      for (int l = L; l >= 0; --l) {
+        // derivative source of this thread's row: 16-bit phases (sine) or the bf16 outputs themselves (ReLU)
+        const uint8_t* src_l = (ACT == B200INR_ACT_SINE)
+                                   ? p.stash_ph + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes +
+                                         size_t(r) * 16 + size_t(2 * s) * (kTileRows * 16)
+                                   : p.stash_y + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes;
+        auto load_src = [&](int kb, uint4 (&dst)[2]) {
+          if (ACT == B200INR_ACT_SINE) {
+            dst[0] = *reinterpret_cast<const uint4*>(src_l + size_t(kb * 8) * (kTileRows * 16));
+            dst[1] = *reinterpret_cast<const uint4*>(src_l + size_t(kb * 8 + 1) * (kTileRows * 16));
+          } else {
+            dst[0] = *reinterpret_cast<const uint4*>(src_l + size_t(kb) * S::kABlock + sw128_chunk_off(r, 2 * s));
+            dst[1] = *reinterpret_cast<const uint4*>(src_l + size_t(kb) * S::kABlock + sw128_chunk_off(r, 2 * s + 1));
+          }
+        };
+        uint4 sv[2], svn[2];
+        load_src(0, svn);
+        mbar_wait(d_full, n & 1);
+        ++n;
+        if (nf > 0) mbar_wait(a_free, (nf - 1) & 1);
+        ++nf;
+        tc_fence_after();
+        const uint32_t d_addr = tmem_d + t_lane + s * 16;
+        uint32_t v[16], vn[16];
+        tmem_ld16(d_addr, vn);
+#pragma unroll 2
+        for (int kb = 0; kb < S::kKB; ++kb) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          sv[0] = svn[0];
+          sv[1] = svn[1];
+          if (kb + 1 < S::kKB) {
+            tmem_ld16(d_addr + (kb + 1) * 64, vn);
+            load_src(kb + 1, svn);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t pw[4] = {sv[c].x, sv[c].y, sv[c].z, sv[c].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float d0 = __uint_as_float(v[c * 8 + 2 * j]);
+              float d1 = __uint_as_float(v[c * 8 + 2 * j + 1]);
+              if (ACT == B200INR_ACT_SINE) {
+                d0 *= gen_cos_from_phase(pw[j] & 0xFFFFu);
+                d1 *= gen_cos_from_phase(pw[j] >> 16);
+              } else {  // bf16 y > 0  <=>  sign bit clear and magnitude non-zero
+                d0 = ((pw[j] & 0x8000u) == 0u && (pw[j] & 0x7FFFu) != 0u) ? d0 : 0.f;
+                d1 = ((pw[j] & 0x80000000u) == 0u && (pw[j] & 0x7FFF0000u) != 0u) ? d1 : 0.f;
+              }
+              o[j] = pack_bf16x2(d0, d1);
+            }
+            sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c), make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
+}
+
+template <int H, int ACT>
+static int launch_gen_bwd_t(const GenBwdParams& p, int grid_x, cudaStream_t stream) {
+  const int smem = GenBwdSmem<H>::kBytes + 1024;
+  if (cudaFuncSetAttribute(gen_bwd_kernel<H, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
+  gen_bwd_kernel<H, ACT><<<grid_x, kGenBwdThreads, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                   int num_sms, cudaStream_t stream) {
+  GenBwdParams p{};
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.g = make_gen_dims(net);
+  p.pl = make_gen_pack_layout(p.g);
+  p.rows = rows;
+  p.num_tiles = int((rows + kTileRows - 1) / kTileRows);
+  p.grad_out = grad_out;
+  const GenStashLayout sl = make_gen_stash_layout(p.g, rows);
+  uint8_t* st = reinterpret_cast<uint8_t*>(stash);
+  p.stash_y = st + sl.y;
+  p.stash_ph = st + sl.ph;
+  p.stash_dz = st + sl.dz;
+  p.stash_dzo = st + sl.dzo;
+  p.layer_stride = sl.layer_stride;
+  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const bool sine = net->activation == B200INR_ACT_SINE;
+  if (p.g.H == 256)
+    return sine ? launch_gen_bwd_t<256, B200INR_ACT_SINE>(p, grid_x, stream)
+                : launch_gen_bwd_t<256, B200INR_ACT_RELU>(p, grid_x, stream);
+  return sine ? launch_gen_bwd_t<512, B200INR_ACT_SINE>(p, grid_x, stream)
+              : launch_gen_bwd_t<512, B200INR_ACT_RELU>(p, grid_x, stream);
+}
+
+}  // namespace b200inr

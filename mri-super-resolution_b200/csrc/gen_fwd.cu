@@ -1,0 +1,398 @@
+// gen_fwd.cu -- fused forward of the "generic" coordinate-MLP family for sm_100a: networks whose FIRST layer is
+// already a tensor-core layer, H = 256 or 512, sine or ReLU activation.
+//
+// Replaces  INR.forward(input_mapping(coords, B))  with the reference's Siren fed by Fourier features
+// (INR/superresDWI.py:105-113,121-122,134: Siren(in_features=2m, hidden 512, ...)) and the Fourier-feature ReLU MLP
+// of BASELINE config 4.  Network input per 128-row tile is produced straight into shared memory as the A operand:
+//   B200INR_IN_FOURIER : [sin(2 pi x B^T), cos(2 pi x B^T)] (INR/SRDWI.py:111-116) from the voxel index or from
+//                        explicit d-dimensional coordinates -- the [N, 2m] feature matrix never exists in HBM,
+//   B200INR_IN_FEATURES: explicit fp32 feature rows (what the reference scripts pass), converted to bf16.
+// Every layer: tcgen05.mma 128 x 256 x 16 over (n-half, k-block) weight chunks streamed by the bulk-copy engine,
+// fp32 accumulators in TMEM (H columns), epilogue tcgen05.ld -> +bias -> sin | relu -> bf16 -> swizzled smem.
+// With H = 512 the activation tile (128 KB) and the 512 accumulator columns fill shared memory and TMEM, so MMA and
+// epilogue of one tile alternate; the epilogue is cheap next to the 4x larger GEMM (ReLU) and the weight ring
+// prefetches across it.
+//
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
+//             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200inr {
+
+constexpr int kGenEpiWarps = 16;
+constexpr int kGenFirstEpiWarp = 3;
+constexpr int kGenThreads = (kGenFirstEpiWarp + kGenEpiWarps) * 32;  // 608
+constexpr int kGenEpiThreads = kGenEpiWarps * 32;
+constexpr uint32_t kGenEpiBarId = 1;
+
+struct GenFwdParams {
+  const uint8_t* packed;
+  GenDims g;
+  GenPackLayout pl;
+  const float* coords;  // IN_FOURIER: [rows, d] or nullptr (grid);  IN_FEATURES: [rows, K0]
+  GridDesc grid;
+  long long rows;
+  int num_tiles;
+  float* out;
+  int clamp;
+  float clamp_min;
+  uint8_t* stash_ain;  // nullptr => inference
+  uint8_t* stash_y;
+  uint8_t* stash_ph;
+  size_t layer_stride;
+};
+
+template <int H>
+struct GenSmem {
+  static constexpr int kKB = H / 64;
+  static constexpr int kABlock = kTileRows * 128;
+  static constexpr int kABytes = kKB * kABlock;
+  static constexpr int kSlots = (H == 512) ? 3 : 4;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = kABytes;
+  static constexpr int kOffBar = kOffW + kSlots * kGenChunkBytes;
+  static constexpr int kBytes = kOffBar + 256;
+};
+
+constexpr float kGenPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
+constexpr float kGenPhaseMagic = 12582912.0f;          // 1.5 * 2^23
+
+template <int H, int ACT, bool kStash>
+__global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdParams p) {
+  using S = GenSmem<H>;
+  constexpr int NH = H / 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem + S::kOffA;
+  uint8_t* w_smem = smem + S::kOffW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* w_full = bars;                    // [kSlots]
+  uint64_t* w_empty = bars + S::kSlots;       // [kSlots]
+  uint64_t* a_ready = bars + 2 * S::kSlots;   // A operand of the next layer complete in shared memory
+  uint64_t* d_full = bars + 2 * S::kSlots + 1;
+  uint64_t* a_free = bars + 2 * S::kSlots + 2;  // stash store of the A tile has been read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const GenDims g = p.g;
+  const int L = g.L;
+  const int KB0 = g.K0 / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::kSlots; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(a_ready, kGenEpiWarps);
+    mbar_init(d_full, 1);
+    mbar_init(a_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l <= L + 1; ++l) {
+          const bool act_layer = (l <= L);
+          const int nchunks = act_layer ? NH * (l == 0 ? KB0 : S::kKB) : S::kKB;
+          const uint8_t* src = act_layer ? p.packed + p.pl.w_layer(g, l) : p.packed + p.pl.wf;
+          const uint32_t bytes = act_layer ? uint32_t(kGenChunkBytes) : uint32_t(kOutPad * 128);
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
+            if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[slot], bytes);
+            bulk_g2s(w_smem + slot * kGenChunkBytes, src + size_t(j) * bytes, bytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint64_t hi = smem_desc_hi_sw128(0, 1024);
+      const uint32_t a_base = smem_u32(a_smem);
+      const uint32_t w_base = smem_u32(w_smem);
+      const uint32_t idesc_h = idesc_bf16(128, 256, false, false);
+      const uint32_t idesc_f = idesc_bf16(128, kOutPad, false, false);
+      uint32_t c = 0, n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l <= L + 1; ++l, ++n) {
+          mbar_wait(a_ready, n & 1);
+          tc_fence_after();
+          const bool act_layer = (l <= L);
+          const int kbn = act_layer ? (l == 0 ? KB0 : S::kKB) : S::kKB;
+          const int nhn = act_layer ? NH : 1;
+          for (int nh = 0; nh < nhn; ++nh) {
+            for (int kb = 0; kb < kbn; ++kb, ++c) {
+              const uint32_t slot = c % S::kSlots;
+              mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
+                const uint64_t db = smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi);
+                umma_bf16_ss(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
+              }
+              umma_commit(&w_empty[slot]);
+            }
+          }
+          umma_commit(d_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =============================== stash store (training) ===============================
+    if (kStash && lane == 0) {
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        for (int l = -1; l <= L; ++l, ++n) {  // l = -1: the network input tile
+          mbar_wait(a_ready, n & 1);
+          if (l < 0)
+            bulk_s2g(p.stash_ain + size_t(tile) * (size_t(KB0) * S::kABlock), a_smem, uint32_t(KB0) * S::kABlock);
+          else
+            bulk_s2g(p.stash_y + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(a_free);
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= kGenFirstEpiWarp) {
+    // =============================== epilogue warps ===============================
+    const int et = threadIdx.x - kGenFirstEpiWarp * 32;
+    const int q = warp & 3;
+    const int s = (warp - kGenFirstEpiWarp) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = uint32_t(q * 32) << 16;
+    const uint32_t a_addr = smem_u32(a_smem);
+    const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
+    const float4* bmat_g = reinterpret_cast<const float4*>(p.packed + p.pl.bmat);
+    uint32_t n = 0, nf = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const long long row0 = (long long)tile * kTileRows;
+
+      // ---- network input -> A operand
+      {
+        long long row = row0 + r;
+        if (row >= p.rows) row = p.rows - 1;
+        float xs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g.in_mode == B200INR_IN_FOURIER) {
+          float x[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.coords != nullptr) {
+            for (int j = 0; j < g.d; ++j) x[j] = p.coords[row * g.d + j];
+          } else {
+            grid_coords(p.grid, row0 + r, x);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xs[j] = __fmul_rn(6.283185307179586f, x[j]);  // (2 pi x) first, like the reference
+        }
+        for (int kb = 0; kb < KB0; ++kb) {
+          const int col0 = kb * 64 + s * 16;
+          float v[16];
+          if (g.in_mode == B200INR_IN_FOURIER) {
+            const bool is_sin = col0 < g.m;  // m is a multiple of 16: a 16-column slice never straddles sin | cos
+            const int k0 = is_sin ? col0 : col0 - g.m;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 bk = __ldg(bmat_g + k0 + j);
+              float pr = xs[0] * bk.x;
+              pr = fmaf(xs[1], bk.y, pr);
+              pr = fmaf(xs[2], bk.z, pr);
+              pr = fmaf(xs[3], bk.w, pr);
+              v[j] = is_sin ? __sinf(pr) : __cosf(pr);
+            }
+          } else {
+            const float4* f = reinterpret_cast<const float4*>(p.coords + row * g.K0 + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 x4 = __ldg(f + j4);
+              v[j4 * 4 + 0] = x4.x; v[j4 * 4 + 1] = x4.y; v[j4 * 4 + 2] = x4.z; v[j4 * 4 + 3] = x4.w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c),
+                   make_uint4(pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                              pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7])));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+
+      // ---- activated layers
+      for (int l = 0; l <= L; ++l) {
+        mbar_wait(d_full, n & 1);
+        ++n;
+        if (kStash) {
+          mbar_wait(a_free, nf & 1);
+          ++nf;
+        }
+        tc_fence_after();
+        const float* bl = bias_g + l * H;
+        const uint32_t d_addr = tmem_d + t_lane + s * 16;
+        uint8_t* ph_l = (kStash && ACT == B200INR_ACT_SINE)
+                            ? p.stash_ph + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes + size_t(r) * 16
+                            : nullptr;
+        uint32_t v[16], vn[16];
+        tmem_ld16(d_addr, vn);
+#pragma unroll 2
+        for (int kb = 0; kb < S::kKB; ++kb) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
+          const int col0 = kb * 64 + s * 16;
+          float th[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b.x;
+            th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b.y;
+            th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b.z;
+            th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t yb[4], ph[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
+              if (ACT == B200INR_ACT_SINE) {
+                yb[j] = pack_bf16x2(__sinf(t0), __sinf(t1));
+                if (kStash) {
+                  const uint32_t p0 = __float_as_uint(fmaf(t0, kGenPhaseScale, kGenPhaseMagic));
+                  const uint32_t p1 = __float_as_uint(fmaf(t1, kGenPhaseScale, kGenPhaseMagic));
+                  ph[j] = __byte_perm(p0, p1, 0x5410);
+                }
+              } else {
+                yb[j] = pack_bf16x2(fmaxf(t0, 0.f), fmaxf(t1, 0.f));
+              }
+            }
+            sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
+            if (kStash && ACT == B200INR_ACT_SINE)
+              *reinterpret_cast<uint4*>(ph_l + size_t(kb * 8 + 2 * s + c) * (kTileRows * 16)) =
+                  make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+
+      // ---- final linear: D[:, 0:32) + bias -> out
+      {
+        mbar_wait(d_full, n & 1);
+        ++n;
+        if (kStash) {
+          mbar_wait(a_free, nf & 1);
+          ++nf;
+        }
+        tc_fence_after();
+        const int C = g.C;
+        if (s == 0) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + t_lane, v);
+          tmem_ld_wait();
+          const float* bf = bias_g + (L + 1) * H;
+#pragma unroll
+          for (int c = 0; c < kOutPad; ++c) {
+            if (c < C) {
+              float o = __uint_as_float(v[c]) + __ldg(bf + c);
+              if (p.clamp) o = fmaxf(o, p.clamp_min);
+              sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
+            }
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(kGenEpiBarId, kGenEpiThreads);
+        long long valid = p.rows - row0;
+        if (valid > kTileRows) valid = kTileRows;
+        const int nout = int(valid) * C;
+        float* dst = p.out + row0 * C;
+        for (int i = et; i < nout; i += kGenEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
+        named_bar_sync(kGenEpiBarId, kGenEpiThreads);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
+}
+
+template <int H, int ACT>
+static int launch_gen_fwd_t(const GenFwdParams& p, bool stash, int grid_x, cudaStream_t stream) {
+  const int smem = GenSmem<H>::kBytes + 1024;
+  if (stash) {
+    if (cudaFuncSetAttribute(gen_fwd_kernel<H, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return B200INR_ERR_CUDA;
+    gen_fwd_kernel<H, ACT, true><<<grid_x, kGenThreads, smem, stream>>>(p);
+  } else {
+    if (cudaFuncSetAttribute(gen_fwd_kernel<H, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return B200INR_ERR_CUDA;
+    gen_fwd_kernel<H, ACT, false><<<grid_x, kGenThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                   int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                   cudaStream_t stream) {
+  GenFwdParams p{};
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.g = make_gen_dims(net);
+  p.pl = make_gen_pack_layout(p.g);
+  p.coords = coords;
+  if (grid) {
+    p.grid.ndim = grid->ndim;
+    long long tot = 1;
+    for (int j = 0; j < 4; ++j) {
+      p.grid.shape[j] = (j < grid->ndim) ? grid->shape[j] : 1;
+      tot *= p.grid.shape[j];
+    }
+    p.grid.row_begin = grid->row_begin;
+    p.grid.total = tot;
+  }
+  p.rows = rows;
+  p.num_tiles = int((rows + kTileRows - 1) / kTileRows);
+  p.out = out;
+  p.clamp = clamp;
+  p.clamp_min = clamp_min;
+  if (stash) {
+    const GenStashLayout sl = make_gen_stash_layout(p.g, rows);
+    uint8_t* st = reinterpret_cast<uint8_t*>(stash);
+    p.stash_ain = st + sl.ain;
+    p.stash_y = st + sl.y;
+    p.stash_ph = st + sl.ph;
+    p.layer_stride = sl.layer_stride;
+  }
+  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const bool sine = net->activation == B200INR_ACT_SINE;
+  if (p.g.H == 256)
+    return sine ? launch_gen_fwd_t<256, B200INR_ACT_SINE>(p, stash != nullptr, grid_x, stream)
+                : launch_gen_fwd_t<256, B200INR_ACT_RELU>(p, stash != nullptr, grid_x, stream);
+  return sine ? launch_gen_fwd_t<512, B200INR_ACT_SINE>(p, stash != nullptr, grid_x, stream)
+              : launch_gen_fwd_t<512, B200INR_ACT_RELU>(p, stash != nullptr, grid_x, stream);
+}
+
+}  // namespace b200inr

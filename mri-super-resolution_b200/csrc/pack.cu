@@ -73,7 +73,80 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
 }
 
+// ------------------------------------------------------------------ generic family (see common.cuh)
+struct GenPackParams {
+  const float* params;
+  uint8_t* packed;
+  GenDims g;
+  GenPackLayout pl;
+  long long off[2 * (kMaxSineLayers + 2) + 1];
+};
+
+__global__ void __launch_bounds__(256) gen_pack_kernel(const GenPackParams p) {
+  const GenDims g = p.g;
+  const int H = g.H, L = g.L, C = g.C;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+
+  float* bias = reinterpret_cast<float*>(p.packed + p.pl.bias);
+  for (long long i = tid; i < (long long)(L + 1) * H + 32; i += nthreads) {
+    float v = 0.f;
+    if (i < (long long)(L + 1) * H) {
+      const int l = int(i / H), h = int(i % H);
+      v = (l == 0 ? g.omega0 : g.omegah) * p.params[p.off[2 * l + 1] + h];
+    } else {
+      const int c = int(i - (long long)(L + 1) * H);
+      if (c < C) v = p.params[p.off[2 * (L + 1) + 1] + c];
+    }
+    bias[i] = v;
+  }
+  for (long long i = tid; i < g.m; i += nthreads) {
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < g.d; ++j) w[j] = p.params[p.off[2 * (L + 2)] + i * g.d + j];
+    reinterpret_cast<float4*>(p.packed + p.pl.bmat)[i] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  // activated layers
+  for (int l = 0; l <= L; ++l) {
+    const int K = (l == 0) ? g.K0 : H;
+    const int kbn = K / 64;
+    const float om = (l == 0) ? g.omega0 : g.omegah;
+    uint8_t* wf = p.packed + p.pl.w_layer(g, l);
+    uint8_t* wt = (l >= 1) ? p.packed + p.pl.wt_layer(g, l) : nullptr;
+    for (long long i = tid; i < (long long)H * K; i += nthreads) {
+      const int o = int(i / K), k = int(i % K);
+      const float v = om * p.params[p.off[2 * l] + i];
+      put_bf16(wf + size_t((o >> 8) * kbn + (k >> 6)) * kGenChunkBytes, o & 255, k & 63, v);
+      if (wt) put_bf16(wt + size_t((k >> 8) * (H / 64) + (o >> 6)) * kGenChunkBytes, k & 255, o & 63, v);
+    }
+  }
+  // final linear
+  for (long long i = tid; i < (long long)kOutPad * H; i += nthreads) {
+    const int c = int(i / H), k = int(i % H);
+    const float v = (c < C) ? p.params[p.off[2 * (L + 1)] + (long long)c * H + k] : 0.f;
+    put_bf16(p.packed + p.pl.wf + size_t(k >> 6) * kOutPad * 128, c, k & 63, v);
+  }
+  for (long long i = tid; i < (long long)H * kDzoPad; i += nthreads) {
+    const int n = int(i / kDzoPad), c = int(i % kDzoPad);
+    const float v = (c < C) ? p.params[p.off[2 * (L + 1)] + (long long)c * H + n] : 0.f;
+    put_bf16(p.packed + p.pl.wft + size_t(n >> 8) * kGenChunkBytes, n & 255, c, v);
+  }
+}
+
+int launch_gen_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream) {
+  GenPackParams p{};
+  p.params = params;
+  p.packed = reinterpret_cast<uint8_t*>(packed);
+  p.g = make_gen_dims(net);
+  p.pl = make_gen_pack_layout(p.g);
+  int64_t off[2 * (kMaxSineLayers + 2) + 1] = {0};
+  gen_param_offsets(p.g, off);
+  for (int i = 0; i < 2 * (p.g.L + 2) + 1; ++i) p.off[i] = off[i];
+  gen_pack_kernel<<<592, 256, 0, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream) {
+  if (net->input_mode != B200INR_IN_COORDS) return launch_gen_pack(net, params, packed, stream);
   PackParams p{};
   p.params = params;
   p.packed = reinterpret_cast<uint8_t*>(packed);

@@ -158,7 +158,151 @@ class _SirenFunction(torch.autograd.Function):
         return (None, None, *grads)
 
 
-class Siren(nn.Module):
+class _FusedMLP(nn.Module):
+    """Engine plumbing shared by the reference-facing modules: flat fp32 parameter vector + bf16 operand buffer on the
+    device, the fused forward / backward calls, and the fused query / fit entry points."""
+
+    def _init_engine(self, desc, grid_dim):
+        self._desc = desc
+        self._grid_dim = grid_dim  # rank of the coordinate grid accepted by query()/fit(); None: explicit features only
+        self._engine = None        # device-side staging (flat fp32 params, packed bf16 operands)
+        self._optim = None         # Adam state of fit()
+
+    def _frozen(self):
+        """Non-trainable tensors stored in the flat vector after the parameters (the Fourier matrix B)."""
+        return []
+
+    # ---------------------------------------------------------------- parameter plumbing
+    def _offsets_canonical(self):
+        return self._engine_state()["offsets"]
+
+    def _engine_state(self):
+        dev = self._canonical()[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("b200inr: the module must be on a CUDA device (call .cuda()); there is no CPU path")
+        eng = self._engine
+        if eng is None or eng["device"] != dev:
+            _lib.load()
+            n = _lib.param_count(self._desc)
+            eng = {
+                "device": dev,
+                "offsets": _lib.param_offsets(self._desc),
+                "flat": torch.zeros(n, dtype=torch.float32, device=dev),
+                "packed": _aligned_bytes(_lib.packed_bytes(self._desc), dev),
+                "key": None,
+            }
+            self._engine = eng
+        return eng
+
+    def _sync_params(self):
+        """Refresh the flat fp32 copy and the bf16 operand buffer when any parameter changed since the last call."""
+        eng = self._engine_state()
+        ps = self._canonical() + self._frozen()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != eng["key"]:
+            flat = eng["flat"]
+            with torch.no_grad():
+                for o, p in zip(eng["offsets"], ps):
+                    flat[o:o + p.numel()].copy_(p.reshape(-1))
+            self._pack(eng)
+            eng["key"] = key
+        return eng
+
+    def _pack(self, eng):
+        with torch.cuda.device(eng["device"]):
+            _lib.check(_lib.load().b200inr_pack_weights(ctypes.byref(self._desc), _ptr(eng["flat"]),
+                                                        _ptr(eng["packed"]), _stream()), "pack_weights")
+
+    def _writeback_params(self, eng):
+        """Copy the flat fp32 master (updated by fit) back into the nn.Parameters."""
+        ps = self._canonical()
+        with torch.no_grad():
+            for o, p in zip(eng["offsets"], ps):
+                p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
+        eng["key"] = tuple((p.data_ptr(), p._version) for p in ps + self._frozen())
+
+    # ---------------------------------------------------------------- kernel calls
+    def _forward_rows(self, coords, grid, rows, train, clamp=None, out=None, eng=None):
+        eng = eng or self._sync_params()
+        dev = eng["device"]
+        if out is None:
+            out = torch.empty((rows, self.out_features), dtype=torch.float32, device=dev)
+        if rows == 0:  # empty input: nothing to launch (an empty tensor has no device pointer)
+            return out, (torch.empty(0, dtype=torch.uint8, device=dev) if train else None)
+        stash = _aligned_bytes(_lib.stash_bytes(self._desc, rows), dev) if train else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200inr_siren_forward(
+                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(coords), ctypes.byref(grid) if grid else None,
+                rows, _ptr(out), int(clamp is not None), float(clamp or 0.0), _ptr(stash), _stream()), "siren_forward")
+        return out, stash
+
+    def _backward_rows(self, stash, coords, grid, rows, grad_out, flat_grad=None, eng=None):
+        eng = eng or self._engine_state()
+        dev = eng["device"]
+        grad_out = grad_out.contiguous().float()
+        if flat_grad is None:
+            flat_grad = torch.zeros_like(eng["flat"])
+        if rows == 0:
+            return flat_grad
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200inr_siren_backward(
+                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(stash), _ptr(coords),
+                ctypes.byref(grid) if grid else None, rows, _ptr(grad_out), _ptr(flat_grad), _stream()),
+                "siren_backward")
+        return flat_grad
+
+    # ---------------------------------------------------------------- nn.Module protocol
+    def forward(self, coords):
+        """out = INR.forward(x) (INR/superresDWI.py:134).  Coordinates carry no gradient: SRDWI.Siren detaches them
+        (INR/SRDWI.py:88); the INRmodel variant's input gradient (PerturbNet phase) is not part of this path."""
+        _require_cuda(coords, "forward input")
+        if coords.dim() != 2 or coords.shape[1] != self.in_features:
+            raise RuntimeError(f"b200inr: expected an input of shape [N, {self.in_features}]")
+        coords = coords.detach().contiguous().float()
+        return _SirenFunction.apply(coords, self, *self._canonical())
+
+    # ---------------------------------------------------------------- fused query
+    def query(self, shape, clamp_min=0.0, out=None, row_range=None):
+        """torch.clamp(INR.forward(get_mgrid(shape)), min=0) of INR/superresDWI.py:161, coordinates derived in-kernel.
+
+        row_range=(begin, end) restricts the call to a contiguous range of the flattened grid (a rank's shard).
+        Returns [rows, out_features] fp32 on the module's device; pass clamp_min=None for the raw output.
+        """
+        shape = tuple(int(s) for s in shape)
+        if self._grid_dim is None:
+            raise RuntimeError("b200inr: a network fed with explicit features has no grid form; call forward(features)")
+        if len(shape) != self._grid_dim:
+            raise RuntimeError("b200inr: query grid rank must equal the coordinate dimension")
+        total = int(np.prod(shape))
+        begin, end = (0, total) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        grid = _lib.make_grid(shape, begin)
+        with torch.no_grad():
+            res, _ = self._forward_rows(None, grid, end - begin, train=False, clamp=clamp_min, out=out)
+        return res
+
+    # ---------------------------------------------------------------- fused fit
+    def fit(self, target, shape, steps, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
+            global_count=None, process_group=None, reset_optimizer=False):
+        """The reference training loop (INR/superresDWI.py:132-138) on a dense coordinate grid, without autograd:
+        per step  fused forward -> loss (+ LR degradation) -> fused backward -> [all-reduce] -> Adam -> re-stage bf16.
+
+        target   CUDA fp32.  degrade=None: [rows, C] values at the grid points.  degrade='pool': the LR volume
+                 [X/2, Y/2, Z, C] (flattened or not) that the 2x2x1 in-plane average of the prediction must match.
+        shape    the (HR) coordinate grid; rows = prod(shape) unless row_range=(begin, end) selects this rank's slab.
+        process_group / global_count: multi-GPU data parallel -- gradients are summed with one all-reduce per step and
+                 the loss is normalised by the global element count (SURVEY.md section 8e).
+        Returns the per-step loss as a CUDA tensor [steps] (this rank's share of the global mean).
+        """
+        session = FitSession(self, target, shape, lr=lr, degrade=degrade, betas=betas, eps=eps, row_range=row_range,
+                             global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer)
+        losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
+        for it in range(steps):
+            losses[it:it + 1].copy_(session.step())
+        session.finish()
+        return losses
+
+
+class Siren(_FusedMLP):
     """Reference INR/SRDWI.py:67-91 (default) or INR/INRmodel.py:122-151 (`variant='INRmodel'`).
 
     Same constructor arguments, registration order (final_linear is both an attribute and the last element of `net`,
@@ -198,12 +342,13 @@ class Siren(nn.Module):
         self.net = nn.Sequential(*net)
         self.first_omega_0 = float(first_omega_0)
         self.hidden_omega_0 = float(net[1].omega_0) if hidden_layers > 0 else float(hidden_omega_0)
-        self._desc = _lib.make_net(in_features, hidden_features, hidden_layers, out_features, self.first_omega_0,
-                                   self.hidden_omega_0)
-        self._engine = None  # device-side staging (flat fp32 params, packed bf16 operands)
-        self._optim = None   # Adam state of fit()
+        # in_features <= 4: raw coordinates (first layer on CUDA cores, grid-mode fit/query available);
+        # wider inputs are explicit feature rows, e.g. pre-computed Fourier features (INR/superresDWI.py:108-122)
+        mode = _lib.IN_COORDS if self.in_features <= 4 else _lib.IN_FEATURES
+        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, self.first_omega_0,
+                                        self.hidden_omega_0, input_mode=mode),
+                          self.in_features if mode == _lib.IN_COORDS else None)
 
-    # ---------------------------------------------------------------- parameter plumbing
     def _canonical(self):
         """Parameters in the flat-layout order of include/b200inr.h: W0 b0 ... WL bL Wf bf."""
         ps = []
@@ -212,131 +357,62 @@ class Siren(nn.Module):
         ps += [self.final_linear.weight, self.final_linear.bias]
         return ps
 
-    def _offsets_canonical(self):
-        return self._engine_state()["offsets"]
 
-    def _engine_state(self):
-        dev = self.final_linear.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("b200inr: the module must be on a CUDA device (call .cuda()); there is no CPU path")
-        eng = self._engine
-        if eng is None or eng["device"] != dev:
-            _lib.load()
-            n = _lib.param_count(self._desc)
-            eng = {
-                "device": dev,
-                "offsets": _lib.param_offsets(self._desc),
-                "flat": torch.zeros(n, dtype=torch.float32, device=dev),
-                "packed": _aligned_bytes(_lib.packed_bytes(self._desc), dev),
-                "key": None,
-            }
-            self._engine = eng
-        return eng
+class FourierMLP(_FusedMLP):
+    """Fourier features + MLP with the feature map fused into the first layer: the [N, 2m] matrix that input_mapping
+    (INR/SRDWI.py:111-116) materialises, and that the reference re-reads from HBM every step, never exists.
 
-    def _sync_params(self):
-        """Refresh the flat fp32 copy and the bf16 operand buffer when any parameter changed since the last call."""
-        eng = self._engine_state()
-        ps = self._canonical()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
-        if key != eng["key"]:
-            flat = eng["flat"]
+    activation="relu": BASELINE config 4, nn.Sequential(Linear, ReLU, ..., Linear) with torch default init
+                       (state-dict keys net.0.*, net.2.*, ...);
+    activation="sine": the reference scripts' own combination, Siren(in_features=2m, ...) fed with
+                       input_mapping(x, B) (INR/superresDWI.py:105-113): same construction order, init and keys.
+    forward(coords [N, d]) == net(input_mapping(coords, B)); query / fit take the coordinate grid.
+    """
+
+    def __init__(self, in_features, mapping_size, hidden_features, hidden_layers, out_features, B, activation="relu",
+                 first_omega_0=30., hidden_omega_0=30.):
+        super().__init__()
+        if activation not in ("relu", "sine"):
+            raise ValueError("activation must be relu or sine")
+        self.in_features, self.mapping_size = int(in_features), int(mapping_size)
+        self.hidden_features, self.hidden_layers = int(hidden_features), int(hidden_layers)
+        self.out_features, self.activation = int(out_features), activation
+        B = torch.as_tensor(B, dtype=torch.float32)
+        if tuple(B.shape) != (self.mapping_size, self.in_features):
+            raise ValueError("B must have shape [mapping_size, in_features]")
+        self.register_buffer("B", B.clone())
+        k0 = 2 * self.mapping_size
+        if activation == "sine":  # built exactly like Siren(in_features=2m, ...) (INR/SRDWI.py:75-85)
+            bound = np.sqrt(6 / hidden_features) / hidden_omega_0
+            self.final_linear = nn.Linear(hidden_features, out_features)
             with torch.no_grad():
-                for o, p in zip(eng["offsets"], ps):
-                    flat[o:o + p.numel()].copy_(p.reshape(-1))
-            self._pack(eng)
-            eng["key"] = key
-        return eng
+                self.final_linear.weight.uniform_(-bound, bound)
+            layers = [SineLayer(k0, hidden_features, is_first=True, omega_0=first_omega_0)]
+            layers += [SineLayer(hidden_features, hidden_features, is_first=False, omega_0=hidden_omega_0)
+                       for _ in range(hidden_layers)]
+            self.net = nn.Sequential(*layers, self.final_linear)
+            self._linears = [layer.linear for layer in layers] + [self.final_linear]
+            act = _lib.ACT_SINE
+        else:
+            mods = [nn.Linear(k0, hidden_features), nn.ReLU()]
+            for _ in range(hidden_layers):
+                mods += [nn.Linear(hidden_features, hidden_features), nn.ReLU()]
+            mods.append(nn.Linear(hidden_features, out_features))
+            self.net = nn.Sequential(*mods)
+            self._linears = [m for m in mods if isinstance(m, nn.Linear)]
+            act = _lib.ACT_RELU
+        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0,
+                                        hidden_omega_0, activation=act, input_mode=_lib.IN_FOURIER,
+                                        mapping_size=mapping_size), self.in_features)
 
-    def _pack(self, eng):
-        with torch.cuda.device(eng["device"]):
-            _lib.check(_lib.load().b200inr_pack_weights(ctypes.byref(self._desc), _ptr(eng["flat"]),
-                                                        _ptr(eng["packed"]), _stream()), "pack_weights")
+    def _canonical(self):
+        ps = []
+        for lin in self._linears:
+            ps += [lin.weight, lin.bias]
+        return ps
 
-    def _writeback_params(self, eng):
-        """Copy the flat fp32 master (updated by fit) back into the nn.Parameters."""
-        ps = self._canonical()
-        with torch.no_grad():
-            for o, p in zip(eng["offsets"], ps):
-                p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
-        eng["key"] = tuple((p.data_ptr(), p._version) for p in ps)
-
-    # ---------------------------------------------------------------- kernel calls
-    def _forward_rows(self, coords, grid, rows, train, clamp=None, out=None, eng=None):
-        eng = eng or self._sync_params()
-        dev = eng["device"]
-        if out is None:
-            out = torch.empty((rows, self.out_features), dtype=torch.float32, device=dev)
-        if rows == 0:  # empty input: nothing to launch (an empty tensor has no device pointer)
-            return out, (torch.empty(0, dtype=torch.uint8, device=dev) if train else None)
-        stash = _aligned_bytes(_lib.stash_bytes(self._desc, rows), dev) if train else None
-        with torch.cuda.device(dev):
-            _lib.check(_lib.load().b200inr_siren_forward(
-                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(coords), ctypes.byref(grid) if grid else None,
-                rows, _ptr(out), int(clamp is not None), float(clamp or 0.0), _ptr(stash), _stream()), "siren_forward")
-        return out, stash
-
-    def _backward_rows(self, stash, coords, grid, rows, grad_out, flat_grad=None, eng=None):
-        eng = eng or self._engine_state()
-        dev = eng["device"]
-        grad_out = grad_out.contiguous().float()
-        if flat_grad is None:
-            flat_grad = torch.zeros_like(eng["flat"])
-        if rows == 0:
-            return flat_grad
-        with torch.cuda.device(dev):
-            _lib.check(_lib.load().b200inr_siren_backward(
-                ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(stash), _ptr(coords),
-                ctypes.byref(grid) if grid else None, rows, _ptr(grad_out), _ptr(flat_grad), _stream()),
-                "siren_backward")
-        return flat_grad
-
-    # ---------------------------------------------------------------- nn.Module protocol
-    def forward(self, coords):
-        """out = INR.forward(x) (INR/superresDWI.py:134).  Coordinates carry no gradient: SRDWI.Siren detaches them
-        (INR/SRDWI.py:88); the INRmodel variant's input gradient (PerturbNet phase) is not part of this path."""
-        _require_cuda(coords, "Siren.forward input")
-        if coords.dim() != 2 or coords.shape[1] != self.in_features:
-            raise RuntimeError(f"b200inr: expected coords of shape [N, {self.in_features}]")
-        coords = coords.detach().contiguous().float()
-        return _SirenFunction.apply(coords, self, *self._canonical())
-
-    # ---------------------------------------------------------------- fused query
-    def query(self, shape, clamp_min=0.0, out=None, row_range=None):
-        """torch.clamp(INR.forward(get_mgrid(shape)), min=0) of INR/superresDWI.py:161, coordinates derived in-kernel.
-
-        row_range=(begin, end) restricts the call to a contiguous range of the flattened grid (a rank's shard).
-        Returns [rows, out_features] fp32 on the module's device; pass clamp_min=None for the raw output.
-        """
-        shape = tuple(int(s) for s in shape)
-        if len(shape) != self.in_features:
-            raise RuntimeError("b200inr: query grid rank must equal in_features")
-        total = int(np.prod(shape))
-        begin, end = (0, total) if row_range is None else (int(row_range[0]), int(row_range[1]))
-        grid = _lib.make_grid(shape, begin)
-        with torch.no_grad():
-            res, _ = self._forward_rows(None, grid, end - begin, train=False, clamp=clamp_min, out=out)
-        return res
-
-    # ---------------------------------------------------------------- fused fit
-    def fit(self, target, shape, steps, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
-            global_count=None, process_group=None, reset_optimizer=False):
-        """The reference training loop (INR/superresDWI.py:132-138) on a dense coordinate grid, without autograd:
-        per step  fused forward -> loss (+ LR degradation) -> fused backward -> [all-reduce] -> Adam -> re-stage bf16.
-
-        target   CUDA fp32.  degrade=None: [rows, C] values at the grid points.  degrade='pool': the LR volume
-                 [X/2, Y/2, Z, C] (flattened or not) that the 2x2x1 in-plane average of the prediction must match.
-        shape    the (HR) coordinate grid; rows = prod(shape) unless row_range=(begin, end) selects this rank's slab.
-        process_group / global_count: multi-GPU data parallel -- gradients are summed with one all-reduce per step and
-                 the loss is normalised by the global element count (SURVEY.md section 8e).
-        Returns the per-step loss as a CUDA tensor [steps] (this rank's share of the global mean).
-        """
-        session = FitSession(self, target, shape, lr=lr, degrade=degrade, betas=betas, eps=eps, row_range=row_range,
-                             global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer)
-        losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
-        for it in range(steps):
-            losses[it:it + 1].copy_(session.step())
-        session.finish()
-        return losses
+    def _frozen(self):
+        return [self.B]
 
 
 class FitSession:
@@ -362,8 +438,8 @@ class FitSession:
         begin, end = (0, total) if row_range is None else (int(row_range[0]), int(row_range[1]))
         rows = self.rows = end - begin
         C = self.C = module.out_features
-        if len(shape) != module.in_features:
-            raise RuntimeError("b200inr: fit grid rank must equal in_features")
+        if module._grid_dim is None or len(shape) != module._grid_dim:
+            raise RuntimeError("b200inr: fit grid rank must equal the coordinate dimension")
         self.grid = _lib.make_grid(shape, begin)
         self.degrade = degrade
         target = target.detach().contiguous().float().reshape(-1)

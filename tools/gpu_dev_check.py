@@ -188,3 +188,98 @@ if __name__ == "__main__":
         print("mlp 3D bigger"); mlp(3, 4, 31, (64, 64, 32), True)
     if "timing" in which:
         timing()
+
+
+def gen_checks():
+    """Generic family (Fourier features in-kernel / explicit features, H = 256 / 512, sine / ReLU) vs fp32 torch."""
+    import numpy as np
+    import b200inr
+
+    def ref_forward(m, x):
+        feats = torch.cat([torch.sin((2.0 * math.pi * x) @ m.B.T), torch.cos((2.0 * math.pi * x) @ m.B.T)], -1)
+        h = feats
+        if m.activation == "relu":
+            return m.net(h)
+        for layer in list(m.net)[:-1]:
+            h = torch.sin(layer.omega_0 * layer.linear(h))
+        return m.net[-1](h)
+
+    rs = np.random.RandomState(0)
+    cases = [("relu", 256, 512, 3, 31, (16, 12, 9)), ("relu", 128, 256, 2, 5, (16, 12, 9)),
+             ("sine", 128, 256, 2, 1, (16, 12, 9)), ("sine", 128, 512, 3, 1, (20, 16, 8)),
+             ("relu", 256, 512, 3, 31, (64, 64, 32))]
+    for act, msz, H, Lh, C, shape in cases:
+        torch.manual_seed(1)
+        B = rs.normal(size=(msz, 3)) * 0.5
+        m = b200inr.FourierMLP(3, msz, H, Lh, C, B, activation=act).to(dev)
+        coords = b200inr.get_mgrid(shape).to(dev)
+        rows = coords.shape[0]
+        out = m(coords)
+        ref = ref_forward(m, coords)
+        print(f"gen {act} m={msz} H={H} L={Lh} C={C} rows={rows}: fwd relerr={relerr(out.detach(), ref.detach()):.3e}",
+              flush=True)
+        q = m.query(shape, clamp_min=None)
+        print(f"   grid-mode vs coords max|diff| = {(q - out.detach()).abs().max().item():.3e} (|out|max {out.abs().max().item():.3e})")
+        tgt = torch.rand(rows, C, device=dev)
+        loss = ((out - tgt) ** 2).mean()
+        loss.backward()
+        g_ours = [p.grad.clone() for p in m._canonical()]
+        for p in m.parameters():
+            p.grad = None
+        loss_r = ((ref - tgt) ** 2).mean()
+        loss_r.backward()
+        for i, (go, p) in enumerate(zip(g_ours, m._canonical())):
+            print(f"     param {i} {tuple(p.shape)}: grad relerr={relerr(go, p.grad):.3e} |g|={p.grad.norm().item():.3e}",
+                  flush=True)
+    # explicit features (the reference scripts' own call pattern): Siren(in_features=256, hidden 512, 3, 1)
+    torch.manual_seed(2)
+    m = b200inr.Siren(256, 512, 3, 1).to(dev)
+    x = b200inr.get_mgrid((12, 10, 8)).to(dev)
+    Bm = torch.from_numpy(rs.normal(size=(128, 3)) * 0.5).float().to(dev)
+    feats = b200inr.input_mapping(x, Bm)
+    out = m(feats)
+    h = feats
+    for layer in list(m.net)[:-1]:
+        h = torch.sin(layer.omega_0 * layer.linear(h))
+    ref = m.net[-1](h)
+    print(f"features Siren(256,512,3,1): fwd relerr={relerr(out.detach(), ref.detach()):.3e}")
+    tgt = torch.rand_like(ref)
+    ((out - tgt) ** 2).mean().backward()
+    g_ours = [p.grad.clone() for p in m._canonical()]
+    for p in m.parameters():
+        p.grad = None
+    ((ref - tgt) ** 2).mean().backward()
+    for i, (go, p) in enumerate(zip(g_ours, m._canonical())):
+        print(f"     param {i} {tuple(p.shape)}: grad relerr={relerr(go, p.grad):.3e}", flush=True)
+    # timing of BASELINE config 4 at full size
+    torch.manual_seed(3)
+    B = rs.normal(size=(256, 3)) * 0.5
+    m = b200inr.FourierMLP(3, 256, 512, 3, 31, B).to(dev)
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    tgt = torch.rand(rows, 31, device=dev)
+    sess = b200inr.inr.FitSession(m, tgt, shape, lr=1e-4)
+    for _ in range(2):
+        sess.step()
+    torch.cuda.synchronize()
+    marks = []
+    sess.step(marks)
+    torch.cuda.synchronize()
+    names = b200inr.inr.FitSession.STAGES
+    st = {nm: marks[i].elapsed_time(marks[i + 1]) for i, nm in enumerate(names)}
+    tot = sum(st.values())
+    print("cfg4 step stages ms:", {k: round(v, 3) for k, v in st.items()}, "total", round(tot, 3),
+          f"-> {rows / tot / 1e3:.1f} M coord/s, {rows * 5863936 / tot / 1e9:.1f} TFLOP/s algorithmic")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.query(shape)
+    e0.record()
+    for _ in range(3):
+        m.query(shape)
+    e1.record()
+    torch.cuda.synchronize()
+    qms = e0.elapsed_time(e1) / 3
+    print(f"cfg4 query {qms:.3f} ms -> {rows / qms / 1e3:.1f} M vox/s, {rows * 2130432 / qms / 1e9:.1f} TFLOP/s")
+
+
+if "gen" in sys.argv[1:]:
+    gen_checks()
