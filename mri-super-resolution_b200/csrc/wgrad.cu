@@ -35,7 +35,7 @@ constexpr int kWgStagesPerTile = kTileRows / kWgStageRows;
 constexpr int kWgMaxItems = 24;
 
 enum WgOut : int {
-  kWgOutBlock = 0,  // gw[(row_off + m) * ldw + col_off + n] += D[m][n], N = 256           (activated layers)
+  kWgOutBlock = 0,  // gw[(row_off + m) * ldw + col_off + n] += D[m][n], N = 64 * nb       (activated layers)
   kWgOutFinal = 1,  // gw[n * ldw + row_off + m] += D[m][n] for n < C, N = 64               (final linear, transposed)
   kWgOutCoord = 2   // gw[m * d + j] += D[m][j] + D[m][4 + j], N = 64                       (SIREN first layer)
 };
@@ -46,6 +46,7 @@ struct WgItem {
   const uint8_t* a_src;    // M operand tiles: a_tile_bytes per tile, 4 blocks used starting at block a_blk0
   const uint8_t* b_src;    // N operand tiles: b_tile_bytes per tile, nb blocks used starting at block b_blk0
   uint32_t a_tile_bytes, a_blk0, b_tile_bytes, b_blk0;
+  int nb;                  // B blocks per stage (1..4); the MMA N is 64 * nb
   float* gw;
   int ldw, row_off, col_off;
   float* gb;               // bias gradient of the summed features, or nullptr
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
   const int tile_begin = int((long long)p.num_tiles * split / item.cta_count);
   const int tile_end = int((long long)p.num_tiles * (split + 1) / item.cta_count);
   const int num_stages = (tile_end - tile_begin) * kWgStagesPerTile;
-  const int nb = item.out == kWgOutBlock ? 4 : 1;             // B blocks per stage
-  const int ncols = item.out == kWgOutBlock ? 256 : kDzoPad;  // N of the MMA == TMEM columns per M half
+  const int nb = item.nb;          // B blocks per stage
+  const int ncols = 64 * item.nb;  // N of the MMA == TMEM columns per M half
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
@@ -247,7 +248,7 @@ static int launch_items(WgParams& p, const double* weight, int num_sms, cudaStre
   }
   // hand the CTAs lost to rounding to the heaviest items, one each
   for (int i = 0; cta < num_sms && i < p.num_items; ++i) {
-    if (weight[i] >= 128.0) {
+    if (weight[i] >= 100.0) {
       for (int j = i + 1; j < p.num_items; ++j) p.items[j].cta_begin += 1;
       p.items[i].cta_count += 1;
       cta += 1;
@@ -282,6 +283,7 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutBlock;
+    w.nb = 4;
     w.a_src = st + sl.dz + size_t(l) * sl.layer_stride;
     w.a_tile_bytes = tile_h;
     w.b_src = st + sl.y + size_t(l - 1) * sl.layer_stride;
@@ -297,6 +299,7 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutFinal;
+    w.nb = 1;
     w.a_src = st + sl.y + size_t(L) * sl.layer_stride;
     w.a_tile_bytes = tile_h;
     w.b_src = st + sl.dzo;
@@ -313,6 +316,7 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutCoord;
+    w.nb = 1;
     w.a_src = st + sl.dz;
     w.a_tile_bytes = tile_h;
     w.b_src = st + sl.xa;
@@ -345,25 +349,26 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
   for (int l = 0; l <= g.L; ++l) {
     const int K = (l == 0) ? g.K0 : g.H;
     for (int mh = 0; mh < g.H / 256; ++mh) {
-      for (int nh = 0; nh < K / 256; ++nh) {
+      for (int b0 = 0; b0 < K / 64; b0 += 4) {
         if (ni >= kWgMaxItems - 2) return B200INR_ERR_BAD_SHAPE;
         WgItem& w = p.items[ni];
         w = WgItem{};
         w.out = kWgOutBlock;
+        w.nb = (K / 64 - b0) < 4 ? (K / 64 - b0) : 4;
         w.a_src = st + sl.dz + size_t(l) * sl.layer_stride;
         w.a_tile_bytes = uint32_t(sl.tile_h);
         w.a_blk0 = 4 * mh;
         w.b_src = (l == 0) ? st + sl.ain : st + sl.y + size_t(l - 1) * sl.layer_stride;
         w.b_tile_bytes = (l == 0) ? uint32_t(sl.tile_in) : uint32_t(sl.tile_h);
-        w.b_blk0 = 4 * nh;
+        w.b_blk0 = b0;
         w.gw = grad_params + off[2 * l];
         w.ldw = K;
         w.row_off = 256 * mh;
-        w.col_off = 256 * nh;
-        w.gb = (nh == 0) ? grad_params + off[2 * l + 1] + 256 * mh : nullptr;
+        w.col_off = 64 * b0;
+        w.gb = (b0 == 0) ? grad_params + off[2 * l + 1] + 256 * mh : nullptr;
         w.gb_count = 256;
         w.scale = (l == 0) ? g.omega0 : g.omegah;
-        weight[ni++] = 128.0;
+        weight[ni++] = 64.0 + 16.0 * w.nb;
       }
     }
   }
@@ -371,6 +376,7 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutFinal;
+    w.nb = 1;
     w.a_src = st + sl.y + size_t(g.L) * sl.layer_stride;
     w.a_tile_bytes = uint32_t(sl.tile_h);
     w.a_blk0 = 4 * mh;

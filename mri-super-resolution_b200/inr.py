@@ -457,8 +457,26 @@ class FitSession:
             if target.numel() != rows * C // 4:
                 raise RuntimeError("b200inr: pooled fit target must have rows*C/4 elements")
             self.count = float(global_count if global_count is not None else rows * C // 4)
+        elif degrade == "blur_pool":
+            # Gaussian sigma = 0.5 (mirror boundary) then 2x2x1 average: skimage rescale(0.5, anti_aliasing=True)
+            # (dwi_inr.ipynb#c6:L8).  The blur crosses slab borders: whole volume only.
+            if len(shape) != 3 or row_range is not None:
+                raise RuntimeError("b200inr: degrade='blur_pool' needs the whole 3-D grid (X, Y, Z) on one GPU")
+            if shape[0] % 2 or shape[1] % 2:
+                raise RuntimeError("b200inr: blurred pooling needs even X and Y")
+            self.X, self.Y, self.ZC = shape[0], shape[1], shape[2] * C
+            if target.numel() != rows * C // 4:
+                raise RuntimeError("b200inr: pooled fit target must have rows*C/4 elements")
+            self.count = float(rows * C // 4)
+            self.taps = []
+            for n_hr in (shape[0], shape[1]):
+                fwd, adj = _lib.build_axis_taps(n_hr, True)
+                self.taps.append((torch.frombuffer(bytearray(bytes(fwd)), dtype=torch.uint8).to(dev),
+                                  torch.frombuffer(bytearray(bytes(adj)), dtype=torch.uint8).to(dev)))
+            self.lr_pred = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
+            self.lr_grad = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
         else:
-            raise ValueError("degrade must be None or 'pool'")
+            raise ValueError("degrade must be None, 'pool' or 'blur_pool'")
         self.target = target
         if module._optim is None or reset_optimizer or module._optim["m"].device != dev:
             module._optim = {"m": torch.zeros_like(eng["flat"]), "v": torch.zeros_like(eng["flat"]),
@@ -500,9 +518,17 @@ class FitSession:
             if self.degrade is None:
                 _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), None, rows * C, self.count,
                                                 _ptr(self.dpred), _ptr(self.loss), s), "mse_loss")
-            else:
+            elif self.degrade == "pool":
                 _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
                                                 self.count, _ptr(self.dpred), _ptr(self.loss), s), "pool_mse")
+            else:  # D pred -> MSE against the LR target -> D^T
+                (fx, ax), (fy, ay) = self.taps
+                _lib.check(lib.b200inr_degrade_forward(_ptr(self.pred), _ptr(self.lr_pred), self.X, self.Y, self.ZC,
+                                                       _ptr(fx), _ptr(fy), s), "degrade_forward")
+                _lib.check(lib.b200inr_mse_loss(_ptr(self.lr_pred), _ptr(self.target), None, self.lr_pred.numel(),
+                                                self.count, _ptr(self.lr_grad), _ptr(self.loss), s), "mse_loss")
+                _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
+                                                       _ptr(ax), _ptr(ay), s), "degrade_adjoint")
             mark()
             _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows, _ptr(self.dpred), s),
                        "siren_dgrad")

@@ -288,12 +288,32 @@ def torch_siren(in_features, hidden_features, hidden_layers, out_features, first
     return _Net()
 
 
+def torch_relu_mlp(in_dim, hidden_features, hidden_layers, out_features):
+    """BASELINE config 4's network: Linear(in, H) + ReLU, `hidden_layers` x (Linear(H, H) + ReLU), Linear(H, C) with
+    torch's default initialisation, fed with input_mapping(coords, B) (the reference only ever
+    feeds Fourier features into a SIREN, so the ReLU variant is a plain nn.Sequential)."""
+    from torch import nn
+    mods = [nn.Linear(in_dim, hidden_features), nn.ReLU()]
+    for _ in range(hidden_layers):
+        mods += [nn.Linear(hidden_features, hidden_features), nn.ReLU()]
+    mods.append(nn.Linear(hidden_features, out_features))
+    return nn.Sequential(*mods)
+
+
+def torch_input_mapping(x, B):
+    """INR/SRDWI.py:111-116 with torch ops (same expression as the reference)."""
+    import torch
+    proj = torch.matmul(2. * np.pi * x, B.T)
+    return torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
+
+
 def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None):
     """The reference's in-lined loop (INR/superresDWI.py:132-138): full batch, fixed order, Adam defaults.
 
-    degrade None   : loss = ((out - target)**2).mean()
-    degrade 'pool' : out reshaped to hr_shape + (C,), 2x2x1 average pooled in-plane, then the same MSE against the LR
-                     target.
+    degrade None        : loss = ((out - target)**2).mean()
+    degrade 'pool'      : out reshaped to hr_shape + (C,), 2x2x1 average pooled in-plane, then the same MSE against the
+                          LR target.
+    degrade 'blur_pool' : Gaussian sigma 0.5 (mirror) pre-blur, then the pooling (degrade_axis_matrix).
     Returns the list of per-step losses (python floats).
     """
     import torch
@@ -307,6 +327,12 @@ def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None):
             vol = out.reshape(X, Y, Z, -1).permute(3, 0, 1, 2).unsqueeze(0)
             pooled = Fn.avg_pool3d(vol, kernel_size=(2, 2, 1), stride=(2, 2, 1))
             out = pooled.squeeze(0).permute(1, 2, 3, 0).reshape(-1, vol.shape[1])
+        elif degrade == "blur_pool":
+            X, Y, Z = hr_shape
+            Dx = torch.from_numpy(degrade_axis_matrix(X, True)).float()
+            Dy = torch.from_numpy(degrade_axis_matrix(Y, True)).float()
+            vol = out.reshape(X, Y, Z, -1)
+            out = torch.einsum("ax,by,xyzc->abzc", Dx, Dy, vol).reshape(-1, vol.shape[-1])
         loss = ((out - target) ** 2).mean()
         opt.zero_grad()
         loss.backward()

@@ -359,3 +359,98 @@ def test_full_size_query_properties(dev):
     parts = torch.cat([m.query(shape, clamp_min=None, row_range=(0, half)),
                        m.query(shape, clamp_min=None, row_range=(half, raw.shape[0]))])
     assert torch.equal(parts, raw)
+
+
+# ------------------------------------------------------------------------------------------------ generic family
+def test_reference_style_fourier_siren_vs_golden(dev, golden_dir):
+    """The reference scripts' call pattern (INR/superresDWI.py:105-138): Siren(in_features=2m, hidden 512, 3, 1) on
+    pre-computed input_mapping features, unmodified loop with torch.optim.Adam -- against the reference's own
+    outputs, gradients and 5-step loss trajectory."""
+    g = np.load(os.path.join(golden_dir, "ff_siren.npz"))
+    torch.manual_seed(16)
+    m = b200inr.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3).to(dev)
+    x = b200inr.get_mgrid(tuple(int(s) for s in g["grid_shape"])).to(dev)
+    B = torch.from_numpy(g["B"]).to(dev)
+    feats = b200inr.input_mapping(x, B)
+    gt = torch.from_numpy(g["gt"]).to(dev)
+    out = m.forward(feats)
+    assert _relerr(out.detach().cpu().numpy(), g["out"]) < BF16_RELERR
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    for k in [f for f in g.files if f.startswith("g/")]:
+        p = dict(m.named_parameters())[k[2:]]
+        assert _relerr(p.grad.cpu().numpy(), g[k]) < BF16_RELERR, k
+    for k in [f for f in g.files if f.startswith("gcs/")]:
+        p = dict(m.named_parameters())[k[4:]]
+        assert abs(float((p.grad.double() ** 2).sum()) - g[k][1]) <= 5e-2 * g[k][1], k  # squared norm of the gradient
+    opt = torch.optim.Adam(lr=1e-4, params=list(m.parameters()))
+    losses = []
+    for _ in range(5):
+        o = m.forward(feats)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    np.testing.assert_allclose(losses, g["losses"], rtol=5e-2)
+    # the fused-feature module computes the same network from raw coordinates
+    fm = b200inr.FourierMLP(3, 128, 512, 3, 1, g["B"], activation="sine").to(dev)
+    fm.load_state_dict({**m.state_dict(), "B": B})
+    with torch.no_grad():
+        a = fm(x).cpu().numpy()
+        b = m(feats).cpu().numpy()
+    assert _relerr(a, b) < 1e-2
+
+
+@pytest.mark.parametrize("act,msz,H,Lh,C", [("relu", 256, 512, 3, 31), ("relu", 128, 256, 2, 5),
+                                            ("sine", 128, 256, 2, 1), ("sine", 64, 512, 1, 3)])
+def test_fourier_mlp_forward_backward_vs_oracle(dev, act, msz, H, Lh, C):
+    """FourierMLP (features fused into layer 1) against the CPU oracle: nn.Sequential ReLU MLP / Siren on
+    input_mapping(coords, B), forward and every parameter gradient."""
+    shape = (20, 16, 12)
+    rs = np.random.RandomState(5)
+    B = (rs.normal(size=(msz, 3)) * 0.5).astype(np.float32)
+    torch.manual_seed(9)
+    m = b200inr.FourierMLP(3, msz, H, Lh, C, B, activation=act)
+    torch.manual_seed(9)
+    ref = O.torch_relu_mlp(2 * msz, H, Lh, C) if act == "relu" else O.torch_siren(2 * msz, H, Lh, C)
+    strip = (lambda k: k[4:]) if act == "relu" else (lambda k: k)  # the oracle's ReLU net is a bare nn.Sequential
+    for (k1, p1), (k2, p2) in zip(sorted(m.named_parameters()), sorted(ref.named_parameters())):
+        assert strip(k1) == k2 and torch.equal(p1, p2)  # same construction order and init
+    x = torch.from_numpy(O.get_mgrid(shape))
+    tgt = torch.rand(x.shape[0], C, generator=torch.Generator().manual_seed(1))
+    out_ref = ref(O.torch_input_mapping(x, torch.from_numpy(B)))
+    ((out_ref - tgt) ** 2).mean().backward()
+    m = m.to(dev)
+    out = m(x.to(dev))
+    assert _relerr(out.detach().cpu().numpy(), out_ref.detach().numpy()) < BF16_RELERR
+    ((out - tgt.to(dev)) ** 2).mean().backward()
+    gref = dict(ref.named_parameters())
+    for k, p in m.named_parameters():
+        assert _relerr(p.grad.cpu().numpy(), gref[strip(k)].grad.numpy()) < 2.5e-2, k
+    q = m.query(shape, clamp_min=None).cpu().numpy()
+    assert np.abs(q - out.detach().cpu().numpy()).max() <= 1e-2 * np.abs(q).max() + 1e-6
+
+
+def test_cfg4_blur_pool_fit_vs_oracle(dev):
+    """BASELINE config 4 at reduced size: Fourier-feature ReLU MLP (256 frequencies, 4 x 512) fitted through the
+    Gaussian(0.5)+2x2x1 degradation operator; loss trajectory and final PSNR against the CPU oracle."""
+    shape, C, steps, lr = (16, 16, 8), 31, 30, 1e-4
+    hr = b200inr.phantom.dwi_phantom(shape, n_dirs=C - 1, noise=0.0)
+    lr_t = O.degrade_forward(hr, blur=True)
+    B = (np.random.RandomState(0).normal(size=(256, 3)) * 0.5).astype(np.float32)
+    torch.manual_seed(4)
+    m = b200inr.FourierMLP(3, 256, 512, 3, C, B)
+    torch.manual_seed(4)
+    ref = O.torch_relu_mlp(512, 512, 3, C)
+    feats = O.torch_input_mapping(torch.from_numpy(O.get_mgrid(shape)), torch.from_numpy(B))
+    ref_losses = O.torch_fit(ref, feats, torch.from_numpy(lr_t.reshape(-1, C)), steps, lr, degrade="blur_pool",
+                             hr_shape=shape)
+    with torch.no_grad():
+        ref_out = ref(feats).numpy().reshape(*shape, C)
+    m = m.to(dev)
+    losses = m.fit(torch.from_numpy(lr_t).to(dev), shape, steps=steps, lr=lr, degrade="blur_pool").cpu().numpy()
+    out = m.query(shape, clamp_min=None).cpu().numpy().reshape(*shape, C)
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+    assert abs(O.psnr(out, hr) - O.psnr(ref_out, hr)) <= 0.1
+    assert torch.equal(m.B.cpu(), torch.from_numpy(B))  # the frequency matrix stays frozen under Adam

@@ -169,3 +169,21 @@ def test_metrics():
     s = O.ssim2d(a, b)
     assert 0.0 < s < 1.0
     assert O.psnr(a, a + 0.1) == pytest.approx(20.0, abs=1e-6)
+
+
+def test_fourier_siren_reference_combination(golden_dir):
+    """Fourier features -> Siren(in_features=2m, hidden 512, 3, 1) (INR/superresDWI.py:102-113): the oracle's torch
+    restatement reproduces the reference's initial weights, forward, gradients and 5-step trajectory."""
+    g = _load(golden_dir, "ff_siren.npz")
+    torch.manual_seed(16)
+    m = O.torch_siren(256, 512, 3, 1)
+    sd = m.state_dict()
+    for k in [f for f in g.files if f.startswith("cs0/")]:
+        np.testing.assert_allclose(_cs(sd[k[4:]]), g[k], rtol=1e-12, atol=0)
+    x = torch.from_numpy(O.get_mgrid(tuple(g["grid_shape"])))
+    feats = O.torch_input_mapping(x, torch.from_numpy(g["B"]))
+    np.testing.assert_allclose(feats.numpy(), O.input_mapping(x.numpy(), g["B"]), atol=3e-6)
+    out = m(feats)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=2e-6, rtol=1e-4)
+    losses = O.torch_fit(m, feats, torch.from_numpy(g["gt"]), 5, 1e-4)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-3)

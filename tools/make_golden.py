@@ -103,6 +103,41 @@ def main():
     siren_case("siren_cfg1", (2, 256, 2, 1), 11, (24, 20), 3e-4, 5, store_weights=True)
     siren_case("siren_cfg2", (3, 256, 4, 31), 12, (10, 9, 8), 1e-4, 5, store_weights=False)
 
+    # ---- the reference scripts' own combination: Fourier features -> Siren(in_features=2m, hidden 512, 3, 1)
+    #      (INR/superresDWI.py:102-113,121-122), 5 steps of the in-lined loop
+    torch.manual_seed(16)
+    rng = np.random.RandomState(17)
+    Bff = torch.from_numpy(rng.normal(size=(128, 3)) * 0.5).float()
+    m = SRDWI.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    xc = SRDWI.get_mgrid((10, 9, 8))
+    feats = SRDWI.input_mapping(xc, Bff)
+    gtf = torch.rand(xc.shape[0], 1, generator=torch.Generator().manual_seed(18))
+    out0 = m.forward(feats)
+    loss0 = ((out0 - gtf) ** 2).mean()
+    loss0.backward()
+    d = {"B": Bff.numpy(), "gt": gtf.numpy(), "out": out0.detach().numpy(), "loss": loss0.item(),
+         "grid_shape": np.array((10, 9, 8))}
+    for k, v in sd0.items():
+        d["cs0/" + k] = checksum(v)
+    for k, pp in m.named_parameters():
+        d["gcs/" + k] = checksum(pp.grad)
+        if pp.grad.numel() <= 1024:
+            d["g/" + k] = pp.grad.numpy().copy()
+    opt = torch.optim.Adam(lr=1e-4, params=list(m.parameters()))
+    losses = []
+    for _ in range(5):
+        o = m.forward(feats)
+        ls = ((o - gtf) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    d["losses"] = np.array(losses)
+    d["out_after"] = m.forward(feats).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "ff_siren.npz"), **d)
+    print("ff_siren losses", losses)
+
     # ---- INRmodel.Siren construction order
     torch.manual_seed(13)
     m = INRmodel.Siren(3, 256, 2, 4)
