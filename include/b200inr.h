@@ -32,6 +32,9 @@ extern "C" {
 
 #define B200INR_ACT_SINE 0 /* sin(omega * z)   (SineLayer, INR/SRDWI.py:59)                                  */
 #define B200INR_ACT_RELU 1 /* max(z, 0)         (Fourier-feature ReLU MLP of BASELINE config 4; omegas ignored) */
+#define B200INR_ACT_GABOR 2 /* complex Gabor wavelet exp(i w0 lin) exp(-s0^2 (|lin|^2 + |orth|^2))
+                               (ComplexGaborLayer2D, INR/INRmodel.py:109-120; WIRE network INR/wiretest.ipynb cell 2):
+                               hidden_features = H complex units (128), IN_COORDS only */
 
 #define B200INR_IN_COORDS 0   /* network input = the d <= 4 raw coordinates; first layer on CUDA cores (H = 256)   */
 #define B200INR_IN_FOURIER 1  /* network input = input_mapping(coords, B) (INR/SRDWI.py:111-116) computed in-kernel
@@ -50,7 +53,7 @@ typedef struct b200inr_net {
   int32_t activation;      /* B200INR_ACT_*                                                                  */
   int32_t input_mode;      /* B200INR_IN_*                                                                   */
   int32_t mapping_size;    /* m of input_mapping (IN_FOURIER only; 2m a multiple of 64, <= H), else 0         */
-  int32_t reserved;
+  float scale_0;           /* s0 of the Gabor window (ACT_GABOR only), else 0                                */
 } b200inr_net;
 
 /* Dense coordinate grid == get_mgrid(shape) (INR/SRDWI.py:12-18) restricted to linear rows

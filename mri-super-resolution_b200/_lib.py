@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200inr.so")
 
 MAX_TAPS = 8
-ACT_SINE, ACT_RELU = 0, 1
+ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2
 IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
 
 
@@ -29,7 +29,7 @@ class Net(ctypes.Structure):
         ("activation", ctypes.c_int32),
         ("input_mode", ctypes.c_int32),
         ("mapping_size", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("scale_0", ctypes.c_float),
     ]
 
 
@@ -98,9 +98,9 @@ def check(code, what):
 
 
 def make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.0, hidden_omega_0=30.0,
-             activation=ACT_SINE, input_mode=IN_COORDS, mapping_size=0):
+             activation=ACT_SINE, input_mode=IN_COORDS, mapping_size=0, scale_0=0.0):
     return Net(int(in_features), int(hidden_features), int(hidden_layers), int(out_features), float(first_omega_0),
-               float(hidden_omega_0), int(activation), int(input_mode), int(mapping_size), 0)
+               float(hidden_omega_0), int(activation), int(input_mode), int(mapping_size), float(scale_0))
 
 
 def make_grid(shape, row_begin=0):
@@ -119,7 +119,10 @@ def param_count(net):
 
 
 def param_offsets(net):
-    n = 2 * (net.hidden_layers + 2) + (1 if net.input_mode == IN_FOURIER else 0)
+    if net.activation == ACT_GABOR:
+        n = 4 * (net.hidden_layers + 1) + 2
+    else:
+        n = 2 * (net.hidden_layers + 2) + (1 if net.input_mode == IN_FOURIER else 0)
     off = (_i64 * n)()
     check(load().b200inr_param_offsets(ctypes.byref(net), off), "param_offsets")
     return list(off)

@@ -23,6 +23,10 @@ int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int6
                    int num_sms, cudaStream_t stream);
 int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, int num_sms,
                      cudaStream_t stream);
+int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream);
+int launch_wire_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                    int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                    cudaStream_t stream);
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
                float* loss_accum, cudaStream_t stream);
 int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
@@ -35,13 +39,19 @@ int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t st
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
 
 static bool is_gen(const b200inr_net* net) { return net->input_mode != B200INR_IN_COORDS; }
+static bool is_wire(const b200inr_net* net) { return net->activation == B200INR_ACT_GABOR; }
 
 static int check_net(const b200inr_net* net) {
   if (!net) return B200INR_ERR_NULL;
   if (net->hidden_layers < 0 || net->hidden_layers + 1 > kMaxSineLayers) return B200INR_ERR_BAD_SHAPE;
   if (net->out_features < 1 || net->out_features > kOutPad) return B200INR_ERR_BAD_SHAPE;
-  if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
   const int H = net->hidden_features;
+  if (net->activation == B200INR_ACT_GABOR) {  // WIRE: 128 complex units on raw coordinates
+    if (net->input_mode != B200INR_IN_COORDS || H != 128 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
+    if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
+    return B200INR_OK;
+  }
+  if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
   switch (net->input_mode) {
     case B200INR_IN_COORDS:  // SIREN on raw coordinates: first layer on CUDA cores, H = 256
       if (H != 256 || net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
@@ -120,7 +130,9 @@ int b200inr_param_count(const b200inr_net* net, int64_t* n_floats) {
   int e = check_net(net);
   if (e) return e;
   if (!n_floats) return B200INR_ERR_NULL;
-  if (is_gen(net))
+  if (is_wire(net))
+    *n_floats = wire_param_offsets(make_wire_dims(net), nullptr);
+  else if (is_gen(net))
     *n_floats = gen_param_offsets(make_gen_dims(net), nullptr);
   else
     *n_floats = param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, nullptr);
@@ -131,7 +143,9 @@ int b200inr_param_offsets(const b200inr_net* net, int64_t* offsets) {
   int e = check_net(net);
   if (e) return e;
   if (!offsets) return B200INR_ERR_NULL;
-  if (is_gen(net))
+  if (is_wire(net))
+    wire_param_offsets(make_wire_dims(net), offsets);
+  else if (is_gen(net))
     gen_param_offsets(make_gen_dims(net), offsets);
   else
     param_offsets(net->in_features, net->hidden_features, net->hidden_layers, net->out_features, offsets);
@@ -142,8 +156,9 @@ int b200inr_packed_bytes(const b200inr_net* net, size_t* bytes) {
   int e = check_net(net);
   if (e) return e;
   if (!bytes) return B200INR_ERR_NULL;
-  *bytes = is_gen(net) ? make_gen_pack_layout(make_gen_dims(net)).total
-                       : make_pack_layout(net->hidden_features, net->hidden_layers).total;
+  *bytes = is_wire(net) ? make_wire_pack_layout(make_wire_dims(net)).total
+           : is_gen(net) ? make_gen_pack_layout(make_gen_dims(net)).total
+                         : make_pack_layout(net->hidden_features, net->hidden_layers).total;
   return B200INR_OK;
 }
 
@@ -152,6 +167,7 @@ int b200inr_pack_weights(const b200inr_net* net, const float* params, void* pack
   if (e) return e;
   if (!params || !packed) return B200INR_ERR_NULL;
   if (!aligned16(params) || (reinterpret_cast<uintptr_t>(packed) & 1023)) return B200INR_ERR_BAD_ALIGN;
+  if (is_wire(net)) return launch_wire_pack(net, params, packed, static_cast<cudaStream_t>(stream));
   return launch_pack(net, params, packed, static_cast<cudaStream_t>(stream));
 }
 
@@ -160,8 +176,9 @@ int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes) {
   if (e) return e;
   if (!bytes) return B200INR_ERR_NULL;
   if (rows < 0) return B200INR_ERR_BAD_SHAPE;
-  *bytes = is_gen(net) ? make_gen_stash_layout(make_gen_dims(net), rows).total
-                       : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
+  *bytes = is_wire(net) ? make_wire_stash_layout(make_wire_dims(net), rows).total
+           : is_gen(net) ? make_gen_stash_layout(make_gen_dims(net), rows).total
+                         : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
   return B200INR_OK;
 }
 
@@ -178,6 +195,9 @@ int b200inr_siren_forward(const b200inr_net* net, const void* packed, const floa
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_wire(net))
+    return launch_wire_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
+                           static_cast<cudaStream_t>(stream));
   if (is_gen(net))
     return launch_gen_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
                           static_cast<cudaStream_t>(stream));
@@ -201,6 +221,7 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;  // WIRE backward: not implemented yet
   if (is_gen(net)) {
     if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
@@ -220,6 +241,7 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;
   if (is_gen(net)) return launch_gen_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
 }
@@ -236,6 +258,7 @@ int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords
   if ((reinterpret_cast<uintptr_t>(stash) & 1023) || !aligned16(grad_params)) return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
+  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;
   if (is_gen(net)) return launch_gen_wgrad(net, stash, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
 }

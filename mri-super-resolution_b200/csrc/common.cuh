@@ -227,6 +227,113 @@ __host__ __device__ inline GenStashLayout make_gen_stash_layout(const GenDims& g
   return s;
 }
 
+// ------------------------------------------------------------------ WIRE family (wire.cu)
+// Complex Gabor network of INR/wiretest.ipynb cell 2 as a real-block GEMM chain: H complex units,
+// activations [h_r | h_i] (K = 2H reals), hidden layers produce the four reals (a, b, c, d) = (Re lin, Im lin, Re orth,
+// Im orth) of every unit, interleaved as column n = 4u + component (N = 4H).
+struct WireDims {
+  int d, H, L, C;
+  float omega0, omegah, s0;
+};
+
+__host__ inline WireDims make_wire_dims(const b200inr_net* n) {
+  WireDims w{};
+  w.d = n->in_features;
+  w.H = n->hidden_features;
+  w.L = n->hidden_layers;
+  w.C = n->out_features;
+  w.omega0 = n->first_omega_0;
+  w.omegah = n->hidden_omega_0;
+  w.s0 = n->scale_0;
+  return w;
+}
+
+// Flat fp32 parameters: layer l: W_lin b_lin W_orth b_orth at off[4l .. 4l+3] (l = 0 real, l >= 1 complex as (re, im)
+// pairs), final W_f b_f (complex) at off[4(L+1)], off[4(L+1)+1].
+__host__ __device__ inline int64_t wire_param_offsets(const WireDims& w, int64_t* off) {
+  int64_t o = 0;
+  auto seg = [&](int64_t n) {
+    int64_t at = o;
+    o += (n + 3) & ~int64_t(3);
+    return at;
+  };
+  for (int l = 0; l <= w.L; ++l) {
+    const int64_t nw = (l == 0) ? int64_t(w.H) * w.d : int64_t(w.H) * w.H * 2;
+    const int64_t nbias = (l == 0) ? w.H : 2 * w.H;
+    for (int j = 0; j < 2; ++j) {
+      const int64_t a = seg(nw), b = seg(nbias);
+      if (off) { off[4 * l + 2 * j] = a; off[4 * l + 2 * j + 1] = b; }
+    }
+  }
+  const int64_t a = seg(int64_t(w.C) * w.H * 2), b = seg(2 * w.C);
+  if (off) { off[4 * (w.L + 1)] = a; off[4 * (w.L + 1) + 1] = b; }
+  return o;
+}
+
+struct WirePackLayout {
+  size_t w0;     // float4 [2H]: unit u -> lin weights at 2u, orth weights at 2u+1 (zero padded to 4 coordinates)
+  size_t b0;     // float2 [H]: (b_lin, b_orth) of the first layer
+  size_t bias;   // float [L*4H + 32]: hidden-layer biases in column order n = 4u + component, then Re(b_f) padded
+  size_t w;      // L x 8 chunks [256 rows (n)][64 (k)]   forward operand, order (n-half, k-block)
+  size_t wt;     // L x 8 chunks [256 rows (k)][64 (n)]   dgrad operand, order k-block over n
+  size_t wf;     // [4][32][64]     final linear: rows c, k < H: Re W_f, k >= H: -Im W_f
+  size_t wft;    // [256 rows (k)][64 (c)]
+  size_t total;
+};
+
+__host__ __device__ inline WirePackLayout make_wire_pack_layout(const WireDims& w) {
+  WirePackLayout p;
+  size_t o = 0;
+  p.w0 = o;
+  o += size_t(2 * w.H) * 16;
+  p.b0 = o;
+  o += size_t(w.H) * 8;
+  p.bias = o;
+  o += (size_t(w.L) * 4 * w.H + 32) * 4;
+  o = (o + 1023) & ~size_t(1023);
+  p.w = o;
+  o += size_t(w.L) * 8 * kGenChunkBytes;
+  p.wt = o;
+  o += size_t(w.L) * 8 * kGenChunkBytes;
+  p.wf = o;
+  o += size_t(4) * kOutPad * 128;
+  p.wft = o;
+  o += kGenChunkBytes;
+  p.total = o;
+  return p;
+}
+
+// Stash of the WIRE training forward: per Gabor layer the activations [h_r | h_i] (bf16 tile, 2H wide) and the
+// pre-activations (a, b, c, d) (bf16 tile, 4H wide; layer 0 stores (a, 0, c, 0)); dz = dL/d(a,b,c,d) written by dgrad.
+struct WireStashLayout {
+  size_t y, z, dz, dzo, xa;
+  size_t tile_y, tile_z, stride_y, stride_z;
+  size_t total;
+  int64_t tiles;
+};
+
+__host__ __device__ inline WireStashLayout make_wire_stash_layout(const WireDims& w, int64_t rows) {
+  WireStashLayout s;
+  s.tiles = (rows + kTileRows - 1) / kTileRows;
+  s.tile_y = size_t(kTileRows) * 2 * w.H * 2;
+  s.tile_z = size_t(kTileRows) * 4 * w.H * 2;
+  s.stride_y = size_t(s.tiles) * s.tile_y;
+  s.stride_z = size_t(s.tiles) * s.tile_z;
+  size_t o = 0;
+  s.y = o;
+  o += size_t(w.L + 1) * s.stride_y;
+  s.z = o;
+  o += size_t(w.L + 1) * s.stride_z;
+  s.dz = o;
+  o += size_t(w.L + 1) * s.stride_z;
+  s.dzo = o;
+  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.xa = o;
+  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.total = o;
+  return s;
+}
+
 struct GridDesc {
   int ndim;
   int shape[4];

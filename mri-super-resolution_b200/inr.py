@@ -154,7 +154,12 @@ class _SirenFunction(torch.autograd.Function):
             raise RuntimeError("b200inr: backward called on a forward that did not record activations")
         flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out)
         ctx.stash = None
-        grads = [flat_grad[o:o + p.numel()].view_as(p) for o, p in zip(module._offsets_canonical(), module._canonical())]
+        grads = []
+        for o, p in zip(module._offsets_canonical(), module._canonical()):
+            if p.is_complex():  # torch's convention for complex parameters: grad = dL/dRe + 1j dL/dIm
+                grads.append(torch.view_as_complex(flat_grad[o:o + 2 * p.numel()].view(*p.shape, 2)))
+            else:
+                grads.append(flat_grad[o:o + p.numel()].view_as(p))
         return (None, None, *grads)
 
 
@@ -203,7 +208,8 @@ class _FusedMLP(nn.Module):
             flat = eng["flat"]
             with torch.no_grad():
                 for o, p in zip(eng["offsets"], ps):
-                    flat[o:o + p.numel()].copy_(p.reshape(-1))
+                    src = torch.view_as_real(p) if p.is_complex() else p  # complex64 -> interleaved (re, im)
+                    flat[o:o + src.numel()].copy_(src.reshape(-1))
             self._pack(eng)
             eng["key"] = key
         return eng
@@ -218,7 +224,10 @@ class _FusedMLP(nn.Module):
         ps = self._canonical()
         with torch.no_grad():
             for o, p in zip(eng["offsets"], ps):
-                p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
+                if p.is_complex():
+                    p.copy_(torch.view_as_complex(eng["flat"][o:o + 2 * p.numel()].view(*p.shape, 2)))
+                else:
+                    p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
         eng["key"] = tuple((p.data_ptr(), p._version) for p in ps + self._frozen())
 
     # ---------------------------------------------------------------- kernel calls
@@ -413,6 +422,57 @@ class FourierMLP(_FusedMLP):
 
     def _frozen(self):
         return [self.B]
+
+
+class ComplexGaborLayer2D(nn.Module):
+    """Reference INR/INRmodel.py:66-120 (== wiretest.ipynb cell 1): parameter container of one complex Gabor layer.
+    omega_0 / scale_0 are frozen nn.Parameters as in the reference (they appear in state_dict and parameters());
+    the nested init_weights of the reference is dead code, so weights keep torch's default (complex) init.
+    The arithmetic runs fused inside Wire."""
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega0=10.0, sigma0=10.0,
+                 trainable=False):
+        super().__init__()
+        self.is_first = is_first
+        self.in_features = in_features
+        dtype = torch.float if is_first else torch.cfloat
+        self.omega_0 = nn.Parameter(omega0 * torch.ones(1), trainable)
+        self.scale_0 = nn.Parameter(sigma0 * torch.ones(1), trainable)
+        self.linear = nn.Linear(in_features, out_features, bias=bias, dtype=dtype)
+        self.scale_orth = nn.Linear(in_features, out_features, bias=bias, dtype=dtype)
+
+    def forward(self, input):
+        raise RuntimeError("b200inr: ComplexGaborLayer2D is executed fused inside Wire.forward / fit / query")
+
+
+class Wire(_FusedMLP):
+    """The WIRE network of the reference (INR/wiretest.ipynb cell 2, there also called `Siren`):
+    Sequential(ComplexGaborLayer2D(first) , hidden_layers x ComplexGaborLayer2D, complex Linear), real part returned.
+    Same constructor arguments, construction order (RNG) and state-dict keys.  hidden_features = complex units (128)."""
+
+    def __init__(self, in_features, hidden_features, hidden_layers, out_features, first_omega_0=10,
+                 hidden_omega_0=30., scale=10.0):
+        super().__init__()
+        self.in_features, self.hidden_features = int(in_features), int(hidden_features)
+        self.hidden_layers, self.out_features = int(hidden_layers), int(out_features)
+        net = [ComplexGaborLayer2D(in_features, hidden_features, omega0=first_omega_0, sigma0=scale, is_first=True,
+                                   trainable=False)]
+        for _ in range(hidden_layers):
+            net.append(ComplexGaborLayer2D(hidden_features, hidden_features, is_first=False, omega0=hidden_omega_0,
+                                           sigma0=scale))
+        self.final_linear = nn.Linear(hidden_features, out_features, dtype=torch.cfloat)
+        net.append(self.final_linear)
+        self.net = nn.Sequential(*net)
+        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0,
+                                        hidden_omega_0, activation=_lib.ACT_GABOR, scale_0=scale), self.in_features)
+
+    def _canonical(self):
+        ps = []
+        for i in range(self.hidden_layers + 1):
+            layer = self.net[i]
+            ps += [layer.linear.weight, layer.linear.bias, layer.scale_orth.weight, layer.scale_orth.bias]
+        ps += [self.final_linear.weight, self.final_linear.bias]
+        return ps
 
 
 class FitSession:

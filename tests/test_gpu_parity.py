@@ -454,3 +454,46 @@ def test_cfg4_blur_pool_fit_vs_oracle(dev):
     np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
     assert abs(O.psnr(out, hr) - O.psnr(ref_out, hr)) <= 0.1
     assert torch.equal(m.B.cpu(), torch.from_numpy(B))  # the frequency matrix stays frozen under Adam
+
+
+# ------------------------------------------------------------------------------------------------ WIRE
+def _wire_layers(m):
+    layers = []
+    for i in range(m.hidden_layers + 1):
+        g = m.net[i]
+        layers.append(tuple(t.detach().cpu().numpy() for t in (g.linear.weight, g.linear.bias, g.scale_orth.weight,
+                                                                g.scale_orth.bias)))
+    return layers, m.final_linear.weight.detach().cpu().numpy(), m.final_linear.bias.detach().cpu().numpy()
+
+
+def test_wire_forward_vs_reference_golden(dev, golden_dir):
+    """WIRE (wiretest.ipynb cells 1-2) at BASELINE config 3's shape, notebook hyper-parameters omega0 = scale = 1.2:
+    same seed -> same weights; fused forward / query against the reference's own output and the NumPy oracle."""
+    g = np.load(os.path.join(golden_dir, "wire_cfg3.npz"))
+    torch.manual_seed(19)
+    m = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2)
+    assert list(m.state_dict().keys()) == list(g["keys"])
+    shape = tuple(int(s) for s in g["grid_shape"])
+    layers, fw, fb = _wire_layers(m)
+    ref = O.wire_forward(layers, fw, fb, O.get_mgrid(shape), 1.2, 1.2)
+    np.testing.assert_allclose(ref, g["out"], atol=2e-6, rtol=1e-4)  # oracle == reference
+    m = m.to(dev)
+    with torch.no_grad():
+        out = m(b200inr.get_mgrid(shape).to(dev)).cpu().numpy()
+    assert _relerr(out, g["out"]) < BF16_RELERR
+    q = m.query(shape, clamp_min=None).cpu().numpy()
+    assert np.abs(q - out).max() <= 1e-2 * np.abs(out).max() + 1e-6
+    np.testing.assert_array_equal(m.query(shape).cpu().numpy(), np.maximum(q, 0.0))
+
+
+def test_wire_full_size_query_sampled(dev):
+    shape = (128, 128, 64)
+    torch.manual_seed(23)
+    m = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2)
+    layers, fw, fb = _wire_layers(m)
+    m = m.to(dev)
+    raw = m.query(shape, clamp_min=None)
+    assert raw.shape == (128 * 128 * 64, 31) and torch.isfinite(raw).all()
+    idx = np.random.RandomState(1).choice(raw.shape[0], 2048, replace=False)
+    ref = O.wire_forward(layers, fw, fb, O.get_mgrid(shape)[idx], 1.2, 1.2)
+    assert _relerr(raw[torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) < BF16_RELERR

@@ -283,3 +283,38 @@ def gen_checks():
 
 if "gen" in sys.argv[1:]:
     gen_checks()
+
+
+def wire_checks():
+    import numpy as np
+    import b200inr
+    sys.path.insert(0, ROOT)
+    from oracle import inr_oracle as O
+    torch.manual_seed(19)
+    m = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2)
+    layers = []
+    for i in range(4):
+        gl = m.net[i]
+        layers.append(tuple(t.detach().numpy() for t in (gl.linear.weight, gl.linear.bias, gl.scale_orth.weight, gl.scale_orth.bias)))
+    fw, fb = m.final_linear.weight.detach().numpy(), m.final_linear.bias.detach().numpy()
+    shape = (16, 12, 10)
+    x = O.get_mgrid(shape)
+    ref = O.wire_forward(layers, fw, fb, x, 1.2, 1.2)
+    m = m.to(dev)
+    out = m.query(shape, clamp_min=None).cpu().numpy()
+    print(f"wire fwd relerr = {np.linalg.norm(out - ref) / np.linalg.norm(ref):.3e}  max|ref| {np.abs(ref).max():.3e}")
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    m.query(shape)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        m.query(shape)
+    e1.record()
+    torch.cuda.synchronize()
+    qms = e0.elapsed_time(e1) / 3
+    print(f"wire query {qms:.3f} ms -> {rows / qms / 1e3:.1f} M vox/s, {rows * 803840 / qms / 1e9:.1f} TFLOP/s")
+
+
+if "wire" in sys.argv[1:]:
+    wire_checks()

@@ -165,6 +165,40 @@ def main():
     np.savez_compressed(os.path.join(OUT, "wire_small.npz"), **d)
     print("wire out", ow.abs().max().item())
 
+    # ---- WIRE at BASELINE config 3's shape: 3 -> 128 complex x (1 + 3) -> 31, omega0 = scale = 1.2, 5 Adam steps (lr 5e-5)
+    torch.manual_seed(19)
+    w = ns["Siren"](in_features=3, hidden_features=128, hidden_layers=3, out_features=31, first_omega_0=1.2,
+                    hidden_omega_0=1.2, scale=1.2)
+    sd0 = {k: v.clone() for k, v in w.state_dict().items()}
+    xw = SRDWI.get_mgrid((10, 9, 8))
+    gtw = torch.rand(xw.shape[0], 31, generator=torch.Generator().manual_seed(20))
+    ow = w(xw)
+    lw = ((ow - gtw) ** 2).mean()
+    lw.backward()
+    d = {"grid_shape": np.array((10, 9, 8)), "gt": gtw.numpy(), "out": ow.detach().numpy(), "loss": lw.item(),
+         "keys": np.array(list(sd0.keys()))}
+    for k, v in sd0.items():
+        d["cs0/" + k] = checksum(torch.view_as_real(v) if v.is_complex() else v)
+    for k, pp in w.named_parameters():
+        if pp.grad is not None:
+            gg = torch.view_as_real(pp.grad) if pp.grad.is_complex() else pp.grad
+            d["gcs/" + k] = checksum(gg)
+            if gg.numel() <= 2048:
+                d["g/" + k] = gg.numpy().copy()
+    opt = torch.optim.Adam(lr=5e-5, params=list(w.parameters()))
+    losses = []
+    for _ in range(5):
+        o = w(xw)
+        ls = ((o - gtw) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    d["losses"] = np.array(losses)
+    d["out_after"] = w(xw).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "wire_cfg3.npz"), **d)
+    print("wire_cfg3 losses", losses)
+
 
 if __name__ == "__main__":
     main()
