@@ -27,6 +27,10 @@ int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, 
 int launch_wire_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                     cudaStream_t stream);
+int launch_wire_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                    int num_sms, cudaStream_t stream);
+int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num_sms, cudaStream_t stream);
+int launch_wire_combine(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, cudaStream_t stream);
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
                float* loss_accum, cudaStream_t stream);
 int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
@@ -221,7 +225,11 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;  // WIRE backward: not implemented yet
+  if (is_wire(net)) {
+    if ((e = launch_wire_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
+    if ((e = launch_wire_wgrad(net, stash, rows, sms, s))) return e;
+    return launch_wire_combine(net, stash, rows, grad_params, s);
+  }
   if (is_gen(net)) {
     if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
@@ -241,7 +249,7 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
-  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;
+  if (is_wire(net)) return launch_wire_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
   if (is_gen(net)) return launch_gen_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
 }
@@ -258,7 +266,11 @@ int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords
   if ((reinterpret_cast<uintptr_t>(stash) & 1023) || !aligned16(grad_params)) return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
-  if (is_wire(net)) return B200INR_ERR_BAD_SHAPE;
+  if (is_wire(net)) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((e = launch_wire_wgrad(net, stash, rows, sms, s))) return e;
+    return launch_wire_combine(net, stash, rows, grad_params, s);
+  }
   if (is_gen(net)) return launch_gen_wgrad(net, stash, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, static_cast<cudaStream_t>(stream));
 }

@@ -307,6 +307,8 @@ __host__ __device__ inline WirePackLayout make_wire_pack_layout(const WireDims& 
 // pre-activations (a, b, c, d) (bf16 tile, 4H wide; layer 0 stores (a, 0, c, 0)); dz = dL/d(a,b,c,d) written by dgrad.
 struct WireStashLayout {
   size_t y, z, dz, dzo, xa;
+  size_t gblk;  // fp32 scratch of wgrad: per layer the real-block gradient [4H][K] + column sums [4H]; final [32][2H] + [32]
+  size_t gblk_bytes;
   size_t tile_y, tile_z, stride_y, stride_z;
   size_t total;
   int64_t tiles;
@@ -330,9 +332,18 @@ __host__ __device__ inline WireStashLayout make_wire_stash_layout(const WireDims
   o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
   s.xa = o;
   o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.gblk = o;
+  s.gblk_bytes = (size_t(w.L + 1) * (size_t(4 * w.H) * 2 * w.H + 4 * w.H) + size_t(kOutPad) * 2 * w.H + kOutPad) * 4;
+  o += (s.gblk_bytes + 1023) & ~size_t(1023);
   s.total = o;
   return s;
 }
+
+// fp32 offsets (in floats) inside the wgrad scratch of the WIRE family
+__host__ __device__ inline size_t wire_gblk_w(const WireDims& w, int l) { return size_t(l) * (size_t(4 * w.H) * 2 * w.H + 4 * w.H); }
+__host__ __device__ inline size_t wire_gblk_b(const WireDims& w, int l) { return wire_gblk_w(w, l) + size_t(4 * w.H) * 2 * w.H; }
+__host__ __device__ inline size_t wire_gblk_wf(const WireDims& w) { return wire_gblk_w(w, w.L + 1); }
+__host__ __device__ inline size_t wire_gblk_bf(const WireDims& w) { return wire_gblk_wf(w) + size_t(kOutPad) * 2 * w.H; }
 
 struct GridDesc {
   int ndim;

@@ -395,4 +395,71 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
   return launch_items(p, weight, num_sms, stream);
 }
 
+// WIRE: the contraction produces the gradient of the real-block matrices into the fp32 scratch of the stash
+// (zeroed here); wire.cu's combine kernel folds them into the complex parameters afterwards.
+int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num_sms, cudaStream_t stream) {
+  const WireDims w = make_wire_dims(net);
+  const WireStashLayout sl = make_wire_stash_layout(w, rows);
+  uint8_t* st = reinterpret_cast<uint8_t*>(stash);
+  float* g = reinterpret_cast<float*>(st + sl.gblk);
+  if (cudaMemsetAsync(g, 0, sl.gblk_bytes, stream) != cudaSuccess) return B200INR_ERR_CUDA;
+
+  WgParams p{};
+  p.num_tiles = int(sl.tiles);
+  p.d = w.d;
+  p.C = w.C;
+  double weight[kWgMaxItems];
+  int ni = 0;
+  const uint32_t tile_s = kTileRows * 128;
+  for (int l = 0; l <= w.L; ++l) {
+    for (int mh = 0; mh < 2; ++mh) {
+      if (ni >= kWgMaxItems - 1) return B200INR_ERR_BAD_SHAPE;
+      WgItem& it = p.items[ni];
+      it = WgItem{};
+      it.a_src = st + sl.dz + size_t(l) * sl.stride_z;
+      it.a_tile_bytes = uint32_t(sl.tile_z);
+      it.a_blk0 = 4 * mh;
+      it.gb = g + wire_gblk_b(w, l) + 256 * mh;
+      it.gb_count = 256;
+      it.scale = 1.0f;
+      if (l == 0) {
+        it.out = kWgOutCoord;
+        it.nb = 1;
+        it.b_src = st + sl.xa;
+        it.b_tile_bytes = tile_s;
+        it.gw = g + wire_gblk_w(w, 0) + size_t(256) * mh * w.d;
+        weight[ni++] = 80.0;
+      } else {
+        it.out = kWgOutBlock;
+        it.nb = 4;
+        it.b_src = st + sl.y + size_t(l - 1) * sl.stride_y;
+        it.b_tile_bytes = uint32_t(sl.tile_y);
+        it.gw = g + wire_gblk_w(w, l);
+        it.ldw = 2 * w.H;
+        it.row_off = 256 * mh;
+        weight[ni++] = 128.0;
+      }
+    }
+  }
+  {
+    WgItem& it = p.items[ni];
+    it = WgItem{};
+    it.out = kWgOutFinal;
+    it.nb = 1;
+    it.a_src = st + sl.y + size_t(w.L) * sl.stride_y;
+    it.a_tile_bytes = uint32_t(sl.tile_y);
+    it.b_src = st + sl.dzo;
+    it.b_tile_bytes = tile_s;
+    it.gw = g + wire_gblk_wf(w);
+    it.ldw = 2 * w.H;
+    it.gb = g + wire_gblk_bf(w);
+    it.sum_b = 1;
+    it.gb_count = w.C;
+    it.scale = 1.0f;
+    weight[ni++] = 80.0;
+  }
+  p.num_items = ni;
+  return launch_items(p, weight, num_sms, stream);
+}
+
 }  // namespace b200inr

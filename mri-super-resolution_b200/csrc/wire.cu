@@ -483,3 +483,349 @@ int launch_wire_fwd(const b200inr_net* net, const void* packed, const float* coo
 }
 
 }  // namespace b200inr
+
+// =====================================================================================================================
+// Backward: activation-gradient chain of the WIRE network.
+// With real upstream gradients (G_r, G_i) of a unit's output (h_r, h_i) and S = G_r h_r + G_i h_i:
+//     da = -2 s0^2 a S + w0 (G_i h_r - G_r h_i)      db = (-w0 - 2 s0^2 b) S
+//     dc = -2 s0^2 c S                               dd = -2 s0^2 d S
+// (first layer: b = d = 0 and their gradients are dropped).  Chain:  dH_L = dOut [Re W_f | -Im W_f],
+// dH_{l-1} = dZ_l Wblk_l (128 x 256 x 512 MMA), dZ_l from dH_l and the stashed pre-activations (a, b, c, d).
+// Every dZ_l tile (4H wide) and the bf16 dOut tile go to the stash for the wgrad contraction.
+namespace b200inr {
+
+constexpr int kWireZBlocks = 4 * kWireH / 64;                // 8 blocks of the dZ tile
+constexpr int kWireZBytes = kWireZBlocks * kWireABlock;      // 128 KB
+constexpr int kWireBwdSlots = 2;
+
+struct WireBwdParams {
+  const uint8_t* packed;
+  WireDims w;
+  WirePackLayout pl;
+  long long rows;
+  int num_tiles;
+  const float* grad_out;
+  const uint8_t* stash_z;
+  uint8_t* stash_dz;
+  uint8_t* stash_dzo;
+  size_t stride_z, tile_z;
+};
+
+struct WireBwdSmem {
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = kWireZBytes;
+  static constexpr int kOffDzo = kOffW + kWireBwdSlots * kGenChunkBytes;
+  static constexpr int kOffBar = kOffDzo + kTileRows * 128;
+  static constexpr int kBytes = kOffBar + 256;
+};
+
+__global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwdParams p) {
+  using S = WireBwdSmem;
+  constexpr int H = kWireH;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem + S::kOffA;
+  uint8_t* w_smem = smem + S::kOffW;
+  uint8_t* dzo_smem = smem + S::kOffDzo;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + kWireBwdSlots;
+  uint64_t* a_ready = bars + 2 * kWireBwdSlots;
+  uint64_t* dzo_ready = bars + 2 * kWireBwdSlots + 1;
+  uint64_t* d_full = bars + 2 * kWireBwdSlots + 2;
+  uint64_t* a_free = bars + 2 * kWireBwdSlots + 3;
+  uint64_t* dzo_free = bars + 2 * kWireBwdSlots + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWireBwdSlots + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const WireDims w = p.w;
+  const int L = w.L;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWireBwdSlots; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(a_ready, kWireEpiWarps);
+    mbar_init(dzo_ready, kWireEpiWarps);
+    mbar_init(d_full, 1);
+    mbar_init(a_free, 1);
+    mbar_init(dzo_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (warp == 0) {
+    if (lane == 0) {  // weight producer: W_f^T (1 chunk), then the 8 chunks of Wblk_l^T for l = L .. 1
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int u = 0; u <= L; ++u) {
+          const int nchunks = (u == 0) ? 1 : kWireZBlocks;
+          const uint8_t* src = (u == 0) ? p.packed + p.pl.wft : p.packed + p.pl.wt + size_t(L - u) * 8 * kGenChunkBytes;
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const uint32_t slot = c % kWireBwdSlots, round = c / kWireBwdSlots;
+            if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[slot], kGenChunkBytes);
+            bulk_g2s(w_smem + slot * kGenChunkBytes, src + size_t(j) * kGenChunkBytes, kGenChunkBytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // MMA issuer
+      const uint64_t hi = smem_desc_hi_sw128(0, 1024);
+      const uint32_t a_base = smem_u32(a_smem);
+      const uint32_t w_base = smem_u32(w_smem);
+      const uint32_t dzo_base = smem_u32(dzo_smem);
+      const uint32_t idesc = idesc_bf16(128, 256, false, false);
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);
+        for (int u = 0; u <= L; ++u) {
+          if (u == 0)
+            mbar_wait(dzo_ready, t & 1);
+          else
+            mbar_wait(a_ready, (inst0 + u - 1) & 1);
+          tc_fence_after();
+          const int kbn = (u == 0) ? 1 : kWireZBlocks;
+          for (int kb = 0; kb < kbn; ++kb, ++c) {
+            const uint32_t slot = c % kWireBwdSlots;
+            mbar_wait(&w_full[slot], (c / kWireBwdSlots) & 1);
+            tc_fence_after();
+            const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * kWireABlock;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_bf16_ss(tmem_d, smem_desc(a_blk + k4 * 32, hi),
+                           smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+            umma_commit(&w_empty[slot]);
+          }
+          umma_commit(d_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {  // stash store
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        mbar_wait(dzo_ready, t & 1);
+        bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(dzo_free);
+        for (int l = L; l >= 0; --l, ++n) {
+          mbar_wait(a_ready, n & 1);
+          bulk_s2g(p.stash_dz + size_t(l) * p.stride_z + size_t(tile) * kWireZBytes, a_smem, kWireZBytes);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(a_free);
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= kWireFirstEpiWarp) {
+    const int q = warp & 3;
+    const int s = (warp - kWireFirstEpiWarp) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = uint32_t(q * 32) << 16;
+    const uint32_t a_addr = smem_u32(a_smem);
+    const uint32_t dzo_addr = smem_u32(dzo_smem);
+    const int C = w.C;
+    const float s2 = w.s0 * w.s0;
+    uint32_t n = 0, nf = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const long long row0 = (long long)tile * kTileRows;
+      if (t > 0) mbar_wait(dzo_free, (t - 1) & 1);
+      {
+        const bool valid = (row0 + r) < p.rows;
+        const float* gp = p.grad_out + (row0 + r) * C;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = 2 * s + cc;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = ch * 8 + j;
+            v[j] = (valid && col < C) ? gp[col] : 0.f;
+          }
+          sts128(dzo_addr + sw128_chunk_off(r, ch),
+                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7])));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dzo_ready);
+      }
+
+      for (int l = L; l >= 0; --l) {
+        const float omega = (l == 0) ? w.omega0 : w.omegah;
+        // this thread owns units 32 s .. 32 s + 31 of its row: z chunks (2 units each) 16 s .. 16 s + 15
+        const uint8_t* z_l = p.stash_z + size_t(l) * p.stride_z + size_t(tile) * p.tile_z + size_t(r) * 16 +
+                             size_t(16 * s) * (kTileRows * 16);
+        mbar_wait(d_full, n & 1);
+        ++n;
+        if (nf > 0) mbar_wait(a_free, (nf - 1) & 1);
+        ++nf;
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // 16 units per pass
+          const int u0 = 32 * s + 16 * half;
+          uint32_t gr[16], gi[16];
+          tmem_ld16(tmem_d + t_lane + u0, gr);
+          tmem_ld16(tmem_d + t_lane + H + u0, gi);
+          uint4 zc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            zc[j] = *reinterpret_cast<const uint4*>(z_l + size_t(8 * half + j) * (kTileRows * 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // chunk j: units u0 + 2j, u0 + 2j + 1
+            const uint32_t zw[4] = {zc[j].x, zc[j].y, zc[j].z, zc[j].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float a = bf16lo(zw[2 * e]), b = bf16hi(zw[2 * e]);
+              const float c = bf16lo(zw[2 * e + 1]), d = bf16hi(zw[2 * e + 1]);
+              float hr, hi_;
+              gabor(a, b, c, d, omega, s2, hr, hi_);
+              const float Gr = __uint_as_float(gr[2 * j + e]), Gi = __uint_as_float(gi[2 * j + e]);
+              const float Ssum = fmaf(Gr, hr, Gi * hi_);
+              const float m2 = -2.f * s2 * Ssum;
+              float da = fmaf(m2, a, omega * (Gi * hr - Gr * hi_));
+              float db = fmaf(m2, b, -omega * Ssum);
+              float dc = m2 * c;
+              float dd = m2 * d;
+              if (l == 0) {  // real first layer: no imaginary pre-activations
+                db = 0.f;
+                dd = 0.f;
+              }
+              o[2 * e] = pack_bf16x2(da, db);
+              o[2 * e + 1] = pack_bf16x2(dc, dd);
+            }
+            const int ncol = 4 * (u0 + 2 * j);  // first dZ column of this unit pair
+            sts128(a_addr + uint32_t(ncol >> 6) * kWireABlock + sw128_chunk_off(r, (ncol & 63) >> 3),
+                   make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_d);
+}
+
+int launch_wire_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
+                    int num_sms, cudaStream_t stream) {
+  WireBwdParams p{};
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.w = make_wire_dims(net);
+  p.pl = make_wire_pack_layout(p.w);
+  p.rows = rows;
+  p.num_tiles = int((rows + kTileRows - 1) / kTileRows);
+  p.grad_out = grad_out;
+  const WireStashLayout sl = make_wire_stash_layout(p.w, rows);
+  uint8_t* st = reinterpret_cast<uint8_t*>(stash);
+  p.stash_z = st + sl.z;
+  p.stash_dz = st + sl.dz;
+  p.stash_dzo = st + sl.dzo;
+  p.stride_z = sl.stride_z;
+  p.tile_z = sl.tile_z;
+  const int smem = WireBwdSmem::kBytes + 1024;
+  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (cudaFuncSetAttribute(wire_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
+  wire_bwd_kernel<<<grid_x, kWireThreads, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ real-block gradients -> complex parameters
+// wgrad.cu leaves, per layer, the gradient of the real-block matrix G[n = 4u + comp][k] (and the column sums bs[n])
+// in the stash scratch; the complex weight W = W_r + i W_i occupies two positions of the block matrix
+// (a = h_r W_r - h_i W_i, b = h_r W_i + h_i W_r), so
+//     dW_r[u, k] = G[4u + 0][k] + G[4u + 1][H + k]        dW_i[u, k] = G[4u + 1][k] - G[4u + 0][H + k]
+// (same with rows 4u + 2, 4u + 3 for the orth weights); the result is ACCUMULATED into the flat parameter gradient.
+struct WireCombineParams {
+  const float* g;   // scratch
+  float* grad;      // flat parameter gradient
+  WireDims w;
+  long long off[4 * kMaxSineLayers + 2];
+};
+
+__global__ void __launch_bounds__(256) wire_combine_kernel(const WireCombineParams p) {
+  const int H = p.w.H, L = p.w.L, C = p.w.C, d = p.w.d;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  // first layer (real): scratch rows 4u (lin) and 4u + 2 (orth), d columns
+  {
+    const float* G = p.g + wire_gblk_w(p.w, 0);
+    const float* bs = p.g + wire_gblk_b(p.w, 0);
+    for (long long i = tid; i < (long long)2 * H * (d + 1); i += nthreads) {
+      const int which = int(i / ((long long)H * (d + 1)));
+      const int rem = int(i % ((long long)H * (d + 1)));
+      const int u = rem / (d + 1), j = rem % (d + 1);
+      const int row = 4 * u + 2 * which;
+      if (j < d)
+        p.grad[p.off[2 * which] + (long long)u * d + j] += G[(long long)row * d + j];
+      else
+        p.grad[p.off[2 * which + 1] + u] += bs[row];
+    }
+  }
+  for (int l = 1; l <= L; ++l) {
+    const float* G = p.g + wire_gblk_w(p.w, l);
+    const float* bs = p.g + wire_gblk_b(p.w, l);
+    const long long nw = (long long)2 * H * H;  // (which, u, k)
+    for (long long i = tid; i < nw; i += nthreads) {
+      const int which = int(i / ((long long)H * H));
+      const int u = int((i / H) % H), k = int(i % H);
+      const float* g0 = G + (long long)(4 * u + 2 * which) * (2 * H);      // Re row
+      const float* g1 = G + (long long)(4 * u + 2 * which + 1) * (2 * H);  // Im row
+      float* dst = p.grad + p.off[4 * l + 2 * which] + ((long long)u * H + k) * 2;
+      dst[0] += g0[k] + g1[H + k];
+      dst[1] += g1[k] - g0[H + k];
+    }
+    for (long long i = tid; i < 4 * H; i += nthreads) {
+      const int u = int(i >> 2), comp = int(i & 3);
+      p.grad[p.off[4 * l + 2 * (comp >> 1) + 1] + 2 * u + (comp & 1)] += bs[i];
+    }
+  }
+  {  // final linear: out = h_r Re W - h_i Im W + Re b
+    const float* G = p.g + wire_gblk_wf(p.w);
+    const float* bs = p.g + wire_gblk_bf(p.w);
+    for (long long i = tid; i < (long long)C * H; i += nthreads) {
+      const int c = int(i / H), k = int(i % H);
+      float* dst = p.grad + p.off[4 * (L + 1)] + ((long long)c * H + k) * 2;
+      dst[0] += G[(long long)c * 2 * H + k];
+      dst[1] -= G[(long long)c * 2 * H + H + k];  // out = ... - h_i Im W
+    }
+    for (long long i = tid; i < C; i += nthreads) p.grad[p.off[4 * (L + 1) + 1] + 2 * i] += bs[i];
+  }
+}
+
+int launch_wire_combine(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, cudaStream_t stream) {
+  WireCombineParams p{};
+  p.w = make_wire_dims(net);
+  const WireStashLayout sl = make_wire_stash_layout(p.w, rows);
+  p.g = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(stash) + sl.gblk);
+  p.grad = grad_params;
+  int64_t off[4 * kMaxSineLayers + 2] = {0};
+  wire_param_offsets(p.w, off);
+  for (int i = 0; i < 4 * (p.w.L + 1) + 2; ++i) p.off[i] = off[i];
+  wire_combine_kernel<<<296, 256, 0, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+}  // namespace b200inr

@@ -497,3 +497,68 @@ def test_wire_full_size_query_sampled(dev):
     idx = np.random.RandomState(1).choice(raw.shape[0], 2048, replace=False)
     ref = O.wire_forward(layers, fw, fb, O.get_mgrid(shape)[idx], 1.2, 1.2)
     assert _relerr(raw[torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) < BF16_RELERR
+
+
+def test_wire_backward_and_trajectory_vs_reference_golden(dev, golden_dir):
+    """loss.backward() through the fused WIRE kernels against the reference's autograd gradients (complex parameters
+    as (re, im) pairs), then the unmodified loop with torch.optim.Adam(lr=5e-5) against its 5-step loss trajectory."""
+    g = np.load(os.path.join(golden_dir, "wire_cfg3.npz"))
+    torch.manual_seed(19)
+    m = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+    shape = tuple(int(s) for s in g["grid_shape"])
+    x = b200inr.get_mgrid(shape).to(dev)
+    gt = torch.from_numpy(g["gt"]).to(dev)
+    out = m(x)
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=2e-2)
+    params = dict(m.named_parameters())
+
+    def real_view(t):
+        return (torch.view_as_real(t) if t.is_complex() else t).detach().cpu().numpy()
+
+    checked = 0
+    for k in [f for f in g.files if f.startswith("g/")]:
+        assert _relerr(real_view(params[k[2:]].grad), g[k]) < 3e-2, k
+        checked += 1
+    for k in [f for f in g.files if f.startswith("gcs/")]:
+        gr = real_view(params[k[4:]].grad).astype(np.float64)
+        assert abs((gr ** 2).sum() - g[k][1]) <= 6e-2 * g[k][1] + 1e-16, k  # squared norm
+        assert abs(gr.sum() - g[k][0]) <= 3e-2 * np.sqrt(g[k][1] * gr.size) + 1e-12, k  # plain sum
+    assert checked >= 8
+    assert params["net.0.omega_0"].grad is None  # frozen, as in the reference
+    opt = torch.optim.Adam(lr=5e-5, params=list(m.parameters()))
+    losses = []
+    for _ in range(5):
+        o = m.forward(x)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    np.testing.assert_allclose(losses, g["losses"], rtol=3e-2)
+    with torch.no_grad():
+        assert _relerr(m(x).cpu().numpy(), g["out_after"]) < 5e-2
+
+
+def test_wire_fused_fit_matches_module_loop(dev):
+    """Wire.fit (fused, flat Adam on (re, im) pairs) == the autograd loop with torch.optim.Adam on the same seed."""
+    shape, C, steps = (12, 10, 8), 31, 4
+    x = b200inr.get_mgrid(shape).to(dev)
+    gt = torch.rand(x.shape[0], C, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    torch.manual_seed(31)
+    a = b200inr.Wire(3, 128, 3, C, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+    torch.manual_seed(31)
+    b = b200inr.Wire(3, 128, 3, C, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+    la = a.fit(gt, shape, steps=steps, lr=5e-5).cpu().numpy()
+    opt = torch.optim.Adam(lr=5e-5, params=list(b.parameters()))
+    lb = []
+    for _ in range(steps):
+        o = b.forward(x)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        lb.append(ls.item())
+    np.testing.assert_allclose(la, lb, rtol=5e-3)
+    assert _relerr(a.query(shape, clamp_min=None).cpu().numpy(), b.query(shape, clamp_min=None).cpu().numpy()) < 1e-2
