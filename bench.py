@@ -260,7 +260,7 @@ def run_ours(args):
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"] or peaks["tflops"],
                     "unit": "TFLOP/s", "frac": achieved / (peaks["tflops_sustained"] or peaks["tflops"]),
                     "traffic": traffic, "peak_source": peaks["src"] + " (sustained: kernel timed inside the step)"}
-    step_tflops = FLOP_TRAIN * global_rows / (ms_step * 1e-3) / 1e12
+    step_tflops = FLOP_TRAIN * rows / (ms_step * 1e-3) / 1e12  # per GPU
 
     # ---- CPU baseline: bounded sample on the host cores
     cpu = None
@@ -286,11 +286,11 @@ def run_ours(args):
         "gpu_launches": sess.kernel_launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "step_tflops_algorithmic": step_tflops,
+        "step_tflops_algorithmic_per_gpu": step_tflops,
         "step_frac_of_peak": step_tflops / (peaks["tflops_sustained"] or peaks["tflops"]),
         "stage_ms": stage_ms,
         "query": {"value": q_value, "unit": "voxels/s", "ms": q_ms,
-                  "tflops": 2 * MAC_FWD * global_rows / (q_ms * 1e-3) / 1e12, "grid": list(qshape)},
+                  "tflops_per_gpu": 2 * MAC_FWD * rows / (q_ms * 1e-3) / 1e12, "grid": list(qshape)},
         "final_loss": loss_last,
     }
     print(json.dumps(line), flush=True)

@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
   uint64_t* a_ready = bars + 2 * kBwdSlots;    // [4] K block kb of dTheta_l is in shared memory
   uint64_t* dzo_ready = bars + 2 * kBwdSlots + 4;
   uint64_t* d_full = bars + 2 * kBwdSlots + 5;
-  uint64_t* a_free = bars + 2 * kBwdSlots + 6;    // stash stores out of a_smem have been read
-  uint64_t* dzo_free = bars + 2 * kBwdSlots + 7;  // stash store out of dzo_smem has been read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBwdSlots + 8);
+  uint64_t* a_free = bars + 2 * kBwdSlots + 6;     // [4] stash store of dTheta block kb has been read out
+  uint64_t* dzo_free = bars + 2 * kBwdSlots + 10;  // stash store out of dzo_smem has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBwdSlots + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
     for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kBwdEpiWarps);
     mbar_init(dzo_ready, kBwdEpiWarps);
     mbar_init(d_full, 1);
-    mbar_init(a_free, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
     mbar_init(dzo_free, 1);
     fence_mbar_init();
   }
@@ -110,10 +110,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
     if (lane == 0) {
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
+        const int tile = int(blockIdx.x) + t * int(gridDim.x);
         for (int j = 0; j < chunks_per_tile; ++j, ++c) {
           const uint32_t slot = c % kBwdSlots;
           const uint32_t round = c / kBwdSlots;
           const uint8_t* src;
+          if (j == 0 || (j - 1) % S::kKB == 0) {  // first chunk of chain step u: its epilogue needs the phases of layer L - u
+            const int u = (j == 0) ? 0 : 1 + (j - 1) / S::kKB;
+            bulk_prefetch_l2(p.stash_ph + size_t(L - u) * p.layer_stride + size_t(tile) * S::kABytes, S::kABytes);
+          }
           if (j == 0) {
             src = p.packed + p.pl.wft;
           } else {
@@ -179,10 +184,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
             mbar_wait(&a_ready[kb], n & 1);
             bulk_s2g(dz_tile + size_t(l) * p.layer_stride + size_t(kb) * S::kABlock, a_smem + kb * S::kABlock,
                      S::kABlock);
+            bulk_commit();
+            if (kb > 0) {
+              bulk_wait_read1();
+              mbar_arrive(&a_free[kb - 1]);
+            }
           }
-          bulk_commit();
           bulk_wait_read0();
-          mbar_arrive(a_free);
+          mbar_arrive(&a_free[S::kKB - 1]);
         }
       }
       bulk_wait0();
@@ -229,14 +238,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
       // ---- dTheta_l = dY_l .* cos(theta_l), l = L .. 0
       for (int l = L; l >= 0; --l) {
         const uint8_t* ph_l = ph_row + size_t(l) * p.layer_stride + size_t(2 * s) * (kTileRows * 16);
-        // phases of the first K block are fetched while the MMAs are still running
+        // phases of the first K block are fetched while the MMAs are still running; the whole phase tile was pulled
+        // into L2 by the producer thread one layer ahead
         uint4 ph[2], phn[2];
         phn[0] = *reinterpret_cast<const uint4*>(ph_l);
         phn[1] = *reinterpret_cast<const uint4*>(ph_l + kTileRows * 16);
         mbar_wait(d_full, n & 1);
         ++n;
-        if (nf > 0) mbar_wait(a_free, (nf - 1) & 1);  // previous dTheta tile has been stored
-        ++nf;
         tc_fence_after();
         const uint32_t d_addr = tmem_d + t_lane + uint32_t((L - l) & 1) * 256 + s * 16;
         uint32_t v[16], vn[16];
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
             phn[0] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8) * (kTileRows * 16));
             phn[1] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8 + 1) * (kTileRows * 16));
           }
+          if (nf > 0) mbar_wait(&a_free[kb], (nf - 1) & 1);  // the previous dTheta block kb has been stored
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint32_t pw[4] = {ph[c].x, ph[c].y, ph[c].z, ph[c].w};
@@ -270,6 +279,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[kb]);
         }
+        ++nf;
       }
     }
   }

@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   uint64_t* w_empty = bars + kFwdSlots;        // [kFwdSlots]
   uint64_t* a_ready = bars + 2 * kFwdSlots;    // [4]  K block kb of the next A operand is in shared memory
   uint64_t* d_full = bars + 2 * kFwdSlots + 4;
-  uint64_t* a_free = bars + 2 * kFwdSlots + 5;  // stash stores of the A tile have been read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 6);
+  uint64_t* a_free = bars + 2 * kFwdSlots + 5;  // [4] stash store of A block kb has been read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     }
     for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kFwdEpiWarps);
     mbar_init(d_full, 1);
-    mbar_init(a_free, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -196,11 +196,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             mbar_wait(&a_ready[kb], n & 1);
             bulk_s2g(y_tile + size_t(l) * p.stash_layer_stride + size_t(kb) * S::kABlock, a_smem + kb * S::kABlock,
                      S::kABlock);
+            if (l == 0 && kb == 0) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
+            bulk_commit();
+            if (kb > 0) {  // the previous block's group has been read out of shared memory
+              bulk_wait_read1();
+              mbar_arrive(&a_free[kb - 1]);
+            }
           }
-          if (l == 0) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
-          bulk_commit();
           bulk_wait_read0();
-          mbar_arrive(a_free);
+          mbar_arrive(&a_free[S::kKB - 1]);
         }
       }
       bulk_wait0();
@@ -268,32 +272,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       for (int l = 1; l <= L; ++l) {
         mbar_wait(d_full, n & 1);
         ++n;
-        if (kStash) {
-          mbar_wait(a_free, nf & 1);
-          ++nf;
-        }
         tc_fence_after();
-        const float* bl = bias_smem + l * H;
+        const uint32_t bl_addr = smem_u32(bias_smem + l * H);
         const uint32_t d_addr = tmem_d + t_lane + uint32_t(l & 1) * 256 + s * 16;
         uint8_t* ph_l = kStash ? ph_row + size_t(l) * p.stash_layer_stride : nullptr;
         uint32_t v[16], vn[16];
         tmem_ld16(d_addr, vn);
 #pragma unroll
         for (int kb = 0; kb < S::kKB; ++kb) {
+          const int col0 = kb * 64 + s * 16;
+          uint4 bq[4];  // biases of this slice: issued before the TMEM wait so both latencies overlap
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) bq[j4] = lds128(bl_addr + uint32_t(col0 + j4 * 4) * 4);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
           if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
-          const int col0 = kb * 64 + s * 16;
           float th[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bl + col0 + j4 * 4);
-            th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b.x;
-            th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b.y;
-            th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b.z;
-            th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b.w;
+            th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + __uint_as_float(bq[j4].x);
+            th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + __uint_as_float(bq[j4].y);
+            th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + __uint_as_float(bq[j4].z);
+            th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + __uint_as_float(bq[j4].w);
           }
+          if (kStash) mbar_wait(&a_free[kb], nf & 1);  // the stash store of this block (previous layer) has been read
           emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
                               kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
           fence_proxy_async_smem();
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[kb]);
         }
+        ++nf;
       }
 
       // ---- final linear: D[:, 0:32) + bias -> out
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         mbar_wait(d_full, n & 1);
         ++n;
         if (kStash) {
-          mbar_wait(a_free, nf & 1);
+          for (int kb = 0; kb < S::kKB; ++kb) mbar_wait(&a_free[kb], nf & 1);
           ++nf;
         }
         tc_fence_after();

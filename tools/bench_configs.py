@@ -1,0 +1,93 @@
+"""Secondary benchmark: one JSON line per BASELINE config (cfg1..cfg5) at its full size, device-resident inputs,
+CUDA-event timing.  bench.py stays the contract line (cfg2); this script documents the other configs.
+    python tools/bench_configs.py [--steps K] > profiles/rNN_configs.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import b200inr  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def fit_line(name, model, target, shape, degrade, lr, flop_per_row, steps):
+    rows = int(np.prod(shape))
+    sess = b200inr.FitSession(model, target, shape, lr=lr, degrade=degrade)
+    ms = timed(sess.step, steps)
+    marks = []
+    sess.step(marks)
+    torch.cuda.synchronize()
+    st = {nm: round(marks[i].elapsed_time(marks[i + 1]), 4) for i, nm in enumerate(b200inr.FitSession.STAGES)}
+    tf = flop_per_row * rows / (ms * 1e-3) / 1e12
+    return {"config": name, "metric": "inr_train_coord_samples_per_s", "value": rows / (ms * 1e-3), "ms_per_step": ms,
+            "rows": rows, "tflops_algorithmic": tf, "frac_of_sustained_peak": tf / PEAK["bf16_tflops_sustained"],
+            "frac_of_burst_peak": tf / PEAK["bf16_tflops"], "stage_ms": st, "final_loss": float(sess.loss.item())}
+
+
+def query_line(name, model, shape, flop_per_row, steps):
+    rows = int(np.prod(shape))
+    out = torch.empty((rows, model.out_features), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: model.query(shape, out=out), steps)
+    tf = flop_per_row * rows / (ms * 1e-3) / 1e12
+    return {"config": name, "metric": "hr_voxel_queries_per_s", "value": rows / (ms * 1e-3), "ms": ms, "rows": rows,
+            "tflops_algorithmic": tf, "frac_of_sustained_peak": tf / PEAK["bf16_tflops_sustained"],
+            "frac_of_burst_peak": tf / PEAK["bf16_tflops"], "output_gb": rows * model.out_features * 4 / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    lines = []
+    # cfg1: SIREN 2D slice fit 256x256, 3x256 hidden (Siren(2,256,2,1)), lr 3e-4
+    m = b200inr.Siren(2, 256, 2, 1).to(dev)
+    tgt = torch.rand(256 * 256, 1, device=dev)
+    lines.append(fit_line("cfg1 SIREN 2->3x256->1, 256x256 slice", m, tgt, (256, 256), None, 3e-4, 790016, a.steps * 5))
+    # cfg2: SIREN 3D DWI fit with 2x LR-consistency loss
+    hr_shape = (128, 128, 64)
+    lr_t = torch.rand(64 * 64 * 64, 31, device=dev)
+    m2 = b200inr.Siren(3, 256, 4, 31).to(dev)
+    lines.append(fit_line("cfg2 SIREN 3->5x256->31, 128x128x64, pooled loss", m2, lr_t, hr_shape, "pool", 1e-4, 1623552,
+                          a.steps))
+    # cfg3: WIRE on the same volume (point-wise loss on the HR grid), omega0 = s0 = 1.2, lr 5e-5
+    m3 = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+    hr_t = torch.rand(128 * 128 * 64, 31, device=dev)
+    lines.append(fit_line("cfg3 WIRE 3->128c x(1+3)->31, 128x128x64", m3, hr_t, hr_shape, None, 5e-5, 2409984, a.steps))
+    lines.append(query_line("cfg3 WIRE query 128x128x64", m3, hr_shape, 803840, a.steps))
+    # cfg4: Fourier-feature ReLU MLP (256 frequencies, 4x512) with the blur+pool degradation operator
+    B = np.random.RandomState(0).normal(size=(256, 3)) * 0.5
+    m4 = b200inr.FourierMLP(3, 256, 512, 3, 31, B).to(dev)
+    lines.append(fit_line("cfg4 FF(256)->ReLU 4x512->31, blur+pool loss", m4, lr_t, hr_shape, "blur_pool", 1e-4, 5863936,
+                          a.steps))
+    lines.append(query_line("cfg4 FF-ReLU query 128x128x64", m4, hr_shape, 2130432, a.steps))
+    # cfg5: 4x HR grid inference 512x512x256 x 31 channels with the cfg2 network (one GPU: the whole grid)
+    lines.append(query_line("cfg5 SIREN query 512x512x256 (whole grid on one GPU)", m2, (512, 512, 256), 541696, 3))
+    for ln in lines:
+        print(json.dumps(ln), flush=True)
+
+
+if __name__ == "__main__":
+    main()
