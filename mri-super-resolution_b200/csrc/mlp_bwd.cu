@@ -10,8 +10,7 @@
 // with the stashed activations over the row dimension.  No input gradient: SRDWI.Siren detaches its coordinates
 // (INR/SRDWI.py:88).
 //
-// Same pipeline as mlp_fwd.cu: the epilogue emits dTheta_l one 64-wide K block at a time (one mbarrier per block),
-// the accumulator is double buffered in TMEM, so the MMAs of the next chain step run underneath the epilogue.
+// Same two-tile ping-pong as mlp_fwd.cu (see the comment above the kernel).
 //
 // Warp roles: warp 0 = weight producer (W'^T chunks), warp 1 = MMA issuer + TMEM owner, warp 2 = stash store,
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
@@ -26,7 +25,7 @@ constexpr int kBwdEpiWarps = 16;
 constexpr int kBwdFirstEpiWarp = 3;
 constexpr int kBwdThreads = (kBwdFirstEpiWarp + kBwdEpiWarps) * 32;  // 608
 constexpr int kBwdEpiThreads = kBwdEpiWarps * 32;
-constexpr int kBwdSlots = 4;
+constexpr int kBwdSlots = 3;
 
 struct BwdParams {
   const uint8_t* packed;
@@ -45,12 +44,11 @@ template <int H>
 struct BwdSmem {
   static constexpr int kKB = H / 64;
   static constexpr int kABlock = kTileRows * 128;
-  static constexpr int kABytes = kKB * kABlock;  // dTheta tile
+  static constexpr int kABytes = kKB * kABlock;  // dTheta tile; block 0 doubles as the dOut block of chain step 0
   static constexpr int kSlotBytes = H * 128;     // [H rows (N = in)][64 (K = out chunk)]
-  static constexpr int kOffA = 0;
-  static constexpr int kOffW = kABytes;
-  static constexpr int kOffDzo = kOffW + kBwdSlots * kSlotBytes;
-  static constexpr int kOffBar = kOffDzo + kTileRows * 128;
+  static constexpr int kOffA = 0;                // two tiles
+  static constexpr int kOffW = 2 * kABytes;
+  static constexpr int kOffBar = kOffW + kBwdSlots * kSlotBytes;
   static constexpr int kBytes = kOffBar + 256;
 };
 
@@ -61,6 +59,10 @@ __device__ __forceinline__ float cos_from_phase(uint32_t ph16) {
   return __cosf(f * kPhaseToRad);
 }
 
+// Two 128-row tiles (X, Y) ping-pong exactly as in mlp_fwd.cu: one dTheta tile in shared memory and one 256-column
+// TMEM accumulator each; the epilogue warps alternate X, Y chain step by chain step, so every MMA runs underneath the
+// other tile's epilogue.  Stage 0 of a tile converts dOut to bf16 into block 0 of its A tile (K = 64 operand of the
+// first chain step), stages 1 .. L+1 produce dTheta_L .. dTheta_0.
 template <int H>
 __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdParams p) {
   using S = BwdSmem<H>;
@@ -69,16 +71,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem + S::kOffA;
   uint8_t* w_smem = smem + S::kOffW;
-  uint8_t* dzo_smem = smem + S::kOffDzo;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;                     // [kBwdSlots]
-  uint64_t* w_empty = bars + kBwdSlots;        // [kBwdSlots]
-  uint64_t* a_ready = bars + 2 * kBwdSlots;    // [4] K block kb of dTheta_l is in shared memory
-  uint64_t* dzo_ready = bars + 2 * kBwdSlots + 4;
-  uint64_t* d_full = bars + 2 * kBwdSlots + 5;
-  uint64_t* a_free = bars + 2 * kBwdSlots + 6;     // [4] stash store of dTheta block kb has been read out
-  uint64_t* dzo_free = bars + 2 * kBwdSlots + 10;  // stash store out of dzo_smem has been read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBwdSlots + 11);
+  uint64_t* w_full = bars;                      // [kBwdSlots]
+  uint64_t* w_empty = bars + kBwdSlots;         // [kBwdSlots]
+  uint64_t* a_ready = bars + 2 * kBwdSlots;     // [2] operand tile j complete in shared memory
+  uint64_t* d_full = bars + 2 * kBwdSlots + 2;  // [2] accumulator j complete
+  uint64_t* a_free = bars + 2 * kBwdSlots + 4;  // [2] stash store out of tile j has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBwdSlots + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,11 +88,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kBwdEpiWarps);
-    mbar_init(dzo_ready, kBwdEpiWarps);
-    mbar_init(d_full, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
-    mbar_init(dzo_free, 1);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&a_ready[j], kBwdEpiWarps);
+      mbar_init(&d_full[j], 1);
+      mbar_init(&a_free[j], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -103,32 +102,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  const int chunks_per_tile = 1 + L * S::kKB;  // W_f^T, then kKB chunks of each W'_l^T, l = L .. 1
+  const int num_pairs = (my_tiles + 1) / 2;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t c = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int tile = int(blockIdx.x) + t * int(gridDim.x);
-        for (int j = 0; j < chunks_per_tile; ++j, ++c) {
-          const uint32_t slot = c % kBwdSlots;
-          const uint32_t round = c / kBwdSlots;
-          const uint8_t* src;
-          if (j == 0 || (j - 1) % S::kKB == 0) {  // first chunk of chain step u: its epilogue needs the phases of layer L - u
-            const int u = (j == 0) ? 0 : 1 + (j - 1) / S::kKB;
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int u = 0; u <= L; ++u) {  // u = 0: W_f^T (one chunk); u >= 1: the kKB chunks of W'^T of layer L - u + 1
+          const int nchunks = (u == 0) ? 1 : S::kKB;
+          const uint8_t* src = (u == 0) ? p.packed + p.pl.wft : p.packed + p.pl.wht + size_t(L - u) * H * H * 2;
+          for (int j = 0; j < nt; ++j) {
+            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            // the epilogue after chain step u needs the phases of layer L - u: pull them into L2 now
             bulk_prefetch_l2(p.stash_ph + size_t(L - u) * p.layer_stride + size_t(tile) * S::kABytes, S::kABytes);
+            for (int kb = 0; kb < nchunks; ++kb, ++c) {
+              const uint32_t slot = c % kBwdSlots, round = c / kBwdSlots;
+              if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+              mbar_arrive_expect_tx(&w_full[slot], S::kSlotBytes);
+              bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * S::kSlotBytes, S::kSlotBytes, &w_full[slot]);
+            }
           }
-          if (j == 0) {
-            src = p.packed + p.pl.wft;
-          } else {
-            const int l = L - (j - 1) / S::kKB;  // hidden layer whose weights are used (L .. 1)
-            const int kb = (j - 1) % S::kKB;
-            src = p.packed + p.pl.wht + size_t(l - 1) * H * H * 2 + size_t(kb) * S::kSlotBytes;
-          }
-          if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
-          mbar_arrive_expect_tx(&w_full[slot], S::kSlotBytes);
-          bulk_g2s(w_smem + slot * S::kSlotBytes, src, S::kSlotBytes, &w_full[slot]);
         }
       }
     }
@@ -138,60 +133,58 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      const uint32_t dzo_base = smem_u32(dzo_smem);
       const uint32_t idesc = idesc_bf16(128, H, false, false);
-      uint32_t c = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        // a_ready completes L + 1 times per tile (layers L .. 0); instance u - 1 feeds chain step u
-        const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);
-        for (int u = 0; u <= L; ++u) {  // u = 0: dOut W_f ; u >= 1: dTheta_{L-u+1} W'_{L-u+1}
-          const uint32_t d_addr = tmem_d + uint32_t(u & 1) * 256;
+      uint32_t c = 0, na[2] = {0, 0};
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int u = 0; u <= L; ++u) {
           const int nkb = (u == 0) ? 1 : S::kKB;
-          for (int kb = 0; kb < nkb; ++kb, ++c) {
-            const uint32_t slot = c % kBwdSlots;
-            if (u == 0)
-              mbar_wait(dzo_ready, t & 1);
-            else
-              mbar_wait(&a_ready[kb], (inst0 + u - 1) & 1);
-            mbar_wait(&w_full[slot], (c / kBwdSlots) & 1);
+          for (int j = 0; j < nt; ++j) {
+            mbar_wait(&a_ready[j], na[j] & 1);
+            ++na[j];
             tc_fence_after();
-            const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * S::kABlock;
+            for (int kb = 0; kb < nkb; ++kb, ++c) {
+              const uint32_t slot = c % kBwdSlots;
+              mbar_wait(&w_full[slot], (c / kBwdSlots) & 1);
+              tc_fence_after();
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_bf16_ss(d_addr, smem_desc(a_blk + k4 * 32, hi),
-                           smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16_ss(tmem_d + j * 256, smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi),
+                             smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+              }
+              umma_commit(&w_empty[slot]);
             }
-            umma_commit(&w_empty[slot]);
+            umma_commit(&d_full[j]);
           }
-          umma_commit(d_full);
+        }
+        // the dTheta_0 tiles feed no MMA, but their a_ready phase must still be observed: a parity wait may only
+        // ever be one phase behind the barrier
+        for (int j = 0; j < nt; ++j) {
+          mbar_wait(&a_ready[j], na[j] & 1);
+          ++na[j];
         }
       }
     }
   } else if (warp == 2) {
     // =============================== stash store ===============================
     if (lane == 0) {
-      uint32_t n = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int tile = int(blockIdx.x) + t * int(gridDim.x);
-        uint8_t* dz_tile = p.stash_dz + size_t(tile) * S::kABytes;
-        mbar_wait(dzo_ready, t & 1);
-        bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
-        bulk_commit();
-        bulk_wait_read0();
-        mbar_arrive(dzo_free);
-        for (int l = L; l >= 0; --l, ++n) {
-          for (int kb = 0; kb < S::kKB; ++kb) {
-            mbar_wait(&a_ready[kb], n & 1);
-            bulk_s2g(dz_tile + size_t(l) * p.layer_stride + size_t(kb) * S::kABlock, a_smem + kb * S::kABlock,
-                     S::kABlock);
+      uint32_t na[2] = {0, 0};
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int st = 0; st <= L + 1; ++st) {  // stage 0: dOut block; stage st >= 1: dTheta of layer L + 1 - st
+          for (int j = 0; j < nt; ++j) {
+            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            mbar_wait(&a_ready[j], na[j] & 1);
+            ++na[j];
+            if (st == 0)
+              bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), a_smem + j * S::kABytes, kTileRows * 128);
+            else
+              bulk_s2g(p.stash_dz + size_t(L + 1 - st) * p.layer_stride + size_t(tile) * S::kABytes,
+                       a_smem + j * S::kABytes, S::kABytes);
             bulk_commit();
-            if (kb > 0) {
-              bulk_wait_read1();
-              mbar_arrive(&a_free[kb - 1]);
-            }
+            bulk_wait_read0();
+            mbar_arrive(&a_free[j]);
           }
-          bulk_wait_read0();
-          mbar_arrive(&a_free[S::kKB - 1]);
         }
       }
       bulk_wait0();
@@ -202,18 +195,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
     const int s = (warp - kBwdFirstEpiWarp) >> 2;
     const int r = q * 32 + lane;
     const uint32_t t_lane = uint32_t(q * 32) << 16;
-    const uint32_t a_addr = smem_u32(a_smem);
-    const uint32_t dzo_addr = smem_u32(dzo_smem);
     const int C = p.C;
-    uint32_t n = 0, nf = 0;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = int(blockIdx.x) + t * int(gridDim.x);
-      const long long row0 = (long long)tile * kTileRows;
-      const uint8_t* ph_row = p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16;
+    uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
+    bool first_store[2] = {true, true};
+    for (int pr = 0; pr < num_pairs; ++pr) {
+      const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
 
-      // ---- dOut tile -> bf16 [128][64] block (columns >= C and rows >= rows are zero); slice s = chunks 2s, 2s+1
-      if (t > 0) mbar_wait(dzo_free, (t - 1) & 1);  // the previous tile's dOut block has been stored and multiplied
-      {
+      // ---- stage 0: dOut tile -> bf16 [128][64] block in block 0 of the tile (columns >= C, rows >= rows zero)
+      for (int j = 0; j < nt; ++j) {
+        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const long long row0 = (long long)tile * kTileRows;
+        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        if (!first_store[j]) {  // the previous pair's dTheta_0 store out of this tile has been read
+          mbar_wait(&a_free[j], nf[j] & 1);
+          ++nf[j];
+        }
+        first_store[j] = false;
         const bool valid = (row0 + r) < p.rows;
         const float* g = p.grad_out + (row0 + r) * C;
 #pragma unroll
@@ -221,65 +218,68 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
           const int ch = 2 * s + cc;
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = ch * 8 + j;
-            v[j] = (valid && col < C) ? g[col] : 0.f;
+          for (int jj = 0; jj < 8; ++jj) {
+            const int col = ch * 8 + jj;
+            v[jj] = (valid && col < C) ? g[col] : 0.f;
           }
-          sts128(dzo_addr + sw128_chunk_off(r, ch),
+          sts128(a_addr + sw128_chunk_off(r, ch),
                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                             pack_bf16x2(v[6], v[7])));
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dzo_ready);
+        if (lane == 0) mbar_arrive(&a_ready[j]);
       }
 
-      // ---- dTheta_l = dY_l .* cos(theta_l), l = L .. 0
+      // ---- dTheta_l = dY_l .* cos(theta_l), l = L .. 0, alternating X, Y
       for (int l = L; l >= 0; --l) {
-        const uint8_t* ph_l = ph_row + size_t(l) * p.layer_stride + size_t(2 * s) * (kTileRows * 16);
-        // phases of the first K block are fetched while the MMAs are still running; the whole phase tile was pulled
-        // into L2 by the producer thread one layer ahead
-        uint4 ph[2], phn[2];
-        phn[0] = *reinterpret_cast<const uint4*>(ph_l);
-        phn[1] = *reinterpret_cast<const uint4*>(ph_l + kTileRows * 16);
-        mbar_wait(d_full, n & 1);
-        ++n;
-        tc_fence_after();
-        const uint32_t d_addr = tmem_d + t_lane + uint32_t((L - l) & 1) * 256 + s * 16;
-        uint32_t v[16], vn[16];
-        tmem_ld16(d_addr, vn);
+        for (int j = 0; j < nt; ++j) {
+          const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+          const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+          const uint8_t* ph_l = p.stash_ph + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes + size_t(r) * 16 +
+                                size_t(2 * s) * (kTileRows * 16);
+          uint4 ph[2], phn[2];
+          phn[0] = *reinterpret_cast<const uint4*>(ph_l);
+          phn[1] = *reinterpret_cast<const uint4*>(ph_l + kTileRows * 16);
+          mbar_wait(&d_full[j], nd[j] & 1);
+          ++nd[j];
+          mbar_wait(&a_free[j], nf[j] & 1);  // the previous store out of this tile (dOut block or dTheta_{l+1})
+          ++nf[j];
+          tc_fence_after();
+          const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
+          uint32_t v[16], vn[16];
+          tmem_ld16(d_addr, vn);
 #pragma unroll
-        for (int kb = 0; kb < S::kKB; ++kb) {
-          tmem_ld_wait();
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = vn[j];
-          ph[0] = phn[0];
-          ph[1] = phn[1];
-          if (kb + 1 < S::kKB) {
-            tmem_ld16(d_addr + (kb + 1) * 64, vn);
-            phn[0] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8) * (kTileRows * 16));
-            phn[1] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8 + 1) * (kTileRows * 16));
-          }
-          if (nf > 0) mbar_wait(&a_free[kb], (nf - 1) & 1);  // the previous dTheta block kb has been stored
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t pw[4] = {ph[c].x, ph[c].y, ph[c].z, ph[c].w};
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float d0 = __uint_as_float(v[c * 8 + 2 * j]) * cos_from_phase(pw[j] & 0xFFFFu);
-              const float d1 = __uint_as_float(v[c * 8 + 2 * j + 1]) * cos_from_phase(pw[j] >> 16);
-              o[j] = pack_bf16x2(d0, d1);
+            for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
+            ph[0] = phn[0];
+            ph[1] = phn[1];
+            if (kb + 1 < S::kKB) {
+              tmem_ld16(d_addr + (kb + 1) * 64, vn);
+              phn[0] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8) * (kTileRows * 16));
+              phn[1] = *reinterpret_cast<const uint4*>(ph_l + size_t((kb + 1) * 8 + 1) * (kTileRows * 16));
             }
-            sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c), make_uint4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t pw[4] = {ph[c].x, ph[c].y, ph[c].z, ph[c].w};
+              uint32_t o[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float d0 = __uint_as_float(v[c * 8 + 2 * jj]) * cos_from_phase(pw[jj] & 0xFFFFu);
+                const float d1 = __uint_as_float(v[c * 8 + 2 * jj + 1]) * cos_from_phase(pw[jj] >> 16);
+                o[jj] = pack_bf16x2(d0, d1);
+              }
+              sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c), make_uint4(o[0], o[1], o[2], o[3]));
+            }
           }
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[kb]);
+          if (lane == 0) mbar_arrive(&a_ready[j]);
         }
-        ++nf;
       }
     }
   }
@@ -305,7 +305,8 @@ int launch_siren_bwd(const b200inr_net* net, const void* packed, void* stash, in
   p.stash_dzo = reinterpret_cast<uint8_t*>(stash) + sl.dzo;
   p.layer_stride = sl.layer_stride;
   const int smem = BwdSmem<H>::kBytes + 1024;
-  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int pairs = (p.num_tiles + 1) / 2;
+  const int grid_x = pairs < num_sms ? pairs : num_sms;
   if (cudaFuncSetAttribute(siren_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
   siren_bwd_kernel<H><<<grid_x, kBwdThreads, smem, stream>>>(p);

@@ -2,17 +2,19 @@
 //
 // Replaces Siren.forward = nn.Sequential(SineLayer x (L+1), nn.Linear)  (reference INR/SRDWI.py:58-59,87-91).
 //
-// One persistent CTA per SM walks 128-row coordinate tiles.  Per tile every layer stays on chip:
+// One persistent CTA per SM walks PAIRS of 128-row coordinate tiles (X, Y).  Per tile every layer stays on chip:
 //   layer 0      : fp32 FMA on CUDA cores straight from the voxel index (get_mgrid never materialised),
 //   layers 1..L  : tcgen05.mma 128x256x256 (bf16 in, fp32 accumulate in TMEM), weights streamed from L2 by the
-//                  bulk-copy (TMA) engine into a 4-slot ring of 64-wide K chunks,
+//                  bulk-copy (TMA) engine into a 3-slot ring of 64-wide K chunks,
 //   epilogue     : tcgen05.ld -> +bias -> sin -> bf16 -> swizzled shared memory (the next layer's A operand),
 //   final linear : tcgen05.mma 128x32x256, +bias, optional clamp, coalesced fp32 store.
-// The epilogue produces the next layer's A operand one 64-wide K block at a time and signals each block on its own
-// mbarrier, and the accumulator is double buffered in TMEM (2 x 256 columns), so the MMAs of layer l+1 run underneath
-// the epilogue of layer l: per layer the tensor pipe is exposed only for its last K block.
-// In training mode the finished A blocks (sin outputs) are bulk-stored to the stash by a dedicated thread, 16-bit
-// phases are stored straight from registers, and layer 0 also emits the coordinate operand used by wgrad.cu.
+// The two tiles of a pair ping-pong: each owns one A tile in shared memory (2 x 64 KB) and one 256-column TMEM
+// accumulator, and the epilogue warps alternate X, Y, X, ... layer by layer, so the MMAs of tile X's next layer run
+// entirely underneath the epilogue of tile Y (and vice versa): the tensor pipe is never exposed and the epilogue
+// never waits for it in steady state.
+// In training mode the finished A tiles (sin outputs) are bulk-stored to the stash by a dedicated thread (overlapped
+// with the other tile's epilogue), 16-bit phases are stored straight from registers, and layer 0 also emits the
+// coordinate operand used by wgrad.cu.
 //
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
@@ -28,7 +30,7 @@ constexpr int kFwdFirstEpiWarp = 3;
 constexpr int kFwdThreads = (kFwdFirstEpiWarp + kFwdEpiWarps) * 32;  // 608
 constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;                   // 512
 constexpr uint32_t kEpiBarId = 1;
-constexpr int kFwdSlots = 4;
+constexpr int kFwdSlots = 3;
 
 struct FwdParams {
   const uint8_t* packed;
@@ -53,12 +55,9 @@ struct FwdSmem {
   static constexpr int kABlock = kTileRows * 128;    // bytes of one [128][64] bf16 block
   static constexpr int kABytes = kKB * kABlock;      // 64 KB for H = 256
   static constexpr int kSlotBytes = H * 128;         // one K chunk of a hidden layer: [H rows][64]
-  static constexpr int kOffA = 0;
-  static constexpr int kOffW = kABytes;
-  static constexpr int kOffW0 = kOffW + kFwdSlots * kSlotBytes;
-  static constexpr int kOffBias = kOffW0 + H * 16;
-  static constexpr int kOffXa = (kOffBias + (kMaxSineLayers * H + 32) * 4 + 1023) / 1024 * 1024;
-  static constexpr int kOffBar = kOffXa + kTileRows * 128;
+  static constexpr int kOffA = 0;                    // two A tiles
+  static constexpr int kOffW = 2 * kABytes;
+  static constexpr int kOffBar = kOffW + kFwdSlots * kSlotBytes;
   static constexpr int kBytes = kOffBar + 256;
 };
 
@@ -96,38 +95,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem + S::kOffA;
   uint8_t* w_smem = smem + S::kOffW;
-  float4* w0_smem = reinterpret_cast<float4*>(smem + S::kOffW0);
-  float* bias_smem = reinterpret_cast<float*>(smem + S::kOffBias);
-  uint8_t* xa_smem = smem + S::kOffXa;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;                     // [kFwdSlots]
-  uint64_t* w_empty = bars + kFwdSlots;        // [kFwdSlots]
-  uint64_t* a_ready = bars + 2 * kFwdSlots;    // [4]  K block kb of the next A operand is in shared memory
-  uint64_t* d_full = bars + 2 * kFwdSlots + 4;
-  uint64_t* a_free = bars + 2 * kFwdSlots + 5;  // [4] stash store of A block kb has been read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 9);
+  uint64_t* w_full = bars;                      // [kFwdSlots]
+  uint64_t* w_empty = bars + kFwdSlots;         // [kFwdSlots]
+  uint64_t* a_ready = bars + 2 * kFwdSlots;     // [2]  A operand of tile j complete in shared memory
+  uint64_t* d_full = bars + 2 * kFwdSlots + 2;  // [2]  accumulator of tile j complete in TMEM
+  uint64_t* a_free = bars + 2 * kFwdSlots + 4;  // [2]  stash store of A tile j has been read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int L = p.L;
 
-  // ---- one-time setup
-  for (int i = threadIdx.x; i < H; i += blockDim.x)
-    w0_smem[i] = reinterpret_cast<const float4*>(p.packed + p.pl.w0)[i];
-  for (int i = threadIdx.x; i < (L + 1) * H + 32; i += blockDim.x)
-    bias_smem[i] = reinterpret_cast<const float*>(p.packed + p.pl.bias)[i];
-  if (kStash) {  // zero once: only the coordinate chunk of every row is rewritten per tile
-    for (int i = threadIdx.x; i < kTileRows * 8; i += blockDim.x)
-      reinterpret_cast<uint4*>(xa_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFwdSlots; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kFwdEpiWarps);
-    mbar_init(d_full, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&a_ready[j], kFwdEpiWarps);
+      mbar_init(&d_full[j], 1);
+      mbar_init(&a_free[j], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -137,21 +126,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int num_pairs = (my_tiles + 1) / 2;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t c = 0;
-      for (int t = 0; t < my_tiles; ++t) {
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
         for (int l = 1; l <= L + 1; ++l) {
           const bool hidden = (l <= L);
           const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
           const uint32_t bytes = hidden ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
-          for (int kb = 0; kb < S::kKB; ++kb, ++c) {
-            const uint32_t slot = c % kFwdSlots, round = c / kFwdSlots;
-            if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
-            mbar_arrive_expect_tx(&w_full[slot], bytes);
-            bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[slot]);
+          for (int j = 0; j < nt; ++j) {
+            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+              const uint32_t slot = c % kFwdSlots, round = c / kFwdSlots;
+              if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+              mbar_arrive_expect_tx(&w_full[slot], bytes);
+              bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[slot]);
+            }
           }
         }
       }
@@ -162,49 +155,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      uint32_t c = 0, n = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        for (int l = 1; l <= L + 1; ++l, ++n) {
+      uint32_t c = 0, na[2] = {0, 0};
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int l = 1; l <= L + 1; ++l) {
           const uint32_t idesc = (l <= L) ? idesc_bf16(128, H, false, false) : idesc_bf16(128, kOutPad, false, false);
-          const uint32_t d_addr = tmem_d + uint32_t(l & 1) * 256;
-          for (int kb = 0; kb < S::kKB; ++kb, ++c) {
-            const uint32_t slot = c % kFwdSlots;
-            mbar_wait(&a_ready[kb], n & 1);
-            mbar_wait(&w_full[slot], (c / kFwdSlots) & 1);
+          for (int j = 0; j < nt; ++j) {
+            mbar_wait(&a_ready[j], na[j] & 1);
+            ++na[j];
             tc_fence_after();
+            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+              const uint32_t slot = c % kFwdSlots;
+              mbar_wait(&w_full[slot], (c / kFwdSlots) & 1);
+              tc_fence_after();
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
-              const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-              umma_bf16_ss(d_addr, da, db, idesc, (kb | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
+                const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+                umma_bf16_ss(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+              }
+              umma_commit(&w_empty[slot]);
             }
-            umma_commit(&w_empty[slot]);
+            umma_commit(&d_full[j]);
           }
-          umma_commit(d_full);
         }
       }
     }
   } else if (warp == 2) {
     // =============================== stash store (training) ===============================
     if (kStash && lane == 0) {
-      uint32_t n = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int tile = int(blockIdx.x) + t * int(gridDim.x);
-        uint8_t* y_tile = p.stash_y + size_t(tile) * S::kABytes;
-        for (int l = 0; l <= L; ++l, ++n) {
-          for (int kb = 0; kb < S::kKB; ++kb) {
-            mbar_wait(&a_ready[kb], n & 1);
-            bulk_s2g(y_tile + size_t(l) * p.stash_layer_stride + size_t(kb) * S::kABlock, a_smem + kb * S::kABlock,
-                     S::kABlock);
-            if (l == 0 && kb == 0) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
+      uint32_t na[2] = {0, 0};
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int l = 0; l <= L; ++l) {
+          for (int j = 0; j < nt; ++j) {
+            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            mbar_wait(&a_ready[j], na[j] & 1);
+            ++na[j];
+            bulk_s2g(p.stash_y + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes,
+                     a_smem + j * S::kABytes, S::kABytes);
             bulk_commit();
-            if (kb > 0) {  // the previous block's group has been read out of shared memory
-              bulk_wait_read1();
-              mbar_arrive(&a_free[kb - 1]);
-            }
+            bulk_wait_read0();
+            mbar_arrive(&a_free[j]);
           }
-          bulk_wait_read0();
-          mbar_arrive(&a_free[S::kKB - 1]);
         }
       }
       bulk_wait0();
@@ -216,117 +209,136 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     const int s = (warp - kFwdFirstEpiWarp) >> 2;        // 16-column slice inside every 64-wide K block
     const int r = q * 32 + lane;                         // row inside the tile
     const uint32_t t_lane = uint32_t(q * 32) << 16;
-    const uint32_t a_addr = smem_u32(a_smem);
-    uint32_t n = 0, nf = 0;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int tile = int(blockIdx.x) + t * int(gridDim.x);
-      const long long row0 = (long long)tile * kTileRows;
-      uint8_t* ph_row = kStash ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
+    const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
+    const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
+    uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
+    for (int pr = 0; pr < num_pairs; ++pr) {
+      const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
 
-      // ---- layer 0 on CUDA cores
-      {
+      // ---- layer 0 on CUDA cores, both tiles
+      for (int j = 0; j < nt; ++j) {
+        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const long long row0 = (long long)tile * kTileRows;
+        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        uint8_t* ph_row = kStash ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
         float x[4];
         if (p.coords != nullptr) {
           long long row = row0 + r;
           if (row >= p.rows) row = p.rows - 1;
           x[0] = x[1] = x[2] = x[3] = 0.0f;
-          for (int j = 0; j < p.d; ++j) x[j] = p.coords[row * p.d + j];
+          for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
         } else {
           grid_coords(p.grid, row0 + r, x);
         }
-        if (kStash && s == 0) {  // x = hi + lo in bf16 (exact to 2^-17): B operand of dW_0 = dTheta_0^T X
-          float hi[4], lo[4];
+        if (kStash) {  // coordinate operand of dW_0: x = hi + lo in bf16 (exact to 2^-17), the other 56 columns zero
+          uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
+          uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
+          if (s == 0) {
+            float hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            hi[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
-            lo[j] = x[j] - hi[j];
+            for (int jj = 0; jj < 4; ++jj) {
+              hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
+              lo[jj] = x[jj] - hi[jj];
+            }
+            c0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
+                            pack_bf16x2(lo[2], lo[3]));
           }
-          sts128(smem_u32(xa_smem) + sw128_chunk_off(r, 0),
-                 make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
-                            pack_bf16x2(lo[2], lo[3])));
+          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = c0;
+          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll 1
         for (int kb = 0; kb < S::kKB; ++kb) {
           const int col0 = kb * 64 + s * 16;
           float th[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 w = w0_smem[col0 + j];
-            float acc = bias_smem[col0 + j];
+          for (int jj = 0; jj < 16; ++jj) {
+            const float4 w = __ldg(w0_g + col0 + jj);
+            float acc = __ldg(bias_g + col0 + jj);
             acc = fmaf(x[0], w.x, acc);
             acc = fmaf(x[1], w.y, acc);
             acc = fmaf(x[2], w.z, acc);
             acc = fmaf(x[3], w.w, acc);
-            th[j] = acc;
+            th[jj] = acc;
           }
           emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
                               kStash ? ph_row + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[kb]);
         }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[j]);
       }
 
-      // ---- hidden layers
+      // ---- hidden layers: X, Y, X, Y, ...
       for (int l = 1; l <= L; ++l) {
-        mbar_wait(d_full, n & 1);
-        ++n;
-        tc_fence_after();
-        const uint32_t bl_addr = smem_u32(bias_smem + l * H);
-        const uint32_t d_addr = tmem_d + t_lane + uint32_t(l & 1) * 256 + s * 16;
-        uint8_t* ph_l = kStash ? ph_row + size_t(l) * p.stash_layer_stride : nullptr;
-        uint32_t v[16], vn[16];
-        tmem_ld16(d_addr, vn);
-#pragma unroll
-        for (int kb = 0; kb < S::kKB; ++kb) {
-          const int col0 = kb * 64 + s * 16;
-          uint4 bq[4];  // biases of this slice: issued before the TMEM wait so both latencies overlap
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) bq[j4] = lds128(bl_addr + uint32_t(col0 + j4 * 4) * 4);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = vn[j];
-          if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
-          float th[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + __uint_as_float(bq[j4].x);
-            th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + __uint_as_float(bq[j4].y);
-            th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + __uint_as_float(bq[j4].z);
-            th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + __uint_as_float(bq[j4].w);
+        for (int j = 0; j < nt; ++j) {
+          const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+          const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+          const float* bl = bias_g + l * H;
+          const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
+          uint8_t* ph_l = kStash ? p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes +
+                                       size_t(r) * 16
+                                 : nullptr;
+          mbar_wait(&d_full[j], nd[j] & 1);
+          ++nd[j];
+          if (kStash) {
+            mbar_wait(&a_free[j], nf[j] & 1);
+            ++nf[j];
           }
-          if (kStash) mbar_wait(&a_free[kb], nf & 1);  // the stash store of this block (previous layer) has been read
-          emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
-                              kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
+          tc_fence_after();
+          uint32_t v[16], vn[16];
+          tmem_ld16(d_addr, vn);
+#pragma unroll
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            const int col0 = kb * 64 + s * 16;
+            float4 bq[4];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
+            if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
+            float th[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bq[j4].x;
+              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bq[j4].y;
+              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bq[j4].z;
+              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bq[j4].w;
+            }
+            emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
+                                kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
+          }
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[kb]);
+          if (lane == 0) mbar_arrive(&a_ready[j]);
         }
-        ++nf;
       }
 
       // ---- final linear: D[:, 0:32) + bias -> out
-      {
-        mbar_wait(d_full, n & 1);
-        ++n;
+      for (int j = 0; j < nt; ++j) {
+        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const long long row0 = (long long)tile * kTileRows;
+        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        mbar_wait(&d_full[j], nd[j] & 1);
+        ++nd[j];
         if (kStash) {
-          for (int kb = 0; kb < S::kKB; ++kb) mbar_wait(&a_free[kb], nf & 1);
-          ++nf;
+          mbar_wait(&a_free[j], nf[j] & 1);
+          ++nf[j];
         }
         tc_fence_after();
         // the A tile is free (its MMAs and stash stores are done): reuse it as the fp32 output staging area
         const int C = p.C;
         if (s == 0) {
           uint32_t v[32];
-          tmem_ld32(tmem_d + t_lane + uint32_t((L + 1) & 1) * 256, v);
+          tmem_ld32(tmem_d + t_lane + uint32_t(j) * 256, v);
           tmem_ld_wait();
-          const float* bf = bias_smem + (L + 1) * H;
+          const float* bf = bias_g + (L + 1) * H;
 #pragma unroll
           for (int c = 0; c < kOutPad; ++c) {
             if (c < C) {
-              float o = __uint_as_float(v[c]) + bf[c];
+              float o = __uint_as_float(v[c]) + __ldg(bf + c);
               if (p.clamp) o = fmaxf(o, p.clamp_min);
               sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
             }
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         const int nout = int(valid) * C;
         float* dst = p.out + row0 * C;
         for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
-        named_bar_sync(kEpiBarId, kFwdEpiThreads);  // staging consumed before the next tile overwrites A
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);  // staging consumed before the next pair overwrites A
       }
     }
   }
@@ -383,7 +395,9 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
     p.stash_layer_stride = sl.layer_stride;
   }
   const int smem = FwdSmem<H>::kBytes + 1024;
-  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  // persistent CTAs walk tile pairs: do not launch more CTAs than there are pairs
+  const int pairs = (p.num_tiles + 1) / 2;
+  const int grid_x = pairs < num_sms ? pairs : num_sms;
   cudaError_t e;
   if (stash) {
     e = cudaFuncSetAttribute(siren_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
