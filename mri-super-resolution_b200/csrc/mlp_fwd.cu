@@ -19,6 +19,7 @@
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -360,6 +361,341 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   if (warp == 1) tmem_dealloc<512>(tmem_d);
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs on an SM pair run the kernel above in lock step and issue every MMA as ONE tcgen05.mma.cta_group::2 of
+// M = 256 (each CTA's own 128 rows) x N = 256: each CTA stages only ITS half of every weight chunk (the B rows of 128
+// of the 256 output features), so per SM the weight-chunk traffic from L2, the shared-memory writes of the ring and
+// the B-operand reads of the tensor core all halve, and the ring gets 6 slots of 16 KB.  The leader CTA's MMA thread waits for both
+// CTAs' A tiles (remote mbarrier arrives) and both weight halves (the peer's MMA warp relays its ring barrier), and
+// commits with a multicast arrive to both CTAs.
+constexpr int kFwd2Slots = 6;
+
+template <int H>
+struct Fwd2Smem {
+  static constexpr int kKB = H / 64;
+  static constexpr int kABlock = kTileRows * 128;
+  static constexpr int kABytes = kKB * kABlock;
+  static constexpr int kSlotBytes = (H / 2) * 128;  // this CTA's half of a K chunk: [H/2 rows][64]
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = 2 * kABytes;
+  static constexpr int kOffBar = kOffW + kFwd2Slots * kSlotBytes;
+  static constexpr int kBytes = kOffBar + 512;
+};
+
+template <int H, bool kStash>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1) siren_fwd2_kernel(const FwdParams p) {
+  using S = Fwd2Smem<H>;
+  static_assert(S::kKB == 4, "epilogue slicing assumes 4 K blocks");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem + S::kOffA;
+  uint8_t* w_smem = smem + S::kOffW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* w_full = bars;                       // [kFwd2Slots] this CTA's half chunk landed
+  uint64_t* w_peer = bars + kFwd2Slots;          // [kFwd2Slots] (leader) the peer's half chunk landed
+  uint64_t* w_empty = bars + 2 * kFwd2Slots;     // [kFwd2Slots] MMAs reading the slot done (multicast commit)
+  uint64_t* a_ready = bars + 3 * kFwd2Slots;     // [2] this CTA's A tile j complete (own stash-store thread)
+  uint64_t* a_pair = bars + 3 * kFwd2Slots + 2;  // [2] (leader) A tile j complete in BOTH CTAs
+  uint64_t* d_full = bars + 3 * kFwd2Slots + 4;  // [2] accumulator j complete (multicast commit)
+  uint64_t* a_free = bars + 3 * kFwd2Slots + 6;  // [2] stash store of A tile j read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kFwd2Slots + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int L = p.L;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFwd2Slots; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_peer[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&a_ready[j], kFwdEpiWarps);
+      mbar_init(&a_pair[j], 2 * kFwdEpiWarps);
+      mbar_init(&d_full[j], 1);
+      mbar_init(&a_free[j], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  // both CTAs of a pair run the slot count of the leader (even block index, which never has fewer tiles)
+  const int lead_block = int(blockIdx.x) & ~1;
+  const int my_tiles = (p.num_tiles - lead_block + int(gridDim.x) - 1) / int(gridDim.x);
+  const int num_pairs = (my_tiles + 1) / 2;
+
+  if (warp == 0) {
+    // =============================== weight producer: this CTA's half of every chunk ===============================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int l = 1; l <= L + 1; ++l) {
+          const bool hidden = (l <= L);
+          const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
+          const uint32_t chunk = hidden ? uint32_t(H * 128) : uint32_t(kOutPad * 128);
+          const uint32_t bytes = chunk / 2;
+          for (int j = 0; j < nt; ++j) {
+            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+              const uint32_t slot = c % kFwd2Slots, round = c / kFwd2Slots;
+              if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+              mbar_arrive_expect_tx(&w_full[slot], bytes);
+              bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * chunk + size_t(rank) * bytes, bytes,
+                       &w_full[slot]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (leader) {
+        // =============================== MMA issuer (leader CTA) ===============================
+        const uint64_t hi = smem_desc_hi_sw128(0, 1024);
+        const uint32_t a_base = smem_u32(a_smem);
+        const uint32_t w_base = smem_u32(w_smem);
+        uint32_t c = 0, na[2] = {0, 0};
+        for (int pr = 0; pr < num_pairs; ++pr) {
+          const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+          for (int l = 1; l <= L + 1; ++l) {
+            const uint32_t idesc = (l <= L) ? idesc_bf16(256, H, false, false) : idesc_bf16(256, kOutPad, false, false);
+            for (int j = 0; j < nt; ++j) {
+              mbar_wait_cluster(&a_pair[j], na[j] & 1);
+              ++na[j];
+              tc_fence_after();
+              for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+                const uint32_t slot = c % kFwd2Slots;
+                mbar_wait(&w_full[slot], (c / kFwd2Slots) & 1);
+                mbar_wait_cluster(&w_peer[slot], (c / kFwd2Slots) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
+                  const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+                  umma_bf16_ss_2cta(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+                }
+                umma_commit_2cta(&w_empty[slot]);
+              }
+              umma_commit_2cta(&d_full[j]);
+            }
+          }
+        }
+      } else {
+        // =============================== relay (peer CTA): my half chunk landed -> tell the leader ===================
+        uint32_t c = 0;
+        for (int pr = 0; pr < num_pairs; ++pr) {
+          const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+          for (int l = 1; l <= L + 1; ++l) {
+            for (int j = 0; j < nt; ++j) {
+              for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+                const uint32_t slot = c % kFwd2Slots;
+                mbar_wait(&w_full[slot], (c / kFwd2Slots) & 1);
+                mbar_arrive_remote(&w_peer[slot], 0);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =============================== stash store (training) ===============================
+    if (kStash && lane == 0) {
+      uint32_t na[2] = {0, 0};
+      for (int pr = 0; pr < num_pairs; ++pr) {
+        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int l = 0; l <= L; ++l) {
+          for (int j = 0; j < nt; ++j) {
+            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            mbar_wait(&a_ready[j], na[j] & 1);
+            ++na[j];
+            if (tile < p.num_tiles) {
+              bulk_s2g(p.stash_y + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes,
+                       a_smem + j * S::kABytes, S::kABytes);
+              bulk_commit();
+              bulk_wait_read0();
+            }
+            mbar_arrive(&a_free[j]);
+          }
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= kFwdFirstEpiWarp) {
+    // =============================== epilogue warps ===============================
+    const int et = threadIdx.x - kFwdFirstEpiWarp * 32;
+    const int q = warp & 3;
+    const int s = (warp - kFwdFirstEpiWarp) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = uint32_t(q * 32) << 16;
+    const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
+    const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
+    uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
+    // A tile j of this CTA is complete: own stash thread (local) and the leader's MMA thread (pair barrier)
+    auto publish = [&](int j) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_ready[j]);
+        mbar_arrive_remote(&a_pair[j], 0);
+      }
+    };
+    for (int pr = 0; pr < num_pairs; ++pr) {
+      const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+
+      // ---- layer 0 on CUDA cores, both tiles
+      for (int j = 0; j < nt; ++j) {
+        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const bool active = tile < p.num_tiles;  // the peer of a pair may run a slot without a tile of its own
+        const long long row0 = (long long)tile * kTileRows;
+        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        uint8_t* ph_row = (kStash && active) ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
+        float x[4];
+        if (p.coords != nullptr) {
+          long long row = row0 + r;
+          if (row >= p.rows) row = p.rows - 1;
+          x[0] = x[1] = x[2] = x[3] = 0.0f;
+          for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
+        } else {
+          grid_coords(p.grid, row0 + r, x);
+        }
+        if (kStash && active) {
+          uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
+          uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
+          if (s == 0) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
+              lo[jj] = x[jj] - hi[jj];
+            }
+            c0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
+                            pack_bf16x2(lo[2], lo[3]));
+          }
+          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = c0;
+          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < S::kKB; ++kb) {
+          const int col0 = kb * 64 + s * 16;
+          float th[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float4 w = __ldg(w0_g + col0 + jj);
+            float acc = __ldg(bias_g + col0 + jj);
+            acc = fmaf(x[0], w.x, acc);
+            acc = fmaf(x[1], w.y, acc);
+            acc = fmaf(x[2], w.z, acc);
+            acc = fmaf(x[3], w.w, acc);
+            th[jj] = acc;
+          }
+          if (kStash && active)
+            emit_sine16<true>(th, a_addr + kb * S::kABlock, r, s, ph_row + size_t(kb * 8 + 2 * s) * (kTileRows * 16));
+          else
+            emit_sine16<false>(th, a_addr + kb * S::kABlock, r, s, nullptr);
+        }
+        publish(j);
+      }
+
+      // ---- hidden layers: X, Y, X, Y, ...
+      for (int l = 1; l <= L; ++l) {
+        for (int j = 0; j < nt; ++j) {
+          const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+          const bool active = tile < p.num_tiles;
+          const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+          const float* bl = bias_g + l * H;
+          const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
+          uint8_t* ph_l = (kStash && active) ? p.stash_ph + size_t(l) * p.stash_layer_stride +
+                                                   size_t(tile) * S::kABytes + size_t(r) * 16
+                                             : nullptr;
+          mbar_wait(&d_full[j], nd[j] & 1);
+          ++nd[j];
+          if (kStash) {
+            mbar_wait(&a_free[j], nf[j] & 1);
+            ++nf[j];
+          }
+          tc_fence_after();
+          uint32_t v[16], vn[16];
+          tmem_ld16(d_addr, vn);
+#pragma unroll
+          for (int kb = 0; kb < S::kKB; ++kb) {
+            const int col0 = kb * 64 + s * 16;
+            float4 bq[4];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
+            if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
+            float th[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bq[j4].x;
+              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bq[j4].y;
+              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bq[j4].z;
+              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bq[j4].w;
+            }
+            if (kStash && active)
+              emit_sine16<true>(th, a_addr + kb * S::kABlock, r, s, ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16));
+            else
+              emit_sine16<false>(th, a_addr + kb * S::kABlock, r, s, nullptr);
+          }
+          publish(j);
+        }
+      }
+
+      // ---- final linear: D[:, 0:32) + bias -> out
+      for (int j = 0; j < nt; ++j) {
+        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const long long row0 = (long long)tile * kTileRows;
+        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        mbar_wait(&d_full[j], nd[j] & 1);
+        ++nd[j];
+        if (kStash) {
+          mbar_wait(&a_free[j], nf[j] & 1);
+          ++nf[j];
+        }
+        tc_fence_after();
+        const int C = p.C;
+        if (s == 0) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + t_lane + uint32_t(j) * 256, v);
+          tmem_ld_wait();
+          const float* bf = bias_g + (L + 1) * H;
+#pragma unroll
+          for (int c = 0; c < kOutPad; ++c) {
+            if (c < C) {
+              float o = __uint_as_float(v[c]) + __ldg(bf + c);
+              if (p.clamp) o = fmaxf(o, p.clamp_min);
+              sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
+            }
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);
+        long long valid = p.rows - row0;
+        if (valid > kTileRows) valid = kTileRows;
+        if (valid < 0) valid = 0;
+        const int nout = int(valid) * C;
+        float* dst = p.out + row0 * C;
+        for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still address it
+  if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
+}
+
 // ------------------------------------------------------------------ launcher
 int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
                      int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
@@ -394,11 +730,31 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
     p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
   }
-  const int smem = FwdSmem<H>::kBytes + 1024;
   // persistent CTAs walk tile pairs: do not launch more CTAs than there are pairs
   const int pairs = (p.num_tiles + 1) / 2;
-  const int grid_x = pairs < num_sms ? pairs : num_sms;
   cudaError_t e;
+  // The CTA-pair kernel is bit-identical but measured slower than the 1-CTA ping-pong (query 0.91 vs 0.77 ms on cfg2:
+  // the lock step couples the two CTAs' epilogues and the epilogue, not shared-memory bandwidth, is the limiter), so
+  // it is opt-in: B200INR_FWD_2CTA=1.
+  const char* env2 = getenv("B200INR_FWD_2CTA");
+  const bool use_2cta = env2 != nullptr && env2[0] == '1';
+  if (use_2cta && pairs >= 2) {  // CTA-pair kernel: an even number of CTAs, at most one per SM
+    int g2 = pairs < num_sms ? pairs : num_sms;
+    g2 &= ~1;
+    const int smem2 = Fwd2Smem<H>::kBytes + 1024;
+    if (stash) {
+      e = cudaFuncSetAttribute(siren_fwd2_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return B200INR_ERR_CUDA;
+      siren_fwd2_kernel<H, true><<<g2, kFwdThreads, smem2, stream>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(siren_fwd2_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return B200INR_ERR_CUDA;
+      siren_fwd2_kernel<H, false><<<g2, kFwdThreads, smem2, stream>>>(p);
+    }
+    return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+  }
+  const int smem = FwdSmem<H>::kBytes + 1024;
+  const int grid_x = pairs < num_sms ? pairs : num_sms;
   if (stash) {
     e = cudaFuncSetAttribute(siren_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return B200INR_ERR_CUDA;
