@@ -562,3 +562,25 @@ def test_wire_fused_fit_matches_module_loop(dev):
         lb.append(ls.item())
     np.testing.assert_allclose(la, lb, rtol=5e-3)
     assert _relerr(a.query(shape, clamp_min=None).cpu().numpy(), b.query(shape, clamp_min=None).cpu().numpy()) < 1e-2
+
+
+def test_cta_pair_forward_is_bit_identical(dev):
+    """The opt-in cta_group::2 forward (B200INR_FWD_2CTA=1: one tcgen05.mma of M = 256 per CTA pair, weight chunks
+    split between the two CTAs) produces exactly the bits of the default 1-CTA kernel, query and training mode."""
+    torch.manual_seed(41)
+    m = b200inr.Siren(3, 256, 4, 31).to(dev)
+    shape = (40, 33, 29)  # 38 280 rows: ragged tile count, odd number of tiles per CTA pair
+    rows = int(np.prod(shape))
+    base = m.query(shape, clamp_min=None)
+    out1, st1 = m._forward_rows(None, L.make_grid(shape), rows, train=True)
+    os.environ["B200INR_FWD_2CTA"] = "1"
+    try:
+        pair = m.query(shape, clamp_min=None)
+        out2, st2 = m._forward_rows(None, L.make_grid(shape), rows, train=True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B200INR_FWD_2CTA"]
+    assert torch.equal(pair, base)
+    assert torch.equal(out2, out1)
+    n_y_ph = 2 * 5 * ((rows + 127) // 128) * 128 * 256 * 2  # y and phase sections of the stash
+    assert torch.equal(st2[:n_y_ph], st1[:n_y_ph])
