@@ -291,7 +291,7 @@ class _FusedMLP(nn.Module):
 
     # ---------------------------------------------------------------- fused fit
     def fit(self, target, shape, steps, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
-            global_count=None, process_group=None, reset_optimizer=False):
+            global_count=None, process_group=None, reset_optimizer=False, graph=None):
         """The reference training loop (INR/superresDWI.py:132-138) on a dense coordinate grid, without autograd:
         per step  fused forward -> loss (+ LR degradation) -> fused backward -> [all-reduce] -> Adam -> re-stage bf16.
 
@@ -305,7 +305,14 @@ class _FusedMLP(nn.Module):
         session = FitSession(self, target, shape, lr=lr, degrade=degrade, betas=betas, eps=eps, row_range=row_range,
                              global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer)
         losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
-        for it in range(steps):
+        if graph is None:  # small per-step work is launch-latency bound: replay the step as one CUDA graph
+            graph = process_group is None and steps >= 16 and session.rows <= (1 << 18)
+        done = 0
+        if graph:
+            losses[0:1].copy_(session.step())  # one eager step (lazy initialisation, allocator warm-up)
+            done = 1
+            session.capture()
+        for it in range(done, steps):
             losses[it:it + 1].copy_(session.step())
         session.finish()
         return losses
@@ -551,12 +558,31 @@ class FitSession:
         self.dpred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.stash = _aligned_bytes(_lib.stash_bytes(module._desc, rows), dev)
         self.kernel_launches_per_step = 7  # forward, loss, dgrad, wgrad, adam, adam_tick, pack
+        self._graph = None
+
+    def capture(self):
+        """Capture one step (memset + 7 kernels, all stream-ordered, Adam's step counter on the device) into a CUDA
+        graph; later step() calls replay it.  Not used with a process group (the all-reduce stays eager)."""
+        if self.process_group is not None:
+            raise RuntimeError("b200inr: graph capture of a multi-GPU step is not supported")
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager(None)
+            self._graph = g
 
     def set_target(self, target):
         """Replace the target values (same size), e.g. from pinned host memory."""
         self.target.copy_(target.reshape(-1), non_blocking=True)
 
     def step(self, marks=None):
+        if self._graph is not None and marks is None:
+            self._graph.replay()
+            return self.loss
+        return self._step_eager(marks)
+
+    def _step_eager(self, marks=None):
         m, eng, lib = self.module, self.eng, self.lib
         net, gref = ctypes.byref(m._desc), ctypes.byref(self.grid)
         rows, C = self.rows, self.C

@@ -31,10 +31,15 @@ def timed(fn, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def fit_line(name, model, target, shape, degrade, lr, flop_per_row, steps):
+def fit_line(name, model, target, shape, degrade, lr, flop_per_row, steps, graph=False):
     rows = int(np.prod(shape))
     sess = b200inr.FitSession(model, target, shape, lr=lr, degrade=degrade)
     ms = timed(sess.step, steps)
+    ms_graph = None
+    if graph:
+        sess.capture()
+        ms_graph = timed(sess.step, steps)
+        sess._graph = None
     marks = []
     sess.step(marks)
     torch.cuda.synchronize()
@@ -42,7 +47,9 @@ def fit_line(name, model, target, shape, degrade, lr, flop_per_row, steps):
     tf = flop_per_row * rows / (ms * 1e-3) / 1e12
     return {"config": name, "metric": "inr_train_coord_samples_per_s", "value": rows / (ms * 1e-3), "ms_per_step": ms,
             "rows": rows, "tflops_algorithmic": tf, "frac_of_sustained_peak": tf / PEAK["bf16_tflops_sustained"],
-            "frac_of_burst_peak": tf / PEAK["bf16_tflops"], "stage_ms": st, "final_loss": float(sess.loss.item())}
+            "frac_of_burst_peak": tf / PEAK["bf16_tflops"], "stage_ms": st, "final_loss": float(sess.loss.item()),
+            "ms_per_step_cuda_graph": ms_graph,
+            "value_cuda_graph": (rows / (ms_graph * 1e-3)) if ms_graph else None}
 
 
 def query_line(name, model, shape, flop_per_row, steps):
@@ -65,7 +72,8 @@ def main():
     # cfg1: SIREN 2D slice fit 256x256, 3x256 hidden (Siren(2,256,2,1)), lr 3e-4
     m = b200inr.Siren(2, 256, 2, 1).to(dev)
     tgt = torch.rand(256 * 256, 1, device=dev)
-    lines.append(fit_line("cfg1 SIREN 2->3x256->1, 256x256 slice", m, tgt, (256, 256), None, 3e-4, 790016, a.steps * 5))
+    lines.append(fit_line("cfg1 SIREN 2->3x256->1, 256x256 slice", m, tgt, (256, 256), None, 3e-4, 790016, a.steps * 5,
+                          graph=True))
     # cfg2: SIREN 3D DWI fit with 2x LR-consistency loss
     hr_shape = (128, 128, 64)
     lr_t = torch.rand(64 * 64 * 64, 31, device=dev)
