@@ -54,7 +54,15 @@ typedef struct b200inr_net {
   int32_t input_mode;      /* B200INR_IN_*                                                                   */
   int32_t mapping_size;    /* m of input_mapping (IN_FOURIER only; 2m a multiple of 64, <= H), else 0         */
   float scale_0;           /* s0 of the Gabor window (ACT_GABOR only), else 0                                */
+  int32_t flags;           /* B200INR_NET_* bits, 0 by default                                               */
 } b200inr_net;
+
+/* SIREN on raw coordinates (IN_COORDS) trains through ONE layer-pipelined backward kernel whose only HBM stream is
+ * the 16-bit phase stash (b200inr_siren_backward).  This bit selects the older staged path instead: forward stashes
+ * sin outputs + phases, b200inr_siren_dgrad writes every dL/dtheta, b200inr_siren_wgrad contracts them (the two
+ * calls b200inr_siren_backward then makes).  The stash layout differs, so forward, backward and
+ * b200inr_stash_bytes must see the same flag.  Ignored by the other network families (always staged). */
+#define B200INR_NET_STAGED_BWD 1
 
 /* Dense coordinate grid == get_mgrid(shape) (INR/SRDWI.py:12-18) restricted to linear rows
  * [row_begin, row_begin + rows).  Coordinates are never materialised; kernels derive them from the index. */
@@ -109,7 +117,8 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
                            const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
                            void* stream);
 
-/* The two kernels of b200inr_siren_backward as separate calls (same arguments; backward == dgrad then wgrad):
+/* The two kernels of the STAGED b200inr_siren_backward as separate calls (same arguments; backward == dgrad then
+ * wgrad).  B200INR_ERR_BAD_SHAPE for a pipelined SIREN (no B200INR_NET_STAGED_BWD): its backward is one kernel.
  * dgrad: activation-gradient chain, fills the stash with dL/dtheta of every sine layer and the bf16 dL/dout tile;
  * wgrad: contracts the stash over the rows and ACCUMULATES into grad_params. */
 int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200inr.so")
 MAX_TAPS = 8
 ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2
 IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
+DEFAULT_PIPED_BWD = "0"  # host default until the pipelined kernel beats the staged pair on the bench
+NET_STAGED_BWD = 1  # B200INR_NET_STAGED_BWD: the older forward-stash / dgrad / wgrad training path of raw-coordinate SIRENs
 
 
 class Net(ctypes.Structure):
@@ -30,6 +32,7 @@ class Net(ctypes.Structure):
         ("input_mode", ctypes.c_int32),
         ("mapping_size", ctypes.c_int32),
         ("scale_0", ctypes.c_float),
+        ("flags", ctypes.c_int32),
     ]
 
 
@@ -98,9 +101,11 @@ def check(code, what):
 
 
 def make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.0, hidden_omega_0=30.0,
-             activation=ACT_SINE, input_mode=IN_COORDS, mapping_size=0, scale_0=0.0):
+             activation=ACT_SINE, input_mode=IN_COORDS, mapping_size=0, scale_0=0.0, flags=None):
+    if flags is None:  # B200INR_PIPED_BWD=1/0 selects the pipelined / staged backward of SIRENs built afterwards (A/B runs)
+        flags = 0 if os.environ.get("B200INR_PIPED_BWD", DEFAULT_PIPED_BWD) == "1" else NET_STAGED_BWD
     return Net(int(in_features), int(hidden_features), int(hidden_layers), int(out_features), float(first_omega_0),
-               float(hidden_omega_0), int(activation), int(input_mode), int(mapping_size), float(scale_0))
+               float(hidden_omega_0), int(activation), int(input_mode), int(mapping_size), float(scale_0), int(flags))
 
 
 def make_grid(shape, row_begin=0):

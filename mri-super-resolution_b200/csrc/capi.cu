@@ -14,6 +14,9 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
                      cudaStream_t stream);
 int launch_siren_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
                      int num_sms, cudaStream_t stream);
+int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, const float* coords,
+                      const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params, int num_sms,
+                      cudaStream_t stream);
 int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords, const b200inr_grid* grid,
                        int64_t rows, float* grad_params, int num_sms, cudaStream_t stream);
 int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
@@ -44,6 +47,10 @@ int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float
 
 static bool is_gen(const b200inr_net* net) { return net->input_mode != B200INR_IN_COORDS; }
 static bool is_wire(const b200inr_net* net) { return net->activation == B200INR_ACT_GABOR; }
+// SIREN on raw coordinates trained through the layer-pipelined backward (mlp_bwdp.cu) unless the staged path is asked for
+static bool is_piped(const b200inr_net* net) {
+  return !is_gen(net) && !is_wire(net) && (net->flags & B200INR_NET_STAGED_BWD) == 0;
+}
 
 static int check_net(const b200inr_net* net) {
   if (!net) return B200INR_ERR_NULL;
@@ -180,9 +187,14 @@ int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes) {
   if (e) return e;
   if (!bytes) return B200INR_ERR_NULL;
   if (rows < 0) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) {
+    *bytes = 0;
+    return B200INR_OK;
+  }
   *bytes = is_wire(net) ? make_wire_stash_layout(make_wire_dims(net), rows).total
            : is_gen(net) ? make_gen_stash_layout(make_gen_dims(net), rows).total
-                         : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
+           : is_piped(net) ? make_pipe_stash_layout(net->hidden_features, net->hidden_layers, rows).total
+                           : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
   return B200INR_OK;
 }
 
@@ -234,6 +246,8 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
     if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
   }
+  if (is_piped(net) && !aligned16(grad_out)) return B200INR_ERR_BAD_ALIGN;  // dOut tiles are bulk-copied
+  if (is_piped(net)) return launch_siren_bwdp(net, packed, stash, coords, grid, rows, grad_out, grad_params, sms, s);
   if ((e = launch_siren_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, s);
 }
@@ -243,6 +257,7 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
   int e = check_net(net);
   if (e) return e;
   if (!packed || !stash || !grad_out) return B200INR_ERR_NULL;
+  if (is_piped(net)) return B200INR_ERR_BAD_SHAPE;  // one-kernel backward: use b200inr_siren_backward
   if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023))
@@ -259,6 +274,7 @@ int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords
   int e = check_net(net);
   if (e) return e;
   if (!stash || !grad_params) return B200INR_ERR_NULL;
+  if (is_piped(net)) return B200INR_ERR_BAD_SHAPE;  // one-kernel backward: use b200inr_siren_backward
   if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
   if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;

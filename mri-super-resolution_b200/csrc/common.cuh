@@ -76,6 +76,46 @@ __host__ __device__ inline StashLayout make_stash_layout(int H, int L, int64_t r
   return s;
 }
 
+// Stash of the pipelined SIREN training path (mlp_bwdp.cu): only the 16-bit phases go to HBM; the rest is the
+// L2-resident ring storage of the layer pipelines and their flag counters.
+constexpr int kPipeTileRows = 64;    // rows per pipeline tile (half a forward tile)
+constexpr int kPipeRing = 8;         // ring depth, in tiles, per layer boundary
+constexpr int kPipeMaxEdges = 96;    // pipelines x (L+1) <= #SM / 2
+struct PipeStashLayout {
+  size_t ph;            // (L+1) x T x [H/8][128][8] u16
+  size_t layer_stride;  // bytes per layer inside ph
+  size_t xa;            // T x 128 rows x 16 bytes: coordinates as bf16 {hi x4, lo x4} (operand of dW_0)
+  size_t ring;          // kPipeMaxEdges x kPipeRing x [64 rows x H bf16]
+  size_t flags;         // kPipeMaxEdges x 4 counters, 128 bytes apart
+  size_t flags_bytes;
+  size_t prof;          // kPipeProfCtas x kPipeProfSlots stall-cycle counters (written only when profiling is on);
+                        // always the LAST kPipeProfCtas * kPipeProfSlots * 8 bytes of the stash
+  size_t total;
+  int64_t tiles;        // 128-row forward tiles
+};
+constexpr int kPipeProfCtas = 192;
+constexpr int kPipeProfSlots = 32;
+
+__host__ __device__ inline PipeStashLayout make_pipe_stash_layout(int H, int L, int64_t rows) {
+  PipeStashLayout s;
+  s.tiles = (rows + kTileRows - 1) / kTileRows;
+  s.layer_stride = size_t(s.tiles) * kTileRows * H * 2;
+  size_t o = 0;
+  s.ph = o;
+  o += size_t(L + 1) * s.layer_stride;
+  s.xa = o;
+  o += size_t(s.tiles) * kTileRows * 16;
+  s.ring = o;
+  o += size_t(kPipeMaxEdges) * kPipeRing * kPipeTileRows * H * 2;
+  s.flags = o;
+  s.flags_bytes = size_t(kPipeMaxEdges) * 4 * 128;
+  o += s.flags_bytes;
+  s.prof = o;
+  o += size_t(kPipeProfCtas) * kPipeProfSlots * 8;
+  s.total = o;
+  return s;
+}
+
 // Flat fp32 parameter offsets (in floats): W_i at off[2i], b_i at off[2i+1], i = 0..L+1.
 __host__ __device__ inline int64_t param_offsets(int d, int H, int L, int C, int64_t* off) {
   int64_t o = 0;

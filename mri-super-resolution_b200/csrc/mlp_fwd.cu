@@ -88,8 +88,12 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
   }
 }
 
-template <int H, bool kStash>
+// kMode: 0 = inference, 1 = staged training (sin outputs + phases + coordinate operand), 2 = pipelined training
+// (phases only: mlp_bwdp.cu recomputes sin and cos from them).
+template <int H, int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
+  constexpr bool kStash = kMode != 0;  // phases are stored
+  constexpr bool kStashY = kMode == 1;  // sin outputs and the coordinate operand are stored too
   using S = FwdSmem<H>;
   static_assert(S::kKB == 4, "epilogue slicing assumes 4 K blocks");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     }
   } else if (warp == 2) {
     // =============================== stash store (training) ===============================
-    if (kStash && lane == 0) {
+    if (kStashY && lane == 0) {
       uint32_t na[2] = {0, 0};
       for (int pr = 0; pr < num_pairs; ++pr) {
         const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
@@ -231,7 +235,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         } else {
           grid_coords(p.grid, row0 + r, x);
         }
-        if (kStash) {  // coordinate operand of dW_0: x = hi + lo in bf16 (exact to 2^-17), the other 56 columns zero
+        if (kMode == 2 && s == 0) {  // pipelined training: compact coordinate record {hi x4, lo x4} per row
+          float hi[4], lo[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
+            lo[jj] = x[jj] - hi[jj];
+          }
+          reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] =
+              make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
+                         pack_bf16x2(lo[2], lo[3]));
+        }
+        if (kStashY) {  // coordinate operand of dW_0: x = hi + lo in bf16 (exact to 2^-17), the other 56 columns zero
           uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
           uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
           if (s == 0) {
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
                                  : nullptr;
           mbar_wait(&d_full[j], nd[j] & 1);
           ++nd[j];
-          if (kStash) {
+          if (kStashY) {
             mbar_wait(&a_free[j], nf[j] & 1);
             ++nf[j];
           }
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
         mbar_wait(&d_full[j], nd[j] & 1);
         ++nd[j];
-        if (kStash) {
+        if (kStashY) {
           mbar_wait(&a_free[j], nf[j] & 1);
           ++nf[j];
         }
@@ -723,9 +738,15 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   p.out = out;
   p.clamp = clamp;
   p.clamp_min = clamp_min;
-  if (stash) {
+  const bool staged = (net->flags & B200INR_NET_STAGED_BWD) != 0;
+  if (stash && staged) {
     StashLayout sl = make_stash_layout(H, net->hidden_layers, rows);
     p.stash_y = reinterpret_cast<uint8_t*>(stash) + sl.y;
+    p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
+    p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
+    p.stash_layer_stride = sl.layer_stride;
+  } else if (stash) {
+    PipeStashLayout sl = make_pipe_stash_layout(H, net->hidden_layers, rows);
     p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
     p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
@@ -738,7 +759,7 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   // it is opt-in: B200INR_FWD_2CTA=1.
   const char* env2 = getenv("B200INR_FWD_2CTA");
   const bool use_2cta = env2 != nullptr && env2[0] == '1';
-  if (use_2cta && pairs >= 2) {  // CTA-pair kernel: an even number of CTAs, at most one per SM
+  if (use_2cta && pairs >= 2 && (!stash || staged)) {  // CTA-pair kernel: an even number of CTAs, at most one per SM
     int g2 = pairs < num_sms ? pairs : num_sms;
     g2 &= ~1;
     const int smem2 = Fwd2Smem<H>::kBytes + 1024;
@@ -755,14 +776,18 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   }
   const int smem = FwdSmem<H>::kBytes + 1024;
   const int grid_x = pairs < num_sms ? pairs : num_sms;
-  if (stash) {
-    e = cudaFuncSetAttribute(siren_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (stash && staged) {
+    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return B200INR_ERR_CUDA;
-    siren_fwd_kernel<H, true><<<grid_x, kFwdThreads, smem, stream>>>(p);
+    siren_fwd_kernel<H, 1><<<grid_x, kFwdThreads, smem, stream>>>(p);
+  } else if (stash) {
+    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return B200INR_ERR_CUDA;
+    siren_fwd_kernel<H, 2><<<grid_x, kFwdThreads, smem, stream>>>(p);
   } else {
-    e = cudaFuncSetAttribute(siren_fwd_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return B200INR_ERR_CUDA;
-    siren_fwd_kernel<H, false><<<grid_x, kFwdThreads, smem, stream>>>(p);
+    siren_fwd_kernel<H, 0><<<grid_x, kFwdThreads, smem, stream>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }

@@ -249,6 +249,8 @@ class _FusedMLP(nn.Module):
         eng = eng or self._engine_state()
         dev = eng["device"]
         grad_out = grad_out.contiguous().float()
+        if grad_out.data_ptr() % 16:  # the pipelined backward bulk-copies dL/dout tiles (16-byte aligned source)
+            grad_out = grad_out.clone()
         if flat_grad is None:
             flat_grad = torch.zeros_like(eng["flat"])
         if rows == 0:
@@ -557,7 +559,13 @@ class FitSession:
         self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.dpred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.stash = _aligned_bytes(_lib.stash_bytes(module._desc, rows), dev)
-        self.kernel_launches_per_step = 7  # forward, loss, dgrad, wgrad, adam, adam_tick, pack
+        d = module._desc
+        # raw-coordinate SIREN without the staged flag: backward is one kernel (the marks 'dgrad' and 'wgrad' then
+        # bracket that kernel and nothing, respectively)
+        self.piped = (d.activation == _lib.ACT_SINE and d.input_mode == _lib.IN_COORDS
+                      and not (d.flags & _lib.NET_STAGED_BWD))
+        # forward, loss, backward (dgrad + wgrad when staged), adam, adam_tick, pack
+        self.kernel_launches_per_step = 6 if self.piped else 7
         self._graph = None
 
     def capture(self):
@@ -616,11 +624,16 @@ class FitSession:
                 _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
                                                        _ptr(ax), _ptr(ay), s), "degrade_adjoint")
             mark()
-            _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows, _ptr(self.dpred), s),
-                       "siren_dgrad")
-            mark()
-            _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
-                       "siren_wgrad")
+            if self.piped:  # one layer-pipelined kernel: dgrad chain + every weight / bias gradient
+                _lib.check(lib.b200inr_siren_backward(net, _ptr(eng["packed"]), _ptr(self.stash), None, gref, rows,
+                                                      _ptr(self.dpred), _ptr(self.grads), s), "siren_backward")
+                mark()
+            else:
+                _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows,
+                                                   _ptr(self.dpred), s), "siren_dgrad")
+                mark()
+                _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
+                           "siren_wgrad")
             mark()
             if self.process_group is not None:
                 torch.distributed.all_reduce(self.grads, group=self.process_group)

@@ -29,16 +29,24 @@ def test_c_abi_exports_every_declared_symbol():
 
 
 def test_param_layout_and_sizes():
-    net = L.make_net(3, 256, 4, 31)
+    net = L.make_net(3, 256, 4, 31, flags=0)
     off = L.param_offsets(net)
     assert off[0] == 0 and all(o % 4 == 0 for o in off)
     n = L.param_count(net)
     assert n >= 272159 and n - 272159 < 4 * len(off)
     assert L.packed_bytes(net) % 1024 == 0 or L.packed_bytes(net) > 0
-    # 3 x (bf16/u16) x 256 features x 5 sine layers per row, in whole 128-row tiles
-    assert L.stash_bytes(net, 128) == 3 * 5 * 128 * 256 * 2 + 2 * 128 * 64 * 2
-    assert L.stash_bytes(net, 129) == 2 * L.stash_bytes(net, 128)
+    # pipelined training path: 16-bit phases x 256 features x 5 sine layers per row in whole 128-row tiles, plus the
+    # fixed ring / flag storage of the layer pipelines
+    per_tile = 5 * 128 * 256 * 2 + 128 * 16  # + the 16-byte coordinate record per row
+    fixed = L.stash_bytes(net, 128) - per_tile
+    assert 0 < fixed < 32 << 20
+    assert L.stash_bytes(net, 129) == 2 * per_tile + fixed
     assert L.stash_bytes(net, 0) == 0
+    # staged path: 3 x (bf16/u16) x 256 features x 5 sine layers per row, in whole 128-row tiles
+    staged = L.make_net(3, 256, 4, 31, flags=L.NET_STAGED_BWD)
+    assert L.stash_bytes(staged, 128) == 3 * 5 * 128 * 256 * 2 + 2 * 128 * 64 * 2
+    assert L.stash_bytes(staged, 129) == 2 * L.stash_bytes(staged, 128)
+    assert L.stash_bytes(staged, 0) == 0
 
 
 def test_error_codes_without_gpu():

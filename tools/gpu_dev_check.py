@@ -131,11 +131,12 @@ def mlp(d, Lh, C, shape, use_grid, rows=None):
     return net, pk, st, grid, out, gout, gflat
 
 
-def timing():
+def timing(staged=False):
     d, Lh, C, H = 3, 4, 31, 256
     shape = (128, 128, 64)
     rows = 128 * 128 * 64
-    net = L.make_net(d, H, Lh, C)
+    net = L.make_net(d, H, Lh, C, flags=L.NET_STAGED_BWD if staged else 0)
+    tag = "staged" if staged else "piped"
     m = RefSiren(d, H, Lh, C).to(dev)
     flat, off = flat_params(net, m)
     packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
@@ -149,8 +150,10 @@ def timing():
     st = stash[(-stash.data_ptr()) % 1024:]
 
     def t(fn, n=5):
-        fn()
+        rc = fn()
         torch.cuda.synchronize()
+        if rc:
+            return float("nan")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
@@ -162,18 +165,97 @@ def timing():
     g = ctypes.byref(grid)
     nb = ctypes.byref(net)
     ms = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 1, 0.0, None, stream()))
-    print(f"timing: query fwd {ms:.3f} ms  -> {rows / ms / 1e3:.1f} M vox/s, {rows * 541696 / ms / 1e9:.1f} TFLOP/s")
+    print(f"timing[{tag}]: query fwd {ms:.3f} ms  -> {rows / ms / 1e3:.1f} M vox/s, {rows * 541696 / ms / 1e9:.1f} TFLOP/s")
     ms_f = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()))
-    print(f"timing: train fwd {ms_f:.3f} ms")
-    for mask in (1, 2, 4, 7):
-        os.environ["B200INR_WGRAD_ITEMS"] = str(mask)
+    print(f"timing[{tag}]: train fwd {ms_f:.3f} ms (stash {L.stash_bytes(net, rows) / 1e9:.2f} GB)")
+    if staged:
         ms_w = t(lambda: lib.b200inr_siren_wgrad(nb, ptr(st), None, g, rows, ptr(gflat), stream()))
-        print(f"timing: wgrad items mask={mask}: {ms_w:.3f} ms")
-    ms_d = t(lambda: lib.b200inr_siren_dgrad(nb, ptr(pk), ptr(st), rows, ptr(gout), stream()))
-    print(f"timing: dgrad {ms_d:.3f} ms")
+        print(f"timing[{tag}]: wgrad {ms_w:.3f} ms")
+        ms_d = t(lambda: lib.b200inr_siren_dgrad(nb, ptr(pk), ptr(st), rows, ptr(gout), stream()))
+        print(f"timing[{tag}]: dgrad {ms_d:.3f} ms")
     ms_b = t(lambda: lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()))
-    print(f"timing: bwd+wgrad {ms_b:.3f} ms  -> step ~{ms_f + ms_b:.3f} ms, "
-          f"{rows * 1623552 / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic")
+    print(f"timing[{tag}]: backward {ms_b:.3f} ms  -> fwd+bwd ~{ms_f + ms_b:.3f} ms, "
+          f"{rows * 1623552 / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic", flush=True)
+
+
+def bwdp_profile():
+    """Per-role stall accounting of the pipelined backward (B200INR_BWDP_PROF=1), cfg2 size."""
+    import numpy as np
+    os.environ["B200INR_BWDP_PROF"] = "1"
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    net = L.make_net(d, H, Lh, C, flags=0)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    gout = torch.randn(rows, C, device=dev) * 1e-6
+    gflat = torch.zeros_like(flat)
+    nbytes = L.stash_bytes(net, rows)
+    stash = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:][:nbytes]
+    g, nb = ctypes.byref(grid), ctypes.byref(net)
+    L.check(lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()), "fwd")
+    for _ in range(3):
+        L.check(lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()), "bwd")
+    torch.cuda.synchronize()
+    os.environ["B200INR_BWDP_PROF"] = "0"
+    prof = st[nbytes - 192 * 32 * 8:].view(torch.int64).reshape(192, 32).cpu().numpy().astype(np.float64)
+    S2 = 2 * (Lh + 1)
+    P = 148 // S2
+    names = {0: "total", 1: "ld:dz_empty", 2: "ld:poll", 3: "ph:empty", 4: "mma:in_full", 5: "mma:acc_empty",
+             6: "mma:y_full", 7: "st:stg_full", 8: "st:credit", 9: "st:read", 10: "st:write", 11: "ep:dob_empty",
+             12: "ep:ph_full", 13: "ep:y_empty", 14: "ep:acc_full", 15: "ep:stg_empty", 16: "ep:sin", 17: "ep:cos",
+             18: "bot:z_empty", 19: "bot:poll", 20: "bot:z_full", 21: "tiles", 22: "ld:fence_proxy", 23: "-",
+             24: "-", 25: "mma:credit", 26: "bot:issue", 27: "bot:mma", 28: "ep:dout", 29: "ep:loop", 30: "ep:fence"}
+    print(f"bwdp profile: {P} pipelines x {S2} CTAs; cycles PER TILE, mean over pipelines (role = stage, half)")
+    for role in range(S2):
+        rowsel = prof[[pp * S2 + role for pp in range(P)]]
+        n = rowsel[:, 21].mean()
+        txt = " ".join(f"{names[k]}={rowsel[:, k].mean() / max(n, 1):.0f}" for k in list(range(21)) + list(range(22, 31)) if rowsel[:, k].mean() > 0)
+        print(f"  role {role} (stage {role // 2}, h {role % 2}) tiles={n:.0f}: {txt}", flush=True)
+
+
+def piped_vs_staged(d, Lh, C, shape, rows=None):
+    """Same weights, same dL/dout: gradients of the one-kernel pipelined backward vs the staged dgrad + wgrad."""
+    H = 256
+    m = RefSiren(d, H, Lh, C).to(dev)
+    total = 1
+    for s in shape:
+        total *= s
+    rows = total if rows is None else rows
+    grid = L.make_grid(shape)
+    gout = torch.randn(rows, C, device=dev) / (rows * C)
+    res = []
+    for flags in (0, L.NET_STAGED_BWD):
+        net = L.make_net(d, H, Lh, C, flags=flags)
+        flat, off = flat_params(net, m)
+        packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+        pk = packed[(-packed.data_ptr()) % 1024:]
+        L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+        stash = torch.zeros(L.stash_bytes(net, rows) + 1024, dtype=torch.uint8, device=dev)
+        st = stash[(-stash.data_ptr()) % 1024:]
+        out = torch.zeros(rows, C, device=dev)
+        L.check(lib.b200inr_siren_forward(ctypes.byref(net), ptr(pk), None, ctypes.byref(grid), rows, ptr(out), 0, 0.0,
+                                          ptr(st), stream()), "fwd")
+        gflat = torch.zeros_like(flat)
+        L.check(lib.b200inr_siren_backward(ctypes.byref(net), ptr(pk), ptr(st), None, ctypes.byref(grid), rows,
+                                           ptr(gout), ptr(gflat), stream()), "bwd")
+        torch.cuda.synchronize()
+        res.append((out, gflat, off))
+    (o0, g0, off), (o1, g1, _) = res
+    print(f"  piped vs staged d={d} L={Lh} C={C} rows={rows}: out max|diff|={(o0 - o1).abs().max().item():.2e} "
+          f"grad relerr(all)={relerr(g0, g1):.3e}")
+    n = g0.numel()
+    ends = list(off[1:]) + [n]
+    for i in range(len(off)):
+        a, b = g0[off[i]:ends[i]], g1[off[i]:ends[i]]
+        print(f"    seg {i} ({'W' if i % 2 == 0 else 'b'}{i // 2}): relerr={relerr(a, b):.3e} |staged|={b.norm().item():.3e}",
+              flush=True)
 
 
 if __name__ == "__main__":
@@ -186,8 +268,17 @@ if __name__ == "__main__":
         print("mlp 3D coords"); mlp(3, 4, 31, (16, 16, 9), False)
         print("mlp 3D grid ragged"); mlp(3, 4, 31, (32, 32, 16), True, rows=32 * 32 * 16 - 77)
         print("mlp 3D bigger"); mlp(3, 4, 31, (64, 64, 32), True)
+    if "pvs" in which:
+        piped_vs_staged(2, 2, 1, (64, 48))
+        piped_vs_staged(3, 4, 31, (32, 32, 16), rows=32 * 32 * 16 - 77)
+        piped_vs_staged(3, 4, 31, (64, 64, 32))
+        piped_vs_staged(3, 0, 5, (16, 16, 8))
+    if "prof" in which:
+        bwdp_profile()
     if "timing" in which:
-        timing()
+        timing(False)
+    if "timing_staged" in which:
+        timing(True)
 
 
 def gen_checks():
