@@ -11,33 +11,37 @@
 // buffers that live in L2, and the weight gradients never leave tensor memory until the end of the kernel.
 //
 // Work split: the SMs form P = floor(#SM / 2(L+1)) independent pipelines of 2(L+1) CTAs; pipeline p walks its share of
-// the 64-row tiles.  Every CTA is WEIGHT-STATIONARY for its whole life:
+// the 64-row tiles.  Every CTA is WEIGHT-STATIONARY for its whole life, with its weights IN TENSOR MEMORY:
 //   stage CTA (l, h), l = L..1, h = 0/1 (feature half):                                   [the 256x256 layers]
-//       holds rows [128h, 128h+128) of W'_l^T (64 KB, A operand) and the [256 x 128] block dW_l[:, 128h..] in TMEM;
-//       per tile:  receive dTheta_l (64 x 256 bf16, 32 KB)                                <- ring l
-//                  D^T[in-half, rows]   = W'_l^T[in-half, :] dTheta_l^T                   (tcgen05 128 x 64 x 256)
-//                  y = sin(phase_l-1), c = cos(phase_l-1)      for its 128 features       (phases by bulk copy from HBM)
+//       TMEM: rows [128h, 128h+128) of W'_l^T (A operand, 128 columns), the block dW_l[:, 128h..]^T (256 columns),
+//             one chain accumulator (64 columns), two y operands (2 x 32 columns) = all 512 columns;
+//       per tile:  receive dTheta_l (64 rows x 256, bf16, 32 KB)                          <- ring l
+//                  D^T[in-half, rows]   = W'_l^T[in-half, :] dTheta_l^T                   (tcgen05 128 x 64 x 256, A in TMEM)
+//                  s, c = sin, cos(phase_l-1) for its 128 features x 64 rows              (phases: bulk copy from HBM)
 //                  dTheta_l-1[:, half]  = D .* c  -> bf16                                  -> ring l-1
-//                  dW_l[:, half]       += dTheta_l^T y                                     (tcgen05 2 x 128 x 128 x 64)
+//                  y^T = s -> bf16 -> TMEM (tcgen05.st)
+//                  dW_l[:, half]^T     += y^T dTheta_l                                     (tcgen05 128 x 256 x 64, A in TMEM)
 //                  db_l-1[half]        += colsum(dTheta_l-1)                               (registers: lane = feature)
 //   edge CTA E(h):                                                                        [both ends of the chain]
-//       top:     dOut tile -> bf16, D^T = W_f^T[half] dOut^T, y = sin(phase_L), dTheta_L = D .* cos(phase_L) -> ring L,
+//       top:     dOut tile -> bf16, D^T = W_f^T[half] dOut^T, s, c of phase_L, dTheta_L = D .* c -> ring L,
 //                dW_f^T[half] += y^T dOut, db_f, db_L
 //       bottom:  receive dTheta_0[:, half]                                                <- ring 0
-//                dW_0[half]   += dTheta_0^T [x_hi | x_lo]    (coordinates from the voxel index, bf16 hi + lo split)
-// The chain is computed TRANSPOSED (features on the 128 TMEM lanes, tile rows on the columns), so a tile may have any
-// row count (64 here: operand slots + weights fit the 227 KB of shared memory) at full tensor-core rate and the bias
-// gradient is a per-thread running sum.  A dTheta tile is stored FEATURE-major ([64 features][64 rows] swizzled
-// blocks: each thread writes its feature's 16 rows with two 16-byte stores); read with MN-major descriptors it is the
-// B operand of the chain step (N = rows, K = features), with K-major descriptors the A operand of the
-// weight-gradient step (M = features, K = rows).
+//                dW_0[half]   += dTheta_0^T [x_hi | x_lo]    (coordinate records stashed by the forward)
+// The chain is computed TRANSPOSED (features on the 128 TMEM lanes, tile rows on the columns): a tile may have any row
+// count (64 here) at full tensor-core rate, the bias gradient is a per-thread running sum, one thread owns one feature
+// for 16 rows, so sin outputs go to TMEM and dTheta to shared memory with 16-byte stores.  A dTheta tile is stored
+// FEATURE-major ([64 features][64 rows] swizzled blocks): read with MN-major descriptors it is the B operand of the
+// chain step (N = rows, K = features), with K-major descriptors the B operand of the weight-gradient step
+// (N = features, K = rows).  Shared-memory traffic per tile: 160 KB (operands in TMEM take none).
 //
-// Rings: per pipeline and layer boundary kRing slots of one tile; producers bulk-store their half and release a
-// counter, consumers acquire, bulk-load and return a credit counter (all bounded spins: a mis-programmed pipeline
-// traps instead of hanging).  All 2(L+1)P CTAs must be co-resident: the grid never exceeds the SM count (1 CTA/SM).
+// Rings: per pipeline and layer boundary kPipeRing slots of one tile; producers bulk-store their half and publish it
+// with a bulk add on a counter (no generic-proxy fence), consumers poll (acquire), bulk-load and return a credit
+// counter (all bounded spins: a mis-programmed pipeline traps instead of hanging).  All 2(L+1)P CTAs must be
+// co-resident: the grid never exceeds the SM count (1 CTA/SM).
 //
-// Warp roles (640 threads): 0 = ring/weight loader (edge: phase loader), 1 = MMA issuer + TMEM owner, 2 = ring store,
-// 3 = phase loader (edge: the whole bottom half), 4..19 = epilogue (TMEM lane quadrant = warp & 3).
+// Warp roles (736 threads): 0 = ring loader (edge: phase loader), 1 = chain MMA issuer + TMEM owner, 2 = ring store,
+// 3 = phase loader (edge: the whole bottom half), 4..19 = epilogue (TMEM lane quadrant = warp & 3),
+// 20..21 = edge: dOut fp32 -> bf16 converters (idle in stage CTAs), 22 = weight-gradient MMA issuer.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -46,15 +50,18 @@
 
 namespace b200inr {
 
-constexpr int kPThreads = 640;
+constexpr int kPThreads = 736;
 constexpr int kPEpiWarps = 16;
 constexpr int kPFirstEpiWarp = 4;
-constexpr int kPEpiThreads = kPEpiWarps * 32;  // 512
+constexpr int kPCvtWarps = 2;
+constexpr int kPFirstCvtWarp = kPFirstEpiWarp + kPEpiWarps;  // 20
+constexpr int kPWgradWarp = kPFirstCvtWarp + kPCvtWarps;      // 22
 constexpr int kPDzSlots = 3;                    // incoming dTheta tiles
-constexpr int kPPhSlots = 2;                    // phase tiles
-constexpr int kPDobSlots = 3;                   // edge: bf16 dOut blocks (converted two tiles ahead)
-constexpr int kPRawSlots = 3;                   // edge: raw fp32 dOut tiles (bulk-copied ahead of the conversion)
-constexpr int kPZSlots = 3;                     // edge bottom: dTheta_0 slots (2 tiles of look-ahead)
+constexpr int kPPhSlots = 4;                    // phase tiles (each epilogue group owns two)
+constexpr int kPStgSlots = 2;                   // outgoing dTheta halves
+constexpr int kPDobSlots = 4;                   // edge: bf16 dOut blocks
+constexpr int kPRawSlots = 2;                   // edge: raw fp32 dOut tiles (bulk-copied ahead of the conversion)
+constexpr int kPZSlots = 2;                     // edge bottom: dTheta_0 slots
 constexpr int kPStoreDepth = 2;                 // bulk stores in flight per ring-store thread
 constexpr int kPBlk = kPipeTileRows * 128;      // one [64][64] bf16 block: 8 KB
 constexpr int kPHalf = 2 * kPBlk;               // 128 features of a tile: 16 KB
@@ -63,49 +70,55 @@ constexpr int kPPhChunk = kPipeTileRows * 16 + 16;  // phases of 8 features x 64
 constexpr int kPPhSlot = 16 * kPPhChunk;            // 16 chunks = 128 features
 constexpr int kPRawSlot = kPipeTileRows * kOutPad * 4;  // fp32 dOut tile, C <= 32
 
-// shared memory map (bytes); operand blocks are 1024-byte aligned
-struct PSmem {
-  // stage CTA
-  static constexpr int kWt = 0;                              // W'^T half: 4 x [128][64]      64 KB
-  static constexpr int kDz = kWt + 4 * 128 * 128;            // kPDzSlots x tile               96 KB
-  static constexpr int kY = kDz + kPDzSlots * kPTile;        // sin outputs, 2 blocks          16 KB
-  static constexpr int kStg = kY + kPHalf;                   // outgoing dTheta half           16 KB
-  static constexpr int kPh = kStg + kPHalf;                  // kPPhSlots phase slots          32.5 KB
+// shared memory maps (bytes); operand blocks are 1024-byte aligned
+struct PSmem {  // stage CTA
+  static constexpr int kDz = 0;                              // kPDzSlots x tile               96 KB
+  static constexpr int kY = kDz + kPDzSlots * kPTile;        // 2 x sin outputs (128 features)  32 KB
+  static constexpr int kStg = kY + 2 * kPHalf;               // kPStgSlots x dTheta half       32 KB
+  static constexpr int kPh = kStg + kPStgSlots * kPHalf;     // kPPhSlots phase slots          65 KB
   static constexpr int kBar = kPh + kPPhSlots * kPPhSlot;
   static constexpr int kBytes = kBar + 512;
-  // edge CTA (re-uses kY, kStg, kPh, kBar)
-  static constexpr int kWf = 0;                              // W_f^T half [128][64]           16 KB
-  static constexpr int kDob = kWf + 128 * 128;               // kPDobSlots x dOut block        24 KB
-  static constexpr int kZ = kDob + kPDobSlots * kPBlk;       // kPZSlots x dTheta_0 half       48 KB
-  static constexpr int kXb = kZ + kPZSlots * kPHalf;         // kPZSlots x coordinate block    24 KB
-  static constexpr int kRaw = kXb + kPZSlots * kPBlk;        // kPRawSlots x fp32 dOut tile    24 KB
-  static_assert(kRaw + kPRawSlots * kPRawSlot <= kY, "edge layout overlaps");
   static_assert(kBytes + 1024 <= 232448, "shared memory budget");
+};
+struct PSmemE {  // edge CTA (same barrier area as the stage CTAs)
+  static constexpr int kWf = 0;                              // W_f^T half [128][64]           16 KB
+  static constexpr int kDob = kWf + 128 * 128;               // kPDobSlots x dOut block        32 KB
+  static constexpr int kZ = kDob + kPDobSlots * kPBlk;       // kPZSlots x dTheta_0 half       32 KB
+  static constexpr int kXb = kZ + kPZSlots * kPHalf;         // kPZSlots x coordinate block    16 KB
+  static constexpr int kRaw = kXb + kPZSlots * kPBlk;        // kPRawSlots x fp32 dOut tile    16 KB
+  static constexpr int kY = kRaw + kPRawSlots * kPRawSlot;   // 2 x sin outputs                32 KB
+  static constexpr int kStg = kY + 2 * kPHalf;               // kPStgSlots x dTheta half       32 KB
+  static constexpr int kPh = kStg + kPStgSlots * kPHalf;     // 3 phase slots                  48.75 KB
+  static constexpr int kPhSlots = 3;
+  static_assert(kPh + kPhSlots * kPPhSlot <= PSmem::kBar, "edge layout overlaps the barrier area");
 };
 
 // barrier indices
 enum PBar : int {
-  kBW = 0,          // static weights landed
-  kBDzFull = 1,     // [3]
-  kBDzEmpty = 4,    // [3]
-  kBPhFull = 7,     // [2]
-  kBPhEmpty = 9,    // [2]
-  kBAccFull = 11,   // [2]
-  kBAccEmpty = 13,  // [2]
-  kBYFull = 15,
-  kBYEmpty = 16,
-  kBStgFull = 17,
-  kBStgEmpty = 18,
-  kBFin = 19,
-  kBDobFull = 20,   // [3] edge
-  kBDobEmpty = 23,  // [3] edge
-  kBZFull = 26,     // [3] edge bottom
-  kBZEmpty = 29,    // [3] edge bottom
-  kBFinB = 32,
-  kBRawFull = 33,   // [3] edge
-  kBRawEmpty = 36,  // [3] edge
-  kBCount = 39
+  // NOTE: a parity wait may be at most one phase behind its barrier, so every barrier is waited on, phase after
+  // phase, by the same thread(s): barriers used by the epilogue come in per-group (tile parity) pairs.
+  kBW = 0,                                // static weights in place
+  kBDzFull = kBW + 1,                     // [kPDzSlots]
+  kBDzEmpty = kBDzFull + kPDzSlots,       // [kPDzSlots]
+  kBPhFull = kBDzEmpty + kPDzSlots,       // [kPPhSlots]
+  kBPhEmpty = kBPhFull + kPPhSlots,       // [kPPhSlots]
+  kBAccFull = kBPhEmpty + kPPhSlots,      // [2] by tile parity (ONE accumulator: the barriers alternate, not the storage)
+  kBAccEmpty = kBAccFull + 2,             // [2]
+  kBYFull = kBAccEmpty + 2,               // [2]
+  kBYEmpty = kBYFull + 2,                 // [2]
+  kBStgFull = kBYEmpty + 2,               // [2]
+  kBStgEmpty = kBStgFull + 2,             // [2]
+  kBFin = kBStgEmpty + 2,
+  kBDobFull = kBFin + 1,                  // [kPDobSlots] edge
+  kBDobEmpty = kBDobFull + kPDobSlots,    // [kPDobSlots] edge
+  kBZFull = kBDobEmpty + kPDobSlots,      // [kPZSlots] edge bottom
+  kBZEmpty = kBZFull + kPZSlots,          // [kPZSlots] edge bottom
+  kBFinB = kBZEmpty + kPZSlots,
+  kBRawFull = kBFinB + 1,                 // [kPRawSlots] edge
+  kBRawEmpty = kBRawFull + kPRawSlots,    // [kPRawSlots] edge
+  kBCount = kBRawEmpty + kPRawSlots
 };
+static_assert(kPStgSlots == 2 && kPZSlots == 2, "per-parity buffers");
 
 struct PipeParams {
   const uint8_t* packed;
@@ -123,6 +136,9 @@ struct PipeParams {
   long long off[2 * (kMaxSineLayers + 2)];
   float omega0, omegah;
   int pipelines;
+  int skew_ns;               // start-up delay of the second epilogue group
+  int dbg;                   // tuning switches (B200INR_BWDP_DBG), 0 in production
+  uint32_t* trace;           // nullptr, or the event trace buffer (see TR)
   unsigned long long* prof;  // nullptr, or [grid][kPipeProfSlots] stall-cycle counters (B200INR_BWDP_PROF=1)
 };
 
@@ -137,6 +153,15 @@ struct PipeParams {
     } else {                                          \
       stmt;                                           \
     }                                                 \
+  } while (0)
+// Event trace (tuning aid, B200INR_BWDP_TRACE_PTR = device pointer): pipeline 0 records the time of event `ev` of tile
+// `tile` as trace[(role * kTraceTiles + tile) * kTraceEvents + ev] (cycles since kernel start, 32 bit).
+constexpr int kTraceTiles = 256;
+constexpr int kTraceEvents = 24;
+#define TR(ev, tile)                                                                                          \
+  do {                                                                                                        \
+    if (trace_on && (tile) < kTraceTiles)                                                                     \
+      p.trace[(size_t(role) * kTraceTiles + (tile)) * kTraceEvents + (ev)] = uint32_t(clock64() - t_begin);  \
   } while (0)
 #define PW_FLUSH(base, cnt)                                                                                  \
   do {                                                                                                       \
@@ -188,52 +213,39 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
   asm volatile("ld.shared.b16 %0, [%1];\n" : "=h"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+
+// ---- tensor-memory operand helpers
+// 32 lanes x 8 / 16 consecutive 32-bit columns: thread i of the warp writes lane (base_lane + i).
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = M row, 2 bf16 per column along K] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
-// phase (u16, 65536 = one turn) -> radians: float(2^23 + ph) is built with one PRMT / LOP, then one FFMA
+// phase (u16, 65536 = one turn) -> radians: float(2^23 + ph) is built with one PRMT, then one FFMA
 constexpr float kPhToRad = 9.587379924285257e-05f;   // 2*pi / 65536
 constexpr float kPhBias = -804.247719318987f;        // -(2^23) * 2*pi / 65536
 __device__ __forceinline__ float rad_lo16(uint32_t w) {
   return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), kPhToRad, kPhBias);
-}
-__device__ __forceinline__ float rad_hi16(uint32_t w) {
-  return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), kPhToRad, kPhBias);
-}
-
-// ---- tile epilogue, shared by stage and edge CTAs ----------------------------------------------------------------
-// TMEM lane = feature f, columns = rows [16 cg, 16 cg + 16).  From ONE phase read per element:
-//   y^T[f][row]      = sin(phase)                 (operand of the weight-gradient MMA)
-//   dTheta^T[f][row] = D^T[f][row] * cos(phase)   (sent on to the next layer)
-// both packed feature-major (16 rows = two 16-byte chunks of the feature's 128-byte row).  Returns the fp32 sum of
-// dTheta over the 16 rows (bias gradient partial).
-__device__ __forceinline__ float sincos_tile(uint32_t acc_t, uint32_t ph_s, int f, int cg, uint32_t (&ys)[8],
-                                             uint32_t (&ds)[8]) {
-  uint32_t v[16];
-  tmem_ld16(acc_t + cg * 16, v);
-  const uint32_t ph_f = ph_s + (f >> 3) * kPPhChunk + (f & 7) * 2 + cg * 16 * 16;
-  uint32_t ph[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + j * 16);
-  tmem_ld_wait();
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
-    const float d0 = __uint_as_float(v[2 * j]) * __cosf(r0);
-    const float d1 = __uint_as_float(v[2 * j + 1]) * __cosf(r1);
-    sum += d0 + d1;
-    ds[j] = pack_bf16x2(d0, d1);
-    ys[j] = pack_bf16x2(__sinf(r0), __sinf(r1));
-  }
-  return sum;
-}
-__device__ __forceinline__ void store_feature_rows(uint32_t half_s, int f, int cg, const uint32_t (&o)[8]) {
-  const uint32_t blk = half_s + (f >> 6) * kPBlk;
-  sts128(blk + sw128_chunk_off(f & 63, 2 * cg), make_uint4(o[0], o[1], o[2], o[3]));
-  sts128(blk + sw128_chunk_off(f & 63, 2 * cg + 1), make_uint4(o[4], o[5], o[6], o[7]));
 }
 
 __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipeParams p) {
@@ -242,8 +254,8 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBCount);
-  uint32_t* one_s = reinterpret_cast<uint32_t*>(smem + S::kBar + 320);  // 16-byte aligned constant {1, 0, 0, 0}
-  static_assert(kBCount * 8 + 4 <= 320 && 320 + 16 <= 512, "barrier area layout");
+  uint32_t* one_s = reinterpret_cast<uint32_t*>(smem + S::kBar + 448);  // 16-byte aligned constant {1, 0, 0, 0}
+  static_assert(kBCount * 8 + 4 <= 448 && 448 + 16 <= 512, "barrier area layout");
   const uint32_t sbase = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5;
@@ -272,27 +284,33 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   if (threadIdx.x == 0) {
     one_s[0] = 1u;  // {1, 0, 0, 0}: source of the bulk add that publishes a ring slot
     one_s[1] = one_s[2] = one_s[3] = 0u;
-    mbar_init(&bars[kBW], 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[kBPhFull + i], 1);
-      mbar_init(&bars[kBPhEmpty + i], kPEpiWarps);
-      mbar_init(&bars[kBAccFull + i], 1);
-      mbar_init(&bars[kBAccEmpty + i], kPEpiWarps);
-    }
-    for (int i = 0; i < 3; ++i) {
+    mbar_init(&bars[kBW], edge ? 1 : 4);
+    for (int i = 0; i < kPDzSlots; ++i) {
       mbar_init(&bars[kBDzFull + i], 1);
       mbar_init(&bars[kBDzEmpty + i], 1);
-      mbar_init(&bars[kBDobFull + i], kPEpiWarps);
+    }
+    for (int i = 0; i < kPPhSlots; ++i) {
+      mbar_init(&bars[kBPhFull + i], 1);
+      mbar_init(&bars[kBPhEmpty + i], kPEpiWarps);
+    }
+    for (int i = 0; i < kPDobSlots; ++i) {
+      mbar_init(&bars[kBDobFull + i], kPCvtWarps);
       mbar_init(&bars[kBDobEmpty + i], 1);
+    }
+    for (int i = 0; i < kPRawSlots; ++i) {
+      mbar_init(&bars[kBRawFull + i], 1);
+      mbar_init(&bars[kBRawEmpty + i], kPCvtWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[kBAccFull + i], 1);
+      mbar_init(&bars[kBAccEmpty + i], kPEpiWarps / 2);
+      mbar_init(&bars[kBYFull + i], kPEpiWarps / 2);
+      mbar_init(&bars[kBYEmpty + i], 1);
+      mbar_init(&bars[kBStgFull + i], kPEpiWarps / 2);
+      mbar_init(&bars[kBStgEmpty + i], 1);
       mbar_init(&bars[kBZFull + i], 1);
       mbar_init(&bars[kBZEmpty + i], 1);
-      mbar_init(&bars[kBRawFull + i], 1);
-      mbar_init(&bars[kBRawEmpty + i], kPEpiWarps);
     }
-    mbar_init(&bars[kBYFull], kPEpiWarps);
-    mbar_init(&bars[kBYEmpty], 1);
-    mbar_init(&bars[kBStgFull], kPEpiWarps);
-    mbar_init(&bars[kBStgEmpty], 1);
     mbar_init(&bars[kBFin], 1);
     mbar_init(&bars[kBFinB], 1);
     fence_mbar_init();
@@ -303,17 +321,25 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns.  stage: dW block [0,256) (two M halves x 128), chain accumulators 256 + 64 j.
+  // TMEM columns.  stage: dW^T block [0,256), W'^T half [256,384), chain accumulators 384 + 64 j.
   //               edge : chain accumulators 0 + 64 j, dW_f^T [128,192), dW_0 [192,256).
-  const uint32_t t_acc = edge ? tmem : tmem + 256;
   const uint32_t t_w = edge ? tmem + 128 : tmem;
+  const uint32_t t_wt = tmem + 256;
+  const uint32_t t_acc = edge ? tmem : tmem + 384;
   const uint32_t t_w0 = tmem + 192;
+
+  using E = PSmemE;
+  const uint32_t oY = sbase + (edge ? E::kY : S::kY);        // 2 x y operand (feature-major [128][64 rows])
+  const uint32_t oStg = edge ? E::kStg : S::kStg;            // staging halves (byte offset from smem)
+  const uint32_t oPh = edge ? E::kPh : S::kPh;               // phase slots (byte offset from smem)
+  const int nph = edge ? E::kPhSlots : kPPhSlots;
 
   const uint64_t hiK = smem_desc_hi_sw128(0, 1024);       // K-major blocks
   const uint64_t hiMN = smem_desc_hi_sw128(kPBlk, 1024);  // MN-major: 64-wide MN blocks kPBlk apart
 
   const bool prof_on = p.prof != nullptr;
-  const long long t_begin = prof_on ? clock64() : 0;
+  const bool trace_on = p.trace != nullptr && pipe == 0;
+  const long long t_begin = (prof_on || trace_on) ? clock64() : 0;
 
   if (n > 0) {
     if (warp == 0) {
@@ -321,15 +347,13 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       if (lane == 0) {
         if (!edge) {
           unsigned long long pw[2] = {0, 0};
-          const uint8_t* src = p.packed + p.pl.wht + size_t(layer - 1) * 256 * 256 * 2 + size_t(h) * 128 * 128;
-          mbar_arrive_expect_tx(&bars[kBW], 4 * 128 * 128);
-          for (int kb = 0; kb < 4; ++kb)
-            bulk_g2s(smem + S::kWt + kb * 128 * 128, src + size_t(kb) * 256 * 128, 128 * 128, &bars[kBW]);
           uint32_t k0 = 0, k1 = 0;
           for (int i = 0; i < n; ++i) {
             const int slot = i % kPDzSlots, round = i / kPDzSlots;
             if (round > 0) PW(0, mbar_wait(&bars[kBDzEmpty + slot], (round - 1) & 1));
+            TR(0, i);
             PW(1, poll2_ge(fl_in + 0 * 32, fl_in + 1 * 32, uint32_t(i + 1), k0, k1));
+            TR(1, i);
             // (no proxy fence: the tile was written AND published through the async proxy, and is read through it)
             mbar_arrive_expect_tx(&bars[kBDzFull + slot], kPTile);
             bulk_g2s(smem + S::kDz + slot * kPTile, ring_in + size_t(i % kPipeRing) * kPTile, kPTile,
@@ -338,119 +362,118 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           PW_FLUSH(1, 2);
         } else {
           mbar_arrive_expect_tx(&bars[kBW], 128 * 128);
-          bulk_g2s(smem + S::kWf, p.packed + p.pl.wft + size_t(h) * 128 * 128, 128 * 128, &bars[kBW]);
+          bulk_g2s(smem + E::kWf, p.packed + p.pl.wft + size_t(h) * 128 * 128, 128 * 128, &bars[kBW]);
         }
       }
     }
     if ((edge && warp == 0) || (!edge && warp == 3)) {
-      // =============================== phase loader (edge: + raw dOut tiles) ===============================
+      // =============================== phase loader ===============================
       if (lane == 0) {
         unsigned long long pw[1] = {0};
-        int next_raw = 0;
         for (int i = 0; i < n; ++i) {
-          if (edge) {  // fp32 dOut tiles run two tiles ahead of the phases (they are converted two tiles ahead)
-            const int lim = (i + 3 < n) ? i + 3 : n;
-            for (; next_raw < lim; ++next_raw) {
-              const int j = next_raw, rs = j % kPRawSlots;
-              if (j >= kPRawSlots) mbar_wait(&bars[kBRawEmpty + rs], ((j / kPRawSlots) - 1) & 1);
-              const int Tj = pipe + (j >> 1) * p.pipelines;
-              const long long row0 = (long long)Tj * 128 + (j & 1) * kPipeTileRows;
-              if (row0 + kPipeTileRows <= p.rows) {
-                const uint32_t bytes = uint32_t(kPipeTileRows) * p.C * 4;
-                mbar_arrive_expect_tx(&bars[kBRawFull + rs], bytes);
-                bulk_g2s(smem + S::kRaw + rs * kPRawSlot, p.grad_out + row0 * p.C, bytes, &bars[kBRawFull + rs]);
-              } else {
-                mbar_arrive(&bars[kBRawFull + rs]);  // ragged last tile: the epilogue reads it from global memory
-              }
-            }
-          }
-          const int slot = i % kPPhSlots, round = i / kPPhSlots;
+          const int slot = i % nph, round = i / nph;
           if (round > 0) PW(0, mbar_wait(&bars[kBPhEmpty + slot], (round - 1) & 1));
           const int T = pipe + (i >> 1) * p.pipelines;
           const uint8_t* src = p.ph + size_t(ph_layer) * p.layer_stride + size_t(T) * (128 * 256 * 2) +
                                size_t(i & 1) * (kPipeTileRows * 16) + size_t(h) * 16 * (128 * 16);
           mbar_arrive_expect_tx(&bars[kBPhFull + slot], 16 * kPipeTileRows * 16);
           for (int c = 0; c < 16; ++c)
-            bulk_g2s(smem + S::kPh + slot * kPPhSlot + c * kPPhChunk, src + size_t(c) * (128 * 16), kPipeTileRows * 16,
+            bulk_g2s(smem + oPh + slot * kPPhSlot + c * kPPhChunk, src + size_t(c) * (128 * 16), kPipeTileRows * 16,
                      &bars[kBPhFull + slot]);
         }
         PW_FLUSH(3, 1);
       }
     } else if (warp == 1) {
-      // =============================== MMA issuer ===============================
-      // The chain MMA of tile i + 1 is issued BEFORE waiting for the epilogue of tile i, so its accumulator is ready
-      // when the epilogue warps get there; the weight-gradient MMA of tile i follows the epilogue of tile i.
-      if (lane == 0) {
+      // =============================== chain MMA issuer ===============================
+      // Chain step of tile i + 1 as soon as its operand tile is here and the (single) accumulator has been read out by
+      // the epilogue group of tile i.  The whole warp runs the loop converged, one elected lane issues (umma_*_w).
+      {
         unsigned long long pw[4] = {0, 0, 0, 0};
         mbar_wait(&bars[kBW], 0);
         tc_fence_after();
         if (!edge) {
-          const uint32_t idesc_d = idesc_bf16(128, kPipeTileRows, false, true);  // A = W'^T (K-major), B = dTheta (MN-major)
-          const uint32_t idesc_w = idesc_bf16(128, 128, false, false);           // A = dTheta, B = y: both K-major
-          auto chain = [&](int i) {  // D^T[in-half][rows] = sum over the 256 outputs: 4 feature blocks x 4 K steps
-            const int ds = i % kPDzSlots, as = i & 1;
+          const uint32_t idesc_d = idesc_bf16(128, kPipeTileRows, false, true);  // A = W'^T (TMEM), B = dTheta (MN-major)
+          for (int i = 0; i < n; ++i) {  // D^T[in-half][rows] = sum over the 256 outputs: 16 K steps of 16 features
+            const int ds = i % kPDzSlots;
             PW(0, mbar_wait(&bars[kBDzFull + ds], (i / kPDzSlots) & 1));
-            PW(3, st_relaxed_gpu(fl_in + (2 + h) * 32, uint32_t(i + 1)));  // credit: the ring slot has been read out
-            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + as], ((i >> 1) - 1) & 1));
+            if (lane == 0) TR(2, i);
+            if (lane == 0) st_relaxed_gpu(fl_in + (2 + h) * 32, uint32_t(i + 1));  // credit: ring slot read out
+            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            if (lane == 0) TR(3, i);
             tc_fence_after();
             const uint32_t dz = sbase + S::kDz + ds * kPTile;
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_ss(t_acc + as * 64, smem_desc(sbase + S::kWt + kb * 128 * 128 + ks * 32, hiK),
-                             smem_desc(dz + kb * kPBlk + ks * 2048, hiMN), idesc_d, (kb | ks) != 0);
-            umma_commit(&bars[kBAccFull + as]);
-          };
-          chain(0);
-          for (int i = 0; i < n; ++i) {
-            if (i + 1 < n) chain(i + 1);
-            const uint32_t dz = sbase + S::kDz + (i % kPDzSlots) * kPTile;
-            PW(2, mbar_wait(&bars[kBYFull], i & 1));
-            tc_fence_after();
-            // dW[out][in-half] += sum over the 64 rows: M halves of 128 outputs, 4 K steps of 16 rows
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh)
-#pragma unroll
-              for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
-                umma_bf16_ss(t_w + mh * 128, smem_desc(dz + 2 * mh * kPBlk + ks * 32, hiK),
-                             smem_desc(sbase + S::kY + ks * 32, hiK), idesc_w, (i | ks) != 0);
-            umma_commit(&bars[kBYEmpty]);
-            umma_commit(&bars[kBDzEmpty + i % kPDzSlots]);
+                umma_bf16_ts_w(t_acc + (i & 1) * 64, t_wt + (kb * 4 + ks) * 8, smem_desc(dz + kb * kPBlk + ks * 2048, hiMN), idesc_d,
+                               (kb | ks) != 0);
+            umma_commit_w(&bars[kBAccFull + (i & 1)]);
+            if (lane == 0) TR(4, i);
           }
         } else {
           const uint32_t idesc_d = idesc_bf16(128, kPipeTileRows, false, false);  // A = W_f^T, B = dOut: both K-major
-          const uint32_t idesc_w = idesc_bf16(128, 64, false, true);              // A = y (K-major), B = dOut (MN-major)
-          auto chain = [&](int i) {
-            const int as = i & 1, bs = i % kPDobSlots;
+          for (int i = 0; i < n; ++i) {
+            const int bs = i % kPDobSlots;
             PW(0, mbar_wait(&bars[kBDobFull + bs], (i / kPDobSlots) & 1));
-            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + as], ((i >> 1) - 1) & 1));
+            if (lane == 0) TR(2, i);
+            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            if (lane == 0) TR(3, i);
             tc_fence_after();
-            const uint32_t dob = sbase + S::kDob + bs * kPBlk;
+            const uint32_t dob = sbase + E::kDob + bs * kPBlk;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_ss(t_acc + as * 64, smem_desc(sbase + S::kWf + k4 * 32, hiK), smem_desc(dob + k4 * 32, hiK),
-                           idesc_d, k4 != 0);
-            umma_commit(&bars[kBAccFull + as]);
-          };
-          chain(0);
+              umma_bf16_ss_w(t_acc + (i & 1) * 64, smem_desc(sbase + E::kWf + k4 * 32, hiK), smem_desc(dob + k4 * 32, hiK), idesc_d,
+                             k4 != 0);
+            umma_commit_w(&bars[kBAccFull + (i & 1)]);
+            if (lane == 0) TR(4, i);
+          }
+        }
+        if (lane == 0) PW_FLUSH(4, 2);
+      }
+    } else if (warp == kPWgradWarp) {
+      // =============================== weight-gradient MMA issuer ===============================
+      // Its own warp: the chain step of the next tile must not queue behind the wait for this tile's epilogue.
+      {
+        unsigned long long pw[1] = {0};
+        if (!edge) {
+          const uint32_t idesc_w = idesc_bf16(128, 256, false, false);  // A = y^T, B = dTheta: both K-major
           for (int i = 0; i < n; ++i) {
-            if (i + 1 < n) chain(i + 1);
-            const int bs = i % kPDobSlots;
-            const uint32_t dob = sbase + S::kDob + bs * kPBlk;
-            PW(2, mbar_wait(&bars[kBYFull], i & 1));
+            const int yb = i & 1, ds = i % kPDzSlots;
+            const uint32_t dz = sbase + S::kDz + ds * kPTile;
+            mbar_wait(&bars[kBDzFull + ds], (i / kPDzSlots) & 1);
+            PW(0, mbar_wait(&bars[kBYFull + yb], (i >> 1) & 1));
+            if (lane == 0) TR(5, i);
+            tc_fence_after();
+            // dW^T[in-half][out] += sum over the 64 rows: 4 K steps of 16 rows, N = all 256 outputs
+#pragma unroll
+            for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
+              umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dz + ks * 32, hiK), idesc_w,
+                             (i | ks) != 0);
+            umma_commit_w(&bars[kBYEmpty + yb]);
+            umma_commit_w(&bars[kBDzEmpty + ds]);
+            if (lane == 0) TR(6, i);
+          }
+        } else {
+          const uint32_t idesc_w = idesc_bf16(128, 64, false, true);  // A = y^T (K-major), B = dOut (MN-major)
+          for (int i = 0; i < n; ++i) {
+            const int bs = i % kPDobSlots, yb = i & 1;
+            const uint32_t dob = sbase + E::kDob + bs * kPBlk;
+            mbar_wait(&bars[kBDobFull + bs], (i / kPDobSlots) & 1);
+            PW(0, mbar_wait(&bars[kBYFull + yb], (i >> 1) & 1));
+            if (lane == 0) TR(5, i);
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
-              umma_bf16_ss(t_w, smem_desc(sbase + S::kY + ks * 32, hiK), smem_desc(dob + ks * 2048, hiMN), idesc_w,
-                           (i | ks) != 0);
-            umma_commit(&bars[kBYEmpty]);
-            umma_commit(&bars[kBDobEmpty + bs]);
+              umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dob + ks * 2048, hiMN), idesc_w,
+                             (i | ks) != 0);
+            umma_commit_w(&bars[kBYEmpty + yb]);
+            umma_commit_w(&bars[kBDobEmpty + bs]);
+            if (lane == 0) TR(6, i);
           }
         }
-        umma_commit(&bars[kBFin]);
-        PW_FLUSH(4, 3);
-        if (prof_on) p.prof[size_t(blockIdx.x) * kPipeProfSlots + 25] = pw[3];
+        umma_commit_w(&bars[kBFin]);
+        if (lane == 0) PW_FLUSH(6, 1);
       }
     } else if (warp == 2) {
       // =============================== ring store ===============================
@@ -463,15 +486,21 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         const uint32_t* fa = fl_out + ((out_edge != 0 || h == 0) ? 2 : 3) * 32;
         const uint32_t* fb = fl_out + ((out_edge != 0 || h == 1) ? 3 : 2) * 32;
         for (int i = 0; i < n; ++i) {
-          PW(0, mbar_wait(&bars[kBStgFull], i & 1));
+          const int ss = i % kPStgSlots;
+          PW(0, mbar_wait(&bars[kBStgFull + ss], (i / kPStgSlots) & 1));
+          TR(7, i);
           if (i >= kPipeRing) PW(1, poll2_ge(fa, fb, uint32_t(i - kPipeRing + 1), c0, c1));  // slot read out
-          bulk_s2g(ring_out + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, smem + S::kStg, kPHalf);
+          TR(8, i);
+          bulk_s2g(ring_out + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, smem + oStg + ss * kPHalf,
+                   kPHalf);
           bulk_commit();
           PW(2, bulk_wait_read0());
-          mbar_arrive(&bars[kBStgEmpty]);
+          mbar_arrive(&bars[kBStgEmpty + ss]);
+          TR(9, i);
           if (i >= kPStoreDepth) {  // the store of tile i - kPStoreDepth is complete: publish it (joins the next group)
             PW(3, bulk_wait_group<kPStoreDepth>());
             bulk_red_add_u32x4(fl_out + h * 32, one_s);
+            TR(10, i - kPStoreDepth);
           }
         }
         PW(3, bulk_wait0());
@@ -485,7 +514,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       // (reached only by edge CTAs: stage CTAs took the phase-loader branch above)
       unsigned long long pw[5] = {0, 0, 0, 0, 0};
       const uint32_t idesc_w = idesc_bf16(128, 64, false, true);  // A = dTheta_0 (K-major), B = coordinates (MN-major)
-      for (int i = lane; i < kPZSlots * kPBlk / 16; i += 32) sts128(sbase + S::kXb + i * 16, make_uint4(0u, 0u, 0u, 0u));
+      for (int i = lane; i < kPZSlots * kPBlk / 16; i += 32) sts128(sbase + E::kXb + i * 16, make_uint4(0u, 0u, 0u, 0u));
       __syncwarp();
       uint32_t k0 = 0;
       auto xa_row = [&](int i, int rr) {  // coordinate record of row lane + 32 rr of tile i
@@ -501,11 +530,11 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           uint32_t dummy = 0xffffffffu;
           PW(1, poll2_ge(fl_in + h * 32, fl_in + h * 32, uint32_t(i + 1), k0, dummy));
           mbar_arrive_expect_tx(&bars[kBZFull + zs], kPHalf);
-          bulk_g2s(smem + S::kZ + zs * kPHalf, ring_in + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, kPHalf,
+          bulk_g2s(smem + E::kZ + zs * kPHalf, ring_in + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, kPHalf,
                    &bars[kBZFull + zs]);
         }
-        sts128(sbase + S::kXb + zs * kPBlk + sw128_chunk_off(lane, 0), xv0);
-        sts128(sbase + S::kXb + zs * kPBlk + sw128_chunk_off(lane + 32, 0), xv1);
+        sts128(sbase + E::kXb + zs * kPBlk + sw128_chunk_off(lane, 0), xv0);
+        sts128(sbase + E::kXb + zs * kPBlk + sw128_chunk_off(lane + 32, 0), xv1);
         if (i + 1 < n) {
           xv0 = __ldg(xa_row(i + 1, 0));
           xv1 = __ldg(xa_row(i + 1, 1));
@@ -516,120 +545,247 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       for (int i = 0; i < kPZSlots - 1 && i < n; ++i) PW(3, issue(i));
       for (int i = 0; i < n; ++i) {
         const int zs = i % kPZSlots;
-        if (lane == 0) {
+        {
           PW(2, mbar_wait(&bars[kBZFull + zs], (i / kPZSlots) & 1));
           const long long tm0 = prof_on ? clock64() : 0;
-          st_relaxed_gpu(fl_in + (2 + h) * 32, uint32_t(i + 1));
+          if (lane == 0) st_relaxed_gpu(fl_in + (2 + h) * 32, uint32_t(i + 1));
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
-            umma_bf16_ss(t_w0, smem_desc(sbase + S::kZ + zs * kPHalf + ks * 32, hiK),
-                         smem_desc(sbase + S::kXb + zs * kPBlk + ks * 2048, hiMN), idesc_w, (i | ks) != 0);
-          umma_commit(&bars[kBZEmpty + zs]);
+            umma_bf16_ss_w(t_w0, smem_desc(sbase + E::kZ + zs * kPHalf + ks * 32, hiK),
+                           smem_desc(sbase + E::kXb + zs * kPBlk + ks * 2048, hiMN), idesc_w, (i | ks) != 0);
+          umma_commit_w(&bars[kBZEmpty + zs]);
           if (prof_on) pw[4] += (unsigned long long)(clock64() - tm0);
         }
         __syncwarp();
         if (i + kPZSlots - 1 < n) PW(3, issue(i + kPZSlots - 1));
       }
+      umma_commit_w(&bars[kBFinB]);
       if (lane == 0) {
-        umma_commit(&bars[kBFinB]);
         PW_FLUSH(18, 3);
         if (prof_on) {
           p.prof[size_t(blockIdx.x) * kPipeProfSlots + 26] = pw[3];
           p.prof[size_t(blockIdx.x) * kPipeProfSlots + 27] = pw[4];
         }
       }
+    } else if (warp >= kPFirstCvtWarp) {
+      // =============================== edge: dOut fp32 -> bf16 converters ===============================
+      // Thread t owns row t of every tile: [64 rows][C] fp32 (bulk-copied to shared memory; a ragged last tile comes
+      // straight from global memory) -> bf16 [64 rows][64] block, zero beyond C / rows; running column sums = db_f.
+      if (edge) {
+        const int t = threadIdx.x - kPFirstCvtWarp * 32;  // 0..63
+        const int C = p.C;
+        float dbf[kOutPad];
+#pragma unroll
+        for (int c = 0; c < kOutPad; ++c) dbf[c] = 0.f;
+        for (int sidx = 0; sidx < kPDobSlots; ++sidx)  // columns 32..63 stay zero for the whole kernel
+#pragma unroll
+          for (int ch = 4; ch < 8; ++ch)
+            sts128(sbase + E::kDob + sidx * kPBlk + sw128_chunk_off(t, ch), make_uint4(0u, 0u, 0u, 0u));
+        // the first converter thread also fetches the fp32 tiles, two tiles ahead (its own stream: a full bf16 ring
+        // must never hold the phase loads back)
+        auto load_raw = [&](int j) {
+          const int rs = j % kPRawSlots;
+          if (j >= kPRawSlots) mbar_wait(&bars[kBRawEmpty + rs], ((j / kPRawSlots) - 1) & 1);
+          const int Tj = pipe + (j >> 1) * p.pipelines;
+          const long long row0 = (long long)Tj * 128 + (j & 1) * kPipeTileRows;
+          if (row0 + kPipeTileRows <= p.rows) {
+            const uint32_t bytes = uint32_t(kPipeTileRows) * p.C * 4;
+            mbar_arrive_expect_tx(&bars[kBRawFull + rs], bytes);
+            bulk_g2s(smem + E::kRaw + rs * kPRawSlot, p.grad_out + row0 * p.C, bytes, &bars[kBRawFull + rs]);
+          } else {
+            mbar_arrive(&bars[kBRawFull + rs]);  // ragged last tile: read from global memory below
+          }
+        };
+        if (t == 0)
+          for (int j = 0; j < kPRawSlots && j < n; ++j) load_raw(j);
+        for (int j = 0; j < n; ++j) {
+          const int bs = j % kPDobSlots, rs = j % kPRawSlots;
+          mbar_wait(&bars[kBRawFull + rs], (j / kPRawSlots) & 1);
+          if (j >= kPDobSlots) mbar_wait(&bars[kBDobEmpty + bs], ((j / kPDobSlots) - 1) & 1);
+          const int T = pipe + (j >> 1) * p.pipelines;
+          const long long row0 = (long long)T * 128 + (j & 1) * kPipeTileRows;
+          float gv[kOutPad];
+          if (row0 + kPipeTileRows <= p.rows) {
+            const uint32_t src = sbase + E::kRaw + rs * kPRawSlot + uint32_t(t * C) * 4;
+#pragma unroll
+            for (int c = 0; c < kOutPad; ++c) gv[c] = (c < C) ? __uint_as_float(lds32(src + c * 4)) : 0.f;
+          } else {
+            const bool valid = row0 + t < p.rows;
+            const float* g = p.grad_out + (row0 + t) * C;
+#pragma unroll
+            for (int c = 0; c < kOutPad; ++c) gv[c] = (valid && c < C) ? __ldg(g + c) : 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < kOutPad; ++c) dbf[c] += gv[c];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            sts128(sbase + E::kDob + bs * kPBlk + sw128_chunk_off(t, ch),
+                   make_uint4(pack_bf16x2(gv[8 * ch], gv[8 * ch + 1]), pack_bf16x2(gv[8 * ch + 2], gv[8 * ch + 3]),
+                              pack_bf16x2(gv[8 * ch + 4], gv[8 * ch + 5]), pack_bf16x2(gv[8 * ch + 6], gv[8 * ch + 7])));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars[kBDobFull + bs]);
+            mbar_arrive(&bars[kBRawEmpty + rs]);
+          }
+          if (t == 0 && j + kPRawSlots < n) load_raw(j + kPRawSlots);  // refill the slot both warps just released
+          __syncwarp();
+        }
+        if (h == 0) {  // db_f: column sums of dOut (one edge CTA per pipeline)
+#pragma unroll
+          for (int c = 0; c < kOutPad; ++c) {
+            float sum = dbf[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0 && c < C) atomicAdd(p.grads + p.off[2 * (L + 1) + 1] + c, sum);
+          }
+        }
+      }
     } else if (warp >= kPFirstEpiWarp) {
       // =============================== epilogue warps ===============================
-      // Per tile: sin and cos of this CTA's 64 x 128 phases (thread = feature x 16 rows), dTheta = D .* cos -> staging
-      // -> ring, y = sin -> operand of the weight-gradient MMA; edge CTAs also turn the dOut tile two tiles ahead into
-      // its bf16 block.  One proxy fence and one round of barrier arrivals per tile.
+      // Two groups of 8 warps alternate tiles (group g takes tiles i = g mod 2), so the barrier / fence / TMEM latency
+      // of one group's tile hides behind the other group's sin / cos work (the MUFU pipe is the floor of this kernel).
+      // Thread = feature f (TMEM lane) x rows [32 rh, 32 rh + 32) of its tiles, in two batches of 16 rows.  From ONE
+      // phase read per element:
+      //   dTheta^T[f][row] = D^T[f][row] * cos(phase) -> staging (feature-major, 16-byte stores) -> ring
+      //   y^T[f][row]      = sin(phase)               -> TMEM operand of the weight-gradient MMA
+      // The chain accumulator and the phase slot are handed back as soon as both batches are in registers.
       unsigned long long pw[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       const long long te0 = prof_on ? clock64() : 0;
-      const int et = threadIdx.x - kPFirstEpiWarp * 32;  // 0..511
       const int ew = warp - kPFirstEpiWarp;
-      const int q = ew & 3;         // TMEM lane quadrant (== warp & 3)
-      const int cg = ew >> 2;       // 16-row column group
-      const int f = q * 32 + lane;  // feature inside this CTA's half
+      const int q = ew & 3;          // TMEM lane quadrant (== warp & 3)
+      const int cg = ew >> 2;        // flush: 64-output column group
+      const int rh = (ew >> 2) & 1;  // row half inside a tile
+      const int grp = ew >> 3;       // tile parity this warp works on
+      const int f = q * 32 + lane;   // feature inside this CTA's half
       const uint32_t t_lane = uint32_t(q * 32) << 16;
       const int C = p.C;
       float dbsum = 0.f;
-      float dbf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      // edge: dOut tile i (fp32, bulk-copied to shared memory; a ragged last tile comes straight from global memory)
-      // -> bf16 [64 rows][64] block: this thread converts row et & 63, columns 8 (et >> 6) .. +8 (zero beyond C / rows)
-      auto convert_dout = [&](int i) {
-        const int bs = i % kPDobSlots, rs = i % kPRawSlots;
-        PW(0, mbar_wait(&bars[kBRawFull + rs], (i / kPRawSlots) & 1));
-        if (i >= kPDobSlots) PW(0, mbar_wait(&bars[kBDobEmpty + bs], ((i / kPDobSlots) - 1) & 1));
-        const int T = pipe + (i >> 1) * p.pipelines;
-        const long long row0 = (long long)T * 128 + (i & 1) * kPipeTileRows;
-        const int r = et & 63, c0 = (et >> 6) * 8;
-        float gv[8];
-        if (row0 + kPipeTileRows <= p.rows) {
-          const uint32_t src = sbase + S::kRaw + rs * kPRawSlot + uint32_t(r * C + c0) * 4;
+
+      if (!edge) {
+        // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
+        if (cg == 0) {
+          const uint8_t* src = p.packed + p.pl.wht + size_t(layer - 1) * 256 * 256 * 2 + size_t(h * 128 + f) * 128;
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) gv[jj] = (c0 + jj < C) ? __uint_as_float(lds32(src + jj * 4)) : 0.f;
-        } else {
-          const bool valid = row0 + r < p.rows;
-          const float* g = p.grad_out + (row0 + r) * C + c0;
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t w[16];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) gv[jj] = (valid && c0 + jj < C) ? __ldg(g + jj) : 0.f;
+              for (int c = 0; c < 4; ++c) {
+                const int ch = hh * 4 + c;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + size_t(kb) * 256 * 128 + ((ch ^ (f & 7)) << 4)));
+                w[4 * c] = v.x;
+                w[4 * c + 1] = v.y;
+                w[4 * c + 2] = v.z;
+                w[4 * c + 3] = v.w;
+              }
+              tmem_st16(t_wt + t_lane + kb * 32 + hh * 16, w);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[kBW]);
+        }
+      }
+
+      // sin / cos of 16 phases, dTheta = D .* cos; packs y (sin) and dTheta as bf16 pairs along the rows
+      auto batch_math = [&](const uint32_t (&v)[16], const uint32_t (&ph)[16], uint32_t (&ys)[8], uint32_t (&ds)[8]) {
+        if (p.dbg & 1) {  // tuning aid: no sin / cos work (results are garbage), shows the pure pipeline rate
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ds[j] = v[2 * j] ^ ph[2 * j + 1];
+            ys[j] = v[2 * j + 1] ^ ph[2 * j];
+          }
+          return;
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) dbf[jj] += gv[jj];
-        sts128(sbase + S::kDob + bs * kPBlk + sw128_chunk_off(r, et >> 6),
-               make_uint4(pack_bf16x2(gv[0], gv[1]), pack_bf16x2(gv[2], gv[3]), pack_bf16x2(gv[4], gv[5]),
-                          pack_bf16x2(gv[6], gv[7])));
+        for (int j = 0; j < 8; ++j) {
+          const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
+          const float d0 = __uint_as_float(v[2 * j]) * __cosf(r0);
+          const float d1 = __uint_as_float(v[2 * j + 1]) * __cosf(r1);
+          dbsum += d0 + d1;
+          ds[j] = pack_bf16x2(d0, d1);
+          ys[j] = pack_bf16x2(__sinf(r0), __sinf(r1));
+        }
       };
-      if (edge) {  // prologue: dOut blocks 0 and 1
-        convert_dout(0);
-        if (n > 1) convert_dout(1);
+      if (grp == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);  // start the two groups half a cycle apart
+      for (int i = 0; i < n; ++i) {
+        const int ps = i % nph;
+        // every warp passes every phase of the phase-slot barriers (a parity wait may not skip a phase)
+        PW(1, mbar_wait(&bars[kBPhFull + ps], (i / nph) & 1));
+        if ((i & 1) != grp) {  // the other group's tile: just let the slot go (it is refilled once ALL warps passed)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[kBPhEmpty + ps]);
+          continue;
+        }
+        const int yb = grp, sb = grp, u = i >> 1;  // u: use count of this group's buffers
+        const bool tr_me = (ew & 7) == 0 && lane == 0;
+        if (tr_me) TR(11, i);
+        PW(3, mbar_wait(&bars[kBAccFull + grp], u & 1));
+        if (tr_me) TR(12, i);
+        tc_fence_after();
+        const long long tc0 = prof_on ? clock64() : 0;
+        const uint32_t ph_f = sbase + oPh + ps * kPPhSlot + (f >> 3) * kPPhChunk + (f & 7) * 2 + rh * 32 * 16;
+        const uint32_t acc = t_acc + t_lane + grp * 64 + rh * 32;
+        uint32_t ys[8], ds[8], ys1[8], ds1[8];
+        {
+          uint32_t v[16], ph[16];
+          tmem_ld16(acc, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + j * 16);
+          tmem_ld_wait();
+          batch_math(v, ph, ys, ds);
+        }
+        {
+          uint32_t v[16], ph[16];
+          tmem_ld16(acc + 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 + j) * 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {  // accumulator and phases are in registers: hand both back
+            mbar_arrive(&bars[kBAccEmpty + grp]);
+            mbar_arrive(&bars[kBPhEmpty + ps]);
+          }
+          if (tr_me) TR(13, i);
+          batch_math(v, ph, ys1, ds1);
+        }
+        if (tr_me) TR(14, i);
+        if (prof_on) pw[6] += (unsigned long long)(clock64() - tc0);
+        if (u >= 1) {  // this group's previous tile: its y consumed by the MMA, its dTheta half read out by the store
+          PW(2, mbar_wait(&bars[kBYEmpty + yb], (u - 1) & 1));
+          PW(4, mbar_wait(&bars[kBStgEmpty + sb], (u - 1) & 1));
+        }
+        if (tr_me) TR(15, i);
+        const long long ts0 = prof_on ? clock64() : 0;
+        {
+          const uint32_t yblk = oY + yb * kPHalf + (f >> 6) * kPBlk;
+          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh), make_uint4(ys[0], ys[1], ys[2], ys[3]));
+          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
+          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 2), make_uint4(ys1[0], ys1[1], ys1[2], ys1[3]));
+          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 3), make_uint4(ys1[4], ys1[5], ys1[6], ys1[7]));
+          const uint32_t blk = sbase + oStg + sb * kPHalf + (f >> 6) * kPBlk;
+          sts128(blk + sw128_chunk_off(f & 63, 4 * rh), make_uint4(ds[0], ds[1], ds[2], ds[3]));
+          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 1), make_uint4(ds[4], ds[5], ds[6], ds[7]));
+          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 2), make_uint4(ds1[0], ds1[1], ds1[2], ds1[3]));
+          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 3), make_uint4(ds1[4], ds1[5], ds1[6], ds1[7]));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&bars[kBDobFull + 0]);
-          mbar_arrive(&bars[kBRawEmpty + 0]);
-          if (n > 1) {
-            mbar_arrive(&bars[kBDobFull + 1]);
-            mbar_arrive(&bars[kBRawEmpty + 1]);
-          }
+          mbar_arrive(&bars[kBYFull + yb]);
+          mbar_arrive(&bars[kBStgFull + sb]);
         }
+        if (tr_me) TR(16, i);
+        if (prof_on) pw[8] += (unsigned long long)(clock64() - ts0);
       }
-      for (int i = 0; i < n; ++i) {
-        const int as = i & 1, ps = i % kPPhSlots;
-        PW(1, mbar_wait(&bars[kBPhFull + ps], (i / kPPhSlots) & 1));
-        PW(3, mbar_wait(&bars[kBAccFull + as], (i >> 1) & 1));
-        tc_fence_after();
-        uint32_t ys[8], ds[8];
-        PW(6, dbsum += sincos_tile(t_acc + t_lane + as * 64, sbase + S::kPh + ps * kPPhSlot, f, cg, ys, ds));
-        tc_fence_before();
-        if (i >= 1) {  // the previous tile's y has been consumed by its MMA, its dTheta half read out by the store
-          PW(2, mbar_wait(&bars[kBYEmpty], (i - 1) & 1));
-          PW(4, mbar_wait(&bars[kBStgEmpty], (i - 1) & 1));
-        }
-        store_feature_rows(sbase + S::kY, f, cg, ys);
-        store_feature_rows(sbase + S::kStg, f, cg, ds);
-        if (edge && i + 2 < n) {
-          const long long td0 = prof_on ? clock64() : 0;
-          convert_dout(i + 2);
-          if (prof_on) pw[7] += (unsigned long long)(clock64() - td0);
-        }
-        PW(8, (fence_proxy_async_smem(), __syncwarp()));
-        if (lane == 0) {
-          mbar_arrive(&bars[kBYFull]);
-          mbar_arrive(&bars[kBStgFull]);
-          mbar_arrive(&bars[kBAccEmpty + as]);
-          mbar_arrive(&bars[kBPhEmpty + ps]);
-          if (edge && i + 2 < n) {
-            mbar_arrive(&bars[kBDobFull + (i + 2) % kPDobSlots]);
-            mbar_arrive(&bars[kBRawEmpty + (i + 2) % kPRawSlots]);
-          }
-        }
-      }
-      if (et == 0) {
+      if (threadIdx.x == kPFirstEpiWarp * 32) {
         PW_FLUSH(11, 7);
         if (prof_on) {
-          p.prof[size_t(blockIdx.x) * kPipeProfSlots + 28] = pw[7];
           p.prof[size_t(blockIdx.x) * kPipeProfSlots + 29] = (unsigned long long)(clock64() - te0);
           p.prof[size_t(blockIdx.x) * kPipeProfSlots + 30] = pw[8];
         }
@@ -643,18 +799,16 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       mbar_wait(&bars[kBFin], 0);
       tc_fence_after();
       if (!edge) {
-        // dW_l[out][128 h + c] += omega_h * D[mh][out % 128][c]; this warp: M half cg >> 1, columns 64 (cg & 1) ..
-        const int mh = cg >> 1;
-        float* dst = p.grads + p.off[2 * layer] + (long long)(mh * 128 + f) * 256 + h * 128 + (cg & 1) * 64;
+        // dW_l[out][128 h + f] += omega_h * D[f][out]; this warp: outputs 64 cg .. 64 cg + 64 (lanes = consecutive inputs)
+        float* dst = p.grads + p.off[2 * layer] + h * 128 + f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(t_w + t_lane + mh * 128 + (cg & 1) * 64 + c0, v);
+          tmem_ld32(t_w + t_lane + cg * 64 + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4f(dst + c0 + j, p.omegah * __uint_as_float(v[j]), p.omegah * __uint_as_float(v[j + 1]),
-                        p.omegah * __uint_as_float(v[j + 2]), p.omegah * __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(dst + (long long)(cg * 64 + c0 + j) * 256, p.omegah * __uint_as_float(v[j]));
         }
       } else {
         // dW_f[c][128 h + f] += D[f][c]
@@ -667,17 +821,6 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           for (int j = 0; j < 16; ++j) {
             const int c = cg * 16 + j;
             if (c < C) atomicAdd(dst + (long long)c * 256, __uint_as_float(v[j]));
-          }
-        }
-        // db_f: column sums of dOut (one edge CTA per pipeline)
-        if (h == 0) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float s = dbf[jj];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const int c = (et >> 6) * 8 + jj;
-            if (lane == 0 && c < C) atomicAdd(p.grads + p.off[2 * (L + 1) + 1] + c, s);
           }
         }
         // dW_0[128 h + f][j] += omega_0 * (D[f][j] + D[f][4 + j])   (x = hi + lo)
@@ -739,6 +882,12 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   if (P > p.fwd_tiles) P = p.fwd_tiles;
   if (P < 1 || P * (L + 1) > kPipeMaxEdges) return B200INR_ERR_BAD_SHAPE;
   p.pipelines = P;
+  const char* env_skew = getenv("B200INR_BWDP_SKEW_NS");
+  p.skew_ns = env_skew != nullptr ? atoi(env_skew) : 0;
+  const char* env_dbg = getenv("B200INR_BWDP_DBG");
+  p.dbg = env_dbg != nullptr ? atoi(env_dbg) : 0;
+  const char* env_trace = getenv("B200INR_BWDP_TRACE_PTR");
+  p.trace = env_trace != nullptr ? reinterpret_cast<uint32_t*>(strtoull(env_trace, nullptr, 0)) : nullptr;
   const char* env_prof = getenv("B200INR_BWDP_PROF");
   if (env_prof != nullptr && env_prof[0] == '1' && P * S2 <= kPipeProfCtas)
     p.prof = reinterpret_cast<unsigned long long*>(st + sl.prof);

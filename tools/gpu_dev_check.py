@@ -220,6 +220,48 @@ def bwdp_profile():
         print(f"  role {role} (stage {role // 2}, h {role % 2}) tiles={n:.0f}: {txt}", flush=True)
 
 
+def bwdp_trace():
+    """Event trace of pipeline 0 of the pipelined backward (cfg2 size): prints per-role timelines of a few tiles."""
+    import numpy as np
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    net = L.make_net(d, H, Lh, C, flags=0)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    gout = torch.randn(rows, C, device=dev) * 1e-6
+    gflat = torch.zeros_like(flat)
+    nbytes = L.stash_bytes(net, rows)
+    stash = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:][:nbytes]
+    g, nb = ctypes.byref(grid), ctypes.byref(net)
+    S2, NT, NE = 2 * (Lh + 1), 256, 24
+    trace = torch.zeros(S2 * NT * NE, dtype=torch.int32, device=dev)
+    L.check(lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()), "fwd")
+    L.check(lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()), "bwd")
+    torch.cuda.synchronize()
+    os.environ["B200INR_BWDP_TRACE_PTR"] = hex(trace.data_ptr())
+    L.check(lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()), "bwd")
+    torch.cuda.synchronize()
+    del os.environ["B200INR_BWDP_TRACE_PTR"]
+    t = trace.cpu().numpy().astype(np.int64).reshape(S2, NT, NE)
+    np.save(os.path.join(ROOT, "gpurun_out", "bwdp_trace.npy"), t)
+    names = ["ld:slot_free", "ld:issued", "ch:dz_full", "ch:acc_empty", "ch:issued", "wg:y_full", "wg:issued",
+             "st:stg_full", "st:issued", "st:read_done", "st:published", "ep:start", "ep:acc_full", "ep:loaded",
+             "ep:math_done", "ep:bufs_free", "ep:arrived"]
+    for role in (0, 2, 4, 8):
+        print(f"role {role}: tile period (ep:arrived, tiles 100..200) = {(t[role, 200, 16] - t[role, 100, 16]) / 100:.0f} clk")
+        for tile in range(100, 106):
+            base = t[role, tile, 11]
+            print(f"  tile {tile} @ {base}: " + " ".join(f"{names[e]}={t[role, tile, e] - base:+d}" for e in range(17)
+                                                         if t[role, tile, e] != 0))
+
+
 def piped_vs_staged(d, Lh, C, shape, rows=None):
     """Same weights, same dL/dout: gradients of the one-kernel pipelined backward vs the staged dgrad + wgrad."""
     H = 256
@@ -275,6 +317,8 @@ if __name__ == "__main__":
         piped_vs_staged(3, 0, 5, (16, 16, 8))
     if "prof" in which:
         bwdp_profile()
+    if "trace" in which:
+        bwdp_trace()
     if "timing" in which:
         timing(False)
     if "timing_staged" in which:
