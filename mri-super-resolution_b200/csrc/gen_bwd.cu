@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // whole warp converged, one elected lane issues (umma_*_w)
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
               const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * S::kABlock;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16_ss(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
+                umma_bf16_ss_w(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
                              smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
               }
-              umma_commit(&w_empty[slot]);
+              umma_commit_w(&w_empty[slot]);
             }
           }
-          umma_commit(d_full);
+          umma_commit_w(d_full);
         }
       }
     }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // whole warp converged, one elected lane issues (umma_*_w)
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -144,12 +144,12 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
                 const uint64_t db = smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi);
-                umma_bf16_ss(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
+                umma_bf16_ss_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
               }
-              umma_commit(&w_empty[slot]);
+              umma_commit_w(&w_empty[slot]);
             }
           }
-          umma_commit(d_full);
+          umma_commit_w(d_full);
         }
       }
     }

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // the whole warp runs the loop converged, one elected lane issues (umma_*_w: no per-instruction R2UR loop)
+    {
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -149,12 +150,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) siren_bwd_kernel(const BwdPara
               tc_fence_after();
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16_ss(tmem_d + j * 256, smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi),
+                umma_bf16_ss_w(tmem_d + j * 256, smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi),
                              smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
               }
-              umma_commit(&w_empty[slot]);
+              umma_commit_w(&w_empty[slot]);
             }
-            umma_commit(&d_full[j]);
+            umma_commit_w(&d_full[j]);
           }
         }
         // the dTheta_0 tiles feed no MMA, but their a_ready phase must still be observed: a parity wait may only

@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // the whole warp runs the loop converged, one elected lane issues (umma_*_w: no per-instruction R2UR loop)
+    {
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -177,11 +178,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
                 const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                umma_bf16_ss(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+                umma_bf16_ss_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
               }
-              umma_commit(&w_empty[slot]);
+              umma_commit_w(&w_empty[slot]);
             }
-            umma_commit(&d_full[j]);
+            umma_commit_w(&d_full[j]);
           }
         }
       }

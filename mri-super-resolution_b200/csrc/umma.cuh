@@ -90,6 +90,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same with a nanosleep back-off between polls: for helper threads that run AHEAD of the critical path (loaders,
+// converters), so that their polling does not take issue slots and barrier-unit bandwidth from the warps that compute.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 24)) {
+      printf("b200inr: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar,
+             parity);
+      __trap();
+    }
+  }
+}
 // Same, with a suspend-time hint: the hardware parks the thread until the phase completes or ~`kNs` ns have passed, so a
 // warp that waits takes (almost) no issue slots away from the warps that compute.  Bounded (~4 s), then traps.
 template <uint32_t kNs = 20000>

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
       }
     } else if (warp == 1) {
       // =============================== MMA issuer ===============================
-      if (lane == 0) {
+      {  // whole warp converged, one elected lane issues (umma_*_w)
         // MN-major operands: LBO = stride between 64-wide feature blocks, SBO = 8-row groups along K.
         const uint64_t hi = smem_desc_hi_sw128(kWgBlkBytes, 1024);
         const uint32_t idesc = idesc_bf16(128, ncols, true, true);
@@ -152,12 +152,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
             for (int mh = 0; mh < 2; ++mh) {
               const uint64_t da = smem_desc(base + (2 * mh) * kWgBlkBytes + ks * 2048, hi);
               const uint64_t db = smem_desc(base + 4 * kWgBlkBytes + ks * 2048, hi);
-              umma_bf16_ss(tmem_d + mh * ncols, da, db, idesc, (s | ks) != 0);
+              umma_bf16_ss_w(tmem_d + mh * ncols, da, db, idesc, (s | ks) != 0);
             }
           }
-          umma_commit(&empty[slot]);
+          umma_commit_w(&empty[slot]);
         }
-        umma_commit(d_full);
+        umma_commit_w(d_full);
       }
     } else {
       // =============================== column sums + flush ===============================

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // whole warp converged, one elected lane issues (umma_*_w)
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -242,12 +242,12 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = smem_desc(a_base + kb * kWireABlock + k4 * 32, hi);
                 const uint64_t db = smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi);
-                umma_bf16_ss(tmem_d + nh * 256, da, db, hidden ? idesc_h : idesc_f, (kb | k4) != 0);
+                umma_bf16_ss_w(tmem_d + nh * 256, da, db, hidden ? idesc_h : idesc_f, (kb | k4) != 0);
               }
-              umma_commit(&w_empty[slot]);
+              umma_commit_w(&w_empty[slot]);
             }
           }
-          umma_commit(d_full);
+          umma_commit_w(d_full);
         }
       }
     }
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwd
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // MMA issuer
+    {  // MMA issuer: whole warp converged, one elected lane issues (umma_*_w)
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
@@ -602,11 +602,11 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwd
             const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * kWireABlock;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_ss(tmem_d, smem_desc(a_blk + k4 * 32, hi),
+              umma_bf16_ss_w(tmem_d, smem_desc(a_blk + k4 * 32, hi),
                            smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
-            umma_commit(&w_empty[slot]);
+            umma_commit_w(&w_empty[slot]);
           }
-          umma_commit(d_full);
+          umma_commit_w(d_full);
         }
       }
     }

@@ -598,3 +598,84 @@ def test_graph_replay_fit_equals_eager(dev):
                     m.query(shape, clamp_min=None).cpu().numpy()))
     np.testing.assert_allclose(res[1][0], res[0][0], rtol=2e-3)  # atomics reorder the fp32 gradient sums
     assert _relerr(res[1][1], res[0][1]) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ pipelined backward
+def _set_backward_path(m, piped):
+    """Select the one-kernel layer-pipelined backward (piped) or the staged dgrad + wgrad pair for a SIREN module."""
+    m._desc.flags = 0 if piped else L.NET_STAGED_BWD
+    return m
+
+
+@pytest.mark.parametrize("d,Lh,C,shape,drop", [(2, 2, 1, (64, 48), 0), (3, 4, 31, (32, 32, 16), 77),
+                                                 (3, 0, 5, (16, 16, 8), 0), (3, 4, 31, (64, 64, 32), 0)])
+def test_pipelined_backward_vs_oracle_and_staged(dev, d, Lh, C, shape, drop):
+    """b200inr_siren_backward of a pipelined SIREN (ONE kernel: dgrad chain + all weight / bias gradients from the
+    16-bit phase stash) against the NumPy oracle's hand-derived backward and against the staged kernels, incl. a
+    ragged row count, L = 0 (no 256x256 layer) and more tiles than pipelines."""
+    torch.manual_seed(5)
+    m = b200inr.Siren(d, 256, Lh, C).to(dev)
+    rows = int(np.prod(shape)) - drop
+    grid = L.make_grid(shape)
+    gout = torch.randn(rows, C, device=dev) / (rows * C)
+    grads = {}
+    for piped in (True, False):
+        _set_backward_path(m, piped)
+        out, stash = m._forward_rows(None, grid, rows, train=True)
+        grads[piped] = m._backward_rows(stash, None, grid, rows, gout).clone()
+        torch.cuda.synchronize()
+    assert _relerr(grads[True].cpu().numpy(), grads[False].cpu().numpy()) < 2e-3
+    Ws, bs = _weights(m)
+    coords = b200inr.get_mgrid(shape)[:rows].numpy()
+    dW, db = O.siren_backward(Ws, bs, coords, gout.cpu().numpy())
+    off = m._engine_state()["offsets"]
+    flat = grads[True].cpu().numpy()
+    for i, (w_ref, b_ref) in enumerate(zip(dW, db)):
+        assert _relerr(flat[off[2 * i]:off[2 * i] + w_ref.size].reshape(w_ref.shape), w_ref) < BF16_RELERR, f"dW{i}"
+        assert _relerr(flat[off[2 * i + 1]:off[2 * i + 1] + b_ref.size], b_ref) < BF16_RELERR, f"db{i}"
+
+
+def test_pipelined_phase_stash_gives_layer_activations(dev, golden_dir):
+    """The pipelined training forward stashes only 16-bit phases: sin(phase) of the first and last sine layer must be
+    the reference's per-layer activations (same bar as the bf16 stash of the staged path)."""
+    g, m = _golden_module(golden_dir, "siren_cfg2.npz", dev)
+    _set_backward_path(m, True)
+    shape = tuple(int(s) for s in g["grid_shape"])
+    rows = int(np.prod(shape))
+    out, stash = m._forward_rows(None, L.make_grid(shape), rows, train=True)
+    torch.cuda.synchronize()
+    tiles = (rows + 127) // 128
+    H, nl = 256, m.hidden_layers + 1
+    ph = stash[:nl * tiles * 128 * H * 2].view(torch.int16).reshape(nl, tiles, H // 8, 128, 8).cpu().numpy()
+    ph = ph.astype(np.int64) & 0xFFFF
+
+    def layer_act(layer):  # [tiles][chunk of 8 features][row][8] -> [rows, H]
+        a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 2, 1, 3).reshape(tiles * 128, H)
+        return a[:rows].astype(np.float32)
+
+    assert _relerr(layer_act(0), g["act_first"]) < BF16_RELERR
+    assert _relerr(layer_act(nl - 1), g["act_last"]) < BF16_RELERR
+    assert _relerr(out.cpu().numpy(), g["out"]) < BF16_RELERR
+
+
+def test_pipelined_fit_matches_staged_fit(dev):
+    """Fused fit (pooled LR-consistency loss) through the pipelined backward: same loss trajectory and queried volume
+    as through the staged kernels; the dgrad / wgrad entry points reject a pipelined network."""
+    shape = (32, 32, 16)
+    C = 31
+    tgt = torch.rand(shape[0] // 2 * shape[1] // 2 * shape[2], C, device=dev,
+                     generator=torch.Generator(device=dev).manual_seed(9))
+    res = {}
+    for piped in (True, False):
+        torch.manual_seed(13)
+        m = _set_backward_path(b200inr.Siren(3, 256, 4, C).to(dev), piped)
+        losses = m.fit(tgt, shape, steps=12, lr=1e-4, degrade="pool").cpu().numpy()
+        res[piped] = (losses, m.query(shape, clamp_min=None).cpu().numpy())
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-3)
+    assert _relerr(res[True][1], res[False][1]) < 1e-2
+    m = _set_backward_path(b200inr.Siren(3, 256, 4, C).to(dev), True)
+    eng = m._sync_params()
+    lib = L.load()
+    dummy = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    rc = lib.b200inr_siren_dgrad(ctypes.byref(m._desc), _ptr(eng["packed"]), _ptr(dummy), 128, _ptr(dummy), _stream())
+    assert rc == -1
