@@ -20,6 +20,8 @@ struct PackLayout {
   size_t wht;    // L x [H/64][H][64]    dgrad   B operand of hidden layer l (N = in, K = out), omega_h * W_l^T
   size_t wf;     // [H/64][32][64]       forward B operand of the final linear (N = c, K = in)
   size_t wft;    // [1][H][64]           dgrad   B operand of the final linear (N = in, K = c padded to 64)
+  size_t w0p;    // [1][H][64]           forward B operand of the FIRST layer on tensor cores (N = out, K = 32 used):
+                 //                      omega0 * W0 and omega0 * b0 split into bf16 hi + lo parts, see pack.cu
   size_t total;
 };
 
@@ -38,6 +40,8 @@ __host__ __device__ inline PackLayout make_pack_layout(int H, int L) {
   p.wf = o;
   o += size_t(H / 64) * kOutPad * 128;
   p.wft = o;
+  o += size_t(H) * 128;
+  p.w0p = o;
   o += size_t(H) * 128;
   p.total = o;
   return p;

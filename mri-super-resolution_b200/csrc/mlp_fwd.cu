@@ -48,6 +48,7 @@ struct FwdParams {
   uint8_t* stash_ph;
   uint8_t* stash_xa;  // coordinate operand of the first-layer weight gradient (wgrad.cu)
   size_t stash_layer_stride;
+  uint32_t* trace;  // tuning aid (B200INR_FWD_TRACE_PTR): CTA 0 records [phase][8] event times, phase = (pair, layer, tile)
 };
 
 template <int H>
@@ -132,6 +133,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const int num_pairs = (my_tiles + 1) / 2;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  const long long t_begin = tr ? clock64() : 0;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
@@ -139,12 +142,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       uint32_t c = 0;
       for (int pr = 0; pr < num_pairs; ++pr) {
         const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 1; l <= L + 1; ++l) {
-          const bool hidden = (l <= L);
-          const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
-          const uint32_t bytes = hidden ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
+        for (int l = 0; l <= L + 1; ++l) {
+          // l = 0: the first layer's hi/lo operand (one chunk, K = 32 used); 1..L: hidden layers; L+1: final linear
+          const bool hidden = (l >= 1 && l <= L);
+          const uint8_t* src = (l == 0) ? p.packed + p.pl.w0p
+                               : hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2
+                                        : p.packed + p.pl.wf;
+          const uint32_t bytes = (l <= L) ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
+          const int nchunks = (l == 0) ? 1 : S::kKB;
           for (int j = 0; j < nt; ++j) {
-            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+            for (int kb = 0; kb < nchunks; ++kb, ++c) {
               const uint32_t slot = c % kFwdSlots, round = c / kFwdSlots;
               if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
               mbar_arrive_expect_tx(&w_full[slot], bytes);
@@ -164,25 +171,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       uint32_t c = 0, na[2] = {0, 0};
       for (int pr = 0; pr < num_pairs; ++pr) {
         const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 1; l <= L + 1; ++l) {
+        for (int l = 0; l <= L + 1; ++l) {
           const uint32_t idesc = (l <= L) ? idesc_bf16(128, H, false, false) : idesc_bf16(128, kOutPad, false, false);
+          const int nkb = (l == 0) ? 1 : S::kKB, nk4 = (l == 0) ? 2 : 4;  // first layer: K = 32 (hi/lo coordinate operand)
           for (int j = 0; j < nt; ++j) {
+            const int tph = (pr * (L + 3) + l) * 2 + j;
+            if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 0] = uint32_t(clock64() - t_begin);
             mbar_wait(&a_ready[j], na[j] & 1);
             ++na[j];
+            if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 1] = uint32_t(clock64() - t_begin);
             tc_fence_after();
-            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
+            for (int kb = 0; kb < nkb; ++kb, ++c) {
               const uint32_t slot = c % kFwdSlots;
               mbar_wait(&w_full[slot], (c / kFwdSlots) & 1);
               tc_fence_after();
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
-                const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                umma_bf16_ss_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+                if (k4 < nk4) {
+                  const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
+                  const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+                  umma_bf16_ss_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+                }
               }
               umma_commit_w(&w_empty[slot]);
             }
             umma_commit_w(&d_full[j]);
+            if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 2] = uint32_t(clock64() - t_begin);
           }
         }
       }
@@ -193,6 +207,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       uint32_t na[2] = {0, 0};
       for (int pr = 0; pr < num_pairs; ++pr) {
         const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+        for (int j = 0; j < nt; ++j) {  // the coordinate operand of the first layer is not stashed
+          mbar_wait(&a_ready[j], na[j] & 1);
+          ++na[j];
+          mbar_arrive(&a_free[j]);
+        }
         for (int l = 0; l <= L; ++l) {
           for (int j = 0; j < nt; ++j) {
             const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
@@ -221,36 +240,51 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     for (int pr = 0; pr < num_pairs; ++pr) {
       const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
 
-      // ---- layer 0 on CUDA cores, both tiles
+      // ---- first-layer operand, both tiles: row r = [x_hi x_hi x_lo x_lo 1 1 0 ...] (bf16, K = 32 of block 0), so that
+      //      theta_0 = omega0 (W0 x + b0) comes out of ONE tcgen05.mma against the hi/lo weight operand of pack.cu
+      //      (coordinates derived from the voxel index: get_mgrid is never materialised)
       for (int j = 0; j < nt; ++j) {
         const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
         const long long row0 = (long long)tile * kTileRows;
         const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-        uint8_t* ph_row = kStash ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
-        float x[4];
-        if (p.coords != nullptr) {
-          long long row = row0 + r;
-          if (row >= p.rows) row = p.rows - 1;
-          x[0] = x[1] = x[2] = x[3] = 0.0f;
-          for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
-        } else {
-          grid_coords(p.grid, row0 + r, x);
-        }
-        if (kMode == 2 && s == 0) {  // pipelined training: compact coordinate record {hi x4, lo x4} per row
+        if (s == 0) {
+          float x[4];
+          if (p.coords != nullptr) {
+            long long row = row0 + r;
+            if (row >= p.rows) row = p.rows - 1;
+            x[0] = x[1] = x[2] = x[3] = 0.0f;
+            for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
+          } else {
+            grid_coords(p.grid, row0 + r, x);
+          }
           float hi[4], lo[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
             lo[jj] = x[jj] - hi[jj];
           }
-          reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] =
-              make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
-                         pack_bf16x2(lo[2], lo[3]));
+          const uint32_t h01 = pack_bf16x2(hi[0], hi[1]), h23 = pack_bf16x2(hi[2], hi[3]);
+          const uint32_t l01 = pack_bf16x2(lo[0], lo[1]), l23 = pack_bf16x2(lo[2], lo[3]);
+          sts128(a_addr + sw128_chunk_off(r, 0), make_uint4(h01, h23, h01, h23));
+          sts128(a_addr + sw128_chunk_off(r, 1), make_uint4(l01, l23, l01, l23));
+          sts128(a_addr + sw128_chunk_off(r, 2), make_uint4(0x3F803F80u, 0u, 0u, 0u));  // {1, 1}: the bias columns
+          sts128(a_addr + sw128_chunk_off(r, 3), make_uint4(0u, 0u, 0u, 0u));
+          if (kMode == 2)  // pipelined training: compact coordinate record {hi x4, lo x4} per row (operand of dW_0)
+            reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] = make_uint4(h01, h23, l01, l23);
         }
-        if (kStashY) {  // coordinate operand of dW_0: x = hi + lo in bf16 (exact to 2^-17), the other 56 columns zero
+        if (kStashY) {  // staged training: coordinate operand of dW_0 as a [128][64] block (cols 0..3 hi, 4..7 lo)
           uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
           uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
           if (s == 0) {
+            float x[4];
+            if (p.coords != nullptr) {
+              long long row = row0 + r;
+              if (row >= p.rows) row = p.rows - 1;
+              x[0] = x[1] = x[2] = x[3] = 0.0f;
+              for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
+            } else {
+              grid_coords(p.grid, row0 + r, x);
+            }
             float hi[4], lo[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -263,31 +297,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = c0;
           *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
         }
-#pragma unroll 1
-        for (int kb = 0; kb < S::kKB; ++kb) {
-          const int col0 = kb * 64 + s * 16;
-          float th[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float4 w = __ldg(w0_g + col0 + jj);
-            float acc = __ldg(bias_g + col0 + jj);
-            acc = fmaf(x[0], w.x, acc);
-            acc = fmaf(x[1], w.y, acc);
-            acc = fmaf(x[2], w.z, acc);
-            acc = fmaf(x[3], w.w, acc);
-            th[jj] = acc;
-          }
-          emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
-                              kStash ? ph_row + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
-        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[j]);
       }
 
-      // ---- hidden layers: X, Y, X, Y, ...
-      for (int l = 1; l <= L; ++l) {
+      // ---- sine layers 0..L: X, Y, X, Y, ...  (layer 0: the bias is part of the GEMM)
+      for (int l = 0; l <= L; ++l) {
         for (int j = 0; j < nt; ++j) {
           const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
           const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
@@ -296,12 +313,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           uint8_t* ph_l = kStash ? p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes +
                                        size_t(r) * 16
                                  : nullptr;
+          const int tph = (pr * (L + 3) + l + 1) * 2 + j;  // the MMA phase that consumes this epilogue's output
+          const bool trw = tr && et == 0 && tph < 512;
+          if (trw) p.trace[tph * 8 + 4] = uint32_t(clock64() - t_begin);
           mbar_wait(&d_full[j], nd[j] & 1);
           ++nd[j];
           if (kStashY) {
             mbar_wait(&a_free[j], nf[j] & 1);
             ++nf[j];
           }
+          if (trw) p.trace[tph * 8 + 5] = uint32_t(clock64() - t_begin);
           tc_fence_after();
           uint32_t v[16], vn[16];
           tmem_ld16(d_addr, vn);
@@ -310,7 +331,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             const int col0 = kb * 64 + s * 16;
             float4 bq[4];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            for (int j4 = 0; j4 < 4; ++j4)
+              bq[j4] = (l == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
             tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
@@ -326,10 +348,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
                                 kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
           }
+          if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[j]);
+          if (trw) p.trace[tph * 8 + 7] = uint32_t(clock64() - t_begin);
         }
       }
 
@@ -471,7 +495,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1) sire
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (leader || lane == 0) {  // leader: the whole warp runs converged, one elected lane issues; peer: one relay thread
       if (leader) {
         // =============================== MMA issuer (leader CTA) ===============================
         const uint64_t hi = smem_desc_hi_sw128(0, 1024);
@@ -495,11 +519,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1) sire
                 for (int k4 = 0; k4 < 4; ++k4) {
                   const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
                   const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                  umma_bf16_ss_2cta(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
+                  umma_bf16_ss_2cta_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
                 }
-                umma_commit_2cta(&w_empty[slot]);
+                umma_commit_2cta_w(&w_empty[slot]);
               }
-              umma_commit_2cta(&d_full[j]);
+              umma_commit_2cta_w(&d_full[j]);
             }
           }
         }
@@ -739,6 +763,8 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   p.out = out;
   p.clamp = clamp;
   p.clamp_min = clamp_min;
+  const char* env_trace = getenv("B200INR_FWD_TRACE_PTR");
+  p.trace = env_trace != nullptr ? reinterpret_cast<uint32_t*>(strtoull(env_trace, nullptr, 0)) : nullptr;
   const bool staged = (net->flags & B200INR_NET_STAGED_BWD) != 0;
   if (stash && staged) {
     StashLayout sl = make_stash_layout(H, net->hidden_layers, rows);

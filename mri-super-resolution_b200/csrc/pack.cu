@@ -34,6 +34,26 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     for (int j = 0; j < d; ++j) w[j] = p.omega0 * p.params[p.off[0] + i * d + j];
     reinterpret_cast<float4*>(p.packed + p.pl.w0)[i] = make_float4(w[0], w[1], w[2], w[3]);
   }
+  // first layer as a tensor-core operand: theta_0 = [x_hi x_hi x_lo x_lo 1 1] . [W_hi W_lo W_hi W_lo b_hi b_lo]
+  // (x = x_hi + x_lo and omega0*W = W_hi + W_lo, omega0*b = b_hi + b_lo in bf16: exact to 2^-17, fp32 accumulation).
+  // Row = output feature; columns 4g + j (g = 0..3, j = coordinate), 16 = b_hi, 17 = b_lo, the rest zero.
+  for (long long i = tid; i < (long long)H * 64; i += nthreads) {
+    const int o = int(i >> 6), k = int(i & 63);
+    float v = 0.f;
+    if (k < 16) {
+      const int g = k >> 2, j = k & 3;
+      if (j < d) {
+        const float w = p.omega0 * p.params[p.off[0] + (long long)o * d + j];
+        const float hi = __bfloat162float(__float2bfloat16_rn(w));
+        v = (g & 1) ? (w - hi) : hi;
+      }
+    } else if (k < 18) {
+      const float b = p.omega0 * p.params[p.off[1] + o];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      v = (k == 17) ? (b - hi) : hi;
+    }
+    put_bf16(p.packed + p.pl.w0p, o, k, v);
+  }
   // biases
   float* bias = reinterpret_cast<float*>(p.packed + p.pl.bias);
   for (long long i = tid; i < (long long)(L + 1) * H + 32; i += nthreads) {

@@ -341,6 +341,28 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       : "memory");
 }
 
+// Warp-converged variants for the CTA pair (see umma_bf16_ss_w).
+__device__ __forceinline__ void umma_bf16_ss_2cta_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(
+          d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+
 // ------------------------------------------------------------------ swizzled tile-block addressing
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][64 x bf16] block.
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(uint32_t row, uint32_t chunk) {

@@ -564,9 +564,10 @@ def test_wire_fused_fit_matches_module_loop(dev):
     assert _relerr(a.query(shape, clamp_min=None).cpu().numpy(), b.query(shape, clamp_min=None).cpu().numpy()) < 1e-2
 
 
-def test_cta_pair_forward_is_bit_identical(dev):
+def test_cta_pair_forward_matches_default(dev):
     """The opt-in cta_group::2 forward (B200INR_FWD_2CTA=1: one tcgen05.mma of M = 256 per CTA pair, weight chunks
-    split between the two CTAs) produces exactly the bits of the default 1-CTA kernel, query and training mode."""
+    split between the two CTAs; first layer on CUDA cores in fp32) agrees with the default 1-CTA kernel (first layer as
+    a hi/lo bf16 tensor-core GEMM) to bf16 rounding, query and training mode."""
     torch.manual_seed(41)
     m = b200inr.Siren(3, 256, 4, 31).to(dev)
     shape = (40, 33, 29)  # 38 280 rows: ragged tile count, odd number of tiles per CTA pair
@@ -580,10 +581,12 @@ def test_cta_pair_forward_is_bit_identical(dev):
         torch.cuda.synchronize()
     finally:
         del os.environ["B200INR_FWD_2CTA"]
-    assert torch.equal(pair, base)
-    assert torch.equal(out2, out1)
-    n_y_ph = 2 * 5 * ((rows + 127) // 128) * 128 * 256 * 2  # y and phase sections of the stash
-    assert torch.equal(st2[:n_y_ph], st1[:n_y_ph])
+    assert _relerr(pair.cpu().numpy(), base.cpu().numpy()) < 5e-3
+    assert _relerr(out2.cpu().numpy(), out1.cpu().numpy()) < 5e-3
+    n_y = 5 * ((rows + 127) // 128) * 128 * 256  # sin outputs of the 5 sine layers (bf16 section of the stash)
+    y1 = st1[:2 * n_y].view(torch.bfloat16).float()
+    y2 = st2[:2 * n_y].view(torch.bfloat16).float()
+    assert ((y1 - y2).norm() / y1.norm()).item() < 5e-3
 
 
 def test_graph_replay_fit_equals_eager(dev):

@@ -262,6 +262,38 @@ def bwdp_trace():
                                                          if t[role, tile, e] != 0))
 
 
+def fwd_trace():
+    """Event trace of CTA 0 of the query forward (cfg2 size)."""
+    import numpy as np
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    net = L.make_net(d, H, Lh, C)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    g, nb = ctypes.byref(grid), ctypes.byref(net)
+    trace = torch.zeros(512 * 8, dtype=torch.int32, device=dev)
+    L.check(lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 1, 0.0, None, stream()), "fwd")
+    torch.cuda.synchronize()
+    os.environ["B200INR_FWD_TRACE_PTR"] = hex(trace.data_ptr())
+    L.check(lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 1, 0.0, None, stream()), "fwd")
+    torch.cuda.synchronize()
+    del os.environ["B200INR_FWD_TRACE_PTR"]
+    t = trace.cpu().numpy().astype(np.int64).reshape(512, 8)
+    print("phase = (pair, layer l, tile j): MMA  wait_start a_ready issued | EPI(producing A for this MMA) wait_start d_full done arrived")
+    for pr in (3, 4):
+        for l in range(1, 6):
+            for j in range(2):
+                ph = (pr * 6 + l) * 2 + j
+                r = t[ph]
+                print(f"  pair {pr} l {l} tile {j}: mma {r[0]} {r[1] - r[0]:+d} {r[2] - r[0]:+d} | epi {r[4]} {r[5] - r[4]:+d} {r[6] - r[4]:+d} {r[7] - r[4]:+d}")
+
+
 def piped_vs_staged(d, Lh, C, shape, rows=None):
     """Same weights, same dL/dout: gradients of the one-kernel pipelined backward vs the staged dgrad + wgrad."""
     H = 256
@@ -319,6 +351,8 @@ if __name__ == "__main__":
         bwdp_profile()
     if "trace" in which:
         bwdp_trace()
+    if "fwd_trace" in which:
+        fwd_trace()
     if "timing" in which:
         timing(False)
     if "timing_staged" in which:
