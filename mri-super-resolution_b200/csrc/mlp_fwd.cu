@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
         const long long row0 = (long long)tile * kTileRows;
         const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-        if (s == 0) {
+        if (s == j) {  // the four warps with slice index j build tile j: the two tiles' operands are built concurrently
           float x[4];
           if (p.coords != nullptr) {
             long long row = row0 + r;
@@ -357,11 +357,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         }
       }
 
-      // ---- final linear: D[:, 0:32) + bias -> out
+      // ---- final linear: D[:, 0:32) + bias -> out.  Warp (q, s) converts rows 32 q .. x channels 8 s .. into the fp32
+      //      staging area (the LAST block of the tile's A buffer: free once the final MMA is done, and not touched by
+      //      the next pair's coordinate operand, which lives in block 0), then all warps copy it out coalesced.
       for (int j = 0; j < nt; ++j) {
         const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
         const long long row0 = (long long)tile * kTileRows;
-        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+        const uint32_t stg = smem_u32(a_smem) + j * S::kABytes + 3 * S::kABlock;
         mbar_wait(&d_full[j], nd[j] & 1);
         ++nd[j];
         if (kStashY) {
@@ -369,19 +371,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           ++nf[j];
         }
         tc_fence_after();
-        // the A tile is free (its MMAs and stash stores are done): reuse it as the fp32 output staging area
         const int C = p.C;
-        if (s == 0) {
-          uint32_t v[32];
-          tmem_ld32(tmem_d + t_lane + uint32_t(j) * 256, v);
+        {
+          uint32_t v[8];
+          tmem_ld8(tmem_d + t_lane + uint32_t(j) * 256 + s * 8, v);
           tmem_ld_wait();
-          const float* bf = bias_g + (L + 1) * H;
+          const float* bf = bias_g + (L + 1) * H + s * 8;
 #pragma unroll
-          for (int c = 0; c < kOutPad; ++c) {
-            if (c < C) {
+          for (int c = 0; c < 8; ++c) {
+            if (s * 8 + c < C) {
               float o = __uint_as_float(v[c]) + __ldg(bf + c);
               if (p.clamp) o = fmaxf(o, p.clamp_min);
-              sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
+              sts32(stg + uint32_t(r * C + s * 8 + c) * 4, __float_as_uint(o));
             }
           }
         }
@@ -391,8 +392,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         if (valid > kTileRows) valid = kTileRows;
         const int nout = int(valid) * C;
         float* dst = p.out + row0 * C;
-        for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
-        named_bar_sync(kEpiBarId, kFwdEpiThreads);  // staging consumed before the next pair overwrites A
+        for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(stg + uint32_t(i) * 4));
       }
     }
   }

@@ -287,9 +287,9 @@ def fwd_trace():
     t = trace.cpu().numpy().astype(np.int64).reshape(512, 8)
     print("phase = (pair, layer l, tile j): MMA  wait_start a_ready issued | EPI(producing A for this MMA) wait_start d_full done arrived")
     for pr in (3, 4):
-        for l in range(1, 6):
+        for l in range(0, 6):
             for j in range(2):
-                ph = (pr * 6 + l) * 2 + j
+                ph = (pr * 7 + l) * 2 + j
                 r = t[ph]
                 print(f"  pair {pr} l {l} tile {j}: mma {r[0]} {r[1] - r[0]:+d} {r[2] - r[0]:+d} | epi {r[4]} {r[5] - r[4]:+d} {r[6] - r[4]:+d} {r[7] - r[4]:+d}")
 
