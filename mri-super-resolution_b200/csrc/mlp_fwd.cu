@@ -237,71 +237,63 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
     const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
     uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
+    // ---- first-layer operand of a tile: row r = [x_hi x_hi x_lo x_lo 1 1 0 ...] (bf16, K = 32 of block 0), so that
+    //      theta_0 = omega0 (W0 x + b0) comes out of ONE tcgen05.mma against the hi/lo weight operand of pack.cu.
+    //      Coordinates are derived from the voxel index (get_mgrid is never materialised).  The four warps with slice
+    //      index s == j build tile j, so the two tiles of a pair are built concurrently; the operands of the NEXT pair
+    //      are built inside the final-layer section of the current one (coordinates computed before its TMEM wait).
+    auto tile_of = [&](int pr_, int j) { return int(blockIdx.x) + (2 * pr_ + j) * int(gridDim.x); };
+    auto coords_of = [&](int tile, float (&x)[4]) {
+      const long long row0 = (long long)tile * kTileRows;
+      if (p.coords != nullptr) {
+        long long row = row0 + r;
+        if (row >= p.rows) row = p.rows - 1;
+        x[0] = x[1] = x[2] = x[3] = 0.0f;
+        for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
+      } else {
+        grid_coords(p.grid, row0 + r, x);
+      }
+    };
+    auto put_operand = [&](int tile, int j, const float (&x)[4]) {  // all warps; x is valid in the warps with s == j
+      const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
+      if (s == j) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
+          lo[jj] = x[jj] - hi[jj];
+        }
+        const uint32_t h01 = pack_bf16x2(hi[0], hi[1]), h23 = pack_bf16x2(hi[2], hi[3]);
+        const uint32_t l01 = pack_bf16x2(lo[0], lo[1]), l23 = pack_bf16x2(lo[2], lo[3]);
+        sts128(a_addr + sw128_chunk_off(r, 0), make_uint4(h01, h23, h01, h23));
+        sts128(a_addr + sw128_chunk_off(r, 1), make_uint4(l01, l23, l01, l23));
+        sts128(a_addr + sw128_chunk_off(r, 2), make_uint4(0x3F803F80u, 0u, 0u, 0u));  // {1, 1}: the bias columns
+        sts128(a_addr + sw128_chunk_off(r, 3), make_uint4(0u, 0u, 0u, 0u));
+        if (kMode == 2)  // pipelined training: compact coordinate record {hi x4, lo x4} per row (operand of dW_0)
+          reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] = make_uint4(h01, h23, l01, l23);
+        if (kStashY)  // staged training: coordinate operand of dW_0 as a [128][64] block (cols 0..3 hi, 4..7 lo)
+          *reinterpret_cast<uint4*>(p.stash_xa + size_t(tile) * (kTileRows * 128) + sw128_chunk_off(r, 0)) =
+              make_uint4(h01, h23, l01, l23);
+      }
+      if (kStashY) {  // the other 56 columns of that block are zero: chunk 1 by slice 0, chunks 2s, 2s+1 by slice s
+        uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
+        if (s > 0) *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[j]);
+    };
+    {  // operands of the first pair
+      const int nt0 = my_tiles < 2 ? my_tiles : 2;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (s < nt0) coords_of(tile_of(0, s), x);
+      for (int j = 0; j < nt0; ++j) put_operand(tile_of(0, j), j, x);
+    }
+
     for (int pr = 0; pr < num_pairs; ++pr) {
       const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-
-      // ---- first-layer operand, both tiles: row r = [x_hi x_hi x_lo x_lo 1 1 0 ...] (bf16, K = 32 of block 0), so that
-      //      theta_0 = omega0 (W0 x + b0) comes out of ONE tcgen05.mma against the hi/lo weight operand of pack.cu
-      //      (coordinates derived from the voxel index: get_mgrid is never materialised)
-      for (int j = 0; j < nt; ++j) {
-        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
-        const long long row0 = (long long)tile * kTileRows;
-        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-        if (s == j) {  // the four warps with slice index j build tile j: the two tiles' operands are built concurrently
-          float x[4];
-          if (p.coords != nullptr) {
-            long long row = row0 + r;
-            if (row >= p.rows) row = p.rows - 1;
-            x[0] = x[1] = x[2] = x[3] = 0.0f;
-            for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
-          } else {
-            grid_coords(p.grid, row0 + r, x);
-          }
-          float hi[4], lo[4];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
-            lo[jj] = x[jj] - hi[jj];
-          }
-          const uint32_t h01 = pack_bf16x2(hi[0], hi[1]), h23 = pack_bf16x2(hi[2], hi[3]);
-          const uint32_t l01 = pack_bf16x2(lo[0], lo[1]), l23 = pack_bf16x2(lo[2], lo[3]);
-          sts128(a_addr + sw128_chunk_off(r, 0), make_uint4(h01, h23, h01, h23));
-          sts128(a_addr + sw128_chunk_off(r, 1), make_uint4(l01, l23, l01, l23));
-          sts128(a_addr + sw128_chunk_off(r, 2), make_uint4(0x3F803F80u, 0u, 0u, 0u));  // {1, 1}: the bias columns
-          sts128(a_addr + sw128_chunk_off(r, 3), make_uint4(0u, 0u, 0u, 0u));
-          if (kMode == 2)  // pipelined training: compact coordinate record {hi x4, lo x4} per row (operand of dW_0)
-            reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] = make_uint4(h01, h23, l01, l23);
-        }
-        if (kStashY) {  // staged training: coordinate operand of dW_0 as a [128][64] block (cols 0..3 hi, 4..7 lo)
-          uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
-          uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
-          if (s == 0) {
-            float x[4];
-            if (p.coords != nullptr) {
-              long long row = row0 + r;
-              if (row >= p.rows) row = p.rows - 1;
-              x[0] = x[1] = x[2] = x[3] = 0.0f;
-              for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
-            } else {
-              grid_coords(p.grid, row0 + r, x);
-            }
-            float hi[4], lo[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
-              lo[jj] = x[jj] - hi[jj];
-            }
-            c0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
-                            pack_bf16x2(lo[2], lo[3]));
-          }
-          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = c0;
-          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[j]);
-      }
 
       // ---- sine layers 0..L: X, Y, X, Y, ...  (layer 0: the bias is part of the GEMM)
       for (int l = 0; l <= L; ++l) {
@@ -360,6 +352,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       // ---- final linear: D[:, 0:32) + bias -> out.  Warp (q, s) converts rows 32 q .. x channels 8 s .. into the fp32
       //      staging area (the LAST block of the tile's A buffer: free once the final MMA is done, and not touched by
       //      the next pair's coordinate operand, which lives in block 0), then all warps copy it out coalesced.
+      const int rest = my_tiles - 2 * (pr + 1);
+      const int nt_next = rest < 0 ? 0 : (rest < 2 ? rest : 2);
+      float xn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (s < nt_next) coords_of(tile_of(pr + 1, s), xn);  // index arithmetic overlaps the wait for the final MMA
       for (int j = 0; j < nt; ++j) {
         const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
         const long long row0 = (long long)tile * kTileRows;
@@ -387,6 +383,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           }
         }
         tc_fence_before();
+        // the tile's accumulator and A blocks 0..2 are free: hand the next pair's first-layer operand to the MMA warp
+        // now, so that its layer-0 MMA runs under the copy-out below and under the other tile's final epilogue
+        if (j < nt_next) put_operand(tile_of(pr + 1, j), j, xn);
         named_bar_sync(kEpiBarId, kFwdEpiThreads);
         long long valid = p.rows - row0;
         if (valid > kTileRows) valid = kTileRows;
@@ -394,6 +393,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         float* dst = p.out + row0 * C;
         for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(stg + uint32_t(i) * 4));
       }
+      // every warp has copied its share out of the staging blocks before any warp's next-pair epilogue overwrites them
+      named_bar_sync(kEpiBarId, kFwdEpiThreads);
     }
   }
 
