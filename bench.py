@@ -210,10 +210,20 @@ def run_ours(args):
     host_loss = torch.zeros(1).pin_memory()
     sync()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def e2e_loop(n):
+        # every step: H2D of its input (the acquired LR volume, pinned memory) and D2H of its result (the loss).  The
+        # copy of step i + 1's input is issued on a side stream while step i computes (double-buffered target).
+        sess.stage_target(lr_host)
+        for i in range(n):
+            sess.commit_target()               # this step's input is in place (the compute stream waits for its copy)
+            if i + 1 < n:
+                sess.stage_target(lr_host)     # next step's input starts travelling
+            host_loss.copy_(sess.step(), non_blocking=False)
+
+    e2e_loop(max(3, args.warmup))              # warm-up of the side stream / back buffer (untimed)
+    sync()
     t0.record()
-    for _ in range(e2e_steps):
-        sess.set_target(lr_host)               # H2D of this step's input (the acquired LR volume), pinned memory
-        host_loss.copy_(sess.step(), non_blocking=False)  # D2H of the step's result
+    e2e_loop(e2e_steps)
     t1.record()
     sync()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
@@ -279,7 +289,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "global_grid": list(gshape), "rows_per_gpu": rows,
                    "parallelism": f"coordinate slabs x{world}, 1 all-reduce of {sess.n_flat + 4} fp32 per step",
                    "l2": "per-step working set (activation stash 8.2 GB/GPU) exceeds the 126 MB L2; no flush needed",
-                   "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state"},
+                   "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state",
+                   "e2e": "per step: H2D of the LR volume from pinned host memory (double-buffered, issued on a side "
+                          "stream while the previous step computes) + D2H of the loss, through FitSession"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coord-samples/s", "h2d_bytes_per_step": int(lr_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},

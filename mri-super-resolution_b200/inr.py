@@ -567,6 +567,7 @@ class FitSession:
         # forward, loss, backward (dgrad + wgrad when staged), adam, adam_tick, pack
         self.kernel_launches_per_step = 6 if self.piped else 7
         self._graph = None
+        self._copy_stream = None
 
     def capture(self):
         """Capture one step (memset + 7 kernels, all stream-ordered, Adam's step counter on the device) into a CUDA
@@ -583,6 +584,30 @@ class FitSession:
     def set_target(self, target):
         """Replace the target values (same size), e.g. from pinned host memory."""
         self.target.copy_(target.reshape(-1), non_blocking=True)
+
+    def stage_target(self, host_target):
+        """Start the host-to-device copy of the NEXT step's target (pinned host memory) on a side stream into the back
+        buffer, so that it travels while the current step computes; commit_target() makes it the current target."""
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+                self._target_back = torch.empty_like(self.target)
+                self._copy_done = torch.cuda.Event()
+                self._steps_done = torch.cuda.Event()
+            if self._graph is not None:
+                raise RuntimeError("b200inr: staged targets cannot be combined with a captured step graph")
+            # the back buffer was the target of the step before last: every step issued so far must be done with it
+            self._steps_done.record(torch.cuda.current_stream())
+            self._copy_stream.wait_event(self._steps_done)
+            with torch.cuda.stream(self._copy_stream):
+                self._target_back.copy_(host_target.reshape(-1), non_blocking=True)
+                self._copy_done.record(self._copy_stream)
+
+    def commit_target(self):
+        """Make the staged target current (the compute stream waits for its copy)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().wait_event(self._copy_done)
+            self.target, self._target_back = self._target_back, self.target
 
     def step(self, marks=None):
         if self._graph is not None and marks is None:

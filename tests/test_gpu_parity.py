@@ -682,3 +682,29 @@ def test_pipelined_fit_matches_staged_fit(dev):
     dummy = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
     rc = lib.b200inr_siren_dgrad(ctypes.byref(m._desc), _ptr(eng["packed"]), _ptr(dummy), 128, _ptr(dummy), _stream())
     assert rc == -1
+
+
+def test_staged_host_targets_equal_direct_upload(dev):
+    """FitSession.stage_target / commit_target (next step's LR volume copied from pinned host memory on a side stream
+    while the current step computes) gives the trajectory of uploading the target before every step."""
+    shape, C = (32, 32, 16), 31
+    host = [torch.rand(shape[0] // 2 * shape[1] // 2 * shape[2] * C, generator=torch.Generator().manual_seed(k)).pin_memory()
+            for k in range(3)]
+    res = []
+    for staged in (False, True):
+        torch.manual_seed(21)
+        m = b200inr.Siren(3, 256, 4, C).to(dev)
+        sess = b200inr.FitSession(m, host[0].to(dev), shape, lr=1e-4, degrade="pool")
+        losses = []
+        if staged:
+            sess.stage_target(host[0])
+        for i in range(9):
+            if staged:
+                sess.commit_target()
+                if i + 1 < 9:
+                    sess.stage_target(host[(i + 1) % 3])
+            else:
+                sess.set_target(host[i % 3])
+            losses.append(float(sess.step().item()))
+        res.append(losses)
+    np.testing.assert_allclose(res[1], res[0], rtol=2e-3)
