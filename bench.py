@@ -9,7 +9,8 @@ Workload at N = 1 = BASELINE configs[1]: SIREN 3 -> 5x256 -> 31 fitted to a synt
 the 2x2x1 LR-consistency loss, full batch (1 048 576 coordinates per step), Adam lr 1e-4.  At N > 1 every rank owns
 its own 128-plane slab of a (128 N)x128x64 volume (weak scaling) and the flat [gradient | loss] buffer is all-reduced
 once per step.  A step = zero-grad, fused forward, pooled loss + its gradient, fused dgrad, wgrad, [all-reduce],
-Adam, bf16 re-staging.  One JSON line is printed by rank 0.
+Adam, bf16 re-staging (dgrad + wgrad are ONE layer-pipelined kernel by default; B200INR_PIPED_BWD=0 selects the staged
+pair).  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -253,20 +254,25 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel
     peaks = measured_peaks()
+    piped = sess.piped  # one-kernel backward: the 'dgrad' slot holds siren_bwdp_kernel, the 'wgrad' slot is empty
+    flop_kernel = dict(FLOP_KERNEL)
+    kernel_name = {"forward": "siren_fwd_kernel", "dgrad": "siren_bwd_kernel", "wgrad": "wgrad_kernel"}
+    if piped:
+        flop_kernel["dgrad"] = FLOP_KERNEL["dgrad"] + FLOP_KERNEL["wgrad"]
+        kernel_name["dgrad"] = "siren_bwdp_kernel"
     dom = max(("forward", "dgrad", "wgrad", "loss"), key=lambda k: stage_ms[k])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        traffic = json.load(open(tpath)).get("pipelined_backward" if (piped and dom == "dgrad") else dom)
     if dom == "loss":
         alg_bytes = rows * C_OUT * 4 * 2 + rows * C_OUT  # read pred, write grad, read LR target (1/4)
         achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
         roofline = {"kernel": "pool_mse_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["gbs"],
                     "unit": "GB/s", "frac": achieved / peaks["gbs"], "traffic": traffic, "peak_source": peaks["src"]}
     else:
-        achieved = FLOP_KERNEL[dom] * rows / (stage_ms[dom] * 1e-3) / 1e12
-        roofline = {"kernel": {"forward": "siren_fwd_kernel", "dgrad": "siren_bwd_kernel",
-                               "wgrad": "siren_wgrad_kernel"}[dom],
+        achieved = flop_kernel[dom] * rows / (stage_ms[dom] * 1e-3) / 1e12
+        roofline = {"kernel": kernel_name[dom],
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"] or peaks["tflops"],
                     "unit": "TFLOP/s", "frac": achieved / (peaks["tflops_sustained"] or peaks["tflops"]),
                     "traffic": traffic, "peak_source": peaks["src"] + " (sustained: kernel timed inside the step)"}
@@ -288,7 +294,9 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_grid": list(gshape), "rows_per_gpu": rows,
                    "parallelism": f"coordinate slabs x{world}, 1 all-reduce of {sess.n_flat + 4} fp32 per step",
-                   "l2": "per-step working set (activation stash 8.2 GB/GPU) exceeds the 126 MB L2; no flush needed",
+                   "l2": f"per-step working set (activation stash {sess.stash.numel() / 1e9:.1f} GB/GPU) exceeds the 126 MB L2; "
+                         "no flush needed",
+                   "backward": "pipelined (one kernel, phase-only stash)" if piped else "staged (dgrad + wgrad)",
                    "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state",
                    "e2e": "per step: H2D of the LR volume from pinned host memory (double-buffered, issued on a side "
                           "stream while the previous step computes) + D2H of the loss, through FitSession"},

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200inr.so")
 MAX_TAPS = 8
 ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2
 IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
-DEFAULT_PIPED_BWD = "0"  # host default until the pipelined kernel beats the staged pair on the bench
+DEFAULT_PIPED_BWD = "1"  # raw-coordinate SIRENs train through the pipelined backward (B200INR_PIPED_BWD=0: staged)
 NET_STAGED_BWD = 1  # B200INR_NET_STAGED_BWD: the older forward-stash / dgrad / wgrad training path of raw-coordinate SIRENs
 
 

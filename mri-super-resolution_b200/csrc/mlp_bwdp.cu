@@ -189,6 +189,12 @@ __device__ __forceinline__ void bulk_wait_group() {
   asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+static __device__ __noinline__ void flag_timeout(const uint32_t* f0, const uint32_t* f1, uint32_t target, uint32_t a,
+                                          uint32_t b) {
+  printf("b200inr: pipeline flag timeout block %d thread %d flags %p %p target %u (%u, %u)\n", blockIdx.x, threadIdx.x,
+         (const void*)f0, (const void*)f1, target, a, b);
+  __trap();
+}
 // Wait until both counters reach `target`; `k0`, `k1` cache the last values seen (the counters only grow).
 // Bounded: a mis-programmed pipeline traps instead of hanging.
 __device__ __forceinline__ void poll2_ge(const uint32_t* f0, const uint32_t* f1, uint32_t target, uint32_t& k0,
@@ -200,11 +206,7 @@ __device__ __forceinline__ void poll2_ge(const uint32_t* f0, const uint32_t* f1,
     k1 = b;
     if (k0 >= target && k1 >= target) break;
     __nanosleep(32);
-    if (++spins > (1u << 23)) {
-      printf("b200inr: pipeline flag timeout block %d thread %d flags %p %p target %u (%u, %u)\n", blockIdx.x,
-             threadIdx.x, (const void*)f0, (const void*)f1, target, a, b);
-      __trap();
-    }
+    if (++spins > (1u << 23)) flag_timeout(f0, f1, target, a, b);
   }
 }
 
@@ -248,6 +250,9 @@ __device__ __forceinline__ float rad_lo16(uint32_t w) {
   return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), kPhToRad, kPhBias);
 }
 
+// kInstr = true compiles the stall counters / event trace in (tuning runs only): they double every wait statement and
+// push the hot loops out of the instruction cache (no_instruction stalls 1.8 per issue with them).
+template <bool kInstr>
 __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipeParams p) {
   using S = PSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -337,8 +342,8 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   const uint64_t hiK = smem_desc_hi_sw128(0, 1024);       // K-major blocks
   const uint64_t hiMN = smem_desc_hi_sw128(kPBlk, 1024);  // MN-major: 64-wide MN blocks kPBlk apart
 
-  const bool prof_on = p.prof != nullptr;
-  const bool trace_on = p.trace != nullptr && pipe == 0;
+  const bool prof_on = kInstr && p.prof != nullptr;
+  const bool trace_on = kInstr && p.trace != nullptr && pipe == 0;
   const long long t_begin = (prof_on || trace_on) ? clock64() : 0;
 
   if (n > 0) {
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             if (lane == 0) TR(3, i);
             tc_fence_after();
             const uint32_t dz = sbase + S::kDz + ds * kPTile;
-#pragma unroll
+#pragma unroll 1  // (compact loops: this warp shares an instruction cache with four epilogue warps)
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
 
       // sin / cos of 16 phases, dTheta = D .* cos; packs y (sin) and dTheta as bf16 pairs along the rows
       auto batch_math = [&](const uint32_t (&v)[16], const uint32_t (&ph)[16], uint32_t (&ys)[8], uint32_t (&ds)[8]) {
-        if (p.dbg & 1) {  // tuning aid: no sin / cos work (results are garbage), shows the pure pipeline rate
+        if (kInstr && (p.dbg & 1)) {  // tuning aid: no sin / cos work (results are garbage), shows the pure pipeline rate
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             ds[j] = v[2 * j] ^ ph[2 * j + 1];
@@ -725,55 +730,44 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         const bool tr_me = (ew & 7) == 0 && lane == 0;
         if (tr_me) TR(11, i);
         PW(3, mbar_wait(&bars[kBAccFull + grp], u & 1));
+        if (u >= 1) {  // this group's previous tile: its y consumed by the MMA, its dTheta half read out by the store
+          PW(2, mbar_wait(&bars[kBYEmpty + yb], (u - 1) & 1));
+          PW(4, mbar_wait(&bars[kBStgEmpty + sb], (u - 1) & 1));
+        }
         if (tr_me) TR(12, i);
         tc_fence_after();
         const long long tc0 = prof_on ? clock64() : 0;
         const uint32_t ph_f = sbase + oPh + ps * kPPhSlot + (f >> 3) * kPPhChunk + (f & 7) * 2 + rh * 32 * 16;
         const uint32_t acc = t_acc + t_lane + grp * 64 + rh * 32;
-        uint32_t ys[8], ds[8], ys1[8], ds1[8];
-        {
-          uint32_t v[16], ph[16];
-          tmem_ld16(acc, v);
+        const uint32_t yblk = oY + yb * kPHalf + (f >> 6) * kPBlk;
+        const uint32_t dblk = sbase + oStg + sb * kPHalf + (f >> 6) * kPBlk;
+        // two batches of 16 rows; NOT unrolled: the loop body has to stay inside the instruction cache
+#pragma unroll 1
+        for (int b2 = 0; b2 < 2; ++b2) {
+          uint32_t v[16], ph[16], ys[8], ds[8];
+          tmem_ld16(acc + 16 * b2, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + j * 16);
+          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 * b2 + j) * 16);
           tmem_ld_wait();
-          batch_math(v, ph, ys, ds);
-        }
-        {
-          uint32_t v[16], ph[16];
-          tmem_ld16(acc + 16, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 + j) * 16);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {  // accumulator and phases are in registers: hand both back
-            mbar_arrive(&bars[kBAccEmpty + grp]);
-            mbar_arrive(&bars[kBPhEmpty + ps]);
+          if (b2 == 1) {  // accumulator and phases are in registers: hand both back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&bars[kBAccEmpty + grp]);
+              mbar_arrive(&bars[kBPhEmpty + ps]);
+            }
+            if (tr_me) TR(13, i);
           }
-          if (tr_me) TR(13, i);
-          batch_math(v, ph, ys1, ds1);
+          batch_math(v, ph, ys, ds);
+          const uint32_t ch = 4 * rh + 2 * b2;
+          sts128(yblk + sw128_chunk_off(f & 63, ch), make_uint4(ys[0], ys[1], ys[2], ys[3]));
+          sts128(yblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
+          sts128(dblk + sw128_chunk_off(f & 63, ch), make_uint4(ds[0], ds[1], ds[2], ds[3]));
+          sts128(dblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ds[4], ds[5], ds[6], ds[7]));
         }
         if (tr_me) TR(14, i);
         if (prof_on) pw[6] += (unsigned long long)(clock64() - tc0);
-        if (u >= 1) {  // this group's previous tile: its y consumed by the MMA, its dTheta half read out by the store
-          PW(2, mbar_wait(&bars[kBYEmpty + yb], (u - 1) & 1));
-          PW(4, mbar_wait(&bars[kBStgEmpty + sb], (u - 1) & 1));
-        }
-        if (tr_me) TR(15, i);
         const long long ts0 = prof_on ? clock64() : 0;
-        {
-          const uint32_t yblk = oY + yb * kPHalf + (f >> 6) * kPBlk;
-          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh), make_uint4(ys[0], ys[1], ys[2], ys[3]));
-          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
-          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 2), make_uint4(ys1[0], ys1[1], ys1[2], ys1[3]));
-          sts128(yblk + sw128_chunk_off(f & 63, 4 * rh + 3), make_uint4(ys1[4], ys1[5], ys1[6], ys1[7]));
-          const uint32_t blk = sbase + oStg + sb * kPHalf + (f >> 6) * kPBlk;
-          sts128(blk + sw128_chunk_off(f & 63, 4 * rh), make_uint4(ds[0], ds[1], ds[2], ds[3]));
-          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 1), make_uint4(ds[4], ds[5], ds[6], ds[7]));
-          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 2), make_uint4(ds1[0], ds1[1], ds1[2], ds1[3]));
-          sts128(blk + sw128_chunk_off(f & 63, 4 * rh + 3), make_uint4(ds1[4], ds1[5], ds1[6], ds1[7]));
-        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -893,9 +887,15 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
     p.prof = reinterpret_cast<unsigned long long*>(st + sl.prof);
   if (cudaMemsetAsync(p.flags, 0, sl.flags_bytes, stream) != cudaSuccess) return B200INR_ERR_CUDA;
   const int smem = PSmem::kBytes + 1024;
-  if (cudaFuncSetAttribute(siren_bwdp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return B200INR_ERR_CUDA;
-  siren_bwdp_kernel<<<P * S2, kPThreads, smem, stream>>>(p);
+  if (p.prof != nullptr || p.trace != nullptr || p.dbg != 0) {
+    if (cudaFuncSetAttribute(siren_bwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return B200INR_ERR_CUDA;
+    siren_bwdp_kernel<true><<<P * S2, kPThreads, smem, stream>>>(p);
+  } else {
+    if (cudaFuncSetAttribute(siren_bwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return B200INR_ERR_CUDA;
+    siren_bwdp_kernel<false><<<P * S2, kPThreads, smem, stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 

@@ -78,15 +78,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a mis-programmed pipeline traps instead of hanging the GPU box.
+// Bounded spin: a mis-programmed pipeline traps instead of hanging the GPU box.  The report is out of line so that the
+// ~40 wait sites of a warp-specialised kernel do not drag printf argument set-up through the instruction cache.
+static __device__ __noinline__ void mbar_timeout(const void* bar, uint32_t parity) {
+  printf("b200inr: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("b200inr: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
-             (void*)bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);
   }
 }
 

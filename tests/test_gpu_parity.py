@@ -107,6 +107,7 @@ def test_forward_vs_reference_golden(dev, golden_dir, name):
 def test_per_layer_activations(dev, golden_dir):
     """Activations after the first and the last sine layer, read back from the training stash (bf16)."""
     g, m = _golden_module(golden_dir, "siren_cfg2.npz", dev)
+    m._desc.flags = L.NET_STAGED_BWD  # the staged training path keeps the sin outputs (the pipelined one: phases only)
     shape = tuple(int(s) for s in g["grid_shape"])
     rows = int(np.prod(shape))
     eng = m._sync_params()
@@ -570,6 +571,7 @@ def test_cta_pair_forward_matches_default(dev):
     a hi/lo bf16 tensor-core GEMM) to bf16 rounding, query and training mode."""
     torch.manual_seed(41)
     m = b200inr.Siren(3, 256, 4, 31).to(dev)
+    m._desc.flags = L.NET_STAGED_BWD  # the pair kernel implements the staged (y-stash) training mode
     shape = (40, 33, 29)  # 38 280 rows: ragged tile count, odd number of tiles per CTA pair
     rows = int(np.prod(shape))
     base = m.query(shape, clamp_min=None)
