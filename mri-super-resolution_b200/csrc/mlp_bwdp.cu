@@ -246,8 +246,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // phase (u16, 65536 = one turn) -> radians: float(2^23 + ph) is built with one PRMT, then one FFMA
 constexpr float kPhToRad = 9.587379924285257e-05f;   // 2*pi / 65536
 constexpr float kPhBias = -804.247719318987f;        // -(2^23) * 2*pi / 65536
-__device__ __forceinline__ float rad_lo16(uint32_t w) {
-  return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), kPhToRad, kPhBias);
+__device__ __forceinline__ float rad_lo16(uint32_t w) {  // w: zero-extended 16-bit phase
+  return fmaf(__uint_as_float(w | 0x4B000000u), kPhToRad, kPhBias);
 }
 
 // kInstr = true compiles the stall counters / event trace in (tuning runs only): they double every wait statement and
@@ -741,24 +741,33 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         const uint32_t acc = t_acc + t_lane + grp * 64 + rh * 32;
         const uint32_t yblk = oY + yb * kPHalf + (f >> 6) * kPBlk;
         const uint32_t dblk = sbase + oStg + sb * kPHalf + (f >> 6) * kPBlk;
-        // two batches of 16 rows; NOT unrolled: the loop body has to stay inside the instruction cache
-#pragma unroll 1
+        // the whole 32-row accumulator slice goes to registers first and is handed back at once: the chain MMA of
+        // this group's NEXT tile (same accumulator) then runs under the sin / cos work below
+        uint32_t v[32];
+        tmem_ld32(acc, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kBAccEmpty + grp]);
+        if (tr_me) TR(13, i);
+#pragma unroll
         for (int b2 = 0; b2 < 2; ++b2) {
-          uint32_t v[16], ph[16], ys[8], ds[8];
-          tmem_ld16(acc + 16 * b2, v);
+          uint32_t ph[16], ys[8], ds[8];
 #pragma unroll
           for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 * b2 + j) * 16);
-          tmem_ld_wait();
-          if (b2 == 1) {  // accumulator and phases are in registers: hand both back
-            tc_fence_before();
+          if (b2 == 1) {  // all phases are in registers: hand the slot back
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&bars[kBAccEmpty + grp]);
-              mbar_arrive(&bars[kBPhEmpty + ps]);
-            }
-            if (tr_me) TR(13, i);
+            if (lane == 0) mbar_arrive(&bars[kBPhEmpty + ps]);
           }
-          batch_math(v, ph, ys, ds);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
+            const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * __cosf(r0);
+            const float d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * __cosf(r1);
+            dbsum += d0 + d1;
+            ds[j] = pack_bf16x2(d0, d1);
+            ys[j] = pack_bf16x2(__sinf(r0), __sinf(r1));
+          }
           const uint32_t ch = 4 * rh + 2 * b2;
           sts128(yblk + sw128_chunk_off(f & 63, ch), make_uint4(ys[0], ys[1], ys[2], ys[3]));
           sts128(yblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
