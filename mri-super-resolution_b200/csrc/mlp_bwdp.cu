@@ -14,13 +14,13 @@
 // the 64-row tiles.  Every CTA is WEIGHT-STATIONARY for its whole life, with its weights IN TENSOR MEMORY:
 //   stage CTA (l, h), l = L..1, h = 0/1 (feature half):                                   [the 256x256 layers]
 //       TMEM: rows [128h, 128h+128) of W'_l^T (A operand, 128 columns), the block dW_l[:, 128h..]^T (256 columns),
-//             one chain accumulator (64 columns), two y operands (2 x 32 columns) = all 512 columns;
+//             two chain accumulators (2 x 64 columns) = all 512 columns;
 //       per tile:  receive dTheta_l (64 rows x 256, bf16, 32 KB)                          <- ring l
 //                  D^T[in-half, rows]   = W'_l^T[in-half, :] dTheta_l^T                   (tcgen05 128 x 64 x 256, A in TMEM)
 //                  s, c = sin, cos(phase_l-1) for its 128 features x 64 rows              (phases: bulk copy from HBM)
 //                  dTheta_l-1[:, half]  = D .* c  -> bf16                                  -> ring l-1
-//                  y^T = s -> bf16 -> TMEM (tcgen05.st)
-//                  dW_l[:, half]^T     += y^T dTheta_l                                     (tcgen05 128 x 256 x 64, A in TMEM)
+//                  y^T = s -> bf16 -> shared memory, feature-major
+//                  dW_l[:, half]^T     += y^T dTheta_l                                     (tcgen05 128 x 256 x 64)
 //                  db_l-1[half]        += colsum(dTheta_l-1)                               (registers: lane = feature)
 //   edge CTA E(h):                                                                        [both ends of the chain]
 //       top:     dOut tile -> bf16, D^T = W_f^T[half] dOut^T, s, c of phase_L, dTheta_L = D .* c -> ring L,
@@ -29,10 +29,11 @@
 //                dW_0[half]   += dTheta_0^T [x_hi | x_lo]    (coordinate records stashed by the forward)
 // The chain is computed TRANSPOSED (features on the 128 TMEM lanes, tile rows on the columns): a tile may have any row
 // count (64 here) at full tensor-core rate, the bias gradient is a per-thread running sum, one thread owns one feature
-// for 16 rows, so sin outputs go to TMEM and dTheta to shared memory with 16-byte stores.  A dTheta tile is stored
+// for 32 rows, so sin outputs and dTheta go to shared memory with 16-byte stores.  A dTheta tile is stored
 // FEATURE-major ([64 features][64 rows] swizzled blocks): read with MN-major descriptors it is the B operand of the
 // chain step (N = rows, K = features), with K-major descriptors the B operand of the weight-gradient step
-// (N = features, K = rows).  Shared-memory traffic per tile: 160 KB (operands in TMEM take none).
+// (N = features, K = rows).  Two groups of 8 epilogue warps alternate tiles, so one group's barrier / fence / TMEM
+// latency hides behind the other's sin / cos work.  The hot loops are kept small on purpose (see the kInstr note).
 //
 // Rings: per pipeline and layer boundary kPipeRing slots of one tile; producers bulk-store their half and publish it
 // with a bulk add on a counter (no generic-proxy fence), consumers poll (acquire), bulk-load and return a credit
