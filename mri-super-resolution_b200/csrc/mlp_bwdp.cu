@@ -63,7 +63,7 @@ constexpr int kPStgSlots = 2;                   // outgoing dTheta halves
 constexpr int kPDobSlots = 4;                   // edge: bf16 dOut blocks
 constexpr int kPRawSlots = 2;                   // edge: raw fp32 dOut tiles (bulk-copied ahead of the conversion)
 constexpr int kPZSlots = 2;                     // edge bottom: dTheta_0 slots
-constexpr int kPStoreDepth = 2;                 // bulk stores in flight per ring-store thread
+constexpr int kPStoreDepth = 1;                 // bulk stores in flight per ring-store thread
 constexpr int kPBlk = kPipeTileRows * 128;      // one [64][64] bf16 block: 8 KB
 constexpr int kPHalf = 2 * kPBlk;               // 128 features of a tile: 16 KB
 constexpr int kPTile = 4 * kPBlk;               // 256 features of a tile: 32 KB
