@@ -85,7 +85,7 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
     }
     sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
     if (kStash)
-      *reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * (kTileRows * 16)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * (kTileRows * 16)), make_uint4(ph[0], ph[1], ph[2], ph[3]));
   }
 }
 
