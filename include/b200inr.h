@@ -36,7 +36,7 @@ extern "C" {
                                (ComplexGaborLayer2D, INR/INRmodel.py:109-120; WIRE network INR/wiretest.ipynb cell 2):
                                hidden_features = H complex units (128), IN_COORDS only */
 
-#define B200INR_IN_COORDS 0   /* network input = the d <= 4 raw coordinates; first layer on CUDA cores (H = 256)   */
+#define B200INR_IN_COORDS 0   /* network input = the d <= 4 raw coordinates; H <= 256, multiple of 8 (zero-padded) */
 #define B200INR_IN_FOURIER 1  /* network input = input_mapping(coords, B) (INR/SRDWI.py:111-116) computed in-kernel
                                  from the d raw coordinates; in_features = d, first layer K = 2 * mapping_size      */
 #define B200INR_IN_FEATURES 2 /* network input = explicit fp32 feature rows [rows, in_features] (what the reference
@@ -45,7 +45,7 @@ extern "C" {
 /* Network description == ctor arguments of Siren (INR/SRDWI.py:68-71, INR/INRmodel.py:123-125). */
 typedef struct b200inr_net {
   int32_t in_features;     /* IN_COORDS / IN_FOURIER: d = 1..4; IN_FEATURES: K0, a multiple of 64, <= H        */
-  int32_t hidden_features; /* H: 256 (all modes) or 512 (IN_FOURIER / IN_FEATURES)                           */
+  int32_t hidden_features; /* H: IN_COORDS 8..256 (multiple of 8); IN_FOURIER / IN_FEATURES 256 or 512      */
   int32_t hidden_layers;   /* L, hidden->hidden layers; there are L+1 activated layers + 1 final linear      */
   int32_t out_features;    /* C, 1..32                                                                       */
   float first_omega_0;     /* omega of the first SineLayer (INR/SRDWI.py:78)                                  */

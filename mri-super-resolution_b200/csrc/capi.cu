@@ -64,8 +64,9 @@ static int check_net(const b200inr_net* net) {
   }
   if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
   switch (net->input_mode) {
-    case B200INR_IN_COORDS:  // SIREN on raw coordinates: first layer on CUDA cores, H = 256
-      if (H != 256 || net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
+    case B200INR_IN_COORDS:  // SIREN on raw coordinates: any width up to 256 (multiple of 8) runs on the 256-wide
+                             // kernels with zero-padded operands; parameters and gradients keep the real width
+      if (H < 8 || H > kSirenWidth || H % 8 != 0 || net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
       if (net->in_features < 1 || net->in_features > 4 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
       return B200INR_OK;
     case B200INR_IN_FOURIER: {
@@ -169,7 +170,7 @@ int b200inr_packed_bytes(const b200inr_net* net, size_t* bytes) {
   if (!bytes) return B200INR_ERR_NULL;
   *bytes = is_wire(net) ? make_wire_pack_layout(make_wire_dims(net)).total
            : is_gen(net) ? make_gen_pack_layout(make_gen_dims(net)).total
-                         : make_pack_layout(net->hidden_features, net->hidden_layers).total;
+                         : make_pack_layout(kSirenWidth, net->hidden_layers).total;
   return B200INR_OK;
 }
 
@@ -193,8 +194,8 @@ int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes) {
   }
   *bytes = is_wire(net) ? make_wire_stash_layout(make_wire_dims(net), rows).total
            : is_gen(net) ? make_gen_stash_layout(make_gen_dims(net), rows).total
-           : is_piped(net) ? make_pipe_stash_layout(net->hidden_features, net->hidden_layers, rows).total
-                           : make_stash_layout(net->hidden_features, net->hidden_layers, rows).total;
+           : is_piped(net) ? make_pipe_stash_layout(kSirenWidth, net->hidden_layers, rows).total
+                           : make_stash_layout(kSirenWidth, net->hidden_layers, rows).total;
   return B200INR_OK;
 }
 

@@ -8,6 +8,7 @@
 namespace b200inr {
 
 constexpr int kTileRows = 128;     // coordinate rows per tile == UMMA M
+constexpr int kSirenWidth = 256;   // width the raw-coordinate SIREN kernels are built for (narrower nets are padded)
 constexpr int kMaxSineLayers = 8;  // L + 1 <= 8
 constexpr int kOutPad = 32;        // final layer N (C <= 32)
 constexpr int kDzoPad = 64;        // dL/dout tile width (one 128-byte swizzle row)

@@ -128,6 +128,7 @@ struct PipeParams {
   long long rows;
   int fwd_tiles;          // 128-row tiles of the forward stash
   int L, C, d;
+  int Hr;                    // parameter width (<= kSirenWidth)
   const uint8_t* ph;      // phase stash: (L+1) x fwd_tiles x [32 chunks][128 rows][8] u16
   size_t layer_stride;
   const uint4* xa;        // coordinate stash: per row bf16 {hi x4, lo x4} (x = hi + lo), written by the forward
@@ -795,24 +796,31 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         }
       }
 
-      // ---- flush: bias gradient of the layer whose dTheta this CTA produced
+      // ---- flush.  The operands are kSirenWidth wide; a narrower network (Hr < 256) has zero rows / columns there and
+      // its gradient buffers are Hr wide, so the padded features are skipped (after the warp-collective TMEM loads).
+      const int Hr = p.Hr;
+      const int fi = h * 128 + f;  // feature owned by this thread
+      // bias gradient of the layer whose dTheta this CTA produced
       {
         const float sc = (ph_layer == 0) ? p.omega0 : p.omegah;
-        atomicAdd(p.grads + p.off[2 * ph_layer + 1] + h * 128 + f, sc * dbsum);
+        if (fi < Hr) atomicAdd(p.grads + p.off[2 * ph_layer + 1] + fi, sc * dbsum);
       }
       mbar_wait(&bars[kBFin], 0);
       tc_fence_after();
       if (!edge) {
         // dW_l[out][128 h + f] += omega_h * D[f][out]; this warp: outputs 64 cg .. 64 cg + 64 (lanes = consecutive inputs)
-        float* dst = p.grads + p.off[2 * layer] + h * 128 + f;
+        float* dst = p.grads + p.off[2 * layer] + fi;
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_w + t_lane + cg * 64 + c0, v);
           tmem_ld_wait();
+          if (fi < Hr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            atomicAdd(dst + (long long)(cg * 64 + c0 + j) * 256, p.omegah * __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (cg * 64 + c0 + j < Hr)
+                atomicAdd(dst + (long long)(cg * 64 + c0 + j) * Hr, p.omegah * __uint_as_float(v[j]));
+          }
         }
       } else {
         // dW_f[c][128 h + f] += D[f][c]
@@ -820,11 +828,11 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           uint32_t v[16];
           tmem_ld16(t_w + t_lane + cg * 16, v);
           tmem_ld_wait();
-          float* dst = p.grads + p.off[2 * (L + 1)] + h * 128 + f;
+          float* dst = p.grads + p.off[2 * (L + 1)] + fi;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c = cg * 16 + j;
-            if (c < C) atomicAdd(dst + (long long)c * 256, __uint_as_float(v[j]));
+            if (c < C && fi < Hr) atomicAdd(dst + (long long)c * Hr, __uint_as_float(v[j]));
           }
         }
         // dW_0[128 h + f][j] += omega_0 * (D[f][j] + D[f][4 + j])   (x = hi + lo)
@@ -834,10 +842,10 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           uint32_t v[16];
           tmem_ld16(t_w0 + t_lane, v);
           tmem_ld_wait();
-          float* dst = p.grads + p.off[0] + (long long)(h * 128 + f) * p.d;
+          float* dst = p.grads + p.off[0] + (long long)fi * p.d;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (j < p.d) atomicAdd(dst + j, p.omega0 * (__uint_as_float(v[j]) + __uint_as_float(v[4 + j])));
+            if (j < p.d && fi < Hr) atomicAdd(dst + j, p.omega0 * (__uint_as_float(v[j]) + __uint_as_float(v[4 + j])));
         }
       }
       tc_fence_before();
@@ -855,10 +863,11 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
 int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, const float* coords,
                       const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params, int num_sms,
                       cudaStream_t stream) {
-  constexpr int H = 256;
+  constexpr int H = kSirenWidth;  // operand width; the parameters are net->hidden_features wide (zero-padded operands)
   const int L = net->hidden_layers;
   const PipeStashLayout sl = make_pipe_stash_layout(H, L, rows);
   PipeParams p{};
+  p.Hr = net->hidden_features;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.pl = make_pack_layout(H, L);
   (void)coords;
@@ -877,7 +886,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.flags = reinterpret_cast<uint32_t*>(st + sl.flags);
   p.grads = grad_params;
   int64_t off[2 * (kMaxSineLayers + 2)];
-  param_offsets(p.d, H, L, p.C, off);
+  param_offsets(p.d, p.Hr, L, p.C, off);
   for (int i = 0; i < 2 * (L + 2); ++i) p.off[i] = off[i];
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;

@@ -15,6 +15,7 @@ struct PackParams {
   PackLayout pl;
   long long off[2 * (kMaxSineLayers + 1)];
   int d, H, L, C;
+  int Hr;  // real hidden width of the network (parameters); H is the padded operand width
   float omega0, omegah;
 };
 
@@ -24,14 +25,15 @@ __device__ __forceinline__ void put_bf16(uint8_t* base, uint32_t row, uint32_t k
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
-  const int H = p.H, L = p.L, C = p.C, d = p.d;
+  const int H = p.H, L = p.L, C = p.C, d = p.d, Hr = p.Hr;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
 
   // first layer: float4 rows, omega0 folded
   for (long long i = tid; i < H; i += nthreads) {
     float w[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < d; ++j) w[j] = p.omega0 * p.params[p.off[0] + i * d + j];
+    if (i < Hr)
+      for (int j = 0; j < d; ++j) w[j] = p.omega0 * p.params[p.off[0] + i * d + j];
     reinterpret_cast<float4*>(p.packed + p.pl.w0)[i] = make_float4(w[0], w[1], w[2], w[3]);
   }
   // first layer as a tensor-core operand: theta_0 = [x_hi x_hi x_lo x_lo 1 1] . [W_hi W_lo W_hi W_lo b_hi b_lo]
@@ -42,12 +44,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     float v = 0.f;
     if (k < 16) {
       const int g = k >> 2, j = k & 3;
-      if (j < d) {
+      if (j < d && o < Hr) {
         const float w = p.omega0 * p.params[p.off[0] + (long long)o * d + j];
         const float hi = __bfloat162float(__float2bfloat16_rn(w));
         v = (g & 1) ? (w - hi) : hi;
       }
-    } else if (k < 18) {
+    } else if (k < 18 && o < Hr) {
       const float b = p.omega0 * p.params[p.off[1] + o];
       const float hi = __bfloat162float(__float2bfloat16_rn(b));
       v = (k == 17) ? (b - hi) : hi;
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     float v = 0.f;
     if (i < (long long)(L + 1) * H) {
       const int l = int(i / H), h = int(i % H);
-      v = (l == 0 ? p.omega0 : p.omegah) * p.params[p.off[2 * l + 1] + h];
+      if (h < Hr) v = (l == 0 ? p.omega0 : p.omegah) * p.params[p.off[2 * l + 1] + h];
     } else {
       const int c = int(i - (long long)(L + 1) * H);
       if (c < C) v = p.params[p.off[2 * (L + 1) + 1] + c];
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     const int l = int(i / per_layer);
     const int o = int((i % per_layer) / H);  // out feature
     const int k = int(i % H);                // in feature
-    const float v = p.omegah * p.params[p.off[2 * (l + 1)] + (long long)o * H + k];
+    const float v = (o < Hr && k < Hr) ? p.omegah * p.params[p.off[2 * (l + 1)] + (long long)o * Hr + k] : 0.f;
     uint8_t* wh = p.packed + p.pl.wh + size_t(l) * per_layer * 2;
     uint8_t* wht = p.packed + p.pl.wht + size_t(l) * per_layer * 2;
     put_bf16(wh + size_t(k >> 6) * H * 128, o, k & 63, v);   // forward: N = out, K = in
@@ -82,13 +84,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   // final linear: forward operand [H/64][32][64], rows >= C zero
   for (long long i = tid; i < (long long)kOutPad * H; i += nthreads) {
     const int c = int(i / H), k = int(i % H);
-    const float v = (c < C) ? p.params[p.off[2 * (L + 1)] + (long long)c * H + k] : 0.f;
+    const float v = (c < C && k < Hr) ? p.params[p.off[2 * (L + 1)] + (long long)c * Hr + k] : 0.f;
     put_bf16(p.packed + p.pl.wf + size_t(k >> 6) * kOutPad * 128, c, k & 63, v);
   }
   // final linear: dgrad operand [H][64] (N = in, K = c padded to 64)
   for (long long i = tid; i < (long long)H * kDzoPad; i += nthreads) {
     const int n = int(i / kDzoPad), c = int(i % kDzoPad);
-    const float v = (c < C) ? p.params[p.off[2 * (L + 1)] + (long long)c * H + n] : 0.f;
+    const float v = (c < C && n < Hr) ? p.params[p.off[2 * (L + 1)] + (long long)c * Hr + n] : 0.f;
     put_bf16(p.packed + p.pl.wft, n, c, v);
   }
 }
@@ -171,14 +173,15 @@ int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaS
   p.params = params;
   p.packed = reinterpret_cast<uint8_t*>(packed);
   p.d = net->in_features;
-  p.H = net->hidden_features;
+  p.H = kSirenWidth;
+  p.Hr = net->hidden_features;
   p.L = net->hidden_layers;
   p.C = net->out_features;
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
   p.pl = make_pack_layout(p.H, p.L);
   int64_t off[2 * (kMaxSineLayers + 1)];
-  param_offsets(p.d, p.H, p.L, p.C, off);
+  param_offsets(p.d, p.Hr, p.L, p.C, off);
   for (int i = 0; i < 2 * (p.L + 2); ++i) p.off[i] = off[i];
   pack_kernel<<<296, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;

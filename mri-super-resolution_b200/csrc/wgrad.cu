@@ -52,6 +52,8 @@ struct WgItem {
   float* gb;               // bias gradient of the summed features, or nullptr
   int sum_b;               // 0: column sums over the A blocks (dTheta), 1: over the B block (dOut)
   int gb_count;            // number of valid bias entries (H features or C channels)
+  int m_valid, n_valid;    // valid M rows / N columns of the block when the network is narrower than the operands
+                           // (0 = all)
   float scale;
 };
 
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
         mbar_wait(d_full, 0);
         tc_fence_after();
         const uint32_t t_lane = uint32_t(q * 32) << 16;
+        const int m_valid = item.m_valid ? item.m_valid : 0x7fffffff;
+        const int n_valid = item.n_valid ? item.n_valid : 0x7fffffff;
 #pragma unroll 1
         for (int mh = 0; mh < 2; ++mh) {
           const int m = mh * 128 + q * 32 + lane;  // M index inside the item
@@ -203,12 +207,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
             uint32_t v[32];
             tmem_ld32(tmem_d + t_lane + mh * ncols + c0, v);
             tmem_ld_wait();
-            if (item.out == kWgOutBlock) {
+            if (m >= m_valid) {
+              // padded feature row: nothing to add (the loads above are warp-collective, so no early exit)
+            } else if (item.out == kWgOutBlock) {
               float* dst = item.gw + (long long)(item.row_off + m) * item.ldw + item.col_off + c0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                red_add_v4(dst + j, item.scale * __uint_as_float(v[j]), item.scale * __uint_as_float(v[j + 1]),
-                           item.scale * __uint_as_float(v[j + 2]), item.scale * __uint_as_float(v[j + 3]));
+                if (c0 + j < n_valid)
+                  red_add_v4(dst + j, item.scale * __uint_as_float(v[j]), item.scale * __uint_as_float(v[j + 1]),
+                             item.scale * __uint_as_float(v[j + 2]), item.scale * __uint_as_float(v[j + 3]));
             } else if (item.out == kWgOutFinal) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -265,12 +272,13 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
                        int64_t rows, float* grad_params, int num_sms, cudaStream_t stream) {
   (void)coords;
   (void)grid;  // the coordinate operand of the first layer comes from the stash (written by the training forward)
-  constexpr int H = 256;
+  constexpr int H = kSirenWidth;           // operand width
+  const int Hr = net->hidden_features;     // parameter width (<= H; the extra operand features are zero)
   const int L = net->hidden_layers, d = net->in_features, C = net->out_features;
   const StashLayout sl = make_stash_layout(H, L, rows);
   const uint8_t* st = reinterpret_cast<const uint8_t*>(stash);
   int64_t off[2 * (kMaxSineLayers + 1)];
-  param_offsets(d, H, L, C, off);
+  param_offsets(d, Hr, L, C, off);
 
   WgParams p{};
   p.num_tiles = int(sl.tiles);
@@ -289,9 +297,10 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     w.b_src = st + sl.y + size_t(l - 1) * sl.layer_stride;
     w.b_tile_bytes = tile_h;
     w.gw = grad_params + off[2 * l];
-    w.ldw = H;
+    w.ldw = Hr;
+    w.m_valid = w.n_valid = Hr;
     w.gb = grad_params + off[2 * l + 1];
-    w.gb_count = H;
+    w.gb_count = Hr;
     w.scale = net->hidden_omega_0;
     weight[ni++] = 128.0;
   }
@@ -305,7 +314,8 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     w.b_src = st + sl.dzo;
     w.b_tile_bytes = tile_s;
     w.gw = grad_params + off[2 * (L + 1)];
-    w.ldw = H;
+    w.ldw = Hr;
+    w.m_valid = Hr;
     w.gb = grad_params + off[2 * (L + 1) + 1];
     w.sum_b = 1;
     w.gb_count = C;
@@ -322,8 +332,9 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     w.b_src = st + sl.xa;
     w.b_tile_bytes = tile_s;
     w.gw = grad_params + off[0];
+    w.m_valid = Hr;
     w.gb = grad_params + off[1];
-    w.gb_count = H;
+    w.gb_count = Hr;
     w.scale = net->first_omega_0;
     weight[ni++] = 80.0;
   }

@@ -732,3 +732,44 @@ def test_pipelined_backward_shapes_vs_oracle(dev, d, Lh, C, rows):
         tol = BF16_RELERR if rows >= 64 else 3 * BF16_RELERR  # a handful of rows: no averaging of the bf16 rounding
         assert _relerr(flat[off[2 * i]:off[2 * i] + w_ref.size].reshape(w_ref.shape), w_ref) < tol, f"dW{i}"
         assert _relerr(flat[off[2 * i + 1]:off[2 * i + 1] + b_ref.size], b_ref) < tol, f"db{i}"
+
+
+# ------------------------------------------------------------------------------------------------ narrow networks
+@pytest.mark.parametrize("piped", [True, False])
+@pytest.mark.parametrize("H,Lh,C,rows", [(128, 3, 31, 1000), (64, 2, 1, 4097), (8, 1, 3, 129), (200, 4, 32, 777)])
+def test_narrow_siren_forward_backward_vs_oracle(dev, H, Lh, C, rows, piped):
+    """hidden_features < 256 (the reference's inr_toy / DWI_SR defaults use 64..256, INR/SRDWI.py:64): the network
+    runs on the 256-wide kernels with zero-padded operands, parameters and gradients keep the real [H] layout.
+    Forward and every gradient against the oracle, through both backward paths."""
+    torch.manual_seed(7 * H + Lh)
+    m = _set_backward_path(b200inr.Siren(3, H, Lh, C).to(dev), piped)
+    coords = (torch.rand(rows, 3, device=dev) * 2 - 1).contiguous()
+    gout = torch.randn(rows, C, device=dev) / (rows * C)
+    out, stash = m._forward_rows(coords, None, rows, train=True)
+    flat_t = m._backward_rows(stash, coords, None, rows, gout)
+    torch.cuda.synchronize()
+    flat = flat_t.cpu().numpy()
+    Ws, bs = _weights(m)
+    assert [tuple(w.shape) for w in Ws] == [(H, 3)] + [(H, H)] * Lh + [(C, H)]
+    ref = O.siren_forward(Ws, bs, coords.cpu().numpy())
+    assert _relerr(out.cpu().numpy(), ref) < BF16_RELERR
+    dW, db = O.siren_backward(Ws, bs, coords.cpu().numpy(), gout.cpu().numpy())
+    off = m._engine_state()["offsets"]
+    for i, (w_ref, b_ref) in enumerate(zip(dW, db)):
+        assert _relerr(flat[off[2 * i]:off[2 * i] + w_ref.size].reshape(w_ref.shape), w_ref) < BF16_RELERR, f"dW{i}"
+        assert _relerr(flat[off[2 * i + 1]:off[2 * i + 1] + b_ref.size], b_ref) < BF16_RELERR, f"db{i}"
+
+
+def test_narrow_siren_fit_vs_oracle(dev):
+    """A 3 -> 3 x 64 -> 5 SIREN fitted on a small volume: loss trajectory against the fp32 torch restatement."""
+    shape, C, steps, lr = (16, 16, 8), 5, 40, 1e-4
+    hr = b200inr.phantom.dwi_phantom(shape, n_dirs=C - 1, noise=0.0)
+    torch.manual_seed(5)
+    m = b200inr.Siren(3, 64, 3, C)
+    torch.manual_seed(5)
+    ref = O.torch_siren(3, 64, 3, C)
+    coords = torch.from_numpy(O.get_mgrid(shape))
+    ref_losses = O.torch_fit(ref, coords, torch.from_numpy(hr.reshape(-1, C)), steps, lr)
+    m = m.to(dev)
+    losses = m.fit(torch.from_numpy(hr).to(dev), shape, steps=steps, lr=lr).cpu().numpy()
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)

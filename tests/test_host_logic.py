@@ -52,8 +52,15 @@ def test_param_layout_and_sizes():
 def test_error_codes_without_gpu():
     lib = L.load()
     n = ctypes.c_int64(0)
-    bad = L.make_net(3, 128, 4, 31)  # only H = 256 is implemented
-    assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    for h in (0, 4, 100, 264, 512):  # raw-coordinate SIREN: 8 <= H <= 256, multiple of 8
+        bad = L.make_net(3, h, 4, 31)
+        assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    narrow = L.make_net(3, 128, 4, 31)  # narrower than the 256-wide kernels: parameters keep the real layout ...
+    assert lib.b200inr_param_count(ctypes.byref(narrow), ctypes.byref(n)) == 0
+    assert n.value == 3 * 128 + 128 + 4 * (128 * 128 + 128) + 31 * 128 + 32  # segments padded to 4 floats
+    wide = L.make_net(3, 256, 4, 31)    # ... the operand buffer and the stash are the 256-wide ones
+    assert L.packed_bytes(narrow) == L.packed_bytes(wide)
+    assert L.stash_bytes(narrow, 1000) == L.stash_bytes(wide, 1000)
     bad = L.make_net(5, 256, 4, 31)
     assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
     bad = L.make_net(3, 256, 4, 33)
