@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200inr.so")
+LIB_PATH = os.environ.get("B200INR_LIB") or os.path.join(_HERE, "lib", "libb200inr.so")  # (override: kernel tuning builds)
 
 MAX_TAPS = 8
 ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2

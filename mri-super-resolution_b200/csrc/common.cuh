@@ -84,10 +84,17 @@ __host__ __device__ inline StashLayout make_stash_layout(int H, int L, int64_t r
 // Stash of the pipelined SIREN training path (mlp_bwdp.cu): only the 16-bit phases go to HBM; the rest is the
 // L2-resident ring storage of the layer pipelines and their flag counters.
 constexpr int kPipeTileRows = 64;    // rows per pipeline tile (half a forward tile)
+// Phase stash of the pipelined path: per (layer, forward tile) two 64-row halves of [H/8 chunks][64 rows][8] u16, every
+// chunk padded by 32 bytes -- the bank spread mlp_bwdp.cu reads with; 32 keeps the forward's 512-byte warp stores on
+// whole sectors (a 16-byte pad cost the forward 15 %) -- so that the 128 features x 64 rows a backward CTA needs are
+// ONE contiguous bulk copy (sixteen 1 KB copies cost the loader thread ~1.6 k cycles per tile).
+constexpr int kPipePhChunk = kPipeTileRows * 16 + 32;                 // 1056 bytes
+constexpr int kPipePhHalf = (kSirenWidth / 8) * kPipePhChunk;        // 64 rows x 256 features: 33 792 bytes
+constexpr int kPipePhTile = 2 * kPipePhHalf;                         // one 128-row forward tile: 67 584 bytes
 constexpr int kPipeRing = 8;         // ring depth, in tiles, per layer boundary
 constexpr int kPipeMaxEdges = 96;    // pipelines x (L+1) <= #SM / 2
 struct PipeStashLayout {
-  size_t ph;            // (L+1) x T x [H/8][128][8] u16
+  size_t ph;            // (L+1) x T x kPipePhTile bytes (see above)
   size_t layer_stride;  // bytes per layer inside ph
   size_t xa;            // T x 128 rows x 16 bytes: coordinates as bf16 {hi x4, lo x4} (operand of dW_0)
   size_t ring;          // kPipeMaxEdges x kPipeRing x [64 rows x H bf16]
@@ -104,10 +111,11 @@ constexpr int kPipeProfSlots = 32;
 __host__ __device__ inline PipeStashLayout make_pipe_stash_layout(int H, int L, int64_t rows) {
   PipeStashLayout s;
   s.tiles = (rows + kTileRows - 1) / kTileRows;
-  s.layer_stride = size_t(s.tiles) * kTileRows * H * 2;
+  s.layer_stride = size_t(s.tiles) * kPipePhTile;
   size_t o = 0;
   s.ph = o;
   o += size_t(L + 1) * s.layer_stride;
+  o = (o + 1023) & ~size_t(1023);
   s.xa = o;
   o += size_t(s.tiles) * kTileRows * 16;
   s.ring = o;

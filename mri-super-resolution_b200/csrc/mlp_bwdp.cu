@@ -51,47 +51,107 @@
 
 namespace b200inr {
 
-constexpr int kPThreads = 736;
+#ifndef B200INR_PCVT
+#define B200INR_PCVT 2
+#endif
+constexpr int kPCvtWarps = B200INR_PCVT;                      // 2 (one pair) or 4 (two pairs alternating tiles)
+constexpr int kPThreads = 672 + 32 * kPCvtWarps;              // 736 / 800
 constexpr int kPEpiWarps = 16;
 constexpr int kPFirstEpiWarp = 4;
-constexpr int kPCvtWarps = 2;
+constexpr int kPCvtPair = 2;                                  // warps converting one tile (64 rows)
 constexpr int kPFirstCvtWarp = kPFirstEpiWarp + kPEpiWarps;  // 20
 constexpr int kPWgradWarp = kPFirstCvtWarp + kPCvtWarps;      // 22
-constexpr int kPDzSlots = 3;                    // incoming dTheta tiles
-constexpr int kPPhSlots = 4;                    // phase tiles (each epilogue group owns two)
-constexpr int kPStgSlots = 2;                   // outgoing dTheta halves
+#ifndef B200INR_PYT
+#define B200INR_PYT 1
+#endif
+#ifndef B200INR_PKO
+#define B200INR_PKO 0
+#endif
+// tuning aid, never set in production builds: knock out one resource at a time (results are garbage) to see what the
+// tile period is made of.  1 = no sin / cos, 2 = one chain MMA instead of 16, 4 = one weight-gradient MMA instead of 4,
+// 8 = no phase loads, 16 = ring loads of half a tile.
+constexpr int kPKo = B200INR_PKO;
+#ifndef B200INR_PTRACE
+#define B200INR_PTRACE 0
+#endif
+constexpr bool kPTraceOnly = B200INR_PTRACE != 0;  // tuning build: event trace compiled into the lean kernel
+#ifndef B200INR_PPF
+#define B200INR_PPF 0
+#endif
+constexpr int kPPhPrefetch = B200INR_PPF;  // forward tiles of phases pulled into L2 ahead of the bulk copies (0 = off)
+#ifndef B200INR_PMC
+#define B200INR_PMC 0
+#endif
+// kPMc: the two CTAs of a stage (feature halves h = 0 / 1) form a thread-block cluster; each bulk-copies HALF of the
+// incoming dTheta tile and multicasts it to both, so a ring tile crosses the L2 fabric once instead of twice (ring
+// loads are 2/3 of this kernel's L2 -> SM traffic, which runs near the fabric's limit).
+constexpr bool kPMc = B200INR_PMC != 0;
+#if B200INR_PMC
+#define B200INR_PCLUSTER __cluster_dims__(2, 1, 1)
+#else
+#define B200INR_PCLUSTER
+#endif
+#ifndef B200INR_PDZ
+#define B200INR_PDZ (B200INR_PYT ? 4 : 3)
+#endif
+#ifndef B200INR_PPH
+#define B200INR_PPH 3
+#endif
+// kPYTmem: the sin outputs (A operand of the weight-gradient MMA) are written to TENSOR memory instead of shared memory
+// (thread = feature = TMEM lane, its 32 rows = 16 packed columns): 32 KB less shared-memory traffic per tile and 32 KB
+// of shared memory freed.  The columns come from the second chain accumulator: ONE accumulator, handed back right
+// after the epilogue's tcgen05.ld.
+constexpr bool kPYTmem = B200INR_PYT != 0;
+constexpr int kPDzSlots = B200INR_PDZ;          // incoming dTheta tiles
+constexpr int kPPhSlots = B200INR_PPH;          // phase tiles (stage CTAs)
+#ifndef B200INR_PEPH
+#define B200INR_PEPH 3
+#endif
+constexpr int kPPhBars = B200INR_PPH > B200INR_PEPH ? B200INR_PPH : B200INR_PEPH;  // phase slots of the edge CTAs: B200INR_PEPH
+#ifndef B200INR_PSTG
+#define B200INR_PSTG 2
+#endif
+constexpr int kPStgSlots = B200INR_PSTG;        // outgoing dTheta halves (even: a slot always belongs to one epilogue group)
 constexpr int kPDobSlots = 4;                   // edge: bf16 dOut blocks
-constexpr int kPRawSlots = 2;                   // edge: raw fp32 dOut tiles (bulk-copied ahead of the conversion)
+#ifndef B200INR_PRAW
+#define B200INR_PRAW (B200INR_PYT ? 6 : 2)
+#endif
+constexpr int kPRawSlots = B200INR_PRAW;        // edge: raw fp32 dOut tiles, bulk-copied ahead of the conversion (the
+                                                // copies come from HBM: two slots leave the converters latency-bound)
 constexpr int kPZSlots = 2;                     // edge bottom: dTheta_0 slots
-constexpr int kPStoreDepth = 1;                 // bulk stores in flight per ring-store thread
+#ifndef B200INR_PSD
+#define B200INR_PSD 1
+#endif
+constexpr int kPStoreDepth = B200INR_PSD;                 // bulk stores in flight per ring-store thread
 constexpr int kPBlk = kPipeTileRows * 128;      // one [64][64] bf16 block: 8 KB
 constexpr int kPHalf = 2 * kPBlk;               // 128 features of a tile: 16 KB
 constexpr int kPTile = 4 * kPBlk;               // 256 features of a tile: 32 KB
-constexpr int kPPhChunk = kPipeTileRows * 16 + 16;  // phases of 8 features x 64 rows, padded (bank spread)
+constexpr int kPPhChunk = kPipePhChunk;              // phases of 8 features x 64 rows, padded (bank spread)
 constexpr int kPPhSlot = 16 * kPPhChunk;            // 16 chunks = 128 features
 constexpr int kPRawSlot = kPipeTileRows * kOutPad * 4;  // fp32 dOut tile, C <= 32
 
 // shared memory maps (bytes); operand blocks are 1024-byte aligned
-struct PSmem {  // stage CTA
-  static constexpr int kDz = 0;                              // kPDzSlots x tile               96 KB
-  static constexpr int kY = kDz + kPDzSlots * kPTile;        // 2 x sin outputs (128 features)  32 KB
-  static constexpr int kStg = kY + 2 * kPHalf;               // kPStgSlots x dTheta half       32 KB
-  static constexpr int kPh = kStg + kPStgSlots * kPHalf;     // kPPhSlots phase slots          65 KB
-  static constexpr int kBar = kPh + kPPhSlots * kPPhSlot;
-  static constexpr int kBytes = kBar + 512;
-  static_assert(kBytes + 1024 <= 232448, "shared memory budget");
-};
-struct PSmemE {  // edge CTA (same barrier area as the stage CTAs)
+struct PSmemE {  // edge CTA
   static constexpr int kWf = 0;                              // W_f^T half [128][64]           16 KB
   static constexpr int kDob = kWf + 128 * 128;               // kPDobSlots x dOut block        32 KB
   static constexpr int kZ = kDob + kPDobSlots * kPBlk;       // kPZSlots x dTheta_0 half       32 KB
   static constexpr int kXb = kZ + kPZSlots * kPHalf;         // kPZSlots x coordinate block    16 KB
-  static constexpr int kRaw = kXb + kPZSlots * kPBlk;        // kPRawSlots x fp32 dOut tile    16 KB
+  static constexpr int kRaw = kXb + kPZSlots * kPBlk;        // kPRawSlots x fp32 dOut tile    8 KB each
   static constexpr int kY = kRaw + kPRawSlots * kPRawSlot;   // 2 x sin outputs                32 KB
-  static constexpr int kStg = kY + 2 * kPHalf;               // kPStgSlots x dTheta half       32 KB
+  static constexpr int kStg = kY + (kPYTmem ? 0 : 2 * kPHalf);               // kPStgSlots x dTheta half       32 KB
   static constexpr int kPh = kStg + kPStgSlots * kPHalf;     // 3 phase slots                  48.75 KB
-  static constexpr int kPhSlots = 3;
-  static_assert(kPh + kPhSlots * kPPhSlot <= PSmem::kBar, "edge layout overlaps the barrier area");
+  static constexpr int kPhSlots = B200INR_PEPH;
+  static constexpr int kEnd = kPh + kPhSlots * kPPhSlot;
+};
+struct PSmem {  // stage CTA
+  static constexpr int kDz = 0;                              // kPDzSlots x tile               96 KB
+  static constexpr int kY = kDz + kPDzSlots * kPTile;        // 2 x sin outputs (128 features)  32 KB
+  static constexpr int kStg = kY + (kPYTmem ? 0 : 2 * kPHalf);               // kPStgSlots x dTheta half       32 KB
+  static constexpr int kPh = kStg + kPStgSlots * kPHalf;     // kPPhSlots phase slots          65 KB
+  static constexpr int kEnd = kPh + kPPhSlots * kPPhSlot;
+  static constexpr int kBar = kEnd > PSmemE::kEnd ? kEnd : PSmemE::kEnd;  // barrier area, shared by both CTA kinds
+  static constexpr int kBytes = kBar + 512;
+  static_assert(kBytes + 1024 <= 232448, "shared memory budget");
 };
 
 // barrier indices
@@ -101,15 +161,15 @@ enum PBar : int {
   kBW = 0,                                // static weights in place
   kBDzFull = kBW + 1,                     // [kPDzSlots]
   kBDzEmpty = kBDzFull + kPDzSlots,       // [kPDzSlots]
-  kBPhFull = kBDzEmpty + kPDzSlots,       // [kPPhSlots]
-  kBPhEmpty = kBPhFull + kPPhSlots,       // [kPPhSlots]
-  kBAccFull = kBPhEmpty + kPPhSlots,      // [2] by tile parity (ONE accumulator: the barriers alternate, not the storage)
+  kBPhFull = kBDzEmpty + kPDzSlots,       // [kPPhBars]
+  kBPhEmpty = kBPhFull + kPPhBars,        // [kPPhBars]
+  kBAccFull = kBPhEmpty + kPPhBars,      // [2] by tile parity (ONE accumulator: the barriers alternate, not the storage)
   kBAccEmpty = kBAccFull + 2,             // [2]
   kBYFull = kBAccEmpty + 2,               // [2]
   kBYEmpty = kBYFull + 2,                 // [2]
-  kBStgFull = kBYEmpty + 2,               // [2]
-  kBStgEmpty = kBStgFull + 2,             // [2]
-  kBFin = kBStgEmpty + 2,
+  kBStgFull = kBYEmpty + 2,               // [kPStgSlots]
+  kBStgEmpty = kBStgFull + kPStgSlots,    // [kPStgSlots]
+  kBFin = kBStgEmpty + kPStgSlots,
   kBDobFull = kBFin + 1,                  // [kPDobSlots] edge
   kBDobEmpty = kBDobFull + kPDobSlots,    // [kPDobSlots] edge
   kBZFull = kBDobEmpty + kPDobSlots,      // [kPZSlots] edge bottom
@@ -119,7 +179,7 @@ enum PBar : int {
   kBRawEmpty = kBRawFull + kPRawSlots,    // [kPRawSlots] edge
   kBCount = kBRawEmpty + kPRawSlots
 };
-static_assert(kPStgSlots == 2 && kPZSlots == 2, "per-parity buffers");
+static_assert(kPStgSlots % 2 == 0 && kPZSlots == 2, "per-parity buffers");
 
 struct PipeParams {
   const uint8_t* packed;
@@ -129,7 +189,7 @@ struct PipeParams {
   int fwd_tiles;          // 128-row tiles of the forward stash
   int L, C, d;
   int Hr;                    // parameter width (<= kSirenWidth)
-  const uint8_t* ph;      // phase stash: (L+1) x fwd_tiles x [32 chunks][128 rows][8] u16
+  const uint8_t* ph;      // phase stash: (L+1) x fwd_tiles x kPipePhTile bytes (common.cuh)
   size_t layer_stride;
   const uint4* xa;        // coordinate stash: per row bf16 {hi x4, lo x4} (x = hi + lo), written by the forward
   uint8_t* ring;          // [pipeline][edge 0..L][kPipeRing][32 KB]
@@ -255,7 +315,7 @@ __device__ __forceinline__ float rad_lo16(uint32_t w) {  // w: zero-extended 16-
 // kInstr = true compiles the stall counters / event trace in (tuning runs only): they double every wait statement and
 // push the hot loops out of the instruction cache (no_instruction stalls 1.8 per issue with them).
 template <bool kInstr>
-__global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipeParams p) {
+__global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipeParams p) {
   using S = PSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -294,29 +354,31 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
     mbar_init(&bars[kBW], edge ? 1 : 4);
     for (int i = 0; i < kPDzSlots; ++i) {
       mbar_init(&bars[kBDzFull + i], 1);
-      mbar_init(&bars[kBDzEmpty + i], 1);
+      mbar_init(&bars[kBDzEmpty + i], kPMc ? 2 : 1);  // multicast loads: released by both CTAs of the pair
     }
-    for (int i = 0; i < kPPhSlots; ++i) {
+    for (int i = 0; i < kPPhBars; ++i) {
       mbar_init(&bars[kBPhFull + i], 1);
       mbar_init(&bars[kBPhEmpty + i], kPEpiWarps);
     }
     for (int i = 0; i < kPDobSlots; ++i) {
-      mbar_init(&bars[kBDobFull + i], kPCvtWarps);
+      mbar_init(&bars[kBDobFull + i], kPCvtPair);
       mbar_init(&bars[kBDobEmpty + i], 1);
     }
     for (int i = 0; i < kPRawSlots; ++i) {
       mbar_init(&bars[kBRawFull + i], 1);
-      mbar_init(&bars[kBRawEmpty + i], kPCvtWarps);
+      mbar_init(&bars[kBRawEmpty + i], kPMc ? 2 * kPCvtPair : kPCvtPair);  // multicast: both CTAs' converters
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[kBAccFull + i], 1);
       mbar_init(&bars[kBAccEmpty + i], kPEpiWarps / 2);
       mbar_init(&bars[kBYFull + i], kPEpiWarps / 2);
       mbar_init(&bars[kBYEmpty + i], 1);
-      mbar_init(&bars[kBStgFull + i], kPEpiWarps / 2);
-      mbar_init(&bars[kBStgEmpty + i], 1);
       mbar_init(&bars[kBZFull + i], 1);
       mbar_init(&bars[kBZEmpty + i], 1);
+    }
+    for (int i = 0; i < kPStgSlots; ++i) {
+      mbar_init(&bars[kBStgFull + i], kPEpiWarps / 2);
+      mbar_init(&bars[kBStgEmpty + i], 1);
     }
     mbar_init(&bars[kBFin], 1);
     mbar_init(&bars[kBFinB], 1);
@@ -326,6 +388,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (kPMc) cluster_sync_all();  // the peer's barriers exist before any multicast copy / remote commit reaches them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // TMEM columns.  stage: dW^T block [0,256), W'^T half [256,384), chain accumulators 384 + 64 j.
@@ -333,6 +396,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   const uint32_t t_w = edge ? tmem + 128 : tmem;
   const uint32_t t_wt = tmem + 256;
   const uint32_t t_acc = edge ? tmem : tmem + 384;
+  const uint32_t t_y = t_acc + 64;  // kPYTmem: y^T of the two epilogue groups, 32 columns each (64 rows, 2 bf16 per column)
   const uint32_t t_w0 = tmem + 192;
 
   using E = PSmemE;
@@ -345,7 +409,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   const uint64_t hiMN = smem_desc_hi_sw128(kPBlk, 1024);  // MN-major: 64-wide MN blocks kPBlk apart
 
   const bool prof_on = kInstr && p.prof != nullptr;
-  const bool trace_on = kInstr && p.trace != nullptr && pipe == 0;
+  const bool trace_on = (kInstr || kPTraceOnly) && p.trace != nullptr && pipe == 0;
   const long long t_begin = (prof_on || trace_on) ? clock64() : 0;
 
   if (n > 0) {
@@ -359,12 +423,23 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             const int slot = i % kPDzSlots, round = i / kPDzSlots;
             if (round > 0) PW(0, mbar_wait(&bars[kBDzEmpty + slot], (round - 1) & 1));
             TR(0, i);
-            PW(1, poll2_ge(fl_in + 0 * 32, fl_in + 1 * 32, uint32_t(i + 1), k0, k1));
-            TR(1, i);
-            // (no proxy fence: the tile was written AND published through the async proxy, and is read through it)
-            mbar_arrive_expect_tx(&bars[kBDzFull + slot], kPTile);
-            bulk_g2s(smem + S::kDz + slot * kPTile, ring_in + size_t(i % kPipeRing) * kPTile, kPTile,
-                     &bars[kBDzFull + slot]);
+            if (kPMc) {
+              // this CTA fetches the half its namesake produced (blocks 2h, 2h + 1) for both CTAs of the pair; the slot
+              // is free in BOTH (kBDzEmpty counts both weight-gradient streams) and the barrier expects the whole tile
+              PW(1, poll2_ge(fl_in + h * 32, fl_in + h * 32, uint32_t(i + 1), k0, k1));
+              TR(1, i);
+              mbar_arrive_expect_tx(&bars[kBDzFull + slot], kPTile);
+              bulk_g2s_mc(smem + S::kDz + slot * kPTile + h * kPHalf,
+                          ring_in + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, kPHalf, &bars[kBDzFull + slot],
+                          uint16_t(3));
+            } else {
+              PW(1, poll2_ge(fl_in + 0 * 32, fl_in + 1 * 32, uint32_t(i + 1), k0, k1));
+              TR(1, i);
+              // (no proxy fence: the tile was written AND published through the async proxy, and is read through it)
+              mbar_arrive_expect_tx(&bars[kBDzFull + slot], kPTile);
+              bulk_g2s(smem + S::kDz + slot * kPTile, ring_in + size_t(i % kPipeRing) * kPTile, kPTile,
+                       &bars[kBDzFull + slot]);
+            }
           }
           PW_FLUSH(1, 2);
         } else {
@@ -378,15 +453,41 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       if (lane == 0) {
         unsigned long long pw[1] = {0};
         for (int i = 0; i < n; ++i) {
+          if (edge) {
+            // the raw fp32 dOut tile of tile i for the converters (kPRawSlots ahead of them; issued from here because
+            // the converter loop is the longest serial loop of the edge CTA)
+            const int rs = i % kPRawSlots;
+            if (i >= kPRawSlots) mbar_wait(&bars[kBRawEmpty + rs], ((i / kPRawSlots) - 1) & 1);
+            const long long row0 = (long long)(pipe + (i >> 1) * p.pipelines) * 128 + (i & 1) * kPipeTileRows;
+            if (row0 + kPipeTileRows <= p.rows) {
+              const uint32_t bytes = uint32_t(kPipeTileRows) * p.C * 4;
+              mbar_arrive_expect_tx(&bars[kBRawFull + rs], bytes);
+              if (kPMc)  // both edge CTAs convert the same dOut tile: each fetches 32 rows of it for the pair
+                bulk_g2s_mc(smem + E::kRaw + rs * kPRawSlot + h * (bytes / 2), p.grad_out + row0 * p.C + h * (bytes / 8),
+                            bytes / 2, &bars[kBRawFull + rs], uint16_t(3));
+              else
+                bulk_g2s(smem + E::kRaw + rs * kPRawSlot, p.grad_out + row0 * p.C, bytes, &bars[kBRawFull + rs]);
+            } else {
+              mbar_arrive(&bars[kBRawFull + rs]);  // ragged last tile: the converters read it from global memory
+            }
+          }
           const int slot = i % nph, round = i / nph;
           if (round > 0) PW(0, mbar_wait(&bars[kBPhEmpty + slot], (round - 1) & 1));
+          TR(18, i);
           const int T = pipe + (i >> 1) * p.pipelines;
-          const uint8_t* src = p.ph + size_t(ph_layer) * p.layer_stride + size_t(T) * (128 * 256 * 2) +
-                               size_t(i & 1) * (kPipeTileRows * 16) + size_t(h) * 16 * (128 * 16);
-          mbar_arrive_expect_tx(&bars[kBPhFull + slot], 16 * kPipeTileRows * 16);
-          for (int c = 0; c < 16; ++c)
-            bulk_g2s(smem + oPh + slot * kPPhSlot + c * kPPhChunk, src + size_t(c) * (128 * 16), kPipeTileRows * 16,
-                     &bars[kBPhFull + slot]);
+          if (kPPhPrefetch > 0 && (i & 1) == 0 && (i >> 1) + kPPhPrefetch < my_fwd)
+            bulk_prefetch_l2(p.ph + size_t(ph_layer) * p.layer_stride + size_t(T + kPPhPrefetch * p.pipelines) * kPipePhTile,
+                             kPipePhTile);
+          const uint8_t* src = p.ph + size_t(ph_layer) * p.layer_stride + size_t(T) * kPipePhTile +
+                               size_t(i & 1) * kPipePhHalf + size_t(h) * kPPhSlot;
+          if (kPKo & 8) {
+            mbar_arrive(&bars[kBPhFull + slot]);
+            continue;
+          }
+          // one copy: the forward stores the 16 chunks of a feature half contiguously, padding included
+          mbar_arrive_expect_tx(&bars[kBPhFull + slot], kPPhSlot);
+          bulk_g2s(smem + oPh + slot * kPPhSlot, src, kPPhSlot, &bars[kBPhFull + slot]);
+          TR(17, i);
         }
         PW_FLUSH(3, 1);
       }
@@ -405,16 +506,18 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             PW(0, mbar_wait(&bars[kBDzFull + ds], (i / kPDzSlots) & 1));
             if (lane == 0) TR(2, i);
             if (lane == 0) st_relaxed_gpu(fl_in + (2 + h) * 32, uint32_t(i + 1));  // credit: ring slot read out
-            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            if (kPYTmem) {  // one accumulator: read out by the group of tile i - 1
+              if (i >= 1) PW(1, mbar_wait(&bars[kBAccEmpty + ((i - 1) & 1)], ((i - 1) >> 1) & 1));
+            } else {
+              if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            }
             if (lane == 0) TR(3, i);
             tc_fence_after();
             const uint32_t dz = sbase + S::kDz + ds * kPTile;
 #pragma unroll 1  // (compact loops: this warp shares an instruction cache with four epilogue warps)
-            for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_ts_w(t_acc + (i & 1) * 64, t_wt + (kb * 4 + ks) * 8, smem_desc(dz + kb * kPBlk + ks * 2048, hiMN), idesc_d,
-                               (kb | ks) != 0);
+            for (int kb = 0; kb < ((kPKo & 2) ? 1 : 4); ++kb)  // four K steps (2048 bytes apart) per batched issue
+              umma_bf16_ts_w4<2048 / 16>(t_acc + (kPYTmem ? 0 : (i & 1) * 64), t_wt + kb * 32,
+                                         smem_desc(dz + kb * kPBlk, hiMN), idesc_d, kb != 0);
             umma_commit_w(&bars[kBAccFull + (i & 1)]);
             if (lane == 0) TR(4, i);
           }
@@ -424,13 +527,17 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             const int bs = i % kPDobSlots;
             PW(0, mbar_wait(&bars[kBDobFull + bs], (i / kPDobSlots) & 1));
             if (lane == 0) TR(2, i);
-            if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            if (kPYTmem) {
+              if (i >= 1) PW(1, mbar_wait(&bars[kBAccEmpty + ((i - 1) & 1)], ((i - 1) >> 1) & 1));
+            } else {
+              if (i >= 2) PW(1, mbar_wait(&bars[kBAccEmpty + (i & 1)], ((i >> 1) - 1) & 1));
+            }
             if (lane == 0) TR(3, i);
             tc_fence_after();
             const uint32_t dob = sbase + E::kDob + bs * kPBlk;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_ss_w(t_acc + (i & 1) * 64, smem_desc(sbase + E::kWf + k4 * 32, hiK), smem_desc(dob + k4 * 32, hiK), idesc_d,
+              umma_bf16_ss_w(t_acc + (kPYTmem ? 0 : (i & 1) * 64), smem_desc(sbase + E::kWf + k4 * 32, hiK), smem_desc(dob + k4 * 32, hiK), idesc_d,
                              k4 != 0);
             umma_commit_w(&bars[kBAccFull + (i & 1)]);
             if (lane == 0) TR(4, i);
@@ -454,11 +561,17 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             tc_fence_after();
             // dW^T[in-half][out] += sum over the 64 rows: 4 K steps of 16 rows, N = all 256 outputs
 #pragma unroll
-            for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
-              umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dz + ks * 32, hiK), idesc_w,
-                             (i | ks) != 0);
+            for (int ks = 0; ks < ((kPKo & 4) ? 1 : kPipeTileRows / 16); ++ks)
+              if (kPYTmem)
+                umma_bf16_ts_w(t_w, t_y + yb * 32 + ks * 8, smem_desc(dz + ks * 32, hiK), idesc_w, (i | ks) != 0);
+              else
+                umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dz + ks * 32, hiK), idesc_w,
+                               (i | ks) != 0);
             umma_commit_w(&bars[kBYEmpty + yb]);
-            umma_commit_w(&bars[kBDzEmpty + ds]);
+            if (kPMc)
+              umma_commit_mc_w(&bars[kBDzEmpty + ds], uint16_t(3));
+            else
+              umma_commit_w(&bars[kBDzEmpty + ds]);
             if (lane == 0) TR(6, i);
           }
         } else {
@@ -472,8 +585,11 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < kPipeTileRows / 16; ++ks)
-              umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dob + ks * 2048, hiMN), idesc_w,
-                             (i | ks) != 0);
+              if (kPYTmem)
+                umma_bf16_ts_w(t_w, t_y + yb * 32 + ks * 8, smem_desc(dob + ks * 2048, hiMN), idesc_w, (i | ks) != 0);
+              else
+                umma_bf16_ss_w(t_w, smem_desc(oY + yb * kPHalf + ks * 32, hiK), smem_desc(dob + ks * 2048, hiMN), idesc_w,
+                               (i | ks) != 0);
             umma_commit_w(&bars[kBYEmpty + yb]);
             umma_commit_w(&bars[kBDobEmpty + bs]);
             if (lane == 0) TR(6, i);
@@ -494,21 +610,23 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         const uint32_t* fb = fl_out + ((out_edge != 0 || h == 1) ? 3 : 2) * 32;
         for (int i = 0; i < n; ++i) {
           const int ss = i % kPStgSlots;
-          PW(0, mbar_wait(&bars[kBStgFull + ss], (i / kPStgSlots) & 1));
-          TR(7, i);
+          // the credit poll (an L2 round trip almost every tile: the consumers run just in time) goes first, under the
+          // wait for the epilogue; the previous tile is published before this tile's read-out wait
           if (i >= kPipeRing) PW(1, poll2_ge(fa, fb, uint32_t(i - kPipeRing + 1), c0, c1));  // slot read out
           TR(8, i);
+          PW(0, mbar_wait(&bars[kBStgFull + ss], (i / kPStgSlots) & 1));
+          TR(7, i);
           bulk_s2g(ring_out + size_t(i % kPipeRing) * kPTile + size_t(h) * kPHalf, smem + oStg + ss * kPHalf,
                    kPHalf);
           bulk_commit();
-          PW(2, bulk_wait_read0());
-          mbar_arrive(&bars[kBStgEmpty + ss]);
-          TR(9, i);
           if (i >= kPStoreDepth) {  // the store of tile i - kPStoreDepth is complete: publish it (joins the next group)
             PW(3, bulk_wait_group<kPStoreDepth>());
             bulk_red_add_u32x4(fl_out + h * 32, one_s);
             TR(10, i - kPStoreDepth);
           }
+          PW(2, bulk_wait_read0());
+          mbar_arrive(&bars[kBStgEmpty + ss]);
+          TR(9, i);
         }
         PW(3, bulk_wait0());
         for (int i = (n > kPStoreDepth ? n - kPStoreDepth : 0); i < n; ++i) bulk_red_add_u32x4(fl_out + h * 32, one_s);
@@ -580,36 +698,27 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
       // Thread t owns row t of every tile: [64 rows][C] fp32 (bulk-copied to shared memory; a ragged last tile comes
       // straight from global memory) -> bf16 [64 rows][64] block, zero beyond C / rows; running column sums = db_f.
       if (edge) {
-        const int t = threadIdx.x - kPFirstCvtWarp * 32;  // 0..63
+        const int t = (threadIdx.x - kPFirstCvtWarp * 32) & 63;  // row of the tile
+        // with four converter warps two pairs alternate tiles (one pair was the slowest loop of the edge CTA: ~2 k
+        // cycles per tile); slot counts are even, so a slot and its barriers always belong to the same pair
+        constexpr int kPairs = kPCvtWarps / kPCvtPair;
+        static_assert(kPRawSlots % kPairs == 0 && kPDobSlots % kPairs == 0, "slot ownership");
+        const int cp = (threadIdx.x - kPFirstCvtWarp * 32) >> 6;
         const int C = p.C;
         float dbf[kOutPad];
 #pragma unroll
         for (int c = 0; c < kOutPad; ++c) dbf[c] = 0.f;
-        for (int sidx = 0; sidx < kPDobSlots; ++sidx)  // columns 32..63 stay zero for the whole kernel
+        for (int sidx = cp; sidx < kPDobSlots; sidx += kPairs)  // columns 32..63 stay zero for the whole kernel
 #pragma unroll
           for (int ch = 4; ch < 8; ++ch)
             sts128(sbase + E::kDob + sidx * kPBlk + sw128_chunk_off(t, ch), make_uint4(0u, 0u, 0u, 0u));
-        // the first converter thread also fetches the fp32 tiles, two tiles ahead (its own stream: a full bf16 ring
-        // must never hold the phase loads back)
-        auto load_raw = [&](int j) {
-          const int rs = j % kPRawSlots;
-          if (j >= kPRawSlots) mbar_wait(&bars[kBRawEmpty + rs], ((j / kPRawSlots) - 1) & 1);
-          const int Tj = pipe + (j >> 1) * p.pipelines;
-          const long long row0 = (long long)Tj * 128 + (j & 1) * kPipeTileRows;
-          if (row0 + kPipeTileRows <= p.rows) {
-            const uint32_t bytes = uint32_t(kPipeTileRows) * p.C * 4;
-            mbar_arrive_expect_tx(&bars[kBRawFull + rs], bytes);
-            bulk_g2s(smem + E::kRaw + rs * kPRawSlot, p.grad_out + row0 * p.C, bytes, &bars[kBRawFull + rs]);
-          } else {
-            mbar_arrive(&bars[kBRawFull + rs]);  // ragged last tile: read from global memory below
-          }
-        };
-        if (t == 0)
-          for (int j = 0; j < kPRawSlots && j < n; ++j) load_raw(j);
-        for (int j = 0; j < n; ++j) {
+        for (int j = cp; j < n; j += kPairs) {
           const int bs = j % kPDobSlots, rs = j % kPRawSlots;
+          if (t == 0) TR(19, j);
           mbar_wait(&bars[kBRawFull + rs], (j / kPRawSlots) & 1);
+          if (t == 0) TR(20, j);
           if (j >= kPDobSlots) mbar_wait(&bars[kBDobEmpty + bs], ((j / kPDobSlots) - 1) & 1);
+          if (t == 0) TR(21, j);
           const int T = pipe + (j >> 1) * p.pipelines;
           const long long row0 = (long long)T * 128 + (j & 1) * kPipeTileRows;
           float gv[kOutPad];
@@ -635,8 +744,9 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           if (lane == 0) {
             mbar_arrive(&bars[kBDobFull + bs]);
             mbar_arrive(&bars[kBRawEmpty + rs]);
+            if (kPMc) mbar_arrive_remote_relaxed(&bars[kBRawEmpty + rs], uint32_t(h ^ 1));
           }
-          if (t == 0 && j + kPRawSlots < n) load_raw(j + kPRawSlots);  // refill the slot both warps just released
+          if (t == 0) TR(22, j);
           __syncwarp();
         }
         if (h == 0) {  // db_f: column sums of dOut (one edge CTA per pipeline)
@@ -698,26 +808,6 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
         }
       }
 
-      // sin / cos of 16 phases, dTheta = D .* cos; packs y (sin) and dTheta as bf16 pairs along the rows
-      auto batch_math = [&](const uint32_t (&v)[16], const uint32_t (&ph)[16], uint32_t (&ys)[8], uint32_t (&ds)[8]) {
-        if (kInstr && (p.dbg & 1)) {  // tuning aid: no sin / cos work (results are garbage), shows the pure pipeline rate
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ds[j] = v[2 * j] ^ ph[2 * j + 1];
-            ys[j] = v[2 * j + 1] ^ ph[2 * j];
-          }
-          return;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
-          const float d0 = __uint_as_float(v[2 * j]) * __cosf(r0);
-          const float d1 = __uint_as_float(v[2 * j + 1]) * __cosf(r1);
-          dbsum += d0 + d1;
-          ds[j] = pack_bf16x2(d0, d1);
-          ys[j] = pack_bf16x2(__sinf(r0), __sinf(r1));
-        }
-      };
       if (grp == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);  // start the two groups half a cycle apart
       for (int i = 0; i < n; ++i) {
         const int ps = i % nph;
@@ -728,19 +818,20 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
           if (lane == 0) mbar_arrive(&bars[kBPhEmpty + ps]);
           continue;
         }
-        const int yb = grp, sb = grp, u = i >> 1;  // u: use count of this group's buffers
+        const int yb = grp, u = i >> 1;  // u: use count of this group's buffers
+        const int sb = i % kPStgSlots, su = i / kPStgSlots;  // staging slot and its use count
         const bool tr_me = (ew & 7) == 0 && lane == 0;
         if (tr_me) TR(11, i);
         PW(3, mbar_wait(&bars[kBAccFull + grp], u & 1));
         if (u >= 1) {  // this group's previous tile: its y consumed by the MMA, its dTheta half read out by the store
           PW(2, mbar_wait(&bars[kBYEmpty + yb], (u - 1) & 1));
-          PW(4, mbar_wait(&bars[kBStgEmpty + sb], (u - 1) & 1));
+          if (su >= 1) PW(4, mbar_wait(&bars[kBStgEmpty + sb], (su - 1) & 1));
         }
         if (tr_me) TR(12, i);
         tc_fence_after();
         const long long tc0 = prof_on ? clock64() : 0;
         const uint32_t ph_f = sbase + oPh + ps * kPPhSlot + (f >> 3) * kPPhChunk + (f & 7) * 2 + rh * 32 * 16;
-        const uint32_t acc = t_acc + t_lane + grp * 64 + rh * 32;
+        const uint32_t acc = t_acc + t_lane + (kPYTmem ? 0 : grp * 64) + rh * 32;
         const uint32_t yblk = oY + yb * kPHalf + (f >> 6) * kPBlk;
         const uint32_t dblk = sbase + oStg + sb * kPHalf + (f >> 6) * kPBlk;
         // the whole 32-row accumulator slice goes to registers first and is handed back at once: the chain MMA of
@@ -764,6 +855,13 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
+            if (kPKo & 1) {
+              const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * r0, d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * r1;
+              dbsum += d0 + d1;
+              ds[j] = pack_bf16x2(d0, d1);
+              ys[j] = pack_bf16x2(r0, r1);
+              continue;
+            }
             const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * __cosf(r0);
             const float d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * __cosf(r1);
             dbsum += d0 + d1;
@@ -771,14 +869,22 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
             ys[j] = pack_bf16x2(__sinf(r0), __sinf(r1));
           }
           const uint32_t ch = 4 * rh + 2 * b2;
-          sts128(yblk + sw128_chunk_off(f & 63, ch), make_uint4(ys[0], ys[1], ys[2], ys[3]));
-          sts128(yblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
+          if (kPYTmem) {
+            tmem_st8(t_y + t_lane + yb * 32 + rh * 16 + b2 * 8, ys);
+          } else {
+            sts128(yblk + sw128_chunk_off(f & 63, ch), make_uint4(ys[0], ys[1], ys[2], ys[3]));
+            sts128(yblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ys[4], ys[5], ys[6], ys[7]));
+          }
           sts128(dblk + sw128_chunk_off(f & 63, ch), make_uint4(ds[0], ds[1], ds[2], ds[3]));
           sts128(dblk + sw128_chunk_off(f & 63, ch + 1), make_uint4(ds[4], ds[5], ds[6], ds[7]));
         }
         if (tr_me) TR(14, i);
         if (prof_on) pw[6] += (unsigned long long)(clock64() - tc0);
         const long long ts0 = prof_on ? clock64() : 0;
+        if (kPYTmem) {
+          tmem_st_wait();
+          tc_fence_before();
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -853,6 +959,7 @@ __global__ void __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipePara
   }
 
   __syncthreads();
+  if (kPMc) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc<512>(tmem);
   if (prof_on && threadIdx.x == 0) {
     p.prof[size_t(blockIdx.x) * kPipeProfSlots + 0] = (unsigned long long)(clock64() - t_begin);
@@ -891,7 +998,33 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
   const int S2 = 2 * (L + 1);
+  const int smem = PSmem::kBytes + 1024;
   int P = num_sms / S2;
+  if (kPMc) {
+    // every CTA of the grid must be resident at once, and with clusters that is the number of CTA PAIRS the GPCs can
+    // hold (cached: a property of the device and the kernel)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      if (cudaFuncSetAttribute(siren_bwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return B200INR_ERR_CUDA;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(unsigned(num_sms & ~1));
+      cfg.blockDim = dim3(kPThreads);
+      cfg.dynamicSmemBytes = size_t(smem);
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2;
+      at.val.clusterDim.y = 1;
+      at.val.clusterDim.z = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, siren_bwdp_kernel<false>, &cfg) != cudaSuccess) return B200INR_ERR_CUDA;
+      max_clusters = nc;
+      if (getenv("B200INR_BWDP_VERBOSE") != nullptr) fprintf(stderr, "b200inr: bwdp max active 2-CTA clusters = %d\n", nc);
+    }
+    if (P > max_clusters / (L + 1)) P = max_clusters / (L + 1);
+  }
   if (P > p.fwd_tiles) P = p.fwd_tiles;
   if (P < 1 || P * (L + 1) > kPipeMaxEdges) return B200INR_ERR_BAD_SHAPE;
   p.pipelines = P;
@@ -905,8 +1038,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   if (env_prof != nullptr && env_prof[0] == '1' && P * S2 <= kPipeProfCtas)
     p.prof = reinterpret_cast<unsigned long long*>(st + sl.prof);
   if (cudaMemsetAsync(p.flags, 0, sl.flags_bytes, stream) != cudaSuccess) return B200INR_ERR_CUDA;
-  const int smem = PSmem::kBytes + 1024;
-  if (p.prof != nullptr || p.trace != nullptr || p.dbg != 0) {
+  if (p.prof != nullptr || (p.trace != nullptr && !kPTraceOnly) || p.dbg != 0) {
     if (cudaFuncSetAttribute(siren_bwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200INR_ERR_CUDA;
     siren_bwdp_kernel<true><<<P * S2, kPThreads, smem, stream>>>(p);

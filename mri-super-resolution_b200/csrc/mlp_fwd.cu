@@ -67,7 +67,7 @@ constexpr float kPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
 constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 
 // sin + stores for the 16 consecutive columns [kb*64 + s*16, +16) of row r.
-template <bool kStash>
+template <bool kStash, int kChunkStride = kTileRows * 16>
 __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_block_addr, int r, int s,
                                             uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */) {
 #pragma unroll
@@ -85,7 +85,7 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
     }
     sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
     if (kStash)
-      __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * (kTileRows * 16)), make_uint4(ph[0], ph[1], ph[2], ph[3]));
+      __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * kChunkStride), make_uint4(ph[0], ph[1], ph[2], ph[3]));
   }
 }
 
@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
           const float* bl = bias_g + l * H;
           const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
-          uint8_t* ph_l = kStash ? p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes +
-                                       size_t(r) * 16
-                                 : nullptr;
+          // phase stash: staged layout [H/8 chunks][128 rows][8]; pipelined layout two 64-row halves of padded chunks
+          // (common.cuh: kPipePhChunk)
+          uint8_t* ph_l = !kStash ? nullptr
+                          : kMode == 2
+                              ? p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * kPipePhTile +
+                                    size_t(r >> 6) * kPipePhHalf + size_t(r & 63) * 16
+                              : p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes + size_t(r) * 16;
           const int tph = (pr * (L + 3) + l + 1) * 2 + j;  // the MMA phase that consumes this epilogue's output
           const bool trw = tr && et == 0 && tph < 512;
           if (trw) p.trace[tph * 8 + 4] = uint32_t(clock64() - t_begin);
@@ -337,8 +341,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
               th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bq[j4].z;
               th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bq[j4].w;
             }
-            emit_sine16<kStash>(th, a_addr + kb * S::kABlock, r, s,
-                                kStash ? ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16) : nullptr);
+            constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
+            emit_sine16<kStash, kPhStride>(th, a_addr + kb * S::kABlock, r, s,
+                                           kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr);
           }
           if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
           fence_proxy_async_smem();

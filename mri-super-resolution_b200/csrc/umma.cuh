@@ -149,6 +149,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// The same copy delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each destination
+// CTA's mbarrier (same offset) receives the complete_tx for the bytes written there.
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                            uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst),
                "r"(smem_u32(smem_src)), "r"(bytes)
@@ -269,11 +279,41 @@ __device__ __forceinline__ void umma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four TS-mode MMAs of one K block from ONE elected lane: A at a_tmem + 8 k columns, B descriptor + k * kDescStep (in
+// 16-byte units), k = 0..3.  One election and one predicate for the batch instead of one per instruction (the per-MMA
+// elect / vote / register-to-uniform moves made a 16-MMA chain step issue-bound: ~62 cycles per 32-cycle MMA).
+template <int kDescStep>
+__device__ __forceinline__ void umma_bf16_ts_w4(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 d1, d2, d3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "add.u64 d1, %2, %5;\n\tadd.u64 d2, %2, %6;\n\tadd.u64 d3, %2, %7;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], d1, %3, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], d2, %3, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], d3, %3, 1;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "n"(kDescStep), "n"(2 * kDescStep), "n"(3 * kDescStep)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+// commit of a 1-CTA MMA stream that arrives on the mbarrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
       : "memory");
 }
 
@@ -293,6 +333,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// The same without the release: for hand-backs of a buffer whose contents this thread has finished READING (its loads
+// have returned); a cluster-scope release costs ~1-2 k cycles under load.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

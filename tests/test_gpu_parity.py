@@ -651,11 +651,13 @@ def test_pipelined_phase_stash_gives_layer_activations(dev, golden_dir):
     torch.cuda.synchronize()
     tiles = (rows + 127) // 128
     H, nl = 256, m.hidden_layers + 1
-    ph = stash[:nl * tiles * 128 * H * 2].view(torch.int16).reshape(nl, tiles, H // 8, 128, 8).cpu().numpy()
-    ph = ph.astype(np.int64) & 0xFFFF
+    # layout (csrc/common.cuh, kPipePhTile): [layer][tile][64-row half][chunk of 8 features][64 rows x 8 u16 + 32 B pad]
+    chunk = 64 * 16 + 32
+    raw = stash[:nl * tiles * 2 * (H // 8) * chunk].reshape(nl, tiles, 2, H // 8, chunk)[..., :64 * 16].contiguous()
+    ph = raw.view(torch.int16).reshape(nl, tiles, 2, H // 8, 64, 8).cpu().numpy().astype(np.int64) & 0xFFFF
 
-    def layer_act(layer):  # [tiles][chunk of 8 features][row][8] -> [rows, H]
-        a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 2, 1, 3).reshape(tiles * 128, H)
+    def layer_act(layer):  # [tiles][half][chunk][row][8] -> [rows, H]
+        a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 1, 3, 2, 4).reshape(tiles * 128, H)
         return a[:rows].astype(np.float32)
 
     assert _relerr(layer_act(0), g["act_first"]) < BF16_RELERR
@@ -773,3 +775,29 @@ def test_narrow_siren_fit_vs_oracle(dev):
     m = m.to(dev)
     losses = m.fit(torch.from_numpy(hr).to(dev), shape, steps=steps, lr=lr).cpu().numpy()
     np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+
+
+@pytest.mark.parametrize("piped", [True, False])
+@pytest.mark.parametrize("name", ["model", "slice_model"])
+def test_reference_trained_checkpoints(dev, golden_dir, name, piped):
+    """The trained checkpoints the reference ships (model.pt / slice_model.pt, a 2 -> 4 x 64 -> 1 SIREN with keys
+    net.*), loaded with load_state_dict the way INR/inr_toy.py:115 / dwi_inr.ipynb do: output on get_mgrid((128, 128))
+    and the gradients of the MSE against the unmodified reference's (tools/make_golden.py: trained_case)."""
+    g = np.load(os.path.join(golden_dir, "trained_siren64.npz"))
+    sd = {k[len(name) + 3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/w/")}
+    m = b200inr.Siren(2, 64, 3, 1)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("final_linear") for k in missing)  # final_linear IS net.4
+    m = _set_backward_path(m.to(dev), piped)
+    coords = b200inr.get_mgrid((128, 128)).to(dev)
+    out = m(coords)
+    ref = g[f"{name}/out"]
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= BF16_RELERR * np.abs(ref).max()
+    q = m.query((128, 128), clamp_min=None).cpu().numpy()
+    assert np.abs(q - ref).max() <= BF16_RELERR * np.abs(ref).max()
+    loss = ((out - torch.from_numpy(g[f"{name}/target"]).to(dev)) ** 2).mean()
+    loss.backward()
+    assert math.isclose(loss.item(), float(g[f"{name}/loss"]), rel_tol=1e-2)
+    for k, p in m.net.named_parameters():
+        gr = g[f"{name}/g/net.{k}"]
+        assert _relerr(p.grad.cpu().numpy(), gr) < BF16_RELERR, k

@@ -37,7 +37,7 @@ def test_param_layout_and_sizes():
     assert L.packed_bytes(net) % 1024 == 0 or L.packed_bytes(net) > 0
     # pipelined training path: 16-bit phases x 256 features x 5 sine layers per row in whole 128-row tiles, plus the
     # fixed ring / flag storage of the layer pipelines
-    per_tile = 5 * 128 * 256 * 2 + 128 * 16  # + the 16-byte coordinate record per row
+    per_tile = 5 * 2 * 32 * (64 * 16 + 32) + 128 * 16  # padded phase chunks + the 16-byte coordinate record per row
     fixed = L.stash_bytes(net, 128) - per_tile
     assert 0 < fixed < 32 << 20
     assert L.stash_bytes(net, 129) == 2 * per_tile + fixed

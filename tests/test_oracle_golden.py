@@ -187,3 +187,23 @@ def test_fourier_siren_reference_combination(golden_dir):
     np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=2e-6, rtol=1e-4)
     losses = O.torch_fit(m, feats, torch.from_numpy(g["gt"]), 5, 1e-4)
     np.testing.assert_allclose(losses, g["losses"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["model", "slice_model"])
+def test_oracle_on_reference_trained_checkpoints(golden_dir, name):
+    """The two trained checkpoints the reference ships (2 -> 4 x 64 -> 1 SIREN), evaluated by the unmodified
+    SRDWI.Siren in tools/make_golden.py: the numpy oracle reproduces the output and every parameter gradient."""
+    g = _load(golden_dir, "trained_siren64.npz")
+    Ws = [g[f"{name}/w/net.{i}.linear.weight"] for i in range(4)] + [g[f"{name}/w/net.4.weight"]]
+    bs = [g[f"{name}/w/net.{i}.linear.bias"] for i in range(4)] + [g[f"{name}/w/net.4.bias"]]
+    x = O.get_mgrid((128, 128))
+    out = O.siren_forward(Ws, bs, x)
+    np.testing.assert_allclose(out, g[f"{name}/out"], atol=2e-4, rtol=0)
+    loss, gout = O.mse_loss(out, g[f"{name}/target"])
+    assert math.isclose(float(loss), float(g[f"{name}/loss"]), rel_tol=1e-4)
+    dW, db = O.siren_backward(Ws, bs, x, gout)
+    keys = [f"net.{i}.linear" for i in range(4)] + ["net.4"]
+    for k, w, b in zip(keys, dW, db):
+        gw, gb = g[f"{name}/g/{k}.weight"], g[f"{name}/g/{k}.bias"]
+        assert np.abs(w - gw).max() <= 2e-3 * np.abs(gw).max(), k
+        assert np.abs(b - gb).max() <= 2e-3 * np.abs(gb).max(), k

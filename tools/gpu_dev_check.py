@@ -253,10 +253,16 @@ def bwdp_trace():
     np.save(os.path.join(ROOT, "gpurun_out", "bwdp_trace.npy"), t)
     names = ["ld:slot_free", "ld:issued", "ch:dz_full", "ch:acc_empty", "ch:issued", "wg:y_full", "wg:issued",
              "st:stg_full", "st:issued", "st:read_done", "st:published", "ep:start", "ep:acc_full", "ep:loaded",
-             "ep:math_done", "ep:bufs_free", "ep:arrived"]
+             "ep:math_done", "ep:bufs_free", "ep:arrived", "ph:issued", "ph:slot_free", "cv:top", "cv:raw_full", "cv:dob_empty", "cv:done"]
+    # averages over tiles 100..199: every event relative to the tile's ld:issued (stage CTAs) or ep:start
+    for role in range(S2):
+        ref = 1 if role >= 2 else 11
+        seg = t[role, 100:200, :]
+        line = " ".join(f"{names[e]}={np.mean(seg[:, e] - seg[:, ref]):+.0f}" for e in range(23) if seg[:, e].all())
+        print(f"role {role:2d}: period {(t[role, 200, 16] - t[role, 100, 16]) / 100:.0f} clk | {line}")
     for role in (0, 2, 4, 8):
         print(f"role {role}: tile period (ep:arrived, tiles 100..200) = {(t[role, 200, 16] - t[role, 100, 16]) / 100:.0f} clk")
-        for tile in range(100, 106):
+        for tile in range(100, 103):
             base = t[role, tile, 11]
             print(f"  tile {tile} @ {base}: " + " ".join(f"{names[e]}={t[role, tile, e] - base:+d}" for e in range(17)
                                                          if t[role, tile, e] != 0))

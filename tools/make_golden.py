@@ -200,5 +200,37 @@ def main():
     print("wire_cfg3 losses", losses)
 
 
+def trained_case():
+    """The two trained checkpoints the reference ships (model.pt, slice_model.pt: a 2 -> 4 x 64 -> 1 SIREN, keys net.*)
+    loaded into the UNMODIFIED SRDWI.Siren: output on get_mgrid((128, 128)) and the parameter gradients of the MSE
+    against a fixed target.  Realistic (trained) weight and phase distributions for the kernel parity tests."""
+    d = {}
+    for name in ("model", "slice_model"):
+        sd = torch.load(os.path.join(REF, name + ".pt"), map_location="cpu", weights_only=False)
+        sd = {k: v.float() for k, v in sd.items() if k.startswith("net.")}
+        m = SRDWI.Siren(2, 64, 3, 1)
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith("final_linear") for k in missing), (missing, unexpected)
+        x = SRDWI.get_mgrid((128, 128))
+        out = m.forward(x)
+        g = torch.Generator().manual_seed(3)
+        target = torch.rand(out.shape, generator=g)
+        loss = ((out - target) ** 2).mean()
+        loss.backward()
+        for k, v in sd.items():
+            d[f"{name}/w/{k}"] = v.numpy()
+        for k, p in m.net.named_parameters():
+            d[f"{name}/g/net.{k}"] = p.grad.numpy()
+        d[f"{name}/out"] = out.detach().numpy()
+        d[f"{name}/target"] = target.numpy()
+        d[f"{name}/loss"] = np.array(loss.item())
+        print(name, "loss", loss.item(), "out range", out.min().item(), out.max().item())
+    np.savez_compressed(os.path.join(OUT, "trained_siren64.npz"), **d)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "trained":
+        trained_case()
+    else:
+        main()
+        trained_case()
