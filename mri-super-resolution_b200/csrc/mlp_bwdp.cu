@@ -814,6 +814,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
         // every warp passes every phase of the phase-slot barriers (a parity wait may not skip a phase)
         PW(1, mbar_wait(&bars[kBPhFull + ps], (i / nph) & 1));
         if ((i & 1) != grp) {  // the other group's tile: just let the slot go (it is refilled once ALL warps passed)
+          if ((ew & 7) == 0 && lane == 0) TR(15, i);
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[kBPhEmpty + ps]);
           continue;

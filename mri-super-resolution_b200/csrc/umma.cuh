@@ -119,11 +119,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         : "r"(smem_u32(bar)), "r"(parity), "r"(kNs)
         : "memory");
     if (ok) return;
-    if (++spins > (4000000000u / kNs)) {
-      printf("b200inr: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar,
-             parity);
-      __trap();
-    }
+    if (++spins > (4000000000u / kNs)) mbar_timeout(bar, parity);
   }
 }
 
