@@ -117,6 +117,15 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
                            const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
                            void* stream);
 
+/* The same for a network fed with explicit feature rows (B200INR_IN_FEATURES), plus the gradient of those rows:
+ * grad_input [rows, in_features] fp32 (overwritten) = dL/d(features) = dTheta_0 (omega_0 W_0).  Replaces the part of
+ * loss.backward() that reaches the network input when it is not detached -- INRmodel.Siren.forward
+ * (INR/INRmodel.py:147-149), which the PerturbNet phase trains through (INR/inrDWI.py:141-147); the SRDWI variant
+ * detaches its input (INR/SRDWI.py:88) and never needs it.  One more tcgen05 chain step inside the dgrad kernel.
+ * B200INR_ERR_BAD_SHAPE for the other input modes. */
+int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, void* stash, int64_t rows,
+                                 const float* grad_out, float* grad_params, float* grad_input, void* stream);
+
 /* The two kernels of the STAGED b200inr_siren_backward as separate calls (same arguments; backward == dgrad then
  * wgrad).  B200INR_ERR_BAD_SHAPE for a pipelined SIREN (no B200INR_NET_STAGED_BWD): its backward is one kernel.
  * dgrad: activation-gradient chain, fills the stash with dL/dtheta of every sine layer and the bf16 dL/dout tile;
@@ -162,6 +171,10 @@ int b200inr_get_mgrid(const b200inr_grid* grid, int64_t rows, float* coords, voi
 /* input_mapping (INR/SRDWI.py:111-116): out [rows, 2m] = cat(sin(2*pi*x@B.T), cos(2*pi*x@B.T)). */
 int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t d, int32_t m, float* out,
                           void* stream);
+/* Its adjoint with respect to x (the PerturbNet phase differentiates through the feature map, INR/inrDWI.py:142-147):
+ * grad_x [rows, d] = 2 pi (grad_out[:, :m] .* cos p - grad_out[:, m:] .* sin p) B,  p = 2 pi x B^T.  d <= 8. */
+int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,
+                                   int32_t m, float* grad_x, void* stream);
 
 /* ---- self test of the tensor-core plumbing ------------------------------------------------------------
  * One CTA computes D[128,N] = A * B^T with tcgen05.mma from swizzled shared memory.

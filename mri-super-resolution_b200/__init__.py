@@ -9,7 +9,8 @@ Modules: ``inr`` (reference-facing nn.Module surface + fused fit/query), ``SRDWI
 with exactly the reference's import names), ``phantom`` (synthetic DWI volumes), ``_lib`` (ctypes binding of the C
 ABI declared in include/b200inr.h), ``csrc`` (the sm_100a kernels).
 """
-from .inr import ComplexGaborLayer2D, FitSession, FourierMLP, Wire, ImageFitting_set, SineLayer, Siren, get_mgrid, input_mapping  # noqa: F401
+from .inr import (ComplexGaborLayer2D, FitSession, FourierMLP, Wire, ImageFitting_set, PN, SineLayer, Siren,  # noqa: F401
+                  get_mgrid, input_mapping)
 from . import _lib  # noqa: F401
 
-__all__ = ["ComplexGaborLayer2D", "FitSession", "FourierMLP", "Wire", "ImageFitting_set", "SineLayer", "Siren", "get_mgrid", "input_mapping"]
+__all__ = ["ComplexGaborLayer2D", "FitSession", "FourierMLP", "Wire", "ImageFitting_set", "PN", "SineLayer", "Siren", "get_mgrid", "input_mapping"]

@@ -61,6 +61,7 @@ SIGNATURES = {
     "b200inr_stash_bytes": (ctypes.c_int, [_P(Net), _i64, _P(_sz)]),
     "b200inr_siren_forward": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, ctypes.c_int, _f32, _vp, _vp]),
     "b200inr_siren_backward": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _P(Grid), _i64, _vp, _vp, _vp]),
+    "b200inr_siren_backward_input": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200inr_siren_dgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp]),
     "b200inr_siren_wgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, _vp]),
     "b200inr_mse_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b200inr_get_mgrid": (ctypes.c_int, [_P(Grid), _i64, _vp, _vp]),
     "b200inr_input_mapping": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "b200inr_input_mapping_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200inr_selftest_umma": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 

@@ -23,7 +23,7 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
                    int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                    cudaStream_t stream);
 int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                   int num_sms, cudaStream_t stream);
+                   float* grad_in, int num_sms, cudaStream_t stream);
 int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, int num_sms,
                      cudaStream_t stream);
 int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream);
@@ -44,6 +44,8 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
                 float* state, cudaStream_t stream);
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
+int launch_ffm_bwd(const float* x, const float* B, const float* grad_out, int64_t rows, int d, int m, float* grad_x,
+                   cudaStream_t stream);
 
 static bool is_gen(const b200inr_net* net) { return net->input_mode != B200INR_IN_COORDS; }
 static bool is_wire(const b200inr_net* net) { return net->activation == B200INR_ACT_GABOR; }
@@ -244,13 +246,31 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
     return launch_wire_combine(net, stash, rows, grad_params, s);
   }
   if (is_gen(net)) {
-    if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
+    if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
   }
   if (is_piped(net) && !aligned16(grad_out)) return B200INR_ERR_BAD_ALIGN;  // dOut tiles are bulk-copied
   if (is_piped(net)) return launch_siren_bwdp(net, packed, stash, coords, grid, rows, grad_out, grad_params, sms, s);
   if ((e = launch_siren_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
   return launch_siren_wgrad(net, stash, coords, grid, rows, grad_params, sms, s);
+}
+
+int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, void* stash, int64_t rows,
+                                 const float* grad_out, float* grad_params, float* grad_input, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !stash || !grad_out || !grad_params || !grad_input) return B200INR_ERR_NULL;
+  if (net->input_mode != B200INR_IN_FEATURES) return B200INR_ERR_BAD_SHAPE;  // explicit feature rows only
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023) ||
+      !aligned16(grad_params) || !aligned16(grad_input))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, grad_input, sms, s))) return e;
+  return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
 }
 
 int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
@@ -266,7 +286,8 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   if (is_wire(net)) return launch_wire_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
-  if (is_gen(net)) return launch_gen_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
+  if (is_gen(net))
+    return launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
 }
 
@@ -419,6 +440,14 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
   if (rows < 0 || d < 1 || m < 1) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   return launch_ffm(x, B, rows, d, m, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,
+                                   int32_t m, float* grad_x, void* stream) {
+  if (!x || !B || !grad_out || !grad_x) return B200INR_ERR_NULL;
+  if (rows < 0 || d < 1 || d > 8 || m < 1) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  return launch_ffm_bwd(x, B, grad_out, rows, d, m, grad_x, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_selftest_umma(int mode, const void* a_bf16, const void* b_bf16, float* d, int32_t N, int32_t K,

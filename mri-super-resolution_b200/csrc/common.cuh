@@ -216,6 +216,7 @@ struct GenPackLayout {
   size_t wt;     // layers 1..L: nh*kbh chunks each
   size_t wf;     // [kbh][32][64]
   size_t wft;    // nh chunks [256][64]
+  size_t wt0;    // layer 0 transposed (input-gradient step): ceil(K0/256) * kbh chunks, rows >= K0 zero
   size_t total;
   __host__ __device__ size_t w_layer(const GenDims& g, int l) const {
     return l == 0 ? w : w + size_t(g.nh()) * g.kb0() * kGenChunkBytes +
@@ -243,6 +244,8 @@ __host__ __device__ inline GenPackLayout make_gen_pack_layout(const GenDims& g) 
   o += size_t(g.kbh()) * kOutPad * 128;
   p.wft = o;
   o += size_t(g.nh()) * kGenChunkBytes;
+  p.wt0 = o;
+  o += size_t((g.K0 + 255) / 256) * g.kbh() * kGenChunkBytes;
   p.total = o;
   return p;
 }

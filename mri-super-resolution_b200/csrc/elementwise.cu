@@ -251,4 +251,52 @@ int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// Adjoint of input_mapping with respect to x: with p = 2 pi x B^T and upstream gradients
+// (g_sin, g_cos) = grad_out[:, :m], grad_out[:, m:],   dx = 2 pi (g_sin .* cos p - g_cos .* sin p) B.
+// One warp per row, lanes stride over the m frequencies, d <= 8 partial sums reduced with shuffles.
+constexpr int kFfmMaxD = 8;
+__global__ void __launch_bounds__(kEwThreads) ffm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ B,
+                                                             const float* __restrict__ grad_out, long long rows, int d,
+                                                             int m, float* __restrict__ grad_x) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    float xr[kFfmMaxD], acc[kFfmMaxD];
+#pragma unroll
+    for (int j = 0; j < kFfmMaxD; ++j) {
+      xr[j] = (j < d) ? __fmul_rn(6.283185307179586f, x[r * d + j]) : 0.f;
+      acc[j] = 0.f;
+    }
+    const float* g = grad_out + r * 2 * m;
+    for (int k = lane; k < m; k += 32) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < kFfmMaxD; ++j)
+        if (j < d) p = fmaf(xr[j], B[(long long)k * d + j], p);
+      float s, c;
+      sincosf(p, &s, &c);
+      const float t = g[k] * c - g[m + k] * s;
+#pragma unroll
+      for (int j = 0; j < kFfmMaxD; ++j)
+        if (j < d) acc[j] = fmaf(t, B[(long long)k * d + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kFfmMaxD; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      if (lane == 0 && j < d) grad_x[r * d + j] = 6.283185307179586f * acc[j];
+    }
+  }
+}
+
+int launch_ffm_bwd(const float* x, const float* B, const float* grad_out, int64_t rows, int d, int m, float* grad_x,
+                   cudaStream_t stream) {
+  if (d > kFfmMaxD) return B200INR_ERR_BAD_SHAPE;
+  long long blocks = (rows * 32 + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  ffm_bwd_kernel<<<int(blocks), kEwThreads, 0, stream>>>(x, B, grad_out, rows, d, m, grad_x);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 }  // namespace b200inr

@@ -5,7 +5,10 @@
 //     dTheta_L   = (dOut  W_f ) .* act'(theta_L)
 //     dTheta_l-1 = (dTheta_l W'_l) .* act'(theta_l-1)          l = L .. 1
 // act' = cos(theta) from the stashed 16-bit phase (sine) or 1[y > 0] from the stashed bf16 output (ReLU).  The chain
-// stops at layer 0: the network input (Fourier features / explicit features) carries no gradient on this path.
+// normally stops at layer 0.  With grad_in != nullptr (explicit feature rows whose producer needs a gradient: the
+// reference's INRmodel.Siren does not detach its input, INR/INRmodel.py:147-149, and the PerturbNet phase trains
+// through it, INR/inrDWI.py:141-147) one more step runs on the tensor cores,
+//     dX = dTheta_0 (omega_0 W_0)                  [rows, K0] fp32, written to grad_in
 // Every dTheta_l tile and the bf16 dOut tile go to the stash for wgrad.cu.
 //
 // Warp roles as in gen_fwd.cu.
@@ -32,6 +35,7 @@ struct GenBwdParams {
   uint8_t* stash_dz;
   uint8_t* stash_dzo;
   size_t layer_stride;
+  float* grad_in;  // nullptr, or [rows, K0] fp32: dL/d(network input)
 };
 
 template <int H>
@@ -97,15 +101,21 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int dx = p.grad_in != nullptr ? 1 : 0;  // extra chain step: gradient of the network input
+  const int NX = (g.K0 + 255) / 256;            // its N, in 256-column halves
 
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        for (int u = 0; u <= L; ++u) {  // u = 0: W_f^T (NH chunks); u >= 1: W'^T of layer L - u + 1 (NH * kKB chunks)
-          const int nchunks = (u == 0) ? NH : NH * S::kKB;
-          const uint8_t* src = (u == 0) ? p.packed + p.pl.wft : p.packed + p.pl.wt_layer(g, L - u + 1);
+        // u = 0: W_f^T (NH chunks); u = 1..L: W'^T of layer L - u + 1 (NH * kKB chunks); u = L + 1 (input gradient):
+        // (omega_0 W_0)^T, NX * kKB chunks
+        for (int u = 0; u <= L + dx; ++u) {
+          const int nchunks = (u == 0) ? NH : (u <= L ? NH : NX) * S::kKB;
+          const uint8_t* src = (u == 0)   ? p.packed + p.pl.wft
+                               : (u <= L) ? p.packed + p.pl.wt_layer(g, L - u + 1)
+                                          : p.packed + p.pl.wt0;
           for (int j = 0; j < nchunks; ++j, ++c) {
             const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
             if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
@@ -126,14 +136,15 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);  // a_ready completes L + 1 times per tile
-        for (int u = 0; u <= L; ++u) {
+        for (int u = 0; u <= L + dx; ++u) {
           if (u == 0)
             mbar_wait(dzo_ready, t & 1);
           else
             mbar_wait(a_ready, (inst0 + u - 1) & 1);
           tc_fence_after();
           const int kbn = (u == 0) ? 1 : S::kKB;
-          for (int nh = 0; nh < NH; ++nh) {
+          const int nhn = (u <= L) ? NH : NX;
+          for (int nh = 0; nh < nhn; ++nh) {
             for (int kb = 0; kb < kbn; ++kb, ++c) {
               const uint32_t slot = c % S::kSlots;
               mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
@@ -272,6 +283,30 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
       }
+
+      // ---- input gradient: D = dTheta_0 (omega_0 W_0), fp32, straight to global memory (row r, 16 columns per block)
+      if (dx) {
+        mbar_wait(d_full, n & 1);
+        ++n;
+        tc_fence_after();
+        const bool valid = (row0 + r) < p.rows;
+        float* gi = p.grad_in + (row0 + r) * (long long)g.K0;
+        const int kb0 = g.K0 / 64;
+#pragma unroll 1
+        for (int kb = 0; kb < kb0; ++kb) {
+          uint32_t v[16];
+          tmem_ld16(tmem_d + t_lane + kb * 64 + s * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(gi + kb * 64 + s * 16 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          }
+        }
+        tc_fence_before();
+      }
     }
   }
 
@@ -289,8 +324,9 @@ static int launch_gen_bwd_t(const GenBwdParams& p, int grid_x, cudaStream_t stre
 }
 
 int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                   int num_sms, cudaStream_t stream) {
+                   float* grad_in, int num_sms, cudaStream_t stream) {
   GenBwdParams p{};
+  p.grad_in = grad_in;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.g = make_gen_dims(net);
   p.pl = make_gen_pack_layout(p.g);

@@ -141,6 +141,17 @@ __global__ void __launch_bounds__(256) gen_pack_kernel(const GenPackParams p) {
       if (wt) put_bf16(wt + size_t((k >> 8) * (H / 64) + (o >> 6)) * kGenChunkBytes, k & 255, o & 63, v);
     }
   }
+  // layer 0 transposed, operand of the input-gradient step dX = dTheta_0 (omega_0 W_0): N = input k (padded to whole
+  // 256-row chunks with zeros), K = output o; chunk order (n-half over inputs, k-block over outputs) like wt
+  {
+    const int K0p = ((g.K0 + 255) / 256) * 256;
+    uint8_t* wt0 = p.packed + p.pl.wt0;
+    for (long long i = tid; i < (long long)H * K0p; i += nthreads) {
+      const int o = int(i / K0p), k = int(i % K0p);
+      const float v = (k < g.K0) ? g.omega0 * p.params[p.off[0] + (long long)o * g.K0 + k] : 0.f;
+      put_bf16(wt0 + size_t((k >> 8) * (H / 64) + (o >> 6)) * kGenChunkBytes, k & 255, o & 63, v);
+    }
+  }
   // final linear
   for (long long i = tid; i < (long long)kOutPad * H; i += nthreads) {
     const int c = int(i / H), k = int(i % H);

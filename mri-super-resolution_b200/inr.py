@@ -90,26 +90,77 @@ class ImageFitting_set(Dataset):
         return self.coords, self.pixels
 
 
+class _InputMappingFunction(torch.autograd.Function):
+    """input_mapping as one kernel; its adjoint with respect to x as another (B carries no gradient: it is a fixed
+    random matrix in the reference, INR/superresDWI.py:105-106)."""
+
+    @staticmethod
+    def forward(ctx, x, B):
+        rows, d = x.shape
+        m = B.shape[0]
+        out = torch.empty((rows, 2 * m), dtype=torch.float32, device=x.device)
+        if rows:
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().b200inr_input_mapping(_ptr(x), _ptr(B), rows, d, m, _ptr(out), _stream()),
+                           "input_mapping")
+        ctx.save_for_backward(x, B)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, B = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        rows, d = x.shape
+        grad_x = torch.empty_like(x)
+        if rows:
+            grad_out = grad_out.contiguous().float()
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().b200inr_input_mapping_backward(_ptr(x), _ptr(B), _ptr(grad_out), rows, d,
+                                                                      B.shape[0], _ptr(grad_x), _stream()),
+                           "input_mapping_backward")
+        return grad_x, None
+
+
 def input_mapping(x, B):
-    """Reference INR/SRDWI.py:111-116: cat([sin(2 pi x B^T), cos(2 pi x B^T)], -1); identity when B is None."""
+    """Reference INR/SRDWI.py:111-116: cat([sin(2 pi x B^T), cos(2 pi x B^T)], -1); identity when B is None.
+    Differentiable with respect to x (the PerturbNet phase trains through it, INR/inrDWI.py:142-147)."""
     if B is None:
         return x
     _require_cuda(x, "input_mapping input")
     _require_cuda(B, "input_mapping B")
-    x = x.detach().contiguous().float()
     B = B.detach().contiguous().float()
-    rows, d = x.shape
-    m = B.shape[0]
-    if B.shape[1] != d:
-        raise RuntimeError("b200inr: input_mapping expects B of shape [m, d]")
-    out = torch.empty((rows, 2 * m), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.load().b200inr_input_mapping(_ptr(x), _ptr(B), rows, d, m, _ptr(out), _stream()),
-                   "input_mapping")
-    return out
+    if x.dim() != 2 or B.dim() != 2 or B.shape[1] != x.shape[1]:
+        raise RuntimeError("b200inr: input_mapping expects x [N, d] and B [m, d]")
+    if x.requires_grad and torch.is_grad_enabled():
+        if x.shape[1] > 8:
+            raise RuntimeError("b200inr: input_mapping is differentiable for d <= 8 coordinates")
+        return _InputMappingFunction.apply(x.contiguous().float(), B)
+    with torch.no_grad():
+        return _InputMappingFunction.apply(x.detach().contiguous().float(), B)
 
 
 # ------------------------------------------------------------------------------------------------ layers
+class PN(nn.Module):
+    """Perturbation network of the reference (INR/INRmodel.py:153-169): a (features + acquisition index) -> hidden ->
+    `dimension` tanh MLP whose output, scaled by eps, replaces the coordinates fed to input_mapping in the PerturbNet
+    phase (INR/inrDWI.py:141-142).  Same constructor, parameter names (state-dict keys
+    perturb_linear.*, perturb_linear2.*) and RNG order.  Two tiny dense layers: plain PyTorch; the expensive part of
+    the phase -- the gradient through input_mapping and the INR -- runs in the fused kernels."""
+
+    def __init__(self, in_features, hidden_features, dimension):
+        super().__init__()
+        self.tanh = nn.Tanh()
+        self.perturb_linear = nn.Linear(in_features + 1, hidden_features)
+        self.perturb_linear2 = nn.Linear(hidden_features, dimension)
+
+    def forward(self, coords, sample=0, eps=0):
+        x = coords.detach()  # the reference detaches its input (INR/INRmodel.py:161)
+        acq = x.new_full((x.shape[0], 1), sample / 10.)
+        hidden = self.tanh(self.perturb_linear(torch.cat((x, acq), -1)))
+        return eps * self.tanh(self.perturb_linear2(hidden))
+
+
 class SineLayer(nn.Module):
     """Reference INR/SRDWI.py:41-64.  Parameter container with the reference's initialisation; the arithmetic runs
     fused inside Siren (one kernel for the whole network), so a stand-alone forward is a 0-hidden-layer fused call."""
@@ -140,7 +191,7 @@ class _SirenFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, coords, module, *params):
-        needs_grad = any(ctx.needs_input_grad[2:])
+        needs_grad = any(ctx.needs_input_grad[2:]) or ctx.needs_input_grad[0]
         out, stash = module._forward_rows(coords=coords, grid=None, rows=coords.shape[0], train=needs_grad)
         ctx.module = module
         ctx.stash = stash
@@ -152,7 +203,8 @@ class _SirenFunction(torch.autograd.Function):
         module = ctx.module
         if ctx.stash is None:
             raise RuntimeError("b200inr: backward called on a forward that did not record activations")
-        flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out)
+        grad_in = torch.empty_like(ctx.coords) if ctx.needs_input_grad[0] else None
+        flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out, grad_in=grad_in)
         ctx.stash = None
         grads = []
         for o, p in zip(module._offsets_canonical(), module._canonical()):
@@ -160,7 +212,7 @@ class _SirenFunction(torch.autograd.Function):
                 grads.append(torch.view_as_complex(flat_grad[o:o + 2 * p.numel()].view(*p.shape, 2)))
             else:
                 grads.append(flat_grad[o:o + p.numel()].view_as(p))
-        return (None, None, *grads)
+        return (grad_in, None, *grads)
 
 
 class _FusedMLP(nn.Module):
@@ -245,7 +297,9 @@ class _FusedMLP(nn.Module):
                 rows, _ptr(out), int(clamp is not None), float(clamp or 0.0), _ptr(stash), _stream()), "siren_forward")
         return out, stash
 
-    def _backward_rows(self, stash, coords, grid, rows, grad_out, flat_grad=None, eng=None):
+    def _backward_rows(self, stash, coords, grid, rows, grad_out, flat_grad=None, eng=None, grad_in=None):
+        """grad_in: None, or a [rows, in_features] fp32 tensor that receives dL/d(input rows) (explicit-feature
+        networks only: b200inr_siren_backward_input)."""
         eng = eng or self._engine_state()
         dev = eng["device"]
         grad_out = grad_out.contiguous().float()
@@ -254,6 +308,12 @@ class _FusedMLP(nn.Module):
         if flat_grad is None:
             flat_grad = torch.zeros_like(eng["flat"])
         if rows == 0:
+            return flat_grad
+        if grad_in is not None:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().b200inr_siren_backward_input(
+                    ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(stash), rows, _ptr(grad_out), _ptr(flat_grad),
+                    _ptr(grad_in), _stream()), "siren_backward_input")
             return flat_grad
         with torch.cuda.device(dev):
             _lib.check(_lib.load().b200inr_siren_backward(
@@ -264,12 +324,17 @@ class _FusedMLP(nn.Module):
 
     # ---------------------------------------------------------------- nn.Module protocol
     def forward(self, coords):
-        """out = INR.forward(x) (INR/superresDWI.py:134).  Coordinates carry no gradient: SRDWI.Siren detaches them
-        (INR/SRDWI.py:88); the INRmodel variant's input gradient (PerturbNet phase) is not part of this path."""
+        """out = INR.forward(x) (INR/superresDWI.py:134).  SRDWI.Siren detaches its input (INR/SRDWI.py:88), so does
+        this; INRmodel.Siren does not (INR/INRmodel.py:147-149): when that variant is fed explicit feature rows that
+        require grad (the PerturbNet phase, INR/inrDWI.py:141-147), dL/d(features) comes out of the backward kernel."""
         _require_cuda(coords, "forward input")
         if coords.dim() != 2 or coords.shape[1] != self.in_features:
             raise RuntimeError(f"b200inr: expected an input of shape [N, {self.in_features}]")
-        coords = coords.detach().contiguous().float()
+        keep = (getattr(self, "variant", "SRDWI") == "INRmodel" and coords.requires_grad and torch.is_grad_enabled())
+        if keep and self._desc.input_mode != _lib.IN_FEATURES:
+            raise RuntimeError("b200inr: the input gradient is implemented for explicit feature rows (in_features >= 64), "
+                               "the way the reference's PerturbNet phase feeds the network; raw coordinates carry none")
+        coords = coords.contiguous().float() if keep else coords.detach().contiguous().float()
         return _SirenFunction.apply(coords, self, *self._canonical())
 
     # ---------------------------------------------------------------- fused query

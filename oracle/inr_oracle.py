@@ -288,6 +288,35 @@ def torch_siren(in_features, hidden_features, hidden_layers, out_features, first
     return _Net()
 
 
+def torch_input_mapping(x, B):
+    """input_mapping (INR/SRDWI.py:111-116) as a differentiable CPU torch expression: cat(sin p, cos p), p = 2 pi x B^T."""
+    import torch
+    p = (2.0 * math.pi * x) @ B.T
+    return torch.cat([torch.sin(p), torch.cos(p)], dim=-1)
+
+
+def torch_pn(in_features, hidden_features, dimension):
+    """CPU restatement of the reference's perturbation network PN (INR/INRmodel.py:153-169): detach the input, append
+    the acquisition index sample / 10 as one more column, Linear -> tanh -> Linear -> eps * tanh.  Same parameter names
+    and construction order (the reference builds its index column with .cuda(); this one stays on the input's device)."""
+    import torch
+    from torch import nn
+
+    class _PN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.perturb_linear = nn.Linear(in_features + 1, hidden_features)
+            self.perturb_linear2 = nn.Linear(hidden_features, dimension)
+
+        def forward(self, coords, sample=0, eps=0):
+            x = coords.detach()
+            col = torch.full((x.shape[0], 1), sample / 10.0, dtype=x.dtype)
+            h = torch.tanh(self.perturb_linear(torch.cat([x, col], dim=-1)))
+            return eps * torch.tanh(self.perturb_linear2(h))
+
+    return _PN()
+
+
 def torch_relu_mlp(in_dim, hidden_features, hidden_layers, out_features):
     """BASELINE config 4's network: Linear(in, H) + ReLU, `hidden_layers` x (Linear(H, H) + ReLU), Linear(H, C) with
     torch's default initialisation, fed with input_mapping(coords, B) (the reference only ever

@@ -801,3 +801,77 @@ def test_reference_trained_checkpoints(dev, golden_dir, name, piped):
     for k, p in m.net.named_parameters():
         gr = g[f"{name}/g/net.{k}"]
         assert _relerr(p.grad.cpu().numpy(), gr) < BF16_RELERR, k
+
+
+# ------------------------------------------------------------------------------------------------ PerturbNet phase
+def test_input_mapping_adjoint_vs_torch(dev):
+    """d/dx of input_mapping against autograd of the torch expression, d = 1..4 and m not a
+    multiple of 32."""
+    for d, m, rows in ((3, 128, 1000), (2, 50, 257), (1, 7, 33), (4, 256, 129)):
+        torch.manual_seed(d * 100 + m)
+        x = (torch.rand(rows, d, device=dev) * 2 - 1).requires_grad_(True)
+        B = torch.randn(m, d, device=dev) * 0.5
+        g = torch.randn(rows, 2 * m, device=dev)
+        out = b200inr.input_mapping(x, B)
+        out.backward(g)
+        x2 = x.detach().clone().requires_grad_(True)
+        ref = O.torch_input_mapping(x2.cpu().double(), B.cpu().double())
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=2e-5)
+        gx, = torch.autograd.grad(ref, x2, g.cpu().double())
+        assert _relerr(x.grad.cpu().numpy(), gx.cpu().numpy()) < 1e-4, (d, m)
+
+
+def test_perturbnet_step_vs_reference_golden(dev, golden_dir):
+    """One PerturbNet step of the reference pipeline (INR/inrDWI.py:141-147) through the drop-in modules at the
+    script's own sizes -- INRmodel.Siren(256, 512, 3, 1) fed with input_mapping(PN(features, sample, eps), B) --
+    against the unmodified reference (tools/make_golden.py: perturb_case): same weights from the seed, same
+    perturbation, loss, dL/d(features) out of the backward kernel, and PN parameter gradients through the
+    input_mapping adjoint."""
+    g = np.load(os.path.join(golden_dir, "perturb_step.npz"))
+    B = torch.from_numpy(g["B"]).to(dev)
+    coords = b200inr.get_mgrid((10, 10, 10)).to(dev)
+    torch.manual_seed(int(g["seed"]))
+    inr = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3)
+    pn = b200inr.INRmodel.PN(in_features=256, hidden_features=128, dimension=3)
+    inr, pn = inr.to(dev), pn.to(dev)
+    model_input = b200inr.input_mapping(coords, B)
+    perturbation = pn.forward(model_input, 3, 1 / 128.)
+    np.testing.assert_allclose(perturbation.detach().cpu().numpy(), g["perturbation"], atol=2e-6)
+    feats = b200inr.input_mapping(perturbation, B)
+    feats.retain_grad()
+    out = inr.forward(feats)
+    loss = ((out - torch.from_numpy(g["gt"]).to(dev)) ** 2).mean()
+    loss.backward()
+    # every row sees nearly the same features here (|perturbation| <= 5e-3), so the outputs are ~6e-3: a 512-term dot
+    # product of O(1) bf16 activations with +-3.6e-3 weights -- the bf16 rounding shows as ~1e-4 absolute
+    assert np.abs(out.detach().cpu().numpy() - g["out"]).max() < 5e-4
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=2e-2)
+    assert feats.grad is not None and feats.grad.shape == (1000, 256)
+    assert _relerr(feats.grad.cpu().numpy()[:128], g["g_feats"]) < BF16_RELERR
+    for k, p in pn.named_parameters():
+        assert _relerr(p.grad.cpu().numpy(), g["g_pn/" + k]) < BF16_RELERR, k
+    assert _relerr(inr.net[0].linear.bias.grad.cpu().numpy(), g["g_inr_first_bias"]) < BF16_RELERR
+    assert _relerr(inr.final_linear.weight.grad.cpu().numpy(), g["g_inr_final_weight"]) < BF16_RELERR
+    # the SRDWI variant detaches its input (INR/SRDWI.py:88): no gradient reaches the features
+    torch.manual_seed(1)
+    srdwi = b200inr.Siren(256, 256, 1, 1).to(dev)
+    f2 = model_input.detach().clone().requires_grad_(True)
+    srdwi(f2).sum().backward()
+    assert f2.grad is None
+
+
+@pytest.mark.parametrize("act_H_K0", [(256, 64), (256, 192), (512, 512)])
+def test_input_gradient_widths_vs_torch(dev, act_H_K0):
+    """dL/d(features) for input widths that are not a whole 256-column MMA half, and K0 = H = 512."""
+    H, K0 = act_H_K0
+    torch.manual_seed(H + K0)
+    m = b200inr.INRmodel.Siren(K0, H, 1, 5).to(dev)
+    ref = O.torch_siren(K0, H, 1, 5, order="INRmodel")
+    ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    x = (torch.rand(300, K0, device=dev) * 2 - 1) * 0.05
+    gout = torch.randn(300, 5, device=dev)
+    xg = x.clone().requires_grad_(True)
+    m(xg).backward(gout)
+    xr = x.cpu().clone().requires_grad_(True)
+    ref(xr).backward(gout.cpu())
+    assert _relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < BF16_RELERR

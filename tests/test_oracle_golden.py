@@ -207,3 +207,32 @@ def test_oracle_on_reference_trained_checkpoints(golden_dir, name):
         gw, gb = g[f"{name}/g/{k}.weight"], g[f"{name}/g/{k}.bias"]
         assert np.abs(w - gw).max() <= 2e-3 * np.abs(gw).max(), k
         assert np.abs(b - gb).max() <= 2e-3 * np.abs(gb).max(), k
+
+
+def test_perturbnet_step_restatement_matches_reference(golden_dir):
+    """One PerturbNet step (INR/inrDWI.py:141-147) of the unmodified reference (tools/make_golden.py: perturb_case):
+    the oracle's PN / input_mapping / INRmodel-order Siren restatements give the same weights from the seed, the same
+    perturbation, loss and gradients (PN parameters, dL/d features)."""
+    g = _load(golden_dir, "perturb_step.npz")
+    B = torch.from_numpy(g["B"])
+    coords = torch.from_numpy(O.get_mgrid((10, 10, 10)))
+    torch.manual_seed(int(g["seed"]))
+    inr = O.torch_siren(256, 512, 3, 1, order="INRmodel")
+    pn = O.torch_pn(256, 128, 3)
+    for k, p in pn.named_parameters():
+        np.testing.assert_allclose(_cs(p), g["cs_pn/" + k], rtol=1e-12, atol=0)
+    for k, p in inr.net.named_parameters():
+        np.testing.assert_allclose(_cs(p), g["cs_inr/" + k], rtol=1e-12, atol=0)
+    model_input = O.torch_input_mapping(coords, B)
+    perturbation = pn(model_input, 3, 1 / 128.)
+    np.testing.assert_allclose(perturbation.detach().numpy(), g["perturbation"], atol=1e-7, rtol=1e-4)
+    feats = O.torch_input_mapping(perturbation, B)
+    feats.retain_grad()
+    out = inr(feats)
+    loss = ((out - torch.from_numpy(g["gt"])) ** 2).mean()
+    loss.backward()
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=1e-5)
+    np.testing.assert_allclose(feats.grad.numpy()[:128], g["g_feats"], atol=1e-9, rtol=1e-3)
+    for k, p in pn.named_parameters():
+        gr = g["g_pn/" + k]
+        assert np.abs(p.grad.numpy() - gr).max() <= 1e-3 * np.abs(gr).max() + 1e-12, k

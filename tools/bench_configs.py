@@ -62,6 +62,34 @@ def query_line(name, model, shape, flop_per_row, steps):
             "frac_of_burst_peak": tf / PEAK["bf16_tflops"], "output_gb": rows * model.out_features * 4 / 1e9}
 
 
+def perturb_line(name, shape, steps):
+    """one PerturbNet step of the reference pipeline (INR/inrDWI.py:141-147) at the script's
+    own network sizes through the drop-in modules and autograd: PN -> input_mapping -> INRmodel.Siren(256, 512, 3, 1)
+    -> MSE -> backward (dL/d features out of the fused backward kernel, input_mapping adjoint kernel) -> Adam on PN."""
+    dev = torch.device("cuda:0")
+    rows = int(np.prod(shape))
+    B = torch.from_numpy(np.random.RandomState(1).normal(size=(128, 3)) * 0.5).float().to(dev)
+    inr = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3).to(dev)
+    pn = b200inr.INRmodel.PN(in_features=256, hidden_features=128, dimension=3).to(dev)
+    opt = torch.optim.Adam(lr=1e-6, params=list(pn.parameters()))
+    model_input = b200inr.input_mapping(b200inr.get_mgrid(shape).to(dev), B)
+    gt = torch.rand(rows, 1, device=dev)
+
+    def step():
+        feats = b200inr.input_mapping(pn.forward(model_input, 3, 1 / 128.), B)
+        loss = ((inr.forward(feats) - gt) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    ms = timed(step, steps)
+    flop_per_row = 6 * (256 * 512 + 3 * 512 * 512 + 512)  # INR forward + dgrad (incl. dL/d features) + wgrad
+    tf = flop_per_row * rows / (ms * 1e-3) / 1e12
+    return {"config": name, "metric": "perturbnet_coord_samples_per_s", "value": rows / (ms * 1e-3), "ms_per_step": ms,
+            "rows": rows, "tflops_algorithmic_inr": tf, "frac_of_sustained_peak": tf / PEAK["bf16_tflops_sustained"],
+            "note": "module loop through torch autograd; INR weight gradients are computed too (as in the reference)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -93,6 +121,10 @@ def main():
     lines.append(query_line("cfg4 FF-ReLU query 128x128x64", m4, hr_shape, 2130432, a.steps))
     # cfg5: 4x HR grid inference 512x512x256 x 31 channels with the cfg2 network (one GPU: the whole grid)
     lines.append(query_line("cfg5 SIREN query 512x512x256 (whole grid on one GPU)", m2, (512, 512, 256), 541696, 3))
+    del m2, m3, m4
+    torch.cuda.empty_cache()
+    lines.append(perturb_line("PerturbNet step (INR/inrDWI.py:141-147), Siren(256,512,3,1) + PN(256,128,3), 128x128x64",
+                              hr_shape, max(3, a.steps // 2)))
     for ln in lines:
         print(json.dumps(ln), flush=True)
 

@@ -228,9 +228,53 @@ def trained_case():
     np.savez_compressed(os.path.join(OUT, "trained_siren64.npz"), **d)
 
 
+def perturb_case():
+    """One PerturbNet step of the reference pipeline (INR/inrDWI.py:141-147) with the UNMODIFIED INRmodel.Siren, PN and
+    input_mapping at the script's own sizes (m = 128, Siren(256, 512, 3, 1), PN(256, 128, 3), eps = 1/128) on 1000
+    coordinates.  PN.forward builds its acquisition column with .cuda(); there is no GPU here, so Tensor.cuda is
+    shimmed to the identity for the duration of the call (an environment shim, the reference code is not touched).
+    Weights come from the seed (our modules reproduce the RNG order), so only checksums of them are stored."""
+    rs = np.random.RandomState(5)
+    B = torch.from_numpy(rs.normal(size=(128, 3)) * 0.5).float()
+    coords = INRmodel.get_mgrid((10, 10, 10))
+    gt = torch.from_numpy(rs.uniform(size=(1000, 1))).float()
+    torch.manual_seed(31)
+    inr = INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3)
+    pn = INRmodel.PN(in_features=256, hidden_features=128, dimension=3)
+    model_input = INRmodel.input_mapping(coords, B)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        perturbation = pn.forward(model_input, 3, 1 / 128.)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    feats = INRmodel.input_mapping(perturbation, B)
+    feats.retain_grad()
+    out = inr.forward(feats)
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    d = {"B": B.numpy(), "gt": gt.numpy(), "seed": np.array(31), "loss": np.array(loss.item()),
+         "perturbation": perturbation.detach().numpy(), "out": out.detach().numpy(),
+         "g_feats": feats.grad.numpy()[:128].copy(), "g_feats_cs": checksum(feats.grad)}
+    for k, p in pn.named_parameters():
+        d["g_pn/" + k] = p.grad.numpy()
+        d["cs_pn/" + k] = checksum(p)
+    for k, p in inr.net.named_parameters():
+        d["cs_inr/" + k] = checksum(p)
+        d["gcs_inr/" + k] = checksum(p.grad)
+    d["g_inr_first_bias"] = inr.net[0].linear.bias.grad.numpy()
+    d["g_inr_final_weight"] = inr.final_linear.weight.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "perturb_step.npz"), **d)
+    print("perturb_step loss", loss.item(), "|perturbation| max", perturbation.abs().max().item(),
+          "|g_feats| max", feats.grad.abs().max().item())
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "trained":
+    if len(sys.argv) > 1 and sys.argv[1] == "perturb":
+        perturb_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trained":
         trained_case()
     else:
         main()
         trained_case()
+        perturb_case()
