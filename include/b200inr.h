@@ -176,6 +176,13 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
 int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,
                                    int32_t m, float* grad_x, void* stream);
 
+/* calculate_ADC (INR/SRDWI.py:118-130), the step right after the query: per voxel the least-squares line through
+ * (b_k / 1000, log(signal_k + 1e-7)); adc[v] = -slope clamped to [-10, 3].  signal [voxels, nb] fp32 on the device
+ * (e.g. the [rows, C] output of b200inr_siren_forward, nb = C), bvalues_host [nb] on the HOST (2 <= nb <= 64, not all
+ * equal), adc [voxels] fp32 on the device. */
+int b200inr_adc_fit(const float* signal, const float* bvalues_host, int64_t voxels, int32_t nb, float* adc,
+                    void* stream);
+
 /* ---- self test of the tensor-core plumbing ------------------------------------------------------------
  * One CTA computes D[128,N] = A * B^T with tcgen05.mma from swizzled shared memory.
  * mode 0: K-major operands, a[128,K], b[N,K] row-major bf16.  mode 1: MN-major operands, a[K,128], b[K,N].

@@ -44,6 +44,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
                 float* state, cudaStream_t stream);
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
+int launch_adc(const float* signal, const float* bvalues_host, int64_t voxels, int nb, float* adc, cudaStream_t stream);
 int launch_ffm_bwd(const float* x, const float* B, const float* grad_out, int64_t rows, int d, int m, float* grad_x,
                    cudaStream_t stream);
 
@@ -440,6 +441,14 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
   if (rows < 0 || d < 1 || m < 1) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   return launch_ffm(x, B, rows, d, m, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_adc_fit(const float* signal, const float* bvalues_host, int64_t voxels, int32_t nb, float* adc,
+                    void* stream) {
+  if (!signal || !bvalues_host || !adc) return B200INR_ERR_NULL;
+  if (voxels < 0) return B200INR_ERR_BAD_SHAPE;
+  if (voxels == 0) return (nb >= 2 && nb <= 64) ? B200INR_OK : B200INR_ERR_BAD_SHAPE;
+  return launch_adc(signal, bvalues_host, voxels, nb, adc, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,

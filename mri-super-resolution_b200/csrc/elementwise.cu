@@ -299,4 +299,49 @@ int launch_ffm_bwd(const float* x, const float* B, const float* grad_out, int64_
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ calculate_ADC   INR/SRDWI.py:118-130
+// Per voxel: least-squares line through (b_k / 1000, log(s_k + 1e-7)), ADC = -slope clamped to [-10, 3].  The reference
+// runs a Python double loop with np.polyfit (float64); here one thread owns one voxel, nb <= 64 samples contiguous in
+// memory, log in fp32 (1 ulp), the four sums in double.  sum_x / sum_xx depend on the b-values only.
+constexpr int kAdcMaxB = 64;
+struct AdcParams {
+  float x[kAdcMaxB];  // b / 1000
+  double sx, sxx;
+  int nb;
+};
+__global__ void __launch_bounds__(kEwThreads) adc_kernel(const float* __restrict__ signal, long long voxels,
+                                                         const AdcParams p, float* __restrict__ adc) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double n = double(p.nb);
+  const double den = n * p.sxx - p.sx * p.sx;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < voxels; v += stride) {
+    const float* s = signal + v * p.nb;
+    double sy = 0.0, sxy = 0.0;
+    for (int k = 0; k < p.nb; ++k) {
+      const double y = double(logf(s[k] + 1e-7f));
+      sy += y;
+      sxy += double(p.x[k]) * y;
+    }
+    const double slope = (n * sxy - p.sx * sy) / den;
+    adc[v] = float(fmin(fmax(-slope, -10.0), 3.0));
+  }
+}
+
+int launch_adc(const float* signal, const float* bvalues_host, int64_t voxels, int nb, float* adc, cudaStream_t stream) {
+  if (nb < 2 || nb > kAdcMaxB) return B200INR_ERR_BAD_SHAPE;
+  AdcParams p{};
+  p.nb = nb;
+  for (int k = 0; k < nb; ++k) {
+    p.x[k] = bvalues_host[k] / 1000.0f;
+    p.sx += double(p.x[k]);
+    p.sxx += double(p.x[k]) * double(p.x[k]);
+  }
+  if (!(double(nb) * p.sxx - p.sx * p.sx > 0.0)) return B200INR_ERR_BAD_SHAPE;  // all b-values equal: no slope
+  long long blocks = (voxels + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  adc_kernel<<<int(blocks), kEwThreads, 0, stream>>>(signal, voxels, p, adc);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 }  // namespace b200inr

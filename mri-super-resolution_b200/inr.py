@@ -140,6 +140,34 @@ def input_mapping(x, B):
         return _InputMappingFunction.apply(x.detach().contiguous().float(), B)
 
 
+def calculate_ADC(bvalues, slicedata):
+    """Reference INR/SRDWI.py:118-130 (= INR/INRmodel.py): per-voxel mono-exponential fit, ADC = -slope of the
+    least-squares line through (b / 1000, log(signal + 1e-7)), clamped to [-10, 3] -- one kernel instead of a Python
+    double loop over np.polyfit.
+
+    slicedata [..., nb]: a CUDA tensor (e.g. query(...).view(X, Y, Z, C): stays on the device, returns a CUDA fp32
+    tensor [...]) or a NumPy array as in the reference (uploaded to the current CUDA device; returns a float64 array
+    of shape slicedata.shape[:-1], the reference's return type).  bvalues: nb values (array / list / tensor).
+    """
+    b = np.asarray(bvalues.detach().cpu() if torch.is_tensor(bvalues) else bvalues, dtype=np.float32).reshape(-1)
+    as_numpy = not torch.is_tensor(slicedata)
+    if as_numpy:
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200inr: calculate_ADC needs a CUDA device; there is no CPU path")
+        slicedata = torch.from_numpy(np.ascontiguousarray(slicedata, dtype=np.float32)).cuda()
+    _require_cuda(slicedata, "calculate_ADC input")
+    if slicedata.shape[-1] != b.size:
+        raise RuntimeError("b200inr: calculate_ADC expects one signal per b-value along the last axis")
+    sig = slicedata.detach().contiguous().float()
+    voxels = sig.numel() // b.size if b.size else 0
+    adc = torch.empty(sig.shape[:-1], dtype=torch.float32, device=sig.device)
+    bh = np.ascontiguousarray(b)
+    with torch.cuda.device(sig.device):
+        _lib.check(_lib.load().b200inr_adc_fit(_ptr(sig), bh.ctypes.data, voxels, int(b.size), _ptr(adc), _stream()),
+                   "adc_fit")
+    return adc.cpu().numpy().astype(np.float64) if as_numpy else adc
+
+
 # ------------------------------------------------------------------------------------------------ layers
 class PN(nn.Module):
     """Perturbation network of the reference (INR/INRmodel.py:153-169): a (features + acquisition index) -> hidden ->

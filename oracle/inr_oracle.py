@@ -288,6 +288,16 @@ def torch_siren(in_features, hidden_features, hidden_layers, out_features, first
     return _Net()
 
 
+def calculate_adc(bvalues, data):
+    """calculate_ADC (INR/SRDWI.py:118-130) vectorised: np.polyfit(b / 1000, log(y + 1e-7), 1) per voxel in closed form
+    (float64), ADC = -slope clamped to [-10, 3].  data [..., nb] -> [...]."""
+    x = np.asarray(bvalues, dtype=np.float64).reshape(-1) / 1000.0
+    y = np.log(np.asarray(data) + 1e-7).astype(np.float64)  # log in the input's own precision, as the reference
+    xc = x - x.mean()
+    slope = (y * xc).sum(-1) / (xc * xc).sum()
+    return np.clip(-slope, -10.0, 3.0)
+
+
 def torch_input_mapping(x, B):
     """input_mapping (INR/SRDWI.py:111-116) as a differentiable CPU torch expression: cat(sin p, cos p), p = 2 pi x B^T."""
     import torch

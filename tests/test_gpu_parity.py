@@ -875,3 +875,22 @@ def test_input_gradient_widths_vs_torch(dev, act_H_K0):
     xr = x.cpu().clone().requires_grad_(True)
     ref(xr).backward(gout.cpu())
     assert _relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < BF16_RELERR
+
+
+# ------------------------------------------------------------------------------------------------ ADC map
+def test_calculate_adc_vs_reference_golden_and_oracle(dev, golden_dir):
+    """calculate_ADC (INR/SRDWI.py:118-130) as one kernel: the reference's own output on the golden slice (NumPy in,
+    float64 NumPy out, like the reference), and the oracle on a full 128 x 128 x 64 x 4 device-resident volume."""
+    g = np.load(os.path.join(golden_dir, "adc_slice.npz"))
+    ours = b200inr.calculate_ADC(g["bvalues"], g["data"])
+    assert isinstance(ours, np.ndarray) and ours.dtype == np.float64 and ours.shape == g["adc"].shape
+    np.testing.assert_allclose(ours, g["adc"], atol=2e-5, rtol=2e-5)
+    rs = np.random.RandomState(3)
+    bv = np.array([0.0, 150.0, 1000.0, 1500.0])
+    vol = (rs.uniform(0.05, 1.0, size=(128, 128, 64, 1)) * np.exp(-bv / 1000.0 * rs.uniform(0.2, 3.5, size=(128, 128, 64, 1))))
+    vol = vol.astype(np.float32)
+    dev_out = b200inr.calculate_ADC(bv, torch.from_numpy(vol).to(dev))
+    assert dev_out.is_cuda and dev_out.shape == (128, 128, 64) and dev_out.dtype == torch.float32
+    np.testing.assert_allclose(dev_out.cpu().numpy(), O.calculate_adc(bv, vol), atol=3e-5, rtol=3e-5)
+    with pytest.raises(RuntimeError):
+        b200inr.calculate_ADC(np.array([5.0, 5.0]), torch.ones(4, 2, device=dev))  # equal b-values: no slope

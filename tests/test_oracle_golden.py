@@ -236,3 +236,13 @@ def test_perturbnet_step_restatement_matches_reference(golden_dir):
     for k, p in pn.named_parameters():
         gr = g["g_pn/" + k]
         assert np.abs(p.grad.numpy() - gr).max() <= 1e-3 * np.abs(gr).max() + 1e-12, k
+
+
+def test_calculate_adc_matches_reference(golden_dir):
+    """Closed-form per-voxel fit == the reference's np.polyfit double loop (tools/make_golden.py: adc_case), clamps and
+    the empty voxel included."""
+    g = _load(golden_dir, "adc_slice.npz")
+    ours = O.calculate_adc(g["bvalues"], g["data"])
+    assert ours.shape == g["adc"].shape
+    np.testing.assert_allclose(ours, g["adc"], atol=1e-9, rtol=1e-9)
+    assert ours[0, 1] == 3.0 and ours[0, 0] < 0 and abs(ours[0, 2]) < 1e-12

@@ -269,8 +269,27 @@ def perturb_case():
           "|g_feats| max", feats.grad.abs().max().item())
 
 
+def adc_case():
+    """calculate_ADC of the unmodified reference (INR/SRDWI.py:118-130) on a small synthetic slice: mono-exponential
+    decays with noise, a few voxels driven into both clamps and to zero signal."""
+    rs = np.random.RandomState(9)
+    bvalues = np.array([0.0, 150.0, 1000.0, 1500.0])
+    adc_true = rs.uniform(0.3, 2.8, size=(12, 10))
+    s0 = rs.uniform(0.2, 1.0, size=(12, 10))
+    data = s0[..., None] * np.exp(-bvalues / 1000.0 * adc_true[..., None]) * (1 + 0.02 * rs.normal(size=(12, 10, 4)))
+    data[0, 0] = [1e-3, 1e-2, 0.5, 1.0]     # growing signal: negative ADC
+    data[0, 1] = [1.0, 0.5, 1e-4, 1e-7]     # very fast decay: upper clamp
+    data[0, 2] = 0.0                        # empty voxel: log(eps) everywhere, slope 0
+    data = np.abs(data).astype(np.float32)
+    ref = SRDWI.calculate_ADC(bvalues, data)
+    np.savez_compressed(os.path.join(OUT, "adc_slice.npz"), bvalues=bvalues, data=data, adc=ref)
+    print("adc_slice", ref.min(), ref.max(), ref[0, :3])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "perturb":
+    if len(sys.argv) > 1 and sys.argv[1] == "adc":
+        adc_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "perturb":
         perturb_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "trained":
         trained_case()
@@ -278,3 +297,4 @@ if __name__ == "__main__":
         main()
         trained_case()
         perturb_case()
+        adc_case()
