@@ -208,18 +208,29 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (`e2e`)
     e2e_steps = args.steps
-    host_loss = torch.zeros(1).pin_memory()
+    host_loss = torch.zeros(2).pin_memory()
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_losses = []
     sync()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     def e2e_loop(n):
-        # every step: H2D of its input (the acquired LR volume, pinned memory) and D2H of its result (the loss).  The
-        # copy of step i + 1's input is issued on a side stream while step i computes (double-buffered target).
+        # every step: H2D of its input (the acquired LR volume, pinned memory) and D2H of its result (the loss).  Both
+        # directions are pipelined one step deep: the copy of step i + 1's input travels on a side stream while step i
+        # computes (double-buffered target), and the host reads the loss of step i - 1 (pinned, event-synchronised)
+        # after it has launched step i, so the GPU is never idle while the host catches up.  Every step's loss reaches
+        # the host inside the timed region.
         sess.stage_target(lr_host)
         for i in range(n):
             sess.commit_target()               # this step's input is in place (the compute stream waits for its copy)
             if i + 1 < n:
                 sess.stage_target(lr_host)     # next step's input starts travelling
-            host_loss.copy_(sess.step(), non_blocking=False)
+            host_loss[i & 1:(i & 1) + 1].copy_(sess.step(), non_blocking=True)
+            loss_ready[i & 1].record()
+            if i >= 1:
+                loss_ready[(i - 1) & 1].synchronize()
+                e2e_losses.append(float(host_loss[(i - 1) & 1]))
+        loss_ready[(n - 1) & 1].synchronize()
+        e2e_losses.append(float(host_loss[(n - 1) & 1]))
 
     e2e_loop(max(3, args.warmup))              # warm-up of the side stream / back buffer (untimed)
     sync()
@@ -229,6 +240,8 @@ def run_ours(args):
     sync()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = global_rows * e2e_steps / (e2e_ms * 1e-3)
+    if not all(np.isfinite(v) for v in e2e_losses):
+        raise RuntimeError("bench: a loss read back in the end-to-end loop is not finite")
     sess.finish()
 
     # ---- HR voxel queries/s (second half of BASELINE.json's metric): cfg2 grid, output written to HBM
@@ -299,7 +312,8 @@ def run_ours(args):
                    "backward": "pipelined (one kernel, phase-only stash)" if piped else "staged (dgrad + wgrad)",
                    "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state",
                    "e2e": "per step: H2D of the LR volume from pinned host memory (double-buffered, issued on a side "
-                          "stream while the previous step computes) + D2H of the loss, through FitSession"},
+                          "stream while the previous step computes) + D2H of the loss (read by the host one step "
+                          "later, event-synchronised), through FitSession"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coord-samples/s", "h2d_bytes_per_step": int(lr_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
