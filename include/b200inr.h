@@ -183,6 +183,13 @@ int b200inr_input_mapping_backward(const float* x, const float* B, const float* 
 int b200inr_adc_fit(const float* signal, const float* bvalues_host, int64_t voxels, int32_t nb, float* adc,
                     void* stream);
 
+/* calculate_combinations (INR/SRDWI.py:143-152) for every voxel at once, the step right before the fit
+ * (INR/superresDWI.py:57-76): b0 [voxels], b1 [voxels, n1], b2 [voxels, n2], b3 [voxels, n3] (one b-value each, one
+ * echo time) -> out [voxels, 4, n1*n2*n3]: column c = (i1, i2, i3) in C order holds (b0, b1[i1], b2[i2], b3[i3]),
+ * i.e. np.asarray(list(itertools.product(...))).T per voxel.  All device pointers, fp32. */
+int b200inr_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int32_t n1,
+                         int32_t n2, int32_t n3, float* out, void* stream);
+
 /* ---- self test of the tensor-core plumbing ------------------------------------------------------------
  * One CTA computes D[128,N] = A * B^T with tcgen05.mma from swizzled shared memory.
  * mode 0: K-major operands, a[128,K], b[N,K] row-major bf16.  mode 1: MN-major operands, a[K,128], b[K,N].

@@ -1,6 +1,6 @@
 """Drop-in for the reference's INR/INRmodel.py (Siren :122-151: sine layers constructed before the final linear, no
 first_omega_0 argument, coordinates not detached by the module)."""
-from .inr import PN, ImageFitting_set, SineLayer, calculate_ADC, get_mgrid, input_mapping  # noqa: F401
+from .inr import PN, ImageFitting_set, SineLayer, calculate_ADC, calculate_combinations, get_mgrid, input_mapping  # noqa: F401
 from .inr import Siren as _Siren
 
 
@@ -10,4 +10,5 @@ class Siren(_Siren):
                          variant="INRmodel")
 
 
-__all__ = ["ImageFitting_set", "PN", "SineLayer", "Siren", "calculate_ADC", "get_mgrid", "input_mapping"]
+__all__ = ["ImageFitting_set", "PN", "SineLayer", "Siren", "calculate_ADC", "calculate_combinations", "get_mgrid",
+           "input_mapping"]

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b200inr_get_mgrid": (ctypes.c_int, [_P(Grid), _i64, _vp, _vp]),
     "b200inr_input_mapping": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "b200inr_combinations": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "b200inr_adc_fit": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "b200inr_input_mapping_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200inr_selftest_umma": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -44,6 +44,8 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
                 float* state, cudaStream_t stream);
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
+int launch_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int n1, int n2,
+                        int n3, float* out, cudaStream_t stream);
 int launch_adc(const float* signal, const float* bvalues_host, int64_t voxels, int nb, float* adc, cudaStream_t stream);
 int launch_ffm_bwd(const float* x, const float* B, const float* grad_out, int64_t rows, int d, int m, float* grad_x,
                    cudaStream_t stream);
@@ -441,6 +443,14 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
   if (rows < 0 || d < 1 || m < 1) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   return launch_ffm(x, B, rows, d, m, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int32_t n1,
+                         int32_t n2, int32_t n3, float* out, void* stream) {
+  if (!b0 || !b1 || !b2 || !b3 || !out) return B200INR_ERR_NULL;
+  if (voxels < 0 || n1 < 1 || n2 < 1 || n3 < 1 || int64_t(n1) * n2 * n3 > (1 << 20)) return B200INR_ERR_BAD_SHAPE;
+  if (voxels == 0) return B200INR_OK;
+  return launch_combinations(b0, b1, b2, b3, voxels, n1, n2, n3, out, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_adc_fit(const float* signal, const float* bvalues_host, int64_t voxels, int32_t nb, float* adc,

@@ -344,4 +344,38 @@ int launch_adc(const float* signal, const float* bvalues_host, int64_t voxels, i
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ calculate_combinations   INR/SRDWI.py:143-152
+// The reference builds, per voxel, itertools.product(b0, b1[:], b2[:], b3[:]) transposed -- a [4, n1*n2*n3] table whose
+// column c = (i1, i2, i3) in C order holds (b0, b1[i1], b2[i2], b3[i3]) -- one Python call per voxel through a
+// 32-process pool.  Here it is one gather over the whole volume: out[v, g, c], written once (HBM-write bound).
+__global__ void __launch_bounds__(kEwThreads) combinations_kernel(const float* __restrict__ b0, const float* __restrict__ b1,
+                                                                  const float* __restrict__ b2, const float* __restrict__ b3,
+                                                                  long long voxels, int n1, int n2, int n3,
+                                                                  float* __restrict__ out) {
+  const int nc = n1 * n2 * n3;
+  const long long total = voxels * 4 * nc;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = int(i % nc);
+    const long long vg = i / nc;
+    const int g = int(vg & 3);
+    const long long v = vg >> 2;
+    float val;
+    if (g == 0) val = b0[v];
+    else if (g == 1) val = b1[v * n1 + c / (n2 * n3)];
+    else if (g == 2) val = b2[v * n2 + (c / n3) % n2];
+    else val = b3[v * n3 + c % n3];
+    out[i] = val;
+  }
+}
+
+int launch_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int n1, int n2,
+                        int n3, float* out, cudaStream_t stream) {
+  long long blocks = (voxels * 4 * n1 * n2 * n3 + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 32) blocks = kSmCount * 32;
+  if (blocks < 1) blocks = 1;
+  combinations_kernel<<<int(blocks), kEwThreads, 0, stream>>>(b0, b1, b2, b3, voxels, n1, n2, n3, out);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 }  // namespace b200inr

@@ -140,6 +140,35 @@ def input_mapping(x, B):
         return _InputMappingFunction.apply(x.detach().contiguous().float(), B)
 
 
+def all_combinations(hybrid_raw_norm, te=0, device=None):
+    """Every voxel's calculate_combinations table in one kernel: what INR/superresDWI.py:57-76 assembles with a
+    32-process pool and a Python loop.  hybrid_raw_norm[b][te]: b = 0 a volume [X, Y, Z], b = 1..3 volumes
+    [X, Y, Z, n_b] (NumPy arrays or tensors).  Returns a CUDA fp32 tensor [X, Y, Z, 4, n1*n2*n3] (`acquisitions`)."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    vols = [torch.as_tensor(np.asarray(hybrid_raw_norm[b][te]) if not torch.is_tensor(hybrid_raw_norm[b][te])
+                            else hybrid_raw_norm[b][te]).to(dev, torch.float32).contiguous() for b in range(4)]
+    shape = tuple(vols[0].shape)
+    if any(tuple(v.shape[:-1]) != shape for v in vols[1:]):
+        raise RuntimeError("b200inr: all_combinations expects b0 [X, Y, Z] and b1..b3 [X, Y, Z, n]")
+    n1, n2, n3 = (int(v.shape[-1]) for v in vols[1:])
+    voxels = int(np.prod(shape))
+    out = torch.empty(shape + (4, n1 * n2 * n3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b200inr_combinations(_ptr(vols[0]), _ptr(vols[1]), _ptr(vols[2]), _ptr(vols[3]), voxels,
+                                                    n1, n2, n3, _ptr(out), _stream()), "combinations")
+    return out
+
+
+def calculate_combinations(voxel, hybrid_raw_norm):
+    """Reference INR/SRDWI.py:143-152, same signature and result (one voxel, echo time 0): a [4, n1*n2*n3] float64
+    array.  One voxel is a 4 x N gather -- done on the host; the whole-volume form is all_combinations()."""
+    i, j, k = voxel
+    b0 = np.asarray(hybrid_raw_norm[0][0])[i, j, k]
+    b1, b2, b3 = (np.asarray(hybrid_raw_norm[b][0])[i, j, k, :] for b in (1, 2, 3))
+    g1, g2, g3 = np.meshgrid(b1, b2, b3, indexing="ij")
+    return np.stack([np.full(g1.size, b0), g1.ravel(), g2.ravel(), g3.ravel()]).astype(np.float64)
+
+
 def calculate_ADC(bvalues, slicedata):
     """Reference INR/SRDWI.py:118-130 (= INR/INRmodel.py): per-voxel mono-exponential fit, ADC = -slope of the
     least-squares line through (b / 1000, log(signal + 1e-7)), clamped to [-10, 3] -- one kernel instead of a Python

@@ -894,3 +894,20 @@ def test_calculate_adc_vs_reference_golden_and_oracle(dev, golden_dir):
     np.testing.assert_allclose(dev_out.cpu().numpy(), O.calculate_adc(bv, vol), atol=3e-5, rtol=3e-5)
     with pytest.raises(RuntimeError):
         b200inr.calculate_ADC(np.array([5.0, 5.0]), torch.ones(4, 2, device=dev))  # equal b-values: no slope
+
+
+def test_all_combinations_vs_reference_golden(dev, golden_dir):
+    """The whole-volume gather kernel: bit-exact against the reference's per-voxel calculate_combinations tables
+    (fp32 copies of the same values), and against the host mirror on a larger random acquisition."""
+    g = np.load(os.path.join(golden_dir, "combinations.npz"))
+    hybrid = [[g[f"b{b}"]] for b in range(4)]
+    out = b200inr.all_combinations(hybrid, device=dev)
+    assert out.shape == g["table"].shape and out.dtype == torch.float32
+    np.testing.assert_array_equal(out.cpu().numpy(), g["table"].astype(np.float32))
+    rs = np.random.RandomState(2)
+    shape = (16, 9, 5)
+    big = [[rs.uniform(size=shape).astype(np.float32)]] + [[rs.uniform(size=shape + (n,)).astype(np.float32)]
+                                                            for n in (4, 1, 7)]
+    out = b200inr.all_combinations(big, device=dev).cpu().numpy()
+    for (i, j, k) in ((0, 0, 0), (15, 8, 4), (7, 3, 2)):
+        np.testing.assert_array_equal(out[i, j, k], b200inr.calculate_combinations((i, j, k), big).astype(np.float32))

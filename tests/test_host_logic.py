@@ -223,3 +223,15 @@ def test_two_rank_gradient_sum_matches_full_batch():
         assert p.exitcode == 0
     for _, err, scale in res:
         assert err <= 1e-5 * max(scale, 1.0)
+
+
+def test_calculate_combinations_matches_reference_golden(golden_dir):
+    """Per-voxel mirror of INR/SRDWI.py:143-152 (host side, NumPy) against the unmodified reference's tables
+    (tools/make_golden.py: combinations_case)."""
+    g = np.load(os.path.join(golden_dir, "combinations.npz"))
+    hybrid = [[g[f"b{b}"]] for b in range(4)]
+    X, Y, Z = g["b0"].shape
+    for (i, j, k) in ((0, 0, 0), (2, 3, 1), (1, 2, 0)):
+        ours = b200inr.calculate_combinations((i, j, k), hybrid)
+        assert ours.shape == (4, 12) and ours.dtype == np.float64
+        np.testing.assert_array_equal(ours, g["table"][i, j, k])

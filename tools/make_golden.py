@@ -286,8 +286,29 @@ def adc_case():
     print("adc_slice", ref.min(), ref.max(), ref[0, :3])
 
 
+def combinations_case():
+    """calculate_combinations of the unmodified reference (INR/SRDWI.py:143-152) for every voxel of a small
+    synthetic hybrid acquisition (b0: 1 image, b1..b3: 2 / 3 / 2 repeats, 4 echo times of which only te = 0 is used)."""
+    rs = np.random.RandomState(11)
+    shape = (3, 4, 2)
+    reps = (None, 2, 3, 2)
+    hybrid = [[rs.uniform(size=shape if reps[b] is None else shape + (reps[b],)) for _te in range(4)] for b in range(4)]
+    table = np.zeros(shape + (4, 12))
+    for i in range(shape[0]):
+        for j in range(shape[1]):
+            for k in range(shape[2]):
+                table[i, j, k] = SRDWI.calculate_combinations((i, j, k), hybrid)
+    d = {"table": table}
+    for b in range(4):
+        d[f"b{b}"] = hybrid[b][0]
+    np.savez_compressed(os.path.join(OUT, "combinations.npz"), **d)
+    print("combinations", table.shape, table[0, 0, 0, :, :3])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "adc":
+    if len(sys.argv) > 1 and sys.argv[1] == "combinations":
+        combinations_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "adc":
         adc_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "perturb":
         perturb_case()
@@ -298,3 +319,4 @@ if __name__ == "__main__":
         trained_case()
         perturb_case()
         adc_case()
+        combinations_case()
