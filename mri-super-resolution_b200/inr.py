@@ -16,6 +16,7 @@ bypass autograd entirely:
                       materialising the coordinate grid
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -39,9 +40,16 @@ def _require_cuda(t, what):
         raise RuntimeError(f"b200inr: {what} must be a CUDA tensor (the B200 kernels are the only implementation)")
 
 
-def _aligned_bytes(nbytes, device, align=1024):
-    """Zero-initialised byte buffer whose data pointer is `align`-aligned."""
-    raw = torch.zeros(int(nbytes) + align, dtype=torch.uint8, device=device)
+def _aligned_bytes(nbytes, device, align=1024, zero=True):
+    """Byte buffer whose data pointer is `align`-aligned.  zero=False skips the fill: the activation stash is written
+    tile by tile before anything reads it (a 13 GB memset per forward otherwise costs 2 ms at cfg4-like sizes).
+    B200INR_POISON_STASH=1 fills such buffers with 0xFF (bf16 NaN) instead -- the tests' proof of that claim."""
+    if zero:
+        raw = torch.zeros(int(nbytes) + align, dtype=torch.uint8, device=device)
+    else:
+        raw = torch.empty(int(nbytes) + align, dtype=torch.uint8, device=device)
+        if os.environ.get("B200INR_POISON_STASH", "0") == "1":
+            raw.fill_(255)
     off = (-raw.data_ptr()) % align
     return raw[off:off + int(nbytes)]
 
@@ -213,8 +221,10 @@ class PN(nn.Module):
 
     def forward(self, coords, sample=0, eps=0):
         x = coords.detach()  # the reference detaches its input (INR/INRmodel.py:161)
-        acq = x.new_full((x.shape[0], 1), sample / 10.)
-        hidden = self.tanh(self.perturb_linear(torch.cat((x, acq), -1)))
+        # Linear(cat(x, acq)) with a constant acq column = x W[:, :-1]^T + (b + acq W[:, -1]): the [N, in + 1] copy of
+        # the features (1 GB per step at the script's sizes) is never made
+        w = self.perturb_linear.weight
+        hidden = self.tanh(nn.functional.linear(x, w[:, :-1], self.perturb_linear.bias + (sample / 10.) * w[:, -1]))
         return eps * self.tanh(self.perturb_linear2(hidden))
 
 
@@ -347,7 +357,7 @@ class _FusedMLP(nn.Module):
             out = torch.empty((rows, self.out_features), dtype=torch.float32, device=dev)
         if rows == 0:  # empty input: nothing to launch (an empty tensor has no device pointer)
             return out, (torch.empty(0, dtype=torch.uint8, device=dev) if train else None)
-        stash = _aligned_bytes(_lib.stash_bytes(self._desc, rows), dev) if train else None
+        stash = _aligned_bytes(_lib.stash_bytes(self._desc, rows), dev, zero=False) if train else None
         with torch.cuda.device(dev):
             _lib.check(_lib.load().b200inr_siren_forward(
                 ctypes.byref(self._desc), _ptr(eng["packed"]), _ptr(coords), ctypes.byref(grid) if grid else None,
