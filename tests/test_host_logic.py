@@ -235,3 +235,28 @@ def test_calculate_combinations_matches_reference_golden(golden_dir):
         ours = b200inr.calculate_combinations((i, j, k), hybrid)
         assert ours.shape == (4, 12) and ours.dtype == np.float64
         np.testing.assert_array_equal(ours, g["table"][i, j, k])
+
+
+def test_error_codes_of_the_widened_entry_points():
+    """Argument validation of the section-8f entry points returns before anything is launched (no GPU needed)."""
+    lib = L.load()
+    feat = L.make_net(256, 512, 3, 1, input_mode=L.IN_FEATURES)
+    raw = L.make_net(3, 256, 4, 31)
+    one = ctypes.c_void_p(1024)
+    # input gradient: explicit-feature networks only, every pointer required
+    assert lib.b200inr_siren_backward_input(ctypes.byref(raw), one, one, 128, one, one, one, None) == -1
+    assert lib.b200inr_siren_backward_input(ctypes.byref(feat), one, one, 128, one, one, None, None) == -5
+    assert lib.b200inr_siren_backward_input(ctypes.byref(feat), one, one, 0, one, one, one, None) == 0
+    assert lib.b200inr_siren_backward_input(ctypes.byref(feat), one, one, -1, one, one, one, None) == -1
+    # feature-map adjoint: d <= 8
+    assert lib.b200inr_input_mapping_backward(one, one, one, 10, 9, 4, one, None) == -1
+    assert lib.b200inr_input_mapping_backward(one, one, None, 10, 3, 4, one, None) == -5
+    assert lib.b200inr_input_mapping_backward(one, one, one, 0, 3, 4, one, None) == 0
+    # ADC fit: 2..64 b-values
+    assert lib.b200inr_adc_fit(one, one, 0, 1, one, None) == -1
+    assert lib.b200inr_adc_fit(one, one, 0, 4, one, None) == 0
+    assert lib.b200inr_adc_fit(None, one, 10, 4, one, None) == -5
+    # combinations
+    assert lib.b200inr_combinations(one, one, one, one, 0, 2, 3, 2, one, None) == 0
+    assert lib.b200inr_combinations(one, one, one, one, 5, 0, 3, 2, one, None) == -1
+    assert lib.b200inr_combinations(one, None, one, one, 5, 2, 3, 2, one, None) == -5
