@@ -14,12 +14,14 @@
 // the 64-row tiles.  Every CTA is WEIGHT-STATIONARY for its whole life, with its weights IN TENSOR MEMORY:
 //   stage CTA (l, h), l = L..1, h = 0/1 (feature half):                                   [the 256x256 layers]
 //       TMEM: rows [128h, 128h+128) of W'_l^T (A operand, 128 columns), the block dW_l[:, 128h..]^T (256 columns),
-//             two chain accumulators (2 x 64 columns) = all 512 columns;
+//             one chain accumulator (64 columns) and the sin outputs y^T of the two epilogue groups (2 x 32
+//             columns, A operand of the weight-gradient MMA) = all 512 columns  [kPYTmem; without it: two
+//             accumulators and y^T in shared memory];
 //       per tile:  receive dTheta_l (64 rows x 256, bf16, 32 KB)                          <- ring l
 //                  D^T[in-half, rows]   = W'_l^T[in-half, :] dTheta_l^T                   (tcgen05 128 x 64 x 256, A in TMEM)
 //                  s, c = sin, cos(phase_l-1) for its 128 features x 64 rows              (phases: bulk copy from HBM)
 //                  dTheta_l-1[:, half]  = D .* c  -> bf16                                  -> ring l-1
-//                  y^T = s -> bf16 -> shared memory, feature-major
+//                  y^T = s -> bf16 -> tensor memory (tcgen05.st: thread = feature = lane)
 //                  dW_l[:, half]^T     += y^T dTheta_l                                     (tcgen05 128 x 256 x 64)
 //                  db_l-1[half]        += colsum(dTheta_l-1)                               (registers: lane = feature)
 //   edge CTA E(h):                                                                        [both ends of the chain]
@@ -40,9 +42,14 @@
 // counter (all bounded spins: a mis-programmed pipeline traps instead of hanging).  All 2(L+1)P CTAs must be
 // co-resident: the grid never exceeds the SM count (1 CTA/SM).
 //
-// Warp roles (736 threads): 0 = ring loader (edge: phase loader), 1 = chain MMA issuer + TMEM owner, 2 = ring store,
-// 3 = phase loader (edge: the whole bottom half), 4..19 = epilogue (TMEM lane quadrant = warp & 3),
+// Warp roles (736 threads): 0 = ring loader (edge: phase + raw dOut loader), 1 = chain MMA issuer + TMEM owner,
+// 2 = ring store, 3 = phase loader (edge: the whole bottom half), 4..19 = epilogue (TMEM lane quadrant = warp & 3),
 // 20..21 = edge: dOut fp32 -> bf16 converters (idle in stage CTAs), 22 = weight-gradient MMA issuer.
+//
+// Tuning builds (tools/build_variant.sh <name> mlp_bwdp.cu -D...; tools/run_variants.sh times them on the box):
+// B200INR_PTRACE=1 compiles the event trace into the lean kernel, B200INR_PKO=<mask> knocks one resource out at a
+// time, B200INR_PMC=1 multicasts ring tiles across a stage's CTA pair, B200INR_PYT / PDZ / PPH / PEPH / PSTG / PRAW /
+// PSD / PCVT / PPF choose buffer placement and depths.  The defaults are the measured best.
 #include <stdio.h>
 #include <stdlib.h>
 
