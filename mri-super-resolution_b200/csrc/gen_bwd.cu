@@ -70,12 +70,14 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + S::kSlots;
-  uint64_t* a_ready = bars + 2 * S::kSlots;
-  uint64_t* dzo_ready = bars + 2 * S::kSlots + 1;
-  uint64_t* d_full = bars + 2 * S::kSlots + 2;
-  uint64_t* a_free = bars + 2 * S::kSlots + 3;
-  uint64_t* dzo_free = bars + 2 * S::kSlots + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 5);
+  // the dTheta tile (A operand of the next chain step) is handed over in two halves of K blocks, as in gen_fwd.cu: at
+  // H = 512 the next step's MMAs into D[0:256) start while the epilogue still works on D[256:512)
+  uint64_t* a_half = bars + 2 * S::kSlots;  // [2]
+  uint64_t* dzo_ready = bars + 2 * S::kSlots + 2;
+  uint64_t* d_full = bars + 2 * S::kSlots + 3;
+  uint64_t* a_free = bars + 2 * S::kSlots + 4;
+  uint64_t* dzo_free = bars + 2 * S::kSlots + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(a_ready, kGenBwdEpiWarps);
+    mbar_init(&a_half[0], kGenBwdEpiWarps);
+    mbar_init(&a_half[1], kGenBwdEpiWarps);
     mbar_init(dzo_ready, kGenBwdEpiWarps);
     mbar_init(d_full, 1);
     mbar_init(a_free, 1);
@@ -137,15 +140,20 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);  // a_ready completes L + 1 times per tile
         for (int u = 0; u <= L + dx; ++u) {
+          bool second = (u == 0);  // second half of the dTheta tile awaited (step 0 reads the dOut block instead)
           if (u == 0)
             mbar_wait(dzo_ready, t & 1);
           else
-            mbar_wait(a_ready, (inst0 + u - 1) & 1);
+            mbar_wait(&a_half[0], (inst0 + u - 1) & 1);
           tc_fence_after();
           const int kbn = (u == 0) ? 1 : S::kKB;
           const int nhn = (u <= L) ? NH : NX;
           for (int nh = 0; nh < nhn; ++nh) {
             for (int kb = 0; kb < kbn; ++kb, ++c) {
+              if (!second && (nh > 0 || kb >= S::kKB / 2)) {
+                mbar_wait(&a_half[1], (inst0 + u - 1) & 1);
+                second = true;
+              }
               const uint32_t slot = c % S::kSlots;
               mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
               tc_fence_after();
@@ -158,7 +166,14 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
               umma_commit_w(&w_empty[slot]);
             }
           }
+          if (!second) mbar_wait(&a_half[1], (inst0 + u - 1) & 1);
           umma_commit_w(d_full);
+        }
+        // without the input-gradient step nobody reads the last tile (dTheta_0) through these barriers' final phase;
+        // consume it so that the next tile's waits stay one phase behind at most
+        if (!dx) {
+          mbar_wait(&a_half[0], (inst0 + L) & 1);
+          mbar_wait(&a_half[1], (inst0 + L) & 1);
         }
       }
     }
@@ -174,7 +189,8 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
         bulk_wait_read0();
         mbar_arrive(dzo_free);
         for (int l = L; l >= 0; --l, ++n) {
-          mbar_wait(a_ready, n & 1);
+          mbar_wait(&a_half[0], n & 1);
+          mbar_wait(&a_half[1], n & 1);
           bulk_s2g(p.stash_dz + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
           bulk_commit();
           bulk_wait_read0();
@@ -277,11 +293,20 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
             }
             sts128(a_addr + kb * S::kABlock + sw128_chunk_off(r, 2 * s + c), make_uint4(o[0], o[1], o[2], o[3]));
           }
+          if (NH == 2 && kb == S::kKB / 2 - 1) {  // blocks 0..kKB/2-1 written, D[0:256) read out
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_half[0]);
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
+        if (lane == 0) {
+          if (NH != 2) mbar_arrive(&a_half[0]);
+          mbar_arrive(&a_half[1]);
+        }
       }
 
       // ---- input gradient: D = dTheta_0 (omega_0 W_0), fp32, straight to global memory (row r, 16 columns per block)

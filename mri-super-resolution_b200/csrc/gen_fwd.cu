@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* w_full = bars;                    // [kSlots]
   uint64_t* w_empty = bars + S::kSlots;       // [kSlots]
-  uint64_t* a_ready = bars + 2 * S::kSlots;   // A operand of the next layer complete in shared memory
-  uint64_t* d_full = bars + 2 * S::kSlots + 1;
-  uint64_t* a_free = bars + 2 * S::kSlots + 2;  // stash store of the A tile has been read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 3);
+  // A operand of the next layer in shared memory, in two halves of K blocks: with two N halves (H = 512) the next
+  // layer's MMAs into D[0:256) over blocks 0..kKB/2-1 start while the epilogue still works on D[256:512)
+  uint64_t* a_half = bars + 2 * S::kSlots;    // [2]
+  uint64_t* d_full = bars + 2 * S::kSlots + 2;
+  uint64_t* a_free = bars + 2 * S::kSlots + 3;  // stash store of the A tile has been read out (training)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(a_ready, kGenEpiWarps);
+    mbar_init(&a_half[0], kGenEpiWarps);
+    mbar_init(&a_half[1], kGenEpiWarps);
     mbar_init(d_full, 1);
     mbar_init(a_free, 1);
     fence_mbar_init();
@@ -130,13 +133,18 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
       uint32_t c = 0, n = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l <= L + 1; ++l, ++n) {
-          mbar_wait(a_ready, n & 1);
+          mbar_wait(&a_half[0], n & 1);
           tc_fence_after();
+          bool second = false;  // second half of the A tile (and D[256:512) read out) awaited
           const bool act_layer = (l <= L);
           const int kbn = act_layer ? (l == 0 ? KB0 : S::kKB) : S::kKB;
           const int nhn = act_layer ? NH : 1;
           for (int nh = 0; nh < nhn; ++nh) {
             for (int kb = 0; kb < kbn; ++kb, ++c) {
+              if (!second && (nh > 0 || kb >= S::kKB / 2)) {
+                mbar_wait(&a_half[1], n & 1);
+                second = true;
+              }
               const uint32_t slot = c % S::kSlots;
               mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
               tc_fence_after();
@@ -149,6 +157,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
               umma_commit_w(&w_empty[slot]);
             }
           }
+          if (!second) mbar_wait(&a_half[1], n & 1);  // (every phase of a barrier is consumed by its waiter)
           umma_commit_w(d_full);
         }
       }
@@ -160,7 +169,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = int(blockIdx.x) + t * int(gridDim.x);
         for (int l = -1; l <= L; ++l, ++n) {  // l = -1: the network input tile
-          mbar_wait(a_ready, n & 1);
+          mbar_wait(&a_half[0], n & 1);
+          mbar_wait(&a_half[1], n & 1);
           if (l < 0)
             bulk_s2g(p.stash_ain + size_t(tile) * (size_t(KB0) * S::kABlock), a_smem, uint32_t(KB0) * S::kABlock);
           else
@@ -234,7 +244,10 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
+        if (lane == 0) {
+          mbar_arrive(&a_half[0]);
+          mbar_arrive(&a_half[1]);
+        }
       }
 
       // ---- activated layers
@@ -291,11 +304,20 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
               *reinterpret_cast<uint4*>(ph_l + size_t(kb * 8 + 2 * s + c) * (kTileRows * 16)) =
                   make_uint4(ph[0], ph[1], ph[2], ph[3]);
           }
+          if (NH == 2 && kb == S::kKB / 2 - 1) {  // blocks 0..kKB/2-1 written, D[0:256) read out
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_half[0]);
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
+        if (lane == 0) {
+          if (NH != 2) mbar_arrive(&a_half[0]);
+          mbar_arrive(&a_half[1]);
+        }
       }
 
       // ---- final linear: D[:, 0:32) + bias -> out
