@@ -808,7 +808,12 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
     return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
   }
   const int smem = FwdSmem<H>::kBytes + 1024;
-  const int grid_x = pairs < num_sms ? pairs : num_sms;
+  int grid_x = pairs < num_sms ? pairs : num_sms;
+  {  // tuning aid: cap the number of CTAs (per-CTA rate vs the number of SMs pulling weights through L2)
+    const char* env_cap = getenv("B200INR_FWD_MAX_CTAS");
+    const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
+    if (cap > 0 && cap < grid_x) grid_x = cap;
+  }
   if (stash && staged) {
     e = cudaFuncSetAttribute(siren_fwd_kernel<H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return B200INR_ERR_CUDA;
