@@ -16,6 +16,7 @@
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -408,7 +409,12 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
     p.stash_ph = st + sl.ph;
     p.layer_stride = sl.layer_stride;
   }
-  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  {  // tuning aid (same switch as mlp_fwd.cu): cap the number of CTAs
+    const char* env_cap = getenv("B200INR_FWD_MAX_CTAS");
+    const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
+    if (cap > 0 && cap < grid_x) grid_x = cap;
+  }
   const bool sine = net->activation == B200INR_ACT_SINE;
   if (p.g.H == 256)
     return sine ? launch_gen_fwd_t<256, B200INR_ACT_SINE>(p, stash != nullptr, grid_x, stream)
