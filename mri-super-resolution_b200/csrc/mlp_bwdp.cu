@@ -78,6 +78,17 @@ constexpr int kPWgradWarp = kPFirstCvtWarp + kPCvtWarps;      // 22
 // tile period is made of.  1 = no sin / cos, 2 = one chain MMA instead of 16, 4 = one weight-gradient MMA instead of 4,
 // 8 = no phase loads, 16 = ring loads of half a tile.
 constexpr int kPKo = B200INR_PKO;
+#ifndef B200INR_PGPH
+#define B200INR_PGPH 1
+#endif
+#ifndef B200INR_PW16
+#define B200INR_PW16 1  // all 16 chain MMAs of a tile behind one election (0: four batches of four)
+#endif
+// kPGroupPh: each epilogue group owns two of four phase slots (and their barriers), so a warp no longer has to pass --
+// wait + arrive, ~100 cycles each on the busy shared-memory pipe -- the barriers of the OTHER group's tiles.  Needs four
+// phase slots in both CTA kinds, which only fit without the 1 KB alignment reserve of the dynamic shared memory (its
+// base is 1024-aligned on this architecture; the kernel traps if it is not).
+constexpr bool kPGroupPh = B200INR_PGPH != 0;
 #ifndef B200INR_PTRACE
 #define B200INR_PTRACE 0
 #endif
@@ -102,7 +113,7 @@ constexpr bool kPMc = B200INR_PMC != 0;
 #define B200INR_PDZ (B200INR_PYT ? 4 : 3)
 #endif
 #ifndef B200INR_PPH
-#define B200INR_PPH 3
+#define B200INR_PPH (B200INR_PGPH ? 4 : 3)
 #endif
 // kPYTmem: the sin outputs (A operand of the weight-gradient MMA) are written to TENSOR memory instead of shared memory
 // (thread = feature = TMEM lane, its 32 rows = 16 packed columns): 32 KB less shared-memory traffic per tile and 32 KB
@@ -112,7 +123,7 @@ constexpr bool kPYTmem = B200INR_PYT != 0;
 constexpr int kPDzSlots = B200INR_PDZ;          // incoming dTheta tiles
 constexpr int kPPhSlots = B200INR_PPH;          // phase tiles (stage CTAs)
 #ifndef B200INR_PEPH
-#define B200INR_PEPH 3
+#define B200INR_PEPH (B200INR_PGPH ? 4 : 3)
 #endif
 constexpr int kPPhBars = B200INR_PPH > B200INR_PEPH ? B200INR_PPH : B200INR_PEPH;  // phase slots of the edge CTAs: B200INR_PEPH
 #ifndef B200INR_PSTG
@@ -121,7 +132,7 @@ constexpr int kPPhBars = B200INR_PPH > B200INR_PEPH ? B200INR_PPH : B200INR_PEPH
 constexpr int kPStgSlots = B200INR_PSTG;        // outgoing dTheta halves (even: a slot always belongs to one epilogue group)
 constexpr int kPDobSlots = 4;                   // edge: bf16 dOut blocks
 #ifndef B200INR_PRAW
-#define B200INR_PRAW (B200INR_PYT ? 6 : 2)
+#define B200INR_PRAW (B200INR_PGPH ? 4 : (B200INR_PYT ? 6 : 2))
 #endif
 constexpr int kPRawSlots = B200INR_PRAW;        // edge: raw fp32 dOut tiles, bulk-copied ahead of the conversion (the
                                                 // copies come from HBM: two slots leave the converters latency-bound)
@@ -158,7 +169,8 @@ struct PSmem {  // stage CTA
   static constexpr int kEnd = kPh + kPPhSlots * kPPhSlot;
   static constexpr int kBar = kEnd > PSmemE::kEnd ? kEnd : PSmemE::kEnd;  // barrier area, shared by both CTA kinds
   static constexpr int kBytes = kBar + 512;
-  static_assert(kBytes + 1024 <= 232448, "shared memory budget");
+  static constexpr int kSlack = kPGroupPh ? 0 : 1024;  // manual 1024-byte alignment reserve
+  static_assert(kBytes + kSlack <= 232448, "shared memory budget");
 };
 
 // barrier indices
@@ -326,6 +338,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
   using S = PSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (PSmem::kSlack == 0 && smem != smem_raw) __trap();  // no reserve: the base must already be aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBCount);
   uint32_t* one_s = reinterpret_cast<uint32_t*>(smem + S::kBar + 448);  // 16-byte aligned constant {1, 0, 0, 0}
@@ -365,7 +378,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
     }
     for (int i = 0; i < kPPhBars; ++i) {
       mbar_init(&bars[kBPhFull + i], 1);
-      mbar_init(&bars[kBPhEmpty + i], kPEpiWarps);
+      mbar_init(&bars[kBPhEmpty + i], kPGroupPh ? kPEpiWarps / 2 : kPEpiWarps);
     }
     for (int i = 0; i < kPDobSlots; ++i) {
       mbar_init(&bars[kBDobFull + i], kPCvtPair);
@@ -478,7 +491,9 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
               mbar_arrive(&bars[kBRawFull + rs]);  // ragged last tile: the converters read it from global memory
             }
           }
-          const int slot = i % nph, round = i / nph;
+          // shared slots: tile i -> slot i mod nph; per-group slots: group i & 1 owns slots {2g, 2g + 1}
+          const int slot = kPGroupPh ? ((i & 1) * 2 + ((i >> 1) & 1)) : i % nph;
+          const int round = kPGroupPh ? (i >> 2) : i / nph;
           if (round > 0) PW(0, mbar_wait(&bars[kBPhEmpty + slot], (round - 1) & 1));
           TR(18, i);
           const int T = pipe + (i >> 1) * p.pipelines;
@@ -521,10 +536,15 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
             if (lane == 0) TR(3, i);
             tc_fence_after();
             const uint32_t dz = sbase + S::kDz + ds * kPTile;
+#if B200INR_PW16
+            // all 16 MMAs of the step (4 K blocks of kPBlk bytes x 4 K steps of 2048 bytes) behind one election
+            umma_bf16_ts_w16<2048 / 16, kPBlk / 16>(t_acc + (kPYTmem ? 0 : (i & 1) * 64), t_wt, smem_desc(dz, hiMN), idesc_d);
+#else
 #pragma unroll 1  // (compact loops: this warp shares an instruction cache with four epilogue warps)
             for (int kb = 0; kb < ((kPKo & 2) ? 1 : 4); ++kb)  // four K steps (2048 bytes apart) per batched issue
               umma_bf16_ts_w4<2048 / 16>(t_acc + (kPYTmem ? 0 : (i & 1) * 64), t_wt + kb * 32,
                                          smem_desc(dz + kb * kPBlk, hiMN), idesc_d, kb != 0);
+#endif
             umma_commit_w(&bars[kBAccFull + (i & 1)]);
             if (lane == 0) TR(4, i);
           }
@@ -817,9 +837,10 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 
       if (grp == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);  // start the two groups half a cycle apart
       for (int i = 0; i < n; ++i) {
-        const int ps = i % nph;
-        // every warp passes every phase of the phase-slot barriers (a parity wait may not skip a phase)
-        PW(1, mbar_wait(&bars[kBPhFull + ps], (i / nph) & 1));
+        if (kPGroupPh && (i & 1) != grp) continue;  // per-group phase slots: the other group's tiles are not our business
+        const int ps = kPGroupPh ? ((i & 1) * 2 + ((i >> 1) & 1)) : i % nph;
+        // shared slots: every warp passes every phase of the phase-slot barriers (a parity wait may not skip a phase)
+        PW(1, mbar_wait(&bars[kBPhFull + ps], (kPGroupPh ? (i >> 2) : (i / nph)) & 1));
         if ((i & 1) != grp) {  // the other group's tile: just let the slot go (it is refilled once ALL warps passed)
           if ((ew & 7) == 0 && lane == 0) TR(15, i);
           __syncwarp();
@@ -1006,7 +1027,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
   const int S2 = 2 * (L + 1);
-  const int smem = PSmem::kBytes + 1024;
+  const int smem = PSmem::kBytes + PSmem::kSlack;
   int P = num_sms / S2;
   if (kPMc) {
     // every CTA of the grid must be resident at once, and with clusters that is the number of CTA PAIRS the GPCs can

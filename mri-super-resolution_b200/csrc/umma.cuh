@@ -294,6 +294,48 @@ __device__ __forceinline__ void umma_bf16_ts_w4(uint32_t d_tmem, uint32_t a_tmem
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "n"(kDescStep), "n"(2 * kDescStep), "n"(3 * kDescStep)
       : "memory");
 }
+// Sixteen TS-mode MMAs (four K blocks of four K steps) from ONE elected lane: A at a_tmem + 8 j columns, B descriptor +
+// (kb * kBlkStep + ks * kStep) 16-byte units, j = 4 kb + ks.  The first one overwrites the accumulator.
+template <int kStep, int kBlkStep>
+__device__ __forceinline__ void umma_bf16_ts_w16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b32 a;\n\t.reg .b64 d;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 0;\n\t"
+      "add.u32 a, %1, 8;\n\tadd.u64 d, %2, %4;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 16;\n\tadd.u64 d, %2, %5;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 24;\n\tadd.u64 d, %2, %6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 32;\n\tadd.u64 d, %2, %7;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 40;\n\tadd.u64 d, %2, %8;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 48;\n\tadd.u64 d, %2, %9;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 56;\n\tadd.u64 d, %2, %10;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 64;\n\tadd.u64 d, %2, %11;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 72;\n\tadd.u64 d, %2, %12;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 80;\n\tadd.u64 d, %2, %13;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 88;\n\tadd.u64 d, %2, %14;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 96;\n\tadd.u64 d, %2, %15;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 104;\n\tadd.u64 d, %2, %16;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 112;\n\tadd.u64 d, %2, %17;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "add.u32 a, %1, 120;\n\tadd.u64 d, %2, %18;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], d, %3, 1;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(0 * kBlkStep + 1 * kStep), "n"(0 * kBlkStep + 2 * kStep), "n"(0 * kBlkStep + 3 * kStep), "n"(1 * kBlkStep + 0 * kStep), "n"(1 * kBlkStep + 1 * kStep), "n"(1 * kBlkStep + 2 * kStep), "n"(1 * kBlkStep + 3 * kStep), "n"(2 * kBlkStep + 0 * kStep), "n"(2 * kBlkStep + 1 * kStep), "n"(2 * kBlkStep + 2 * kStep), "n"(2 * kBlkStep + 3 * kStep), "n"(3 * kBlkStep + 0 * kStep), "n"(3 * kBlkStep + 1 * kStep), "n"(3 * kBlkStep + 2 * kStep), "n"(3 * kBlkStep + 3 * kStep)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
