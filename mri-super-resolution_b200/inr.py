@@ -425,7 +425,7 @@ class _FusedMLP(nn.Module):
 
     # ---------------------------------------------------------------- fused fit
     def fit(self, target, shape, steps, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
-            global_count=None, process_group=None, reset_optimizer=False, graph=None):
+            global_count=None, process_group=None, reset_optimizer=False, graph=None, weight=None):
         """The reference training loop (INR/superresDWI.py:132-138) on a dense coordinate grid, without autograd:
         per step  fused forward -> loss (+ LR degradation) -> fused backward -> [all-reduce] -> Adam -> re-stage bf16.
 
@@ -434,10 +434,12 @@ class _FusedMLP(nn.Module):
         shape    the (HR) coordinate grid; rows = prod(shape) unless row_range=(begin, end) selects this rank's slab.
         process_group / global_count: multi-GPU data parallel -- gradients are summed with one all-reduce per step and
                  the loss is normalised by the global element count.
+        weight   optional [rows, C] loss weights: (w * (out - gt)**2).mean() of INR/INR_ERD.py:265 (degrade=None only).
         Returns the per-step loss as a CUDA tensor [steps] (this rank's share of the global mean).
         """
         session = FitSession(self, target, shape, lr=lr, degrade=degrade, betas=betas, eps=eps, row_range=row_range,
-                             global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer)
+                             global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer,
+                             weight=weight)
         losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
         if graph is None:  # small per-step work is launch-latency bound: replay the step as one CUDA graph
             graph = process_group is None and steps >= 16 and session.rows <= (1 << 18)
@@ -628,7 +630,7 @@ class FitSession:
     STAGES = ("zero", "forward", "loss", "dgrad", "wgrad", "allreduce", "adam", "pack")
 
     def __init__(self, module, target, shape, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
-                 global_count=None, process_group=None, reset_optimizer=False):
+                 global_count=None, process_group=None, reset_optimizer=False, weight=None):
         _require_cuda(target, "fit target")
         self.module = module
         eng = self.eng = module._sync_params()
@@ -679,6 +681,15 @@ class FitSession:
         else:
             raise ValueError("degrade must be None, 'pool' or 'blur_pool'")
         self.target = target
+        # per-element loss weights: (w * (out - gt)**2).mean() of INR/INR_ERD.py:265 (point-wise loss only)
+        self.weight = None
+        if weight is not None:
+            if degrade is not None:
+                raise RuntimeError("b200inr: loss weights go with the point-wise loss (degrade=None)")
+            _require_cuda(weight, "fit weight")
+            self.weight = weight.detach().contiguous().float().reshape(-1)
+            if self.weight.numel() != rows * C:
+                raise RuntimeError("b200inr: fit weight must have rows*C elements")
         if module._optim is None or reset_optimizer or module._optim["m"].device != dev:
             module._optim = {"m": torch.zeros_like(eng["flat"]), "v": torch.zeros_like(eng["flat"]),
                              "state": torch.zeros(4, dtype=torch.float32, device=dev)}
@@ -767,8 +778,8 @@ class FitSession:
                                                  _ptr(self.stash), s), "siren_forward")
             mark()
             if self.degrade is None:
-                _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), None, rows * C, self.count,
-                                                _ptr(self.dpred), _ptr(self.loss), s), "mse_loss")
+                _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C,
+                                                self.count, _ptr(self.dpred), _ptr(self.loss), s), "mse_loss")
             elif self.degrade == "pool":
                 _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
                                                 self.count, _ptr(self.dpred), _ptr(self.loss), s), "pool_mse")

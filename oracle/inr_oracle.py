@@ -346,7 +346,7 @@ def torch_input_mapping(x, B):
     return torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
 
 
-def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None):
+def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None, weight=None):
     """The reference's in-lined loop (INR/superresDWI.py:132-138): full batch, fixed order, Adam defaults.
 
     degrade None        : loss = ((out - target)**2).mean()
@@ -372,7 +372,8 @@ def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None):
             Dy = torch.from_numpy(degrade_axis_matrix(Y, True)).float()
             vol = out.reshape(X, Y, Z, -1)
             out = torch.einsum("ax,by,xyzc->abzc", Dx, Dy, vol).reshape(-1, vol.shape[-1])
-        loss = ((out - target) ** 2).mean()
+        # weight: the per-element loss weights of INR/INR_ERD.py:265, (w * (out - gt)**2).mean()
+        loss = ((out - target) ** 2).mean() if weight is None else (weight * (out - target) ** 2).mean()
         opt.zero_grad()
         loss.backward()
         opt.step()

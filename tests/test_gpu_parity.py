@@ -911,3 +911,25 @@ def test_all_combinations_vs_reference_golden(dev, golden_dir):
     out = b200inr.all_combinations(big, device=dev).cpu().numpy()
     for (i, j, k) in ((0, 0, 0), (15, 8, 4), (7, 3, 2)):
         np.testing.assert_array_equal(out[i, j, k], b200inr.calculate_combinations((i, j, k), big).astype(np.float32))
+
+
+def test_weighted_fit_vs_oracle(dev):
+    """fit(..., weight=w): the weighted loss (w * (out - gt)**2).mean() of INR/INR_ERD.py:265 in the fused loop, same
+    seed / inputs / steps as the CPU oracle; softmax-like positive weights spanning two decades."""
+    shape, C, steps, lr = (32, 32), 1, 40, 3e-4
+    torch.manual_seed(17)
+    m = b200inr.Siren(2, 256, 2, C)
+    torch.manual_seed(17)
+    ref = O.torch_siren(2, 256, 2, C)
+    rs = np.random.RandomState(4)
+    gt = rs.uniform(size=(32 * 32, C)).astype(np.float32)
+    w = np.exp(rs.uniform(-2.3, 2.3, size=(32 * 32, C))).astype(np.float32)
+    coords = torch.from_numpy(O.get_mgrid(shape))
+    ref_losses = O.torch_fit(ref, coords, torch.from_numpy(gt), steps, lr, weight=torch.from_numpy(w))
+    m = m.to(dev)
+    losses = m.fit(torch.from_numpy(gt).to(dev), shape, steps=steps, lr=lr, weight=torch.from_numpy(w).to(dev),
+                   graph=False).cpu().numpy()
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+    with pytest.raises(RuntimeError):
+        m.fit(torch.zeros(16 * 16 * 8 * C // 4, device=dev), (16, 16, 8), steps=1, degrade="pool",
+              weight=torch.ones(16 * 16 * 8, C, device=dev))
