@@ -80,18 +80,22 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
+            try:
+                pw.append(float(r[3].split()[0]))
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(pw)) if pw else None}
 
 
 def cpu_fit_sample(steps, warmup, threads):
