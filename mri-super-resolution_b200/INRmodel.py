@@ -1,6 +1,7 @@
-"""Drop-in for the reference's INR/INRmodel.py (Siren :122-151: sine layers constructed before the final linear, no
-first_omega_0 argument, coordinates not detached by the module)."""
-from .inr import PN, ImageFitting_set, SineLayer, calculate_ADC, calculate_combinations, get_mgrid, input_mapping  # noqa: F401
+"""Drop-in for the reference's INR/INRmodel.py (imported at INR/inrDWI.py:9): Siren :122-151 builds its sine layers
+before the final linear, has no first_omega_0 argument and does not detach its input; ComplexGaborLayer2D :66-120."""
+from .inr import (PN, ComplexGaborLayer2D, ImageFitting_set, SineLayer, calculate_ADC, calculate_combinations,  # noqa: F401
+                  get_mgrid, input_mapping, resize_array)
 from .inr import Siren as _Siren
 
 
@@ -10,5 +11,5 @@ class Siren(_Siren):
                          variant="INRmodel")
 
 
-__all__ = ["ImageFitting_set", "PN", "SineLayer", "Siren", "calculate_ADC", "calculate_combinations", "get_mgrid",
-           "input_mapping"]
+__all__ = ["ComplexGaborLayer2D", "ImageFitting_set", "PN", "SineLayer", "Siren", "calculate_ADC",
+           "calculate_combinations", "get_mgrid", "input_mapping", "resize_array"]

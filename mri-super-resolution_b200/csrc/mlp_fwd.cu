@@ -18,11 +18,30 @@
 //
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
+//
+// kPair (the default whenever there are two tile pairs): two CTAs on an SM pair (thread-block cluster of 2) run the
+// schedule above in lock step and every MMA is ONE tcgen05.mma.cta_group::2 of M = 256 (each CTA's own 128 rows) x
+// N: each CTA stages only ITS half of every weight chunk (the B rows of 128 of the 256 output features), so per SM the
+// weight traffic from L2, the shared-memory writes of the ring and the B-operand reads of the tensor core all halve:
+// 256 KB of shared-memory traffic per 128x256x256 layer-tile instead of 384 KB, which was what paced the 1-CTA kernel
+// (event trace: two layer-tiles per 6.1 k cycles = 768 KB at 128 B/clk).  The leader CTA's MMA warp waits for both
+// CTAs' A tiles and both weight halves and commits with multicast arrives to both CTAs.  Cross-CTA arrives carry the
+// DEFAULT (cta-scope release) semantics behind a fence.proxy.async: an arrive.release.cluster compiles to
+// MEMBAR.ALL.GPU, which waits for every outstanding phase-stash store of the warp (~1-2 k cycles per layer-tile; that
+// membar, not the lock step, is what made the first pair kernel slower than the 1-CTA one).
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
+
+#ifndef B200INR_TUNING
+#define B200INR_TUNING 0
+#endif
+#ifndef B200INR_FKO
+#define B200INR_FKO 0  // tuning knock-outs (results are garbage): 1 = weights loaded once, never waited for again,
+                       // 2 = no sin, 4 = no shared-memory stores of the activations
+#endif
 
 namespace b200inr {
 
@@ -31,7 +50,6 @@ constexpr int kFwdFirstEpiWarp = 3;
 constexpr int kFwdThreads = (kFwdFirstEpiWarp + kFwdEpiWarps) * 32;  // 608
 constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;                   // 512
 constexpr uint32_t kEpiBarId = 1;
-constexpr int kFwdSlots = 3;
 
 struct FwdParams {
   const uint8_t* packed;
@@ -51,16 +69,17 @@ struct FwdParams {
   uint32_t* trace;  // tuning aid (B200INR_FWD_TRACE_PTR): CTA 0 records [phase][8] event times, phase = (pair, layer, tile)
 };
 
-template <int H>
+template <int H, bool kPair>
 struct FwdSmem {
   static constexpr int kKB = H / 64;                 // 64-wide K blocks
   static constexpr int kABlock = kTileRows * 128;    // bytes of one [128][64] bf16 block
   static constexpr int kABytes = kKB * kABlock;      // 64 KB for H = 256
-  static constexpr int kSlotBytes = H * 128;         // one K chunk of a hidden layer: [H rows][64]
+  static constexpr int kSlots = kPair ? 6 : 3;       // weight ring: 96 KB either way
+  static constexpr int kSlotBytes = (kPair ? H / 2 : H) * 128;  // one K chunk of a hidden layer: [H (or H/2) rows][64]
   static constexpr int kOffA = 0;                    // two A tiles
   static constexpr int kOffW = 2 * kABytes;
-  static constexpr int kOffBar = kOffW + kFwdSlots * kSlotBytes;
-  static constexpr int kBytes = kOffBar + 256;
+  static constexpr int kOffBar = kOffW + kSlots * kSlotBytes;
+  static constexpr int kBytes = kOffBar + 512;
 };
 
 constexpr float kPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
@@ -76,130 +95,241 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
-      yb[j] = pack_bf16x2(__sinf(t0), __sinf(t1));
+      yb[j] = (B200INR_FKO & 2) ? pack_bf16x2(t0, t1) : pack_bf16x2(__sinf(t0), __sinf(t1));
       if (kStash) {
         const uint32_t p0 = __float_as_uint(fmaf(t0, kPhaseScale, kPhaseMagic));
         const uint32_t p1 = __float_as_uint(fmaf(t1, kPhaseScale, kPhaseMagic));
         ph[j] = __byte_perm(p0, p1, 0x5410);
       }
     }
-    sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
+    if (!(B200INR_FKO & 4) || yb[0] == 0x12345678u)
+      sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
     if (kStash)
       __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * kChunkStride), make_uint4(ph[0], ph[1], ph[2], ph[3]));
   }
 }
 
+// ------------------------------------------------------------------ weight-slot schedule
+// Both tiles of a pair slot run the same layer back to back, so a layer's weight chunks are loaded ONCE per tile pair:
+// tile 0 consumes K chunks 0 .. n-1 as they land, tile 1 consumes the same (still resident) chunks in the same order
+// and releases each slot after its use.  The ring therefore holds a whole layer (4 slots) plus 2 slots of look-ahead;
+// slots are reused in the order they are released (a FIFO, not a round robin), so the next layer's first two chunks
+// are prefetched while the current layer is still in use and the last two land in the slots tile 1 releases first.  Producer, MMA issuer and
+// the peer's relay thread all replay the same deterministic schedule with this little state machine; the barriers
+// only carry the timing.  (Before: every chunk was re-streamed per tile, and waiting for weights cost the training
+// forward 10 % -- knock-out measurement B200INR_FKO=1.)
+struct WSlots {
+  uint32_t fifo;   // free slots, 4 bits each, oldest first (low nibble)
+  uint32_t nfree;
+  uint32_t par;    // bit s: parity of the number of loads into slot s so far
+  uint32_t used;   // bit s: slot s has been loaded at least once
+  __device__ __forceinline__ void init(int nslots) {
+    fifo = 0;
+    for (int i = 0; i < nslots; ++i) fifo |= uint32_t(i) << (4 * i);
+    nfree = uint32_t(nslots);
+    par = used = 0;
+  }
+  __device__ __forceinline__ uint32_t pop() {
+    const uint32_t s = fifo & 15u;
+    fifo >>= 4;
+    --nfree;
+    return s;
+  }
+  __device__ __forceinline__ void push(uint32_t s) {
+    fifo |= s << (4 * nfree);
+    ++nfree;
+  }
+};
+
+// Walks the schedule of one CTA: on_tile(pr, l, j) before the chunks of tile j of layer step l, then
+// on_chunk(l, j, k, i, slot, first_use, last_use) for every chunk use (k = K chunk, i = position in this tile's order).
+template <class FT, class FC>
+__device__ __forceinline__ void walk_weight_schedule(int num_pairs, int my_tiles, int L, int nslots, FT&& on_tile,
+                                                     FC&& on_chunk) {
+  WSlots ws;
+  ws.init(nslots);
+  for (int pr = 0; pr < num_pairs; ++pr) {
+    const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
+    for (int l = 0; l <= L + 1; ++l) {
+      const int nk = (l == 0) ? 1 : 4;
+      uint32_t slot_of = 0;  // 4 bits per K chunk
+      on_tile(pr, l, 0);
+      for (int k = 0; k < nk; ++k) {
+        const uint32_t s = ws.pop();
+        slot_of |= s << (4 * k);
+        on_chunk(ws, l, 0, k, k, s, true, nt == 1);
+        ws.par ^= 1u << s;
+        ws.used |= 1u << s;
+        if (nt == 1) ws.push(s);
+      }
+      if (nt == 2) {
+        on_tile(pr, l, 1);
+        for (int k = 0; k < nk; ++k) {  // same K order as tile 0: results do not depend on a tile's position
+          const uint32_t s = (slot_of >> (4 * k)) & 15u;
+          on_chunk(ws, l, 1, k, k, s, false, true);
+          ws.push(s);
+        }
+      }
+    }
+  }
+}
+
 // kMode: 0 = inference, 1 = staged training (sin outputs + phases + coordinate operand), 2 = pipelined training
 // (phases only: mlp_bwdp.cu recomputes sin and cos from them).
-template <int H, int kMode>
+template <int H, int kMode, bool kPair>
 __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
   constexpr bool kStash = kMode != 0;  // phases are stored
   constexpr bool kStashY = kMode == 1;  // sin outputs and the coordinate operand are stored too
-  using S = FwdSmem<H>;
+  using S = FwdSmem<H, kPair>;
+  constexpr int kFwdSlots = S::kSlots;
   static_assert(S::kKB == 4, "epilogue slicing assumes 4 K blocks");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem + S::kOffA;
   uint8_t* w_smem = smem + S::kOffW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;                      // [kFwdSlots]
-  uint64_t* w_empty = bars + kFwdSlots;         // [kFwdSlots]
-  uint64_t* a_ready = bars + 2 * kFwdSlots;     // [2]  A operand of tile j complete in shared memory
-  uint64_t* d_full = bars + 2 * kFwdSlots + 2;  // [2]  accumulator of tile j complete in TMEM
-  uint64_t* a_free = bars + 2 * kFwdSlots + 4;  // [2]  stash store of A tile j has been read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFwdSlots + 6);
+  uint64_t* w_full = bars;                      // [kFwdSlots] this CTA's (half) chunk landed
+  uint64_t* w_empty = bars + kFwdSlots;         // [kFwdSlots] MMAs reading the slot done (pair: multicast commit)
+  uint64_t* a_ready = bars + 3 * kFwdSlots;     // [2]  A operand of this CTA's tile j complete in shared memory
+  uint64_t* d_full = bars + 3 * kFwdSlots + 2;  // [2]  accumulator of tile j complete in TMEM (pair: multicast commit)
+  uint64_t* a_free = bars + 3 * kFwdSlots + 4;  // [2]  stash store of A tile j has been read out (staged training)
+  uint64_t* a_pair = bars + 3 * kFwdSlots + 6;  // [2]  (pair leader) A tile j complete in BOTH CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kFwdSlots + 8);
+  static_assert((3 * S::kSlots + 8) * 8 + 4 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int L = p.L;
+  const bool leader = !kPair || cluster_ctarank() == 0;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFwdSlots; ++i) {
-      mbar_init(&w_full[i], 1);
+      mbar_init(&w_full[i], (kPair && leader) ? 2 : 1);  // leader: own producer (+ tx bytes) and the peer's relay
       mbar_init(&w_empty[i], 1);
     }
     for (int j = 0; j < 2; ++j) {
       mbar_init(&a_ready[j], kFwdEpiWarps);
+      mbar_init(&a_pair[j], 2 * kFwdEpiWarps);  // the epilogue warps of both CTAs
       mbar_init(&d_full[j], 1);
       mbar_init(&a_free[j], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (kPair)
+      tmem_alloc_2cta<512>(tmem_slot);
+    else
+      tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair)
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  // a pair runs the slot count of its leader (even block index, which never has fewer tiles); the peer's last slot
+  // may then be a tile beyond the end: it is computed (clamped coordinates) but nothing of it is stored
+  const int lead_block = kPair ? (int(blockIdx.x) & ~1) : int(blockIdx.x);
+  const int my_tiles = (p.num_tiles - lead_block + int(gridDim.x) - 1) / int(gridDim.x);
   const int num_pairs = (my_tiles + 1) / 2;
   const bool tr = p.trace != nullptr && blockIdx.x == 0;
   const long long t_begin = tr ? clock64() : 0;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
+    // one load per (layer step, K chunk) and tile PAIR (see WSlots); the slot's previous occupant must have been
+    // released by its last reader (w_empty: commit of the MMAs of tile 1, or of tile 0 in a single-tile slot)
     if (lane == 0) {
-      uint32_t c = 0;
-      for (int pr = 0; pr < num_pairs; ++pr) {
-        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 0; l <= L + 1; ++l) {
-          // l = 0: the first layer's hi/lo operand (one chunk, K = 32 used); 1..L: hidden layers; L+1: final linear
-          const bool hidden = (l >= 1 && l <= L);
-          const uint8_t* src = (l == 0) ? p.packed + p.pl.w0p
-                               : hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2
-                                        : p.packed + p.pl.wf;
-          const uint32_t bytes = (l <= L) ? uint32_t(S::kSlotBytes) : uint32_t(kOutPad * 128);
-          const int nchunks = (l == 0) ? 1 : S::kKB;
-          for (int j = 0; j < nt; ++j) {
-            for (int kb = 0; kb < nchunks; ++kb, ++c) {
-              const uint32_t slot = c % kFwdSlots, round = c / kFwdSlots;
-              if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
-              mbar_arrive_expect_tx(&w_full[slot], bytes);
-              bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * bytes, bytes, &w_full[slot]);
-            }
-          }
-        }
-      }
+      walk_weight_schedule(
+          num_pairs, my_tiles, L, kFwdSlots, [](int, int, int) {},
+          [&](const WSlots& ws, int l, int, int k, int, uint32_t slot, bool first_use, bool) {
+            if (!first_use) return;
+            if ((B200INR_FKO & 1) && ((ws.used >> slot) & 1u)) return;
+            // l = 0: the first layer's hi/lo operand (one chunk, K = 32 used); 1..L: hidden layers; L+1: final linear
+            const bool hidden = (l >= 1 && l <= L);
+            const uint8_t* src = (l == 0) ? p.packed + p.pl.w0p
+                                 : hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2
+                                          : p.packed + p.pl.wf;
+            // chunk = [N rows][64] of one K block; a pair member stages the rows of ITS half of the output features
+            const uint32_t chunk = (l <= L) ? uint32_t(H * 128) : uint32_t(kOutPad * 128);
+            const uint32_t bytes = kPair ? chunk / 2 : chunk;
+            if ((ws.used >> slot) & 1u) mbar_wait(&w_empty[slot], ((ws.par >> slot) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&w_full[slot], bytes);
+            bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(k) * chunk + size_t(rank) * bytes, bytes,
+                     &w_full[slot]);
+          });
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // the whole warp runs the loop converged, one elected lane issues (umma_*_w: no per-instruction R2UR loop)
-    {
+    // the whole warp runs the loop converged, one elected lane issues (umma_*_w: no per-instruction R2UR loop);
+    // pair: the leader issues for both CTAs; the peer's lane 0 mirrors the leader's waits and relays them.
+    if (leader) {
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      uint32_t c = 0, na[2] = {0, 0};
-      for (int pr = 0; pr < num_pairs; ++pr) {
-        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 0; l <= L + 1; ++l) {
-          const uint32_t idesc = (l <= L) ? idesc_bf16(128, H, false, false) : idesc_bf16(128, kOutPad, false, false);
-          const int nkb = (l == 0) ? 1 : S::kKB, nk4 = (l == 0) ? 2 : 4;  // first layer: K = 32 (hi/lo coordinate operand)
-          for (int j = 0; j < nt; ++j) {
-            const int tph = (pr * (L + 3) + l) * 2 + j;
+      constexpr int kM = kPair ? 256 : 128;
+      uint64_t* a_mma = kPair ? a_pair : a_ready;
+      uint32_t na[2] = {0, 0};
+      uint32_t idesc = 0;
+      int nk4 = 4, cur_tph = 0;
+      walk_weight_schedule(
+          num_pairs, my_tiles, L, kFwdSlots,
+          [&](int pr, int l, int j) {
+            idesc = (l <= L) ? idesc_bf16(kM, H, false, false) : idesc_bf16(kM, kOutPad, false, false);
+            nk4 = (l == 0) ? 2 : 4;  // first layer: K = 32 (hi/lo coordinate operand)
+            const int tph = cur_tph = (pr * (L + 3) + l) * 2 + j;
             if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 0] = uint32_t(clock64() - t_begin);
-            mbar_wait(&a_ready[j], na[j] & 1);
+            mbar_wait(&a_mma[j], na[j] & 1);
             ++na[j];
             if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 1] = uint32_t(clock64() - t_begin);
             tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb, ++c) {
-              const uint32_t slot = c % kFwdSlots;
-              mbar_wait(&w_full[slot], (c / kFwdSlots) & 1);
+          },
+          [&](const WSlots& ws, int l, int j, int k, int i, uint32_t slot, bool first_use, bool last_use) {
+            if (first_use && (!(B200INR_FKO & 1) || !((ws.used >> slot) & 1u))) {
+              mbar_wait(&w_full[slot], (ws.par >> slot) & 1u);  // pair: own half landed AND the peer's relay arrived
               tc_fence_after();
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                if (k4 < nk4) {
-                  const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
-                  const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                  umma_bf16_ss_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
-                }
-              }
-              umma_commit_w(&w_empty[slot]);
             }
-            umma_commit_w(&d_full[j]);
-            if (tr && lane == 0 && tph < 512) p.trace[tph * 8 + 2] = uint32_t(clock64() - t_begin);
-          }
-        }
-      }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (k4 < nk4) {
+                const uint64_t da = smem_desc(a_base + j * S::kABytes + k * S::kABlock + k4 * 32, hi);
+                const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+                if (kPair)
+                  umma_bf16_ss_2cta_w(tmem_d + j * 256, da, db, idesc, (i | k4) != 0);
+                else
+                  umma_bf16_ss_w(tmem_d + j * 256, da, db, idesc, (i | k4) != 0);
+              }
+            }
+            if (last_use) {
+              if (kPair)
+                umma_commit_2cta_w(&w_empty[slot]);
+              else
+                umma_commit_w(&w_empty[slot]);
+            }
+            if (i == ((l == 0) ? 0 : 3)) {  // last chunk of this tile's layer step: accumulator complete
+              if (kPair)
+                umma_commit_2cta_w(&d_full[j]);
+              else
+                umma_commit_w(&d_full[j]);
+              if (tr && lane == 0 && cur_tph < 512) p.trace[cur_tph * 8 + 2] = uint32_t(clock64() - t_begin);
+            }
+          });
+    } else if (lane == 0) {
+      // relay (pair peer): "my half chunk has landed" (bulk copy = async proxy, read by the async proxy: no fence) ->
+      // second arrival on the leader's w_full barrier of that slot, so the MMA warp waits ONCE per chunk (every
+      // mbarrier wait costs the issuing warp ~100-150 cycles on the busy shared-memory pipe, and with two waits per
+      // chunk the issue loop, not the tensor pipe, paced the layer)
+      walk_weight_schedule(
+          num_pairs, my_tiles, L, kFwdSlots, [](int, int, int) {},
+          [&](const WSlots& ws, int, int, int, int, uint32_t slot, bool first_use, bool) {
+            if (!first_use) return;
+            if ((B200INR_FKO & 1) && ((ws.used >> slot) & 1u)) return;
+            mbar_wait(&w_full[slot], (ws.par >> slot) & 1u);
+            mbar_arrive_peer(&w_full[slot], 0);
+          });
     }
   } else if (warp == 2) {
     // =============================== stash store (training) ===============================
@@ -214,7 +344,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         }
         for (int l = 0; l <= L; ++l) {
           for (int j = 0; j < nt; ++j) {
-            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+            if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // pair peer past the end: recomputes the last tile
             mbar_wait(&a_ready[j], na[j] & 1);
             ++na[j];
             bulk_s2g(p.stash_y + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes,
@@ -242,7 +373,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     //      Coordinates are derived from the voxel index (get_mgrid is never materialised).  The four warps with slice
     //      index s == j build tile j, so the two tiles of a pair are built concurrently; the operands of the NEXT pair
     //      are built inside the final-layer section of the current one (coordinates computed before its TMEM wait).
-    auto tile_of = [&](int pr_, int j) { return int(blockIdx.x) + (2 * pr_ + j) * int(gridDim.x); };
+    // (a pair peer whose last slot lies past the end recomputes the LAST tile: identical values stored twice, so the
+    //  lock-stepped schedule needs no inactive-tile branches in the hot loops)
+    auto tile_of = [&](int pr_, int j) {
+      const int t = int(blockIdx.x) + (2 * pr_ + j) * int(gridDim.x);
+      return t < p.num_tiles ? t : p.num_tiles - 1;
+    };
+    // A tile j of this CTA is complete in shared memory: writer-side generic -> async proxy fence, then every warp
+    // tells the leader's MMA warp directly (pair peer: plain remote arrive, see the header comment).  The local
+    // barrier is only needed by the stash-store thread of the staged training mode.
+    auto publish = [&](int j) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (!kPair || kStashY) mbar_arrive(&a_ready[j]);
+        if (kPair) {
+          if (leader)
+            mbar_arrive(&a_pair[j]);
+          else
+            mbar_arrive_peer(&a_pair[j], 0);
+        }
+      }
+    };
     auto coords_of = [&](int tile, float (&x)[4]) {
       const long long row0 = (long long)tile * kTileRows;
       if (p.coords != nullptr) {
@@ -280,10 +433,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         if (s > 0) *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_ready[j]);
+      publish(j);
     };
     {  // operands of the first pair
       const int nt0 = my_tiles < 2 ? my_tiles : 2;
@@ -298,7 +448,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       // ---- sine layers 0..L: X, Y, X, Y, ...  (layer 0: the bias is part of the GEMM)
       for (int l = 0; l <= L; ++l) {
         for (int j = 0; j < nt; ++j) {
-          const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+          const int tile = tile_of(pr, j);
           const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
           const float* bl = bias_g + l * H;
           const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
@@ -346,10 +496,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
                                            kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr);
           }
           if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[j]);
+          publish(j);
           if (trw) p.trace[tph * 8 + 7] = uint32_t(clock64() - t_begin);
         }
       }
@@ -362,7 +509,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       float xn[4] = {0.f, 0.f, 0.f, 0.f};
       if (s < nt_next) coords_of(tile_of(pr + 1, s), xn);  // index arithmetic overlaps the wait for the final MMA
       for (int j = 0; j < nt; ++j) {
-        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
+        const int tile = tile_of(pr, j);
         const long long row0 = (long long)tile * kTileRows;
         const uint32_t stg = smem_u32(a_smem) + j * S::kABytes + 3 * S::kABlock;
         mbar_wait(&d_full[j], nd[j] & 1);
@@ -403,346 +550,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     }
   }
 
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_d);
-}
-
-// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
-// Two CTAs on an SM pair run the kernel above in lock step and issue every MMA as ONE tcgen05.mma.cta_group::2 of
-// M = 256 (each CTA's own 128 rows) x N = 256: each CTA stages only ITS half of every weight chunk (the B rows of 128
-// of the 256 output features), so per SM the weight-chunk traffic from L2, the shared-memory writes of the ring and
-// the B-operand reads of the tensor core all halve, and the ring gets 6 slots of 16 KB.  The leader CTA's MMA thread waits for both
-// CTAs' A tiles (remote mbarrier arrives) and both weight halves (the peer's MMA warp relays its ring barrier), and
-// commits with a multicast arrive to both CTAs.
-constexpr int kFwd2Slots = 6;
-
-template <int H>
-struct Fwd2Smem {
-  static constexpr int kKB = H / 64;
-  static constexpr int kABlock = kTileRows * 128;
-  static constexpr int kABytes = kKB * kABlock;
-  static constexpr int kSlotBytes = (H / 2) * 128;  // this CTA's half of a K chunk: [H/2 rows][64]
-  static constexpr int kOffA = 0;
-  static constexpr int kOffW = 2 * kABytes;
-  static constexpr int kOffBar = kOffW + kFwd2Slots * kSlotBytes;
-  static constexpr int kBytes = kOffBar + 512;
-};
-
-template <int H, bool kStash>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1) siren_fwd2_kernel(const FwdParams p) {
-  using S = Fwd2Smem<H>;
-  static_assert(S::kKB == 4, "epilogue slicing assumes 4 K blocks");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_smem = smem + S::kOffA;
-  uint8_t* w_smem = smem + S::kOffW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;                       // [kFwd2Slots] this CTA's half chunk landed
-  uint64_t* w_peer = bars + kFwd2Slots;          // [kFwd2Slots] (leader) the peer's half chunk landed
-  uint64_t* w_empty = bars + 2 * kFwd2Slots;     // [kFwd2Slots] MMAs reading the slot done (multicast commit)
-  uint64_t* a_ready = bars + 3 * kFwd2Slots;     // [2] this CTA's A tile j complete (own stash-store thread)
-  uint64_t* a_pair = bars + 3 * kFwd2Slots + 2;  // [2] (leader) A tile j complete in BOTH CTAs
-  uint64_t* d_full = bars + 3 * kFwd2Slots + 4;  // [2] accumulator j complete (multicast commit)
-  uint64_t* a_free = bars + 3 * kFwd2Slots + 6;  // [2] stash store of A tile j read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kFwd2Slots + 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int L = p.L;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kFwd2Slots; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_peer[i], 1);
-      mbar_init(&w_empty[i], 1);
-    }
-    for (int j = 0; j < 2; ++j) {
-      mbar_init(&a_ready[j], kFwdEpiWarps);
-      mbar_init(&a_pair[j], 2 * kFwdEpiWarps);
-      mbar_init(&d_full[j], 1);
-      mbar_init(&a_free[j], 1);
-    }
-    fence_mbar_init();
+  if (kPair) {
+    tc_fence_before();
+    cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still address it
+    if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_d);
   }
-  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
-  tc_fence_before();
-  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
-
-  // both CTAs of a pair run the slot count of the leader (even block index, which never has fewer tiles)
-  const int lead_block = int(blockIdx.x) & ~1;
-  const int my_tiles = (p.num_tiles - lead_block + int(gridDim.x) - 1) / int(gridDim.x);
-  const int num_pairs = (my_tiles + 1) / 2;
-
-  if (warp == 0) {
-    // =============================== weight producer: this CTA's half of every chunk ===============================
-    if (lane == 0) {
-      uint32_t c = 0;
-      for (int pr = 0; pr < num_pairs; ++pr) {
-        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 1; l <= L + 1; ++l) {
-          const bool hidden = (l <= L);
-          const uint8_t* src = hidden ? p.packed + p.pl.wh + size_t(l - 1) * H * H * 2 : p.packed + p.pl.wf;
-          const uint32_t chunk = hidden ? uint32_t(H * 128) : uint32_t(kOutPad * 128);
-          const uint32_t bytes = chunk / 2;
-          for (int j = 0; j < nt; ++j) {
-            for (int kb = 0; kb < S::kKB; ++kb, ++c) {
-              const uint32_t slot = c % kFwd2Slots, round = c / kFwd2Slots;
-              if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
-              mbar_arrive_expect_tx(&w_full[slot], bytes);
-              bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(kb) * chunk + size_t(rank) * bytes, bytes,
-                       &w_full[slot]);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (leader || lane == 0) {  // leader: the whole warp runs converged, one elected lane issues; peer: one relay thread
-      if (leader) {
-        // =============================== MMA issuer (leader CTA) ===============================
-        const uint64_t hi = smem_desc_hi_sw128(0, 1024);
-        const uint32_t a_base = smem_u32(a_smem);
-        const uint32_t w_base = smem_u32(w_smem);
-        uint32_t c = 0, na[2] = {0, 0};
-        for (int pr = 0; pr < num_pairs; ++pr) {
-          const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-          for (int l = 1; l <= L + 1; ++l) {
-            const uint32_t idesc = (l <= L) ? idesc_bf16(256, H, false, false) : idesc_bf16(256, kOutPad, false, false);
-            for (int j = 0; j < nt; ++j) {
-              mbar_wait_cluster(&a_pair[j], na[j] & 1);
-              ++na[j];
-              tc_fence_after();
-              for (int kb = 0; kb < S::kKB; ++kb, ++c) {
-                const uint32_t slot = c % kFwd2Slots;
-                mbar_wait(&w_full[slot], (c / kFwd2Slots) & 1);
-                mbar_wait_cluster(&w_peer[slot], (c / kFwd2Slots) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const uint64_t da = smem_desc(a_base + j * S::kABytes + kb * S::kABlock + k4 * 32, hi);
-                  const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                  umma_bf16_ss_2cta_w(tmem_d + j * 256, da, db, idesc, (kb | k4) != 0);
-                }
-                umma_commit_2cta_w(&w_empty[slot]);
-              }
-              umma_commit_2cta_w(&d_full[j]);
-            }
-          }
-        }
-      } else {
-        // =============================== relay (peer CTA): my half chunk landed -> tell the leader ===================
-        uint32_t c = 0;
-        for (int pr = 0; pr < num_pairs; ++pr) {
-          const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-          for (int l = 1; l <= L + 1; ++l) {
-            for (int j = 0; j < nt; ++j) {
-              for (int kb = 0; kb < S::kKB; ++kb, ++c) {
-                const uint32_t slot = c % kFwd2Slots;
-                mbar_wait(&w_full[slot], (c / kFwd2Slots) & 1);
-                mbar_arrive_remote(&w_peer[slot], 0);
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // =============================== stash store (training) ===============================
-    if (kStash && lane == 0) {
-      uint32_t na[2] = {0, 0};
-      for (int pr = 0; pr < num_pairs; ++pr) {
-        const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-        for (int l = 0; l <= L; ++l) {
-          for (int j = 0; j < nt; ++j) {
-            const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
-            mbar_wait(&a_ready[j], na[j] & 1);
-            ++na[j];
-            if (tile < p.num_tiles) {
-              bulk_s2g(p.stash_y + size_t(l) * p.stash_layer_stride + size_t(tile) * S::kABytes,
-                       a_smem + j * S::kABytes, S::kABytes);
-              bulk_commit();
-              bulk_wait_read0();
-            }
-            mbar_arrive(&a_free[j]);
-          }
-        }
-      }
-      bulk_wait0();
-    }
-  } else if (warp >= kFwdFirstEpiWarp) {
-    // =============================== epilogue warps ===============================
-    const int et = threadIdx.x - kFwdFirstEpiWarp * 32;
-    const int q = warp & 3;
-    const int s = (warp - kFwdFirstEpiWarp) >> 2;
-    const int r = q * 32 + lane;
-    const uint32_t t_lane = uint32_t(q * 32) << 16;
-    const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
-    const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
-    uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
-    // A tile j of this CTA is complete: own stash thread (local) and the leader's MMA thread (pair barrier)
-    auto publish = [&](int j) {
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&a_ready[j]);
-        mbar_arrive_remote(&a_pair[j], 0);
-      }
-    };
-    for (int pr = 0; pr < num_pairs; ++pr) {
-      const int nt = (my_tiles - 2 * pr) < 2 ? (my_tiles - 2 * pr) : 2;
-
-      // ---- layer 0 on CUDA cores, both tiles
-      for (int j = 0; j < nt; ++j) {
-        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
-        const bool active = tile < p.num_tiles;  // the peer of a pair may run a slot without a tile of its own
-        const long long row0 = (long long)tile * kTileRows;
-        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-        uint8_t* ph_row = (kStash && active) ? p.stash_ph + size_t(tile) * S::kABytes + size_t(r) * 16 : nullptr;
-        float x[4];
-        if (p.coords != nullptr) {
-          long long row = row0 + r;
-          if (row >= p.rows) row = p.rows - 1;
-          x[0] = x[1] = x[2] = x[3] = 0.0f;
-          for (int jj = 0; jj < p.d; ++jj) x[jj] = p.coords[row * p.d + jj];
-        } else {
-          grid_coords(p.grid, row0 + r, x);
-        }
-        if (kStash && active) {
-          uint8_t* xa_row = p.stash_xa + size_t(tile) * (kTileRows * 128);
-          uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
-          if (s == 0) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              hi[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));
-              lo[jj] = x[jj] - hi[jj];
-            }
-            c0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]),
-                            pack_bf16x2(lo[2], lo[3]));
-          }
-          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s)) = c0;
-          *reinterpret_cast<uint4*>(xa_row + sw128_chunk_off(r, 2 * s + 1)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll 1
-        for (int kb = 0; kb < S::kKB; ++kb) {
-          const int col0 = kb * 64 + s * 16;
-          float th[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float4 w = __ldg(w0_g + col0 + jj);
-            float acc = __ldg(bias_g + col0 + jj);
-            acc = fmaf(x[0], w.x, acc);
-            acc = fmaf(x[1], w.y, acc);
-            acc = fmaf(x[2], w.z, acc);
-            acc = fmaf(x[3], w.w, acc);
-            th[jj] = acc;
-          }
-          if (kStash && active)
-            emit_sine16<true>(th, a_addr + kb * S::kABlock, r, s, ph_row + size_t(kb * 8 + 2 * s) * (kTileRows * 16));
-          else
-            emit_sine16<false>(th, a_addr + kb * S::kABlock, r, s, nullptr);
-        }
-        publish(j);
-      }
-
-      // ---- hidden layers: X, Y, X, Y, ...
-      for (int l = 1; l <= L; ++l) {
-        for (int j = 0; j < nt; ++j) {
-          const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
-          const bool active = tile < p.num_tiles;
-          const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-          const float* bl = bias_g + l * H;
-          const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
-          uint8_t* ph_l = (kStash && active) ? p.stash_ph + size_t(l) * p.stash_layer_stride +
-                                                   size_t(tile) * S::kABytes + size_t(r) * 16
-                                             : nullptr;
-          mbar_wait(&d_full[j], nd[j] & 1);
-          ++nd[j];
-          if (kStash) {
-            mbar_wait(&a_free[j], nf[j] & 1);
-            ++nf[j];
-          }
-          tc_fence_after();
-          uint32_t v[16], vn[16];
-          tmem_ld16(d_addr, vn);
-#pragma unroll
-          for (int kb = 0; kb < S::kKB; ++kb) {
-            const int col0 = kb * 64 + s * 16;
-            float4 bq[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
-            tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
-            if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
-            float th[16];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bq[j4].x;
-              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bq[j4].y;
-              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bq[j4].z;
-              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bq[j4].w;
-            }
-            if (kStash && active)
-              emit_sine16<true>(th, a_addr + kb * S::kABlock, r, s, ph_l + size_t(kb * 8 + 2 * s) * (kTileRows * 16));
-            else
-              emit_sine16<false>(th, a_addr + kb * S::kABlock, r, s, nullptr);
-          }
-          publish(j);
-        }
-      }
-
-      // ---- final linear: D[:, 0:32) + bias -> out
-      for (int j = 0; j < nt; ++j) {
-        const int tile = int(blockIdx.x) + (2 * pr + j) * int(gridDim.x);
-        const long long row0 = (long long)tile * kTileRows;
-        const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-        mbar_wait(&d_full[j], nd[j] & 1);
-        ++nd[j];
-        if (kStash) {
-          mbar_wait(&a_free[j], nf[j] & 1);
-          ++nf[j];
-        }
-        tc_fence_after();
-        const int C = p.C;
-        if (s == 0) {
-          uint32_t v[32];
-          tmem_ld32(tmem_d + t_lane + uint32_t(j) * 256, v);
-          tmem_ld_wait();
-          const float* bf = bias_g + (L + 1) * H;
-#pragma unroll
-          for (int c = 0; c < kOutPad; ++c) {
-            if (c < C) {
-              float o = __uint_as_float(v[c]) + __ldg(bf + c);
-              if (p.clamp) o = fmaxf(o, p.clamp_min);
-              sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
-            }
-          }
-        }
-        tc_fence_before();
-        named_bar_sync(kEpiBarId, kFwdEpiThreads);
-        long long valid = p.rows - row0;
-        if (valid > kTileRows) valid = kTileRows;
-        if (valid < 0) valid = 0;
-        const int nout = int(valid) * C;
-        float* dst = p.out + row0 * C;
-        for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(a_addr + uint32_t(i) * 4));
-        named_bar_sync(kEpiBarId, kFwdEpiThreads);
-      }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still address it
-  if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
 }
 
 // ------------------------------------------------------------------ launcher
+template <int H, int kMode, bool kPair>
+static int launch_fwd_variant(const FwdParams& p, int grid_x, cudaStream_t stream) {
+  const int smem = FwdSmem<H, kPair>::kBytes + 1024;
+  auto kern = siren_fwd_kernel<H, kMode, kPair>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid_x));
+  cfg.blockDim = dim3(kFwdThreads);
+  cfg.dynamicSmemBytes = size_t(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = kPair ? 2 : 1;
+  at.val.clusterDim.y = 1;
+  at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return B200INR_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
                      int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                      cudaStream_t stream) {
@@ -769,8 +609,14 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   p.out = out;
   p.clamp = clamp;
   p.clamp_min = clamp_min;
+  // tuning builds (-DB200INR_TUNING=1, tools/build_variant.sh) honour B200INR_FWD_TRACE_PTR (event trace buffer of
+  // CTA 0) and B200INR_FWD_MAX_CTAS (grid cap); a production library never reads a pointer from the environment
+  const char* env_cap = nullptr;
+#if B200INR_TUNING
   const char* env_trace = getenv("B200INR_FWD_TRACE_PTR");
   p.trace = env_trace != nullptr ? reinterpret_cast<uint32_t*>(strtoull(env_trace, nullptr, 0)) : nullptr;
+  env_cap = getenv("B200INR_FWD_MAX_CTAS");
+#endif
   const bool staged = (net->flags & B200INR_NET_STAGED_BWD) != 0;
   if (stash && staged) {
     StashLayout sl = make_stash_layout(H, net->hidden_layers, rows);
@@ -784,50 +630,16 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
     p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
   }
-  // persistent CTAs walk tile pairs: do not launch more CTAs than there are pairs
+  // persistent CTA pairs (clusters of 2) walk tile pairs: an even number of CTAs, at most one per SM, no more than
+  // there are tile pairs (a single tile pair still runs on one CTA pair: the peer recomputes the last tile)
   const int pairs = (p.num_tiles + 1) / 2;
-  cudaError_t e;
-  // The CTA-pair kernel is bit-identical but measured slower than the 1-CTA ping-pong (query 0.91 vs 0.77 ms on cfg2:
-  // the lock step couples the two CTAs' epilogues and the epilogue, not shared-memory bandwidth, is the limiter), so
-  // it is opt-in: B200INR_FWD_2CTA=1.
-  const char* env2 = getenv("B200INR_FWD_2CTA");
-  const bool use_2cta = env2 != nullptr && env2[0] == '1';
-  if (use_2cta && pairs >= 2 && (!stash || staged)) {  // CTA-pair kernel: an even number of CTAs, at most one per SM
-    int g2 = pairs < num_sms ? pairs : num_sms;
-    g2 &= ~1;
-    const int smem2 = Fwd2Smem<H>::kBytes + 1024;
-    if (stash) {
-      e = cudaFuncSetAttribute(siren_fwd2_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e != cudaSuccess) return B200INR_ERR_CUDA;
-      siren_fwd2_kernel<H, true><<<g2, kFwdThreads, smem2, stream>>>(p);
-    } else {
-      e = cudaFuncSetAttribute(siren_fwd2_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e != cudaSuccess) return B200INR_ERR_CUDA;
-      siren_fwd2_kernel<H, false><<<g2, kFwdThreads, smem2, stream>>>(p);
-    }
-    return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
-  }
-  const int smem = FwdSmem<H>::kBytes + 1024;
   int grid_x = pairs < num_sms ? pairs : num_sms;
-  {  // tuning aid: cap the number of CTAs (per-CTA rate vs the number of SMs pulling weights through L2)
-    const char* env_cap = getenv("B200INR_FWD_MAX_CTAS");
-    const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
-    if (cap > 0 && cap < grid_x) grid_x = cap;
-  }
-  if (stash && staged) {
-    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return B200INR_ERR_CUDA;
-    siren_fwd_kernel<H, 1><<<grid_x, kFwdThreads, smem, stream>>>(p);
-  } else if (stash) {
-    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return B200INR_ERR_CUDA;
-    siren_fwd_kernel<H, 2><<<grid_x, kFwdThreads, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(siren_fwd_kernel<H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return B200INR_ERR_CUDA;
-    siren_fwd_kernel<H, 0><<<grid_x, kFwdThreads, smem, stream>>>(p);
-  }
-  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+  const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
+  if (cap > 0 && cap < grid_x) grid_x = cap;
+  grid_x = grid_x < 2 ? 2 : (grid_x & ~1);
+  if (!stash) return launch_fwd_variant<H, 0, true>(p, grid_x, stream);
+  if (staged) return launch_fwd_variant<H, 1, true>(p, grid_x, stream);
+  return launch_fwd_variant<H, 2, true>(p, grid_x, stream);
 }
 
 }  // namespace b200inr

@@ -374,6 +374,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// Plain remote arrive (default semantics: release at CTA scope).  This is the hand-off used after a
+// fence.proxy.async by the warps that fill an operand tile read by the peer-issued tcgen05.mma: the writes are local
+// shared-memory stores, complete before the fence returns, and the arrive is issued after it; a cluster-scope release
+// would add a MEMBAR.ALL.GPU that waits for every outstanding GLOBAL store of the warp.
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // The same without the release: for hand-backs of a buffer whose contents this thread has finished READING (its loads
 // have returned); a cluster-scope release costs ~1-2 k cycles under load.
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {

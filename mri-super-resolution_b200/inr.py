@@ -177,6 +177,20 @@ def calculate_combinations(voxel, hybrid_raw_norm):
     return np.stack([np.full(g1.size, b0), g1.ravel(), g2.ravel(), g3.ravel()]).astype(np.float64)
 
 
+def resize_array(arr, new_size=128, kind='cubic'):
+    """Reference INR/SRDWI.py:132-141 (= INR/INRmodel.py:192-201): resample the third axis of a [X, Y, Z] array to
+    `new_size` samples with SciPy's 1-D interpolator (cubic spline by default), both axes spanning [0, 1] inclusive.
+    Host-side data preparation exactly like the reference (same SciPy call, evaluated for all new positions at once
+    instead of one plane per Python iteration); float64 [X, Y, new_size]."""
+    from scipy.interpolate import interp1d
+    arr = np.asarray(arr)
+    if arr.ndim != 3:
+        raise ValueError("resize_array expects a 3-D array [X, Y, Z]")
+    x_old = np.linspace(0, 1, arr.shape[2])
+    x_new = np.linspace(0, 1, int(new_size))
+    return np.asarray(interp1d(x_old, arr, kind=kind, axis=2)(x_new), dtype=np.float64)
+
+
 def calculate_ADC(bvalues, slicedata):
     """Reference INR/SRDWI.py:118-130 (= INR/INRmodel.py): per-voxel mono-exponential fit, ADC = -slope of the
     least-squares line through (b / 1000, log(signal + 1e-7)), clamped to [-10, 3] -- one kernel instead of a Python

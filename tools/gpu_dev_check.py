@@ -178,6 +178,43 @@ def timing(staged=False):
           f"{rows * 1623552 / (ms_f + ms_b) / 1e9:.1f} TFLOP/s algorithmic", flush=True)
 
 
+def fwd_ab():
+    """Forward kernel timing: query and pipelined-training mode, cfg2 size (B200INR_LIB selects a variant build)."""
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (128, 128, 64)
+    rows = 128 * 128 * 64
+    net = L.make_net(d, H, Lh, C, flags=0)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    stash = torch.zeros(L.stash_bytes(net, rows) + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:]
+    g, nb = ctypes.byref(grid), ctypes.byref(net)
+
+    once = os.environ.get("AB_ONCE") == "1"  # one launch per variant (ncu captures)
+
+    def t(fn, n=10):
+        for _ in range(0 if once else 3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(1 if once else n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (1 if once else n)
+
+    q = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 1, 0.0, None, stream()))
+    f = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()))
+    print(f"fwd_ab: query {q:.3f} ms ({rows * 541696 / q / 1e9:.0f} TF/s)  train fwd {f:.3f} ms "
+          f"({rows * 541696 / f / 1e9:.0f} TF/s)", flush=True)
+
+
 def bwdp_profile():
     """Per-role stall accounting of the pipelined backward (B200INR_BWDP_PROF=1), cfg2 size."""
     import numpy as np
@@ -341,6 +378,8 @@ def piped_vs_staged(d, Lh, C, shape, rows=None):
 if __name__ == "__main__":
     print(lib.b200inr_version().decode(), torch.cuda.get_device_name(0), flush=True)
     which = sys.argv[1:] or ["selftest", "mlp", "timing"]
+    if "fwd_ab" in which:
+        fwd_ab()
     if "selftest" in which:
         selftest()
     if "mlp" in which:
