@@ -88,7 +88,9 @@ const char* b200inr_error_string(int code);
  * Flat fp32 parameter vector in reference units (W, not omega*W), canonical order
  *   W0[H,d] b0[H]  W1[H,H] b1[H] ... WL[H,H] bL[H]  Wf[C,H] bf[C]
  * each segment starting at a multiple of 4 floats.  offsets[2*i], offsets[2*i+1] = start of W_i, b_i;
- * offsets has 2*(L+2) entries.  (nn.Linear weight layout [out,in], INR/SRDWI.py:47.) */
+ * offsets has b200inr_param_offset_count entries: 2*(L+2) here, one more (the frequency matrix B) for
+ * B200INR_IN_FOURIER, and for B200INR_ACT_GABOR 4*(L+1)+2: per Gabor layer W_lin b_lin W_orth b_orth (complex values as
+ * (re, im) pairs), then W_f b_f.  (nn.Linear weight layout [out,in], INR/SRDWI.py:47.) */
 int b200inr_param_count(const b200inr_net* net, int64_t* n_floats);
 int b200inr_param_offsets(const b200inr_net* net, int64_t* offsets);
 
@@ -109,6 +111,17 @@ int b200inr_stash_bytes(const b200inr_net* net, int64_t rows, size_t* bytes);
 int b200inr_siren_forward(const b200inr_net* net, const void* packed, const float* coords,
                           const b200inr_grid* grid, int64_t rows, float* out, int clamp, float clamp_min,
                           void* stash, void* stream);
+
+/* The training forward of the fused fit with the 2x2x1 pooled LR-consistency loss taken in the kernel's final
+ * epilogue: replaces b200inr_siren_forward (stash != NULL) followed by b200inr_pool_mse -- the [rows, C] prediction
+ * never goes to HBM.  target_lr: this slab's LR volume [X/2, Y/2, Z, C]; grad_hr [rows, C] fp32 receives dL/dpred;
+ * loss_accum[0] += this slab's share of the loss; count = global number of LR elements.  Same arithmetic as
+ * b200inr_pool_mse.  Supported for SIREN on raw coordinates with the pipelined backward, a 3-D grid with
+ * 128 % (2 Z) == 0, Y even, (Y Z) % 128 == 0, and a slab of whole x-plane pairs (rows, row_begin multiples of 2 Y Z);
+ * B200INR_ERR_BAD_SHAPE otherwise (call the two-kernel form). */
+int b200inr_siren_forward_pool_loss(const b200inr_net* net, const void* packed, const b200inr_grid* grid, int64_t rows,
+                                    const float* target_lr, double count, float* grad_hr, float* loss_accum,
+                                    void* stash, void* stream);
 
 /* loss.backward() through Siren (autograd of INR/SRDWI.py:58-59,87-91): given dL/dout [rows,C] fp32,
  * ACCUMULATES dL/dparams into grad_params (flat layout above, reference units).  No input gradient
@@ -164,6 +177,25 @@ int b200inr_pool_mse(const float* pred_hr, const float* target_lr, int32_t X, in
  * caller, advanced by the kernel (so the call can be captured in a CUDA graph). */
 int b200inr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, float* state, void* stream);
+
+/* opt.step() + opt.zero_grad() of the reference loop (INR/superresDWI.py:136-138) plus the bf16 re-staging of the
+ * operands, for the fused fit: Adam (same arithmetic as b200inr_adam_step) over the n = b200inr_param_count floats of
+ * `net`, every consumed gradient cleared (grads is all-zero on return, so the next step needs no memset), the step
+ * counter advanced on the device, and `packed` rewritten from the updated parameters.  grads has n + 4 floats: the
+ * loss accumulator of the step rides at grads[n] (see b200inr_mse_loss / b200inr_pool_mse); it is moved to
+ * loss_out[0] (may be NULL) and cleared.  state: 4 floats, zero-initialised by the caller ({step, ticket, -, -}).
+ * ONE launch for SIREN on raw coordinates (every parameter is updated by the thread that packs it), two for the
+ * other families.  Graph-capturable. */
+int b200inr_optimizer_step(const b200inr_net* net, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                           float lr, float beta1, float beta2, float eps, float* state, void* packed,
+                           float* loss_out, void* stream);
+
+/* sizeof(b200inr_net) as this library was compiled: a binding whose struct definition has drifted (fewer fields)
+ * must refuse to call rather than pass a short struct. */
+size_t b200inr_net_size(void);
+/* Number of entries b200inr_param_offsets writes for `net` (2(L+2) for SIREN on raw coordinates / explicit features,
+ * one more for B200INR_IN_FOURIER -- the frequency matrix B --, 4(L+1)+2 for B200INR_ACT_GABOR). */
+int b200inr_param_offset_count(const b200inr_net* net, int32_t* count);
 
 /* ---- coordinate helpers (API parity; the fused kernels do not need them) ------------------------------ */
 /* get_mgrid (INR/SRDWI.py:12-18): coords [rows, ndim] fp32. */

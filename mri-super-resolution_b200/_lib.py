@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200inr_pack_weights": (ctypes.c_int, [_P(Net), _vp, _vp, _vp]),
     "b200inr_stash_bytes": (ctypes.c_int, [_P(Net), _i64, _P(_sz)]),
     "b200inr_siren_forward": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, ctypes.c_int, _f32, _vp, _vp]),
+    "b200inr_siren_forward_pool_loss": (ctypes.c_int, [_P(Net), _vp, _P(Grid), _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "b200inr_siren_backward": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _P(Grid), _i64, _vp, _vp, _vp]),
     "b200inr_siren_backward_input": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200inr_siren_dgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp]),
@@ -70,6 +71,9 @@ SIGNATURES = {
     "b200inr_degrade_adjoint": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "b200inr_pool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp]),
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "b200inr_optimizer_step": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "b200inr_net_size": (_sz, []),
+    "b200inr_param_offset_count": (ctypes.c_int, [_P(Net), _P(_i32)]),
     "b200inr_get_mgrid": (ctypes.c_int, [_P(Grid), _i64, _vp, _vp]),
     "b200inr_input_mapping": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200inr_combinations": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
@@ -94,6 +98,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if lib.b200inr_net_size() != ctypes.sizeof(Net):  # struct drift between this binding and the built library
+        raise RuntimeError(f"b200inr: {LIB_PATH} was built for a {lib.b200inr_net_size()}-byte b200inr_net, this "
+                           f"binding passes {ctypes.sizeof(Net)} bytes - rebuild with __graft_entry__.build()")
     _lib = lib
     return lib
 
@@ -128,11 +135,9 @@ def param_count(net):
 
 
 def param_offsets(net):
-    if net.activation == ACT_GABOR:
-        n = 4 * (net.hidden_layers + 1) + 2
-    else:
-        n = 2 * (net.hidden_layers + 2) + (1 if net.input_mode == IN_FOURIER else 0)
-    off = (_i64 * n)()
+    cnt = _i32(0)
+    check(load().b200inr_param_offset_count(ctypes.byref(net), ctypes.byref(cnt)), "param_offset_count")
+    off = (_i64 * cnt.value)()
     check(load().b200inr_param_offsets(ctypes.byref(net), off), "param_offsets")
     return list(off)
 

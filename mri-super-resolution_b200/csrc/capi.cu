@@ -12,6 +12,10 @@ int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaS
 int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
                      int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                      cudaStream_t stream);
+bool fwd_pool_loss_supported(const b200inr_net* net, const b200inr_grid* grid, int64_t rows);
+int launch_siren_fwd_pool_loss(const b200inr_net* net, const void* packed, const b200inr_grid* grid, int64_t rows,
+                               const float* target_lr, double count, float* grad_out, float* loss_accum, void* stash,
+                               int num_sms, cudaStream_t stream);
 int launch_siren_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
                      int num_sms, cudaStream_t stream);
 int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, const float* coords,
@@ -42,6 +46,9 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
                 const b200inr_axis_taps* ty, cudaStream_t stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float* state, cudaStream_t stream);
+int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
+                          cudaStream_t stream);
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
 int launch_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int n1, int n2,
@@ -215,6 +222,7 @@ int b200inr_siren_forward(const b200inr_net* net, const void* packed, const floa
   if (grid && (e = check_grid(net, grid, rows))) return e;
   if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (stash && (reinterpret_cast<uintptr_t>(stash) & 1023)))
     return B200INR_ERR_BAD_ALIGN;
+  if (net->input_mode == B200INR_IN_FEATURES && !aligned16(coords)) return B200INR_ERR_BAD_ALIGN;  // float4 row loads
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   if (is_wire(net))
@@ -225,6 +233,23 @@ int b200inr_siren_forward(const b200inr_net* net, const void* packed, const floa
                           static_cast<cudaStream_t>(stream));
   return launch_siren_fwd(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, sms,
                           static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_siren_forward_pool_loss(const b200inr_net* net, const void* packed, const b200inr_grid* grid, int64_t rows,
+                                    const float* target_lr, double count, float* grad_hr, float* loss_accum,
+                                    void* stash, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !grid || !target_lr || !grad_hr || !loss_accum || !stash) return B200INR_ERR_NULL;
+  if (rows < 0 || rows > (int64_t(1) << 37) || !(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  if ((e = check_grid(net, grid, rows))) return e;
+  if (!fwd_pool_loss_supported(net, grid, rows)) return B200INR_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  return launch_siren_fwd_pool_loss(net, packed, grid, rows, target_lr, count, grad_hr, loss_accum, stash, sms,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* stash, const float* coords,
@@ -417,6 +442,32 @@ int b200inr_adam_step(float* params, const float* grads, float* exp_avg, float* 
   if (n == 0) return B200INR_OK;
   return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state,
                      static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_optimizer_step(const b200inr_net* net, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                           float lr, float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
+                           void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !packed) return B200INR_ERR_NULL;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(packed) & 1023)) return B200INR_ERR_BAD_ALIGN;
+  int64_t n = 0;
+  if ((e = b200inr_param_count(net, &n))) return e;
+  return launch_optimizer_step(net, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state, packed,
+                               loss_out, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200inr_net_size(void) { return sizeof(b200inr_net); }
+
+int b200inr_param_offset_count(const b200inr_net* net, int32_t* count) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!count) return B200INR_ERR_NULL;
+  if (is_wire(net))
+    *count = 4 * (net->hidden_layers + 1) + 2;
+  else
+    *count = 2 * (net->hidden_layers + 2) + (net->input_mode == B200INR_IN_FOURIER ? 1 : 0);
+  return B200INR_OK;
 }
 
 int b200inr_get_mgrid(const b200inr_grid* grid, int64_t rows, float* coords, void* stream) {

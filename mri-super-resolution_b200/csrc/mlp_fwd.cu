@@ -62,6 +62,13 @@ struct FwdParams {
   float* out;
   int clamp;
   float clamp_min;
+  // fused pooled loss (kLoss): LR target of this slab [X/2, Y/2, Z, C], dL/dpred [rows, C], loss accumulator
+  const float* target_lr;
+  float* grad_out;
+  float* loss_accum;
+  float inv_count;     // 1 / (global number of LR elements)
+  int tiles_per_plane; // Y * Z / 128: tiles of one x-plane (the pooling partner of tile t is tile t + tiles_per_plane)
+  int Z;
   uint8_t* stash_y;   // nullptr => inference
   uint8_t* stash_ph;
   uint8_t* stash_xa;  // coordinate operand of the first-layer weight gradient (wgrad.cu)
@@ -176,8 +183,13 @@ __device__ __forceinline__ void walk_weight_schedule(int num_pairs, int my_tiles
 
 // kMode: 0 = inference, 1 = staged training (sin outputs + phases + coordinate operand), 2 = pipelined training
 // (phases only: mlp_bwdp.cu recomputes sin and cos from them).
-template <int H, int kMode, bool kPair>
+// kLoss (pipelined training only): the 2x2x1 pooled LR-consistency loss of the fit is taken in the final epilogue --
+// the two tiles of a CTA's slot are the two x-planes of one pooling window set, so the prediction never goes to HBM:
+// the kernel writes dL/dpred and accumulates the loss (what b200inr_pool_mse does in a second pass otherwise).
+template <int H, int kMode, bool kLoss>
 __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
+  constexpr bool kPair = true;  // (the 1-CTA schedule was retired; the switch documents what belongs to the pairing)
+  static_assert(!kLoss || kMode == 2, "the fused loss belongs to the pipelined training forward");
   constexpr bool kStash = kMode != 0;  // phases are stored
   constexpr bool kStashY = kMode == 1;  // sin outputs and the coordinate operand are stored too
   using S = FwdSmem<H, kPair>;
@@ -233,7 +245,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   // a pair runs the slot count of its leader (even block index, which never has fewer tiles); the peer's last slot
   // may then be a tile beyond the end: it is computed (clamped coordinates) but nothing of it is stored
   const int lead_block = kPair ? (int(blockIdx.x) & ~1) : int(blockIdx.x);
-  const int my_tiles = (p.num_tiles - lead_block + int(gridDim.x) - 1) / int(gridDim.x);
+  // (fused loss: a CTA walks whole slots of two tiles -- the two x-planes of a pooling window set)
+  const int my_tiles = kLoss ? 2 * ((p.num_tiles / 2 - lead_block + int(gridDim.x) - 1) / int(gridDim.x))
+                             : (p.num_tiles - lead_block + int(gridDim.x) - 1) / int(gridDim.x);
   const int num_pairs = (my_tiles + 1) / 2;
   const bool tr = p.trace != nullptr && blockIdx.x == 0;
   const long long t_begin = tr ? clock64() : 0;
@@ -368,6 +382,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
     const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
     uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
+    float loss_part = 0.f;  // kLoss: this thread's share of sum((pool(pred) - target)^2)
     // ---- first-layer operand of a tile: row r = [x_hi x_hi x_lo x_lo 1 1 0 ...] (bf16, K = 32 of block 0), so that
     //      theta_0 = omega0 (W0 x + b0) comes out of ONE tcgen05.mma against the hi/lo weight operand of pack.cu.
     //      Coordinates are derived from the voxel index (get_mgrid is never materialised).  The four warps with slice
@@ -376,6 +391,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     // (a pair peer whose last slot lies past the end recomputes the LAST tile: identical values stored twice, so the
     //  lock-stepped schedule needs no inactive-tile branches in the hot loops)
     auto tile_of = [&](int pr_, int j) {
+      if (kLoss) {  // slot = (x-plane pair u, tile v inside the plane): tiles (2u, v) and (2u + 1, v)
+        int slot = int(blockIdx.x) + pr_ * int(gridDim.x);
+        if (slot >= p.num_tiles / 2) slot = p.num_tiles / 2 - 1;
+        const int u = slot / p.tiles_per_plane, v = slot - u * p.tiles_per_plane;
+        return (2 * u + j) * p.tiles_per_plane + v;
+      }
       const int t = int(blockIdx.x) + (2 * pr_ + j) * int(gridDim.x);
       return t < p.num_tiles ? t : p.num_tiles - 1;
     };
@@ -508,6 +529,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       const int nt_next = rest < 0 ? 0 : (rest < 2 ? rest : 2);
       float xn[4] = {0.f, 0.f, 0.f, 0.f};
       if (s < nt_next) coords_of(tile_of(pr + 1, s), xn);  // index arithmetic overlaps the wait for the final MMA
+      // fused loss: this thread's (up to) four LR target values of the slot, fetched from HBM now -- a load inside the
+      // loss loop would put four serialised DRAM latencies on every slot
+      float tg[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* tgt = nullptr;
+      if (kLoss) {
+        const int t0 = tile_of(pr, 0);
+        const int u = t0 / (2 * p.tiles_per_plane), v0 = t0 - 2 * u * p.tiles_per_plane;
+        tgt = p.target_lr + ((long long)u * p.tiles_per_plane + v0) * (kTileRows / 2) * p.C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (et + k * kFwdEpiThreads < (kTileRows / 2) * p.C) tg[k] = __ldg(tgt + et + k * kFwdEpiThreads);
+      }
       for (int j = 0; j < nt; ++j) {
         const int tile = tile_of(pr, j);
         const long long row0 = (long long)tile * kTileRows;
@@ -538,6 +571,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         // the tile's accumulator and A blocks 0..2 are free: hand the next pair's first-layer operand to the MMA warp
         // now, so that its layer-0 MMA runs under the copy-out below and under the other tile's final epilogue
         if (j < nt_next) put_operand(tile_of(pr + 1, j), j, xn);
+        if (kLoss) continue;  // both tiles are staged first, see below
         named_bar_sync(kEpiBarId, kFwdEpiThreads);
         long long valid = p.rows - row0;
         if (valid > kTileRows) valid = kTileRows;
@@ -545,8 +579,46 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         float* dst = p.out + row0 * C;
         for (int i = et; i < nout; i += kFwdEpiThreads) dst[i] = __uint_as_float(lds32(stg + uint32_t(i) * 4));
       }
+      if (kLoss) {
+        // ---- fused LR-consistency loss (same arithmetic and association as pool_mse_kernel):
+        //      the slot's tiles are the x-planes 2u and 2u + 1 of one set of 2x2x1 pooling windows, and a tile holds
+        //      whole y pairs (128 % 2Z == 0), so LR voxel v = (y pair, z) of the slot averages tile rows r0, r0 + Z of
+        //      both staged tiles.  The 64 x C LR values and the four dL/dpred blocks are contiguous in memory.
+        named_bar_sync(kEpiBarId, kFwdEpiThreads);
+        const int C = p.C, Z = p.Z;
+        const int t0 = tile_of(pr, 0), t1 = tile_of(pr, 1);
+        const bool dup = int(blockIdx.x) + pr * int(gridDim.x) >= p.num_tiles / 2;  // pair peer past the end
+        float* g0 = p.grad_out + (long long)t0 * kTileRows * C;
+        float* g1 = p.grad_out + (long long)t1 * kTileRows * C;
+        const uint32_t s0 = smem_u32(a_smem) + 3 * S::kABlock, s1 = s0 + S::kABytes;
+        const float gsc = 0.5f * p.inv_count;
+#pragma unroll
+        for (int k = 0; k < ((B200INR_FKO & 16) ? 0 : 4); ++k) {
+          const int e = et + k * kFwdEpiThreads;
+          if (e >= (kTileRows / 2) * C) break;
+          const int v = e / C, c = e - v * C;
+          const int yy = v / Z, z = v - yy * Z;
+          const uint32_t r0 = uint32_t((2 * yy * Z + z) * C + c) * 4, r1 = r0 + uint32_t(Z * C) * 4;
+          const float a = __uint_as_float(lds32(s0 + r0)), b = __uint_as_float(lds32(s0 + r1));
+          const float cc = __uint_as_float(lds32(s1 + r0)), d = __uint_as_float(lds32(s1 + r1));
+          const float res = 0.25f * ((a + b) + (cc + d)) - tg[k];
+          if (!dup) loss_part = fmaf(res, res, loss_part);
+          const float g = gsc * res;
+          if (!(B200INR_FKO & 32) || g == 123.f) {
+            g0[r0 >> 2] = g;
+            g0[r1 >> 2] = g;
+            g1[r0 >> 2] = g;
+            g1[r1 >> 2] = g;
+          }
+        }
+      }
       // every warp has copied its share out of the staging blocks before any warp's next-pair epilogue overwrites them
       named_bar_sync(kEpiBarId, kFwdEpiThreads);
+    }
+    if (kLoss) {  // one atomic per warp for the whole kernel
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+      if (lane == 0) atomicAdd(p.loss_accum, loss_part * p.inv_count);
     }
   }
 
@@ -561,10 +633,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
 }
 
 // ------------------------------------------------------------------ launcher
-template <int H, int kMode, bool kPair>
+template <int H, int kMode, bool kLoss>
 static int launch_fwd_variant(const FwdParams& p, int grid_x, cudaStream_t stream) {
+  constexpr bool kPair = true;
   const int smem = FwdSmem<H, kPair>::kBytes + 1024;
-  auto kern = siren_fwd_kernel<H, kMode, kPair>;
+  auto kern = siren_fwd_kernel<H, kMode, kLoss>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
   cudaLaunchConfig_t cfg{};
@@ -583,9 +656,27 @@ static int launch_fwd_variant(const FwdParams& p, int grid_x, cudaStream_t strea
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
-int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
-                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
-                     cudaStream_t stream) {
+// loss != nullptr: the training forward with the pooled LR-consistency loss fused into its final epilogue
+// (b200inr_siren_forward_pool_loss); the caller has checked the geometry (fwd_pool_loss_supported).
+struct FwdLossArgs {
+  const float* target_lr;
+  float* grad_out;
+  float* loss_accum;
+  double count;
+};
+
+bool fwd_pool_loss_supported(const b200inr_net* net, const b200inr_grid* grid, int64_t rows) {
+  if (net->input_mode != B200INR_IN_COORDS || net->activation != B200INR_ACT_SINE) return false;
+  if ((net->flags & B200INR_NET_STAGED_BWD) != 0 || grid == nullptr || grid->ndim != 3) return false;
+  const long long Y = grid->shape[1], Z = grid->shape[2];
+  if (Z < 1 || (kTileRows % (2 * Z)) != 0 || (Y & 1) || ((Y * Z) % kTileRows) != 0) return false;
+  const long long pair_rows = 2 * Y * Z;  // a slab of whole x-plane pairs, starting on one
+  return rows > 0 && rows % pair_rows == 0 && grid->row_begin % pair_rows == 0;
+}
+
+static int launch_siren_fwd_impl(const b200inr_net* net, const void* packed, const float* coords,
+                                 const b200inr_grid* grid, int64_t rows, float* out, int clamp, float clamp_min,
+                                 void* stash, int num_sms, cudaStream_t stream, const FwdLossArgs* loss) {
   constexpr int H = 256;
   FwdParams p{};
   p.packed = reinterpret_cast<const uint8_t*>(packed);
@@ -637,9 +728,33 @@ int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* co
   const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
   if (cap > 0 && cap < grid_x) grid_x = cap;
   grid_x = grid_x < 2 ? 2 : (grid_x & ~1);
-  if (!stash) return launch_fwd_variant<H, 0, true>(p, grid_x, stream);
-  if (staged) return launch_fwd_variant<H, 1, true>(p, grid_x, stream);
-  return launch_fwd_variant<H, 2, true>(p, grid_x, stream);
+  if (loss != nullptr) {
+    p.target_lr = loss->target_lr;
+    p.grad_out = loss->grad_out;
+    p.loss_accum = loss->loss_accum;
+    p.inv_count = float(1.0 / loss->count);
+    p.tiles_per_plane = int((long long)grid->shape[1] * grid->shape[2] / kTileRows);
+    p.Z = grid->shape[2];
+    int g = p.num_tiles / 2 < num_sms ? p.num_tiles / 2 : num_sms;  // one slot = two tiles
+    g = g < 2 ? 2 : (g & ~1);
+    return launch_fwd_variant<H, 2, true>(p, g, stream);
+  }
+  if (!stash) return launch_fwd_variant<H, 0, false>(p, grid_x, stream);
+  if (staged) return launch_fwd_variant<H, 1, false>(p, grid_x, stream);
+  return launch_fwd_variant<H, 2, false>(p, grid_x, stream);
+}
+
+int launch_siren_fwd_pool_loss(const b200inr_net* net, const void* packed, const b200inr_grid* grid, int64_t rows,
+                               const float* target_lr, double count, float* grad_out, float* loss_accum, void* stash,
+                               int num_sms, cudaStream_t stream) {
+  FwdLossArgs la{target_lr, grad_out, loss_accum, count};
+  return launch_siren_fwd_impl(net, packed, nullptr, grid, rows, nullptr, 0, 0.f, stash, num_sms, stream, &la);
+}
+
+int launch_siren_fwd(const b200inr_net* net, const void* packed, const float* coords, const b200inr_grid* grid,
+                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
+                     cudaStream_t stream) {
+  return launch_siren_fwd_impl(net, packed, coords, grid, rows, out, clamp, clamp_min, stash, num_sms, stream, nullptr);
 }
 
 }  // namespace b200inr

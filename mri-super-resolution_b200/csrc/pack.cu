@@ -95,6 +95,163 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------ fused optimiser step (raw-coordinate SIREN)
+// ONE launch for what the reference does with opt.step() + opt.zero_grad() (INR/superresDWI.py:136-138) plus the
+// bf16 re-staging of the operands: the thread that would pack parameter i first applies Adam to it (same arithmetic
+// as adam_kernel in elementwise.cu, torch.optim.Adam defaults), clears its gradient for the next step, and writes
+// the updated value into every operand buffer it belongs to.  Each parameter is visited by exactly one thread.
+// The step counter is advanced by the last block to finish (ticket), so the launch is graph-capturable and there is
+// no separate zero / tick / pack kernel (4 launches -> 1: the launch-latency regime of cfg1 and of strong-scaled
+// shards).  The loss accumulator that rides behind the gradients is moved to loss_out and cleared as well.
+struct AdamArgs {
+  float* params;
+  float* grads;
+  float* m;
+  float* v;
+  float* state;     // {step, ticket (u32), -, -}
+  float* loss_out;  // nullptr, or receives grads[n] (the step's loss) before it is cleared
+  long long n;
+  float lr, beta1, beta2, eps;
+};
+
+struct AdamCoef {
+  float step_size, bc2_sqrt, omb1, omb2, beta2, eps;
+};
+
+__device__ __forceinline__ AdamCoef adam_coefficients(const AdamArgs& a, float* s_tmp /* 2 shared floats */) {
+  if (threadIdx.x == 0) {
+    const double step = double(a.state[0]) + 1.0;
+    const double bc1 = 1.0 - pow(double(a.beta1), step);
+    const double bc2 = 1.0 - pow(double(a.beta2), step);
+    s_tmp[0] = float(double(a.lr) / bc1);
+    s_tmp[1] = float(sqrt(bc2));
+  }
+  __syncthreads();
+  AdamCoef c;
+  c.step_size = s_tmp[0];
+  c.bc2_sqrt = s_tmp[1];
+  c.omb1 = 1.f - a.beta1;
+  c.omb2 = 1.f - a.beta2;
+  c.beta2 = a.beta2;
+  c.eps = a.eps;
+  return c;
+}
+
+__device__ __forceinline__ float adam_apply(const AdamArgs& a, const AdamCoef& c, long long i) {
+  const float gi = a.grads[i];
+  float mi = a.m[i], vi = a.v[i];
+  mi = fmaf(gi - mi, c.omb1, mi);
+  vi = fmaf(c.omb2 * gi, gi, c.beta2 * vi);
+  const float denom = __fsqrt_rn(vi) / c.bc2_sqrt + c.eps;
+  const float pi = a.params[i] - c.step_size * (mi / denom);
+  a.m[i] = mi;
+  a.v[i] = vi;
+  a.params[i] = pi;
+  a.grads[i] = 0.f;
+  return pi;
+}
+
+// last block out: advance the step counter, move the loss, reset the ticket
+__device__ __forceinline__ void adam_finish(const AdamArgs& a) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(a.state + 1);
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    a.state[0] += 1.f;
+    *reinterpret_cast<unsigned int*>(a.state + 1) = 0u;
+    if (a.loss_out != nullptr) a.loss_out[0] = a.grads[a.n];
+    a.grads[a.n] = 0.f;
+  }
+}
+
+// Work items (one per thread, so that every thread's load -> update -> store chain is a single short one and the
+// whole kernel is one wave of independent chains): [0, 32 H) first layer, one warp per output feature (lanes = the 32
+// live columns of the hi/lo operand row; lanes j < d own W0[o][j], lane 16 owns b0[o], the values travel by shuffle);
+// then L H^2 hidden weights, 64 H final-linear entries, L H + 32 remaining biases.  H = kSirenWidth (operand width).
+constexpr int kAdamPackThreads = 256;
+__host__ __device__ inline long long siren_adam_pack_items(int L) {
+  constexpr long long H = kSirenWidth;
+  return 32 * H + (long long)L * H * H + kDzoPad * H + (long long)L * H + 32;
+}
+
+__global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const PackParams p, const AdamArgs a) {
+  __shared__ float s_coef[2];
+  const AdamCoef c = adam_coefficients(a, s_coef);
+  constexpr int H = kSirenWidth;
+  const int L = p.L, C = p.C, d = p.d, Hr = p.Hr;
+  float* bias = reinterpret_cast<float*>(p.packed + p.pl.bias);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+
+  if (i < 32 * H) {
+    // ---- first layer: row o of the float4 table, of the hi/lo tensor-core operand and of the bias table
+    const int o = int(i >> 5), k = int(i & 31);
+    float mine = 0.f;
+    if (o < Hr) {
+      if (k < d) mine = p.omega0 * adam_apply(a, c, p.off[0] + (long long)o * d + k);
+      if (k == 16) mine = p.omega0 * adam_apply(a, c, p.off[1] + o);
+    }
+    const float wj = __shfl_sync(0xffffffffu, mine, k & 3);
+    const float b = __shfl_sync(0xffffffffu, mine, 16);
+    const float w0 = __shfl_sync(0xffffffffu, mine, 0), w1 = __shfl_sync(0xffffffffu, mine, 1);
+    const float w2 = __shfl_sync(0xffffffffu, mine, 2), w3 = __shfl_sync(0xffffffffu, mine, 3);
+    if (k == 0) {
+      reinterpret_cast<float4*>(p.packed + p.pl.w0)[o] = make_float4(w0, w1, w2, w3);
+      bias[o] = b;
+    }
+    float v = 0.f;  // columns 4g + j (g = 0..3: hi lo hi lo), 16 = b_hi, 17 = b_lo, the rest zero (32..63 stay zero)
+    if (k < 16) {
+      const float hi = __bfloat162float(__float2bfloat16_rn(wj));
+      v = ((k >> 2) & 1) ? (wj - hi) : hi;
+    } else if (k < 18) {
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      v = (k == 17) ? (b - hi) : hi;
+    }
+    put_bf16(p.packed + p.pl.w0p, uint32_t(o), uint32_t(k), v);
+  } else if ((i -= 32 * H) < (long long)L * H * H) {
+    // ---- hidden layers, both orientations
+    const int l = int(i >> 16), o = int(i >> 8) & (H - 1), k = int(i) & (H - 1);
+    static_assert(H == 256, "index arithmetic above");
+    const float v = (o < Hr && k < Hr) ? p.omegah * adam_apply(a, c, p.off[2 * (l + 1)] + (long long)o * Hr + k) : 0.f;
+    uint8_t* wh = p.packed + p.pl.wh + size_t(l) * H * H * 2;
+    uint8_t* wht = p.packed + p.pl.wht + size_t(l) * H * H * 2;
+    put_bf16(wh + size_t(k >> 6) * H * 128, o, k & 63, v);   // forward: N = out, K = in
+    put_bf16(wht + size_t(o >> 6) * H * 128, k, o & 63, v);  // dgrad:   N = in,  K = out
+  } else if ((i -= (long long)L * H * H) < kDzoPad * H) {
+    // ---- final linear: forward operand [H/64][32][64] (rows >= C zero) and dgrad operand [H][64] (N = in, K = c)
+    const int cc = int(i >> 8), k = int(i) & (H - 1);
+    const float v = (cc < C && k < Hr) ? adam_apply(a, c, p.off[2 * (L + 1)] + (long long)cc * Hr + k) : 0.f;
+    if (cc < kOutPad) put_bf16(p.packed + p.pl.wf + size_t(k >> 6) * kOutPad * 128, cc, k & 63, v);
+    put_bf16(p.packed + p.pl.wft, k, cc, v);
+  } else if ((i -= kDzoPad * H) < (long long)L * H + 32) {
+    // ---- biases of the hidden sine layers, then the final bias (padded to 32)
+    float v = 0.f;
+    if (i < (long long)L * H) {
+      const int l = int(i >> 8) + 1, h = int(i) & (H - 1);
+      if (h < Hr) v = p.omegah * adam_apply(a, c, p.off[2 * l + 1] + h);
+    } else {
+      const int cc = int(i - (long long)L * H);
+      if (cc < C) v = adam_apply(a, c, p.off[2 * (L + 1) + 1] + cc);
+    }
+    bias[H + i] = v;
+  }
+  adam_finish(a);
+}
+
+// The other families: Adam + gradient clearing + step counter in one launch (the packing stays a second one).
+__global__ void __launch_bounds__(256) adam_zero_kernel(const AdamArgs a) {
+  __shared__ float s_coef[2];
+  const AdamCoef c = adam_coefficients(a, s_coef);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += stride) adam_apply(a, c, i);
+  adam_finish(a);
+}
+
 // ------------------------------------------------------------------ generic family (see common.cuh)
 struct GenPackParams {
   const float* params;
@@ -197,5 +354,40 @@ int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaS
   pack_kernel<<<296, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
+
+int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream);  // wire.cu
+
+int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
+                          cudaStream_t stream) {
+  AdamArgs a{params, grads, m, v, state, loss_out, (long long)n, lr, beta1, beta2, eps};
+  if (net->input_mode == B200INR_IN_COORDS && net->activation == B200INR_ACT_SINE) {
+    PackParams p{};
+    p.params = params;
+    p.packed = reinterpret_cast<uint8_t*>(packed);
+    p.d = net->in_features;
+    p.H = kSirenWidth;
+    p.Hr = net->hidden_features;
+    p.L = net->hidden_layers;
+    p.C = net->out_features;
+    p.omega0 = net->first_omega_0;
+    p.omegah = net->hidden_omega_0;
+    p.pl = make_pack_layout(p.H, p.L);
+    int64_t off[2 * (kMaxSineLayers + 1)];
+    param_offsets(p.d, p.Hr, p.L, p.C, off);
+    for (int i = 0; i < 2 * (p.L + 2); ++i) p.off[i] = off[i];
+    const long long items = siren_adam_pack_items(p.L);
+    siren_adam_pack_kernel<<<int((items + kAdamPackThreads - 1) / kAdamPackThreads), kAdamPackThreads, 0, stream>>>(p, a);
+    return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+  }
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  adam_zero_kernel<<<int(blocks), 256, 0, stream>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return B200INR_ERR_CUDA;
+  if (net->activation == B200INR_ACT_GABOR) return launch_wire_pack(net, params, packed, stream);
+  return launch_pack(net, params, packed, stream);
+}
+
 
 }  // namespace b200inr

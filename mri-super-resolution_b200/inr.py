@@ -636,12 +636,13 @@ class FitSession:
     """Device-resident state of one fused fit (buffers, Adam moments, activation stash) and its step function.
 
     step() issues, on the current stream and without host synchronisation:
-        zero [grad | loss] -> fused forward (stash) -> loss / degradation + dL/dpred -> dgrad -> wgrad
-        -> [all-reduce of the flat [grad | loss] buffer] -> Adam -> bf16 re-staging of the weights
+        fused forward (stash) -> loss / degradation + dL/dpred -> dgrad -> wgrad
+        -> [all-reduce of the flat [grad | loss] buffer] -> optimiser step (Adam + gradient clearing + step counter +
+        bf16 re-staging of the weights: b200inr_optimizer_step, one launch for raw-coordinate SIRENs)
     `marks`, when given, receives a CUDA event after every stage (used by bench.py for per-kernel timing).
     """
 
-    STAGES = ("zero", "forward", "loss", "dgrad", "wgrad", "allreduce", "adam", "pack")
+    STAGES = ("forward", "loss", "dgrad", "wgrad", "allreduce", "optimizer")
 
     def __init__(self, module, target, shape, lr=1e-4, degrade=None, betas=(0.9, 0.999), eps=1e-8, row_range=None,
                  global_count=None, process_group=None, reset_optimizer=False, weight=None):
@@ -711,8 +712,10 @@ class FitSession:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.process_group = process_group
         self.n_flat = eng["flat"].numel()
-        self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)  # [grad ..., loss, pad]
-        self.loss = self.grads[self.n_flat:self.n_flat + 1]
+        # [grad ..., loss accumulator, pad]: cleared once here, then by every optimiser step (no per-step memset)
+        self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)
+        self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)  # the last finished step's loss
         self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.dpred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.stash = _aligned_bytes(_lib.stash_bytes(module._desc, rows), dev)
@@ -721,13 +724,26 @@ class FitSession:
         # bracket that kernel and nothing, respectively)
         self.piped = (d.activation == _lib.ACT_SINE and d.input_mode == _lib.IN_COORDS
                       and not (d.flags & _lib.NET_STAGED_BWD))
-        # forward, loss, backward (dgrad + wgrad when staged), adam, adam_tick, pack
-        self.kernel_launches_per_step = 6 if self.piped else 7
+        # Pooled loss fused into the forward's final epilogue (b200inr_siren_forward_pool_loss): possible when a 128-row
+        # tile holds whole y pairs and its pooling partner is a whole tile away.  Opt-in (B200INR_FUSED_LOSS=1): it
+        # removes one launch and 260 MB of HBM traffic per cfg2 step, but measured on B200 it is a tie (0.754 ms vs
+        # 0.706 + 0.049 ms) -- the epilogue warps are the forward's critical resource and, unlike the plain copy-out,
+        # the loss arithmetic does not hide under their waits for the final MMAs.
+        self.fused_loss = False
+        if degrade == "pool" and self.piped and os.environ.get("B200INR_FUSED_LOSS", "0") == "1":
+            Y, Z = shape[1], shape[2]
+            self.fused_loss = (128 % (2 * Z) == 0 and (Y * Z) % 128 == 0 and rows % (2 * Y * Z) == 0
+                               and begin % (2 * Y * Z) == 0)
+        # forward, loss (3 kernels for blur_pool), backward (dgrad + wgrad when staged), optimiser step (+ pack kernel
+        # for the families whose operands are re-staged by a second launch)
+        self.kernel_launches_per_step = (1 + (3 if degrade == "blur_pool" else (0 if self.fused_loss else 1)) +
+                                         (1 if self.piped else 2) +
+                                         (1 if (d.activation == _lib.ACT_SINE and d.input_mode == _lib.IN_COORDS) else 2))
         self._graph = None
         self._copy_stream = None
 
     def capture(self):
-        """Capture one step (memset + 7 kernels, all stream-ordered, Adam's step counter on the device) into a CUDA
+        """Capture one step (every kernel is stream-ordered, Adam's step counter lives on the device) into a CUDA
         graph; later step() calls replay it.  Not used with a process group (the all-reduce stays eager)."""
         if self.process_group is not None:
             raise RuntimeError("b200inr: graph capture of a multi-GPU step is not supported")
@@ -786,23 +802,28 @@ class FitSession:
         with torch.cuda.device(self.device), torch.no_grad():
             s = _stream()
             mark()
-            self.grads.zero_()
+            if self.fused_loss:  # forward + pooled loss + dL/dpred in one kernel: the prediction stays on chip
+                _lib.check(lib.b200inr_siren_forward_pool_loss(net, _ptr(eng["packed"]), gref, rows, _ptr(self.target),
+                                                               self.count, _ptr(self.dpred), _ptr(self.loss_acc),
+                                                               _ptr(self.stash), s), "siren_forward_pool_loss")
+            else:
+                _lib.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, gref, rows, _ptr(self.pred), 0,
+                                                     0.0, _ptr(self.stash), s), "siren_forward")
             mark()
-            _lib.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, gref, rows, _ptr(self.pred), 0, 0.0,
-                                                 _ptr(self.stash), s), "siren_forward")
-            mark()
-            if self.degrade is None:
+            if self.fused_loss:
+                pass
+            elif self.degrade is None:
                 _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C,
-                                                self.count, _ptr(self.dpred), _ptr(self.loss), s), "mse_loss")
+                                                self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "mse_loss")
             elif self.degrade == "pool":
                 _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
-                                                self.count, _ptr(self.dpred), _ptr(self.loss), s), "pool_mse")
+                                                self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")
             else:  # D pred -> MSE against the LR target -> D^T
                 (fx, ax), (fy, ay) = self.taps
                 _lib.check(lib.b200inr_degrade_forward(_ptr(self.pred), _ptr(self.lr_pred), self.X, self.Y, self.ZC,
                                                        _ptr(fx), _ptr(fy), s), "degrade_forward")
                 _lib.check(lib.b200inr_mse_loss(_ptr(self.lr_pred), _ptr(self.target), None, self.lr_pred.numel(),
-                                                self.count, _ptr(self.lr_grad), _ptr(self.loss), s), "mse_loss")
+                                                self.count, _ptr(self.lr_grad), _ptr(self.loss_acc), s), "mse_loss")
                 _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
                                                        _ptr(ax), _ptr(ay), s), "degrade_adjoint")
             mark()
@@ -820,11 +841,10 @@ class FitSession:
             if self.process_group is not None:
                 torch.distributed.all_reduce(self.grads, group=self.process_group)
             mark()
-            _lib.check(lib.b200inr_adam_step(_ptr(eng["flat"]), _ptr(self.grads), _ptr(self.opt["m"]),
-                                             _ptr(self.opt["v"]), self.n_flat, self.lr, self.betas[0], self.betas[1],
-                                             self.eps, _ptr(self.opt["state"]), s), "adam_step")
-            mark()
-            _lib.check(lib.b200inr_pack_weights(net, _ptr(eng["flat"]), _ptr(eng["packed"]), s), "pack_weights")
+            _lib.check(lib.b200inr_optimizer_step(net, _ptr(eng["flat"]), _ptr(self.grads), _ptr(self.opt["m"]),
+                                                  _ptr(self.opt["v"]), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                  _ptr(self.opt["state"]), _ptr(eng["packed"]), _ptr(self.loss), s),
+                       "optimizer_step")
             mark()
         return self.loss
 

@@ -923,3 +923,111 @@ def test_weighted_fit_vs_oracle(dev):
     with pytest.raises(RuntimeError):
         m.fit(torch.zeros(16 * 16 * 8 * C // 4, device=dev), (16, 16, 8), steps=1, degrade="pool",
               weight=torch.ones(16 * 16 * 8, C, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------ fused fit stages
+@pytest.mark.parametrize("shape,row_range", [((4, 8, 64), None), ((4, 16, 16), None), ((16, 8, 64), (4096, 8192)),
+                                             ((6, 32, 4), (0, 512))])
+def test_forward_with_fused_pool_loss_equals_two_kernels(dev, shape, row_range):
+    """b200inr_siren_forward_pool_loss (pooled LR-consistency loss in the forward's final epilogue, the prediction
+    never written) == b200inr_siren_forward + b200inr_pool_mse: dL/dpred bit for bit (same pooling arithmetic on the
+    same outputs), the loss to fp32 summation order, and the phase stash it leaves for the backward."""
+    C = 31
+    torch.manual_seed(3)
+    m = b200inr.Siren(3, 256, 4, C).to(dev)
+    eng = m._sync_params()
+    total = int(np.prod(shape))
+    b, e = (0, total) if row_range is None else row_range
+    rows = e - b
+    X, Y, Z = (rows // (shape[1] * shape[2]), shape[1], shape[2])
+    grid = L.make_grid(shape, b)
+    tgt = torch.rand(rows * C // 4, device=dev)
+    count = float(total * C // 4)
+    lib, net = L.load(), ctypes.byref(m._desc)
+    nst = L.stash_bytes(m._desc, rows)
+    st = [b200inr.inr._aligned_bytes(nst, dev) for _ in range(2)]
+    pred = torch.empty(rows, C, device=dev)
+    g_ref, g_fused = torch.zeros(rows, C, device=dev), torch.full((rows, C), 7.0, device=dev)
+    loss = torch.zeros(2, device=dev)
+    L.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, ctypes.byref(grid), rows, _ptr(pred), 0, 0.0,
+                                      _ptr(st[0]), _stream()), "fwd")
+    L.check(lib.b200inr_pool_mse(_ptr(pred), _ptr(tgt), X, Y, Z * C, count, _ptr(g_ref), _ptr(loss[0:1]), _stream()), "pool")
+    L.check(lib.b200inr_siren_forward_pool_loss(net, _ptr(eng["packed"]), ctypes.byref(grid), rows, _ptr(tgt), count,
+                                                _ptr(g_fused), _ptr(loss[1:2]), _ptr(st[1]), _stream()), "fused")
+    torch.cuda.synchronize()
+    assert torch.equal(g_fused, g_ref)
+    assert abs(loss[1].item() - loss[0].item()) <= 1e-5 * abs(loss[0].item())
+    t = (rows + 127) // 128
+    n_ph = 5 * t * 67584
+    assert torch.equal(st[1][:n_ph].view(-1, 1056)[:, :1024], st[0][:n_ph].view(-1, 1056)[:, :1024])
+    xa0 = (n_ph + 1023) // 1024 * 1024
+    assert torch.equal(st[1][xa0:xa0 + t * 2048], st[0][xa0:xa0 + t * 2048])
+
+
+def test_fused_pool_loss_rejects_unsupported_geometry(dev):
+    """Z = 24 (a tile would split y pairs) and a staged-backward network fall back to the two-kernel form:
+    the C ABI says BAD_SHAPE, FitSession does not select the fused kernel."""
+    m = b200inr.Siren(3, 256, 4, 31).to(dev)
+    eng = m._sync_params()
+    shape = (4, 8, 24)
+    rows = int(np.prod(shape))
+    grid = L.make_grid(shape)
+    buf = torch.zeros(rows * 31, device=dev)
+    st = b200inr.inr._aligned_bytes(L.stash_bytes(m._desc, rows), dev)
+    rc = L.load().b200inr_siren_forward_pool_loss(ctypes.byref(m._desc), _ptr(eng["packed"]), ctypes.byref(grid), rows,
+                                                  _ptr(buf), 1.0, _ptr(buf), _ptr(buf), _ptr(st), _stream())
+    assert rc == -1
+    os.environ["B200INR_FUSED_LOSS"] = "1"
+    try:
+        sess = b200inr.inr.FitSession(m, torch.zeros(rows * 31 // 4, device=dev), shape, degrade="pool")
+        assert not sess.fused_loss
+        ok = b200inr.inr.FitSession(m, torch.zeros(4 * 8 * 64 * 31 // 4, device=dev), (4, 8, 64), degrade="pool")
+        assert ok.fused_loss
+        l_fused = [ok.step().item() for _ in range(3)]
+    finally:
+        del os.environ["B200INR_FUSED_LOSS"]
+    torch.manual_seed(0)
+    assert all(np.isfinite(l_fused)) and l_fused[2] <= l_fused[0]
+
+
+@pytest.mark.parametrize("kind", ["siren", "siren_narrow", "fourier", "wire"])
+def test_optimizer_step_equals_adam_then_pack(dev, kind):
+    """b200inr_optimizer_step (Adam + gradient clearing + device step counter + bf16 re-staging; one launch for
+    raw-coordinate SIRENs) == b200inr_adam_step followed by b200inr_pack_weights, bit for bit, over several steps;
+    the loss accumulator behind the gradients is moved out and cleared."""
+    torch.manual_seed(9)
+    if kind == "siren":
+        m = b200inr.Siren(3, 256, 4, 31)
+    elif kind == "siren_narrow":
+        m = b200inr.Siren(2, 64, 2, 1)
+    elif kind == "fourier":
+        m = b200inr.FourierMLP(3, 128, 256, 2, 5, np.random.RandomState(0).normal(size=(128, 3)), activation="relu")
+    else:
+        m = b200inr.Wire(3, 128, 2, 4, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2)
+    m = m.to(dev)
+    eng = m._sync_params()
+    lib, net = L.load(), ctypes.byref(m._desc)
+    n = eng["flat"].numel()
+    p_a, p_b = eng["flat"].clone(), eng["flat"].clone()
+    pk_a, pk_b = eng["packed"].clone(), torch.zeros_like(eng["packed"])
+    pk_a = b200inr.inr._aligned_bytes(pk_a.numel(), dev); pk_b = b200inr.inr._aligned_bytes(pk_a.numel(), dev)
+    m_a, v_a, m_b, v_b = (torch.zeros(n, device=dev) for _ in range(4))
+    s_a, s_b = torch.zeros(4, device=dev), torch.zeros(4, device=dev)
+    loss_out = torch.zeros(1, device=dev)
+    live = torch.zeros(n + 4, device=dev)  # the flat layout pads every segment to 4 floats: no gradient ever lands there
+    for o, prm in zip(eng["offsets"], m._canonical()):
+        live[o:o + prm.numel() * (2 if prm.is_complex() else 1)] = 1.0
+    live[n] = 1.0  # the loss accumulator
+    for step in range(3):
+        g = torch.randn(n + 4, device=dev) * 1e-3 * live
+        g_b = g.clone()
+        L.check(lib.b200inr_adam_step(_ptr(p_a), _ptr(g), _ptr(m_a), _ptr(v_a), n, 1e-4, 0.9, 0.999, 1e-8, _ptr(s_a),
+                                      _stream()), "adam")
+        L.check(lib.b200inr_pack_weights(net, _ptr(p_a), _ptr(pk_a), _stream()), "pack")
+        L.check(lib.b200inr_optimizer_step(net, _ptr(p_b), _ptr(g_b), _ptr(m_b), _ptr(v_b), 1e-4, 0.9, 0.999, 1e-8,
+                                           _ptr(s_b), _ptr(pk_b), _ptr(loss_out), _stream()), "optimizer_step")
+        torch.cuda.synchronize()
+        assert torch.equal(p_a, p_b) and torch.equal(m_a, m_b) and torch.equal(v_a, v_b)
+        assert torch.equal(pk_a, pk_b)
+        assert float(s_b[0]) == step + 1
+        assert loss_out.item() == g[n].item() and not g_b[:n + 1].any()

@@ -213,6 +213,26 @@ def fwd_ab():
     f = t(lambda: lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()))
     print(f"fwd_ab: query {q:.3f} ms ({rows * 541696 / q / 1e9:.0f} TF/s)  train fwd {f:.3f} ms "
           f"({rows * 541696 / f / 1e9:.0f} TF/s)", flush=True)
+    tgt = torch.rand(rows * C // 4, device=dev)
+    gout = torch.zeros(rows, C, device=dev)
+    acc = torch.zeros(4, device=dev)
+    cnt = float(rows * C // 4)
+
+    def two():
+        lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream())
+        return lib.b200inr_pool_mse(ptr(out), ptr(tgt), shape[0], shape[1], shape[2] * C, cnt, ptr(gout), ptr(acc), stream())
+
+    t2 = t(two)
+    tf = t(lambda: lib.b200inr_siren_forward_pool_loss(nb, ptr(pk), g, rows, ptr(tgt), cnt, ptr(gout), ptr(acc), ptr(st),
+                                                       stream()))
+    tl = t(lambda: lib.b200inr_pool_mse(ptr(out), ptr(tgt), shape[0], shape[1], shape[2] * C, cnt, ptr(gout), ptr(acc), stream()))
+    print(f"fwd_ab: train fwd + pool_mse {t2:.3f} ms (pool_mse alone {tl:.3f})   fused forward+loss {tf:.3f} ms", flush=True)
+    n = flat.numel()
+    gr = torch.zeros(n + 4, device=dev)
+    m1, v1, state = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(4, device=dev)
+    to = t(lambda: lib.b200inr_optimizer_step(nb, ptr(flat), ptr(gr), ptr(m1), ptr(v1), 1e-4, 0.9, 0.999, 1e-8, ptr(state),
+                                              ptr(pk), None, stream()), n=20)
+    print(f"fwd_ab: optimizer_step {to * 1e3:.1f} us", flush=True)
 
 
 def bwdp_profile():
