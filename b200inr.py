@@ -10,9 +10,10 @@ _pkg = importlib.import_module("mri-super-resolution_b200")
 inr = importlib.import_module("mri-super-resolution_b200.inr")
 SRDWI = importlib.import_module("mri-super-resolution_b200.SRDWI")
 INRmodel = importlib.import_module("mri-super-resolution_b200.INRmodel")
+nn_mri = importlib.import_module("mri-super-resolution_b200.nn_mri")
 phantom = importlib.import_module("mri-super-resolution_b200.phantom")
 parallel = importlib.import_module("mri-super-resolution_b200.parallel")
 _lib = importlib.import_module("mri-super-resolution_b200._lib")
 from_pkg = _pkg.__all__
 globals().update({k: getattr(_pkg, k) for k in from_pkg})
-__all__ = list(from_pkg) + ["inr", "SRDWI", "INRmodel", "phantom", "parallel"]
+__all__ = list(from_pkg) + ["inr", "SRDWI", "INRmodel", "nn_mri", "phantom", "parallel"]

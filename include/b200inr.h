@@ -208,6 +208,11 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
 int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,
                                    int32_t m, float* grad_x, void* stream);
 
+/* The pre-activation returned by SineLayer.forward_with_intermediate (INR/SRDWI.py:61-64) for a coordinate-fed layer:
+ * out [rows, H] = omega * (x [rows, d] W[H, d]^T + b[H]), fp32, d <= 8. */
+int b200inr_sine_layer_pre(const float* x, const float* W, const float* b, int64_t rows, int32_t d, int32_t H,
+                           float omega, float* out, void* stream);
+
 /* calculate_ADC (INR/SRDWI.py:118-130), the step right after the query: per voxel the least-squares line through
  * (b_k / 1000, log(signal_k + 1e-7)); adc[v] = -slope clamped to [-10, 3].  signal [voxels, nb] fp32 on the device
  * (e.g. the [rows, C] output of b200inr_siren_forward, nb = C), bvalues_host [nb] on the HOST (2 <= nb <= 64, not all

@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200inr_param_offset_count": (ctypes.c_int, [_P(Net), _P(_i32)]),
     "b200inr_get_mgrid": (ctypes.c_int, [_P(Grid), _i64, _vp, _vp]),
     "b200inr_input_mapping": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "b200inr_sine_layer_pre": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp]),
     "b200inr_combinations": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "b200inr_adc_fit": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "b200inr_input_mapping_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -49,6 +49,8 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
 int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
                           float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
                           cudaStream_t stream);
+int launch_sine_pre(const float* x, const float* W, const float* b, int64_t rows, int d, int H, float omega, float* out,
+                    cudaStream_t stream);
 int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t stream);
 int launch_ffm(const float* x, const float* B, int64_t rows, int d, int m, float* out, cudaStream_t stream);
 int launch_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int n1, int n2,
@@ -494,6 +496,14 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
   if (rows < 0 || d < 1 || m < 1) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   return launch_ffm(x, B, rows, d, m, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_sine_layer_pre(const float* x, const float* W, const float* b, int64_t rows, int32_t d, int32_t H,
+                           float omega, float* out, void* stream) {
+  if (!x || !W || !b || !out) return B200INR_ERR_NULL;
+  if (rows < 0 || d < 1 || d > 8 || H < 1) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  return launch_sine_pre(x, W, b, rows, d, H, omega, out, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_combinations(const float* b0, const float* b1, const float* b2, const float* b3, int64_t voxels, int32_t n1,

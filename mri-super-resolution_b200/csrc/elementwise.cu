@@ -225,6 +225,32 @@ int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t st
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ SineLayer pre-activation   INR/SRDWI.py:62
+// pre[r, h] = omega * (sum_j x[r, j] W[h, j] + b[h]) for coordinate-fed layers (d <= 8): the "intermediate" of
+// SineLayer.forward_with_intermediate, fp32.  A d-term dot product per output: not a GEMM worth a tensor core.
+__global__ void __launch_bounds__(kEwThreads) sine_pre_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                              const float* __restrict__ b, long long rows, int d, int H,
+                                                              float omega, float* __restrict__ out) {
+  const long long total = rows * H;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / H;
+    const int h = int(i - r * H);
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) acc = fmaf(x[r * d + j], W[(long long)h * d + j], acc);
+    out[i] = omega * (acc + b[h]);
+  }
+}
+
+int launch_sine_pre(const float* x, const float* W, const float* b, int64_t rows, int d, int H, float omega, float* out,
+                    cudaStream_t stream) {
+  long long blocks = (rows * H + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  sine_pre_kernel<<<int(blocks), kEwThreads, 0, stream>>>(x, W, b, rows, d, H, omega, out);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------ input_mapping   INR/SRDWI.py:111-116
 // out[r, k] = sin(p), out[r, m + k] = cos(p), p = sum_j (2*pi*x[r, j]) * B[k, j]   (sin block first).
 __global__ void __launch_bounds__(kEwThreads) ffm_kernel(const float* __restrict__ x, const float* __restrict__ B,

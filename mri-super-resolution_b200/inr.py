@@ -262,9 +262,73 @@ class SineLayer(nn.Module):
                 bound = np.sqrt(6 / self.in_features) / self.omega_0
             self.linear.weight.uniform_(-bound, bound)
 
+    def _fused(self, input):
+        """sin(omega_0 (x W^T + b)) through the fused kernels as a 0-hidden-layer network whose (unused) final linear
+        is zero: the layer's activations are read back from the training stash (bf16 sin outputs, UMMA tile layout).
+        Inference only -- training goes through the enclosing Siren, whose backward is fused as well."""
+        _require_cuda(input, "SineLayer input")
+        lin = self.linear
+        k, h = lin.in_features, lin.out_features
+        if input.dim() != 2 or input.shape[1] != k:
+            raise RuntimeError(f"b200inr: expected an input of shape [N, {k}]")
+        dev = input.device
+        if k <= 4:    # raw coordinates: the 256-wide SIREN kernels (any width 8..256), staged stash keeps sin outputs
+            desc = _lib.make_net(k, h, 0, 1, self.omega_0, self.omega_0, flags=_lib.NET_STAGED_BWD)
+            width, y_off = 256, 0
+        else:         # explicit feature rows: the generic family (K a multiple of 64 <= H, H in {256, 512})
+            desc = _lib.make_net(k, h, 0, 1, self.omega_0, self.omega_0, input_mode=_lib.IN_FEATURES)
+            width = h
+        rows = input.shape[0]
+        if rows == 0:
+            return torch.empty((0, h), dtype=torch.float32, device=dev)
+        tiles = (rows + 127) // 128
+        if k > 4:
+            y_off = tiles * 128 * k * 2  # the network input (A operand of layer 0) is stashed first
+        with torch.no_grad(), torch.cuda.device(dev):
+            lib = _lib.load()
+            off = _lib.param_offsets(desc)  # raises for unsupported widths
+            flat = torch.zeros(_lib.param_count(desc), dtype=torch.float32, device=dev)
+            flat[off[0]:off[0] + h * k].copy_(lin.weight.detach().reshape(-1))
+            if lin.bias is not None:
+                flat[off[1]:off[1] + h].copy_(lin.bias.detach())
+            packed = _aligned_bytes(_lib.packed_bytes(desc), dev)
+            _lib.check(lib.b200inr_pack_weights(ctypes.byref(desc), _ptr(flat), _ptr(packed), _stream()), "pack_weights")
+            x = input.detach().contiguous().float()
+            out = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+            stash = _aligned_bytes(_lib.stash_bytes(desc, rows), dev, zero=False)
+            _lib.check(lib.b200inr_siren_forward(ctypes.byref(desc), _ptr(packed), _ptr(x), None, rows, _ptr(out), 0,
+                                                 0.0, _ptr(stash), _stream()), "siren_forward")
+            y = stash[y_off:y_off + tiles * 128 * width * 2].view(torch.bfloat16).view(tiles, width // 64, 128, 8, 8)
+            r = torch.arange(128, device=dev)
+            phys = torch.arange(8, device=dev)[None, :] ^ (r[:, None] & 7)  # logical 16-byte chunk -> SWIZZLE_128B slot
+            y = y[:, :, r[:, None], phys]                                    # [tiles, kb, 128, 8, 8]
+            return y.permute(0, 2, 1, 3, 4).reshape(tiles * 128, width)[:rows, :h].float()
+
     def forward(self, input):
-        raise RuntimeError("b200inr: SineLayer is executed fused inside Siren.forward / fit / query; "
-                           "call the enclosing Siren instead")
+        """Reference INR/SRDWI.py:58-59 for a stand-alone layer call (activation probing): one fused kernel, bf16
+        activations (rel-err <= 2e-2 against the fp32 expression).  No autograd: train through Siren."""
+        return self._fused(input)
+
+    def forward_with_intermediate(self, input):
+        """Reference INR/SRDWI.py:61-64: (sin(i), i) with i = omega_0 * linear(input), "for visualization of activation
+        distributions".  The pre-activation does not survive the fused kernel (it stashes 16-bit phases, i mod 2 pi),
+        so it is evaluated by the fp32 coordinate kernel b200inr_sine_layer_pre, which exists for coordinate-fed
+        layers (in_features <= 8), the case the reference plots."""
+        lin = self.linear
+        if lin.in_features > 8:
+            raise RuntimeError("b200inr: forward_with_intermediate is implemented for coordinate-fed layers "
+                               "(in_features <= 8)")
+        _require_cuda(input, "SineLayer input")
+        x = input.detach().contiguous().float()
+        rows, h = x.shape[0], lin.out_features
+        pre = torch.empty((rows, h), dtype=torch.float32, device=x.device)
+        bias = lin.bias.detach().contiguous() if lin.bias is not None else torch.zeros(h, device=x.device)
+        if rows:
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().b200inr_sine_layer_pre(_ptr(x), _ptr(lin.weight.detach().contiguous()), _ptr(bias),
+                                                              rows, lin.in_features, h, float(self.omega_0), _ptr(pre),
+                                                              _stream()), "sine_layer_pre")
+        return self._fused(input), pre
 
 
 class _SirenFunction(torch.autograd.Function):
@@ -277,6 +341,7 @@ class _SirenFunction(torch.autograd.Function):
         ctx.module = module
         ctx.stash = stash
         ctx.coords = coords
+        ctx.key = module._engine["key"]  # identity + version of every parameter the stash was computed with
         return out
 
     @staticmethod
@@ -284,6 +349,10 @@ class _SirenFunction(torch.autograd.Function):
         module = ctx.module
         if ctx.stash is None:
             raise RuntimeError("b200inr: backward called on a forward that did not record activations")
+        if module._engine is None or module._engine["key"] != ctx.key:
+            # forward A, optimizer.step(), forward B, A.backward(): the bf16 operands no longer match A's stash
+            raise RuntimeError("b200inr: one of the parameters needed for gradient computation has been modified by an "
+                               "inplace operation since this forward (the operand buffer was re-staged)")
         grad_in = torch.empty_like(ctx.coords) if ctx.needs_input_grad[0] else None
         flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out, grad_in=grad_in)
         ctx.stash = None
@@ -309,6 +378,19 @@ class _FusedMLP(nn.Module):
     def _frozen(self):
         """Non-trainable tensors stored in the flat vector after the parameters (the Fourier matrix B)."""
         return []
+
+    def invalidate(self):
+        """Drop the device-side staging (flat fp32 copy, bf16 operands): the next call rebuilds it from the
+        nn.Parameters.  Needed after writes that bypass autograd's version counter (`p.data.copy_(...)`)."""
+        self._engine = None
+
+    def __getstate__(self):
+        # copy.deepcopy / torch.save(module): the staging buffers are derived state (and the operand buffer is an
+        # aligned VIEW whose alignment a copy does not preserve); the copy rebuilds them on first use
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_optim"] = None
+        return state
 
     # ---------------------------------------------------------------- parameter plumbing
     def _offsets_canonical(self):
@@ -599,7 +681,41 @@ class ComplexGaborLayer2D(nn.Module):
         self.scale_orth = nn.Linear(in_features, out_features, bias=bias, dtype=dtype)
 
     def forward(self, input):
-        raise RuntimeError("b200inr: ComplexGaborLayer2D is executed fused inside Wire.forward / fit / query")
+        """Reference INR/INRmodel.py:109-120 for a stand-alone call of a FIRST layer (real coordinates in, complex64
+        out): the layer runs as a 0-hidden-layer WIRE network whose final linear is zero and its activations
+        [h_r | h_i] are read back from the training stash (bf16).  Hidden layers take complex inputs, which only exist
+        on chip inside Wire.forward / fit / query."""
+        if not self.is_first:
+            raise RuntimeError("b200inr: a hidden ComplexGaborLayer2D runs fused inside Wire (its complex input never "
+                               "leaves the chip); only first layers can be called stand-alone")
+        _require_cuda(input, "ComplexGaborLayer2D input")
+        lin, orth = self.linear, self.scale_orth
+        k, h = lin.in_features, lin.out_features
+        dev, rows = input.device, input.shape[0]
+        if rows == 0:
+            return torch.empty((0, h), dtype=torch.complex64, device=dev)
+        desc = _lib.make_net(k, h, 0, 1, float(self.omega_0), float(self.omega_0), activation=_lib.ACT_GABOR,
+                             scale_0=float(self.scale_0))
+        tiles = (rows + 127) // 128
+        with torch.no_grad(), torch.cuda.device(dev):
+            lib = _lib.load()
+            off = _lib.param_offsets(desc)  # W_lin b_lin W_orth b_orth | W_f b_f
+            flat = torch.zeros(_lib.param_count(desc), dtype=torch.float32, device=dev)
+            for o, t in zip(off[:4], (lin.weight, lin.bias, orth.weight, orth.bias)):
+                if t is not None:
+                    flat[o:o + t.numel()].copy_(t.detach().reshape(-1))
+            packed = _aligned_bytes(_lib.packed_bytes(desc), dev)
+            _lib.check(lib.b200inr_pack_weights(ctypes.byref(desc), _ptr(flat), _ptr(packed), _stream()), "pack_weights")
+            x = input.detach().contiguous().float()
+            out = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+            stash = _aligned_bytes(_lib.stash_bytes(desc, rows), dev, zero=False)
+            _lib.check(lib.b200inr_siren_forward(ctypes.byref(desc), _ptr(packed), _ptr(x), None, rows, _ptr(out), 0,
+                                                 0.0, _ptr(stash), _stream()), "siren_forward")
+            y = stash[:tiles * 128 * 2 * h * 2].view(torch.bfloat16).view(tiles, 2 * h // 64, 128, 8, 8)
+            r = torch.arange(128, device=dev)
+            phys = torch.arange(8, device=dev)[None, :] ^ (r[:, None] & 7)
+            y = y[:, :, r[:, None], phys].permute(0, 2, 1, 3, 4).reshape(tiles * 128, 2 * h)[:rows].float()
+            return torch.complex(y[:, :h].contiguous(), y[:, h:].contiguous())
 
 
 class Wire(_FusedMLP):

@@ -1031,3 +1031,42 @@ def test_optimizer_step_equals_adam_then_pack(dev, kind):
         assert torch.equal(pk_a, pk_b)
         assert float(s_b[0]) == step + 1
         assert loss_out.item() == g[n].item() and not g_b[:n + 1].any()
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone layers
+@pytest.mark.parametrize("k,h,first", [(3, 256, True), (2, 64, True), (256, 256, False), (128, 512, False)])
+def test_sine_layer_standalone_forward(dev, k, h, first):
+    """SineLayer.forward / forward_with_intermediate (INR/SRDWI.py:58-64) as a fused 0-hidden-layer call."""
+    torch.manual_seed(12)
+    layer = b200inr.SineLayer(k, h, is_first=first, omega_0=30).to(dev)
+    x = (torch.rand(777, k, device=dev) * 2 - 1) if first else torch.sin(torch.randn(777, k, device=dev))
+    with torch.no_grad():
+        pre_ref = 30 * (x @ layer.linear.weight.T + layer.linear.bias)
+    out = layer(x)
+    assert out.shape == (777, h) and out.dtype == torch.float32
+    assert _relerr(out.cpu().numpy(), torch.sin(pre_ref).cpu().numpy()) < BF16_RELERR
+    if k <= 8:
+        s, pre = layer.forward_with_intermediate(x)
+        assert torch.equal(s, out)
+        assert _relerr(pre.cpu().numpy(), pre_ref.cpu().numpy()) < 1e-5
+    else:
+        with pytest.raises(RuntimeError):
+            layer.forward_with_intermediate(x)
+    assert layer(x[:0]).shape == (0, h)
+
+
+def test_gabor_first_layer_standalone_forward(dev):
+    """ComplexGaborLayer2D.forward (INR/INRmodel.py:109-120) of a first layer: complex64 activations."""
+    torch.manual_seed(4)
+    layer = b200inr.ComplexGaborLayer2D(3, 128, is_first=True, omega0=1.2, sigma0=1.2).to(dev)
+    x = torch.rand(500, 3, device=dev) * 2 - 1
+    with torch.no_grad():
+        lin = x @ layer.linear.weight.T + layer.linear.bias
+        orth = x @ layer.scale_orth.weight.T + layer.scale_orth.bias
+        ref = torch.exp(1j * 1.2 * lin - (1.2 ** 2) * (lin.abs().square() + orth.abs().square()))
+    out = layer(x)
+    assert out.dtype == torch.complex64 and out.shape == (500, 128)
+    assert _relerr(torch.view_as_real(out).cpu().numpy(), torch.view_as_real(ref).cpu().numpy()) < BF16_RELERR
+    hidden = b200inr.ComplexGaborLayer2D(128, 128, is_first=False).to(dev)
+    with pytest.raises(RuntimeError):
+        hidden(out)

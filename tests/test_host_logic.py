@@ -260,3 +260,88 @@ def test_error_codes_of_the_widened_entry_points():
     assert lib.b200inr_combinations(one, one, one, one, 0, 2, 3, 2, one, None) == 0
     assert lib.b200inr_combinations(one, one, one, one, 5, 0, 3, 2, one, None) == -1
     assert lib.b200inr_combinations(one, None, one, one, 5, 2, 3, 2, one, None) == -5
+
+
+# ------------------------------------------------------------------------------------------------ drop-in boundary
+REFERENCE_IMPORT_LINES = [
+    # the literal import statements of the reference's drivers (file:line), executed against the drop-in directory
+    ("INR/superresDWI.py:13", "from SRDWI import calculate_combinations, ImageFitting_set, Siren, PN, get_mgrid, "
+                              "input_mapping, calculate_ADC, resize_array"),
+    ("INR/inrDWI.py:9", "from INRmodel import calculate_combinations, ImageFitting_set, Siren, PN, input_mapping, "
+                        "get_mgrid, calculate_ADC, resize_array"),
+    ("INR/superresHybrid.py:13", "from SRDWI import  ImageFitting_set, Siren, get_mgrid, input_mapping, calculate_ADC, "
+                                 "resize_array"),
+    ("INR/forbagci.py:10", "from SRDWI import calculate_combinations, ImageFitting_set, Siren, PN, input_mapping"),
+    ("INR/inr_toy.py:3", "from nn_mri import ImageFitting_set, SineLayer, get_mgrid"),
+    ("INR/automate_INR.py:9", "from nn_mri import Siren, PN, input_mapping"),
+    ("INR/automate_INR.py:10", "from SRDWI import get_mgrid, ImageFitting_set"),
+    ("wiretest.ipynb#c0 (INRmodel surface)", "from INRmodel import ComplexGaborLayer2D, SineLayer"),
+]
+
+
+@pytest.mark.parametrize("where,line", REFERENCE_IMPORT_LINES)
+def test_reference_import_lines_run_verbatim(where, line):
+    """With mri-super-resolution_b200/dropin first on sys.path the reference's own import lines resolve to this
+    package, unedited."""
+    import subprocess
+    import sys
+    dropin = os.path.join(ROOT, "mri-super-resolution_b200", "dropin")
+    code = (f"import sys; sys.path.insert(0, {dropin!r}); {line}\n"
+            "import inspect\n"
+            "mods = {v.__module__ for k, v in list(globals().items())\n"
+            "        if not k.startswith('_') and (inspect.isclass(v) or inspect.isfunction(v))}\n"
+            "assert mods and all(m.startswith('mri-super-resolution_b200') for m in mods), mods\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert res.returncode == 0, f"{where}: {res.stderr[-800:]}"
+
+
+def test_net_struct_size_matches_header_and_library():
+    """The ctypes mirror of b200inr_net, the struct in include/b200inr.h and the compiled library agree (a short
+    struct would make check_net read past the caller's buffer)."""
+    hdr = open(os.path.join(ROOT, "include", "b200inr.h")).read()
+    body = re.search(r"typedef struct b200inr_net \{(.*?)\} b200inr_net;", hdr, re.S).group(1)
+    fields = re.findall(r"^\s*(int32_t|float)\s+(\w+);", body, re.M)
+    assert [f for _, f in fields] == [n for n, _ in L.Net._fields_]
+    assert ctypes.sizeof(L.Net) == 4 * len(fields) == L.load().b200inr_net_size()
+    # INTEGRATION.md documents the same struct
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name, _ in L.Net._fields_:
+        assert f'("{name}"' in doc, f"INTEGRATION.md stub lacks field {name}"
+    cnt = ctypes.c_int32(0)
+    for net, want in ((L.make_net(3, 256, 4, 31), 12), (L.make_net(3, 512, 3, 31, activation=L.ACT_RELU,
+                                                                   input_mode=L.IN_FOURIER, mapping_size=256), 11),
+                      (L.make_net(3, 128, 3, 31, activation=L.ACT_GABOR, scale_0=1.2), 18)):
+        assert L.load().b200inr_param_offset_count(ctypes.byref(net), ctypes.byref(cnt)) == 0 and cnt.value == want
+        assert len(L.param_offsets(net)) == want
+
+
+def test_resize_array_matches_scipy_expression():
+    """resize_array (INR/SRDWI.py:132-141): cubic interpolation of the third axis on [0, 1]."""
+    from scipy.interpolate import interp1d
+    rng = np.random.RandomState(0)
+    arr = rng.rand(5, 4, 9)
+    out = b200inr.SRDWI.resize_array(arr, new_size=16)
+    assert out.shape == (5, 4, 16) and out.dtype == np.float64
+    f = interp1d(np.linspace(0, 1, 9), arr, kind="cubic", axis=2)
+    ref = np.stack([f(x) for x in np.linspace(0, 1, 16)], axis=2)  # the reference's plane-by-plane loop
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out[:, :, 0], arr[:, :, 0], atol=1e-12)
+    assert b200inr.INRmodel.resize_array is b200inr.SRDWI.resize_array
+    lin = b200inr.SRDWI.resize_array(arr, new_size=9, kind="linear")
+    np.testing.assert_allclose(lin, arr, atol=1e-12)
+
+
+def test_nn_mri_surface():
+    """nn_mri flavours: get_mgrid(sidelen, dim), PN with a fixed 2-D output, ImageFitting_set over PIL images."""
+    from PIL import Image
+    nm = b200inr.nn_mri
+    g = nm.get_mgrid(5, 2)
+    assert g.shape == (25, 2) and torch.equal(g, b200inr.get_mgrid((5, 5)))
+    pn = nm.PN(6, 8)
+    assert pn.perturb_linear.in_features == 7 and pn.perturb_linear2.out_features == 2
+    imgs = [Image.fromarray((np.random.RandomState(i).rand(8, 8) * 255).astype(np.uint8)) for i in range(2)]
+    ds = nm.ImageFitting_set(imgs)
+    assert ds.pixels.shape == (2, 64, 1) and ds.coords.shape == (2, 64, 2) and len(ds) == 2
+    want = (torch.from_numpy(np.array(imgs[0])).float() / 255.0 - 0.5) / 0.5
+    assert torch.allclose(ds.pixels[0].reshape(8, 8), want, atol=1e-6)
+    assert ds.mean.shape == (8, 8) and ds.shape == (8, 8)
