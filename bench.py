@@ -5,12 +5,13 @@ HR voxel queries/s).
     python bench.py --gpus N --steps K --warmup W            # our arm, one rank per GPU (torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
 
-Workload at N = 1 = BASELINE configs[1]: SIREN 3 -> 5x256 -> 31 fitted to a synthetic 128x128x64x31 DWI volume through
-the 2x2x1 LR-consistency loss, full batch (1 048 576 coordinates per step), Adam lr 1e-4.  At N > 1 every rank owns
-its own 128-plane slab of a (128 N)x128x64 volume (weak scaling) and the flat [gradient | loss] buffer is all-reduced
-once per step.  A step = zero-grad, fused forward, pooled loss + its gradient, fused dgrad, wgrad, [all-reduce],
-Adam, bf16 re-staging (dgrad + wgrad are ONE layer-pipelined kernel by default; B200INR_PIPED_BWD=0 selects the staged
-pair).  One JSON line is printed by rank 0.
+Workload = BASELINE configs[1]: SIREN 3 -> 5x256 -> 31 fitted to THE synthetic 128x128x64x31 DWI volume through the
+2x2x1 LR-consistency loss, full batch (1 048 576 coordinates per step), Adam lr 1e-4.  At N > 1 the same volume is cut
+into N slabs of 128 / N x-planes (STRONG scaling, what BASELINE.json's north_star asks for); the gradients meet inside
+the optimiser-step kernel (peer-mapped buffers summed over NVLink) or in one ncclAllReduce.  A step = fused forward,
+pooled loss + its gradient, one layer-pipelined backward kernel, one optimiser-step kernel (Adam + zero_grad + bf16
+re-staging).  Extra legs: cfg2-grid and cfg5 (512x512x256, x-planes sharded) queries, weak scaling (`weak_scaling`).
+One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -127,7 +128,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "inr_train_coord_samples_per_s", "value": value, "unit": "coord-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "each step = full fit step on a 32x32x64 sub-volume (65 536 coords)"},
         "cpu_baseline": {"value": value, "unit": "coord-samples/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} fit steps on a 32x32x64x31 sub-volume (65 536 coordinates/step), "
@@ -154,22 +155,8 @@ def run_ours(args):
         group = dist.group.WORLD
     if world != args.gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
-
-    # ---- synthetic workload: every rank regenerates its own slab of the (128*world) x 128 x 64 volume
-    gshape = (HR_SHAPE[0] * world, HR_SHAPE[1], HR_SHAPE[2])
     par = b200inr.parallel
-    r0, r1 = par.shard_rows(gshape, world, rank, pooled=True)
     plane = HR_SHAPE[1] * HR_SHAPE[2]
-    hr = b200inr.phantom.dwi_phantom(gshape, n_dirs=C_OUT - 1, noise=0.01, seed=0, x_range=(r0 // plane, r1 // plane))
-    lr_host = torch.from_numpy(b200inr.phantom.avg_pool_inplane(hr)).pin_memory()
-    del hr
-    rows = r1 - r0
-    global_rows = int(np.prod(gshape))
-    torch.manual_seed(0)
-    model = b200inr.Siren(*NET).to(dev)
-    target = lr_host.to(dev, non_blocking=True)
-    sess = b200inr.inr.FitSession(model, target, gshape, lr=LR, degrade="pool", row_range=(r0, r1),
-                                  global_count=global_rows * C_OUT // 4, process_group=group)
 
     def sync():
         torch.cuda.synchronize()
@@ -184,39 +171,62 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput (`value`)
+    def make_session(gshape):
+        """This rank's x-slab of the fit of a gshape x 31 volume: every rank regenerates its own slab of the phantom."""
+        r0, r1 = par.shard_rows(gshape, world, rank, pooled=True)
+        hr = b200inr.phantom.dwi_phantom(gshape, n_dirs=C_OUT - 1, noise=0.01, seed=0,
+                                         x_range=(r0 // plane, r1 // plane))
+        lr_host = torch.from_numpy(b200inr.phantom.avg_pool_inplane(hr)).pin_memory()
+        del hr
+        torch.manual_seed(0)
+        model = b200inr.Siren(*NET).to(dev)
+        sess = b200inr.inr.FitSession(model, lr_host.to(dev, non_blocking=True), gshape, lr=LR, degrade="pool",
+                                      row_range=(r0, r1), global_count=int(np.prod(gshape)) * C_OUT // 4,
+                                      process_group=group)
+        return model, sess, lr_host, (r0, r1)
+
+    def timed_steps(sess, steps, warmup):
+        for _ in range(warmup):
+            sess.step()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sess.step()
+        e1.record()
+        sync()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- the contract workload: THE 128 x 128 x 64 x 31 volume (strong scaling: 128 / N x-planes per rank)
+    gshape = HR_SHAPE
+    global_rows = int(np.prod(gshape))
+    model, sess, lr_host, (r0, r1) = make_session(gshape)
+    rows = r1 - r0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # nvidia-smi needs ~0.2 s to deliver its first sample: start it before the warm-up
-    for _ in range(args.warmup):
-        sess.step()
-    sync()
-    marks = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        marks.append([])
-        sess.step(marks[-1])
-    e1.record()
-    sync()
+    ms_total = timed_steps(sess, args.steps, args.warmup)  # no events inside: nothing but the step's own kernels
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = global_rows * args.steps / (ms_total * 1e-3)
     loss_last = float(sess.loss.item())
 
-    stage_ms = {}
+    # ---- per-stage device times (separate pass: an event between two kernels costs a few microseconds of idle GPU)
+    marks = []
+    for _ in range(max(5, min(args.steps, 20))):
+        marks.append([])
+        sess.step(marks[-1])
+    sync()
     names = b200inr.inr.FitSession.STAGES
-    for i, nm in enumerate(names):
-        stage_ms[nm] = float(np.mean([mk[i].elapsed_time(mk[i + 1]) for mk in marks]))
+    stage_ms = {nm: float(np.mean([mk[i].elapsed_time(mk[i + 1]) for mk in marks])) for i, nm in enumerate(names)}
 
     # ---- end to end through the public API with HOST buffers (`e2e`)
     e2e_steps = args.steps
     host_loss = torch.zeros(2).pin_memory()
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_losses = []
-    sync()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def e2e_loop(n):
         # every step: H2D of its input (the acquired LR volume, pinned memory) and D2H of its result (the loss).  Both
         # directions are pipelined one step deep: the copy of step i + 1's input travels on a side stream while step i
@@ -247,53 +257,79 @@ def run_ours(args):
     if not all(np.isfinite(v) for v in e2e_losses):
         raise RuntimeError("bench: a loss read back in the end-to-end loop is not finite")
     sess.finish()
+    launches_per_step = sess.kernel_launches_per_step
+    piped, n_flat, stash_gb, peer = sess.piped, sess.n_flat, sess.stash.numel() / 1e9, sess.peer is not None
 
-    # ---- HR voxel queries/s (second half of BASELINE.json's metric): cfg2 grid, output written to HBM
-    qshape = gshape
-    qout = torch.empty((rows, C_OUT), dtype=torch.float32, device=dev)
-    for _ in range(3):
-        model.query(qshape, out=qout, row_range=(r0, r1))
-    sync()
-    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    q0.record()
-    nq = max(5, args.steps)
-    for _ in range(nq):
-        model.query(qshape, out=qout, row_range=(r0, r1))
-    q1.record()
-    sync()
-    q_ms = max_over_ranks(q0.elapsed_time(q1)) / nq
-    q_value = global_rows / (q_ms * 1e-3)
+    # ---- HR voxel queries/s (second half of BASELINE.json's metric): the cfg2 grid and BASELINE configs[4]
+    #      (512 x 512 x 256 x 31, x-planes sharded over the ranks, no collective), output written to HBM
+    def time_query(qshape, iters):
+        q0r, q1r = par.shard_rows(qshape, world, rank)
+        qout = torch.empty((q1r - q0r, C_OUT), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            model.query(qshape, out=qout, row_range=(q0r, q1r))
+        sync()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(iters):
+            model.query(qshape, out=qout, row_range=(q0r, q1r))
+        q1.record()
+        sync()
+        ms = max_over_ranks(q0.elapsed_time(q1)) / iters
+        nrows = int(np.prod(qshape))
+        del qout
+        return {"value": nrows / (ms * 1e-3), "unit": "voxels/s", "ms": ms, "grid": list(qshape),
+                "rows_per_gpu": q1r - q0r, "tflops_per_gpu": 2 * MAC_FWD * (q1r - q0r) / (ms * 1e-3) / 1e12}
+
+    query = time_query(HR_SHAPE, max(5, args.steps))
+    query_cfg5 = time_query((512, 512, 256), 3)
+
+    # ---- weak scaling as an extra (N > 1): every rank owns a whole 128 x 128 x 64 slab of a (128 N) x 128 x 64 volume
+    weak = None
+    if world > 1:
+        del sess
+        wshape = (HR_SHAPE[0] * world, HR_SHAPE[1], HR_SHAPE[2])
+        _, wsess, _, _ = make_session(wshape)
+        wms = timed_steps(wsess, args.steps, args.warmup) / args.steps
+        weak = {"global_grid": list(wshape), "ms_per_step": wms,
+                "value": int(np.prod(wshape)) / (wms * 1e-3), "unit": "coord-samples/s"}
+        del wsess
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (denominator: the measured BURST bf16 peak; the
+    #      sustained figure -- a seconds-long cuBLAS loop under the power cap -- is quoted beside it)
     peaks = measured_peaks()
-    piped = sess.piped  # one-kernel backward: the 'dgrad' slot holds siren_bwdp_kernel, the 'wgrad' slot is empty
     flop_kernel = dict(FLOP_KERNEL)
     kernel_name = {"forward": "siren_fwd_kernel", "dgrad": "siren_bwd_kernel", "wgrad": "wgrad_kernel"}
-    if piped:
+    if piped:  # one-kernel backward: the 'dgrad' slot holds siren_bwdp_kernel, the 'wgrad' slot is empty
         flop_kernel["dgrad"] = FLOP_KERNEL["dgrad"] + FLOP_KERNEL["wgrad"]
         kernel_name["dgrad"] = "siren_bwdp_kernel"
-    dom = max(("forward", "dgrad", "wgrad", "loss"), key=lambda k: stage_ms[k])
+    dom = max(("forward", "dgrad", "wgrad"), key=lambda k: stage_ms[k])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         traffic = json.load(open(tpath)).get("pipelined_backward" if (piped and dom == "dgrad") else dom)
-    if dom == "loss":
-        alg_bytes = rows * C_OUT * 4 * 2 + rows * C_OUT  # read pred, write grad, read LR target (1/4)
-        achieved = alg_bytes / (stage_ms[dom] * 1e-3) / 1e9
-        roofline = {"kernel": "pool_mse_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["gbs"],
-                    "unit": "GB/s", "frac": achieved / peaks["gbs"], "traffic": traffic, "peak_source": peaks["src"]}
-    else:
-        achieved = flop_kernel[dom] * rows / (stage_ms[dom] * 1e-3) / 1e12
-        roofline = {"kernel": kernel_name[dom],
-                    "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"] or peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": achieved / (peaks["tflops_sustained"] or peaks["tflops"]),
-                    "traffic": traffic, "peak_source": peaks["src"] + " (sustained: kernel timed inside the step)"}
+    achieved = flop_kernel[dom] * rows / (stage_ms[dom] * 1e-3) / 1e12
+    roofline = {"kernel": kernel_name[dom], "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "peak_source": peaks["src"] + " burst bf16 (cuBLAS 8192^3, best of 10)",
+                "frac_of_sustained": achieved / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None}
     step_tflops = FLOP_TRAIN * rows / (ms_step * 1e-3) / 1e12  # per GPU
+    # the HBM-bound kernels of the step (north_star: "achieved HBM GB/s for the degradation and Adam kernels")
+    loss_bytes = rows * C_OUT * 4 * 2 + rows * C_OUT  # read pred, write dL/dpred, read the LR target (1/4)
+    hbm = {
+        "pool_mse_kernel": {"ms": stage_ms["loss"], "algorithmic_bytes": loss_bytes,
+                            "achieved_gbs": loss_bytes / (stage_ms["loss"] * 1e-3) / 1e9 if stage_ms["loss"] > 1e-4 else None,
+                            "frac_of_hbm_peak": loss_bytes / (stage_ms["loss"] * 1e-3) / 1e9 / peaks["gbs"]
+                            if stage_ms["loss"] > 1e-4 else None},
+        "optimizer_step": {"us": stage_ms["optimizer"] * 1e3, "algorithmic_bytes": (n_flat * 30),
+                           "note": "Adam + zero_grad + step counter + bf16 re-staging" +
+                                   (" + in-kernel gradient exchange over peer-mapped memory" if peer else "") +
+                                   ", one launch; 8 MB: launch-latency bound, GB/s not meaningful"},
+    }
 
     # ---- CPU baseline: bounded sample on the host cores
     cpu = None
@@ -305,30 +341,40 @@ def run_ours(args):
                "sample": f"{cpu_steps} fit steps on a 32x32x64x31 sub-volume (65 536 coordinates/step, {cms:.0f} ms/step), "
                          "CPU PyTorch fp32 restatement of the reference loop (oracle/inr_oracle.py)"}
 
+    exchange = ("none (1 GPU)" if world == 1 else
+                f"in-kernel sum of the {world} peer-mapped [grad | loss] buffers ({n_flat + 4} fp32 each) inside the "
+                "optimiser-step kernel (NVLink P2P loads, flag barrier)" if peer else
+                f"1 ncclAllReduce of {n_flat + 4} fp32 per step")
     line = {
         "metric": "inr_train_coord_samples_per_s", "value": value, "unit": "coord-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_grid": list(gshape), "rows_per_gpu": rows,
-                   "parallelism": f"coordinate slabs x{world}, 1 all-reduce of {sess.n_flat + 4} fp32 per step",
-                   "l2": f"per-step working set (activation stash {sess.stash.numel() / 1e9:.1f} GB/GPU) exceeds the 126 MB L2; "
-                         "no flush needed",
+                   "parallelism": f"x-plane slabs x{world} of the fixed volume ({gshape[0] // world} planes per GPU), "
+                                  f"weights replicated; gradient exchange: {exchange}",
+                   "l2": f"per-step working set (phase stash {stash_gb:.2f} GB/GPU) exceeds the 126 MB L2; no flush needed"
+                         if stash_gb > 0.2 else
+                         f"per-step working set {stash_gb * 1e3:.0f} MB/GPU of phase stash + 2 x {rows * C_OUT * 4 / 1e6:.0f} MB "
+                         "of prediction / gradient rows, rewritten every step",
                    "backward": "pipelined (one kernel, phase-only stash)" if piped else "staged (dgrad + wgrad)",
                    "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state",
-                   "e2e": "per step: H2D of the LR volume from pinned host memory (double-buffered, issued on a side "
-                          "stream while the previous step computes) + D2H of the loss (read by the host one step "
+                   "e2e": "per step: H2D of this rank's LR slab from pinned host memory (double-buffered, issued on a "
+                          "side stream while the previous step computes) + D2H of the loss (read by the host one step "
                           "later, event-synchronised), through FitSession"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coord-samples/s", "h2d_bytes_per_step": int(lr_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps},
-        "gpu_launches": sess.kernel_launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "step_tflops_algorithmic_per_gpu": step_tflops,
-        "step_frac_of_peak": step_tflops / (peaks["tflops_sustained"] or peaks["tflops"]),
+        "step_frac_of_peak": step_tflops / peaks["tflops"],
+        "step_frac_of_sustained_peak": step_tflops / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
         "stage_ms": stage_ms,
-        "query": {"value": q_value, "unit": "voxels/s", "ms": q_ms,
-                  "tflops_per_gpu": 2 * MAC_FWD * rows / (q_ms * 1e-3) / 1e12, "grid": list(qshape)},
+        "hbm_kernels": hbm,
+        "query": query,
+        "query_cfg5": query_cfg5,
+        "weak_scaling": weak,
         "final_loss": loss_last,
     }
     print(json.dumps(line), flush=True)

@@ -190,6 +190,19 @@ int b200inr_optimizer_step(const b200inr_net* net, float* params, float* grads, 
                            float lr, float beta1, float beta2, float eps, float* state, void* packed,
                            float* loss_out, void* stream);
 
+/* The same step for data-parallel ranks (one process per GPU) with the gradient exchange INSIDE
+ * the kernel: instead of ncclAllReduce + b200inr_optimizer_step, every rank's [grad | loss] buffer of this step lives in
+ * peer-mapped (symmetric) memory, the kernel waits until every rank has entered it (flag words written over NVLink),
+ * sums the `world` buffers in rank order -- identical arithmetic on every rank, so the replicated weights stay
+ * bit-identical -- applies Adam, re-stages the operands and clears grads_next, the buffer the NEXT step accumulates
+ * into (the two buffers alternate, so no rank clears what a peer may still be reading and no end barrier is needed).
+ * peer_grads / peer_flags: DEVICE arrays of `world` pointers (peer_flags[p] = rank p's flag words, >= world uint32,
+ * zero-initialised once).  loss_out[0] = sum over ranks of the loss accumulators (at index n of each buffer). */
+int b200inr_optimizer_step_peers(const b200inr_net* net, float* params, float* grads_next,
+                                 const float* const* peer_grads, uint32_t* const* peer_flags, int32_t world,
+                                 int32_t rank, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                                 float eps, float* state, void* packed, float* loss_out, void* stream);
+
 /* sizeof(b200inr_net) as this library was compiled: a binding whose struct definition has drifted (fewer fields)
  * must refuse to call rather than pass a short struct. */
 size_t b200inr_net_size(void);

@@ -72,6 +72,8 @@ SIGNATURES = {
     "b200inr_pool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp]),
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b200inr_optimizer_step": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "b200inr_optimizer_step_peers": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _f32, _f32,
+                                                    _f32, _vp, _vp, _vp, _vp]),
     "b200inr_net_size": (_sz, []),
     "b200inr_param_offset_count": (ctypes.c_int, [_P(Net), _P(_i32)]),
     "b200inr_get_mgrid": (ctypes.c_int, [_P(Grid), _i64, _vp, _vp]),

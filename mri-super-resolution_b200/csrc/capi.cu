@@ -48,6 +48,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
                 float* state, cudaStream_t stream);
 int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
                           float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
+                          const float* const* peer_grads, uint32_t* const* peer_flags, int world, int rank,
                           cudaStream_t stream);
 int launch_sine_pre(const float* x, const float* W, const float* b, int64_t rows, int d, int H, float omega, float* out,
                     cudaStream_t stream);
@@ -456,7 +457,25 @@ int b200inr_optimizer_step(const b200inr_net* net, float* params, float* grads, 
   int64_t n = 0;
   if ((e = b200inr_param_count(net, &n))) return e;
   return launch_optimizer_step(net, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state, packed,
-                               loss_out, static_cast<cudaStream_t>(stream));
+                               loss_out, nullptr, nullptr, 1, 0, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_optimizer_step_peers(const b200inr_net* net, float* params, float* grads_next, const float* const* peer_grads,
+                                 uint32_t* const* peer_flags, int32_t world, int32_t rank, float* exp_avg,
+                                 float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float* state,
+                                 void* packed, float* loss_out, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!params || !grads_next || !peer_grads || !peer_flags || !exp_avg || !exp_avg_sq || !state || !packed)
+    return B200INR_ERR_NULL;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return B200INR_ERR_BAD_SHAPE;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(packed) & 1023)) return B200INR_ERR_BAD_ALIGN;
+  int64_t n = 0;
+  if ((e = b200inr_param_count(net, &n))) return e;
+  // (world == 1 runs the same code path -- a sum over one "peer", this rank's own buffer -- and is how one GPU tests it)
+  return launch_optimizer_step(net, params, grads_next, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state, packed,
+                               loss_out, peer_grads, peer_flags, world, rank,
+                               static_cast<cudaStream_t>(stream));
 }
 
 size_t b200inr_net_size(void) { return sizeof(b200inr_net); }

@@ -106,14 +106,56 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
 // shards).  The loss accumulator that rides behind the gradients is moved to loss_out and cleared as well.
 struct AdamArgs {
   float* params;
-  float* grads;
+  float* grads;     // single GPU: read and cleared.  Multi GPU: the buffer to clear for the NEXT step (other parity)
   float* m;
   float* v;
   float* state;     // {step, ticket (u32), -, -}
   float* loss_out;  // nullptr, or receives grads[n] (the step's loss) before it is cleared
   long long n;
   float lr, beta1, beta2, eps;
+  // multi GPU (peer_grads != nullptr): every rank's [grad | loss] buffer of this step in peer-mapped memory, summed here in rank
+  // order (the same order on every rank: replicated weights stay bit-identical), and the flag words of the start barrier
+  const float* const* peer_grads;  // device array [world]
+  uint32_t* const* peer_flags;     // device array [world]: flags[p][r] = last epoch rank r has announced to rank p
+  int world, rank;
 };
+
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// Start barrier of the multi-GPU optimiser step: rank r announces epoch = step + 1 to every peer, and every block
+// waits until all peers have announced it -- i.e. until every rank has ENTERED this kernel, which in stream order means
+// its backward of this step is complete (its gradients are final) and its previous optimiser step is over (nobody reads
+// the other-parity buffer any more, so it may be cleared).  One kernel per GPU, all resident at the same time: the
+// ranks are different devices.  Bounded spin: a missing rank traps instead of hanging the box.
+__device__ __forceinline__ void peer_barrier(const AdamArgs& a) {
+  if (a.peer_grads == nullptr) return;
+  const uint32_t epoch = uint32_t(a.state[0]) + 1u;
+  if (blockIdx.x == 0 && int(threadIdx.x) < a.world) st_release_sys_u32(a.peer_flags[threadIdx.x] + a.rank, epoch);
+  if (int(threadIdx.x) < a.world) {
+    const uint32_t* f = a.peer_flags[a.rank] + threadIdx.x;
+    uint32_t spins = 0;
+    while (ld_acquire_sys_u32(f) < epoch) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        printf("b200inr: optimiser-step barrier timeout: rank %d waits for rank %d (epoch %u)\n", a.rank, threadIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
 
 struct AdamCoef {
   float step_size, bc2_sqrt, omb1, omb2, beta2, eps;
@@ -139,7 +181,13 @@ __device__ __forceinline__ AdamCoef adam_coefficients(const AdamArgs& a, float* 
 }
 
 __device__ __forceinline__ float adam_apply(const AdamArgs& a, const AdamCoef& c, long long i) {
-  const float gi = a.grads[i];
+  float gi;
+  if (a.peer_grads != nullptr) {
+    gi = 0.f;
+    for (int r = 0; r < a.world; ++r) gi += ld_relaxed_sys_f32(a.peer_grads[r] + i);
+  } else {
+    gi = a.grads[i];
+  }
   float mi = a.m[i], vi = a.v[i];
   mi = fmaf(gi - mi, c.omb1, mi);
   vi = fmaf(c.omb2 * gi, gi, c.beta2 * vi);
@@ -165,7 +213,14 @@ __device__ __forceinline__ void adam_finish(const AdamArgs& a) {
   if (s_last && threadIdx.x == 0) {
     a.state[0] += 1.f;
     *reinterpret_cast<unsigned int*>(a.state + 1) = 0u;
-    if (a.loss_out != nullptr) a.loss_out[0] = a.grads[a.n];
+    float loss;
+    if (a.peer_grads != nullptr) {
+      loss = 0.f;
+      for (int r = 0; r < a.world; ++r) loss += ld_relaxed_sys_f32(a.peer_grads[r] + a.n);
+    } else {
+      loss = a.grads[a.n];
+    }
+    if (a.loss_out != nullptr) a.loss_out[0] = loss;
     a.grads[a.n] = 0.f;
   }
 }
@@ -182,6 +237,7 @@ __host__ __device__ inline long long siren_adam_pack_items(int L) {
 
 __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const PackParams p, const AdamArgs a) {
   __shared__ float s_coef[2];
+  peer_barrier(a);
   const AdamCoef c = adam_coefficients(a, s_coef);
   constexpr int H = kSirenWidth;
   const int L = p.L, C = p.C, d = p.d, Hr = p.Hr;
@@ -246,6 +302,7 @@ __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const
 // The other families: Adam + gradient clearing + step counter in one launch (the packing stays a second one).
 __global__ void __launch_bounds__(256) adam_zero_kernel(const AdamArgs a) {
   __shared__ float s_coef[2];
+  peer_barrier(a);
   const AdamCoef c = adam_coefficients(a, s_coef);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += stride) adam_apply(a, c, i);
@@ -359,8 +416,9 @@ int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, 
 
 int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
                           float beta1, float beta2, float eps, float* state, void* packed, float* loss_out,
+                          const float* const* peer_grads, uint32_t* const* peer_flags, int world, int rank,
                           cudaStream_t stream) {
-  AdamArgs a{params, grads, m, v, state, loss_out, (long long)n, lr, beta1, beta2, eps};
+  AdamArgs a{params, grads, m, v, state, loss_out, (long long)n, lr, beta1, beta2, eps, peer_grads, peer_flags, world, rank};
   if (net->input_mode == B200INR_IN_COORDS && net->activation == B200INR_ACT_SINE) {
     PackParams p{};
     p.params = params;

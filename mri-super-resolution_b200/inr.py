@@ -828,8 +828,26 @@ class FitSession:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.process_group = process_group
         self.n_flat = eng["flat"].numel()
-        # [grad ..., loss accumulator, pad]: cleared once here, then by every optimiser step (no per-step memset)
-        self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)
+        # [grad ..., loss accumulator, pad]: cleared once here, then by every optimiser step (no per-step memset).
+        # Multi-GPU: two alternating buffers in peer-mapped memory, summed across ranks INSIDE the optimiser-step
+        # kernel (b200inr_optimizer_step_peers); without peer access (or with B200INR_PEER_ALLREDUCE=0) one NCCL
+        # all-reduce of the buffer precedes the single-GPU optimiser step.
+        self.peer = None
+        self._parity = 0
+        if process_group is not None and torch.distributed.get_world_size(process_group) > 1 and \
+                os.environ.get("B200INR_PEER_ALLREDUCE", "1") == "1":
+            from . import parallel
+            try:
+                self.peer = parallel.PeerGradients(self.n_flat + 4, dev, process_group)
+            except Exception as exc:  # no symmetric memory on this topology: keep the NCCL path
+                if os.environ.get("B200INR_PEER_ALLREDUCE_STRICT", "0") == "1":
+                    raise
+                import warnings
+                warnings.warn(f"b200inr: peer-mapped gradient exchange unavailable ({exc}); using ncclAllReduce")
+        if self.peer is not None:
+            self.grads = self.peer.grads[0]
+        else:
+            self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)
         self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)  # the last finished step's loss
         self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
@@ -918,51 +936,72 @@ class FitSession:
         with torch.cuda.device(self.device), torch.no_grad():
             s = _stream()
             mark()
-            if self.fused_loss:  # forward + pooled loss + dL/dpred in one kernel: the prediction stays on chip
-                _lib.check(lib.b200inr_siren_forward_pool_loss(net, _ptr(eng["packed"]), gref, rows, _ptr(self.target),
-                                                               self.count, _ptr(self.dpred), _ptr(self.loss_acc),
-                                                               _ptr(self.stash), s), "siren_forward_pool_loss")
+            if rows == 0:
+                # a rank without rows (more ranks than x-plane pairs): it only takes part in the gradient exchange
+                for _ in range(4):
+                    mark()
             else:
-                _lib.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, gref, rows, _ptr(self.pred), 0,
-                                                     0.0, _ptr(self.stash), s), "siren_forward")
-            mark()
-            if self.fused_loss:
-                pass
-            elif self.degrade is None:
-                _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C,
-                                                self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "mse_loss")
-            elif self.degrade == "pool":
-                _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
-                                                self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")
-            else:  # D pred -> MSE against the LR target -> D^T
-                (fx, ax), (fy, ay) = self.taps
-                _lib.check(lib.b200inr_degrade_forward(_ptr(self.pred), _ptr(self.lr_pred), self.X, self.Y, self.ZC,
-                                                       _ptr(fx), _ptr(fy), s), "degrade_forward")
-                _lib.check(lib.b200inr_mse_loss(_ptr(self.lr_pred), _ptr(self.target), None, self.lr_pred.numel(),
-                                                self.count, _ptr(self.lr_grad), _ptr(self.loss_acc), s), "mse_loss")
-                _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
-                                                       _ptr(ax), _ptr(ay), s), "degrade_adjoint")
-            mark()
-            if self.piped:  # one layer-pipelined kernel: dgrad chain + every weight / bias gradient
-                _lib.check(lib.b200inr_siren_backward(net, _ptr(eng["packed"]), _ptr(self.stash), None, gref, rows,
-                                                      _ptr(self.dpred), _ptr(self.grads), s), "siren_backward")
-                mark()
-            else:
-                _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows,
-                                                   _ptr(self.dpred), s), "siren_dgrad")
-                mark()
-                _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
-                           "siren_wgrad")
-            mark()
-            if self.process_group is not None:
+                self._issue_compute(net, gref, s, mark)
+            if self.process_group is not None and self.peer is None:
                 torch.distributed.all_reduce(self.grads, group=self.process_group)
             mark()
-            _lib.check(lib.b200inr_optimizer_step(net, _ptr(eng["flat"]), _ptr(self.grads), _ptr(self.opt["m"]),
-                                                  _ptr(self.opt["v"]), self.lr, self.betas[0], self.betas[1], self.eps,
-                                                  _ptr(self.opt["state"]), _ptr(eng["packed"]), _ptr(self.loss), s),
-                       "optimizer_step")
+            if self.peer is not None:  # gradient exchange inside the kernel; the other buffer is cleared for the next step
+                pg, par = self.peer, self._parity
+                _lib.check(lib.b200inr_optimizer_step_peers(
+                    net, _ptr(eng["flat"]), _ptr(pg.grads[par ^ 1]), _ptr(pg.peer_grads[par]), _ptr(pg.peer_flags),
+                    pg.world, pg.rank, _ptr(self.opt["m"]), _ptr(self.opt["v"]), self.lr, self.betas[0], self.betas[1],
+                    self.eps, _ptr(self.opt["state"]), _ptr(eng["packed"]), _ptr(self.loss), s), "optimizer_step_peers")
+                self._parity = par ^ 1
+                self.grads = pg.grads[self._parity]
+                self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
+            else:
+                _lib.check(lib.b200inr_optimizer_step(net, _ptr(eng["flat"]), _ptr(self.grads), _ptr(self.opt["m"]),
+                                                      _ptr(self.opt["v"]), self.lr, self.betas[0], self.betas[1],
+                                                      self.eps, _ptr(self.opt["state"]), _ptr(eng["packed"]),
+                                                      _ptr(self.loss), s), "optimizer_step")
             mark()
         return self.loss
+
+    def _issue_compute(self, net, gref, s, mark):
+        """forward -> loss (+ degradation) -> backward of this rank's rows; `mark` records the stage boundaries."""
+        m, eng, lib = self.module, self.eng, self.lib
+        rows, C = self.rows, self.C
+        if self.fused_loss:  # forward + pooled loss + dL/dpred in one kernel: the prediction stays on chip
+            _lib.check(lib.b200inr_siren_forward_pool_loss(net, _ptr(eng["packed"]), gref, rows, _ptr(self.target),
+                                                           self.count, _ptr(self.dpred), _ptr(self.loss_acc),
+                                                           _ptr(self.stash), s), "siren_forward_pool_loss")
+        else:
+            _lib.check(lib.b200inr_siren_forward(net, _ptr(eng["packed"]), None, gref, rows, _ptr(self.pred), 0,
+                                                 0.0, _ptr(self.stash), s), "siren_forward")
+        mark()
+        if self.fused_loss:
+            pass
+        elif self.degrade is None:
+            _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C,
+                                            self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "mse_loss")
+        elif self.degrade == "pool":
+            _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
+                                            self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")
+        else:  # D pred -> MSE against the LR target -> D^T
+            (fx, ax), (fy, ay) = self.taps
+            _lib.check(lib.b200inr_degrade_forward(_ptr(self.pred), _ptr(self.lr_pred), self.X, self.Y, self.ZC,
+                                                   _ptr(fx), _ptr(fy), s), "degrade_forward")
+            _lib.check(lib.b200inr_mse_loss(_ptr(self.lr_pred), _ptr(self.target), None, self.lr_pred.numel(),
+                                            self.count, _ptr(self.lr_grad), _ptr(self.loss_acc), s), "mse_loss")
+            _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
+                                                   _ptr(ax), _ptr(ay), s), "degrade_adjoint")
+        mark()
+        if self.piped:  # one layer-pipelined kernel: dgrad chain + every weight / bias gradient
+            _lib.check(lib.b200inr_siren_backward(net, _ptr(eng["packed"]), _ptr(self.stash), None, gref, rows,
+                                                  _ptr(self.dpred), _ptr(self.grads), s), "siren_backward")
+            mark()
+        else:
+            _lib.check(lib.b200inr_siren_dgrad(net, _ptr(eng["packed"]), _ptr(self.stash), rows,
+                                               _ptr(self.dpred), s), "siren_dgrad")
+            mark()
+            _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
+                       "siren_wgrad")
+        mark()
 
     def finish(self):
         """Write the fp32 master weights back into the module's nn.Parameters."""

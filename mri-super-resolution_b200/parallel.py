@@ -31,3 +31,38 @@ def lr_slab(target_lr, shape, row_range):
     plane = int(np.prod(shape[1:]))
     x0, x1 = row_range[0] // plane, row_range[1] // plane
     return target_lr[x0 // 2:x1 // 2]
+
+
+class PeerGradients:
+    """Peer-mapped (symmetric) storage for the in-kernel gradient exchange of b200inr_optimizer_step_peers.
+
+    One symmetric allocation per rank holds the two alternating [grad | loss | pad] buffers (a step accumulates into one
+    while the other is being cleared for the next step) and the flag words of the kernel's start barrier;
+    torch.distributed._symmetric_memory maps every rank's allocation into every other rank's address space over
+    NVLink (torch supplies the memory and the rendezvous; the exchange itself is in the kernel).  Raises when the
+    process group / device topology has no peer access: the caller then falls back to an NCCL all-reduce followed by
+    b200inr_optimizer_step.
+    """
+
+    FLAG_WORDS = 64
+
+    def __init__(self, n_floats, device, group):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if n_floats % 4:
+            raise ValueError("the gradient buffer length must keep 16-byte alignment")
+        self.n = int(n_floats)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > self.FLAG_WORDS:
+            raise ValueError("too many ranks for the flag area")
+        self.buf = symm.empty(2 * self.n + self.FLAG_WORDS, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        base = [int(p) for p in self.handle.buffer_ptrs]
+        self.grads = [self.buf[0:self.n], self.buf[self.n:2 * self.n]]
+        self.peer_grads = [torch.tensor([b + par * self.n * 4 for b in base], dtype=torch.int64, device=device)
+                           for par in (0, 1)]
+        self.peer_flags = torch.tensor([b + 2 * self.n * 4 for b in base], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffers are zero before any kernel announces an epoch

@@ -1070,3 +1070,56 @@ def test_gabor_first_layer_standalone_forward(dev):
     hidden = b200inr.ComplexGaborLayer2D(128, 128, is_first=False).to(dev)
     with pytest.raises(RuntimeError):
         hidden(out)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def test_optimizer_step_peers_single_rank(dev):
+    """b200inr_optimizer_step_peers with world = 1 (the sum over one peer-mapped buffer, this rank's own, the start
+    barrier against itself, the alternating clear) == b200inr_optimizer_step, bit for bit."""
+    torch.manual_seed(2)
+    m = b200inr.Siren(3, 256, 4, 31).to(dev)
+    eng = m._sync_params()
+    lib, net = L.load(), ctypes.byref(m._desc)
+    n = eng["flat"].numel()
+    p_a, p_b = eng["flat"].clone(), eng["flat"].clone()
+    pk_a = b200inr.inr._aligned_bytes(eng["packed"].numel(), dev)
+    pk_b = b200inr.inr._aligned_bytes(eng["packed"].numel(), dev)
+    pk_a.copy_(eng["packed"]); pk_b.copy_(eng["packed"])
+    m_a, v_a, m_b, v_b = (torch.zeros(n, device=dev) for _ in range(4))
+    s_a, s_b = torch.zeros(4, device=dev), torch.zeros(4, device=dev)
+    bufs = [torch.zeros(n + 4, device=dev), torch.zeros(n + 4, device=dev)]
+    flags = torch.zeros(64, dtype=torch.int32, device=dev)
+    peer_flags = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=dev)
+    loss_a, loss_b = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    live = torch.zeros(n + 4, device=dev)  # (segments are padded to 4 floats: no gradient ever lands in the padding)
+    for o, prm in zip(eng["offsets"], m._canonical()):
+        live[o:o + prm.numel()] = 1.0
+    live[n] = 1.0
+    for step in range(4):
+        par = step & 1
+        g = torch.randn(n + 4, device=dev) * 1e-3 * live
+        bufs[par].copy_(g)
+        g_a = g.clone()
+        peer_grads = torch.tensor([bufs[par].data_ptr()], dtype=torch.int64, device=dev)
+        L.check(lib.b200inr_optimizer_step(net, _ptr(p_a), _ptr(g_a), _ptr(m_a), _ptr(v_a), 1e-4, 0.9, 0.999, 1e-8,
+                                           _ptr(s_a), _ptr(pk_a), _ptr(loss_a), _stream()), "optimizer_step")
+        L.check(lib.b200inr_optimizer_step_peers(net, _ptr(p_b), _ptr(bufs[par ^ 1]), _ptr(peer_grads), _ptr(peer_flags),
+                                                 1, 0, _ptr(m_b), _ptr(v_b), 1e-4, 0.9, 0.999, 1e-8, _ptr(s_b), _ptr(pk_b),
+                                                 _ptr(loss_b), _stream()), "optimizer_step_peers")
+        torch.cuda.synchronize()
+        assert torch.equal(p_a, p_b) and torch.equal(m_a, m_b) and torch.equal(v_a, v_b) and torch.equal(pk_a, pk_b)
+        assert loss_a.item() == loss_b.item() == g[n].item()
+        assert int(flags[0]) == step + 1 and not bufs[par ^ 1].any()
+
+
+def test_multi_gpu_fit_equals_single_rank(dev):
+    """2-rank NCCL + peer-memory fit == single-rank fit (tools/multi_gpu_check.py under torchrun); needs 2 GPUs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi_gpu)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29511",
+                          os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MULTI_GPU_CHECK OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
