@@ -166,6 +166,16 @@ int b200inr_degrade_forward(const float* hr, float* lr, int32_t X, int32_t Y, in
 /* D^T: lr [X/2,Y/2,ZC] -> hr [X,Y,ZC] (adjoint taps). */
 int b200inr_degrade_adjoint(const float* lr, float* hr, int32_t X, int32_t Y, int64_t ZC,
                             const b200inr_axis_taps* ax, const b200inr_axis_taps* ay, void* stream);
+/* The blurred degradation as a banded operator (host helper): fwd6_host [n_hr/2][6] = D[i][2i-2 .. 2i+3] (mirror-merged
+ * weights, zero where a tap leaves the volume), adj3_host [n_hr][3] = D[((x-2)>>1) + t][x], t = 0..2. */
+int b200inr_degrade_build_band_host(int32_t n_hr, int blur, float* fwd6_host, float* adj3_host);
+/* Fused blur + pool consistency loss (dwi_inr.ipynb#c6:L8's rescale(.5, anti_aliasing=True) as the degradation; SURVEY.md
+ * section 8c) in two streaming passes: resid_lr [X/2, Y/2, ZC] = D pred - target (workspace, also an output),
+ * loss_accum[0] += sum(resid^2)/count, grad_hr = D^T (2 resid / count) (skipped when NULL).  bx6/by6/ax3/ay3: DEVICE copies
+ * of the band tables of the x and y axes.  Replaces b200inr_degrade_forward + b200inr_mse_loss + b200inr_degrade_adjoint. */
+int b200inr_blurpool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC, double count,
+                         const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid_lr,
+                         float* grad_hr, float* loss_accum, void* stream);
 /* Fused 2x2x1 average-pool consistency loss: loss_accum[0] += sum((pool(pred)-target_lr)^2)/count and
  * grad_hr = pool^T(2*(pool(pred)-target_lr)/count), one pass (the fast path of BASELINE config 2). */
 int b200inr_pool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC,

@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200inr_degrade_build_axis_host": (ctypes.c_int, [_i32, ctypes.c_int, _P(AxisTaps), _P(AxisTaps)]),
     "b200inr_degrade_forward": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "b200inr_degrade_adjoint": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "b200inr_degrade_build_band_host": (ctypes.c_int, [_i32, ctypes.c_int, _P(_f32), _P(_f32)]),
+    "b200inr_blurpool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200inr_pool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp]),
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b200inr_optimizer_step": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
@@ -155,6 +157,16 @@ def stash_bytes(net, rows):
     n = _sz(0)
     check(load().b200inr_stash_bytes(ctypes.byref(net), int(rows), ctypes.byref(n)), "stash_bytes")
     return n.value
+
+
+def build_band_tables(n_hr, blur):
+    """(fwd6 [n_hr/2, 6], adj3 [n_hr, 3]) float32 NumPy arrays: the banded form of the degradation along one axis."""
+    import numpy as np
+    fwd = np.zeros((n_hr // 2, 6), dtype=np.float32)
+    adj = np.zeros((n_hr, 3), dtype=np.float32)
+    check(load().b200inr_degrade_build_band_host(int(n_hr), int(bool(blur)), fwd.ctypes.data_as(_P(_f32)),
+                                                 adj.ctypes.data_as(_P(_f32))), "degrade_build_band_host")
+    return fwd, adj
 
 
 def build_axis_taps(n_hr, blur):

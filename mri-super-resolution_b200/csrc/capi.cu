@@ -44,6 +44,9 @@ int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_
                     float* loss_accum, cudaStream_t stream);
 int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int64_t ZC, const b200inr_axis_taps* tx,
                 const b200inr_axis_taps* ty, cudaStream_t stream);
+int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count,
+                        const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid,
+                        float* grad, float* loss_accum, cudaStream_t stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float* state, cudaStream_t stream);
 int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
@@ -415,6 +418,44 @@ int b200inr_degrade_build_axis_host(int32_t n_hr, int blur, b200inr_axis_taps* f
     }
   }
   return B200INR_OK;
+}
+
+int b200inr_degrade_build_band_host(int32_t n_hr, int blur, float* fwd6_host, float* adj3_host) {
+  if (!fwd6_host || !adj3_host) return B200INR_ERR_NULL;
+  if (n_hr < 2 || (n_hr & 1) || n_hr > (1 << 20)) return B200INR_ERR_BAD_SHAPE;
+  const int n_lr = n_hr / 2;
+  b200inr_axis_taps* fwd = new b200inr_axis_taps[n_lr];
+  b200inr_axis_taps* adj = new b200inr_axis_taps[n_hr];
+  int e = b200inr_degrade_build_axis_host(n_hr, blur, fwd, adj);
+  if (e == B200INR_OK) {
+    memset(fwd6_host, 0, sizeof(float) * size_t(n_lr) * 6);
+    memset(adj3_host, 0, sizeof(float) * size_t(n_hr) * 3);
+    for (int i = 0; i < n_lr && e == B200INR_OK; ++i)
+      for (int k = 0; k < B200INR_DEGRADE_MAX_TAPS; ++k) {
+        if (fwd[i].w[k] == 0.f) continue;
+        const int x = fwd[i].idx[k];
+        const int a = x - (2 * i - 2);    // position inside LR row i's band of HR rows
+        const int t = i - ((x - 2) >> 1);  // position inside HR row x's band of LR rows
+        if (a < 0 || a >= 6 || t < 0 || t >= 3) {
+          e = B200INR_ERR_BAD_SHAPE;
+          break;
+        }
+        fwd6_host[i * 6 + a] += fwd[i].w[k];
+        adj3_host[x * 3 + t] += fwd[i].w[k];
+      }
+  }
+  delete[] fwd;
+  delete[] adj;
+  return e;
+}
+
+int b200inr_blurpool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC, double count,
+                         const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid_lr,
+                         float* grad_hr, float* loss_accum, void* stream) {
+  if (!pred_hr || !target_lr || !bx6 || !by6 || !ax3 || !ay3 || !resid_lr) return B200INR_ERR_NULL;
+  if (!(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  return launch_blurpool_mse(pred_hr, target_lr, X, Y, ZC, count, bx6, by6, ax3, ay3, resid_lr, grad_hr, loss_accum,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_degrade_forward(const float* hr, float* lr, int32_t X, int32_t Y, int64_t ZC, const b200inr_axis_taps* tx,

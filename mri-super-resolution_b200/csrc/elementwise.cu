@@ -165,6 +165,195 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ fused blur + pool consistency loss
+// D = (2x2x1 average) o (5-tap Gaussian, sigma 0.5, mirror boundary) is separable and BANDED: LR row i reads HR rows
+// 2i-2 .. 2i+3 (6 dense taps per axis, mirror-merged weights; zeros outside the volume), and HR row x is read by the LR
+// rows ((x-2)>>1) .. +2 (3 dense taps).  Two streaming passes replace the three generic tap kernels:
+//   residual: r = D pred - target (+ the loss).  A thread owns 4 consecutive zc of one LR column j and MARCHES along x with
+//             a 6-deep register window of y-filtered rows, so every new LR row costs 12 loads (2 new HR rows x 6 y taps,
+//             float4, coalesced along zc; the y neighbours come from L1) instead of 36;
+//   adjoint : dL/dpred = D^T 2 r / count.  A thread owns 4 zc of one HR column y and marches along x with a 3-deep window
+//             of y-filtered residual rows: 3 loads per LR row, two HR rows written per step.
+// HBM traffic is the algorithmic minimum (pred + target read, residual written and re-read from L2, gradient written).
+constexpr int kBandFwd = 6, kBandAdj = 3, kBlurChunk = 8;
+
+template <int V>
+struct VecF {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ VecF<V> ldv(const float* p) {
+  VecF<V> r;
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[V > 2 ? 2 : 0] = t.z; r.v[V > 3 ? 3 : 0] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const VecF<V>& r) {
+  if (V == 4)
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[V > 2 ? 2 : 0], r.v[V > 3 ? 3 : 0]);
+  else
+    p[0] = r.v[0];
+}
+
+template <int V>
+__global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
+    const float* __restrict__ pred, const float* __restrict__ target, int X, int Y, long long ZC,
+    const float* __restrict__ bx6, const float* __restrict__ by6, float inv_count, float* __restrict__ resid,
+    float* loss_accum) {
+  const int XL = X / 2, YL = Y / 2;
+  const long long zcv = ZC / V;
+  const int chunks = (XL + kBlurChunk - 1) / kBlurChunk;
+  const long long total = (long long)chunks * YL * zcv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long zc = (t % zcv) * V;
+    const int j = int((t / zcv) % YL);
+    const int ic = int(t / (zcv * YL));
+    const int i0 = ic * kBlurChunk, i1 = min(i0 + kBlurChunk, XL);
+    float wy[kBandFwd];
+#pragma unroll
+    for (int b = 0; b < kBandFwd; ++b) wy[b] = __ldg(by6 + j * kBandFwd + b);
+    // y-filtered HR row x of this column: sum_b wy[b] pred[x, 2j-2+b, zc]  (zero weight where the tap leaves the volume)
+    auto row = [&](int x) {
+      VecF<V> s;
+#pragma unroll
+      for (int e = 0; e < V; ++e) s.v[e] = 0.f;
+      if (x < 0 || x >= X) return s;
+#pragma unroll
+      for (int b = 0; b < kBandFwd; ++b) {
+        const int y = 2 * j - 2 + b;
+        if (y < 0 || y >= Y) continue;
+        const VecF<V> pv = ldv<V>(pred + ((long long)x * Y + y) * ZC + zc);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], pv.v[e], s.v[e]);
+      }
+      return s;
+    };
+    VecF<V> w[kBandFwd];
+#pragma unroll
+    for (int a = 0; a < kBandFwd; ++a) w[a] = row(2 * i0 - 2 + a);
+    for (int i = i0; i < i1; ++i) {
+      const VecF<V> tg = ldv<V>(target + ((long long)i * YL + j) * ZC + zc);
+      VecF<V> r;
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.v[e] = 0.f;
+#pragma unroll
+      for (int a = 0; a < kBandFwd; ++a) {
+        const float wx = __ldg(bx6 + i * kBandFwd + a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) r.v[e] = fmaf(wx, w[a].v[e], r.v[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        r.v[e] -= tg.v[e];
+        acc = fmaf(r.v[e], r.v[e], acc);
+      }
+      stv<V>(resid + ((long long)i * YL + j) * ZC + zc, r);
+      if (i + 1 < i1) {
+#pragma unroll
+        for (int a = 0; a < kBandFwd - 2; ++a) w[a] = w[a + 2];
+        w[kBandFwd - 2] = row(2 * i + 4);
+        w[kBandFwd - 1] = row(2 * i + 5);
+      }
+    }
+  }
+  if (loss_accum) block_accumulate(acc * inv_count, loss_accum);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
+    const float* __restrict__ resid, int X, int Y, long long ZC, const float* __restrict__ ax3,
+    const float* __restrict__ ay3, float gscale, float* __restrict__ grad) {
+  const int XL = X / 2, YL = Y / 2;
+  const long long zcv = ZC / V;
+  const int chunks = (XL + kBlurChunk - 1) / kBlurChunk;
+  const long long total = (long long)chunks * Y * zcv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long zc = (t % zcv) * V;
+    const int y = int((t / zcv) % Y);
+    const int mc = int(t / (zcv * Y));
+    const int m0 = mc * kBlurChunk, m1 = min(m0 + kBlurChunk, XL);
+    const int j0 = (y - 2) >> 1;  // LR columns j0 .. j0+2 read HR column y
+    float wy[kBandAdj];
+#pragma unroll
+    for (int b = 0; b < kBandAdj; ++b) wy[b] = __ldg(ay3 + y * kBandAdj + b);
+    auto row = [&](int i) {  // y-filtered residual row i of this HR column
+      VecF<V> s;
+#pragma unroll
+      for (int e = 0; e < V; ++e) s.v[e] = 0.f;
+      if (i < 0 || i >= XL) return s;
+#pragma unroll
+      for (int b = 0; b < kBandAdj; ++b) {
+        const int j = j0 + b;
+        if (j < 0 || j >= YL) continue;
+        const VecF<V> rv = ldv<V>(resid + ((long long)i * YL + j) * ZC + zc);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], rv.v[e], s.v[e]);
+      }
+      return s;
+    };
+    // HR rows 2m and 2m+1 are both read by the LR rows m-1, m, m+1
+    VecF<V> w[kBandAdj];
+#pragma unroll
+    for (int a = 0; a < kBandAdj; ++a) w[a] = row(m0 - 1 + a);
+    for (int m = m0; m < m1; ++m) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = 2 * m + h;
+        VecF<V> g;
+#pragma unroll
+        for (int e = 0; e < V; ++e) g.v[e] = 0.f;
+#pragma unroll
+        for (int a = 0; a < kBandAdj; ++a) {
+          const float wx = __ldg(ax3 + x * kBandAdj + a);
+#pragma unroll
+          for (int e = 0; e < V; ++e) g.v[e] = fmaf(wx, w[a].v[e], g.v[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) g.v[e] *= gscale;
+        stv<V>(grad + ((long long)x * Y + y) * ZC + zc, g);
+      }
+      if (m + 1 < m1) {
+        w[0] = w[1];
+        w[1] = w[2];
+        w[2] = row(m + 2);
+      }
+    }
+  }
+}
+
+int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count,
+                        const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid,
+                        float* grad, float* loss_accum, cudaStream_t stream) {
+  if ((X & 1) || (Y & 1) || X < 2 || Y < 2 || ZC < 1) return B200INR_ERR_BAD_SHAPE;
+  const bool vec = (ZC % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
+                                      reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
+  const int chunks = (X / 2 + kBlurChunk - 1) / kBlurChunk;
+  const long long zcv = vec ? ZC / 4 : ZC;
+  auto nblocks = [&](long long total) {
+    long long b = (total + kEwThreads - 1) / kEwThreads;
+    if (b > kSmCount * 16) b = kSmCount * 16;
+    return int(b < 1 ? 1 : b);
+  };
+  const int b1 = nblocks((long long)chunks * (Y / 2) * zcv), b2 = nblocks((long long)chunks * Y * zcv);
+  const float inv = float(1.0 / count), gsc = float(2.0 / count);
+  if (vec) {
+    blurpool_residual_kernel<4><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum);
+    if (grad) blurpool_adjoint_kernel<4><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad);
+  } else {
+    blurpool_residual_kernel<1><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum);
+    if (grad) blurpool_adjoint_kernel<1><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad);
+  }
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------ torch.optim.Adam.step   INR/superresDWI.py:115-116,138
 // Arithmetic follows torch's single-tensor formulation (bias corrections in double on the step count, everything
 // else fp32): m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).

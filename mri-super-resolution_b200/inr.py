@@ -802,13 +802,12 @@ class FitSession:
             if target.numel() != rows * C // 4:
                 raise RuntimeError("b200inr: pooled fit target must have rows*C/4 elements")
             self.count = float(rows * C // 4)
-            self.taps = []
+            # banded form of D along x and y (6 taps per LR row, 3 per HR row): operands of b200inr_blurpool_mse
+            self.bands = []
             for n_hr in (shape[0], shape[1]):
-                fwd, adj = _lib.build_axis_taps(n_hr, True)
-                self.taps.append((torch.frombuffer(bytearray(bytes(fwd)), dtype=torch.uint8).to(dev),
-                                  torch.frombuffer(bytearray(bytes(adj)), dtype=torch.uint8).to(dev)))
-            self.lr_pred = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
-            self.lr_grad = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
+                fwd6, adj3 = _lib.build_band_tables(n_hr, True)
+                self.bands.append((torch.from_numpy(fwd6).to(dev), torch.from_numpy(adj3).to(dev)))
+            self.lr_resid = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
         else:
             raise ValueError("degrade must be None, 'pool' or 'blur_pool'")
         self.target = target
@@ -859,18 +858,20 @@ class FitSession:
         self.piped = (d.activation == _lib.ACT_SINE and d.input_mode == _lib.IN_COORDS
                       and not (d.flags & _lib.NET_STAGED_BWD))
         # Pooled loss fused into the forward's final epilogue (b200inr_siren_forward_pool_loss): possible when a 128-row
-        # tile holds whole y pairs and its pooling partner is a whole tile away.  Opt-in (B200INR_FUSED_LOSS=1): it
-        # removes one launch and 260 MB of HBM traffic per cfg2 step, but measured on B200 it is a tie (0.754 ms vs
-        # 0.706 + 0.049 ms) -- the epilogue warps are the forward's critical resource and, unlike the plain copy-out,
-        # the loss arithmetic does not hide under their waits for the final MMAs.
+        # tile holds whole y pairs and its pooling partner is a whole tile away.  It removes one launch and 260 MB of
+        # HBM traffic per cfg2 step, but measured on B200 it is a tie at full size (0.754 ms vs 0.706 + 0.049 ms: the
+        # epilogue warps are the forward's critical resource and, unlike the plain copy-out, the loss arithmetic does
+        # not hide under their waits for the final MMAs), so it is the default only for small slabs (strong-scaled
+        # shards, cfg1-like sizes), where the saved launch counts.  B200INR_FUSED_LOSS=0/1 overrides.
         self.fused_loss = False
-        if degrade == "pool" and self.piped and os.environ.get("B200INR_FUSED_LOSS", "0") == "1":
+        want = os.environ.get("B200INR_FUSED_LOSS", "1" if rows <= (1 << 18) else "0") == "1"
+        if degrade == "pool" and self.piped and want:
             Y, Z = shape[1], shape[2]
             self.fused_loss = (128 % (2 * Z) == 0 and (Y * Z) % 128 == 0 and rows % (2 * Y * Z) == 0
                                and begin % (2 * Y * Z) == 0)
-        # forward, loss (3 kernels for blur_pool), backward (dgrad + wgrad when staged), optimiser step (+ pack kernel
+        # forward, loss (2 kernels for blur_pool), backward (dgrad + wgrad when staged), optimiser step (+ pack kernel
         # for the families whose operands are re-staged by a second launch)
-        self.kernel_launches_per_step = (1 + (3 if degrade == "blur_pool" else (0 if self.fused_loss else 1)) +
+        self.kernel_launches_per_step = (1 + (2 if degrade == "blur_pool" else (0 if self.fused_loss else 1)) +
                                          (1 if self.piped else 2) +
                                          (1 if (d.activation == _lib.ACT_SINE and d.input_mode == _lib.IN_COORDS) else 2))
         self._graph = None
@@ -982,14 +983,11 @@ class FitSession:
         elif self.degrade == "pool":
             _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
                                             self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")
-        else:  # D pred -> MSE against the LR target -> D^T
-            (fx, ax), (fy, ay) = self.taps
-            _lib.check(lib.b200inr_degrade_forward(_ptr(self.pred), _ptr(self.lr_pred), self.X, self.Y, self.ZC,
-                                                   _ptr(fx), _ptr(fy), s), "degrade_forward")
-            _lib.check(lib.b200inr_mse_loss(_ptr(self.lr_pred), _ptr(self.target), None, self.lr_pred.numel(),
-                                            self.count, _ptr(self.lr_grad), _ptr(self.loss_acc), s), "mse_loss")
-            _lib.check(lib.b200inr_degrade_adjoint(_ptr(self.lr_grad), _ptr(self.dpred), self.X, self.Y, self.ZC,
-                                                   _ptr(ax), _ptr(ay), s), "degrade_adjoint")
+        else:  # r = D pred - target (+ loss), then dL/dpred = D^T 2 r / count: two streaming passes
+            (bx6, ax3), (by6, ay3) = self.bands
+            _lib.check(lib.b200inr_blurpool_mse(_ptr(self.pred), _ptr(self.target), self.X, self.Y, self.ZC, self.count,
+                                                _ptr(bx6), _ptr(by6), _ptr(ax3), _ptr(ay3), _ptr(self.lr_resid),
+                                                _ptr(self.dpred), _ptr(self.loss_acc), s), "blurpool_mse")
         mark()
         if self.piped:  # one layer-pipelined kernel: dgrad chain + every weight / bias gradient
             _lib.check(lib.b200inr_siren_backward(net, _ptr(eng["packed"]), _ptr(self.stash), None, gref, rows,

@@ -1123,3 +1123,26 @@ def test_multi_gpu_fit_equals_single_rank(dev):
                           "--master-addr", "127.0.0.1", "--master-port", "29511",
                           os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MULTI_GPU_CHECK OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("shape,C", [((12, 10, 5), 31), ((8, 16, 4), 4), ((2, 2, 3), 1), ((34, 6, 2), 6)])
+def test_blurpool_mse_vs_oracle(dev, shape, C):
+    """b200inr_blurpool_mse (banded blur + pool residual and adjoint, two streaming passes) against the oracle's
+    dense operator: residual D pred - target, loss, and dL/dpred = D^T 2 r / count; includes volumes smaller than the
+    tap support (mirror boundary folds back) and ZC not divisible by 4 (scalar path)."""
+    X, Y, Z = shape
+    rng = np.random.RandomState(7)
+    hr = rng.rand(X, Y, Z, C).astype(np.float32)
+    tgt = rng.rand(X // 2, Y // 2, Z, C).astype(np.float32)
+    d_ref = O.degrade_forward(hr, True) - tgt
+    count = float(tgt.size)
+    g_ref = O.degrade_adjoint((2.0 * d_ref / count).astype(np.float32), True)
+    (bx6, ax3), (by6, ay3) = [tuple(torch.from_numpy(t).to(dev) for t in L.build_band_tables(n, True)) for n in (X, Y)]
+    pred, target = torch.from_numpy(hr).to(dev), torch.from_numpy(tgt).to(dev)
+    resid, grad, loss = torch.empty_like(target), torch.empty_like(pred), torch.zeros(1, device=dev)
+    L.check(L.load().b200inr_blurpool_mse(_ptr(pred), _ptr(target), X, Y, Z * C, count, _ptr(bx6), _ptr(by6), _ptr(ax3),
+                                          _ptr(ay3), _ptr(resid), _ptr(grad), _ptr(loss), _stream()), "blurpool_mse")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(resid.cpu().numpy(), d_ref, atol=3e-6)
+    np.testing.assert_allclose(grad.cpu().numpy(), g_ref, atol=3e-6 / count * 4 + 1e-9)
+    assert abs(loss.item() - float((d_ref.astype(np.float64) ** 2).mean())) <= 1e-5 * float((d_ref ** 2).mean())
