@@ -16,7 +16,8 @@ constexpr int kDzoPad = 64;        // dL/dout tile width (one 128-byte swizzle r
 // Byte offsets inside the packed (bf16, omega-folded) weight buffer of a width-H SIREN.
 struct PackLayout {
   size_t w0;     // float4[H]            omega0 * W0 rows, zero padded to 4 inputs
-  size_t bias;   // float[(L+1)*H + 32]  omega * b of the sine layers, then the final bias (padded to 32)
+  size_t bias;   // float[(L+1)*H + 32 + H]  omega * b of the sine layers, the final bias (padded to 32), then H zeros
+                 //                      (what the forward adds in the first layer, whose bias is part of the GEMM)
   size_t wh;     // L x [H/64][H][64]    forward B operand of hidden layer l (N = out, K = in), omega_h * W_l
   size_t wht;    // L x [H/64][H][64]    dgrad   B operand of hidden layer l (N = in, K = out), omega_h * W_l^T
   size_t wf;     // [H/64][32][64]       forward B operand of the final linear (N = c, K = in)
@@ -32,7 +33,7 @@ __host__ __device__ inline PackLayout make_pack_layout(int H, int L) {
   p.w0 = o;
   o += size_t(H) * 16;
   p.bias = o;
-  o += (size_t(L + 1) * H + 32) * 4;
+  o += (size_t(L + 1) * H + 32 + H) * 4;
   o = (o + 1023) & ~size_t(1023);
   p.wh = o;
   o += size_t(L) * H * H * 2;

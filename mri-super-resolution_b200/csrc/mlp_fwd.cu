@@ -104,9 +104,9 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
       const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
       yb[j] = (B200INR_FKO & 2) ? pack_bf16x2(t0, t1) : pack_bf16x2(__sinf(t0), __sinf(t1));
       if (kStash) {
-        const uint32_t p0 = __float_as_uint(fmaf(t0, kPhaseScale, kPhaseMagic));
-        const uint32_t p1 = __float_as_uint(fmaf(t1, kPhaseScale, kPhaseMagic));
-        ph[j] = __byte_perm(p0, p1, 0x5410);
+        float p0, p1;
+        fma_f32x2(t0, t1, kPhaseScale, kPhaseMagic, p0, p1);
+        ph[j] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x5410);
       }
     }
     if (!(B200INR_FKO & 4) || yb[0] == 0x12345678u)
@@ -148,7 +148,8 @@ struct WSlots {
   }
 };
 
-// Walks the schedule of one CTA: on_tile(pr, l, j) before the chunks of tile j of layer step l, then
+// Walks the schedule of one CTA: on_tile(ws, pr, l, j, nk, slots) before the chunks of tile j of layer step l (slots: 4
+// bits per K chunk; for j = 0 none of them has been loaded / waited for yet and ws holds their parities), then
 // on_chunk(l, j, k, i, slot, first_use, last_use) for every chunk use (k = K chunk, i = position in this tile's order).
 template <class FT, class FC>
 __device__ __forceinline__ void walk_weight_schedule(int num_pairs, int my_tiles, int L, int nslots, FT&& on_tile,
@@ -160,17 +161,17 @@ __device__ __forceinline__ void walk_weight_schedule(int num_pairs, int my_tiles
     for (int l = 0; l <= L + 1; ++l) {
       const int nk = (l == 0) ? 1 : 4;
       uint32_t slot_of = 0;  // 4 bits per K chunk
-      on_tile(pr, l, 0);
+      for (int k = 0; k < nk; ++k) slot_of |= ws.pop() << (4 * k);
+      on_tile(ws, pr, l, 0, nk, slot_of);
       for (int k = 0; k < nk; ++k) {
-        const uint32_t s = ws.pop();
-        slot_of |= s << (4 * k);
+        const uint32_t s = (slot_of >> (4 * k)) & 15u;
         on_chunk(ws, l, 0, k, k, s, true, nt == 1);
         ws.par ^= 1u << s;
         ws.used |= 1u << s;
         if (nt == 1) ws.push(s);
       }
       if (nt == 2) {
-        on_tile(pr, l, 1);
+        on_tile(ws, pr, l, 1, nk, slot_of);
         for (int k = 0; k < nk; ++k) {  // same K order as tile 0: results do not depend on a tile's position
           const uint32_t s = (slot_of >> (4 * k)) & 15u;
           on_chunk(ws, l, 1, k, k, s, false, true);
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     // released by its last reader (w_empty: commit of the MMAs of tile 1, or of tile 0 in a single-tile slot)
     if (lane == 0) {
       walk_weight_schedule(
-          num_pairs, my_tiles, L, kFwdSlots, [](int, int, int) {},
+          num_pairs, my_tiles, L, kFwdSlots, [](const WSlots&, int, int, int, int, uint32_t) {},
           [&](const WSlots& ws, int l, int, int k, int, uint32_t slot, bool first_use, bool) {
             if (!first_use) return;
             if ((B200INR_FKO & 1) && ((ws.used >> slot) & 1u)) return;
@@ -291,7 +292,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       int nk4 = 4, cur_tph = 0;
       walk_weight_schedule(
           num_pairs, my_tiles, L, kFwdSlots,
-          [&](int pr, int l, int j) {
+          [&](const WSlots& ws, int pr, int l, int j, int nk, uint32_t slots) {
+            // Weights first, THEN the A tile: the layer's chunks were requested a tile ago and have (almost always)
+            // landed, so their barrier round trips (~100-150 cycles each on the busy shared-memory pipe) are spent
+            // while the warp would idle waiting for the epilogue anyway, and the MMAs go out back to back the moment
+            // the operand is ready (tile 0's MMA phase was 0.5 k cycles longer than tile 1's for these four waits).
+            if (j == 0) {
+              for (int k = 0; k < nk; ++k) {
+                const uint32_t slot = (slots >> (4 * k)) & 15u;
+                if (!(B200INR_FKO & 1) || !((ws.used >> slot) & 1u)) mbar_wait(&w_full[slot], (ws.par >> slot) & 1u);
+              }
+            }
             idesc = (l <= L) ? idesc_bf16(kM, H, false, false) : idesc_bf16(kM, kOutPad, false, false);
             nk4 = (l == 0) ? 2 : 4;  // first layer: K = 32 (hi/lo coordinate operand)
             const int tph = cur_tph = (pr * (L + 3) + l) * 2 + j;
@@ -302,10 +313,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             tc_fence_after();
           },
           [&](const WSlots& ws, int l, int j, int k, int i, uint32_t slot, bool first_use, bool last_use) {
-            if (first_use && (!(B200INR_FKO & 1) || !((ws.used >> slot) & 1u))) {
-              mbar_wait(&w_full[slot], (ws.par >> slot) & 1u);  // pair: own half landed AND the peer's relay arrived
-              tc_fence_after();
-            }
+            (void)first_use;  // (tile 0's chunks were waited for in on_tile; pair: own half landed AND the peer relayed)
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               if (k4 < nk4) {
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
       // mbarrier wait costs the issuing warp ~100-150 cycles on the busy shared-memory pipe, and with two waits per
       // chunk the issue loop, not the tensor pipe, paced the layer)
       walk_weight_schedule(
-          num_pairs, my_tiles, L, kFwdSlots, [](int, int, int) {},
+          num_pairs, my_tiles, L, kFwdSlots, [](const WSlots&, int, int, int, int, uint32_t) {},
           [&](const WSlots& ws, int, int, int, int, uint32_t slot, bool first_use, bool) {
             if (!first_use) return;
             if ((B200INR_FKO & 1) && ((ws.used >> slot) & 1u)) return;
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         for (int j = 0; j < nt; ++j) {
           const int tile = tile_of(pr, j);
           const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-          const float* bl = bias_g + l * H;
+          const float* bl = (l == 0) ? bias_g + (L + 1) * H + 32 : bias_g + l * H;  // l = 0: H zeros
           const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
           // phase stash: staged layout [H/8 chunks][128 rows][8]; pipelined layout two 64-row halves of padded chunks
           // (common.cuh: kPipePhChunk)
@@ -496,21 +504,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
 #pragma unroll
           for (int kb = 0; kb < S::kKB; ++kb) {
             const int col0 = kb * 64 + s * 16;
-            float4 bq[4];
+            float4 bq[4];  // (layer 0: its bias is part of the GEMM; bl points at the zero block of the bias table)
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              bq[j4] = (l == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
             tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
             if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
             float th[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bq[j4].x;
-              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bq[j4].y;
-              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bq[j4].z;
-              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bq[j4].w;
+            for (int j4 = 0; j4 < 4; ++j4) {  // packed fp32x2 adds: 8 instructions for the 16 biases
+              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]);
+              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]);
+              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]);
+              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]);
+              add_f32x2(th[j4 * 4 + 0], th[j4 * 4 + 1], bq[j4].x, bq[j4].y);
+              add_f32x2(th[j4 * 4 + 2], th[j4 * 4 + 3], bq[j4].z, bq[j4].w);
             }
             constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
             emit_sine16<kStash, kPhStride>(th, a_addr + kb * S::kABlock, r, s,

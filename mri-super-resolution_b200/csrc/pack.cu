@@ -58,15 +58,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
   // biases
   float* bias = reinterpret_cast<float*>(p.packed + p.pl.bias);
-  for (long long i = tid; i < (long long)(L + 1) * H + 32; i += nthreads) {
+  for (long long i = tid; i < (long long)(L + 1) * H + 32 + H; i += nthreads) {
     float v = 0.f;
     if (i < (long long)(L + 1) * H) {
       const int l = int(i / H), h = int(i % H);
       if (h < Hr) v = (l == 0 ? p.omega0 : p.omegah) * p.params[p.off[2 * l + 1] + h];
-    } else {
+    } else if (i < (long long)(L + 1) * H + 32) {
       const int c = int(i - (long long)(L + 1) * H);
       if (c < C) v = p.params[p.off[2 * (L + 1) + 1] + c];
-    }
+    }  // else: the zero block (written here once; the fused optimiser step never touches it)
     bias[i] = v;
   }
   // hidden layers, both orientations

@@ -475,6 +475,26 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(uint32_t row, uint3
   return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }
 
+// ------------------------------------------------------------------ packed fp32 pairs (sm_100: FADD2 / FFMA2)
+// Two fp32 lanes per instruction: the fused epilogues are ISSUE-bound (a polynomial sine that moved work from the MUFU
+// to the FMA pipe made the forward slower, not faster), so every pair of element-wise adds / fmas is one instruction.
+__device__ __forceinline__ unsigned long long f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f32x2(a0, a1)), "l"(f32x2(b0, b1)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+}
+// (a0, a1) * (m, m) + (c, c)
+__device__ __forceinline__ void fma_f32x2(float a0, float a1, float m, float c, float& d0, float& d1) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f32x2(a0, a1)), "l"(f32x2(m, m)), "l"(f32x2(c, c)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
