@@ -63,6 +63,12 @@ typedef struct b200inr_net {
  * calls b200inr_siren_backward then makes).  The stash layout differs, so forward, backward and
  * b200inr_stash_bytes must see the same flag.  Ignored by the other network families (always staged). */
 #define B200INR_NET_STAGED_BWD 1
+/* The ReLU-tail SIREN of INR/INR_ERD.py:28-67 (SIREN on raw coordinates, pipelined backward only): the LAST of the
+ * hidden_layers hidden layers is nn.Linear + nn.ReLU (no omega) instead of a SineLayer, and the network output passes
+ * through a ReLU:  net = SineLayer(first), (hidden_layers - 1) x SineLayer, Linear + ReLU, final Linear, ReLU.
+ * hidden_layers >= 1.  b200inr_siren_forward then always returns relu(out); the loss gradient handed to
+ * b200inr_siren_backward must already carry the output ReLU's mask (b200inr_mse_loss_relu_out). */
+#define B200INR_NET_RELU_TAIL 2
 
 /* Dense coordinate grid == get_mgrid(shape) (INR/SRDWI.py:12-18) restricted to linear rows
  * [row_begin, row_begin + rows).  Coordinates are never materialised; kernels derive them from the index. */
@@ -153,6 +159,20 @@ int b200inr_siren_wgrad(const b200inr_net* net, void* stash, const float* coords
  * loss_accum[0] += sum(w*(pred-target)^2)/count ; grad = 2*w*(pred-target)/count.  weight may be NULL. */
 int b200inr_mse_loss(const float* pred, const float* target, const float* weight, int64_t n, double count,
                      float* grad, float* loss_accum, void* stream);
+
+/* The same loss when `pred` is the output of a ReLU-tail network (relu(raw)): grad = 2 w (pred - target) / count where
+ * pred > 0 and 0 elsewhere, i.e. dL/d(raw) (INR/INR_ERD.py:65-66 followed by :203-204 / :264-266). */
+int b200inr_mse_loss_relu_out(const float* pred, const float* target, const float* weight, int64_t n, double count,
+                              float* grad, float* loss_accum, void* stream);
+
+/* Soft-ERD loss weights (INR/INR_ERD.py:222-235) and the soft-ERD image (:126-160), one thread per voxel:
+ * x = signal[v, 0:n] (the acquisitions of one b-value), b0[v]; if mean(x) > 2 noise_level:
+ *   T = max(mul * exp(-slope * mean(x) / b0), 2),  weights[v, :] = exp(x / T),  soft_mean[v] = sum(softmax(x / T) * x)
+ *   (one-hot on overflow, like the reference's RuntimeWarning branch);
+ * else weights[v, :] = 1 / n and soft_mean[v] = mean(x).  Double arithmetic inside (the reference is NumPy float64),
+ * fp32 in and out.  weights / soft_mean may be NULL.  2 <= n <= 64. */
+int b200inr_soft_erd(const float* signal, const float* b0, int64_t voxels, int32_t n, double noise_level, double mul,
+                     double slope, float* weights, float* soft_mean, void* stream);
 
 /* Host helper: per-axis taps of D (LR row i <- HR columns) and of its transpose (HR column x <- LR rows).
  * n_hr must be even; blur = 0 -> 2-tap box mean; blur = 1 -> Gaussian sigma 0.5 (5 taps, mirror) then box. */

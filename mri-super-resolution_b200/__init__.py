@@ -10,8 +10,10 @@ with exactly the reference's import names), ``phantom`` (synthetic DWI volumes),
 ABI declared in include/b200inr.h), ``csrc`` (the sm_100a kernels).
 """
 from .inr import (ComplexGaborLayer2D, FitSession, FourierMLP, Wire, ImageFitting_set, PN, SineLayer, Siren,  # noqa: F401
-                  all_combinations, calculate_ADC, calculate_combinations, get_mgrid, input_mapping)
+                  SirenERD, all_combinations, calculate_ADC, calculate_combinations, get_mgrid, input_mapping,
+                  resize_array, soft_erd)
 from . import _lib  # noqa: F401
 
-__all__ = ["ComplexGaborLayer2D", "FitSession", "FourierMLP", "Wire", "ImageFitting_set", "PN", "SineLayer", "Siren", "all_combinations", "calculate_ADC", "calculate_combinations", "get_mgrid",
-           "input_mapping"]
+__all__ = ["ComplexGaborLayer2D", "FitSession", "FourierMLP", "Wire", "ImageFitting_set", "PN", "SineLayer", "Siren",
+           "SirenERD", "all_combinations", "calculate_ADC", "calculate_combinations", "get_mgrid", "input_mapping",
+           "resize_array", "soft_erd"]

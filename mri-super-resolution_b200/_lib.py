@@ -15,6 +15,7 @@ MAX_TAPS = 8
 ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2
 IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
 DEFAULT_PIPED_BWD = "1"  # raw-coordinate SIRENs train through the pipelined backward (B200INR_PIPED_BWD=0: staged)
+NET_RELU_TAIL = 2   # B200INR_NET_RELU_TAIL: last hidden layer Linear + ReLU, ReLU on the output (INR/INR_ERD.py:28-67)
 NET_STAGED_BWD = 1  # B200INR_NET_STAGED_BWD: the older forward-stash / dgrad / wgrad training path of raw-coordinate SIRENs
 
 
@@ -66,6 +67,8 @@ SIGNATURES = {
     "b200inr_siren_dgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp]),
     "b200inr_siren_wgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, _vp]),
     "b200inr_mse_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp]),
+    "b200inr_mse_loss_relu_out": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp]),
+    "b200inr_soft_erd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _f64, _f64, _f64, _vp, _vp, _vp]),
     "b200inr_degrade_build_axis_host": (ctypes.c_int, [_i32, ctypes.c_int, _P(AxisTaps), _P(AxisTaps)]),
     "b200inr_degrade_forward": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "b200inr_degrade_adjoint": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),

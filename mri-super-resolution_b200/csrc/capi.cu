@@ -39,7 +39,9 @@ int launch_wire_bwd(const b200inr_net* net, const void* packed, void* stash, int
 int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num_sms, cudaStream_t stream);
 int launch_wire_combine(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, cudaStream_t stream);
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
-               float* loss_accum, cudaStream_t stream);
+               float* loss_accum, cudaStream_t stream, int relu_out = 0);
+int launch_soft_erd(const float* signal, const float* b0, int64_t voxels, int n, double noise_level, double mul,
+                    double slope, float* weights, float* soft_mean, cudaStream_t stream);
 int launch_pool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count, float* grad,
                     float* loss_accum, cudaStream_t stream);
 int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int64_t ZC, const b200inr_axis_taps* tx,
@@ -81,11 +83,14 @@ static int check_net(const b200inr_net* net) {
     return B200INR_OK;
   }
   if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
+  if ((net->flags & B200INR_NET_RELU_TAIL) && net->input_mode != B200INR_IN_COORDS) return B200INR_ERR_BAD_SHAPE;
   switch (net->input_mode) {
     case B200INR_IN_COORDS:  // SIREN on raw coordinates: any width up to 256 (multiple of 8) runs on the 256-wide
                              // kernels with zero-padded operands; parameters and gradients keep the real width
       if (H < 8 || H > kSirenWidth || H % 8 != 0 || net->activation != B200INR_ACT_SINE) return B200INR_ERR_BAD_SHAPE;
       if (net->in_features < 1 || net->in_features > 4 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
+      if (net->flags & B200INR_NET_RELU_TAIL)  // ReLU-tail SIREN: pipelined backward only, at least the ReLU layer
+        if ((net->flags & B200INR_NET_STAGED_BWD) || net->hidden_layers < 1) return B200INR_ERR_BAD_SHAPE;
       return B200INR_OK;
     case B200INR_IN_FOURIER: {
       if (H != 256 && H != 512) return B200INR_ERR_BAD_SHAPE;
@@ -353,6 +358,23 @@ int b200inr_mse_loss(const float* pred, const float* target, const float* weight
   if (n < 0 || !(count > 0)) return B200INR_ERR_BAD_SHAPE;
   if (n == 0) return B200INR_OK;
   return launch_mse(pred, target, weight, n, count, grad, loss_accum, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_mse_loss_relu_out(const float* pred, const float* target, const float* weight, int64_t n, double count,
+                              float* grad, float* loss_accum, void* stream) {
+  if (!pred || !target) return B200INR_ERR_NULL;
+  if (n < 0 || !(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  if (n == 0) return B200INR_OK;
+  return launch_mse(pred, target, weight, n, count, grad, loss_accum, static_cast<cudaStream_t>(stream), 1);
+}
+
+int b200inr_soft_erd(const float* signal, const float* b0, int64_t voxels, int32_t n, double noise_level, double mul,
+                     double slope, float* weights, float* soft_mean, void* stream) {
+  if (!signal || !b0) return B200INR_ERR_NULL;
+  if (voxels < 0 || n < 2 || n > 64) return B200INR_ERR_BAD_SHAPE;
+  if (voxels == 0) return B200INR_OK;
+  return launch_soft_erd(signal, b0, voxels, n, noise_level, mul, slope, weights, soft_mean,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_degrade_build_axis_host(int32_t n_hr, int blur, b200inr_axis_taps* fwd_host, b200inr_axis_taps* adj_host) {

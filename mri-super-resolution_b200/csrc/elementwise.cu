@@ -28,26 +28,81 @@ __device__ __forceinline__ void block_accumulate(float v, float* dst) {
 }
 
 // ------------------------------------------------------------------ ((out - gt)**2).mean()   INR/superresDWI.py:135
+// relu_out: pred = relu(raw) of a ReLU-tail network and grad is dL/d(raw): zero where the ReLU clipped (pred == 0).
 __global__ void __launch_bounds__(kEwThreads) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                                          const float* __restrict__ weight, long long n, float inv_count,
-                                                         float* __restrict__ grad, float* loss_accum) {
+                                                         float* __restrict__ grad, float* loss_accum, int relu_out) {
   float acc = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float r = pred[i] - target[i];
+    const float pv = pred[i];
+    const float r = pv - target[i];
     const float w = weight ? weight[i] : 1.f;
     acc = fmaf(w * r, r, acc);
-    if (grad) grad[i] = 2.f * w * r * inv_count;
+    if (grad) grad[i] = (relu_out && !(pv > 0.f)) ? 0.f : 2.f * w * r * inv_count;
   }
   if (loss_accum) block_accumulate(acc * inv_count, loss_accum);
 }
 
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
-               float* loss_accum, cudaStream_t stream) {
+               float* loss_accum, cudaStream_t stream, int relu_out) {
   long long blocks = (n + kEwThreads * 4 - 1) / (kEwThreads * 4);
   if (blocks < 1) blocks = 1;
   if (blocks > kSmCount * 8) blocks = kSmCount * 8;
-  mse_kernel<<<int(blocks), kEwThreads, 0, stream>>>(pred, target, weight, n, float(1.0 / count), grad, loss_accum);
+  mse_kernel<<<int(blocks), kEwThreads, 0, stream>>>(pred, target, weight, n, float(1.0 / count), grad, loss_accum,
+                                                     relu_out);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ soft-ERD   INR/INR_ERD.py:126-160, 222-235
+// One thread per voxel over its n acquisitions (n <= 64, held in registers as doubles: the reference is NumPy float64
+// and exp(x / T) spans its whole range).
+__global__ void __launch_bounds__(kEwThreads) soft_erd_kernel(const float* __restrict__ signal, const float* __restrict__ b0,
+                                                              long long voxels, int n, double noise_level, double mul,
+                                                              double slope, float* __restrict__ weights,
+                                                              float* __restrict__ soft_mean) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < voxels; v += stride) {
+    const float* x = signal + v * n;
+    double mean = 0.0;
+    for (int k = 0; k < n; ++k) mean += double(x[k]);
+    mean /= double(n);
+    if (!(mean > 2.0 * noise_level)) {
+      if (weights)
+        for (int k = 0; k < n; ++k) weights[v * n + k] = float(1.0 / double(n));
+      if (soft_mean) soft_mean[v] = float(mean);
+      continue;
+    }
+    double T = mul * exp(-slope * (mean / double(b0[v])));
+    if (!(T > 2.0)) T = 2.0;  // max(T, 2), NaN-safe like Python's max(nan, 2) == nan is not: b0 == 0 gives exp(-inf) = 0
+    double sum = 0.0, wsum = 0.0;
+    bool overflow = false;
+    int arg = 0;
+    for (int k = 0; k < n; ++k) {
+      const double w = exp(double(x[k]) / T);
+      if (isinf(w)) overflow = true;
+      if (x[k] > x[arg]) arg = k;
+      sum += w;
+      wsum += w * double(x[k]);
+      if (weights) weights[v * n + k] = float(w);
+    }
+    if (overflow) {  // the reference's RuntimeWarning branch: one-hot at the arg-max
+      if (weights)
+        for (int k = 0; k < n; ++k) weights[v * n + k] = (k == arg) ? 1.f : 0.f;
+      if (soft_mean) soft_mean[v] = x[arg];
+    } else if (soft_mean) {
+      soft_mean[v] = float(wsum / sum);
+    }
+  }
+}
+
+int launch_soft_erd(const float* signal, const float* b0, int64_t voxels, int n, double noise_level, double mul,
+                    double slope, float* weights, float* soft_mean, cudaStream_t stream) {
+  long long blocks = (voxels + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 16) blocks = kSmCount * 16;
+  if (blocks < 1) blocks = 1;
+  soft_erd_kernel<<<int(blocks), kEwThreads, 0, stream>>>(signal, b0, voxels, n, noise_level, mul, slope, weights,
+                                                          soft_mean);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 

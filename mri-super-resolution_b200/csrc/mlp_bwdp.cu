@@ -56,6 +56,10 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+#ifndef B200INR_TUNING
+#define B200INR_TUNING 0  // 1: the launcher honours the B200INR_BWDP_* environment hooks (trace pointer, stall counters)
+#endif
+
 namespace b200inr {
 
 #ifndef B200INR_PCVT
@@ -216,6 +220,7 @@ struct PipeParams {
   float* grads;
   long long off[2 * (kMaxSineLayers + 2)];
   float omega0, omegah;
+  int relu_tail;             // B200INR_NET_RELU_TAIL: activated layer L is Linear + ReLU (its stash slot holds bf16 y)
   int pipelines;
   int skew_ns;               // start-up delay of the second epilogue group
   int dbg;                   // tuning switches (B200INR_BWDP_DBG), 0 in production
@@ -806,6 +811,8 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       const uint32_t t_lane = uint32_t(q * 32) << 16;
       const int C = p.C;
       float dbsum = 0.f;
+      // ReLU-tail network: the top activated layer (whose stash the edge CTAs read) is Linear + ReLU
+      const bool relu_top = edge && p.relu_tail != 0;
 
       if (!edge) {
         // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
@@ -891,6 +898,15 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
               ys[j] = pack_bf16x2(r0, r1);
               continue;
             }
+            if (relu_top) {  // stash slot = bf16 y = relu(theta): dTheta = D where y > 0, the operand of dW_f is y itself
+              const uint32_t y0 = ph[2 * j], y1 = ph[2 * j + 1];
+              const float d0 = (y0 & 0x7FFFu) ? __uint_as_float(v[16 * b2 + 2 * j]) : 0.f;  // (y >= 0: no sign to test)
+              const float d1 = (y1 & 0x7FFFu) ? __uint_as_float(v[16 * b2 + 2 * j + 1]) : 0.f;
+              dbsum += d0 + d1;
+              ds[j] = pack_bf16x2(d0, d1);
+              ys[j] = y0 | (y1 << 16);
+              continue;
+            }
             const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * __cosf(r0);
             const float d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * __cosf(r1);
             dbsum += d0 + d1;
@@ -937,7 +953,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       const int fi = h * 128 + f;  // feature owned by this thread
       // bias gradient of the layer whose dTheta this CTA produced
       {
-        const float sc = (ph_layer == 0) ? p.omega0 : p.omegah;
+        const float sc = (ph_layer == 0) ? p.omega0 : (relu_top ? 1.0f : p.omegah);
         if (fi < Hr) atomicAdd(p.grads + p.off[2 * ph_layer + 1] + fi, sc * dbsum);
       }
       mbar_wait(&bars[kBFin], 0);
@@ -945,6 +961,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       if (!edge) {
         // dW_l[out][128 h + f] += omega_h * D[f][out]; this warp: outputs 64 cg .. 64 cg + 64 (lanes = consecutive inputs)
         float* dst = p.grads + p.off[2 * layer] + fi;
+        const float wsc = (p.relu_tail != 0 && layer == L) ? 1.0f : p.omegah;  // (the Linear + ReLU layer has no omega)
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
@@ -954,7 +971,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (cg * 64 + c0 + j < Hr)
-                atomicAdd(dst + (long long)(cg * 64 + c0 + j) * Hr, p.omegah * __uint_as_float(v[j]));
+                atomicAdd(dst + (long long)(cg * 64 + c0 + j) * Hr, wsc * __uint_as_float(v[j]));
           }
         }
       } else {
@@ -1026,16 +1043,23 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   for (int i = 0; i < 2 * (L + 2); ++i) p.off[i] = off[i];
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
+  p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
   const int S2 = 2 * (L + 1);
   const int smem = PSmem::kBytes + PSmem::kSlack;
-  int P = num_sms / S2;
-  if (kPMc) {
-    // every CTA of the grid must be resident at once, and with clusters that is the number of CTA PAIRS the GPCs can
-    // hold (cached: a property of the device and the kernel)
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      if (cudaFuncSetAttribute(siren_bwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return B200INR_ERR_CUDA;
+  // Every CTA of the grid waits on flags written by other CTAs of its pipeline, so the whole grid must be resident at
+  // once.  That is not assumed: the launch is COOPERATIVE (the driver refuses it -- a clean error code, no hang and no
+  // trap -- when the grid does not fit, e.g. with SMs taken by another context, MPS partition or debugger), and the
+  // number of pipelines comes from the occupancy the driver reports for this kernel on this device (cached).
+  static int resident_ctas[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200INR_ERR_CUDA;
+  const bool instr = false;
+  auto kern = siren_bwdp_kernel<false>;
+  if (dev < 0 || dev >= 64 || resident_ctas[dev] == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return B200INR_ERR_CUDA;
+    int per_sm = 0;
+    if (kPMc) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(unsigned(num_sms & ~1));
       cfg.blockDim = dim3(kPThreads);
@@ -1048,15 +1072,22 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
       cfg.attrs = &at;
       cfg.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, siren_bwdp_kernel<false>, &cfg) != cudaSuccess) return B200INR_ERR_CUDA;
-      max_clusters = nc;
-      if (getenv("B200INR_BWDP_VERBOSE") != nullptr) fprintf(stderr, "b200inr: bwdp max active 2-CTA clusters = %d\n", nc);
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) return B200INR_ERR_CUDA;
+      per_sm = -2 * nc;  // (negative: an absolute CTA count)
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPThreads, size_t(smem)) != cudaSuccess) {
+      return B200INR_ERR_CUDA;
     }
-    if (P > max_clusters / (L + 1)) P = max_clusters / (L + 1);
+    const int total = per_sm < 0 ? -per_sm : per_sm * num_sms;
+    if (total < S2) return B200INR_ERR_CUDA;
+    if (dev >= 0 && dev < 64) resident_ctas[dev] = total;
   }
+  const int resident = (dev >= 0 && dev < 64) ? resident_ctas[dev] : num_sms;
+  int P = (resident < num_sms ? resident : num_sms) / S2;  // one CTA per SM: the kernel is sized for a whole SM
   if (P > p.fwd_tiles) P = p.fwd_tiles;
   if (P < 1 || P * (L + 1) > kPipeMaxEdges) return B200INR_ERR_BAD_SHAPE;
   p.pipelines = P;
+#if B200INR_TUNING
+  // tuning builds only (tools/build_variant.sh ... -DB200INR_TUNING=1): event trace / stall counters / start skew
   const char* env_skew = getenv("B200INR_BWDP_SKEW_NS");
   p.skew_ns = env_skew != nullptr ? atoi(env_skew) : 0;
   const char* env_dbg = getenv("B200INR_BWDP_DBG");
@@ -1066,15 +1097,33 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   const char* env_prof = getenv("B200INR_BWDP_PROF");
   if (env_prof != nullptr && env_prof[0] == '1' && P * S2 <= kPipeProfCtas)
     p.prof = reinterpret_cast<unsigned long long*>(st + sl.prof);
+#endif
   if (cudaMemsetAsync(p.flags, 0, sl.flags_bytes, stream) != cudaSuccess) return B200INR_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(P * S2));
+  cfg.blockDim = dim3(kPThreads);
+  cfg.dynamicSmemBytes = size_t(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeCooperative;
+  at.val.cooperative = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+#if B200INR_TUNING
   if (p.prof != nullptr || (p.trace != nullptr && !kPTraceOnly) || p.dbg != 0) {
     if (cudaFuncSetAttribute(siren_bwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200INR_ERR_CUDA;
-    siren_bwdp_kernel<true><<<P * S2, kPThreads, smem, stream>>>(p);
-  } else {
-    if (cudaFuncSetAttribute(siren_bwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return B200INR_ERR_CUDA;
-    siren_bwdp_kernel<false><<<P * S2, kPThreads, smem, stream>>>(p);
+    e = cudaLaunchKernelEx(&cfg, siren_bwdp_kernel<true>, p);
+  } else
+#endif
+  {
+    (void)instr;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return B200INR_ERR_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }

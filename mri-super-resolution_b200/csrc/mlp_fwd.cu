@@ -67,6 +67,7 @@ struct FwdParams {
   float* grad_out;
   float* loss_accum;
   float inv_count;     // 1 / (global number of LR elements)
+  int relu_tail;       // B200INR_NET_RELU_TAIL: activated layer L is Linear + ReLU, the output is ReLU'd (clamp)
   int tiles_per_plane; // Y * Z / 128: tiles of one x-plane (the pooling partner of tile t is tile t + tiles_per_plane)
   int Z;
   uint8_t* stash_y;   // nullptr => inference
@@ -93,12 +94,26 @@ constexpr float kPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
 constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 
 // sin + stores for the 16 consecutive columns [kb*64 + s*16, +16) of row r.
+// relu: the layer is Linear + ReLU (ReLU-tail network): y = max(theta, 0), and the 16-bit stash slot of an element
+// holds the bf16 OUTPUT instead of a phase (the backward needs y and the mask y > 0, not an angle).
 template <bool kStash, int kChunkStride = kTileRows * 16>
 __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_block_addr, int r, int s,
-                                            uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */) {
+                                            uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */,
+                                            bool relu = false) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t yb[4], ph[4];
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        yb[j] = pack_bf16x2(fmaxf(th[c * 8 + 2 * j], 0.f), fmaxf(th[c * 8 + 2 * j + 1], 0.f));
+        ph[j] = yb[j];
+      }
+      sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
+      if (kStash)
+        __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * kChunkStride), make_uint4(ph[0], ph[1], ph[2], ph[3]));
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
@@ -523,7 +538,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             }
             constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
             emit_sine16<kStash, kPhStride>(th, a_addr + kb * S::kABlock, r, s,
-                                           kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr);
+                                           kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr,
+                                           p.relu_tail != 0 && l == L);
           }
           if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
           publish(j);
@@ -676,7 +692,7 @@ struct FwdLossArgs {
 
 bool fwd_pool_loss_supported(const b200inr_net* net, const b200inr_grid* grid, int64_t rows) {
   if (net->input_mode != B200INR_IN_COORDS || net->activation != B200INR_ACT_SINE) return false;
-  if ((net->flags & B200INR_NET_STAGED_BWD) != 0 || grid == nullptr || grid->ndim != 3) return false;
+  if ((net->flags & (B200INR_NET_STAGED_BWD | B200INR_NET_RELU_TAIL)) != 0 || grid == nullptr || grid->ndim != 3) return false;
   const long long Y = grid->shape[1], Z = grid->shape[2];
   if (Z < 1 || (kTileRows % (2 * Z)) != 0 || (Y & 1) || ((Y * Z) % kTileRows) != 0) return false;
   const long long pair_rows = 2 * Y * Z;  // a slab of whole x-plane pairs, starting on one
@@ -709,6 +725,11 @@ static int launch_siren_fwd_impl(const b200inr_net* net, const void* packed, con
   p.out = out;
   p.clamp = clamp;
   p.clamp_min = clamp_min;
+  p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
+  if (p.relu_tail) {  // the output ReLU of INR/INR_ERD.py:65-66 (a later clamp at a higher floor still applies)
+    p.clamp_min = clamp ? (clamp_min > 0.f ? clamp_min : 0.f) : 0.f;
+    p.clamp = 1;
+  }
   // tuning builds (-DB200INR_TUNING=1, tools/build_variant.sh) honour B200INR_FWD_TRACE_PTR (event trace buffer of
   // CTA 0) and B200INR_FWD_MAX_CTAS (grid cap); a production library never reads a pointer from the environment
   const char* env_cap = nullptr;

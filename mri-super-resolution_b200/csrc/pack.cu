@@ -17,6 +17,9 @@ struct PackParams {
   int d, H, L, C;
   int Hr;  // real hidden width of the network (parameters); H is the padded operand width
   float omega0, omegah;
+  int relu_tail;  // B200INR_NET_RELU_TAIL: the last hidden layer is Linear + ReLU (omega = 1)
+  // omega folded into the operands of activated layer l (0 = first)
+  __host__ __device__ float omega(int l) const { return l == 0 ? omega0 : ((relu_tail && l == L) ? 1.0f : omegah); }
 };
 
 __device__ __forceinline__ void put_bf16(uint8_t* base, uint32_t row, uint32_t k, float v) {
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     float v = 0.f;
     if (i < (long long)(L + 1) * H) {
       const int l = int(i / H), h = int(i % H);
-      if (h < Hr) v = (l == 0 ? p.omega0 : p.omegah) * p.params[p.off[2 * l + 1] + h];
+      if (h < Hr) v = p.omega(l) * p.params[p.off[2 * l + 1] + h];
     } else if (i < (long long)(L + 1) * H + 32) {
       const int c = int(i - (long long)(L + 1) * H);
       if (c < C) v = p.params[p.off[2 * (L + 1) + 1] + c];
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     const int l = int(i / per_layer);
     const int o = int((i % per_layer) / H);  // out feature
     const int k = int(i % H);                // in feature
-    const float v = (o < Hr && k < Hr) ? p.omegah * p.params[p.off[2 * (l + 1)] + (long long)o * Hr + k] : 0.f;
+    const float v = (o < Hr && k < Hr) ? p.omega(l + 1) * p.params[p.off[2 * (l + 1)] + (long long)o * Hr + k] : 0.f;
     uint8_t* wh = p.packed + p.pl.wh + size_t(l) * per_layer * 2;
     uint8_t* wht = p.packed + p.pl.wht + size_t(l) * per_layer * 2;
     put_bf16(wh + size_t(k >> 6) * H * 128, o, k & 63, v);   // forward: N = out, K = in
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const
     // ---- hidden layers, both orientations
     const int l = int(i >> 16), o = int(i >> 8) & (H - 1), k = int(i) & (H - 1);
     static_assert(H == 256, "index arithmetic above");
-    const float v = (o < Hr && k < Hr) ? p.omegah * adam_apply(a, c, p.off[2 * (l + 1)] + (long long)o * Hr + k) : 0.f;
+    const float v = (o < Hr && k < Hr) ? p.omega(l + 1) * adam_apply(a, c, p.off[2 * (l + 1)] + (long long)o * Hr + k) : 0.f;
     uint8_t* wh = p.packed + p.pl.wh + size_t(l) * H * H * 2;
     uint8_t* wht = p.packed + p.pl.wht + size_t(l) * H * H * 2;
     put_bf16(wh + size_t(k >> 6) * H * 128, o, k & 63, v);   // forward: N = out, K = in
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const
     float v = 0.f;
     if (i < (long long)L * H) {
       const int l = int(i >> 8) + 1, h = int(i) & (H - 1);
-      if (h < Hr) v = p.omegah * adam_apply(a, c, p.off[2 * l + 1] + h);
+      if (h < Hr) v = p.omega(l) * adam_apply(a, c, p.off[2 * l + 1] + h);
     } else {
       const int cc = int(i - (long long)L * H);
       if (cc < C) v = adam_apply(a, c, p.off[2 * (L + 1) + 1] + cc);
@@ -404,6 +407,7 @@ int launch_pack(const b200inr_net* net, const float* params, void* packed, cudaS
   p.C = net->out_features;
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
+  p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
   p.pl = make_pack_layout(p.H, p.L);
   int64_t off[2 * (kMaxSineLayers + 1)];
   param_offsets(p.d, p.Hr, p.L, p.C, off);
@@ -430,6 +434,7 @@ int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, f
     p.C = net->out_features;
     p.omega0 = net->first_omega_0;
     p.omegah = net->hidden_omega_0;
+    p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
     p.pl = make_pack_layout(p.H, p.L);
     int64_t off[2 * (kMaxSineLayers + 1)];
     param_offsets(p.d, p.Hr, p.L, p.C, off);

@@ -342,6 +342,7 @@ class _SirenFunction(torch.autograd.Function):
         ctx.stash = stash
         ctx.coords = coords
         ctx.key = module._engine["key"]  # identity + version of every parameter the stash was computed with
+        ctx.relu_out = out if (module._desc.flags & _lib.NET_RELU_TAIL) else None  # output ReLU: mask of the backward
         return out
 
     @staticmethod
@@ -353,6 +354,8 @@ class _SirenFunction(torch.autograd.Function):
             # forward A, optimizer.step(), forward B, A.backward(): the bf16 operands no longer match A's stash
             raise RuntimeError("b200inr: one of the parameters needed for gradient computation has been modified by an "
                                "inplace operation since this forward (the operand buffer was re-staged)")
+        if ctx.relu_out is not None:  # d relu(raw) / d raw (INR/INR_ERD.py:65-66)
+            grad_out = grad_out * (ctx.relu_out > 0)
         grad_in = torch.empty_like(ctx.coords) if ctx.needs_input_grad[0] else None
         flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out, grad_in=grad_in)
         ctx.stash = None
@@ -606,6 +609,81 @@ class Siren(_FusedMLP):
         return ps
 
 
+class SirenERD(_FusedMLP):
+    """The ReLU-tail SIREN of the reference's soft-ERD script (INR/INR_ERD.py:28-67, there called `Siren`):
+    SineLayer(first), hidden_layers x SineLayer, nn.Linear(H, H) + ReLU, final nn.Linear, ReLU on the output.
+    Same constructor arguments, module registration order, RNG consumption (the perturbation head's two linears are
+    created and initialised last, exactly like the reference) and state-dict keys.  forward = one fused kernel
+    (b200inr_net.flags = B200INR_NET_RELU_TAIL), backward = the layer-pipelined kernel; fit(weight=...) is the
+    weighted loss of :264-266.  perturb=True is the notebook-only path that reads a global `model_input` (SURVEY.md
+    App. A-14) and is not provided."""
+
+    def __init__(self, in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.,
+                 hidden_omega_0=30., perturb=False):
+        super().__init__()
+        if perturb:
+            raise NotImplementedError("b200inr: INR_ERD.Siren(perturb=True) depends on a notebook global in the reference")
+        self.in_features, self.hidden_features = int(in_features), int(hidden_features)
+        self.hidden_layers, self.out_features = int(hidden_layers), int(out_features)
+        net = [SineLayer(in_features, hidden_features, is_first=True, omega_0=first_omega_0)]
+        self.relu = nn.ReLU()
+        for _ in range(hidden_layers):
+            net.append(SineLayer(hidden_features, hidden_features, is_first=False, omega_0=hidden_omega_0))
+        net.append(nn.Linear(hidden_features, hidden_features))
+        net.append(nn.ReLU())
+        self.final_linear = nn.Linear(hidden_features, out_features)
+        bound = np.sqrt(6 / hidden_features) / hidden_omega_0
+        with torch.no_grad():
+            self.final_linear.weight.uniform_(-bound, bound)
+        self.net = nn.Sequential(*net)
+        self.perturb_linear = nn.Linear(3, hidden_features)
+        self.perturb_linear2 = nn.Linear(hidden_features, out_features)
+        with torch.no_grad():
+            self.perturb_linear.weight.uniform_(-bound, bound)
+            self.perturb_linear2.weight.uniform_(-bound, bound)
+        self.tanh = nn.Tanh()
+        self.perturb = perturb
+        self.first_omega_0, self.hidden_omega_0 = float(first_omega_0), float(hidden_omega_0)
+        # engine view: hidden_layers + 1 hidden layers, the last of them Linear + ReLU
+        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers + 1, out_features,
+                                        self.first_omega_0, self.hidden_omega_0, flags=_lib.NET_RELU_TAIL),
+                          self.in_features)
+
+    def _canonical(self):
+        ps = []
+        for i in range(self.hidden_layers + 1):
+            ps += [self.net[i].linear.weight, self.net[i].linear.bias]
+        lin = self.net[self.hidden_layers + 1]
+        ps += [lin.weight, lin.bias, self.final_linear.weight, self.final_linear.bias]
+        return ps
+
+    def forward(self, coords, sample=0, eps=0):
+        return super().forward(coords)
+
+    def query(self, shape, clamp_min=0.0, out=None, row_range=None):
+        # (the network output is already >= 0; clamp_min=None cannot undo the output ReLU)
+        return super().query(shape, clamp_min=clamp_min, out=out, row_range=row_range)
+
+
+def soft_erd(signal, b0, noise_level, mul=1000.0, slope=20.0):
+    """Soft-ERD over the last axis of `signal` (the acquisitions of one b-value), one kernel for the whole volume:
+    returns (weights, soft_mean) -- the loss weights `accept` of INR/INR_ERD.py:222-235 (exp(x / T), or 1/n below the
+    noise floor) and the softmax-weighted image of calc_adc_erd_single2 (:126-160).  CUDA fp32 tensors in and out."""
+    _require_cuda(signal, "soft_erd signal")
+    sig = signal.detach().contiguous().float()
+    n = sig.shape[-1]
+    b0t = b0.detach().to(sig.device).contiguous().float()
+    if tuple(b0t.shape) != tuple(sig.shape[:-1]):
+        raise RuntimeError("b200inr: soft_erd expects b0 of shape signal.shape[:-1]")
+    weights = torch.empty_like(sig)
+    mean = torch.empty(sig.shape[:-1], dtype=torch.float32, device=sig.device)
+    voxels = mean.numel()
+    with torch.cuda.device(sig.device):
+        _lib.check(_lib.load().b200inr_soft_erd(_ptr(sig), _ptr(b0t), voxels, int(n), float(noise_level), float(mul),
+                                               float(slope), _ptr(weights), _ptr(mean), _stream()), "soft_erd")
+    return weights, mean
+
+
 class FourierMLP(_FusedMLP):
     """Fourier features + MLP with the feature map fused into the first layer: the [N, 2m] matrix that input_mapping
     (INR/SRDWI.py:111-116) materialises, and that the reference re-reads from HBM every step, never exists.
@@ -810,6 +888,9 @@ class FitSession:
             self.lr_resid = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
         else:
             raise ValueError("degrade must be None, 'pool' or 'blur_pool'")
+        if degrade is not None and (module._desc.flags & _lib.NET_RELU_TAIL):
+            raise RuntimeError("b200inr: the ReLU-tail network is fitted with the point-wise (weighted) loss of "
+                               "INR/INR_ERD.py; the degradation losses have no output-ReLU mask")
         self.target = target
         # per-element loss weights: (w * (out - gt)**2).mean() of INR/INR_ERD.py:265 (point-wise loss only)
         self.weight = None
@@ -978,8 +1059,9 @@ class FitSession:
         if self.fused_loss:
             pass
         elif self.degrade is None:
-            _lib.check(lib.b200inr_mse_loss(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C,
-                                            self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "mse_loss")
+            mse = lib.b200inr_mse_loss_relu_out if (m._desc.flags & _lib.NET_RELU_TAIL) else lib.b200inr_mse_loss
+            _lib.check(mse(_ptr(self.pred), _ptr(self.target), _ptr(self.weight), rows * C, self.count,
+                           _ptr(self.dpred), _ptr(self.loss_acc), s), "mse_loss")
         elif self.degrade == "pool":
             _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
                                             self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")

@@ -288,6 +288,72 @@ def torch_siren(in_features, hidden_features, hidden_layers, out_features, first
     return _Net()
 
 
+def torch_siren_erd(in_features, hidden_features, hidden_layers, out_features, first_omega_0=30.0, hidden_omega_0=30.0):
+    """The ReLU-tail network of INR/INR_ERD.py:28-67 (perturb=False): SineLayer(first), hidden_layers x SineLayer,
+    Linear(H, H) + ReLU, final Linear (U(+-sqrt(6/H)/omega_h) weights), ReLU on the output -- with the reference's
+    registration order (final_linear before net) and RNG consumption (sine layers, Linear(H, H), final linear, then
+    the two linears of the unused perturbation head, :47-51)."""
+    import torch
+    from torch import nn
+
+    class _Sine(nn.Module):
+        def __init__(self, fan_in, fan_out, first, omega):
+            super().__init__()
+            self.omega_0 = omega
+            self.linear = nn.Linear(fan_in, fan_out)
+            bound = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in) / omega
+            with torch.no_grad():
+                self.linear.weight.uniform_(-bound, bound)
+
+        def forward(self, h):
+            return torch.sin(self.omega_0 * self.linear(h))
+
+    class _Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            layers = [_Sine(in_features, hidden_features, True, first_omega_0)]
+            self.relu = nn.ReLU()
+            layers += [_Sine(hidden_features, hidden_features, False, hidden_omega_0) for _ in range(hidden_layers)]
+            layers += [nn.Linear(hidden_features, hidden_features), nn.ReLU()]
+            self.final_linear = nn.Linear(hidden_features, out_features)
+            bound = math.sqrt(6.0 / hidden_features) / hidden_omega_0
+            with torch.no_grad():
+                self.final_linear.weight.uniform_(-bound, bound)
+            self.net = nn.Sequential(*layers)
+            self.perturb_linear = nn.Linear(3, hidden_features)
+            self.perturb_linear2 = nn.Linear(hidden_features, out_features)
+            with torch.no_grad():
+                self.perturb_linear.weight.uniform_(-bound, bound)
+                self.perturb_linear2.weight.uniform_(-bound, bound)
+
+        def forward(self, coords):
+            return self.relu(self.final_linear(self.net(coords)))
+
+    return _Net()
+
+
+def soft_erd(signal, b0, noise_level, mul=1000.0, slope=20.0):
+    """Soft-ERD of INR/INR_ERD.py in float64, vectorised over voxels: signal [..., n], b0 [...].
+    weights [..., n] = the `accept` loop of :222-235 (exp(x / T) with T = max(mul exp(-slope mean(x)/b0), 2) where
+    mean(x) > 2 noise_level, one-hot at the arg-max when exp overflows -- the script turns RuntimeWarning into that
+    branch --, 1/n below the noise floor); soft_mean [...] = calc_adc_erd_single2's image (:143-156): sum(softmax(x/T) x),
+    or mean(x) below the noise floor."""
+    x = np.asarray(signal, dtype=np.float64)
+    b0 = np.asarray(b0, dtype=np.float64)
+    n = x.shape[-1]
+    mean = x.mean(-1)
+    strong = mean > 2.0 * noise_level
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        T = np.maximum(mul * np.exp(-slope * (mean / b0)), 2.0)
+        w = np.exp(x / T[..., None])
+        over = np.isinf(w).any(-1)
+        onehot = (np.arange(n) == np.argmax(x, -1)[..., None]).astype(np.float64)
+        soft = (w * x).sum(-1) / w.sum(-1)
+    weights = np.where(strong[..., None], np.where(over[..., None], onehot, w), 1.0 / n)
+    soft_mean = np.where(strong, np.where(over, x.max(-1), soft), mean)
+    return weights, soft_mean
+
+
 def calculate_adc(bvalues, data):
     """calculate_ADC (INR/SRDWI.py:118-130) vectorised: np.polyfit(b / 1000, log(y + 1e-7), 1) per voxel in closed form
     (float64), ADC = -slope clamped to [-10, 3].  data [..., nb] -> [...]."""
@@ -337,13 +403,6 @@ def torch_relu_mlp(in_dim, hidden_features, hidden_layers, out_features):
         mods += [nn.Linear(hidden_features, hidden_features), nn.ReLU()]
     mods.append(nn.Linear(hidden_features, out_features))
     return nn.Sequential(*mods)
-
-
-def torch_input_mapping(x, B):
-    """INR/SRDWI.py:111-116 with torch ops (same expression as the reference)."""
-    import torch
-    proj = torch.matmul(2. * np.pi * x, B.T)
-    return torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
 
 
 def torch_fit(model, coords, target, steps, lr, degrade=None, hr_shape=None, weight=None):

@@ -246,3 +246,34 @@ def test_calculate_adc_matches_reference(golden_dir):
     assert ours.shape == g["adc"].shape
     np.testing.assert_allclose(ours, g["adc"], atol=1e-9, rtol=1e-9)
     assert ours[0, 1] == 3.0 and ours[0, 0] < 0 and abs(ours[0, 2]) < 1e-12
+
+
+def test_relu_tail_siren_and_soft_erd_match_reference(golden_dir):
+    """oracle.torch_siren_erd / oracle.soft_erd against tests/golden/siren_erd.npz (the unmodified `Siren` and
+    `calc_adc_erd_single2` of INR/INR_ERD.py, exec'd by tools/make_golden.py erd, and its in-lined weight loop)."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "siren_erd.npz"))
+    torch.manual_seed(11)
+    m = O.torch_siren_erd(*[int(v) for v in g["ctor"]])
+    sd = m.state_dict()
+    keys = [k[3:] for k in g.files if k.startswith("sd/")]
+    assert sorted(keys) == sorted(sd.keys())
+    for k in keys:  # same seed -> same initial weights: construction order and RNG consumption match
+        np.testing.assert_array_equal(sd[k].numpy(), g["sd/" + k], err_msg=k)
+    coords = torch.from_numpy(O.get_mgrid(tuple(int(v) for v in g["grid_shape"])))
+    gt, w = torch.from_numpy(g["gt"]), torch.from_numpy(g["w"])
+    out = m(coords)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=2e-6)
+    (w * (out - gt) ** 2).mean().backward()
+    for k, p in m.named_parameters():
+        if p.grad is not None and "perturb" not in k:
+            np.testing.assert_allclose(p.grad.numpy(), g["g/" + k], atol=1e-6, rtol=1e-4, err_msg=k)
+    m.zero_grad()
+    net = torch.nn.Sequential(m.net, m.final_linear, m.relu)
+    losses = O.torch_fit(net, coords, gt, 5, 3e-4, weight=w)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-4)
+    weights, soft = O.soft_erd(g["b3"], g["b0"], float(g["noise_level"]))
+    np.testing.assert_allclose(weights, g["accept"], rtol=1e-5)
+    np.testing.assert_allclose(soft, g["soft_mean"], rtol=1e-5)
+    assert (g["accept"][0, 0] == np.eye(6)[3]).all()            # the overflow voxel took the one-hot branch
+    assert np.allclose(g["accept"][1], 1.0 / 6)                 # the row below the noise floor: uniform weights

@@ -305,8 +305,102 @@ def combinations_case():
     print("combinations", table.shape, table[0, 0, 0, :, :3])
 
 
+def erd_classes():
+    """exec the unmodified source of INR/INR_ERD.py's `Siren` (lines 28-67, the ReLU-tail network) and
+    `calc_adc_erd_single2` (:126-160): the module itself cannot be imported here (it needs matplotlib, SimpleITK, cv2
+    data files ...), but the two definitions only need torch / numpy and the SineLayer of nn_mri.py, whose source
+    (:96-120) is exec'd the same way."""
+    import ast
+    ns = {"torch": torch, "nn": torch.nn, "np": np}
+    for fname, names in (("nn_mri.py", ("SineLayer",)), ("INR_ERD.py", ("Siren", "calc_adc_erd_single2"))):
+        src = open(os.path.join(REF, fname)).read()
+        tree = ast.parse(src)
+        for node in tree.body:
+            if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in names:
+                exec(ast.get_source_segment(src, node), ns)
+    return ns
+
+
+def erd_case():
+    """ReLU-tail SIREN of INR/INR_ERD.py (Siren(2, 128, 3, 1), the script's own sizes :190-192): forward, autograd
+    gradients and a 5-step WEIGHTED-loss Adam trajectory (:264-266, lr 3e-4 :195), plus the soft-ERD image / ADC of
+    calc_adc_erd_single2 on a small synthetic case and the loss weights of :222-235 (that loop is in-lined in the
+    script's main(); it is reproduced here verbatim over the same synthetic case)."""
+    from types import SimpleNamespace
+    import warnings
+    ns = erd_classes()
+    torch.manual_seed(11)
+    m = ns["Siren"](in_features=2, out_features=1, hidden_features=128, hidden_layers=3)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    coords = SRDWI.get_mgrid((24, 30))
+    gen = torch.Generator().manual_seed(12)
+    gt = torch.rand(coords.shape[0], 1, generator=gen)
+    w = torch.rand(coords.shape[0], 1, generator=gen) * 2
+    out = m(coords)
+    loss = (w * (out - gt) ** 2).mean()
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    params = list(m.net.parameters()) + list(m.final_linear.parameters())
+    opt = torch.optim.Adam(lr=3e-4, params=params)
+    losses = []
+    for _ in range(5):
+        o = m(coords)
+        ls = (w * (o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    with torch.no_grad():
+        out_after = m(coords)
+    # soft ERD on a synthetic case: b3 [X, Y, S, n], b0 [X, Y, S]
+    rng = np.random.RandomState(5)
+    X, Y, S, n = 12, 10, 2, 6
+    b0 = (rng.rand(X, Y, S) * 900 + 100).astype(np.float64)
+    b3 = (b0[..., None] * np.exp(-rng.rand(X, Y, S, n) * 2.5)).astype(np.float64)
+    b3[0, 0, 1, :] = 5e3  # exp(x / T) overflows float64 at T = 2: the one-hot branch
+    b3[0, 0, 1, 3] = 6e3
+    b0[0, 0, 1] = 1.0
+    b3[1, :, 1, :] *= 1e-3  # below the noise floor: plain mean, uniform weights
+    case = SimpleNamespace(b0=b0, b3=b3, noise=(6, 5), cancer_slice=1, b=[0, 150, 1000, 1500])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)  # the script runs with warnings as errors for this branch
+        mean_image, adc = ns["calc_adc_erd_single2"](case)
+    _slice = case.cancer_slice
+    noise_level = np.std(b3[3:8, 2:7, _slice]) / np.sqrt(2 - np.pi / 2)
+    accept = (1 / n) * np.ones(b3.shape)
+    mul, slope = 1000, 20
+
+    def onehot(x):
+        a = np.zeros_like(x)
+        a[np.argmax(x)] = 1
+        return a
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)
+        for i in range(X):          # INR/INR_ERD.py:222-235, verbatim
+            for j in range(Y):
+                x = b3[i, j, _slice, :]
+                b_zero = b0[i, j, _slice]
+                if np.mean(x) > 2 * noise_level:
+                    temp = max(mul * np.exp(-slope * (np.mean(x) / b_zero)), 2)
+                    try:
+                        ww = np.exp(x / temp)
+                    except RuntimeWarning:
+                        ww = onehot(x)
+                    accept[i, j, _slice, :] = ww
+    np.savez_compressed(
+        os.path.join(OUT, "siren_erd.npz"), ctor=np.array([2, 128, 3, 1]), grid_shape=np.array([24, 30]),
+        gt=gt.numpy(), w=w.numpy(), out=out.detach().numpy(), losses=np.array(losses), out_after=out_after.numpy(),
+        b0=b0[:, :, _slice].astype(np.float32), b3=b3[:, :, _slice, :].astype(np.float32),
+        noise_level=np.array(noise_level), soft_mean=mean_image[:, :, _slice], accept=accept[:, :, _slice, :],
+        **{"sd/" + k: v.numpy() for k, v in sd0.items()}, **{"g/" + k: v.numpy() for k, v in grads.items()})
+    print("siren_erd.npz:", out.shape, losses, float(noise_level))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "combinations":
+    if len(sys.argv) > 1 and sys.argv[1] == "erd":
+        erd_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "combinations":
         combinations_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "adc":
         adc_case()
@@ -320,3 +414,4 @@ if __name__ == "__main__":
         perturb_case()
         adc_case()
         combinations_case()
+        erd_case()
