@@ -189,6 +189,13 @@ def run_ours(args):
         for _ in range(warmup):
             sess.step()
         sync()
+        # strong-scaled shards are short steps (0.3 ms at N = 8): replay them as CUDA graphs -- possible because the
+        # gradient exchange is inside the optimiser-step kernel, not an NCCL call (one graph per buffer parity)
+        if world > 1 and sess.peer is not None and os.environ.get("B200INR_BENCH_GRAPH", "1") == "1":
+            sess.capture()
+            for _ in range(2):
+                sess.step()
+            sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -211,7 +218,18 @@ def run_ours(args):
     value = global_rows * args.steps / (ms_total * 1e-3)
     loss_last = float(sess.loss.item())
 
+    def rest():
+        """Every leg starts from the same power state: under a sustained load the board's power governor lowers the
+        SM clocks within a fraction of a second (a 50-step run of this very loop settles 10 % below a 20-step run on
+        some boards), so a leg measured right after another one would be measured on a different GPU.  A leg is its
+        own warm-up + timed region; the idle gap between legs is not part of any of them."""
+        sync()
+        time.sleep(2.0)
+
     # ---- per-stage device times (separate pass: an event between two kernels costs a few microseconds of idle GPU)
+    rest()
+    graphed = sess._graph is not None
+    sess._graph = None  # (eager from here on: stage marks and the staged host targets of the e2e loop)
     marks = []
     for _ in range(max(5, min(args.steps, 20))):
         marks.append([])
@@ -246,6 +264,7 @@ def run_ours(args):
         loss_ready[(n - 1) & 1].synchronize()
         e2e_losses.append(float(host_loss[(n - 1) & 1]))
 
+    rest()
     e2e_loop(max(3, args.warmup))              # warm-up of the side stream / back buffer (untimed)
     sync()
     t0.record()
@@ -256,6 +275,9 @@ def run_ours(args):
     e2e_value = global_rows * e2e_steps / (e2e_ms * 1e-3)
     if not all(np.isfinite(v) for v in e2e_losses):
         raise RuntimeError("bench: a loss read back in the end-to-end loop is not finite")
+    # the device-resident loop once more, AFTER the end-to-end loop: separates what the host copies cost from the drift
+    # of a GPU that has been busy for longer (clocks / power state), which both later legs see
+    ms_repeat = timed_steps(sess, args.steps, 3) / args.steps if world == 1 else None  # (no rest() before this one)
     sess.finish()
     launches_per_step = sess.kernel_launches_per_step
     piped, n_flat, stash_gb, peer = sess.piped, sess.n_flat, sess.stash.numel() / 1e9, sess.peer is not None
@@ -280,7 +302,9 @@ def run_ours(args):
         return {"value": nrows / (ms * 1e-3), "unit": "voxels/s", "ms": ms, "grid": list(qshape),
                 "rows_per_gpu": q1r - q0r, "tflops_per_gpu": 2 * MAC_FWD * (q1r - q0r) / (ms * 1e-3) / 1e12}
 
+    rest()
     query = time_query(HR_SHAPE, max(5, args.steps))
+    rest()
     query_cfg5 = time_query((512, 512, 256), 3)
 
     # ---- weak scaling as an extra (N > 1): every rank owns a whole 128 x 128 x 64 slab of a (128 N) x 128 x 64 volume
@@ -289,6 +313,7 @@ def run_ours(args):
         del sess
         wshape = (HR_SHAPE[0] * world, HR_SHAPE[1], HR_SHAPE[2])
         _, wsess, _, _ = make_session(wshape)
+        rest()
         wms = timed_steps(wsess, args.steps, args.warmup) / args.steps
         weak = {"global_grid": list(wshape), "ms_per_step": wms,
                 "value": int(np.prod(wshape)) / (wms * 1e-3), "unit": "coord-samples/s"}
@@ -358,6 +383,10 @@ def run_ours(args):
                          "of prediction / gradient rows, rewritten every step",
                    "backward": "pipelined (one kernel, phase-only stash)" if piped else "staged (dgrad + wgrad)",
                    "accumulate": "fp32 (TMEM), bf16 operands, fp32 master weights / Adam state",
+                   "legs": "value, stage marks, e2e, queries and weak scaling are separate legs (own warm-up + timed "
+                           "region) with a 2 s idle gap between them; ms_per_step_after_e2e repeats the first leg "
+                           "right after the e2e leg without a gap (power-governor drift)",
+                   "launch": "CUDA-graph replay of the step (one graph per gradient-buffer parity)" if graphed else "eager",
                    "e2e": "per step: H2D of this rank's LR slab from pinned host memory (double-buffered, issued on a "
                           "side stream while the previous step computes) + D2H of the loss (read by the host one step "
                           "later, event-synchronised), through FitSession"},
@@ -371,6 +400,7 @@ def run_ours(args):
         "step_frac_of_peak": step_tflops / peaks["tflops"],
         "step_frac_of_sustained_peak": step_tflops / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
         "stage_ms": stage_ms,
+        "ms_per_step_after_e2e": ms_repeat,
         "hbm_kernels": hbm,
         "query": query,
         "query_cfg5": query_cfg5,

@@ -961,14 +961,31 @@ class FitSession:
     def capture(self):
         """Capture one step (every kernel is stream-ordered, Adam's step counter lives on the device) into a CUDA
         graph; later step() calls replay it.  Not used with a process group (the all-reduce stays eager)."""
-        if self.process_group is not None:
-            raise RuntimeError("b200inr: graph capture of a multi-GPU step is not supported")
+        if self.process_group is not None and self.peer is None:
+            raise RuntimeError("b200inr: graph capture of a multi-GPU step needs the in-kernel gradient exchange "
+                               "(the NCCL all-reduce stays eager)")
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_eager(None)
-            self._graph = g
+            if self.peer is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_eager(None)
+                self._graph = g
+            else:
+                # the two gradient buffers alternate: one graph per parity (every rank captures and replays the same
+                # sequence, so the kernels' start barriers keep meeting; the epoch counter lives on the device)
+                start = self._parity
+                graphs = {}
+                for _ in range(2):
+                    par = self._parity
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step_eager(None)  # (toggles self._parity on the host)
+                    graphs[par] = g
+                self._parity = start
+                self.grads = self.peer.grads[start]
+                self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
+                self._graph = graphs
 
     def set_target(self, target):
         """Replace the target values (same size), e.g. from pinned host memory."""
@@ -1000,7 +1017,13 @@ class FitSession:
 
     def step(self, marks=None):
         if self._graph is not None and marks is None:
-            self._graph.replay()
+            if isinstance(self._graph, dict):  # multi-GPU: one graph per gradient-buffer parity
+                self._graph[self._parity].replay()
+                self._parity ^= 1
+                self.grads = self.peer.grads[self._parity]
+                self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
+            else:
+                self._graph.replay()
             return self.loss
         return self._step_eager(marks)
 

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import b200inr  # noqa: E402
 
 
-def fit(dev, shape, C, lr_full, group, rank, world, steps, peer):
+def fit(dev, shape, C, lr_full, group, rank, world, steps, peer, graph=False):
     os.environ["B200INR_PEER_ALLREDUCE"] = "1" if peer else "0"
     os.environ["B200INR_PEER_ALLREDUCE_STRICT"] = "1"
     torch.manual_seed(0)
@@ -31,7 +31,11 @@ def fit(dev, shape, C, lr_full, group, rank, world, steps, peer):
     sess = b200inr.inr.FitSession(m, tgt, shape, lr=1e-4, degrade="pool", row_range=(r0, r1),
                                   global_count=lr_full.size, process_group=group)
     assert (sess.peer is not None) == (peer and group is not None)
-    losses = [float(sess.step().item()) for _ in range(steps)]
+    losses = []
+    for it in range(steps):
+        if graph and it == 2:
+            sess.capture()  # one CUDA graph per gradient-buffer parity; later steps replay them
+        losses.append(float(sess.step().item()))
     sess.finish()
     return m, losses, sess.eng["flat"].clone()
 
@@ -49,6 +53,8 @@ def main():
 
     m_peer, l_peer, flat_peer = fit(dev, shape, C, lr_full, group, rank, world, steps, peer=True)
     m_nccl, l_nccl, flat_nccl = fit(dev, shape, C, lr_full, group, rank, world, steps, peer=False)
+    _, l_graph, flat_graph = fit(dev, shape, C, lr_full, group, rank, world, steps, peer=True, graph=True)
+    np.testing.assert_allclose(l_graph, l_peer, rtol=2e-3)  # (the backward's atomics are not order-deterministic)
     # replicated weights: bit-identical across ranks on the in-kernel path
     gathered = [torch.empty_like(flat_peer) for _ in range(world)]
     dist.all_gather(gathered, flat_peer)
