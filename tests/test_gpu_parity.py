@@ -317,6 +317,45 @@ def test_pooled_fit_vs_oracle_psnr(dev):
     assert abs(O.ssim_volume(out, hr) - O.ssim_volume(ref_out, hr)) <= 0.002
 
 
+def _pooled_fit_vs_oracle(dev, shape, steps):
+    C, lr = 31, 1e-4
+    hr = b200inr.phantom.dwi_phantom(shape, n_dirs=C - 1, noise=0.0)
+    lr_t = b200inr.phantom.avg_pool_inplane(hr)
+    torch.manual_seed(21)
+    m = b200inr.Siren(3, 256, 4, C)
+    torch.manual_seed(21)
+    ref = O.torch_siren(3, 256, 4, C)
+    coords = torch.from_numpy(O.get_mgrid(shape))
+    ref_losses = O.torch_fit(ref, coords, torch.from_numpy(lr_t.reshape(-1, C)), steps, lr, degrade="pool",
+                             hr_shape=shape)
+    with torch.no_grad():
+        ref_out = ref(coords).numpy().reshape(*shape, C)
+    m = m.to(dev)
+    losses = m.fit(torch.from_numpy(lr_t).to(dev), shape, steps=steps, lr=lr, degrade="pool").cpu().numpy()
+    out = m.query(shape, clamp_min=None).cpu().numpy().reshape(*shape, C)
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+    d_psnr = abs(O.psnr(out, hr) - O.psnr(ref_out, hr))
+    d_ssim = abs(O.ssim_volume(out, hr) - O.ssim_volume(ref_out, hr))
+    assert d_psnr <= 0.1 and d_ssim <= 0.002, (d_psnr, d_ssim)  # BASELINE.json north_star gates
+    return d_psnr, d_ssim
+
+
+def test_pooled_fit_vs_oracle_psnr_mid_size(dev):
+    """cfg2 network, 64x64x32x31 volume (131 072 coordinates, 1024 tiles: every SM busy, multi-slot CTAs), 50 steps:
+    loss trajectory within 3 % per step, final PSNR within 0.1 dB and SSIM within 0.002 of the CPU oracle's fit."""
+    _pooled_fit_vs_oracle(dev, (64, 64, 32), 50)
+
+
+@pytest.mark.skipif(os.environ.get("B200INR_FULL_SIZE_TESTS", "0") != "1",
+                    reason="cfg2 at its full size: ~4 minutes of CPU oracle; set B200INR_FULL_SIZE_TESTS=1")
+def test_cfg2_full_size_fit_vs_oracle(dev):
+    """BASELINE configs[1] at its stated size -- 128x128x64x31, 50 steps -- against the CPU oracle (PSNR +-0.1 dB,
+    SSIM +-0.002).  Opt-in: the oracle needs minutes on the host cores; the result of the last run is recorded in
+    DESIGN.md section 4."""
+    d_psnr, d_ssim = _pooled_fit_vs_oracle(dev, (128, 128, 64), 50)
+    print(f"full-size cfg2 fit vs oracle: |dPSNR| = {d_psnr:.4f} dB, |dSSIM| = {d_ssim:.5f}")
+
+
 def test_sharded_fit_equals_single(dev):
     """Two row slabs accumulated into one gradient (what two ranks + all-reduce compute) == the full-batch gradient."""
     shape, C = (8, 16, 8), 31
