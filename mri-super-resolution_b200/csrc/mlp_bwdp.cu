@@ -338,7 +338,10 @@ __device__ __forceinline__ float rad_lo16(uint32_t w) {  // w: zero-extended 16-
 
 // kInstr = true compiles the stall counters / event trace in (tuning runs only): they double every wait statement and
 // push the hot loops out of the instruction cache (no_instruction stalls 1.8 per issue with them).
-template <bool kInstr>
+// kRelu: the ReLU-tail network (B200INR_NET_RELU_TAIL).  A TEMPLATE switch, not a run-time one: the hot loops of this
+// kernel live on the edge of the instruction cache, and the extra path cost the plain SIREN 13 % (cycles 1.93 M ->
+// 2.19 M, no_instruction stalls 0.21 -> 0.36 per issue) when it was a branch.
+template <bool kInstr, bool kRelu = false>
 __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kernel(const PipeParams p) {
   using S = PSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -812,7 +815,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       const int C = p.C;
       float dbsum = 0.f;
       // ReLU-tail network: the top activated layer (whose stash the edge CTAs read) is Linear + ReLU
-      const bool relu_top = edge && p.relu_tail != 0;
+      const bool relu_top = kRelu && edge;
 
       if (!edge) {
         // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
@@ -961,7 +964,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       if (!edge) {
         // dW_l[out][128 h + f] += omega_h * D[f][out]; this warp: outputs 64 cg .. 64 cg + 64 (lanes = consecutive inputs)
         float* dst = p.grads + p.off[2 * layer] + fi;
-        const float wsc = (p.relu_tail != 0 && layer == L) ? 1.0f : p.omegah;  // (the Linear + ReLU layer has no omega)
+        const float wsc = (kRelu && layer == L) ? 1.0f : p.omegah;  // (the Linear + ReLU layer has no omega)
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
@@ -1021,6 +1024,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   const PipeStashLayout sl = make_pipe_stash_layout(H, L, rows);
   PipeParams p{};
   p.Hr = net->hidden_features;
+  p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.pl = make_pack_layout(H, L);
   (void)coords;
@@ -1043,7 +1047,6 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   for (int i = 0; i < 2 * (L + 2); ++i) p.off[i] = off[i];
   p.omega0 = net->first_omega_0;
   p.omegah = net->hidden_omega_0;
-  p.relu_tail = (net->flags & B200INR_NET_RELU_TAIL) != 0;
   const int S2 = 2 * (L + 1);
   const int smem = PSmem::kBytes + PSmem::kSlack;
   // Every CTA of the grid waits on flags written by other CTAs of its pipeline, so the whole grid must be resident at
@@ -1054,10 +1057,10 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200INR_ERR_CUDA;
   const bool instr = false;
-  auto kern = siren_bwdp_kernel<false>;
+  auto kern = p.relu_tail ? siren_bwdp_kernel<false, true> : siren_bwdp_kernel<false, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
   if (dev < 0 || dev >= 64 || resident_ctas[dev] == 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return B200INR_ERR_CUDA;
     int per_sm = 0;
     if (kPMc) {
       cudaLaunchConfig_t cfg{};

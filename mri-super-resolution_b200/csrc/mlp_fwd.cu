@@ -96,14 +96,14 @@ constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 // sin + stores for the 16 consecutive columns [kb*64 + s*16, +16) of row r.
 // relu: the layer is Linear + ReLU (ReLU-tail network): y = max(theta, 0), and the 16-bit stash slot of an element
 // holds the bf16 OUTPUT instead of a phase (the backward needs y and the mask y > 0, not an angle).
-template <bool kStash, int kChunkStride = kTileRows * 16>
+template <bool kStash, int kChunkStride = kTileRows * 16, bool kReluNet = false>
 __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_block_addr, int r, int s,
                                             uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */,
                                             bool relu = false) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t yb[4], ph[4];
-    if (relu) {
+    if (kReluNet && relu) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         yb[j] = pack_bf16x2(fmaxf(th[c * 8 + 2 * j], 0.f), fmaxf(th[c * 8 + 2 * j + 1], 0.f));
@@ -202,7 +202,9 @@ __device__ __forceinline__ void walk_weight_schedule(int num_pairs, int my_tiles
 // kLoss (pipelined training only): the 2x2x1 pooled LR-consistency loss of the fit is taken in the final epilogue --
 // the two tiles of a CTA's slot are the two x-planes of one pooling window set, so the prediction never goes to HBM:
 // the kernel writes dL/dpred and accumulates the loss (what b200inr_pool_mse does in a second pass otherwise).
-template <int H, int kMode, bool kLoss>
+// kRelu: the ReLU-tail network (a template switch: an extra run-time path in the epilogue loop costs every network
+// instruction-cache misses, see mlp_bwdp.cu).
+template <int H, int kMode, bool kLoss, bool kRelu = false>
 __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdParams p) {
   constexpr bool kPair = true;  // (the 1-CTA schedule was retired; the switch documents what belongs to the pairing)
   static_assert(!kLoss || kMode == 2, "the fused loss belongs to the pipelined training forward");
@@ -537,9 +539,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
               add_f32x2(th[j4 * 4 + 2], th[j4 * 4 + 3], bq[j4].z, bq[j4].w);
             }
             constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
-            emit_sine16<kStash, kPhStride>(th, a_addr + kb * S::kABlock, r, s,
-                                           kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr,
-                                           p.relu_tail != 0 && l == L);
+            emit_sine16<kStash, kPhStride, kRelu>(th, a_addr + kb * S::kABlock, r, s,
+                                                  kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr,
+                                                  kRelu && l == L);
           }
           if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
           publish(j);
@@ -658,11 +660,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
 }
 
 // ------------------------------------------------------------------ launcher
-template <int H, int kMode, bool kLoss>
+template <int H, int kMode, bool kLoss, bool kRelu = false>
 static int launch_fwd_variant(const FwdParams& p, int grid_x, cudaStream_t stream) {
   constexpr bool kPair = true;
   const int smem = FwdSmem<H, kPair>::kBytes + 1024;
-  auto kern = siren_fwd_kernel<H, kMode, kLoss>;
+  auto kern = siren_fwd_kernel<H, kMode, kLoss, kRelu>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
   cudaLaunchConfig_t cfg{};
@@ -769,6 +771,9 @@ static int launch_siren_fwd_impl(const b200inr_net* net, const void* packed, con
     g = g < 2 ? 2 : (g & ~1);
     return launch_fwd_variant<H, 2, true>(p, g, stream);
   }
+  if (p.relu_tail)  // (check_net: never combined with the staged backward)
+    return stash ? launch_fwd_variant<H, 2, false, true>(p, grid_x, stream)
+                 : launch_fwd_variant<H, 0, false, true>(p, grid_x, stream);
   if (!stash) return launch_fwd_variant<H, 0, false>(p, grid_x, stream);
   if (staged) return launch_fwd_variant<H, 1, false>(p, grid_x, stream);
   return launch_fwd_variant<H, 2, false>(p, grid_x, stream);
