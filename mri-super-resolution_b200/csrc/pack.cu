@@ -186,8 +186,16 @@ __device__ __forceinline__ AdamCoef adam_coefficients(const AdamArgs& a, float* 
 __device__ __forceinline__ float adam_apply(const AdamArgs& a, const AdamCoef& c, long long i) {
   float gi;
   if (a.peer_grads != nullptr) {
+    // all peer loads are issued before the first add (a load-add-load-add chain would pay one NVLink round trip per
+    // rank); the sum is taken in rank order on every rank
     gi = 0.f;
-    for (int r = 0; r < a.world; ++r) gi += ld_relaxed_sys_f32(a.peer_grads[r] + i);
+    for (int r0 = 0; r0 < a.world; r0 += 8) {
+      float part[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) part[r] = (r0 + r < a.world) ? ld_relaxed_sys_f32(a.peer_grads[r0 + r] + i) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) gi += part[r];
+    }
   } else {
     gi = a.grads[i];
   }
@@ -219,7 +227,13 @@ __device__ __forceinline__ void adam_finish(const AdamArgs& a) {
     float loss;
     if (a.peer_grads != nullptr) {
       loss = 0.f;
-      for (int r = 0; r < a.world; ++r) loss += ld_relaxed_sys_f32(a.peer_grads[r] + a.n);
+      for (int r0 = 0; r0 < a.world; r0 += 8) {  // (loads first, then the sum: see adam_apply)
+        float part[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r] = (r0 + r < a.world) ? ld_relaxed_sys_f32(a.peer_grads[r0 + r] + a.n) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) loss += part[r];
+      }
     } else {
       loss = a.grads[a.n];
     }
