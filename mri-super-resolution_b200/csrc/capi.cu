@@ -35,7 +35,7 @@ int launch_wire_fwd(const b200inr_net* net, const void* packed, const float* coo
                     int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                     cudaStream_t stream);
 int launch_wire_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                    int num_sms, cudaStream_t stream);
+                    float* grad_in, int num_sms, cudaStream_t stream);
 int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num_sms, cudaStream_t stream);
 int launch_wire_combine(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, cudaStream_t stream);
 int launch_mse(const float* pred, const float* target, const float* weight, int64_t n, double count, float* grad,
@@ -77,10 +77,23 @@ static int check_net(const b200inr_net* net) {
   if (net->hidden_layers < 0 || net->hidden_layers + 1 > kMaxSineLayers) return B200INR_ERR_BAD_SHAPE;
   if (net->out_features < 1 || net->out_features > kOutPad) return B200INR_ERR_BAD_SHAPE;
   const int H = net->hidden_features;
-  if (net->activation == B200INR_ACT_GABOR) {  // WIRE: 128 complex units on raw coordinates
-    if (net->input_mode != B200INR_IN_COORDS || H != 128 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
-    if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
-    return B200INR_OK;
+  if (net->activation == B200INR_ACT_GABOR) {  // WIRE: 128 complex units
+    if (H != 128) return B200INR_ERR_BAD_SHAPE;
+    switch (net->input_mode) {
+      case B200INR_IN_COORDS:  // raw coordinates (first layer on CUDA cores)
+        if (net->in_features < 1 || net->in_features > 4 || net->mapping_size != 0) return B200INR_ERR_BAD_SHAPE;
+        return B200INR_OK;
+      case B200INR_IN_FOURIER:  // input_mapping fused into the first layer (wiretest.ipynb cells 6-9)
+        if (net->in_features < 1 || net->in_features > 4) return B200INR_ERR_BAD_SHAPE;
+        if (net->mapping_size < 32 || net->mapping_size % 32 != 0 || net->mapping_size > 256) return B200INR_ERR_BAD_SHAPE;
+        return B200INR_OK;
+      case B200INR_IN_FEATURES:  // explicit feature rows: Siren(in_features=2*mapping_size, ...) of wiretest.ipynb cell 7
+        if (net->in_features < 64 || net->in_features % 64 != 0 || net->in_features > 512 || net->mapping_size != 0)
+          return B200INR_ERR_BAD_SHAPE;
+        return B200INR_OK;
+      default:
+        return B200INR_ERR_BAD_SHAPE;
+    }
   }
   if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
   if ((net->flags & B200INR_NET_RELU_TAIL) && net->input_mode != B200INR_IN_COORDS) return B200INR_ERR_BAD_SHAPE;
@@ -280,7 +293,7 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   if ((e = device_sms(&sms))) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (is_wire(net)) {
-    if ((e = launch_wire_bwd(net, packed, stash, rows, grad_out, sms, s))) return e;
+    if ((e = launch_wire_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s))) return e;
     if ((e = launch_wire_wgrad(net, stash, rows, sms, s))) return e;
     return launch_wire_combine(net, stash, rows, grad_params, s);
   }
@@ -308,6 +321,11 @@ int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, voi
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_wire(net)) {
+    if ((e = launch_wire_bwd(net, packed, stash, rows, grad_out, grad_input, sms, s))) return e;
+    if ((e = launch_wire_wgrad(net, stash, rows, sms, s))) return e;
+    return launch_wire_combine(net, stash, rows, grad_params, s);
+  }
   if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, grad_input, sms, s))) return e;
   return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
 }
@@ -324,7 +342,7 @@ int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash,
     return B200INR_ERR_BAD_ALIGN;
   int sms = 0;
   if ((e = device_sms(&sms))) return e;
-  if (is_wire(net)) return launch_wire_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
+  if (is_wire(net)) return launch_wire_bwd(net, packed, stash, rows, grad_out, nullptr, sms, static_cast<cudaStream_t>(stream));
   if (is_gen(net))
     return launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, static_cast<cudaStream_t>(stream));
   return launch_siren_bwd(net, packed, stash, rows, grad_out, sms, static_cast<cudaStream_t>(stream));
@@ -548,7 +566,7 @@ int b200inr_param_offset_count(const b200inr_net* net, int32_t* count) {
   if (e) return e;
   if (!count) return B200INR_ERR_NULL;
   if (is_wire(net))
-    *count = 4 * (net->hidden_layers + 1) + 2;
+    *count = 4 * (net->hidden_layers + 1) + 2 + (net->input_mode == B200INR_IN_FOURIER ? 1 : 0);
   else
     *count = 2 * (net->hidden_layers + 2) + (net->input_mode == B200INR_IN_FOURIER ? 1 : 0);
   return B200INR_OK;

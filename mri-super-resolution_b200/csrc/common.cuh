@@ -291,6 +291,12 @@ __host__ __device__ inline GenStashLayout make_gen_stash_layout(const GenDims& g
 struct WireDims {
   int d, H, L, C;
   float omega0, omegah, s0;
+  int in_mode;  // B200INR_IN_COORDS: first layer on raw coordinates (CUDA cores); IN_FEATURES / IN_FOURIER: explicit or
+                // in-kernel Fourier feature rows (wiretest.ipynb cell 7), first layer on the tensor cores
+  int m;        // mapping size (IN_FOURIER) or 0
+  int K0;       // feature width (2m or in_features; multiple of 64, <= 512), 0 for raw coordinates
+  __host__ __device__ int kin() const { return K0 ? K0 : d; }  // columns of the first layer's weight matrices
+  __host__ __device__ int kb0() const { return K0 / 64; }
 };
 
 __host__ inline WireDims make_wire_dims(const b200inr_net* n) {
@@ -302,11 +308,16 @@ __host__ inline WireDims make_wire_dims(const b200inr_net* n) {
   w.omega0 = n->first_omega_0;
   w.omegah = n->hidden_omega_0;
   w.s0 = n->scale_0;
+  w.in_mode = n->input_mode;
+  w.m = n->input_mode == B200INR_IN_FOURIER ? n->mapping_size : 0;
+  w.K0 = n->input_mode == B200INR_IN_FOURIER ? 2 * n->mapping_size
+         : n->input_mode == B200INR_IN_FEATURES ? n->in_features : 0;
+  if (n->input_mode == B200INR_IN_FEATURES) w.d = 0;
   return w;
 }
 
 // Flat fp32 parameters: layer l: W_lin b_lin W_orth b_orth at off[4l .. 4l+3] (l = 0 real, l >= 1 complex as (re, im)
-// pairs), final W_f b_f (complex) at off[4(L+1)], off[4(L+1)+1].
+// pairs), final W_f b_f (complex) at off[4(L+1)], off[4(L+1)+1]; IN_FOURIER: the frozen matrix B [m, d] at off[4(L+1)+2].
 __host__ __device__ inline int64_t wire_param_offsets(const WireDims& w, int64_t* off) {
   int64_t o = 0;
   auto seg = [&](int64_t n) {
@@ -315,7 +326,7 @@ __host__ __device__ inline int64_t wire_param_offsets(const WireDims& w, int64_t
     return at;
   };
   for (int l = 0; l <= w.L; ++l) {
-    const int64_t nw = (l == 0) ? int64_t(w.H) * w.d : int64_t(w.H) * w.H * 2;
+    const int64_t nw = (l == 0) ? int64_t(w.H) * w.kin() : int64_t(w.H) * w.H * 2;
     const int64_t nbias = (l == 0) ? w.H : 2 * w.H;
     for (int j = 0; j < 2; ++j) {
       const int64_t a = seg(nw), b = seg(nbias);
@@ -324,6 +335,10 @@ __host__ __device__ inline int64_t wire_param_offsets(const WireDims& w, int64_t
   }
   const int64_t a = seg(int64_t(w.C) * w.H * 2), b = seg(2 * w.C);
   if (off) { off[4 * (w.L + 1)] = a; off[4 * (w.L + 1) + 1] = b; }
+  if (w.in_mode == B200INR_IN_FOURIER) {
+    const int64_t bm = seg(int64_t(w.m) * w.d);
+    if (off) off[4 * (w.L + 1) + 2] = bm;
+  }
   return o;
 }
 
@@ -335,6 +350,9 @@ struct WirePackLayout {
   size_t wt;     // L x 8 chunks [256 rows (k)][64 (n)]   dgrad operand, order k-block over n
   size_t wf;     // [4][32][64]     final linear: rows c, k < H: Re W_f, k >= H: -Im W_f
   size_t wft;    // [256 rows (k)][64 (c)]
+  size_t w0f;    // feature-fed first layer: K0/64 chunks [256 rows (n = 2u + {lin, orth})][64 (k)]
+  size_t wt0;    // feature-fed first layer, input-gradient operand: (K0/256 n-halves) x 8 chunks [256 rows (input k)][64 (n = 4u + comp)]
+  size_t bmat;   // float4 [m]: rows of the Fourier matrix B (zero padded to 4 coordinates)
   size_t total;
 };
 
@@ -356,14 +374,37 @@ __host__ __device__ inline WirePackLayout make_wire_pack_layout(const WireDims& 
   o += size_t(4) * kOutPad * 128;
   p.wft = o;
   o += kGenChunkBytes;
+  p.w0f = o;
+  o += size_t(w.kb0()) * kGenChunkBytes;
+  p.wt0 = o;
+  o += size_t((w.K0 + 255) / 256) * 8 * kGenChunkBytes;
+  p.bmat = o;
+  o += size_t(w.m) * 16;
   p.total = o;
   return p;
 }
+
+// fp32 offsets (in floats) inside the wgrad scratch of the WIRE family: per layer the real-block gradient [4H][K] and
+// the column sums [4H] (K = 2H; the first layer of a feature-fed network has K = K0 columns, so its slot is sized for
+// the wider of the two), then the final layer's [32][2H] + [32].
+__host__ __device__ inline size_t wire_gblk_w(const WireDims& w, int l) {
+  const size_t k_first = size_t(w.K0 > 2 * w.H ? w.K0 : 2 * w.H);
+  const size_t first = size_t(4 * w.H) * k_first + 4 * w.H;
+  return l == 0 ? 0 : first + size_t(l - 1) * (size_t(4 * w.H) * 2 * w.H + 4 * w.H);
+}
+__host__ __device__ inline size_t wire_gblk_b(const WireDims& w, int l) {
+  const size_t k = (l == 0) ? size_t(w.K0 > 2 * w.H ? w.K0 : 2 * w.H) : size_t(2 * w.H);
+  return wire_gblk_w(w, l) + size_t(4 * w.H) * k;
+}
+__host__ __device__ inline size_t wire_gblk_wf(const WireDims& w) { return wire_gblk_w(w, w.L + 1); }
+__host__ __device__ inline size_t wire_gblk_bf(const WireDims& w) { return wire_gblk_wf(w) + size_t(kOutPad) * 2 * w.H; }
 
 // Stash of the WIRE training forward: per Gabor layer the activations [h_r | h_i] (bf16 tile, 2H wide) and the
 // pre-activations (a, b, c, d) (bf16 tile, 4H wide; layer 0 stores (a, 0, c, 0)); dz = dL/d(a,b,c,d) written by dgrad.
 struct WireStashLayout {
   size_t y, z, dz, dzo, xa;
+  size_t ain;   // feature-fed networks: T x [K0/64][128][64] bf16, the network input (A operand of layer 0, B operand of dW_0)
+  size_t tile_in;
   size_t gblk;  // fp32 scratch of wgrad: per layer the real-block gradient [4H][K] + column sums [4H]; final [32][2H] + [32]
   size_t gblk_bytes;
   size_t tile_y, tile_z, stride_y, stride_z;
@@ -389,18 +430,15 @@ __host__ __device__ inline WireStashLayout make_wire_stash_layout(const WireDims
   o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
   s.xa = o;
   o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.ain = o;
+  s.tile_in = size_t(kTileRows) * w.K0 * 2;
+  o += size_t(s.tiles) * s.tile_in;
   s.gblk = o;
-  s.gblk_bytes = (size_t(w.L + 1) * (size_t(4 * w.H) * 2 * w.H + 4 * w.H) + size_t(kOutPad) * 2 * w.H + kOutPad) * 4;
+  s.gblk_bytes = (wire_gblk_w(w, w.L + 1) + size_t(kOutPad) * 2 * w.H + kOutPad) * 4;
   o += (s.gblk_bytes + 1023) & ~size_t(1023);
   s.total = o;
   return s;
 }
-
-// fp32 offsets (in floats) inside the wgrad scratch of the WIRE family
-__host__ __device__ inline size_t wire_gblk_w(const WireDims& w, int l) { return size_t(l) * (size_t(4 * w.H) * 2 * w.H + 4 * w.H); }
-__host__ __device__ inline size_t wire_gblk_b(const WireDims& w, int l) { return wire_gblk_w(w, l) + size_t(4 * w.H) * 2 * w.H; }
-__host__ __device__ inline size_t wire_gblk_wf(const WireDims& w) { return wire_gblk_w(w, w.L + 1); }
-__host__ __device__ inline size_t wire_gblk_bf(const WireDims& w) { return wire_gblk_wf(w) + size_t(kOutPad) * 2 * w.H; }
 
 struct GridDesc {
   int ndim;

@@ -424,31 +424,46 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
   const uint32_t tile_s = kTileRows * 128;
   for (int l = 0; l <= w.L; ++l) {
     for (int mh = 0; mh < 2; ++mh) {
-      if (ni >= kWgMaxItems - 1) return B200INR_ERR_BAD_SHAPE;
-      WgItem& it = p.items[ni];
-      it = WgItem{};
-      it.a_src = st + sl.dz + size_t(l) * sl.stride_z;
-      it.a_tile_bytes = uint32_t(sl.tile_z);
-      it.a_blk0 = 4 * mh;
-      it.gb = g + wire_gblk_b(w, l) + 256 * mh;
-      it.gb_count = 256;
-      it.scale = 1.0f;
-      if (l == 0) {
-        it.out = kWgOutCoord;
-        it.nb = 1;
-        it.b_src = st + sl.xa;
-        it.b_tile_bytes = tile_s;
-        it.gw = g + wire_gblk_w(w, 0) + size_t(256) * mh * w.d;
-        weight[ni++] = 80.0;
-      } else {
-        it.out = kWgOutBlock;
-        it.nb = 4;
-        it.b_src = st + sl.y + size_t(l - 1) * sl.stride_y;
-        it.b_tile_bytes = uint32_t(sl.tile_y);
-        it.gw = g + wire_gblk_w(w, l);
-        it.ldw = 2 * w.H;
-        it.row_off = 256 * mh;
-        weight[ni++] = 128.0;
+      // feature-fed first layer: K0 columns in groups of up to 4 blocks of the stashed network input
+      const int ngroups = (l == 0 && w.K0) ? (w.kb0() + 3) / 4 : 1;
+      for (int gq = 0; gq < ngroups; ++gq) {
+        if (ni >= kWgMaxItems - 1) return B200INR_ERR_BAD_SHAPE;
+        WgItem& it = p.items[ni];
+        it = WgItem{};
+        it.a_src = st + sl.dz + size_t(l) * sl.stride_z;
+        it.a_tile_bytes = uint32_t(sl.tile_z);
+        it.a_blk0 = 4 * mh;
+        it.gb = (gq == 0) ? g + wire_gblk_b(w, l) + 256 * mh : nullptr;
+        it.gb_count = 256;
+        it.scale = 1.0f;
+        if (l == 0 && w.K0) {
+          it.out = kWgOutBlock;
+          it.nb = (w.kb0() - 4 * gq) < 4 ? (w.kb0() - 4 * gq) : 4;
+          it.b_src = st + sl.ain;
+          it.b_tile_bytes = uint32_t(sl.tile_in);
+          it.b_blk0 = 4 * gq;
+          it.gw = g + wire_gblk_w(w, 0);
+          it.ldw = w.K0;
+          it.row_off = 256 * mh;
+          it.col_off = 256 * gq;
+          weight[ni++] = 64.0 + 16.0 * it.nb;
+        } else if (l == 0) {
+          it.out = kWgOutCoord;
+          it.nb = 1;
+          it.b_src = st + sl.xa;
+          it.b_tile_bytes = tile_s;
+          it.gw = g + wire_gblk_w(w, 0) + size_t(256) * mh * w.d;
+          weight[ni++] = 80.0;
+        } else {
+          it.out = kWgOutBlock;
+          it.nb = 4;
+          it.b_src = st + sl.y + size_t(l - 1) * sl.stride_y;
+          it.b_tile_bytes = uint32_t(sl.tile_y);
+          it.gw = g + wire_gblk_w(w, l);
+          it.ldw = 2 * w.H;
+          it.row_off = 256 * mh;
+          weight[ni++] = 128.0;
+        }
       }
     }
   }

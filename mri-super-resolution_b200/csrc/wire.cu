@@ -26,7 +26,7 @@ struct WirePackParams {
   uint8_t* packed;
   WireDims w;
   WirePackLayout pl;
-  long long off[4 * kMaxSineLayers + 2];
+  long long off[4 * kMaxSineLayers + 3];
 };
 
 __device__ __forceinline__ void wire_put_bf16(uint8_t* base, uint32_t row, uint32_t k, float v) {
@@ -38,12 +38,36 @@ __global__ void __launch_bounds__(256) wire_pack_kernel(const WirePackParams p) 
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   // first layer (real)
+  const int K0 = p.w.K0;
   for (long long i = tid; i < 2 * H; i += nthreads) {
     const int u = int(i >> 1), which = int(i & 1);  // 0: lin, 1: orth
     float wv[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < d; ++j) wv[j] = p.params[p.off[2 * which] + (long long)u * d + j];
+    if (K0 == 0)
+      for (int j = 0; j < d; ++j) wv[j] = p.params[p.off[2 * which] + (long long)u * d + j];
     reinterpret_cast<float4*>(p.packed + p.pl.w0)[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
     reinterpret_cast<float*>(p.packed + p.pl.b0)[i] = p.params[p.off[2 * which + 1] + u];
+  }
+  if (K0) {
+    // feature-fed first layer on the tensor cores: forward operand N = 2u + {lin, orth}, K = feature;
+    // input-gradient operand N = feature (whole 256-row chunks, zero padded), K = 4u + {a, b, c, d} (b, d rows zero)
+    for (long long i = tid; i < (long long)2 * H * K0; i += nthreads) {
+      const int n = int(i / K0), k = int(i % K0);
+      const float v = p.params[p.off[2 * (n & 1)] + (long long)(n >> 1) * K0 + k];
+      wire_put_bf16(p.packed + p.pl.w0f + size_t(k >> 6) * kGenChunkBytes, n, k & 63, v);
+    }
+    const int K0p = ((K0 + 255) / 256) * 256;
+    for (long long i = tid; i < (long long)4 * H * K0p; i += nthreads) {
+      const int n = int(i / K0p), k = int(i % K0p);  // n = 4u + comp
+      const int comp = n & 3;
+      float v = 0.f;
+      if ((comp & 1) == 0 && k < K0) v = p.params[p.off[comp] + (long long)(n >> 2) * K0 + k];  // comp 0: lin, 2: orth
+      wire_put_bf16(p.packed + p.pl.wt0 + size_t((k >> 8) * 8 + (n >> 6)) * kGenChunkBytes, k & 255, n & 63, v);
+    }
+    for (long long i = tid; i < p.w.m; i += nthreads) {
+      float wv[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < d; ++j) wv[j] = p.params[p.off[4 * (L + 1) + 2] + i * d + j];
+      reinterpret_cast<float4*>(p.packed + p.pl.bmat)[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    }
   }
   // hidden layers: biases in column order, real-block weights in both orientations
   float* bias = reinterpret_cast<float*>(p.packed + p.pl.bias);
@@ -99,9 +123,9 @@ int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, 
   p.packed = reinterpret_cast<uint8_t*>(packed);
   p.w = make_wire_dims(net);
   p.pl = make_wire_pack_layout(p.w);
-  int64_t off[4 * kMaxSineLayers + 2] = {0};
+  int64_t off[4 * kMaxSineLayers + 3] = {0};
   wire_param_offsets(p.w, off);
-  for (int i = 0; i < 4 * (p.w.L + 1) + 2; ++i) p.off[i] = off[i];
+  for (int i = 0; i < 4 * (p.w.L + 1) + 3; ++i) p.off[i] = off[i];
   wire_pack_kernel<<<592, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
@@ -132,7 +156,8 @@ struct WireFwdParams {
   uint8_t* stash_y;  // nullptr => inference
   uint8_t* stash_z;
   uint8_t* stash_xa;
-  size_t stride_y, stride_z, tile_z;
+  uint8_t* stash_ain;  // feature-fed networks: the network input tiles (bf16)
+  size_t stride_y, stride_z, tile_z, tile_in;
 };
 
 struct WireSmem {
@@ -156,7 +181,10 @@ __device__ __forceinline__ void gabor(float a, float b, float c, float d, float 
   hi = e * sn;
 }
 
-template <bool kStash>
+// kFeat: the first layer reads K0 (<= 512) explicit or in-kernel Fourier features per row and runs on the tensor cores
+// (N = 256 columns n = 2u + {lin, orth}); the A tile holds K = 256 columns, so wider inputs are fed in passes of four
+// 64-column blocks that accumulate into the same TMEM columns.
+template <bool kStash, bool kFeat>
 __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwdParams p) {
   using S = WireSmem;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -199,12 +227,21 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int KB0 = kFeat ? w.K0 / 64 : 0;
+  const int npass = (KB0 + kWireKB - 1) / kWireKB;
 
   if (warp == 0) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
+        for (int j = 0; j < KB0; ++j, ++c) {  // feature-fed first layer
+          const uint32_t slot = c % kWireSlots, round = c / kWireSlots;
+          if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
+          mbar_arrive_expect_tx(&w_full[slot], kGenChunkBytes);
+          bulk_g2s(w_smem + slot * kGenChunkBytes, p.packed + p.pl.w0f + size_t(j) * kGenChunkBytes, kGenChunkBytes,
+                   &w_full[slot]);
+        }
         for (int l = 1; l <= L + 1; ++l) {
           const bool hidden = (l <= L);
           const int nchunks = hidden ? 8 : kWireKB;
@@ -229,6 +266,24 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
       const uint32_t idesc_f = idesc_bf16(128, kOutPad, false, false);
       uint32_t c = 0, n = 0;
       for (int t = 0; t < my_tiles; ++t) {
+        for (int ps = 0; ps < npass; ++ps, ++n) {  // feature-fed first layer, four K blocks per pass
+          mbar_wait(a_ready, n & 1);
+          tc_fence_after();
+          const int nblk = (KB0 - ps * kWireKB) < kWireKB ? (KB0 - ps * kWireKB) : kWireKB;
+          for (int kb = 0; kb < nblk; ++kb, ++c) {
+            const uint32_t slot = c % kWireSlots;
+            mbar_wait(&w_full[slot], (c / kWireSlots) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t da = smem_desc(a_base + kb * kWireABlock + k4 * 32, hi);
+              const uint64_t db = smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi);
+              umma_bf16_ss_w(tmem_d, da, db, idesc_h, (ps | kb | k4) != 0);
+            }
+            umma_commit_w(&w_empty[slot]);
+          }
+          umma_commit_w(d_full);
+        }
         for (int l = 1; l <= L + 1; ++l, ++n) {
           mbar_wait(a_ready, n & 1);
           tc_fence_after();
@@ -257,10 +312,19 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
       uint32_t n = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        for (int ps = 0; ps < npass; ++ps, ++n) {  // the network input, one pass of feature blocks at a time
+          mbar_wait(a_ready, n & 1);
+          const int nblk = (KB0 - ps * kWireKB) < kWireKB ? (KB0 - ps * kWireKB) : kWireKB;
+          bulk_s2g(p.stash_ain + size_t(tile) * p.tile_in + size_t(ps) * kWireABytes, a_smem,
+                   uint32_t(nblk) * kWireABlock);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(a_free);
+        }
         for (int l = 0; l <= L; ++l, ++n) {
           mbar_wait(a_ready, n & 1);
           bulk_s2g(p.stash_y + size_t(l) * p.stride_y + size_t(tile) * kWireABytes, a_smem, kWireABytes);
-          if (l == 0) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
+          if (l == 0 && !kFeat) bulk_s2g(p.stash_xa + size_t(tile) * (kTileRows * 128), xa_smem, kTileRows * 128);
           bulk_commit();
           bulk_wait_read0();
           mbar_arrive(a_free);
@@ -296,6 +360,107 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_fwd_kernel(const WireFwd
       const long long row0 = (long long)tile * kTileRows;
       uint8_t* z_row = kStash ? p.stash_z + size_t(tile) * p.tile_z + size_t(r) * 16 : nullptr;
 
+      if (kFeat) {
+        // ---- feature-fed first Gabor layer: features -> A operand (passes of four blocks), MMA, then the epilogue
+        long long row = row0 + r;
+        if (row >= p.rows) row = p.rows - 1;
+        float xs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (w.in_mode == B200INR_IN_FOURIER) {
+          float x[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.coords != nullptr) {
+            for (int j = 0; j < w.d; ++j) x[j] = p.coords[row * w.d + j];
+          } else {
+            grid_coords(p.grid, row0 + r, x);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xs[j] = __fmul_rn(6.283185307179586f, x[j]);  // (2 pi x) first, like the reference
+        }
+        const float4* bmat_g = reinterpret_cast<const float4*>(p.packed + p.pl.bmat);
+        for (int ps = 0; ps < npass; ++ps) {
+          if (ps > 0) {  // the previous pass has been consumed by its MMAs (and stored, when training)
+            mbar_wait(d_full, n & 1);
+            ++n;
+            if (kStash) {
+              mbar_wait(a_free, nf & 1);
+              ++nf;
+            }
+          }
+          const int nblk = (KB0 - ps * kWireKB) < kWireKB ? (KB0 - ps * kWireKB) : kWireKB;
+          for (int kb = 0; kb < nblk; ++kb) {
+            const int col0 = (ps * kWireKB + kb) * 64 + s * 16;
+            float v[16];
+            if (w.in_mode == B200INR_IN_FOURIER) {
+              const bool is_sin = col0 < w.m;  // m is a multiple of 16: a 16-column slice never straddles sin | cos
+              const int k0 = is_sin ? col0 : col0 - w.m;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 bk = __ldg(bmat_g + k0 + j);
+                float pr = xs[0] * bk.x;
+                pr = fmaf(xs[1], bk.y, pr);
+                pr = fmaf(xs[2], bk.z, pr);
+                pr = fmaf(xs[3], bk.w, pr);
+                v[j] = is_sin ? __sinf(pr) : __cosf(pr);
+              }
+            } else {
+              const float4* f = reinterpret_cast<const float4*>(p.coords + row * w.K0 + col0);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 x4 = __ldg(f + j4);
+                v[j4 * 4 + 0] = x4.x; v[j4 * 4 + 1] = x4.y; v[j4 * 4 + 2] = x4.z; v[j4 * 4 + 3] = x4.w;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              sts128(a_addr + kb * kWireABlock + sw128_chunk_off(r, 2 * s + c),
+                     make_uint4(pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                                pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7])));
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready);
+        }
+        // epilogue of the first layer: D[:, 0:256), column n = 2u + {lin, orth}
+        mbar_wait(d_full, n & 1);
+        ++n;
+        if (kStash) {
+          mbar_wait(a_free, nf & 1);
+          ++nf;
+        }
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {  // 64-column groups: columns 64 g + 16 s .. + 15 = units 32 g + 8 s .. + 7
+          uint32_t v[16];
+          tmem_ld16(tmem_d + t_lane + g * 64 + s * 16, v);
+          tmem_ld_wait();
+          const int u0 = 32 * g + 8 * s;
+          float av[8], cv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 bb = __ldg(b0_g + u0 + j);
+            av[j] = __uint_as_float(v[2 * j]) + bb.x;
+            cv[j] = __uint_as_float(v[2 * j + 1]) + bb.y;
+          }
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            float hr[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gabor(av[4 * h4 + j], 0.f, cv[4 * h4 + j], 0.f, w.omega0, s2, hr[j], hi[j]);
+            store_units(u0 + 4 * h4, hr, hi);
+          }
+          if (kStash) {  // pre-activations (a, 0, c, 0), 8 columns (2 units) per 16-byte chunk
+#pragma unroll
+            for (int h2 = 0; h2 < 4; ++h2)
+              *reinterpret_cast<uint4*>(z_row + size_t(u0 / 2 + h2) * (kTileRows * 16)) =
+                  make_uint4(pack_bf16x2(av[2 * h2], 0.f), pack_bf16x2(cv[2 * h2], 0.f),
+                             pack_bf16x2(av[2 * h2 + 1], 0.f), pack_bf16x2(cv[2 * h2 + 1], 0.f));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      } else
       // ---- first Gabor layer (real inputs) on CUDA cores: this thread owns units 32 s .. 32 s + 31 of its row
       {
         float x[4];
@@ -464,21 +629,20 @@ int launch_wire_fwd(const b200inr_net* net, const void* packed, const float* coo
     p.stash_y = st + sl.y;
     p.stash_z = st + sl.z;
     p.stash_xa = st + sl.xa;
+    p.stash_ain = st + sl.ain;
     p.stride_y = sl.stride_y;
     p.stride_z = sl.stride_z;
     p.tile_z = sl.tile_z;
+    p.tile_in = sl.tile_in;
   }
   const int smem = WireSmem::kBytes + 1024;
   const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  if (stash) {
-    if (cudaFuncSetAttribute(wire_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return B200INR_ERR_CUDA;
-    wire_fwd_kernel<true><<<grid_x, kWireThreads, smem, stream>>>(p);
-  } else {
-    if (cudaFuncSetAttribute(wire_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return B200INR_ERR_CUDA;
-    wire_fwd_kernel<false><<<grid_x, kWireThreads, smem, stream>>>(p);
-  }
+  void (*kern)(const WireFwdParams) =
+      p.w.K0 ? (stash ? wire_fwd_kernel<true, true> : wire_fwd_kernel<false, true>)
+             : (stash ? wire_fwd_kernel<true, false> : wire_fwd_kernel<false, false>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
+  kern<<<grid_x, kWireThreads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
@@ -509,6 +673,8 @@ struct WireBwdParams {
   uint8_t* stash_dz;
   uint8_t* stash_dzo;
   size_t stride_z, tile_z;
+  float* grad_in;  // nullptr, or [rows, K0] fp32: dL/d(feature rows) of a feature-fed network (one more chain step,
+                   // dX = dZ_0 [W_lin ; W_orth] on the tensor cores -- the PerturbNet phase of wiretest.ipynb cell 10)
 };
 
 struct WireBwdSmem {
@@ -554,21 +720,25 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwd
     mbar_init(dzo_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int dx = p.grad_in != nullptr ? 1 : 0;  // extra chain step: gradient of the feature rows
+  const int NX = (w.K0 + 255) / 256;            // its N, in 256-column halves
 
   if (warp == 0) {
-    if (lane == 0) {  // weight producer: W_f^T (1 chunk), then the 8 chunks of Wblk_l^T for l = L .. 1
+    if (lane == 0) {  // weight producer: W_f^T (1 chunk), the 8 chunks of Wblk_l^T for l = L .. 1, [first layer^T]
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        for (int u = 0; u <= L; ++u) {
-          const int nchunks = (u == 0) ? 1 : kWireZBlocks;
-          const uint8_t* src = (u == 0) ? p.packed + p.pl.wft : p.packed + p.pl.wt + size_t(L - u) * 8 * kGenChunkBytes;
+        for (int u = 0; u <= L + dx; ++u) {
+          const int nchunks = (u == 0) ? 1 : (u <= L ? 1 : NX) * kWireZBlocks;
+          const uint8_t* src = (u == 0)   ? p.packed + p.pl.wft
+                               : (u <= L) ? p.packed + p.pl.wt + size_t(L - u) * 8 * kGenChunkBytes
+                                          : p.packed + p.pl.wt0;
           for (int j = 0; j < nchunks; ++j, ++c) {
             const uint32_t slot = c % kWireBwdSlots, round = c / kWireBwdSlots;
             if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
@@ -588,23 +758,25 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwd
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);
-        for (int u = 0; u <= L; ++u) {
+        for (int u = 0; u <= L + dx; ++u) {
           if (u == 0)
             mbar_wait(dzo_ready, t & 1);
           else
             mbar_wait(a_ready, (inst0 + u - 1) & 1);
           tc_fence_after();
           const int kbn = (u == 0) ? 1 : kWireZBlocks;
-          for (int kb = 0; kb < kbn; ++kb, ++c) {
-            const uint32_t slot = c % kWireBwdSlots;
-            mbar_wait(&w_full[slot], (c / kWireBwdSlots) & 1);
-            tc_fence_after();
-            const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * kWireABlock;
+          for (int nh = 0; nh < (u <= L ? 1 : NX); ++nh) {
+            for (int kb = 0; kb < kbn; ++kb, ++c) {
+              const uint32_t slot = c % kWireBwdSlots;
+              mbar_wait(&w_full[slot], (c / kWireBwdSlots) & 1);
+              tc_fence_after();
+              const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * kWireABlock;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_ss_w(tmem_d, smem_desc(a_blk + k4 * 32, hi),
-                           smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
-            umma_commit_w(&w_empty[slot]);
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_bf16_ss_w(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
+                               smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+              umma_commit_w(&w_empty[slot]);
+            }
           }
           umma_commit_w(d_full);
         }
@@ -721,16 +893,39 @@ __global__ void __launch_bounds__(kWireThreads, 1) wire_bwd_kernel(const WireBwd
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
       }
+
+      if (dx) {  // D[:, 0:K0) = dL/d(feature rows) -> grad_in
+        mbar_wait(d_full, n & 1);
+        ++n;
+        tc_fence_after();
+        const bool valid = (row0 + r) < p.rows;
+        float* gi = p.grad_in + (row0 + r) * (long long)w.K0;
+#pragma unroll 1
+        for (int kb = 0; kb < w.K0 / 64; ++kb) {
+          uint32_t v[16];
+          tmem_ld16(tmem_d + t_lane + kb * 64 + s * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(gi + kb * 64 + s * 16 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          }
+        }
+        tc_fence_before();
+      }
     }
   }
 
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem_d);
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
 }
 
 int launch_wire_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                    int num_sms, cudaStream_t stream) {
+                    float* grad_in, int num_sms, cudaStream_t stream) {
   WireBwdParams p{};
+  p.grad_in = grad_in;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.w = make_wire_dims(net);
   p.pl = make_wire_pack_layout(p.w);
@@ -762,11 +957,11 @@ struct WireCombineParams {
   const float* g;   // scratch
   float* grad;      // flat parameter gradient
   WireDims w;
-  long long off[4 * kMaxSineLayers + 2];
+  long long off[4 * kMaxSineLayers + 3];
 };
 
 __global__ void __launch_bounds__(256) wire_combine_kernel(const WireCombineParams p) {
-  const int H = p.w.H, L = p.w.L, C = p.w.C, d = p.w.d;
+  const int H = p.w.H, L = p.w.L, C = p.w.C, d = p.w.kin();  // d: columns of the first layer's (real) weights
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   // first layer (real): scratch rows 4u (lin) and 4u + 2 (orth), d columns
@@ -821,9 +1016,9 @@ int launch_wire_combine(const b200inr_net* net, void* stash, int64_t rows, float
   const WireStashLayout sl = make_wire_stash_layout(p.w, rows);
   p.g = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(stash) + sl.gblk);
   p.grad = grad_params;
-  int64_t off[4 * kMaxSineLayers + 2] = {0};
+  int64_t off[4 * kMaxSineLayers + 3] = {0};
   wire_param_offsets(p.w, off);
-  for (int i = 0; i < 4 * (p.w.L + 1) + 2; ++i) p.off[i] = off[i];
+  for (int i = 0; i < 4 * (p.w.L + 1) + 3; ++i) p.off[i] = off[i];
   wire_combine_kernel<<<296, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }

@@ -497,6 +497,8 @@ class _FusedMLP(nn.Module):
         if coords.dim() != 2 or coords.shape[1] != self.in_features:
             raise RuntimeError(f"b200inr: expected an input of shape [N, {self.in_features}]")
         keep = (getattr(self, "variant", "SRDWI") == "INRmodel" and coords.requires_grad and torch.is_grad_enabled())
+        if keep and self._desc.input_mode != _lib.IN_FEATURES and self._desc.activation == _lib.ACT_GABOR:
+            keep = False  # WIRE on raw coordinates: the coordinate grid is data, no producer needs its gradient
         if keep and self._desc.input_mode != _lib.IN_FEATURES:
             raise RuntimeError("b200inr: the input gradient is implemented for explicit feature rows (in_features >= 64), "
                                "the way the reference's PerturbNet phase feeds the network; raw coordinates carry none")
@@ -799,14 +801,33 @@ class ComplexGaborLayer2D(nn.Module):
 class Wire(_FusedMLP):
     """The WIRE network of the reference (INR/wiretest.ipynb cell 2, there also called `Siren`):
     Sequential(ComplexGaborLayer2D(first) , hidden_layers x ComplexGaborLayer2D, complex Linear), real part returned.
-    Same constructor arguments, construction order (RNG) and state-dict keys.  hidden_features = complex units (128)."""
+    Same constructor arguments, construction order (RNG) and state-dict keys.  hidden_features = complex units (128).
+
+    in_features <= 4: raw coordinates (grid-mode fit / query available).
+    in_features  > 4: explicit feature rows, the notebook's own configuration (cell 7:
+        Siren(in_features=2*mapping_size, hidden_features=128, hidden_layers=3, out_features=1, first_omega_0=1.2,
+        hidden_omega_0=1.2, scale=1.2) fed with input_mapping(coords, B)): the first Gabor layer is a tensor-core layer
+        (K = in_features, a multiple of 64 up to 512), and forward() hands back dL/d(features) when its input requires
+        grad (the PerturbNet phase of cell 10).
+    B=[m, in_features] (extension): input_mapping fused into the first layer -- forward(coords) ==
+        net(input_mapping(coords, B)) without the [N, 2m] matrix, and query / fit take the coordinate grid."""
 
     def __init__(self, in_features, hidden_features, hidden_layers, out_features, first_omega_0=10,
-                 hidden_omega_0=30., scale=10.0):
+                 hidden_omega_0=30., scale=10.0, B=None):
         super().__init__()
         self.in_features, self.hidden_features = int(in_features), int(hidden_features)
         self.hidden_layers, self.out_features = int(hidden_layers), int(out_features)
-        net = [ComplexGaborLayer2D(in_features, hidden_features, omega0=first_omega_0, sigma0=scale, is_first=True,
+        self.variant = "INRmodel"  # the notebook's class does not detach its input
+        mode, mapping, k_in = _lib.IN_COORDS, 0, self.in_features
+        if B is not None:
+            B = torch.as_tensor(B, dtype=torch.float32)
+            if B.dim() != 2 or B.shape[1] != self.in_features:
+                raise ValueError("B must have shape [mapping_size, in_features]")
+            self.register_buffer("B", B.clone())
+            mode, mapping, k_in = _lib.IN_FOURIER, int(B.shape[0]), 2 * int(B.shape[0])
+        elif self.in_features > 4:
+            mode = _lib.IN_FEATURES
+        net = [ComplexGaborLayer2D(k_in, hidden_features, omega0=first_omega_0, sigma0=scale, is_first=True,
                                    trainable=False)]
         for _ in range(hidden_layers):
             net.append(ComplexGaborLayer2D(hidden_features, hidden_features, is_first=False, omega0=hidden_omega_0,
@@ -815,7 +836,9 @@ class Wire(_FusedMLP):
         net.append(self.final_linear)
         self.net = nn.Sequential(*net)
         self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0,
-                                        hidden_omega_0, activation=_lib.ACT_GABOR, scale_0=scale), self.in_features)
+                                        hidden_omega_0, activation=_lib.ACT_GABOR, scale_0=scale, input_mode=mode,
+                                        mapping_size=mapping),
+                          None if mode == _lib.IN_FEATURES else self.in_features)
 
     def _canonical(self):
         ps = []
@@ -824,6 +847,9 @@ class Wire(_FusedMLP):
             ps += [layer.linear.weight, layer.linear.bias, layer.scale_orth.weight, layer.scale_orth.bias]
         ps += [self.final_linear.weight, self.final_linear.bias]
         return ps
+
+    def _frozen(self):
+        return [self.B] if "B" in self._buffers else []
 
 
 class FitSession:

@@ -393,6 +393,45 @@ def torch_pn(in_features, hidden_features, dimension):
     return _PN()
 
 
+def torch_wire(in_features, hidden_features, hidden_layers, out_features, first_omega_0=10.0, hidden_omega_0=30.0,
+               scale=10.0):
+    """CPU PyTorch restatement of the WIRE network of INR/wiretest.ipynb cells 1-2 (layer: INR/INRmodel.py:66-120) with
+    the reference's parameter names, registration and RNG order: per Gabor layer the frozen omega_0 / scale_0, then
+    `linear` and `scale_orth` (real in the first layer, complex64 after it, torch default init -- the reference's
+    nested init_weights is dead code); complex final linear; the real part is returned.
+        out = exp(1j * omega_0 * lin) * exp(-scale_0^2 * (|lin|^2 + |orth|^2))"""
+    import torch
+    from torch import nn
+
+    class _Gabor(nn.Module):
+        def __init__(self, fan_in, fan_out, first, omega, sigma):
+            super().__init__()
+            self.omega_0 = nn.Parameter(omega * torch.ones(1), False)
+            self.scale_0 = nn.Parameter(sigma * torch.ones(1), False)
+            dt = torch.float if first else torch.cfloat
+            self.linear = nn.Linear(fan_in, fan_out, dtype=dt)
+            self.scale_orth = nn.Linear(fan_in, fan_out, dtype=dt)
+
+        def forward(self, h):
+            lin, orth = self.linear(h), self.scale_orth(h)
+            env = torch.exp(-self.scale_0 * self.scale_0 * (lin.abs().square() + orth.abs().square()))
+            return torch.exp(1j * self.omega_0 * lin) * env
+
+    class _Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            layers = [_Gabor(in_features, hidden_features, True, first_omega_0, scale)]
+            layers += [_Gabor(hidden_features, hidden_features, False, hidden_omega_0, scale)
+                       for _ in range(hidden_layers)]
+            self.final_linear = nn.Linear(hidden_features, out_features, dtype=torch.cfloat)
+            self.net = nn.Sequential(*layers, self.final_linear)
+
+        def forward(self, coords):
+            return self.net(coords).real
+
+    return _Net()
+
+
 def torch_relu_mlp(in_dim, hidden_features, hidden_layers, out_features):
     """BASELINE config 4's network: Linear(in, H) + ReLU, `hidden_layers` x (Linear(H, H) + ReLU), Linear(H, C) with
     torch's default initialisation, fed with input_mapping(coords, B) (the reference only ever

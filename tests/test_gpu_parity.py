@@ -604,6 +604,139 @@ def test_wire_fused_fit_matches_module_loop(dev):
     assert _relerr(a.query(shape, clamp_min=None).cpu().numpy(), b.query(shape, clamp_min=None).cpu().numpy()) < 1e-2
 
 
+def test_wire_on_fourier_features_vs_reference_golden(dev, golden_dir):
+    """WIRE exactly as wiretest.ipynb builds and feeds it (cell 7: Siren(in_features=512, hidden 128, 3 hidden layers,
+    out 1, omega0 = scale = 1.2) on input_mapping features of the 4-D grid): fused forward, loss.backward() gradients,
+    the unmodified 5-step Adam(5e-5) loop, and the PerturbNet step of cell 10 (gradient through the feature rows into
+    PN) against the unmodified reference (tools/make_golden.py: wire_ff_case)."""
+    g = np.load(os.path.join(golden_dir, "wire_ff.npz"))
+    shape = tuple(int(v) for v in g["grid_shape"])
+    B = torch.from_numpy(g["B"]).to(dev)
+    gt = torch.from_numpy(g["gt"]).to(dev)
+    torch.manual_seed(int(g["seed"]))
+    m = b200inr.Wire(in_features=512, out_features=1, hidden_features=128, hidden_layers=3, first_omega_0=1.2,
+                     hidden_omega_0=1.2, scale=1.2)
+    pn = b200inr.INRmodel.PN(in_features=512, hidden_features=128, dimension=4)
+    assert list(m.state_dict().keys()) == list(g["keys"])
+    m, pn = m.to(dev), pn.to(dev)
+    feats = b200inr.input_mapping(b200inr.get_mgrid(shape).to(dev), B)
+    out = m.forward(feats)
+    assert _relerr(out.detach().cpu().numpy(), g["out"]) < BF16_RELERR
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=2e-2)
+    params = dict(m.named_parameters())
+
+    def real_view(t):
+        return (torch.view_as_real(t) if t.is_complex() else t).detach().cpu().numpy()
+
+    checked = 0
+    for k in [f for f in g.files if f.startswith("g/")]:
+        assert _relerr(real_view(params[k[2:]].grad), g[k]) < 3e-2, k
+        checked += 1
+    for k in [f for f in g.files if f.startswith("gcs/")]:
+        gr = real_view(params[k[4:]].grad).astype(np.float64)
+        assert abs((gr ** 2).sum() - g[k][1]) <= 6e-2 * g[k][1] + 1e-16, k
+    assert checked >= 6
+    assert _relerr(params["net.0.linear.weight"].grad.cpu().numpy()[:4], g["g_first_lin_rows"]) < 3e-2
+    # PerturbNet step
+    for p in m.parameters():
+        p.grad = None
+    perturbation = pn.forward(feats, 2, 1 / 128.)
+    np.testing.assert_allclose(perturbation.detach().cpu().numpy(), g["p_perturbation"], atol=2e-6)
+    pfeats = b200inr.input_mapping(perturbation, B)
+    pfeats.retain_grad()
+    pout = m.forward(pfeats)
+    ploss = ((pout - gt) ** 2).mean()
+    ploss.backward()
+    assert math.isclose(ploss.item(), float(g["p_loss"]), rel_tol=2e-2)
+    assert pfeats.grad is not None and pfeats.grad.shape == (feats.shape[0], 512)
+    assert _relerr(pfeats.grad.cpu().numpy()[:48], g["p_g_feats"]) < 3e-2
+    gf = pfeats.grad.double()
+    assert abs(float((gf * gf).sum()) - g["p_g_feats_cs"][1]) <= 6e-2 * g["p_g_feats_cs"][1]
+    for k, p in pn.named_parameters():
+        assert _relerr(p.grad.cpu().numpy()[:16], g["p_g_pn/" + k]) < 3e-2, k
+    # the unmodified INR loop
+    for p in m.parameters():
+        p.grad = None
+    opt = torch.optim.Adam(lr=5e-5, params=list(m.parameters()))
+    losses = []
+    for _ in range(5):
+        o = m.forward(feats)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    np.testing.assert_allclose(losses, g["losses"], rtol=3e-2)
+    with torch.no_grad():
+        assert _relerr(m(feats).cpu().numpy(), g["out_after"]) < 5e-2
+
+
+@pytest.mark.parametrize("k0", [64, 192, 256, 320, 512])
+def test_wire_feature_widths_vs_oracle(dev, k0):
+    """Feature-fed WIRE for input widths that need one or two passes of feature blocks (and a partial second pass):
+    output, every parameter gradient and dL/d(features) against the CPU oracle (torch_wire) on ragged row counts."""
+    torch.manual_seed(100 + k0)
+    m = b200inr.Wire(k0, 128, 2, 5, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2)
+    ref = O.torch_wire(k0, 128, 2, 5, 1.2, 1.2, 1.2)
+    ref.load_state_dict(m.state_dict())
+    m = m.to(dev)
+    rows = 300 + k0 % 7
+    x = (torch.rand(rows, k0, generator=torch.Generator().manual_seed(k0)) * 2 - 1) * 0.5
+    gout = torch.randn(rows, 5, generator=torch.Generator().manual_seed(k0 + 1))
+    xr = x.clone().requires_grad_(True)
+    out_ref = ref(xr)
+    out_ref.backward(gout)
+    xg = x.to(dev).requires_grad_(True)
+    out = m(xg)
+    assert _relerr(out.detach().cpu().numpy(), out_ref.detach().numpy()) < BF16_RELERR
+    out.backward(gout.to(dev))
+    assert _relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < 3e-2
+    gref = dict(ref.named_parameters())
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            assert gref[k].grad is None
+            continue
+        a, b = p.grad, gref[k].grad
+        a = (torch.view_as_real(a) if a.is_complex() else a).cpu().numpy()
+        b = (torch.view_as_real(b) if b.is_complex() else b).numpy()
+        assert _relerr(a, b) < 3e-2, k
+
+
+def test_wire_fused_fourier_matches_explicit_features(dev):
+    """Wire(B=...) computes input_mapping inside the first layer: same network as the explicit-feature module, from
+    raw coordinates; grid-mode query and fit are available."""
+    shape = (10, 9, 8)
+    rs = np.random.RandomState(2)
+    B = (rs.normal(size=(128, 3)) * 0.5).astype(np.float32)
+    torch.manual_seed(77)
+    a = b200inr.Wire(256, 128, 2, 3, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+    torch.manual_seed(77)
+    b = b200inr.Wire(3, 128, 2, 3, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2, B=B).to(dev)
+    for (k1, p1), (k2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert k1 == k2 and torch.equal(p1, p2)
+    x = b200inr.get_mgrid(shape).to(dev)
+    feats = b200inr.input_mapping(x, torch.from_numpy(B).to(dev))
+    with torch.no_grad():
+        oa, ob = a(feats), b(x)
+    assert _relerr(ob.cpu().numpy(), oa.cpu().numpy()) < 1e-2
+    q = b.query(shape, clamp_min=None)
+    assert _relerr(q.cpu().numpy(), ob.cpu().numpy()) < 1e-2
+    gt = torch.rand(x.shape[0], 3, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    lb = b.fit(gt, shape, steps=4, lr=5e-5).cpu().numpy()
+    opt = torch.optim.Adam(lr=5e-5, params=list(a.parameters()))
+    la = []
+    for _ in range(4):
+        ls = ((a(feats) - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        la.append(ls.item())
+    np.testing.assert_allclose(lb, la, rtol=1e-2)
+    assert torch.equal(b.B.cpu(), torch.from_numpy(B))
+
+
 def test_forward_grid_size_independent(dev):
     """The forward runs on CTA pairs (cta_group::2) that walk tile pairs in lock step; a pair member whose last slot
     lies past the end recomputes the last tile.  One tile, an odd tile count and a count that leaves a peer without a

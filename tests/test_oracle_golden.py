@@ -238,6 +238,60 @@ def test_perturbnet_step_restatement_matches_reference(golden_dir):
         assert np.abs(p.grad.numpy() - gr).max() <= 1e-3 * np.abs(gr).max() + 1e-12, k
 
 
+def test_wire_on_fourier_features_restatement_matches_reference(golden_dir):
+    """WIRE as wiretest.ipynb builds and feeds it (cells 6-10; tools/make_golden.py: wire_ff_case): the oracle's
+    torch_wire / torch_pn / input_mapping restatements give the same weights from the seed, output, gradients, 5-step
+    Adam(5e-5) trajectory and the PerturbNet step's gradients (dL/d features, PN parameters)."""
+    g = _load(golden_dir, "wire_ff.npz")
+    shape = tuple(int(v) for v in g["grid_shape"])
+    B = torch.from_numpy(g["B"])
+    gt = torch.from_numpy(g["gt"])
+    torch.manual_seed(int(g["seed"]))
+    w = O.torch_wire(512, 128, 3, 1, 1.2, 1.2, 1.2)
+    pn = O.torch_pn(512, 128, 4)
+    sd = w.state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    for k in sd:
+        v = torch.view_as_real(sd[k]) if sd[k].is_complex() else sd[k]
+        np.testing.assert_allclose(_cs(v), g["cs0/" + k], rtol=1e-12, atol=0)
+    for k, p in pn.named_parameters():
+        np.testing.assert_allclose(_cs(p), g["cs_pn/" + k], rtol=1e-12, atol=0)
+    feats = O.torch_input_mapping(torch.from_numpy(O.get_mgrid(shape)), B)
+    out = w(feats)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=2e-6, rtol=1e-4)
+    # the NumPy forward agrees as well
+    layers = [tuple(t.detach().numpy() for t in (l.linear.weight, l.linear.bias, l.scale_orth.weight, l.scale_orth.bias))
+              for l in list(w.net)[:-1]]
+    out_np = O.wire_forward(layers, w.final_linear.weight.detach().numpy(), w.final_linear.bias.detach().numpy(),
+                            feats.numpy(), 1.2, 1.2)
+    np.testing.assert_allclose(out_np, g["out"], atol=5e-6, rtol=1e-4)
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=1e-5)
+    params = dict(w.named_parameters())
+    for k in [f for f in g.files if f.startswith("g/")]:
+        gr = params[k[2:]].grad
+        gr = (torch.view_as_real(gr) if gr.is_complex() else gr).numpy()
+        assert np.abs(gr - g[k]).max() <= 1e-3 * np.abs(g[k]).max() + 1e-12, k
+    for p in w.parameters():
+        p.grad = None
+    perturbation = pn(feats, 2, 1 / 128.)
+    np.testing.assert_allclose(perturbation.detach().numpy(), g["p_perturbation"], atol=1e-7, rtol=1e-4)
+    pfeats = O.torch_input_mapping(perturbation, B)
+    pfeats.retain_grad()
+    ploss = ((w(pfeats) - gt) ** 2).mean()
+    ploss.backward()
+    assert math.isclose(ploss.item(), float(g["p_loss"]), rel_tol=1e-5)
+    np.testing.assert_allclose(pfeats.grad.numpy()[:48], g["p_g_feats"], atol=1e-9, rtol=1e-3)
+    for k, p in pn.named_parameters():
+        gr = g["p_g_pn/" + k]
+        assert np.abs(p.grad.numpy()[:16] - gr).max() <= 1e-3 * np.abs(gr).max() + 1e-12, k
+    for p in w.parameters():
+        p.grad = None
+    losses = O.torch_fit(w, feats, gt, 5, 5e-5)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-4)
+
+
 def test_calculate_adc_matches_reference(golden_dir):
     """Closed-form per-voxel fit == the reference's np.polyfit double loop (tools/make_golden.py: adc_case), clamps and
     the empty voxel included."""

@@ -269,6 +269,78 @@ def perturb_case():
           "|g_feats| max", feats.grad.abs().max().item())
 
 
+def wire_ff_case():
+    """WIRE exactly as wiretest.ipynb builds and feeds it (cells 6-10): B = N(0, 1)[256, 4] * 0.5 over the 4-D
+    (x, y, z, b) grid, model_input = input_mapping(get_mgrid(shape), B), Siren(in_features=512, hidden_features=128,
+    hidden_layers=3, out_features=1, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2) from cells 1-2, Adam(lr=5e-5),
+    on a small grid: output, autograd gradients, 5-step loss trajectory; then one PerturbNet step of cell 10
+    (PN(512, 128, 4), eps = 1/128) through the same network with the gradient reaching the feature rows."""
+    ns = wire_classes()
+    rs = np.random.RandomState(21)
+    shape = (6, 5, 4, 4)
+    B = torch.from_numpy(rs.normal(size=(256, 4)) * 0.5).float()
+    coords = INRmodel.get_mgrid(shape)
+    gt = torch.from_numpy(rs.uniform(size=(coords.shape[0], 1))).float()
+    torch.manual_seed(41)
+    w = ns["Siren"](in_features=512, out_features=1, hidden_features=128, hidden_layers=3, first_omega_0=1.2,
+                    hidden_omega_0=1.2, scale=1.2)
+    pn = INRmodel.PN(in_features=512, hidden_features=128, dimension=4)
+    sd0 = {k: v.clone() for k, v in w.state_dict().items()}
+    feats = INRmodel.input_mapping(coords, B)
+    out = w(feats)
+    loss = ((out - gt) ** 2).mean()
+    loss.backward()
+    d = {"grid_shape": np.array(shape), "B": B.numpy(), "gt": gt.numpy(), "out": out.detach().numpy(),
+         "loss": np.array(loss.item()), "keys": np.array(list(sd0.keys())), "seed": np.array(41)}
+    for k, v in sd0.items():
+        d["cs0/" + k] = checksum(torch.view_as_real(v) if v.is_complex() else v)
+    for k, pp in w.named_parameters():
+        if pp.grad is not None:
+            gg = torch.view_as_real(pp.grad) if pp.grad.is_complex() else pp.grad
+            d["gcs/" + k] = checksum(gg)
+            if gg.numel() <= 2048:
+                d["g/" + k] = gg.numpy().copy()
+    d["g_first_lin_rows"] = w.net[0].linear.weight.grad.numpy()[:4].copy()
+    # PerturbNet step (cell 10, else-branch) on the initial weights
+    for pp in w.parameters():
+        pp.grad = None
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        perturbation = pn.forward(feats, 2, 1 / 128.)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    pfeats = INRmodel.input_mapping(perturbation, B)
+    pfeats.retain_grad()
+    pout = w(pfeats)
+    ploss = ((pout - gt) ** 2).mean()
+    ploss.backward()
+    d.update({"p_out": pout.detach().numpy(), "p_loss": np.array(ploss.item()),
+              "p_perturbation": perturbation.detach().numpy(), "p_g_feats": pfeats.grad.numpy()[:48].copy(),
+              "p_g_feats_cs": checksum(pfeats.grad)})
+    for k, pp in pn.named_parameters():
+        d["p_g_pn/" + k] = pp.grad.numpy()[:16].copy()
+        d["p_gcs_pn/" + k] = checksum(pp.grad)
+        d["cs_pn/" + k] = checksum(pp)
+    # 5 Adam steps of the INR branch (cell 10, first branch)
+    for pp in w.parameters():
+        pp.grad = None
+    opt = torch.optim.Adam(lr=5e-5, params=list(w.parameters()))
+    losses = []
+    for _ in range(5):
+        o = w(feats)
+        ls = ((o - gt) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    d["losses"] = np.array(losses)
+    d["out_after"] = w(feats).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "wire_ff.npz"), **d)
+    print("wire_ff loss", loss.item(), "losses", losses, "p_loss", ploss.item(), "|g_feats| max",
+          pfeats.grad.abs().max().item(), "out range", out.min().item(), out.max().item())
+
+
 def adc_case():
     """calculate_ADC of the unmodified reference (INR/SRDWI.py:118-130) on a small synthetic slice: mono-exponential
     decays with noise, a few voxels driven into both clamps and to zero signal."""
@@ -406,12 +478,15 @@ if __name__ == "__main__":
         adc_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "perturb":
         perturb_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "wire_ff":
+        wire_ff_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "trained":
         trained_case()
     else:
         main()
         trained_case()
         perturb_case()
+        wire_ff_case()
         adc_case()
         combinations_case()
         erd_case()
