@@ -196,6 +196,16 @@ int b200inr_degrade_build_band_host(int32_t n_hr, int blur, float* fwd6_host, fl
 int b200inr_blurpool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC, double count,
                          const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid_lr,
                          float* grad_hr, float* loss_accum, void* stream);
+/* The same loss for ONE RANK'S SLAB of the volume (multi-GPU fit): the rank owns the HR planes
+ * [x_begin, x_end) (even bounds) of the X-plane volume.  pred_ext holds the planes [max(x_begin-4, 0), min(x_end+4, X))
+ * (own planes plus the neighbours' four halo planes), target_ext and resid_ext the LR rows
+ * [max(x_begin/2-1, 0), min(x_end/2+1, X/2)) (one halo row on either side: what the adjoint of the own planes reads);
+ * loss_accum[0] += sum over the OWN LR rows of resid^2 / count, grad_hr [x_end-x_begin, Y, ZC] = own planes of
+ * D^T (2 resid / count).  count is the global LR element count.  x_begin = 0, x_end = X is b200inr_blurpool_mse. */
+int b200inr_blurpool_mse_slab(const float* pred_ext, const float* target_ext, int32_t X, int32_t Y, int64_t ZC,
+                              double count, const float* bx6, const float* by6, const float* ax3, const float* ay3,
+                              int32_t x_begin, int32_t x_end, float* resid_ext, float* grad_hr, float* loss_accum,
+                              void* stream);
 /* Fused 2x2x1 average-pool consistency loss: loss_accum[0] += sum((pool(pred)-target_lr)^2)/count and
  * grad_hr = pool^T(2*(pool(pred)-target_lr)/count), one pass (the fast path of BASELINE config 2). */
 int b200inr_pool_mse(const float* pred_hr, const float* target_lr, int32_t X, int32_t Y, int64_t ZC,

@@ -74,6 +74,8 @@ SIGNATURES = {
     "b200inr_degrade_adjoint": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "b200inr_degrade_build_band_host": (ctypes.c_int, [_i32, ctypes.c_int, _P(_f32), _P(_f32)]),
     "b200inr_blurpool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200inr_blurpool_mse_slab": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                                                 _vp, _vp, _vp]),
     "b200inr_pool_mse": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _f64, _vp, _vp, _vp]),
     "b200inr_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "b200inr_optimizer_step": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),

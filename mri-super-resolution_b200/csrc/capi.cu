@@ -48,7 +48,7 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
                 const b200inr_axis_taps* ty, cudaStream_t stream);
 int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count,
                         const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid,
-                        float* grad, float* loss_accum, cudaStream_t stream);
+                        float* grad, float* loss_accum, int x_begin, int x_end, cudaStream_t stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float* state, cudaStream_t stream);
 int launch_optimizer_step(const b200inr_net* net, float* params, float* grads, float* m, float* v, int64_t n, float lr,
@@ -495,7 +495,17 @@ int b200inr_blurpool_mse(const float* pred_hr, const float* target_lr, int32_t X
   if (!pred_hr || !target_lr || !bx6 || !by6 || !ax3 || !ay3 || !resid_lr) return B200INR_ERR_NULL;
   if (!(count > 0)) return B200INR_ERR_BAD_SHAPE;
   return launch_blurpool_mse(pred_hr, target_lr, X, Y, ZC, count, bx6, by6, ax3, ay3, resid_lr, grad_hr, loss_accum,
-                             static_cast<cudaStream_t>(stream));
+                             0, X, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_blurpool_mse_slab(const float* pred_ext, const float* target_ext, int32_t X, int32_t Y, int64_t ZC,
+                              double count, const float* bx6, const float* by6, const float* ax3, const float* ay3,
+                              int32_t x_begin, int32_t x_end, float* resid_ext, float* grad_hr, float* loss_accum,
+                              void* stream) {
+  if (!pred_ext || !target_ext || !bx6 || !by6 || !ax3 || !ay3 || !resid_ext) return B200INR_ERR_NULL;
+  if (!(count > 0)) return B200INR_ERR_BAD_SHAPE;
+  return launch_blurpool_mse(pred_ext, target_ext, X, Y, ZC, count, bx6, by6, ax3, ay3, resid_ext, grad_hr, loss_accum,
+                             x_begin, x_end, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_degrade_forward(const float* hr, float* lr, int32_t X, int32_t Y, int64_t ZC, const b200inr_axis_taps* tx,

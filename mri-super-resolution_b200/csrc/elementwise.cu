@@ -255,22 +255,37 @@ __device__ __forceinline__ void stv(float* p, const VecF<V>& r) {
     p[0] = r.v[0];
 }
 
+// Slab form (a rank's share of the volume): the rank owns the HR planes [xa, xb) (even bounds) of
+// the X-plane volume.  `pred` holds the planes [px0, ...) = own planes plus up to four halo planes on either side
+// (received from the neighbours); the residual is evaluated for the LR rows [ie0, ie1) = own rows plus one halo row on
+// either side (what the adjoint of the own planes reads), `target` and `resid` start at LR row ie0, the loss only counts
+// the own rows [xa/2, xb/2).  The whole volume is the slab px0 = 0, ie0 = 0, ie1 = X/2.
+struct BlurSlab {
+  int px0;       // global x of the first plane of pred
+  int ie0, ie1;  // global LR rows evaluated (and stored in resid / target, first row ie0)
+  int il0, il1;  // global LR rows that count for the loss
+  int xa;        // global x of the first plane of grad (adjoint)
+};
+
 template <int V>
 __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
     const float* __restrict__ pred, const float* __restrict__ target, int X, int Y, long long ZC,
     const float* __restrict__ bx6, const float* __restrict__ by6, float inv_count, float* __restrict__ resid,
-    float* loss_accum) {
-  const int XL = X / 2, YL = Y / 2;
+    float* loss_accum, const BlurSlab sb) {
+  const int YL = Y / 2;
   const long long zcv = ZC / V;
-  const int chunks = (XL + kBlurChunk - 1) / kBlurChunk;
+  const int chunks = (sb.ie1 - sb.ie0 + kBlurChunk - 1) / kBlurChunk;
   const long long total = (long long)chunks * YL * zcv;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  pred -= (long long)sb.px0 * Y * ZC;                 // index with global plane / row numbers below
+  target -= (long long)sb.ie0 * YL * ZC;
+  resid -= (long long)sb.ie0 * YL * ZC;
   float acc = 0.f;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
     const long long zc = (t % zcv) * V;
     const int j = int((t / zcv) % YL);
     const int ic = int(t / (zcv * YL));
-    const int i0 = ic * kBlurChunk, i1 = min(i0 + kBlurChunk, XL);
+    const int i0 = sb.ie0 + ic * kBlurChunk, i1 = min(i0 + kBlurChunk, sb.ie1);
     float wy[kBandFwd];
 #pragma unroll
     for (int b = 0; b < kBandFwd; ++b) wy[b] = __ldg(by6 + j * kBandFwd + b);
@@ -304,10 +319,11 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
 #pragma unroll
         for (int e = 0; e < V; ++e) r.v[e] = fmaf(wx, w[a].v[e], r.v[e]);
       }
+      const bool counts = (i >= sb.il0 && i < sb.il1);
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         r.v[e] -= tg.v[e];
-        acc = fmaf(r.v[e], r.v[e], acc);
+        if (counts) acc = fmaf(r.v[e], r.v[e], acc);
       }
       stv<V>(resid + ((long long)i * YL + j) * ZC + zc, r);
       if (i + 1 < i1) {
@@ -324,17 +340,19 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
 template <int V>
 __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
     const float* __restrict__ resid, int X, int Y, long long ZC, const float* __restrict__ ax3,
-    const float* __restrict__ ay3, float gscale, float* __restrict__ grad) {
+    const float* __restrict__ ay3, float gscale, float* __restrict__ grad, const BlurSlab sb) {
   const int XL = X / 2, YL = Y / 2;
   const long long zcv = ZC / V;
-  const int chunks = (XL + kBlurChunk - 1) / kBlurChunk;
+  const int chunks = (sb.il1 - sb.il0 + kBlurChunk - 1) / kBlurChunk;
   const long long total = (long long)chunks * Y * zcv;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  resid -= (long long)sb.ie0 * YL * ZC;  // global LR row numbers below
+  grad -= (long long)sb.xa * Y * ZC;     // global HR plane numbers below
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
     const long long zc = (t % zcv) * V;
     const int y = int((t / zcv) % Y);
     const int mc = int(t / (zcv * Y));
-    const int m0 = mc * kBlurChunk, m1 = min(m0 + kBlurChunk, XL);
+    const int m0 = sb.il0 + mc * kBlurChunk, m1 = min(m0 + kBlurChunk, sb.il1);
     const int j0 = (y - 2) >> 1;  // LR columns j0 .. j0+2 read HR column y
     float wy[kBandAdj];
 #pragma unroll
@@ -386,25 +404,34 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
 
 int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, int64_t ZC, double count,
                         const float* bx6, const float* by6, const float* ax3, const float* ay3, float* resid,
-                        float* grad, float* loss_accum, cudaStream_t stream) {
+                        float* grad, float* loss_accum, int x_begin, int x_end, cudaStream_t stream) {
   if ((X & 1) || (Y & 1) || X < 2 || Y < 2 || ZC < 1) return B200INR_ERR_BAD_SHAPE;
+  if (x_begin < 0 || x_end > X || x_begin >= x_end || (x_begin & 1) || (x_end & 1)) return B200INR_ERR_BAD_SHAPE;
+  BlurSlab sb;
+  sb.px0 = x_begin - 4 > 0 ? x_begin - 4 : 0;
+  sb.il0 = x_begin / 2;
+  sb.il1 = x_end / 2;
+  sb.ie0 = sb.il0 > 0 ? sb.il0 - 1 : 0;
+  sb.ie1 = sb.il1 < X / 2 ? sb.il1 + 1 : X / 2;
+  sb.xa = x_begin;
   const bool vec = (ZC % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
                                       reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
-  const int chunks = (X / 2 + kBlurChunk - 1) / kBlurChunk;
   const long long zcv = vec ? ZC / 4 : ZC;
   auto nblocks = [&](long long total) {
     long long b = (total + kEwThreads - 1) / kEwThreads;
     if (b > kSmCount * 16) b = kSmCount * 16;
     return int(b < 1 ? 1 : b);
   };
-  const int b1 = nblocks((long long)chunks * (Y / 2) * zcv), b2 = nblocks((long long)chunks * Y * zcv);
+  const int chunks1 = (sb.ie1 - sb.ie0 + kBlurChunk - 1) / kBlurChunk;
+  const int chunks2 = (sb.il1 - sb.il0 + kBlurChunk - 1) / kBlurChunk;
+  const int b1 = nblocks((long long)chunks1 * (Y / 2) * zcv), b2 = nblocks((long long)chunks2 * Y * zcv);
   const float inv = float(1.0 / count), gsc = float(2.0 / count);
   if (vec) {
-    blurpool_residual_kernel<4><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum);
-    if (grad) blurpool_adjoint_kernel<4><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad);
+    blurpool_residual_kernel<4><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum, sb);
+    if (grad) blurpool_adjoint_kernel<4><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad, sb);
   } else {
-    blurpool_residual_kernel<1><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum);
-    if (grad) blurpool_adjoint_kernel<1><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad);
+    blurpool_residual_kernel<1><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum, sb);
+    if (grad) blurpool_adjoint_kernel<1><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad, sb);
   }
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }

@@ -897,21 +897,45 @@ class FitSession:
             self.count = float(global_count if global_count is not None else rows * C // 4)
         elif degrade == "blur_pool":
             # Gaussian sigma = 0.5 (mirror boundary) then 2x2x1 average: skimage rescale(0.5, anti_aliasing=True)
-            # (dwi_inr.ipynb#c6:L8).  The blur crosses slab borders: whole volume only.
-            if len(shape) != 3 or row_range is not None:
-                raise RuntimeError("b200inr: degrade='blur_pool' needs the whole 3-D grid (X, Y, Z) on one GPU")
+            # (dwi_inr.ipynb#c6:L8).  The blur crosses slab borders: a rank that owns the x-planes
+            # [xa, xb) receives its neighbours' four edge planes of the prediction after the forward (one grouped
+            # send/recv) and evaluates the residual on one extra LR row per side (b200inr_blurpool_mse_slab); its
+            # `target` then holds the LR rows [max(xa/2-1, 0), min(xb/2+1, X/2)) (parallel.lr_slab(..., halo=1)).
+            if len(shape) != 3:
+                raise RuntimeError("b200inr: degrade='blur_pool' needs a 3-D grid (X, Y, Z)")
             if shape[0] % 2 or shape[1] % 2:
                 raise RuntimeError("b200inr: blurred pooling needs even X and Y")
+            plane = shape[1] * shape[2]
+            if rows % (2 * plane) or begin % (2 * plane) or rows == 0:
+                raise RuntimeError("b200inr: a blurred-pooling slab is a non-empty range of whole pairs of x-planes")
             self.X, self.Y, self.ZC = shape[0], shape[1], shape[2] * C
-            if target.numel() != rows * C // 4:
-                raise RuntimeError("b200inr: pooled fit target must have rows*C/4 elements")
-            self.count = float(rows * C // 4)
+            xa, xb = begin // plane, end // plane
+            self.slab = (xa, xb)
+            px0, px1 = max(xa - 4, 0), min(xb + 4, shape[0])
+            ie0, ie1 = max(xa // 2 - 1, 0), min(xb // 2 + 1, shape[0] // 2)
+            lr_row = (shape[1] // 2) * shape[2] * C
+            if target.numel() != (ie1 - ie0) * lr_row:
+                raise RuntimeError("b200inr: blurred-pooling target must hold the slab's LR rows plus one halo row per "
+                                   "interior side (parallel.lr_slab(target, shape, row_range, halo=1))")
+            self.count = float(global_count if global_count is not None else total * C // 4)
+            self.halo = None
+            if px0 < xa or px1 > xb:  # interior borders: neighbours' planes are needed
+                if process_group is None:
+                    raise RuntimeError("b200inr: a partial blur_pool slab needs the process group of its neighbours")
+                if xb - xa < 4:
+                    raise RuntimeError("b200inr: blur_pool slabs must hold at least four x-planes (the halo width)")
+                import torch.distributed as dist
+                rk = dist.get_rank(process_group)
+                self.halo = {"left": dist.get_global_rank(process_group, rk - 1) if px0 < xa else None,
+                             "right": dist.get_global_rank(process_group, rk + 1) if px1 > xb else None,
+                             "nl": (xa - px0) * plane, "nr": (px1 - xb) * plane, "edge": 4 * plane}
             # banded form of D along x and y (6 taps per LR row, 3 per HR row): operands of b200inr_blurpool_mse
             self.bands = []
             for n_hr in (shape[0], shape[1]):
                 fwd6, adj3 = _lib.build_band_tables(n_hr, True)
                 self.bands.append((torch.from_numpy(fwd6).to(dev), torch.from_numpy(adj3).to(dev)))
-            self.lr_resid = torch.empty(rows * C // 4, dtype=torch.float32, device=dev)
+            self.lr_resid = torch.empty((ie1 - ie0) * lr_row, dtype=torch.float32, device=dev)
+            self.pred_ext = torch.empty(((px1 - px0) * plane, C), dtype=torch.float32, device=dev)
         else:
             raise ValueError("degrade must be None, 'pool' or 'blur_pool'")
         if degrade is not None and (module._desc.flags & _lib.NET_RELU_TAIL):
@@ -956,7 +980,11 @@ class FitSession:
             self.grads = torch.zeros(self.n_flat + 4, dtype=torch.float32, device=dev)
         self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)  # the last finished step's loss
-        self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        if degrade == "blur_pool":  # the forward writes the own planes into the middle of the halo-extended buffer
+            lo = (self.slab[0] - max(self.slab[0] - 4, 0)) * shape[1] * shape[2]
+            self.pred = self.pred_ext[lo:lo + rows]
+        else:
+            self.pred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.dpred = torch.empty((rows, C), dtype=torch.float32, device=dev)
         self.stash = _aligned_bytes(_lib.stash_bytes(module._desc, rows), dev)
         d = module._desc
@@ -990,6 +1018,9 @@ class FitSession:
         if self.process_group is not None and self.peer is None:
             raise RuntimeError("b200inr: graph capture of a multi-GPU step needs the in-kernel gradient exchange "
                                "(the NCCL all-reduce stays eager)")
+        if getattr(self, "halo", None) is not None:
+            raise RuntimeError("b200inr: a sharded blur_pool step exchanges halo planes with NCCL send/recv and stays "
+                               "eager")
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             if self.peer is None:
@@ -1115,10 +1146,13 @@ class FitSession:
             _lib.check(lib.b200inr_pool_mse(_ptr(self.pred), _ptr(self.target), self.x_local, self.Y, self.ZC,
                                             self.count, _ptr(self.dpred), _ptr(self.loss_acc), s), "pool_mse")
         else:  # r = D pred - target (+ loss), then dL/dpred = D^T 2 r / count: two streaming passes
+            if self.halo is not None:
+                self._exchange_halo()
             (bx6, ax3), (by6, ay3) = self.bands
-            _lib.check(lib.b200inr_blurpool_mse(_ptr(self.pred), _ptr(self.target), self.X, self.Y, self.ZC, self.count,
-                                                _ptr(bx6), _ptr(by6), _ptr(ax3), _ptr(ay3), _ptr(self.lr_resid),
-                                                _ptr(self.dpred), _ptr(self.loss_acc), s), "blurpool_mse")
+            _lib.check(lib.b200inr_blurpool_mse_slab(_ptr(self.pred_ext), _ptr(self.target), self.X, self.Y, self.ZC,
+                                                     self.count, _ptr(bx6), _ptr(by6), _ptr(ax3), _ptr(ay3),
+                                                     self.slab[0], self.slab[1], _ptr(self.lr_resid), _ptr(self.dpred),
+                                                     _ptr(self.loss_acc), s), "blurpool_mse_slab")
         mark()
         if self.piped:  # one layer-pipelined kernel: dgrad chain + every weight / bias gradient
             _lib.check(lib.b200inr_siren_backward(net, _ptr(eng["packed"]), _ptr(self.stash), None, gref, rows,
@@ -1131,6 +1165,23 @@ class FitSession:
             _lib.check(lib.b200inr_siren_wgrad(net, _ptr(self.stash), None, gref, rows, _ptr(self.grads), s),
                        "siren_wgrad")
         mark()
+
+    def _exchange_halo(self):
+        """Blurred pooling across slab borders: the four edge planes of this rank's prediction go to each neighbour and
+        theirs arrive in the halo planes of pred_ext -- one grouped NCCL send/recv per step, stream-ordered (the only
+        data-path exchange of the fit besides the gradient sum)."""
+        import torch.distributed as dist
+        h, pg = self.halo, self.process_group
+        n = self.pred_ext.shape[0]
+        ops = []
+        if h["left"] is not None:
+            ops.append(dist.P2POp(dist.isend, self.pred[:h["edge"]], h["left"], group=pg))
+            ops.append(dist.P2POp(dist.irecv, self.pred_ext[:h["nl"]], h["left"], group=pg))
+        if h["right"] is not None:
+            ops.append(dist.P2POp(dist.isend, self.pred[self.rows - h["edge"]:], h["right"], group=pg))
+            ops.append(dist.P2POp(dist.irecv, self.pred_ext[n - h["nr"]:], h["right"], group=pg))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
 
     def finish(self):
         """Write the fp32 master weights back into the module's nn.Parameters."""

@@ -26,11 +26,14 @@ def shard_rows(shape, world_size, rank, pooled=False):
     return u0 * unit_planes * plane, u1 * unit_planes * plane
 
 
-def lr_slab(target_lr, shape, row_range):
-    """The part of an LR target volume [X/2, Y/2, Z, C] matching the HR row range of a pooled shard."""
+def lr_slab(target_lr, shape, row_range, halo=0):
+    """The part of an LR target volume [X/2, Y/2, Z, C] matching the HR row range of a pooled shard.
+
+    halo=1 (degrade='blur_pool'): one more LR row on every interior side -- the blurred degradation's adjoint of the
+    slab's own planes reads the residual of those rows."""
     plane = int(np.prod(shape[1:]))
     x0, x1 = row_range[0] // plane, row_range[1] // plane
-    return target_lr[x0 // 2:x1 // 2]
+    return target_lr[max(x0 // 2 - halo, 0):min(x1 // 2 + halo, target_lr.shape[0])]
 
 
 class PeerGradients:

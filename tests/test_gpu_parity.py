@@ -1320,6 +1320,39 @@ def test_blurpool_mse_vs_oracle(dev, shape, C):
     assert abs(loss.item() - float((d_ref.astype(np.float64) ** 2).mean())) <= 1e-5 * float((d_ref ** 2).mean())
 
 
+@pytest.mark.parametrize("shape,C,cuts", [((24, 10, 5), 8, (0, 8, 12, 24)), ((16, 6, 3), 3, (0, 4, 8, 12, 16)),
+                                          ((12, 8, 4), 4, (0, 12))])
+def test_blurpool_slabs_equal_whole_volume(dev, shape, C, cuts):
+    """b200inr_blurpool_mse_slab, the per-rank form of the blurred pooling loss: slabs of whole x-plane pairs, fed with
+    their four halo planes of the prediction and one halo row of the target, give the whole-volume call's gradient
+    planes BIT for bit and losses that add up to its loss (what a multi-GPU fit computes, here on one device)."""
+    X, Y, Z = shape
+    rng = np.random.RandomState(11)
+    pred = torch.from_numpy(rng.rand(X, Y, Z, C).astype(np.float32)).to(dev)
+    target = torch.from_numpy(rng.rand(X // 2, Y // 2, Z, C).astype(np.float32)).to(dev)
+    count = float(target.numel())
+    (bx6, ax3), (by6, ay3) = [tuple(torch.from_numpy(t).to(dev) for t in L.build_band_tables(n, True)) for n in (X, Y)]
+    lib = L.load()
+    resid, grad, loss = torch.empty_like(target), torch.empty_like(pred), torch.zeros(1, device=dev)
+    L.check(lib.b200inr_blurpool_mse(_ptr(pred), _ptr(target), X, Y, Z * C, count, _ptr(bx6), _ptr(by6), _ptr(ax3),
+                                     _ptr(ay3), _ptr(resid), _ptr(grad), _ptr(loss), _stream()), "blurpool_mse")
+    total = 0.0
+    for xa, xb in zip(cuts[:-1], cuts[1:]):
+        p_ext = pred[max(xa - 4, 0):min(xb + 4, X)].contiguous()
+        t_ext = target[max(xa // 2 - 1, 0):min(xb // 2 + 1, X // 2)].contiguous()
+        r_ext, g_own, l_own = torch.empty_like(t_ext), torch.empty_like(pred[xa:xb]), torch.zeros(1, device=dev)
+        L.check(lib.b200inr_blurpool_mse_slab(_ptr(p_ext), _ptr(t_ext), X, Y, Z * C, count, _ptr(bx6), _ptr(by6),
+                                              _ptr(ax3), _ptr(ay3), xa, xb, _ptr(r_ext), _ptr(g_own), _ptr(l_own),
+                                              _stream()), "blurpool_mse_slab")
+        assert torch.equal(g_own, grad[xa:xb]), (xa, xb)
+        assert torch.equal(r_ext, resid[max(xa // 2 - 1, 0):min(xb // 2 + 1, X // 2)])
+        total += l_own.item()
+    assert abs(total - loss.item()) <= 1e-5 * loss.item()
+    bad = lib.b200inr_blurpool_mse_slab(_ptr(pred), _ptr(target), X, Y, Z * C, count, _ptr(bx6), _ptr(by6), _ptr(ax3),
+                                        _ptr(ay3), 1, X, _ptr(resid), _ptr(grad), _ptr(loss), _stream())
+    assert bad != 0  # odd slab bounds are refused
+
+
 # ------------------------------------------------------------------------------------------------ soft-ERD path
 def test_relu_tail_siren_vs_reference_golden(dev, golden_dir):
     """SirenERD (INR/INR_ERD.py:28-67) through the fused kernels against the unmodified reference class: seeded
