@@ -36,6 +36,9 @@ extern "C" {
                                (ComplexGaborLayer2D, INR/INRmodel.py:109-120; WIRE network INR/wiretest.ipynb cell 2):
                                hidden_features = H complex units (128), IN_COORDS only */
 
+#define B200INR_ACT_TANH 3 /* tanh(z): the perturbation network PN (INR/INRmodel.py:153-169) as a generic-family
+                              network (H = 256 operands; a 128-wide PN is zero padded); omegas ignored            */
+
 #define B200INR_IN_COORDS 0   /* network input = the d <= 4 raw coordinates; H <= 256, multiple of 8 (zero-padded) */
 #define B200INR_IN_FOURIER 1  /* network input = input_mapping(coords, B) (INR/SRDWI.py:111-116) computed in-kernel
                                  from the d raw coordinates; in_features = d, first layer K = 2 * mapping_size      */
@@ -63,6 +66,15 @@ typedef struct b200inr_net {
  * calls b200inr_siren_backward then makes).  The stash layout differs, so forward, backward and
  * b200inr_stash_bytes must see the same flag.  Ignored by the other network families (always staged). */
 #define B200INR_NET_STAGED_BWD 1
+/* Generic family (IN_FOURIER / IN_FEATURES): the forward's activations are only needed for the activation-gradient
+ * chain (a FROZEN network whose input gradient is wanted: the INR inside the PerturbNet phase, INR/inrDWI.py:141-147,
+ * where the reference's autograd computes INR weight gradients that nobody uses).  The training forward then stashes
+ * only what the chain reads (16-bit phases for sine, bf16 outputs for ReLU / tanh), the backward stores no dL/dtheta
+ * tiles, and parameter gradients are unavailable (b200inr_siren_backward_coords with grad_params = NULL). */
+#define B200INR_NET_DGRAD_ONLY 4
+/* Generic family: the network output passes through scale_0 * tanh(.) (PN's `eps * tanh(...)`, INR/INRmodel.py:167).
+ * The backward needs the forward's output to form the derivative: b200inr_siren_backward_tanh_out. */
+#define B200INR_NET_TANH_OUT 8
 /* The ReLU-tail SIREN of INR/INR_ERD.py:28-67 (SIREN on raw coordinates, pipelined backward only): the LAST of the
  * hidden_layers hidden layers is nn.Linear + nn.ReLU (no omega) instead of a SineLayer, and the network output passes
  * through a ReLU:  net = SineLayer(first), (hidden_layers - 1) x SineLayer, Linear + ReLU, final Linear, ReLU.
@@ -144,6 +156,28 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
  * B200INR_ERR_BAD_SHAPE for the other input modes. */
 int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, void* stash, int64_t rows,
                                  const float* grad_out, float* grad_params, float* grad_input, void* stream);
+
+/* Generic-family network on in-kernel Fourier features (B200INR_IN_FOURIER): backward that also returns
+ * dL/d(coordinates) [rows, d] -- the input gradient chained through the adjoint of input_mapping (INR/SRDWI.py:111-116)
+ * inside the kernel, so neither the [rows, 2m] features nor their gradient touch HBM.  This is the INR's share of the
+ * reference's PerturbNet phase (INR/inrDWI.py:141-147: loss.backward() through INR.forward(input_mapping(PN(...), B))).
+ * grad_params = NULL with B200INR_NET_DGRAD_ONLY set (frozen network, lean stash); otherwise parameter gradients are
+ * accumulated as in b200inr_siren_backward.  coords / grid: the same rows the forward was given. */
+int b200inr_siren_backward_coords(const b200inr_net* net, const void* packed, void* stash, const float* coords,
+                                  const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
+                                  float* grad_coords, void* stream);
+/* Backward of a generic-family network with B200INR_NET_TANH_OUT (PN: out = scale_0 * tanh(final linear)): `out` is the
+ * forward's output [rows, C], grad_out the gradient with respect to it. */
+int b200inr_siren_backward_tanh_out(const b200inr_net* net, const void* packed, void* stash, int64_t rows,
+                                    const float* out, const float* grad_out, float* grad_params, void* stream);
+/* PN (INR/INRmodel.py:153-169) feeds its first layer cat(features, acq) with the constant acq = sample / 10: the same as
+ * a bias b + acq * w_last.  master = [generic-family parameters (n_net floats) | w_last[H]].
+ * effective_params: eff[0:n_net] = master[0:n_net] with eff[bias_off + h] += acq * w_last[h] (input of
+ * b200inr_pack_weights), and clear_grads[0 : n_net + H] = 0 when not NULL (the step's zero_grad);
+ * fold_grad: grads[n_net + h] = acq * grads[bias_off + h] after the weight-gradient pass. */
+int b200inr_pn_effective_params(const float* master, int64_t n_net, int64_t bias_off, int32_t H, float acq, float* eff,
+                                float* clear_grads, void* stream);
+int b200inr_pn_fold_grad(float* grads, int64_t n_net, int64_t bias_off, int32_t H, float acq, void* stream);
 
 /* The two kernels of the STAGED b200inr_siren_backward as separate calls (same arguments; backward == dgrad then
  * wgrad).  B200INR_ERR_BAD_SHAPE for a pipelined SIREN (no B200INR_NET_STAGED_BWD): its backward is one kernel.

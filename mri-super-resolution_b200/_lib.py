@@ -12,10 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200INR_LIB") or os.path.join(_HERE, "lib", "libb200inr.so")  # (override: kernel tuning builds)
 
 MAX_TAPS = 8
-ACT_SINE, ACT_RELU, ACT_GABOR = 0, 1, 2
+ACT_SINE, ACT_RELU, ACT_GABOR, ACT_TANH = 0, 1, 2, 3
 IN_COORDS, IN_FOURIER, IN_FEATURES = 0, 1, 2
 DEFAULT_PIPED_BWD = "1"  # raw-coordinate SIRENs train through the pipelined backward (B200INR_PIPED_BWD=0: staged)
 NET_RELU_TAIL = 2   # B200INR_NET_RELU_TAIL: last hidden layer Linear + ReLU, ReLU on the output (INR/INR_ERD.py:28-67)
+NET_DGRAD_ONLY = 4  # B200INR_NET_DGRAD_ONLY: generic family, frozen network: stash only what the dgrad chain reads
+NET_TANH_OUT = 8    # B200INR_NET_TANH_OUT: generic family, out = scale_0 * tanh(final linear) (PN)
 NET_STAGED_BWD = 1  # B200INR_NET_STAGED_BWD: the older forward-stash / dgrad / wgrad training path of raw-coordinate SIRENs
 
 
@@ -64,6 +66,10 @@ SIGNATURES = {
     "b200inr_siren_forward_pool_loss": (ctypes.c_int, [_P(Net), _vp, _P(Grid), _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "b200inr_siren_backward": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _P(Grid), _i64, _vp, _vp, _vp]),
     "b200inr_siren_backward_input": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200inr_siren_backward_coords": (ctypes.c_int, [_P(Net), _vp, _vp, _vp, _P(Grid), _i64, _vp, _vp, _vp, _vp]),
+    "b200inr_siren_backward_tanh_out": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200inr_pn_effective_params": (ctypes.c_int, [_vp, _i64, _i64, _i32, _f32, _vp, _vp, _vp]),
+    "b200inr_pn_fold_grad": (ctypes.c_int, [_vp, _i64, _i64, _i32, _f32, _vp]),
     "b200inr_siren_dgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _i64, _vp, _vp]),
     "b200inr_siren_wgrad": (ctypes.c_int, [_P(Net), _vp, _vp, _P(Grid), _i64, _vp, _vp]),
     "b200inr_mse_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp]),

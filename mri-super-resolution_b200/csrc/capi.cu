@@ -27,7 +27,11 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
                    int64_t rows, float* out, int clamp, float clamp_min, void* stash, int num_sms,
                    cudaStream_t stream);
 int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                   float* grad_in, int num_sms, cudaStream_t stream);
+                   float* grad_in, int num_sms, cudaStream_t stream, float* grad_coords = nullptr,
+                   const float* coords = nullptr, const b200inr_grid* grid = nullptr, const float* out_y = nullptr);
+int launch_pn_effective(const float* master, int64_t n_net, int64_t bias_off, int H, float acq, float* eff,
+                        float* clear, cudaStream_t stream);
+int launch_pn_fold_grad(float* grads, int64_t n_net, int64_t bias_off, int H, float acq, cudaStream_t stream);
 int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, int num_sms,
                      cudaStream_t stream);
 int launch_wire_pack(const b200inr_net* net, const float* params, void* packed, cudaStream_t stream);
@@ -95,8 +99,16 @@ static int check_net(const b200inr_net* net) {
         return B200INR_ERR_BAD_SHAPE;
     }
   }
-  if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU) return B200INR_ERR_BAD_SHAPE;
+  if (net->activation != B200INR_ACT_SINE && net->activation != B200INR_ACT_RELU &&
+      net->activation != B200INR_ACT_TANH)
+    return B200INR_ERR_BAD_SHAPE;
   if ((net->flags & B200INR_NET_RELU_TAIL) && net->input_mode != B200INR_IN_COORDS) return B200INR_ERR_BAD_SHAPE;
+  // tanh networks (the perturbation network), tanh output and the dgrad-only stash belong to the generic family
+  if (net->input_mode == B200INR_IN_COORDS &&
+      (net->activation == B200INR_ACT_TANH || (net->flags & (B200INR_NET_DGRAD_ONLY | B200INR_NET_TANH_OUT))))
+    return B200INR_ERR_BAD_SHAPE;
+  if (net->activation == B200INR_ACT_TANH && H != 256) return B200INR_ERR_BAD_SHAPE;
+  if ((net->flags & B200INR_NET_TANH_OUT) && !(net->scale_0 != 0.f)) return B200INR_ERR_BAD_SHAPE;
   switch (net->input_mode) {
     case B200INR_IN_COORDS:  // SIREN on raw coordinates: any width up to 256 (multiple of 8) runs on the 256-wide
                              // kernels with zero-padded operands; parameters and gradients keep the real width
@@ -298,6 +310,9 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
     return launch_wire_combine(net, stash, rows, grad_params, s);
   }
   if (is_gen(net)) {
+    // tanh output: the derivative needs the forward's output (b200inr_siren_backward_tanh_out); dgrad-only stash: there
+    // is nothing to contract weight gradients from (b200inr_siren_backward_coords)
+    if (net->flags & (B200INR_NET_TANH_OUT | B200INR_NET_DGRAD_ONLY)) return B200INR_ERR_BAD_SHAPE;
     if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
   }
@@ -313,6 +328,7 @@ int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, voi
   if (e) return e;
   if (!packed || !stash || !grad_out || !grad_params || !grad_input) return B200INR_ERR_NULL;
   if (net->input_mode != B200INR_IN_FEATURES) return B200INR_ERR_BAD_SHAPE;  // explicit feature rows only
+  if (net->flags & (B200INR_NET_TANH_OUT | B200INR_NET_DGRAD_ONLY)) return B200INR_ERR_BAD_SHAPE;
   if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023) ||
@@ -328,6 +344,62 @@ int b200inr_siren_backward_input(const b200inr_net* net, const void* packed, voi
   }
   if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, grad_input, sms, s))) return e;
   return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
+}
+
+int b200inr_siren_backward_coords(const b200inr_net* net, const void* packed, void* stash, const float* coords,
+                                  const b200inr_grid* grid, int64_t rows, const float* grad_out, float* grad_params,
+                                  float* grad_coords, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !stash || !grad_out || !grad_coords) return B200INR_ERR_NULL;
+  if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
+  if (is_wire(net) || net->input_mode != B200INR_IN_FOURIER) return B200INR_ERR_BAD_SHAPE;
+  if ((net->flags & B200INR_NET_TANH_OUT)) return B200INR_ERR_BAD_SHAPE;
+  if (((net->flags & B200INR_NET_DGRAD_ONLY) != 0) != (grad_params == nullptr)) return B200INR_ERR_BAD_SHAPE;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if (grid && (e = check_grid(net, grid, rows))) return e;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023) ||
+      (grad_params && !aligned16(grad_params)))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s, grad_coords, coords, grid))) return e;
+  if (grad_params) return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
+  return B200INR_OK;
+}
+
+int b200inr_siren_backward_tanh_out(const b200inr_net* net, const void* packed, void* stash, int64_t rows,
+                                    const float* out, const float* grad_out, float* grad_params, void* stream) {
+  int e = check_net(net);
+  if (e) return e;
+  if (!packed || !stash || !out || !grad_out || !grad_params) return B200INR_ERR_NULL;
+  if (is_wire(net) || !is_gen(net) || !(net->flags & B200INR_NET_TANH_OUT) || (net->flags & B200INR_NET_DGRAD_ONLY))
+    return B200INR_ERR_BAD_SHAPE;
+  if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
+  if (rows == 0) return B200INR_OK;
+  if ((reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(stash) & 1023) ||
+      !aligned16(grad_params))
+    return B200INR_ERR_BAD_ALIGN;
+  int sms = 0;
+  if ((e = device_sms(&sms))) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s, nullptr, nullptr, nullptr, out))) return e;
+  return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
+}
+
+int b200inr_pn_effective_params(const float* master, int64_t n_net, int64_t bias_off, int32_t H, float acq, float* eff,
+                                float* clear_grads, void* stream) {
+  if (!master || !eff) return B200INR_ERR_NULL;
+  if (n_net < 1 || bias_off < 0 || H < 1 || bias_off + H > n_net) return B200INR_ERR_BAD_SHAPE;
+  return launch_pn_effective(master, n_net, bias_off, H, acq, eff, clear_grads, static_cast<cudaStream_t>(stream));
+}
+
+int b200inr_pn_fold_grad(float* grads, int64_t n_net, int64_t bias_off, int32_t H, float acq, void* stream) {
+  if (!grads) return B200INR_ERR_NULL;
+  if (n_net < 1 || bias_off < 0 || H < 1 || bias_off + H > n_net) return B200INR_ERR_BAD_SHAPE;
+  return launch_pn_fold_grad(grads, n_net, bias_off, H, acq, static_cast<cudaStream_t>(stream));
 }
 
 int b200inr_siren_dgrad(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,

@@ -163,6 +163,7 @@ struct GenDims {
   int H, L, C;
   int act, in_mode;
   float omega0, omegah;
+  int lean;  // B200INR_NET_DGRAD_ONLY: the stash only holds what the activation-gradient chain reads
   __host__ __device__ int kb0() const { return K0 / 64; }
   __host__ __device__ int kbh() const { return H / 64; }
   __host__ __device__ int nh() const { return H / 256; }
@@ -180,6 +181,7 @@ __host__ inline GenDims make_gen_dims(const b200inr_net* n) {
   g.act = n->activation;
   g.omega0 = n->activation == B200INR_ACT_SINE ? n->first_omega_0 : 1.0f;
   g.omegah = n->activation == B200INR_ACT_SINE ? n->hidden_omega_0 : 1.0f;
+  g.lean = (n->flags & B200INR_NET_DGRAD_ONLY) ? 1 : 0;
   return g;
 }
 
@@ -271,16 +273,16 @@ __host__ __device__ inline GenStashLayout make_gen_stash_layout(const GenDims& g
   s.layer_stride = size_t(s.tiles) * s.tile_h;
   size_t o = 0;
   s.ain = o;
-  o += size_t(s.tiles) * s.tile_in;
+  if (!g.lean) o += size_t(s.tiles) * s.tile_in;
   s.y = o;
-  o += size_t(g.L + 1) * s.layer_stride;
+  if (!g.lean || g.act != B200INR_ACT_SINE) o += size_t(g.L + 1) * s.layer_stride;
   s.ph = o;
   if (g.act == B200INR_ACT_SINE) o += size_t(g.L + 1) * s.layer_stride;
   s.dz = o;
-  o += size_t(g.L + 1) * s.layer_stride;
+  if (!g.lean) o += size_t(g.L + 1) * s.layer_stride;
   s.dzo = o;
-  o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
-  s.total = o;
+  if (!g.lean) o += size_t(s.tiles) * kTileRows * kDzoPad * 2;
+  s.total = o > 0 ? o : 1024;
   return s;
 }
 

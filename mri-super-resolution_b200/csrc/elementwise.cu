@@ -675,4 +675,42 @@ int launch_combinations(const float* b0, const float* b1, const float* b2, const
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ perturbation network PN   INR/INRmodel.py:153-169
+// PN's first layer reads cat(features, acq) with a CONSTANT acquisition column acq = sample / 10, i.e. it is
+// Linear(features) with the bias b + acq * w_last.  The trained vector w_last lives behind the generic-family
+// parameters in PN's master vector ([net parameters | w_last[H]]); these two helpers keep it in the loop:
+//   effective parameters (what b200inr_pack_weights reads):  eff = master[0:n_net], eff[bias_off + h] += acq * w_last[h]
+//   gradient fold (after the weight-gradient pass):           grads[n_net + h] = acq * grads[bias_off + h]
+__global__ void __launch_bounds__(kEwThreads) pn_effective_kernel(const float* __restrict__ master, long long n_net,
+                                                                  long long bias_off, int H, float acq,
+                                                                  float* __restrict__ eff, float* __restrict__ clear) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_net + H; i += stride) {
+    if (clear != nullptr) clear[i] = 0.f;  // the step's gradient accumulator ([net | w_last], like master)
+    if (i >= n_net) continue;
+    float v = master[i];
+    if (i >= bias_off && i < bias_off + H) v = fmaf(acq, master[n_net + (i - bias_off)], v);
+    eff[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) pn_fold_grad_kernel(float* __restrict__ grads, long long n_net,
+                                                                  long long bias_off, int H, float acq) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < H) grads[n_net + h] = acq * grads[bias_off + h];
+}
+
+int launch_pn_effective(const float* master, int64_t n_net, int64_t bias_off, int H, float acq, float* eff,
+                        float* clear, cudaStream_t stream) {
+  long long blocks = (n_net + H + kEwThreads - 1) / kEwThreads;
+  if (blocks > kSmCount * 8) blocks = kSmCount * 8;
+  pn_effective_kernel<<<int(blocks), kEwThreads, 0, stream>>>(master, n_net, bias_off, H, acq, eff, clear);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
+int launch_pn_fold_grad(float* grads, int64_t n_net, int64_t bias_off, int H, float acq, cudaStream_t stream) {
+  pn_fold_grad_kernel<<<(H + kEwThreads - 1) / kEwThreads, kEwThreads, 0, stream>>>(grads, n_net, bias_off, H, acq);
+  return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
+}
+
 }  // namespace b200inr

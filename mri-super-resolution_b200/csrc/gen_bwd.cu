@@ -36,6 +36,15 @@ struct GenBwdParams {
   uint8_t* stash_dzo;
   size_t layer_stride;
   float* grad_in;  // nullptr, or [rows, K0] fp32: dL/d(network input)
+  // IN_FOURIER: dL/d(coordinates) [rows, d] instead -- the adjoint of input_mapping (SURVEY.md App. B.2:
+  // dp = dphi_sin cos p - dphi_cos sin p, dx = 2 pi dp B) applied to the input gradient while it is still in TMEM, so
+  // the [rows, 2m] feature gradient never exists (the PerturbNet phase, INR/inrDWI.py:141-147)
+  float* grad_coords;
+  const float* coords;  // explicit coordinates [rows, d] or nullptr (grid)
+  GridDesc grid;
+  const float* out_y;   // B200INR_NET_TANH_OUT: the forward's output y = s tanh(.), [rows, C]; dOut *= s - y^2 / s
+  float out_tanh;
+  int lean;             // B200INR_NET_DGRAD_ONLY: no dL/dtheta tiles are stored (there is no weight-gradient pass)
 };
 
 template <int H>
@@ -48,7 +57,8 @@ struct GenBwdSmem {
   static constexpr int kOffW = kABytes;
   static constexpr int kOffDzo = kOffW + kSlots * kGenChunkBytes;
   static constexpr int kOffBar = kOffDzo + kTileRows * 128;
-  static constexpr int kBytes = kOffBar + 256;
+  static constexpr int kOffRed = kOffBar + 256;                   // [4 slices][128 rows] float4: coordinate-gradient partials
+  static constexpr int kBytes = kOffRed + 4 * kTileRows * 16;
 };
 
 constexpr float kGenPhaseToRad = 9.587379924285257e-05f;  // 2*pi / 65536
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
   const uint32_t tmem_d = *tmem_slot;
 
   const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  const int dx = p.grad_in != nullptr ? 1 : 0;  // extra chain step: gradient of the network input
+  const int dx = (p.grad_in != nullptr || p.grad_coords != nullptr) ? 1 : 0;  // extra chain step: input gradient
   const int NX = (g.K0 + 255) / 256;            // its N, in 256-column halves
 
   if (warp == 0) {
@@ -184,16 +194,20 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = int(blockIdx.x) + t * int(gridDim.x);
         mbar_wait(dzo_ready, t & 1);
-        bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
-        bulk_commit();
-        bulk_wait_read0();
+        if (!p.lean) {
+          bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
+          bulk_commit();
+          bulk_wait_read0();
+        }
         mbar_arrive(dzo_free);
         for (int l = L; l >= 0; --l, ++n) {
           mbar_wait(&a_half[0], n & 1);
           mbar_wait(&a_half[1], n & 1);
-          bulk_s2g(p.stash_dz + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
-          bulk_commit();
-          bulk_wait_read0();
+          if (!p.lean) {
+            bulk_s2g(p.stash_dz + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
+            bulk_commit();
+            bulk_wait_read0();
+          }
           mbar_arrive(a_free);
         }
       }
@@ -218,6 +232,8 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       {
         const bool valid = (row0 + r) < p.rows;
         const float* gp = p.grad_out + (row0 + r) * C;
+        const float* yp = p.out_y ? p.out_y + (row0 + r) * C : nullptr;
+        const float inv_s = p.out_y ? 1.0f / p.out_tanh : 0.f;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int ch = 2 * s + cc;
@@ -226,6 +242,10 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
           for (int j = 0; j < 8; ++j) {
             const int col = ch * 8 + j;
             v[j] = (valid && col < C) ? gp[col] : 0.f;
+            if (yp != nullptr && valid && col < C) {  // d(s tanh z)/dz = s (1 - tanh^2) = s - y^2 / s
+              const float y = yp[col];
+              v[j] *= p.out_tanh - y * y * inv_s;
+            }
           }
           sts128(dzo_addr + sw128_chunk_off(r, ch),
                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -285,6 +305,10 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
               if (ACT == B200INR_ACT_SINE) {
                 d0 *= gen_cos_from_phase(pw[j] & 0xFFFFu);
                 d1 *= gen_cos_from_phase(pw[j] >> 16);
+              } else if (ACT == B200INR_ACT_TANH) {  // 1 - y^2 from the stashed bf16 outputs
+                const float y0 = bf16lo(pw[j]), y1 = bf16hi(pw[j]);
+                d0 *= fmaf(-y0, y0, 1.0f);
+                d1 *= fmaf(-y1, y1, 1.0f);
               } else {  // bf16 y > 0  <=>  sign bit clear and magnitude non-zero
                 d0 = ((pw[j] & 0x8000u) == 0u && (pw[j] & 0x7FFFu) != 0u) ? d0 : 0.f;
                 d1 = ((pw[j] & 0x80000000u) == 0u && (pw[j] & 0x7FFF0000u) != 0u) ? d1 : 0.f;
@@ -310,7 +334,59 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
       }
 
       // ---- input gradient: D = dTheta_0 (omega_0 W_0), fp32, straight to global memory (row r, 16 columns per block)
-      if (dx) {
+      if (dx && p.grad_coords != nullptr) {
+        // ---- adjoint of input_mapping on the fly: this thread owns row r and 16 of every 64 feature columns
+        mbar_wait(d_full, n & 1);
+        ++n;
+        tc_fence_after();
+        long long row = row0 + r;
+        if (row >= p.rows) row = p.rows - 1;
+        float x[4] = {0.f, 0.f, 0.f, 0.f}, xs[4];
+        if (p.coords != nullptr) {
+          for (int j = 0; j < g.d; ++j) x[j] = p.coords[row * g.d + j];
+        } else {
+          grid_coords(p.grid, row0 + r, x);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xs[j] = __fmul_rn(6.283185307179586f, x[j]);
+        const float4* bmat_g = reinterpret_cast<const float4*>(p.packed + p.pl.bmat);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int kb0 = g.K0 / 64;
+#pragma unroll 1
+        for (int kb = 0; kb < kb0; ++kb) {
+          uint32_t v[16];
+          tmem_ld16(tmem_d + t_lane + kb * 64 + s * 16, v);
+          tmem_ld_wait();
+          const int col0 = kb * 64 + s * 16;
+          const bool is_sin = col0 < g.m;
+          const int k0 = is_sin ? col0 : col0 - g.m;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 bk = __ldg(bmat_g + k0 + j);
+            float pr = xs[0] * bk.x;
+            pr = fmaf(xs[1], bk.y, pr);
+            pr = fmaf(xs[2], bk.z, pr);
+            pr = fmaf(xs[3], bk.w, pr);
+            float sn, cs;
+            __sincosf(pr, &sn, &cs);
+            const float dp = __uint_as_float(v[j]) * (is_sin ? cs : -sn);
+            acc[0] = fmaf(dp, bk.x, acc[0]);
+            acc[1] = fmaf(dp, bk.y, acc[1]);
+            acc[2] = fmaf(dp, bk.z, acc[2]);
+            acc[3] = fmaf(dp, bk.w, acc[3]);
+          }
+        }
+        tc_fence_before();
+        float4* red = reinterpret_cast<float4*>(smem + S::kOffRed);
+        red[s * kTileRows + r] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        named_bar_sync(1, kGenBwdEpiWarps * 32);
+        if (s == 0 && (row0 + r) < p.rows) {
+          const float4 a0 = red[r], a1 = red[kTileRows + r], a2 = red[2 * kTileRows + r], a3 = red[3 * kTileRows + r];
+          const float tot[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w)};
+          for (int j = 0; j < g.d; ++j) p.grad_coords[(row0 + r) * g.d + j] = 6.283185307179586f * tot[j];
+        }
+      } else if (dx) {
         mbar_wait(d_full, n & 1);
         ++n;
         tc_fence_after();
@@ -349,9 +425,25 @@ static int launch_gen_bwd_t(const GenBwdParams& p, int grid_x, cudaStream_t stre
 }
 
 int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int64_t rows, const float* grad_out,
-                   float* grad_in, int num_sms, cudaStream_t stream) {
+                   float* grad_in, int num_sms, cudaStream_t stream, float* grad_coords, const float* coords,
+                   const b200inr_grid* grid, const float* out_y) {
   GenBwdParams p{};
   p.grad_in = grad_in;
+  p.grad_coords = grad_coords;
+  p.coords = coords;
+  if (grid) {
+    p.grid.ndim = grid->ndim;
+    long long tot = 1;
+    for (int j = 0; j < 4; ++j) {
+      p.grid.shape[j] = (j < grid->ndim) ? grid->shape[j] : 1;
+      tot *= p.grid.shape[j];
+    }
+    p.grid.row_begin = grid->row_begin;
+    p.grid.total = tot;
+  }
+  p.out_y = (net->flags & B200INR_NET_TANH_OUT) ? out_y : nullptr;
+  p.out_tanh = net->scale_0;
+  p.lean = (net->flags & B200INR_NET_DGRAD_ONLY) ? 1 : 0;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.g = make_gen_dims(net);
   p.pl = make_gen_pack_layout(p.g);
@@ -367,6 +459,7 @@ int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int6
   p.layer_stride = sl.layer_stride;
   const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   const bool sine = net->activation == B200INR_ACT_SINE;
+  if (net->activation == B200INR_ACT_TANH) return launch_gen_bwd_t<256, B200INR_ACT_TANH>(p, grid_x, stream);
   if (p.g.H == 256)
     return sine ? launch_gen_bwd_t<256, B200INR_ACT_SINE>(p, grid_x, stream)
                 : launch_gen_bwd_t<256, B200INR_ACT_RELU>(p, grid_x, stream);

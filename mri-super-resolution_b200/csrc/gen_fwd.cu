@@ -44,6 +44,8 @@ struct GenFwdParams {
   uint8_t* stash_y;
   uint8_t* stash_ph;
   size_t layer_stride;
+  int lean;         // B200INR_NET_DGRAD_ONLY: no bulk stores of the input / output tiles a weight gradient would read
+  float out_tanh;   // B200INR_NET_TANH_OUT: out = out_tanh * tanh(out) (0: plain linear output)
 };
 
 template <int H>
@@ -172,12 +174,16 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
         for (int l = -1; l <= L; ++l, ++n) {  // l = -1: the network input tile
           mbar_wait(&a_half[0], n & 1);
           mbar_wait(&a_half[1], n & 1);
-          if (l < 0)
-            bulk_s2g(p.stash_ain + size_t(tile) * (size_t(KB0) * S::kABlock), a_smem, uint32_t(KB0) * S::kABlock);
-          else
-            bulk_s2g(p.stash_y + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
-          bulk_commit();
-          bulk_wait_read0();
+          // lean stash: the input tile is only a weight-gradient operand; sine derivatives come from the phases
+          const bool store = !p.lean || (l >= 0 && ACT != B200INR_ACT_SINE);
+          if (store) {
+            if (l < 0)
+              bulk_s2g(p.stash_ain + size_t(tile) * (size_t(KB0) * S::kABlock), a_smem, uint32_t(KB0) * S::kABlock);
+            else
+              bulk_s2g(p.stash_y + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
+            bulk_commit();
+            bulk_wait_read0();
+          }
           mbar_arrive(a_free);
         }
       }
@@ -296,6 +302,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
                   const uint32_t p1 = __float_as_uint(fmaf(t1, kGenPhaseScale, kGenPhaseMagic));
                   ph[j] = __byte_perm(p0, p1, 0x5410);
                 }
+              } else if (ACT == B200INR_ACT_TANH) {
+                yb[j] = pack_bf16x2(tanh_approx(t0), tanh_approx(t1));
               } else {
                 yb[j] = pack_bf16x2(fmaxf(t0, 0.f), fmaxf(t1, 0.f));
               }
@@ -340,6 +348,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
           for (int c = 0; c < kOutPad; ++c) {
             if (c < C) {
               float o = __uint_as_float(v[c]) + __ldg(bf + c);
+              if (p.out_tanh != 0.f) o = p.out_tanh * tanhf(o);
               if (p.clamp) o = fmaxf(o, p.clamp_min);
               sts32(a_addr + uint32_t(r * C + c) * 4, __float_as_uint(o));
             }
@@ -409,6 +418,8 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
     p.stash_ph = st + sl.ph;
     p.layer_stride = sl.layer_stride;
   }
+  p.lean = (net->flags & B200INR_NET_DGRAD_ONLY) ? 1 : 0;
+  p.out_tanh = (net->flags & B200INR_NET_TANH_OUT) ? net->scale_0 : 0.f;
   int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   {  // tuning aid (same switch as mlp_fwd.cu): cap the number of CTAs
     const char* env_cap = getenv("B200INR_FWD_MAX_CTAS");
@@ -416,6 +427,8 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
     if (cap > 0 && cap < grid_x) grid_x = cap;
   }
   const bool sine = net->activation == B200INR_ACT_SINE;
+  if (net->activation == B200INR_ACT_TANH)  // the perturbation network: 256-wide operands only
+    return launch_gen_fwd_t<256, B200INR_ACT_TANH>(p, stash != nullptr, grid_x, stream);
   if (p.g.H == 256)
     return sine ? launch_gen_fwd_t<256, B200INR_ACT_SINE>(p, stash != nullptr, grid_x, stream)
                 : launch_gen_fwd_t<256, B200INR_ACT_RELU>(p, stash != nullptr, grid_x, stream);

@@ -432,6 +432,35 @@ def torch_wire(in_features, hidden_features, hidden_layers, out_features, first_
     return _Net()
 
 
+def torch_perturb_loop(inr, pn, B, coords, mean_target, targets, number_of_epochs, pertubation_epochs, lr_inr=5e-5,
+                       lr_pn=1e-6, eps=1 / 128.0):
+    """The alternating INR / PerturbNet loop of INR/inrDWI.py:122-148 around CPU torch modules (torch_siren with
+    order='INRmodel', torch_pn): INR steps on input_mapping(coords, B) against mean_target while
+    ctr < number_of_epochs - pertubation_epochs or ctr is odd, otherwise one PerturbNet step per acquisition through
+    INR(input_mapping(PN(model_input, sample, eps), B)).  Returns (inr_losses, pn_losses) as python lists."""
+    import torch
+    inr_optim = torch.optim.Adam(lr=lr_inr, params=list(inr.parameters()))
+    pn_optim = torch.optim.Adam(lr=lr_pn, params=list(pn.parameters()))
+    model_input = torch_input_mapping(coords, B)
+    inr_losses, pn_losses = [], []
+    for ctr in range(number_of_epochs):
+        if ctr < number_of_epochs - pertubation_epochs or ctr % 2:
+            loss = ((inr(model_input) - mean_target) ** 2).mean()
+            inr_optim.zero_grad()
+            loss.backward()
+            inr_optim.step()
+            inr_losses.append(float(loss.detach()))
+        else:
+            for sample, gt in enumerate(targets):
+                feats = torch_input_mapping(pn(model_input, sample, eps), B)
+                loss = ((inr(feats) - gt) ** 2).mean()
+                pn_optim.zero_grad()
+                loss.backward()
+                pn_optim.step()
+                pn_losses.append(float(loss.detach()))
+    return inr_losses, pn_losses
+
+
 def torch_relu_mlp(in_dim, hidden_features, hidden_layers, out_features):
     """BASELINE config 4's network: Linear(in, H) + ReLU, `hidden_layers` x (Linear(H, H) + ReLU), Linear(H, C) with
     torch's default initialisation, fed with input_mapping(coords, B) (the reference only ever

@@ -1039,6 +1039,117 @@ def test_input_gradient_widths_vs_torch(dev, act_H_K0):
     assert _relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < BF16_RELERR
 
 
+def test_fused_perturb_step_vs_reference_golden(dev, golden_dir):
+    """The fused PerturbNet step (perturb.PerturbSession.perturb_step: PN as a tanh generic-family network on in-kernel
+    features, INR with the dgrad-only stash, input_mapping adjoint inside the backward kernel, no autograd) against the
+    unmodified reference's step (tools/make_golden.py: perturb_case): perturbation, loss, PN parameter gradients."""
+    g = np.load(os.path.join(golden_dir, "perturb_step.npz"))
+    B = torch.from_numpy(g["B"]).to(dev)
+    shape = (10, 10, 10)
+    torch.manual_seed(int(g["seed"]))
+    inr = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3).to(dev)
+    pn = b200inr.INRmodel.PN(in_features=256, hidden_features=128, dimension=3).to(dev)
+    sess = b200inr.PerturbSession(inr, pn, B, shape, lr_pn=1e-6, eps=1 / 128.)
+    pert = sess.perturbation(3)
+    np.testing.assert_allclose(pert.cpu().numpy(), g["perturbation"], atol=3e-5)  # bf16 features and hidden units
+    gt = torch.from_numpy(g["gt"]).to(dev)
+    loss = sess.perturb_step(gt, 3)
+    assert math.isclose(loss.item(), float(g["loss"]), rel_tol=2e-2)
+    assert np.abs(sess.pred.cpu().numpy() - g["out"]).max() < 5e-4
+    k0, hp, n_net, off = 256, 128, sess.n_net, sess.pn_off
+    gr = sess.pn_grads
+    g_w1 = gr[off[0]:off[0] + 256 * k0].view(256, k0)
+    g_b1 = gr[off[1]:off[1] + 256]
+    g_w2 = gr[off[2]:off[2] + 3 * 256].view(3, 256)
+    g_b2 = gr[off[3]:off[3] + 3]
+    ref_w1 = g["g_pn/perturb_linear.weight"]
+    assert _relerr(g_w1[:hp].cpu().numpy(), ref_w1[:, :k0]) < 3e-2
+    assert _relerr(gr[n_net:n_net + hp].cpu().numpy(), ref_w1[:, k0]) < 3e-2  # acquisition column: acq * db1
+    assert _relerr(g_b1[:hp].cpu().numpy(), g["g_pn/perturb_linear.bias"]) < 3e-2
+    assert _relerr(g_w2[:, :hp].cpu().numpy(), g["g_pn/perturb_linear2.weight"]) < 3e-2
+    assert _relerr(g_b2.cpu().numpy(), g["g_pn/perturb_linear2.bias"]) < 3e-2
+    assert float(g_w1[hp:].abs().max()) == 0.0 and float(g_w2[:, hp:].abs().max()) == 0.0  # padding stays untouched
+
+
+@pytest.mark.parametrize("tag,lr_pn", [("ref", 1e-6), ("fast", 1e-3)])
+def test_fused_perturb_fit_vs_reference_loop_golden(dev, golden_dir, tag, lr_pn):
+    """perturb_fit (the alternating loop of INR/inrDWI.py:122-148, fused) against the same loop run verbatim around the
+    unmodified reference classes: INR and PerturbNet loss trajectories, the trained PN's perturbation and the INR output.
+    'fast' repeats it with a PerturbNet learning rate at which six Adam steps visibly move the perturbation."""
+    g = np.load(os.path.join(golden_dir, "perturb_loop.npz"))
+    shape = tuple(int(v) for v in g["grid_shape"])
+    B = torch.from_numpy(g["B"]).to(dev)
+    torch.manual_seed(int(g["seed"]))
+    inr = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3).to(dev)
+    pn = b200inr.INRmodel.PN(in_features=256, hidden_features=128, dimension=4).to(dev)
+    coords = b200inr.get_mgrid(shape).to(dev)
+    model_input = b200inr.input_mapping(coords, B)
+    with torch.no_grad():
+        pert0 = pn.forward(model_input, 1, 1 / 128.).cpu().numpy()
+    targets = [torch.from_numpy(t).to(dev) for t in g["pixels"]]
+    inr_l, pn_l = b200inr.perturb_fit(inr, pn, B, shape, torch.from_numpy(g["mean_gt"]).to(dev), targets, 5, 4,
+                                      lr_inr=5e-5, lr_pn=lr_pn, eps=1 / 128.)
+    np.testing.assert_allclose(inr_l.cpu().numpy(), g[tag + "/inr_losses"], rtol=3e-2)
+    np.testing.assert_allclose(pn_l.cpu().numpy(), g[tag + "/pn_losses"], rtol=3e-2)
+    with torch.no_grad():  # the written-back modules reproduce the reference's trained state
+        pert = pn.forward(model_input, 1, 1 / 128.).cpu().numpy()
+        out = inr.forward(model_input).cpu().numpy()
+    ref_pert = g[tag + "/perturbation1"]
+    moved = np.abs(ref_pert - pert0).max()
+    assert np.abs(pert - ref_pert).max() <= max(0.15 * moved, 3e-5), (np.abs(pert - ref_pert).max(), moved)
+    if tag == "fast":
+        assert moved > 1e-4  # the test has teeth: training changed the perturbation by far more than the tolerance
+        np.testing.assert_allclose(pn.perturb_linear2.bias.detach().cpu().numpy(), g[tag + "/pn_b2"], atol=1.5e-3)
+    assert _relerr(out, g[tag + "/out"]) < 5e-2
+
+
+def test_fourier_mlp_coordinate_gradient_vs_torch(dev):
+    """b200inr_siren_backward_coords: dL/d(coordinates) of a sine network on in-kernel Fourier features (the adjoint of
+    input_mapping applied in tensor memory), with and without the dgrad-only stash, against CPU autograd through
+    torch_input_mapping + torch_siren; explicit coordinates and the grid form; ragged row count."""
+    shape = (9, 7, 5)
+    rows = int(np.prod(shape))
+    rs = np.random.RandomState(4)
+    B = (rs.normal(size=(64, 3)) * 0.5).astype(np.float32)
+    torch.manual_seed(21)
+    fm = b200inr.FourierMLP(3, 64, 256, 2, 5, B, activation="sine").to(dev)
+    ref = O.torch_siren(128, 256, 2, 5)
+    ref.load_state_dict({k: v.cpu() for k, v in fm.state_dict().items() if k != "B"})
+    xc = torch.from_numpy(O.get_mgrid(shape))
+    gout = torch.randn(rows, 5, generator=torch.Generator().manual_seed(2))
+    xr = xc.clone().requires_grad_(True)
+    ref(O.torch_input_mapping(xr, torch.from_numpy(B))).backward(gout)
+    eng = fm._sync_params()
+    lib = L.load()
+    for lean in (False, True):
+        d0 = fm._desc
+        net = L.make_net(d0.in_features, d0.hidden_features, d0.hidden_layers, d0.out_features, d0.first_omega_0,
+                         d0.hidden_omega_0, activation=L.ACT_SINE, input_mode=L.IN_FOURIER, mapping_size=64,
+                         flags=L.NET_DGRAD_ONLY if lean else 0)
+        for use_grid in (False, True):
+            stash = b200inr.inr._aligned_bytes(L.stash_bytes(net, rows), dev, zero=False)
+            out = torch.empty(rows, 5, device=dev)
+            x = xc.to(dev)
+            grid = L.make_grid(shape)
+            gref = ctypes.byref(grid) if use_grid else None
+            L.check(lib.b200inr_siren_forward(ctypes.byref(net), _ptr(eng["packed"]), None if use_grid else _ptr(x), gref,
+                                              rows, _ptr(out), 0, 0.0, _ptr(stash), _stream()), "fwd")
+            gx = torch.zeros(rows, 3, device=dev)
+            gp = None if lean else torch.zeros_like(eng["flat"])
+            L.check(lib.b200inr_siren_backward_coords(ctypes.byref(net), _ptr(eng["packed"]), _ptr(stash),
+                                                      None if use_grid else _ptr(x), gref, rows, _ptr(gout.to(dev)),
+                                                      _ptr(gp), _ptr(gx), _stream()), "bwd_coords")
+            assert _relerr(gx.cpu().numpy(), xr.grad.numpy()) < 3e-2, (lean, use_grid)
+            if gp is not None:
+                o = eng["offsets"]
+                gw0 = gp[o[0]:o[0] + 256 * 128].view(256, 128).cpu().numpy()
+                assert _relerr(gw0, ref.net[0].linear.weight.grad.numpy()) < 3e-2
+    # a lean network has no weight gradients to give
+    bad = lib.b200inr_siren_backward(ctypes.byref(net), _ptr(eng["packed"]), _ptr(stash), _ptr(x), None, rows,
+                                     _ptr(gout.to(dev)), _ptr(torch.zeros_like(eng["flat"])), _stream())
+    assert bad != 0
+
+
 # ------------------------------------------------------------------------------------------------ ADC map
 def test_calculate_adc_vs_reference_golden_and_oracle(dev, golden_dir):
     """calculate_ADC (INR/SRDWI.py:118-130) as one kernel: the reference's own output on the golden slice (NumPy in,

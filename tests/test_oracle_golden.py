@@ -292,6 +292,28 @@ def test_wire_on_fourier_features_restatement_matches_reference(golden_dir):
     np.testing.assert_allclose(losses, g["losses"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("tag,lr_pn", [("ref", 1e-6), ("fast", 1e-3)])
+def test_alternating_perturb_loop_restatement_matches_reference(golden_dir, tag, lr_pn):
+    """INR/inrDWI.py:122-148 run verbatim around the unmodified classes (tools/make_golden.py: perturb_loop_case) vs the
+    oracle's torch_perturb_loop: both loss trajectories, PN's trained acquisition column / output bias and the
+    perturbation of acquisition 1 after training."""
+    g = _load(golden_dir, "perturb_loop.npz")
+    shape = tuple(int(v) for v in g["grid_shape"])
+    B = torch.from_numpy(g["B"])
+    torch.manual_seed(int(g["seed"]))
+    inr = O.torch_siren(256, 512, 3, 1, order="INRmodel")
+    pn = O.torch_pn(256, 128, 4)
+    coords = torch.from_numpy(O.get_mgrid(shape))
+    targets = [torch.from_numpy(t) for t in g["pixels"]]
+    inr_l, pn_l = O.torch_perturb_loop(inr, pn, B, coords, torch.from_numpy(g["mean_gt"]), targets, 5, 4, lr_pn=lr_pn)
+    np.testing.assert_allclose(inr_l, g[tag + "/inr_losses"], rtol=1e-4)
+    np.testing.assert_allclose(pn_l, g[tag + "/pn_losses"], rtol=1e-4)
+    np.testing.assert_allclose(pn.perturb_linear2.bias.detach().numpy(), g[tag + "/pn_b2"], atol=2e-6)
+    np.testing.assert_allclose(pn.perturb_linear.weight.detach().numpy()[:, -1], g[tag + "/pn_wlast"], atol=2e-4)
+    pert = pn(O.torch_input_mapping(coords, B), 1, 1 / 128.).detach().numpy()
+    assert np.abs(pert - g[tag + "/perturbation1"]).max() <= 2e-2 * np.abs(g[tag + "/perturbation1"]).max()
+
+
 def test_calculate_adc_matches_reference(golden_dir):
     """Closed-form per-voxel fit == the reference's np.polyfit double loop (tools/make_golden.py: adc_case), clamps and
     the empty voxel included."""

@@ -341,6 +341,74 @@ def wire_ff_case():
           pfeats.grad.abs().max().item(), "out range", out.min().item(), out.max().item())
 
 
+def perturb_loop_case():
+    """The alternating loop of INR/inrDWI.py:122-148 run VERBATIM (same statements, same order) around the unmodified
+    INRmodel.Siren / PN / input_mapping at the script's sizes (m = 128, Siren(256, 512, 3, 1), PN(256, 128, 4), eps =
+    1/128, lr 5e-5 / 1e-6) on a small 4-D grid with 3 acquisitions: number_of_epochs = 5, pertubation_epochs = 4, i.e.
+    INR, INR, PN x 3, INR, PN x 3.  A second run with perturb lr 1e-3 makes PN's training visible in the numbers (Adam
+    moves every parameter by ~lr per step; at 1e-6 six steps change nothing measurable)."""
+    rs = np.random.RandomState(33)
+    shape = (6, 5, 4, 4)
+    B = torch.from_numpy(rs.normal(size=(128, 4)) * 0.5).float()
+    coords = INRmodel.get_mgrid(shape)
+    n = coords.shape[0]
+    mean_gt = torch.from_numpy(rs.uniform(size=(n, 1))).float()
+    pixels = [torch.from_numpy(np.clip(mean_gt.numpy() + 0.1 * rs.normal(size=(n, 1)), 0, 1)).float() for _ in range(3)]
+    d = {"grid_shape": np.array(shape), "B": B.numpy(), "mean_gt": mean_gt.numpy(),
+         "pixels": np.stack([p.numpy() for p in pixels]), "seed": np.array(51)}
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for tag, lr_pn in (("ref", 1e-6), ("fast", 1e-3)):
+            torch.manual_seed(51)
+            INR = INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3)
+            PerturbNet = INRmodel.PN(in_features=256, hidden_features=128, dimension=4)
+            inr_optim = torch.optim.Adam(lr=5e-5, params=list(INR.parameters()))
+            perturb_optim = torch.optim.Adam(lr=lr_pn, params=list(PerturbNet.parameters()))
+            model_input = INRmodel.input_mapping(coords, B)
+            number_of_epochs, pertubation_epochs = 5, 4
+            inr_losses, pn_losses = [], []
+            for ctr in range(number_of_epochs):
+                if ctr < number_of_epochs - pertubation_epochs:
+                    model_output = INR.forward(model_input)
+                    loss = ((model_output - mean_gt) ** 2).mean()
+                    inr_optim.zero_grad()
+                    loss.backward()
+                    inr_optim.step()
+                    inr_losses.append(loss.item())
+                else:
+                    if ctr % 2:
+                        model_output = INR.forward(model_input)
+                        loss = ((model_output - mean_gt) ** 2).mean()
+                        inr_optim.zero_grad()
+                        loss.backward()
+                        inr_optim.step()
+                        inr_losses.append(loss.item())
+                    else:
+                        for sample in range(len(pixels)):
+                            ground_truth = pixels[sample]
+                            perturbed_input = PerturbNet.forward(model_input, sample, 1 / 128.)
+                            perturbed_input = INRmodel.input_mapping(perturbed_input, B)
+                            model_output = INR.forward(perturbed_input)
+                            loss = ((model_output - ground_truth) ** 2).mean()
+                            perturb_optim.zero_grad()
+                            loss.backward()
+                            perturb_optim.step()
+                            pn_losses.append(loss.item())
+            d[tag + "/inr_losses"] = np.array(inr_losses)
+            d[tag + "/pn_losses"] = np.array(pn_losses)
+            d[tag + "/perturbation1"] = PerturbNet.forward(model_input, 1, 1 / 128.).detach().numpy()
+            d[tag + "/out"] = INR.forward(model_input).detach().numpy()
+            for k, p in PerturbNet.named_parameters():
+                d[tag + "/cs_pn/" + k] = checksum(p)
+            d[tag + "/pn_b2"] = PerturbNet.perturb_linear2.bias.detach().numpy().copy()
+            d[tag + "/pn_wlast"] = PerturbNet.perturb_linear.weight.detach().numpy()[:, -1].copy()
+            print("perturb_loop", tag, inr_losses, pn_losses)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(OUT, "perturb_loop.npz"), **d)
+
+
 def adc_case():
     """calculate_ADC of the unmodified reference (INR/SRDWI.py:118-130) on a small synthetic slice: mono-exponential
     decays with noise, a few voxels driven into both clamps and to zero signal."""
@@ -480,6 +548,8 @@ if __name__ == "__main__":
         perturb_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "wire_ff":
         wire_ff_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "perturb_loop":
+        perturb_loop_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "trained":
         trained_case()
     else:
@@ -487,6 +557,7 @@ if __name__ == "__main__":
         trained_case()
         perturb_case()
         wire_ff_case()
+        perturb_loop_case()
         adc_case()
         combinations_case()
         erd_case()
