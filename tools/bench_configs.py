@@ -90,6 +90,30 @@ def perturb_line(name, shape, steps):
             "note": "module loop through torch autograd; INR weight gradients are computed too (as in the reference)"}
 
 
+def perturb_fused_line(name, shape, steps):
+    """The same step through the fused loop (perturb.PerturbSession.perturb_step): PN on in-kernel features as a tanh
+    generic-family network, the frozen INR with the dgrad-only stash, dL/d(perturbation) straight out of the backward
+    kernel, no autograd.  Algorithmic work: INR forward + activation-gradient chain incl. the input gradient (the
+    reference's INR weight gradients are never used in this phase) + PN forward / backward."""
+    dev = torch.device("cuda:0")
+    rows = int(np.prod(shape))
+    B = torch.from_numpy(np.random.RandomState(1).normal(size=(128, 3)) * 0.5).float().to(dev)
+    inr = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=512, hidden_layers=3).to(dev)
+    pn = b200inr.INRmodel.PN(in_features=256, hidden_features=128, dimension=3).to(dev)
+    sess = b200inr.PerturbSession(inr, pn, B, shape, lr_pn=1e-6)
+    gt = torch.rand(rows, 1, device=dev)
+    ms = timed(lambda: sess.perturb_step(gt, 3), steps)
+    mac_inr = 256 * 512 + 3 * 512 * 512 + 512
+    mac_pn = 257 * 128 + 128 * 3
+    flop_per_row = 2 * (2 * mac_inr) + 6 * mac_pn
+    tf = flop_per_row * rows / (ms * 1e-3) / 1e12
+    # stage split: events around the calls of one step
+    return {"config": name, "metric": "perturbnet_coord_samples_per_s", "value": rows / (ms * 1e-3), "ms_per_step": ms,
+            "rows": rows, "tflops_algorithmic": tf, "frac_of_burst_peak": tf / PEAK["bf16_tflops"],
+            "kernel_launches_per_step": sess.kernel_launches_per_perturb_step, "final_loss": float(sess.loss_acc.item()),
+            "note": "fused loop, no autograd, INR weight gradients skipped (unused by the reference's perturb_optim)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -125,6 +149,17 @@ def main():
     torch.cuda.empty_cache()
     lines.append(perturb_line("PerturbNet step (INR/inrDWI.py:141-147), Siren(256,512,3,1) + PN(256,128,3), 128x128x64",
                               hr_shape, max(3, a.steps // 2)))
+    torch.cuda.empty_cache()
+    lines.append(perturb_fused_line("PerturbNet step, fused loop (perturb_fit), same sizes", hr_shape, max(3, a.steps // 2)))
+    torch.cuda.empty_cache()
+    # WIRE the way the notebook feeds it (wiretest.ipynb cell 7): 512 Fourier features of a 4-D grid -> 128c x (1 + 3) -> 1
+    Bw = np.random.RandomState(2).normal(size=(256, 4)) * 0.5
+    mw = b200inr.Wire(4, 128, 3, 1, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2, B=Bw).to(dev)
+    wshape = (64, 64, 64, 4)
+    wt = torch.rand(int(np.prod(wshape)), 1, device=dev)
+    flop_w = 6 * (512 * 256 + 3 * 256 * 512 + 256) - 2 * 512 * 256
+    lines.append(fit_line("WIRE on 512 Fourier features (wiretest.ipynb cell 7), 64x64x64x4 grid", mw, wt, wshape, None,
+                          5e-5, flop_w, a.steps))
     for ln in lines:
         print(json.dumps(ln), flush=True)
 
