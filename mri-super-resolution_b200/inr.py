@@ -275,9 +275,9 @@ class SineLayer(nn.Module):
         if k <= 4:    # raw coordinates: the 256-wide SIREN kernels (any width 8..256), staged stash keeps sin outputs
             desc = _lib.make_net(k, h, 0, 1, self.omega_0, self.omega_0, flags=_lib.NET_STAGED_BWD)
             width, y_off = 256, 0
-        else:         # explicit feature rows: the generic family (K a multiple of 64 <= H, H in {256, 512})
-            desc = _lib.make_net(k, h, 0, 1, self.omega_0, self.omega_0, input_mode=_lib.IN_FEATURES)
-            width = h
+        else:         # explicit feature rows: the generic family (K a multiple of 64; other widths run zero padded)
+            width = _generic_width(h, k)
+            desc = _lib.make_net(k, width, 0, 1, self.omega_0, self.omega_0, input_mode=_lib.IN_FEATURES)
         rows = input.shape[0]
         if rows == 0:
             return torch.empty((0, h), dtype=torch.float32, device=dev)
@@ -288,7 +288,8 @@ class SineLayer(nn.Module):
             lib = _lib.load()
             off = _lib.param_offsets(desc)  # raises for unsupported widths
             flat = torch.zeros(_lib.param_count(desc), dtype=torch.float32, device=dev)
-            flat[off[0]:off[0] + h * k].copy_(lin.weight.detach().reshape(-1))
+            hw = width if k > 4 else h  # rows of the (padded) weight segment
+            flat[off[0]:off[0] + hw * k].view(hw, k)[:h].copy_(lin.weight.detach())
             if lin.bias is not None:
                 flat[off[1]:off[1] + h].copy_(lin.bias.detach())
             packed = _aligned_bytes(_lib.packed_bytes(desc), dev)
@@ -331,6 +332,29 @@ class SineLayer(nn.Module):
         return self._fused(input), pre
 
 
+def _generic_width(hidden_features, k0):
+    """Operand width the generic-family kernels run a (hidden_features, input width k0) network at: 256 or 512."""
+    need = max(int(hidden_features), int(k0))
+    if need <= 256:
+        return 256
+    if need <= 512:
+        return 512
+    raise RuntimeError("b200inr: hidden / input widths above 512 are not supported")
+
+
+def _mlp_padded_shape(hp, hidden_layers, idx, p):
+    """Flat-segment shape of canonical parameter idx (W0 b0 ... WL bL Wf bf [B]) of an MLP whose hidden width is zero
+    padded to hp (None: not padded)."""
+    if hp is None or idx >= 2 * (hidden_layers + 2):
+        return None
+    layer, is_w = idx // 2, idx % 2 == 0
+    if layer == 0:
+        return (hp, p.shape[1]) if is_w else (hp,)
+    if layer <= hidden_layers:
+        return (hp, hp) if is_w else (hp,)
+    return (p.shape[0], hp) if is_w else None
+
+
 class _SirenFunction(torch.autograd.Function):
     """Siren.forward as one fused kernel, loss.backward() as the fused dgrad + wgrad kernels."""
 
@@ -360,11 +384,10 @@ class _SirenFunction(torch.autograd.Function):
         flat_grad = module._backward_rows(ctx.stash, ctx.coords, None, ctx.coords.shape[0], grad_out, grad_in=grad_in)
         ctx.stash = None
         grads = []
-        for o, p in zip(module._offsets_canonical(), module._canonical()):
-            if p.is_complex():  # torch's convention for complex parameters: grad = dL/dRe + 1j dL/dIm
-                grads.append(torch.view_as_complex(flat_grad[o:o + 2 * p.numel()].view(*p.shape, 2)))
-            else:
-                grads.append(flat_grad[o:o + p.numel()].view_as(p))
+        for i, (o, p) in enumerate(zip(module._offsets_canonical(), module._canonical())):
+            v = module._param_view(flat_grad, o, p, i)
+            # torch's convention for complex parameters: grad = dL/dRe + 1j dL/dIm
+            grads.append(torch.view_as_complex(v) if p.is_complex() else v)
         return (grad_in, None, *grads)
 
 
@@ -399,6 +422,22 @@ class _FusedMLP(nn.Module):
     def _offsets_canonical(self):
         return self._engine_state()["offsets"]
 
+    def _padded_shape(self, idx, p):
+        """Shape of the flat-vector segment that holds canonical parameter `idx` when the engine runs a zero-padded
+        (wider) network than the module describes; None: the segment has the parameter's own shape."""
+        return None
+
+    def _param_view(self, flat, o, p, idx):
+        """The (strided) view of `flat` where parameter p lives: real parameters in their own shape, complex ones as
+        interleaved (re, im) pairs [..., 2]; a padded engine keeps the parameter in the leading corner of its segment."""
+        shp = tuple(p.shape) + ((2,) if p.is_complex() else ())
+        pad = self._padded_shape(idx, p)
+        if pad is None:
+            n = int(np.prod(shp)) if shp else 1
+            return flat[o:o + n].view(shp)
+        n = int(np.prod(pad))
+        return flat[o:o + n].view(pad)[tuple(slice(0, d) for d in shp)]
+
     def _engine_state(self):
         dev = self._canonical()[0].device
         if dev.type != "cuda":
@@ -425,9 +464,9 @@ class _FusedMLP(nn.Module):
         if key != eng["key"]:
             flat = eng["flat"]
             with torch.no_grad():
-                for o, p in zip(eng["offsets"], ps):
+                for i, (o, p) in enumerate(zip(eng["offsets"], ps)):
                     src = torch.view_as_real(p) if p.is_complex() else p  # complex64 -> interleaved (re, im)
-                    flat[o:o + src.numel()].copy_(src.reshape(-1))
+                    self._param_view(flat, o, p, i).copy_(src)
             self._pack(eng)
             eng["key"] = key
         return eng
@@ -441,11 +480,9 @@ class _FusedMLP(nn.Module):
         """Copy the flat fp32 master (updated by fit) back into the nn.Parameters."""
         ps = self._canonical()
         with torch.no_grad():
-            for o, p in zip(eng["offsets"], ps):
-                if p.is_complex():
-                    p.copy_(torch.view_as_complex(eng["flat"][o:o + 2 * p.numel()].view(*p.shape, 2)))
-                else:
-                    p.copy_(eng["flat"][o:o + p.numel()].view_as(p))
+            for i, (o, p) in enumerate(zip(eng["offsets"], ps)):
+                v = self._param_view(eng["flat"], o, p, i)
+                p.copy_(torch.view_as_complex(v.contiguous()) if p.is_complex() else v)
         eng["key"] = tuple((p.data_ptr(), p._version) for p in ps + self._frozen())
 
     # ---------------------------------------------------------------- kernel calls
@@ -596,9 +633,18 @@ class Siren(_FusedMLP):
         self.first_omega_0 = float(first_omega_0)
         self.hidden_omega_0 = float(net[1].omega_0) if hidden_layers > 0 else float(hidden_omega_0)
         # in_features <= 4: raw coordinates (first layer on CUDA cores, grid-mode fit/query available);
-        # wider inputs are explicit feature rows, e.g. pre-computed Fourier features (INR/superresDWI.py:108-122)
+        # wider inputs are explicit feature rows, e.g. pre-computed Fourier features (INR/superresDWI.py:108-122).
+        # The generic family's kernels are built for 256- and 512-wide operands: other widths (the reference's
+        # Siren(in_features=256, hidden_features=128, ...) of SR3D.ipynb cell 4 / INR/automate_INR.py:23-27, or an input
+        # wider than the hidden layers) run zero padded -- sin(0) = 0 units with zero outgoing weights change nothing
+        # and receive zero gradients --, while parameters, gradients and state dicts keep the module's own shapes.
         mode = _lib.IN_COORDS if self.in_features <= 4 else _lib.IN_FEATURES
-        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, self.first_omega_0,
+        self._hp = None
+        h_eng = self.hidden_features
+        if mode == _lib.IN_FEATURES:
+            h_eng = _generic_width(self.hidden_features, self.in_features)
+            self._hp = h_eng if h_eng != self.hidden_features else None
+        self._init_engine(_lib.make_net(in_features, h_eng, hidden_layers, out_features, self.first_omega_0,
                                         self.hidden_omega_0, input_mode=mode),
                           self.in_features if mode == _lib.IN_COORDS else None)
 
@@ -609,6 +655,9 @@ class Siren(_FusedMLP):
             ps += [self.net[i].linear.weight, self.net[i].linear.bias]
         ps += [self.final_linear.weight, self.final_linear.bias]
         return ps
+
+    def _padded_shape(self, idx, p):
+        return _mlp_padded_shape(self._hp, self.hidden_layers, idx, p)
 
 
 class SirenERD(_FusedMLP):
@@ -729,7 +778,9 @@ class FourierMLP(_FusedMLP):
             self.net = nn.Sequential(*mods)
             self._linears = [m for m in mods if isinstance(m, nn.Linear)]
             act = _lib.ACT_RELU
-        self._init_engine(_lib.make_net(in_features, hidden_features, hidden_layers, out_features, first_omega_0,
+        h_eng = _generic_width(self.hidden_features, k0)  # other widths run zero padded (see Siren)
+        self._hp = h_eng if h_eng != self.hidden_features else None
+        self._init_engine(_lib.make_net(in_features, h_eng, hidden_layers, out_features, first_omega_0,
                                         hidden_omega_0, activation=act, input_mode=_lib.IN_FOURIER,
                                         mapping_size=mapping_size), self.in_features)
 
@@ -738,6 +789,9 @@ class FourierMLP(_FusedMLP):
         for lin in self._linears:
             ps += [lin.weight, lin.bias]
         return ps
+
+    def _padded_shape(self, idx, p):
+        return _mlp_padded_shape(self._hp, self.hidden_layers, idx, p)
 
     def _frozen(self):
         return [self.B]

@@ -442,6 +442,73 @@ def test_reference_style_fourier_siren_vs_golden(dev, golden_dir):
     assert _relerr(a, b) < 1e-2
 
 
+@pytest.mark.parametrize("k0,H,Lh,C", [(256, 128, 3, 1), (128, 64, 1, 3), (512, 256, 2, 2), (320, 384, 1, 4)])
+def test_explicit_feature_siren_padded_widths_vs_oracle(dev, k0, H, Lh, C):
+    """Explicit-feature SIRENs whose widths are not the kernels' 256 / 512 -- the reference's own
+    Siren(in_features=256, hidden_features=128, hidden_layers=3, out_features=1) (SR3D.ipynb cell 4,
+    INR/automate_INR.py:23-27) and inputs wider than the hidden layers -- run zero padded: same seeded weights,
+    forward, every parameter gradient, dL/d(features), a 4-step torch.optim.Adam loop, state-dict shapes unchanged."""
+    torch.manual_seed(5 + H)
+    m = b200inr.INRmodel.Siren(in_features=k0, out_features=C, hidden_features=H, hidden_layers=Lh)
+    torch.manual_seed(5 + H)
+    ref = O.torch_siren(k0, H, Lh, C, order="INRmodel")
+    for (k1, p1), (k2, p2) in zip(sorted(m.named_parameters()), sorted(ref.named_parameters())):
+        assert k1 == k2 and torch.equal(p1, p2)
+    rows = 333
+    x = (torch.rand(rows, k0, generator=torch.Generator().manual_seed(k0)) * 2 - 1)
+    gt = torch.rand(rows, C, generator=torch.Generator().manual_seed(k0 + 1))
+    xr = x.clone().requires_grad_(True)
+    out_ref = ref(xr)
+    ((out_ref - gt) ** 2).mean().backward()
+    m = m.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    out = m(xg)
+    assert out.shape == (rows, C)
+    assert _relerr(out.detach().cpu().numpy(), out_ref.detach().numpy()) < BF16_RELERR
+    ((out - gt.to(dev)) ** 2).mean().backward()
+    assert _relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < 3e-2
+    gref = dict(ref.named_parameters())
+    for k, p in m.named_parameters():
+        assert p.grad.shape == p.shape
+        assert _relerr(p.grad.cpu().numpy(), gref[k].grad.numpy()) < 3e-2, k
+    opt = torch.optim.Adam(lr=1e-4, params=list(m.parameters()))
+    ref_losses = O.torch_fit(ref, x, gt, 4, 1e-4)
+    losses = []
+    for _ in range(4):
+        ls = ((m(x.to(dev)) - gt.to(dev)) ** 2).mean()
+        opt.zero_grad()
+        ls.backward()
+        opt.step()
+        losses.append(ls.item())
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+    # a stand-alone first layer of that width
+    if Lh == 3:
+        with torch.no_grad():
+            a = m.net[0](x.to(dev)).cpu().numpy()
+            b = ref.net[0](x).numpy()
+        assert a.shape == (rows, H) and _relerr(a, b) < BF16_RELERR
+
+
+def test_fourier_mlp_narrow_fit_vs_oracle(dev):
+    """FourierMLP with 128 hidden units (padded engine): the fused fit (flat Adam over the padded vector) follows the
+    oracle loop and writes parameters of the module's own shapes back."""
+    shape, C = (12, 10, 6), 2
+    B = (np.random.RandomState(8).normal(size=(64, 3)) * 0.5).astype(np.float32)
+    torch.manual_seed(3)
+    m = b200inr.FourierMLP(3, 64, 128, 2, C, B, activation="sine")
+    torch.manual_seed(3)
+    ref = O.torch_siren(128, 128, 2, C)
+    x = torch.from_numpy(O.get_mgrid(shape))
+    gt = torch.rand(x.shape[0], C, generator=torch.Generator().manual_seed(4))
+    ref_losses = O.torch_fit(ref, O.torch_input_mapping(x, torch.from_numpy(B)), gt, 6, 1e-4)
+    m = m.to(dev)
+    losses = m.fit(gt.to(dev), shape, steps=6, lr=1e-4).cpu().numpy()
+    np.testing.assert_allclose(losses, ref_losses, rtol=3e-2)
+    for (k1, p1), (k2, p2) in zip(sorted(m.named_parameters()), sorted(ref.named_parameters())):
+        assert p1.shape == p2.shape
+        assert _relerr(p1.detach().cpu().numpy(), p2.detach().numpy()) < 2e-2, k1
+
+
 @pytest.mark.parametrize("act,msz,H,Lh,C", [("relu", 256, 512, 3, 31), ("relu", 128, 256, 2, 5),
                                             ("sine", 128, 256, 2, 1), ("sine", 64, 512, 1, 3)])
 def test_fourier_mlp_forward_backward_vs_oracle(dev, act, msz, H, Lh, C):
