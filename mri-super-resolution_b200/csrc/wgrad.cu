@@ -42,7 +42,8 @@ enum WgOut : int {
 
 struct WgItem {
   int out;                 // WgOut
-  int cta_begin, cta_count;
+  int cta_begin, cta_count;  // blocks cta_begin + k * cta_stride, k < cta_count, work on this item (row split k)
+  int cta_stride;            // the items of a group are interleaved: blocks that stream the same tiles are neighbours
   const uint8_t* a_src;    // M operand tiles: a_tile_bytes per tile, 4 blocks used starting at block a_blk0
   const uint8_t* b_src;    // N operand tiles: b_tile_bytes per tile, nb blocks used starting at block b_blk0
   uint32_t a_tile_bytes, a_blk0, b_tile_bytes, b_blk0;
@@ -90,10 +91,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
 
   // ---- which item, which tile range
   int it = 0;
-  for (int i = 0; i < p.num_items; ++i)
-    if (int(blockIdx.x) >= p.items[i].cta_begin && int(blockIdx.x) < p.items[i].cta_begin + p.items[i].cta_count) it = i;
+  for (int i = 0; i < p.num_items; ++i) {
+    const int rel = int(blockIdx.x) - p.items[i].cta_begin;
+    if (rel >= 0 && rel % p.items[i].cta_stride == 0 && rel / p.items[i].cta_stride < p.items[i].cta_count) it = i;
+  }
   const WgItem item = p.items[it];
-  const int split = int(blockIdx.x) - item.cta_begin;
+  const int split = (int(blockIdx.x) - item.cta_begin) / item.cta_stride;
   const int tile_begin = int((long long)p.num_tiles * split / item.cta_count);
   const int tile_end = int((long long)p.num_tiles * (split + 1) / item.cta_count);
   const int num_stages = (tile_end - tile_begin) * kWgStagesPerTile;
@@ -242,29 +245,54 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
 }
 
 // Distribute CTAs over the items in proportion to `weight` (bytes streamed per tile) and launch.
-static int launch_items(WgParams& p, const double* weight, int num_sms, cudaStream_t stream) {
+// group[i]: items that stream the SAME stash tiles (the blocks of one layer's dW) carry the same group id; they get the
+// same CTA count, hence the same row splits, and their blocks are interleaved (neighbouring blocks stream the same
+// tiles): cfg4 reads 13.8 GB from DRAM instead of 15.8 GB for 9.8 GB of unique tiles.  Measured and NOT kept: holding a
+// group's producers within a few tiles of each other through global progress counters brings DRAM reads down to the
+// unique 9.8 GB, but every check costs the producer ~4 us under load (the L2 fabric is the busy resource: 18.5 GB
+// cross it either way) and the kernel got slower (2.6 -> 3.7-7.4 ms); sharing tiles inside a cluster (multicast or a
+// cta_group::2 MMA that splits B) is the remaining way to cut the fabric traffic itself.
+static int launch_items(WgParams& p, const double* weight, const int* group, int num_sms, cudaStream_t stream) {
   double total = 0.0;
   for (int i = 0; i < p.num_items; ++i) total += weight[i];
+  int count[kWgMaxItems];
   int cta = 0;
   for (int i = 0; i < p.num_items; ++i) {
     int n = int(num_sms * weight[i] / total);
-    if (n < 1) n = 1;
-    p.items[i].cta_begin = cta;
-    p.items[i].cta_count = n;
-    cta += n;
+    count[i] = n < 1 ? 1 : n;
+    cta += count[i];
   }
-  // hand the CTAs lost to rounding to the heaviest items, one each
-  for (int i = 0; cta < num_sms && i < p.num_items; ++i) {
-    if (weight[i] >= 100.0) {
-      for (int j = i + 1; j < p.num_items; ++j) p.items[j].cta_begin += 1;
-      p.items[i].cta_count += 1;
-      cta += 1;
+  // leftovers: one more CTA for every member of a group, heaviest groups first, while whole groups still fit
+  for (bool progress = true; progress && cta < num_sms;) {
+    progress = false;
+    for (int i = 0; i < p.num_items && cta < num_sms; ++i) {
+      if (i > 0 && group[i] == group[i - 1]) continue;  // group leader only
+      int members = 0;
+      for (int j = i; j < p.num_items && group[j] == group[i]; ++j) ++members;
+      if (weight[i] < 100.0 || cta + members > num_sms) continue;
+      for (int j = i; j < i + members; ++j) count[j] += 1;
+      cta += members;
+      progress = true;
     }
+  }
+  if (cta > num_sms) {  // more items than SMs can take one CTA each: the grid still launches (CTAs queue)
+  }
+  int begin = 0;
+  for (int i = 0; i < p.num_items;) {  // one group at a time: its members' blocks interleaved
+    int members = 1;
+    while (i + members < p.num_items && group[i + members] == group[i]) ++members;
+    for (int j = 0; j < members; ++j) {
+      p.items[i + j].cta_begin = begin + j;
+      p.items[i + j].cta_stride = members;
+      p.items[i + j].cta_count = count[i];
+    }
+    begin += members * count[i];
+    i += members;
   }
   const int smem = WgSmem::kBytes + 1024;
   if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
-  wgrad_kernel<<<cta, kWgThreads, smem, stream>>>(p);
+  wgrad_kernel<<<begin, kWgThreads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
@@ -285,9 +313,11 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
   p.d = d;
   p.C = C;
   double weight[kWgMaxItems];
+  int group[kWgMaxItems];
   int ni = 0;
   const uint32_t tile_h = uint32_t(sl.tile_bytes), tile_s = kTileRows * 128;
   for (int l = 1; l <= L; ++l) {
+    group[ni] = ni;
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutBlock;
@@ -320,9 +350,11 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     w.sum_b = 1;
     w.gb_count = C;
     w.scale = 1.0f;
+    group[ni] = ni;
     weight[ni++] = 80.0;
   }
   {
+    group[ni] = ni;
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutCoord;
@@ -339,7 +371,7 @@ int launch_siren_wgrad(const b200inr_net* net, void* stash, const float* coords,
     weight[ni++] = 80.0;
   }
   p.num_items = ni;
-  return launch_items(p, weight, num_sms, stream);
+  return launch_items(p, weight, group, num_sms, stream);
 }
 
 int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* grad_params, int num_sms,
@@ -355,6 +387,7 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
   p.d = 0;
   p.C = g.C;
   double weight[kWgMaxItems];
+  int group[kWgMaxItems];
   int ni = 0;
   const uint32_t tile_s = kTileRows * 128;
   for (int l = 0; l <= g.L; ++l) {
@@ -362,6 +395,7 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
     for (int mh = 0; mh < g.H / 256; ++mh) {
       for (int b0 = 0; b0 < K / 64; b0 += 4) {
         if (ni >= kWgMaxItems - 2) return B200INR_ERR_BAD_SHAPE;
+        group[ni] = l;
         WgItem& w = p.items[ni];
         w = WgItem{};
         w.out = kWgOutBlock;
@@ -379,11 +413,14 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
         w.gb = (b0 == 0) ? grad_params + off[2 * l + 1] + 256 * mh : nullptr;
         w.gb_count = 256;
         w.scale = (l == 0) ? g.omega0 : g.omegah;
-        weight[ni++] = 64.0 + 16.0 * w.nb;
+        // (one weight per layer, so that the whole group gets equal CTA counts: a partial last column group streams
+        // fewer bytes but keeps the layer's row splits)
+        weight[ni++] = 128.0;
       }
     }
   }
   for (int mh = 0; mh < g.H / 256; ++mh) {
+    group[ni] = g.L + 1;
     WgItem& w = p.items[ni];
     w = WgItem{};
     w.out = kWgOutFinal;
@@ -403,7 +440,7 @@ int launch_gen_wgrad(const b200inr_net* net, void* stash, int64_t rows, float* g
     weight[ni++] = 80.0;
   }
   p.num_items = ni;
-  return launch_items(p, weight, num_sms, stream);
+  return launch_items(p, weight, group, num_sms, stream);
 }
 
 // WIRE: the contraction produces the gradient of the real-block matrices into the fp32 scratch of the stash
@@ -420,6 +457,7 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
   p.d = w.d;
   p.C = w.C;
   double weight[kWgMaxItems];
+  int group[kWgMaxItems];
   int ni = 0;
   const uint32_t tile_s = kTileRows * 128;
   for (int l = 0; l <= w.L; ++l) {
@@ -428,6 +466,7 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
       const int ngroups = (l == 0 && w.K0) ? (w.kb0() + 3) / 4 : 1;
       for (int gq = 0; gq < ngroups; ++gq) {
         if (ni >= kWgMaxItems - 1) return B200INR_ERR_BAD_SHAPE;
+        group[ni] = l;
         WgItem& it = p.items[ni];
         it = WgItem{};
         it.a_src = st + sl.dz + size_t(l) * sl.stride_z;
@@ -446,7 +485,7 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
           it.ldw = w.K0;
           it.row_off = 256 * mh;
           it.col_off = 256 * gq;
-          weight[ni++] = 64.0 + 16.0 * it.nb;
+          weight[ni++] = 128.0;
         } else if (l == 0) {
           it.out = kWgOutCoord;
           it.nb = 1;
@@ -468,6 +507,7 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
     }
   }
   {
+    group[ni] = w.L + 1;
     WgItem& it = p.items[ni];
     it = WgItem{};
     it.out = kWgOutFinal;
@@ -485,7 +525,7 @@ int launch_wire_wgrad(const b200inr_net* net, void* stash, int64_t rows, int num
     weight[ni++] = 80.0;
   }
   p.num_items = ni;
-  return launch_items(p, weight, num_sms, stream);
+  return launch_items(p, weight, group, num_sms, stream);
 }
 
 }  // namespace b200inr
