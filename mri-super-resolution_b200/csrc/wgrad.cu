@@ -250,8 +250,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
 // tiles): cfg4 reads 13.8 GB from DRAM instead of 15.8 GB for 9.8 GB of unique tiles.  Measured and NOT kept: holding a
 // group's producers within a few tiles of each other through global progress counters brings DRAM reads down to the
 // unique 9.8 GB, but every check costs the producer ~4 us under load (the L2 fabric is the busy resource: 18.5 GB
-// cross it either way) and the kernel got slower (2.6 -> 3.7-7.4 ms); sharing tiles inside a cluster (multicast or a
-// cta_group::2 MMA that splits B) is the remaining way to cut the fabric traffic itself.
+// cross it either way) and the kernel got slower (2.6 -> 3.7-7.4 ms).  Also measured and NOT kept: clusters of four CTAs
+// (one row split of a layer's four blocks) in which every CTA bulk-copies half of each shared operand and multicasts
+// it to its partner, consumers releasing a slot on the `empty` barriers of all CTAs that copy into it -- bit-identical
+// results, but 5.0 ms on cfg4 (B pairs only: 3.6 ms; the cluster launch alone, without sharing: 3.1 ms, fewer
+// co-resident CTAs): with 32-row stages the cross-CTA release -> copy -> full round trip exceeds the six-stage ring.
 static int launch_items(WgParams& p, const double* weight, const int* group, int num_sms, cudaStream_t stream) {
   double total = 0.0;
   for (int i = 0; i < p.num_items; ++i) total += weight[i];
