@@ -295,8 +295,9 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
 int b200inr_input_mapping_backward(const float* x, const float* B, const float* grad_out, int64_t rows, int32_t d,
                                    int32_t m, float* grad_x, void* stream);
 
-/* The pre-activation returned by SineLayer.forward_with_intermediate (INR/SRDWI.py:61-64) for a coordinate-fed layer:
- * out [rows, H] = omega * (x [rows, d] W[H, d]^T + b[H]), fp32, d <= 8. */
+/* The pre-activation returned by SineLayer.forward_with_intermediate (INR/SRDWI.py:61-64), a probing helper ("for
+ * visualization of activation distributions"): out [rows, H] = omega * (x [rows, d] W[H, d]^T + b[H]), fp32 on CUDA
+ * cores, any input width d <= 4096. */
 int b200inr_sine_layer_pre(const float* x, const float* W, const float* b, int64_t rows, int32_t d, int32_t H,
                            float omega, float* out, void* stream);
 

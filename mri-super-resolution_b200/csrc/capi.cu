@@ -683,7 +683,7 @@ int b200inr_input_mapping(const float* x, const float* B, int64_t rows, int32_t 
 int b200inr_sine_layer_pre(const float* x, const float* W, const float* b, int64_t rows, int32_t d, int32_t H,
                            float omega, float* out, void* stream) {
   if (!x || !W || !b || !out) return B200INR_ERR_NULL;
-  if (rows < 0 || d < 1 || d > 8 || H < 1) return B200INR_ERR_BAD_SHAPE;
+  if (rows < 0 || d < 1 || d > 4096 || H < 1) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   return launch_sine_pre(x, W, b, rows, d, H, omega, out, static_cast<cudaStream_t>(stream));
 }

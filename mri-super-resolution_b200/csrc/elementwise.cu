@@ -497,8 +497,10 @@ int launch_mgrid(const GridDesc& g, int64_t rows, float* coords, cudaStream_t st
 }
 
 // ------------------------------------------------------------------ SineLayer pre-activation   INR/SRDWI.py:62
-// pre[r, h] = omega * (sum_j x[r, j] W[h, j] + b[h]) for coordinate-fed layers (d <= 8): the "intermediate" of
-// SineLayer.forward_with_intermediate, fp32.  A d-term dot product per output: not a GEMM worth a tensor core.
+// pre[r, h] = omega * (sum_j x[r, j] W[h, j] + b[h]): the "intermediate" of SineLayer.forward_with_intermediate
+// ("for visualization of activation distributions"), fp32 on CUDA cores.  A d-term dot product per output: for the
+// coordinate-fed layers the reference plots (d <= 4) not a GEMM worth a tensor core; wider layers are accepted for
+// the same probing use (one thread per output, x rows and W rows served by L1 / L2), not as a training path.
 __global__ void __launch_bounds__(kEwThreads) sine_pre_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                               const float* __restrict__ b, long long rows, int d, int H,
                                                               float omega, float* __restrict__ out) {

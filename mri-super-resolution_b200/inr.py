@@ -313,12 +313,8 @@ class SineLayer(nn.Module):
     def forward_with_intermediate(self, input):
         """Reference INR/SRDWI.py:61-64: (sin(i), i) with i = omega_0 * linear(input), "for visualization of activation
         distributions".  The pre-activation does not survive the fused kernel (it stashes 16-bit phases, i mod 2 pi),
-        so it is evaluated by the fp32 coordinate kernel b200inr_sine_layer_pre, which exists for coordinate-fed
-        layers (in_features <= 8), the case the reference plots."""
+        so it is evaluated in fp32 by b200inr_sine_layer_pre (a probing helper on CUDA cores, any input width)."""
         lin = self.linear
-        if lin.in_features > 8:
-            raise RuntimeError("b200inr: forward_with_intermediate is implemented for coordinate-fed layers "
-                               "(in_features <= 8)")
         _require_cuda(input, "SineLayer input")
         x = input.detach().contiguous().float()
         rows, h = x.shape[0], lin.out_features
