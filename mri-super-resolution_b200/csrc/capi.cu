@@ -295,6 +295,9 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
   if (e) return e;
   if (!packed || !stash || !grad_out || !grad_params) return B200INR_ERR_NULL;
   if ((coords == nullptr) == (grid == nullptr)) return B200INR_ERR_NULL;
+  // tanh output: the derivative needs the forward's output (b200inr_siren_backward_tanh_out); dgrad-only stash: there
+  // is nothing to contract weight gradients from (b200inr_siren_backward_coords)
+  if (net->flags & (B200INR_NET_TANH_OUT | B200INR_NET_DGRAD_ONLY)) return B200INR_ERR_BAD_SHAPE;
   if (rows < 0 || rows > (int64_t(1) << 37)) return B200INR_ERR_BAD_SHAPE;
   if (rows == 0) return B200INR_OK;
   if (grid && (e = check_grid(net, grid, rows))) return e;
@@ -310,9 +313,6 @@ int b200inr_siren_backward(const b200inr_net* net, const void* packed, void* sta
     return launch_wire_combine(net, stash, rows, grad_params, s);
   }
   if (is_gen(net)) {
-    // tanh output: the derivative needs the forward's output (b200inr_siren_backward_tanh_out); dgrad-only stash: there
-    // is nothing to contract weight gradients from (b200inr_siren_backward_coords)
-    if (net->flags & (B200INR_NET_TANH_OUT | B200INR_NET_DGRAD_ONLY)) return B200INR_ERR_BAD_SHAPE;
     if ((e = launch_gen_bwd(net, packed, stash, rows, grad_out, nullptr, sms, s))) return e;
     return launch_gen_wgrad(net, stash, rows, grad_params, sms, s);
   }

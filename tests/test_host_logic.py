@@ -262,6 +262,102 @@ def test_error_codes_of_the_widened_entry_points():
     assert lib.b200inr_combinations(one, None, one, one, 5, 2, 3, 2, one, None) == -5
 
 
+def test_round2_families_layouts_and_argument_checks():
+    """Host side of the round-2 additions, no GPU needed: WIRE on features / Fourier features (parameter layout ==
+    the module's parameters), the tanh / tanh-out / dgrad-only descriptors of the fused PerturbNet loop, their stash
+    sizes, and the argument validation of the new entry points."""
+    lib = L.load()
+    one = ctypes.c_void_p(1024)
+    n = ctypes.c_int64(0)
+    # WIRE exactly as wiretest.ipynb cell 7 builds it: real first layer [128, 512] x 2, complex hidden / final layers
+    m = b200inr.Wire(in_features=512, out_features=1, hidden_features=128, hidden_layers=3, first_omega_0=1.2,
+                     hidden_omega_0=1.2, scale=1.2)
+    reals = sum(p.numel() * (2 if p.is_complex() else 1) for p in m._canonical())
+    assert m._desc.input_mode == L.IN_FEATURES and m._grid_dim is None
+    cnt = L.param_count(m._desc)
+    assert reals <= cnt < reals + 4 * len(L.param_offsets(m._desc))
+    assert len(L.param_offsets(m._desc)) == 4 * 4 + 2
+    B = np.zeros((256, 4), dtype=np.float32)
+    mf = b200inr.Wire(4, 128, 3, 1, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2, B=B)
+    assert mf._desc.input_mode == L.IN_FOURIER and mf._grid_dim == 4
+    assert len(L.param_offsets(mf._desc)) == 4 * 4 + 3 and L.param_count(mf._desc) >= cnt + 256 * 4
+    assert [tuple(p.shape) for p in m.parameters()] == [tuple(p.shape) for p in mf.parameters()]
+    # the feature-fed stash also holds the network input tiles (bf16): 128 rows x 512 features more per tile
+    raw = L.make_net(3, 128, 3, 1, activation=L.ACT_GABOR, scale_0=1.2)
+    assert L.stash_bytes(m._desc, 128) - L.stash_bytes(raw, 128) >= 128 * 512 * 2
+    for bad in (L.make_net(96, 128, 3, 1, activation=L.ACT_GABOR, input_mode=L.IN_FEATURES),     # not a multiple of 64
+                L.make_net(576, 128, 3, 1, activation=L.ACT_GABOR, input_mode=L.IN_FEATURES),    # wider than 512
+                L.make_net(512, 64, 3, 1, activation=L.ACT_GABOR, input_mode=L.IN_FEATURES),     # 128 complex units only
+                L.make_net(4, 128, 3, 1, activation=L.ACT_GABOR, input_mode=L.IN_FOURIER, mapping_size=48)):
+        assert lib.b200inr_param_count(ctypes.byref(bad), ctypes.byref(n)) == -1
+    # PN as a generic-family network; the frozen INR's dgrad-only stash
+    pn = L.make_net(4, 256, 0, 4, activation=L.ACT_TANH, input_mode=L.IN_FOURIER, mapping_size=128, scale_0=1 / 128.,
+                    flags=L.NET_TANH_OUT)
+    assert L.param_count(pn) >= 256 * 256 + 256 + 4 * 256 + 4 + 128 * 4
+    assert lib.b200inr_param_count(ctypes.byref(L.make_net(4, 512, 0, 4, activation=L.ACT_TANH, input_mode=L.IN_FOURIER,
+                                                           mapping_size=128)), ctypes.byref(n)) == -1  # 256-wide only
+    assert lib.b200inr_param_count(ctypes.byref(L.make_net(3, 256, 2, 4, activation=L.ACT_TANH)), ctypes.byref(n)) == -1
+    assert lib.b200inr_param_count(ctypes.byref(L.make_net(4, 256, 0, 4, activation=L.ACT_TANH, input_mode=L.IN_FOURIER,
+                                                           mapping_size=128, flags=L.NET_TANH_OUT)),
+                                   ctypes.byref(n)) == -1                                              # scale_0 missing
+    full = L.make_net(4, 512, 3, 1, input_mode=L.IN_FOURIER, mapping_size=128)
+    lean = L.make_net(4, 512, 3, 1, input_mode=L.IN_FOURIER, mapping_size=128, flags=L.NET_DGRAD_ONLY)
+    assert L.stash_bytes(lean, 1 << 14) == 4 * (1 << 14) * 512 * 2          # the 16-bit phases of four sine layers
+    assert L.stash_bytes(full, 1 << 14) > 2 * L.stash_bytes(lean, 1 << 14)
+    assert L.packed_bytes(full) == L.packed_bytes(lean) and L.param_count(full) == L.param_count(lean)
+    # coordinate-gradient backward: Fourier networks, grad_params NULL exactly when the stash is dgrad-only
+    g = L.make_grid((16, 16, 8, 8))
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(lean), one, one, one, None, 0, one, None, one, None) == 0
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(lean), one, one, one, None, 0, one, one, one, None) == -1
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(full), one, one, one, None, 0, one, None, one, None) == -1
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(full), one, one, None, ctypes.byref(g), 0, one, one, one,
+                                             None) == 0
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(full), one, one, one, ctypes.byref(g), 0, one, one, one,
+                                             None) == -5                                          # coords XOR grid
+    feat = L.make_net(256, 512, 3, 1, input_mode=L.IN_FEATURES)
+    assert lib.b200inr_siren_backward_coords(ctypes.byref(feat), one, one, one, None, 0, one, one, one, None) == -1
+    # a lean or tanh-out network cannot go through the plain backward
+    assert lib.b200inr_siren_backward(ctypes.byref(lean), one, one, one, None, 128, one, one, None) == -1
+    assert lib.b200inr_siren_backward(ctypes.byref(pn), one, one, one, None, 128, one, one, None) == -1
+    assert lib.b200inr_siren_backward_tanh_out(ctypes.byref(pn), one, one, 0, one, one, one, None) == 0
+    assert lib.b200inr_siren_backward_tanh_out(ctypes.byref(full), one, one, 0, one, one, one, None) == -1
+    assert lib.b200inr_siren_backward_tanh_out(ctypes.byref(pn), one, one, 0, None, one, one, None) == -5
+    assert lib.b200inr_pn_effective_params(one, 100, 90, 20, 0.3, one, None, None) == -1    # bias segment out of range
+    assert lib.b200inr_pn_fold_grad(None, 100, 10, 20, 0.3, None) == -5
+    # blurred pooling slab: even plane bounds inside the volume
+    for xb, xe in ((1, 8), (0, 7), (4, 4), (0, 18)):
+        assert lib.b200inr_blurpool_mse_slab(one, one, 16, 8, 32, 1.0, one, one, one, one, xb, xe, one, one, one,
+                                             None) == -1
+
+
+def test_padded_engine_views_and_halo_slabs():
+    """Zero-padded generic widths: the flat-vector view of every parameter of Siren(256, 128, 3, 1) (SR3D.ipynb cell 4)
+    is the leading corner of its 256-wide segment; blur_pool slabs carry one LR halo row per interior side."""
+    m = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=128, hidden_layers=3)
+    assert m._hp == 256 and m._desc.hidden_features == 256 and m.hidden_features == 128
+    off = L.param_offsets(m._desc)
+    flat = torch.arange(L.param_count(m._desc), dtype=torch.float32)
+    ps = m._canonical()
+    for i, (o, p) in enumerate(zip(off, ps)):
+        v = m._param_view(flat, o, p, i)
+        assert tuple(v.shape) == tuple(p.shape)
+        assert v.reshape(-1)[0].item() == o
+        if p.dim() == 2 and i < 2 * 5 - 2:          # hidden weights: rows of the 256-wide segment
+            assert v[1, 0].item() == o + (256 if i >= 2 else p.shape[1])
+    assert m._padded_shape(2 * 4, ps[8]) == (1, 256)     # final linear [C, H] lives in a [C, 256] segment
+    same = b200inr.INRmodel.Siren(in_features=256, out_features=1, hidden_features=256, hidden_layers=3)
+    assert same._hp is None and b200inr.INRmodel.Siren(512, 256, 1, 1)._hp == 512
+    with pytest.raises(RuntimeError):
+        b200inr.INRmodel.Siren(in_features=1024, out_features=1, hidden_features=256, hidden_layers=1)
+    lr = np.arange(8 * 3 * 2 * 1).reshape(8, 3, 2, 1)
+    shape = (16, 6, 2)
+    plane = 12
+    assert b200inr.parallel.lr_slab(lr, shape, (0, 8 * plane), halo=1).shape[0] == 5          # rows 0..4
+    assert b200inr.parallel.lr_slab(lr, shape, (4 * plane, 12 * plane), halo=1)[0, 0, 0, 0] == lr[1, 0, 0, 0]
+    assert b200inr.parallel.lr_slab(lr, shape, (8 * plane, 16 * plane), halo=1).shape[0] == 5  # rows 3..7
+    assert b200inr.parallel.lr_slab(lr, shape, (0, 16 * plane), halo=1).shape[0] == 8
+
+
 # ------------------------------------------------------------------------------------------------ drop-in boundary
 REFERENCE_IMPORT_LINES = [
     # the literal import statements of the reference's drivers (file:line), executed against the drop-in directory
