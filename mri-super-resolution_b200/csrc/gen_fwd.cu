@@ -13,13 +13,26 @@
 // epilogue of one tile alternate; the epilogue is cheap next to the 4x larger GEMM (ReLU) and the weight ring
 // prefetches across it.
 //
-// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner, warp 2 = stash store (training),
+// CTA PAIRS (cta_group::2): two CTAs of a cluster work on two neighbouring 128-row tiles with ONE tcgen05.mma of
+// M = 256 per K step, issued by the leader; each CTA stages only HALF of every weight chunk (128 of its 256 output
+// rows).  At H = 512 a single CTA's shared-memory pipe was the limit: the tensor core re-reads the whole B operand per
+// tile (96 B/clk with the A slices) while the ring re-streams the layer's 512 KB of weights (64 B/clk) against 128 B/clk
+// of bandwidth; in a pair both halve (64 + 32 B/clk).  Barriers: weights `w_full` (leader: own bytes + the peer's relay),
+// `w_empty` / `d_full` by multicast commit, operand tiles `a_half` on the leader (32 epilogue warps of both CTAs, plain
+// remote arrives behind fence.proxy.async -- see mlp_fwd.cu) and `a_loc` locally for the stash-store thread.
+//
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (leader) / weight relay (peer) + TMEM owner,
+//             warp 2 = stash store (training),
 //             warps 3..18 = epilogue (TMEM lane quadrant = warp & 3, 16-column slice = (warp - 3) >> 2).
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
+
+#ifndef B200INR_GKO
+#define B200INR_GKO 0  // tuning knock-outs (results are garbage): 1 = weight slots loaded once and never waited for again
+#endif
 
 namespace b200inr {
 
@@ -53,10 +66,11 @@ struct GenSmem {
   static constexpr int kKB = H / 64;
   static constexpr int kABlock = kTileRows * 128;
   static constexpr int kABytes = kKB * kABlock;
-  static constexpr int kSlots = (H == 512) ? 3 : 4;
+  static constexpr int kSlots = 6;                       // weight ring: this CTA's half of a chunk per slot
+  static constexpr int kSlotBytes = kGenChunkBytes / 2;  // [128 rows (its half of N)][64 (K)]
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kABytes;
-  static constexpr int kOffBar = kOffW + kSlots * kGenChunkBytes;
+  static constexpr int kOffBar = kOffW + kSlots * kSlotBytes;
   static constexpr int kBytes = kOffBar + 256;
 };
 
@@ -72,42 +86,60 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
   uint8_t* a_smem = smem + S::kOffA;
   uint8_t* w_smem = smem + S::kOffW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;                    // [kSlots]
-  uint64_t* w_empty = bars + S::kSlots;       // [kSlots]
+  uint64_t* w_full = bars;                    // [kSlots] leader: own half landed + the peer's relay; peer: own half
+  uint64_t* w_empty = bars + S::kSlots;       // [kSlots] MMAs reading the slot done (multicast commit)
   // A operand of the next layer in shared memory, in two halves of K blocks: with two N halves (H = 512) the next
-  // layer's MMAs into D[0:256) over blocks 0..kKB/2-1 start while the epilogue still works on D[256:512)
+  // layer's MMAs into D[0:256) over blocks 0..kKB/2-1 start while the epilogue still works on D[256:512).
+  // a_half: on the LEADER, counts the epilogue warps of both CTAs (what the MMA issuer waits for);
+  // a_loc: the same events of this CTA alone (what its stash-store thread waits for)
   uint64_t* a_half = bars + 2 * S::kSlots;    // [2]
-  uint64_t* d_full = bars + 2 * S::kSlots + 2;
+  uint64_t* d_full = bars + 2 * S::kSlots + 2;  // (multicast commit)
   uint64_t* a_free = bars + 2 * S::kSlots + 3;  // stash store of the A tile has been read out (training)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 4);
+  uint64_t* a_loc = bars + 2 * S::kSlots + 4;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 6);
+  static_assert((2 * S::kSlots + 6) * 8 + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const GenDims g = p.g;
   const int L = g.L;
   const int KB0 = g.K0 / 64;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S::kSlots; ++i) {
-      mbar_init(&w_full[i], 1);
+      mbar_init(&w_full[i], leader ? 2 : 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_half[0], kGenEpiWarps);
-    mbar_init(&a_half[1], kGenEpiWarps);
+    mbar_init(&a_half[0], 2 * kGenEpiWarps);
+    mbar_init(&a_half[1], 2 * kGenEpiWarps);
+    mbar_init(&a_loc[0], kGenEpiWarps);
+    mbar_init(&a_loc[1], kGenEpiWarps);
     mbar_init(d_full, 1);
     mbar_init(a_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  // the pair walks tile pairs: tile = 2 * (pair + t * pairs) + rank; a peer whose last tile lies past the end recomputes
+  // the last tile (identical values stored twice), so the lock-stepped schedule needs no inactive-tile branches
+  const int num_pairs_grid = int(gridDim.x) / 2;
+  const int tile_pairs = (p.num_tiles + 1) / 2;
+  const int my_tiles = (tile_pairs - int(blockIdx.x) / 2 + num_pairs_grid - 1) / num_pairs_grid;
+  auto tile_of = [&](int t) {
+    const int tile = 2 * (int(blockIdx.x) / 2 + t * num_pairs_grid) + int(rank);
+    return tile < p.num_tiles ? tile : p.num_tiles - 1;
+  };
 
   if (warp == 0) {
     // =============================== weight producer ===============================
+    // every CTA stages ITS half of each chunk: rows [128 rank, 128 rank + 128) of the chunk's 256 output rows (final
+    // linear: 16 of the 32), i.e. accumulator column == output feature for the M = 256 pair MMA
     if (lane == 0) {
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
@@ -115,24 +147,27 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
           const bool act_layer = (l <= L);
           const int nchunks = act_layer ? NH * (l == 0 ? KB0 : S::kKB) : S::kKB;
           const uint8_t* src = act_layer ? p.packed + p.pl.w_layer(g, l) : p.packed + p.pl.wf;
-          const uint32_t bytes = act_layer ? uint32_t(kGenChunkBytes) : uint32_t(kOutPad * 128);
+          const uint32_t chunk = act_layer ? uint32_t(kGenChunkBytes) : uint32_t(kOutPad * 128);
+          const uint32_t bytes = chunk / 2;
           for (int j = 0; j < nchunks; ++j, ++c) {
             const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
+            if ((B200INR_GKO & 1) && round > 0) continue;
             if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
             mbar_arrive_expect_tx(&w_full[slot], bytes);
-            bulk_g2s(w_smem + slot * kGenChunkBytes, src + size_t(j) * bytes, bytes, &w_full[slot]);
+            bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(j) * chunk + size_t(rank) * bytes, bytes, &w_full[slot]);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    {  // whole warp converged, one elected lane issues (umma_*_w)
+    if (leader) {
+      // =============================== MMA issuer (pair leader) ===============================
+      // whole warp converged, one elected lane issues (umma_*_w)
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      const uint32_t idesc_h = idesc_bf16(128, 256, false, false);
-      const uint32_t idesc_f = idesc_bf16(128, kOutPad, false, false);
+      const uint32_t idesc_h = idesc_bf16(256, 256, false, false);
+      const uint32_t idesc_f = idesc_bf16(256, kOutPad, false, false);
       uint32_t c = 0, n = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l <= L + 1; ++l, ++n) {
@@ -149,19 +184,36 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
                 second = true;
               }
               const uint32_t slot = c % S::kSlots;
-              mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
+              if (!(B200INR_GKO & 1) || c < uint32_t(S::kSlots)) mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
               tc_fence_after();
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
-                const uint64_t db = smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi);
-                umma_bf16_ss_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
+                const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
+                umma_bf16_ss_2cta_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
               }
-              umma_commit_w(&w_empty[slot]);
+              umma_commit_2cta_w(&w_empty[slot]);
             }
           }
           if (!second) mbar_wait(&a_half[1], n & 1);  // (every phase of a barrier is consumed by its waiter)
-          umma_commit_w(d_full);
+          umma_commit_2cta_w(d_full);
+        }
+      }
+    } else if (lane == 0) {
+      // =============================== weight relay (pair peer) ===============================
+      // "my half of the chunk has landed" (bulk copy = async proxy, read by the async proxy: no fence) -> second
+      // arrival on the leader's w_full barrier of that slot
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l <= L + 1; ++l) {
+          const bool act_layer = (l <= L);
+          const int nchunks = act_layer ? NH * (l == 0 ? KB0 : S::kKB) : S::kKB;
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const uint32_t slot = c % S::kSlots;
+            if ((B200INR_GKO & 1) && c >= uint32_t(S::kSlots)) continue;
+            mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
+            mbar_arrive_peer(&w_full[slot], 0);
+          }
         }
       }
     }
@@ -170,10 +222,10 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
     if (kStash && lane == 0) {
       uint32_t n = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int tile = int(blockIdx.x) + t * int(gridDim.x);
+        const int tile = tile_of(t);
         for (int l = -1; l <= L; ++l, ++n) {  // l = -1: the network input tile
-          mbar_wait(&a_half[0], n & 1);
-          mbar_wait(&a_half[1], n & 1);
+          mbar_wait(&a_loc[0], n & 1);
+          mbar_wait(&a_loc[1], n & 1);
           // lean stash: the input tile is only a weight-gradient operand; sine derivatives come from the phases
           const bool store = !p.lean || (l >= 0 && ACT != B200INR_ACT_SINE);
           if (store) {
@@ -200,8 +252,16 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
     const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
     const float4* bmat_g = reinterpret_cast<const float4*>(p.packed + p.pl.bmat);
     uint32_t n = 0, nf = 0;
+    // half i of the A tile is complete: the leader's MMA issuer (both CTAs' warps) and this CTA's stash-store thread
+    auto arrive_half = [&](int i) {
+      if (kStash) mbar_arrive(&a_loc[i]);
+      if (leader)
+        mbar_arrive(&a_half[i]);
+      else
+        mbar_arrive_peer(&a_half[i], 0);
+    };
     for (int t = 0; t < my_tiles; ++t) {
-      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const int tile = tile_of(t);
       const long long row0 = (long long)tile * kTileRows;
 
       // ---- network input -> A operand
@@ -252,8 +312,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&a_half[0]);
-          mbar_arrive(&a_half[1]);
+          arrive_half(0);
+          arrive_half(1);
         }
       }
 
@@ -317,15 +377,15 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_half[0]);
+            if (lane == 0) arrive_half(0);
           }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (NH != 2) mbar_arrive(&a_half[0]);
-          mbar_arrive(&a_half[1]);
+          if (NH != 2) arrive_half(0);
+          arrive_half(1);
         }
       }
 
@@ -366,24 +426,30 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
     }
   }
 
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_d);
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still address it
+  if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
 }
 
 template <int H, int ACT>
 static int launch_gen_fwd_t(const GenFwdParams& p, bool stash, int grid_x, cudaStream_t stream) {
   const int smem = GenSmem<H>::kBytes + 1024;
-  if (stash) {
-    if (cudaFuncSetAttribute(gen_fwd_kernel<H, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return B200INR_ERR_CUDA;
-    gen_fwd_kernel<H, ACT, true><<<grid_x, kGenThreads, smem, stream>>>(p);
-  } else {
-    if (cudaFuncSetAttribute(gen_fwd_kernel<H, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return B200INR_ERR_CUDA;
-    gen_fwd_kernel<H, ACT, false><<<grid_x, kGenThreads, smem, stream>>>(p);
-  }
+  void (*kern)(const GenFwdParams) = stash ? gen_fwd_kernel<H, ACT, true> : gen_fwd_kernel<H, ACT, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return B200INR_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid_x));
+  cfg.blockDim = dim3(kGenThreads);
+  cfg.dynamicSmemBytes = size_t(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2;
+  at.val.clusterDim.y = 1;
+  at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return B200INR_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
@@ -420,12 +486,10 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
   }
   p.lean = (net->flags & B200INR_NET_DGRAD_ONLY) ? 1 : 0;
   p.out_tanh = (net->flags & B200INR_NET_TANH_OUT) ? net->scale_0 : 0.f;
-  int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  {  // tuning aid (same switch as mlp_fwd.cu): cap the number of CTAs
-    const char* env_cap = getenv("B200INR_FWD_MAX_CTAS");
-    const int cap = env_cap != nullptr ? atoi(env_cap) : 0;
-    if (cap > 0 && cap < grid_x) grid_x = cap;
-  }
+  // persistent CTA pairs (clusters of 2) walk tile pairs: an even number of CTAs, at most one per SM
+  const int tile_pairs = (p.num_tiles + 1) / 2;
+  int grid_x = 2 * (tile_pairs < num_sms / 2 ? tile_pairs : num_sms / 2);
+  if (grid_x < 2) grid_x = 2;
   const bool sine = net->activation == B200INR_ACT_SINE;
   if (net->activation == B200INR_ACT_TANH)  // the perturbation network: 256-wide operands only
     return launch_gen_fwd_t<256, B200INR_ACT_TANH>(p, stash != nullptr, grid_x, stream);
