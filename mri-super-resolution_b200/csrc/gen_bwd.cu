@@ -52,10 +52,13 @@ struct GenBwdSmem {
   static constexpr int kKB = H / 64;
   static constexpr int kABlock = kTileRows * 128;
   static constexpr int kABytes = kKB * kABlock;
-  static constexpr int kSlots = (H == 512) ? 2 : 4;  // 128 KB A + 16 KB dOut block leave room for two chunks at H = 512
+  // CTA pairs (cta_group::2, as in gen_fwd.cu): every CTA stages HALF of a weight chunk (128 of its 256 rows), so the
+  // 64 KB the two whole chunks took at H = 512 now hold a four-deep ring
+  static constexpr int kSlots = (H == 512) ? 4 : 6;
+  static constexpr int kSlotBytes = kGenChunkBytes / 2;
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kABytes;
-  static constexpr int kOffDzo = kOffW + kSlots * kGenChunkBytes;
+  static constexpr int kOffDzo = kOffW + kSlots * kSlotBytes;
   static constexpr int kOffBar = kOffDzo + kTileRows * 128;
   static constexpr int kOffRed = kOffBar + 256;                   // [4 slices][128 rows] float4: coordinate-gradient partials
   static constexpr int kBytes = kOffRed + 4 * kTileRows * 16;
@@ -78,42 +81,59 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
   uint8_t* w_smem = smem + S::kOffW;
   uint8_t* dzo_smem = smem + S::kOffDzo;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = bars + S::kSlots;
+  uint64_t* w_full = bars;               // leader: own half landed + the peer's relay; peer: own half
+  uint64_t* w_empty = bars + S::kSlots;  // multicast commit
   // the dTheta tile (A operand of the next chain step) is handed over in two halves of K blocks, as in gen_fwd.cu: at
-  // H = 512 the next step's MMAs into D[0:256) start while the epilogue still works on D[256:512)
+  // H = 512 the next step's MMAs into D[0:256) start while the epilogue still works on D[256:512).
+  // a_half / dzo_ready: on the LEADER, count the epilogue warps of both CTAs (the MMA issuer's view);
+  // a_loc / dzo_loc: this CTA's own warps (its stash-store thread's view)
   uint64_t* a_half = bars + 2 * S::kSlots;  // [2]
   uint64_t* dzo_ready = bars + 2 * S::kSlots + 2;
-  uint64_t* d_full = bars + 2 * S::kSlots + 3;
+  uint64_t* d_full = bars + 2 * S::kSlots + 3;  // multicast commit
   uint64_t* a_free = bars + 2 * S::kSlots + 4;
   uint64_t* dzo_free = bars + 2 * S::kSlots + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 6);
+  uint64_t* a_loc = bars + 2 * S::kSlots + 6;  // [2]
+  uint64_t* dzo_loc = bars + 2 * S::kSlots + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kSlots + 9);
+  static_assert((2 * S::kSlots + 9) * 8 + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const GenDims g = p.g;
   const int L = g.L;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S::kSlots; ++i) {
-      mbar_init(&w_full[i], 1);
+      mbar_init(&w_full[i], leader ? 2 : 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_half[0], kGenBwdEpiWarps);
-    mbar_init(&a_half[1], kGenBwdEpiWarps);
-    mbar_init(dzo_ready, kGenBwdEpiWarps);
+    mbar_init(&a_half[0], 2 * kGenBwdEpiWarps);
+    mbar_init(&a_half[1], 2 * kGenBwdEpiWarps);
+    mbar_init(dzo_ready, 2 * kGenBwdEpiWarps);
+    mbar_init(&a_loc[0], kGenBwdEpiWarps);
+    mbar_init(&a_loc[1], kGenBwdEpiWarps);
+    mbar_init(dzo_loc, kGenBwdEpiWarps);
     mbar_init(d_full, 1);
     mbar_init(a_free, 1);
     mbar_init(dzo_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  const int my_tiles = (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  // the pair walks tile pairs (tile = 2 * (pair + t * pairs) + rank); a peer past the end recomputes the last tile
+  const int num_pairs_grid = int(gridDim.x) / 2;
+  const int tile_pairs = (p.num_tiles + 1) / 2;
+  const int my_tiles = (tile_pairs - int(blockIdx.x) / 2 + num_pairs_grid - 1) / num_pairs_grid;
+  auto tile_of = [&](int t) {
+    const int tile = 2 * (int(blockIdx.x) / 2 + t * num_pairs_grid) + int(rank);
+    return tile < p.num_tiles ? tile : p.num_tiles - 1;
+  };
   const int dx = (p.grad_in != nullptr || p.grad_coords != nullptr) ? 1 : 0;  // extra chain step: input gradient
   const int NX = (g.K0 + 255) / 256;            // its N, in 256-column halves
 
@@ -130,22 +150,25 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
                                : (u <= L) ? p.packed + p.pl.wt_layer(g, L - u + 1)
                                           : p.packed + p.pl.wt0;
           for (int j = 0; j < nchunks; ++j, ++c) {
+            // this CTA's half of the chunk: rows [128 rank, 128 rank + 128) (accumulator column == input feature)
             const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
             if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
-            mbar_arrive_expect_tx(&w_full[slot], kGenChunkBytes);
-            bulk_g2s(w_smem + slot * kGenChunkBytes, src + size_t(j) * kGenChunkBytes, kGenChunkBytes, &w_full[slot]);
+            mbar_arrive_expect_tx(&w_full[slot], S::kSlotBytes);
+            bulk_g2s(w_smem + slot * S::kSlotBytes, src + size_t(j) * kGenChunkBytes + size_t(rank) * S::kSlotBytes,
+                     S::kSlotBytes, &w_full[slot]);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    {  // whole warp converged, one elected lane issues (umma_*_w)
+    if (leader) {
+      // =============================== MMA issuer (pair leader) ===============================
+      // whole warp converged, one elected lane issues (umma_*_w); M = 256: both CTAs' tiles in one instruction
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
       const uint32_t dzo_base = smem_u32(dzo_smem);
-      const uint32_t idesc = idesc_bf16(128, 256, false, false);
+      const uint32_t idesc = idesc_bf16(256, 256, false, false);
       uint32_t c = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t inst0 = uint32_t(t) * uint32_t(L + 1);  // a_ready completes L + 1 times per tile
@@ -170,14 +193,14 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
               const uint32_t a_blk = (u == 0) ? dzo_base : a_base + kb * S::kABlock;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16_ss_w(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
-                             smem_desc(w_base + slot * kGenChunkBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
+                umma_bf16_ss_2cta_w(tmem_d + nh * 256, smem_desc(a_blk + k4 * 32, hi),
+                                    smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi), idesc, (kb | k4) != 0);
               }
-              umma_commit_w(&w_empty[slot]);
+              umma_commit_2cta_w(&w_empty[slot]);
             }
           }
           if (!second) mbar_wait(&a_half[1], (inst0 + u - 1) & 1);
-          umma_commit_w(d_full);
+          umma_commit_2cta_w(d_full);
         }
         // without the input-gradient step nobody reads the last tile (dTheta_0) through these barriers' final phase;
         // consume it so that the next tile's waits stay one phase behind at most
@@ -186,14 +209,27 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
           mbar_wait(&a_half[1], (inst0 + L) & 1);
         }
       }
+    } else if (lane == 0) {
+      // =============================== weight relay (pair peer) ===============================
+      uint32_t c = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int u = 0; u <= L + dx; ++u) {
+          const int nchunks = (u == 0) ? NH : (u <= L ? NH : NX) * S::kKB;
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const uint32_t slot = c % S::kSlots;
+            mbar_wait(&w_full[slot], (c / S::kSlots) & 1);
+            mbar_arrive_peer(&w_full[slot], 0);
+          }
+        }
+      }
     }
   } else if (warp == 2) {
     // =============================== stash store ===============================
     if (lane == 0) {
       uint32_t n = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int tile = int(blockIdx.x) + t * int(gridDim.x);
-        mbar_wait(dzo_ready, t & 1);
+        const int tile = tile_of(t);
+        mbar_wait(dzo_loc, t & 1);
         if (!p.lean) {
           bulk_s2g(p.stash_dzo + size_t(tile) * (kTileRows * 128), dzo_smem, kTileRows * 128);
           bulk_commit();
@@ -201,8 +237,8 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
         }
         mbar_arrive(dzo_free);
         for (int l = L; l >= 0; --l, ++n) {
-          mbar_wait(&a_half[0], n & 1);
-          mbar_wait(&a_half[1], n & 1);
+          mbar_wait(&a_loc[0], n & 1);
+          mbar_wait(&a_loc[1], n & 1);
           if (!p.lean) {
             bulk_s2g(p.stash_dz + size_t(l) * p.layer_stride + size_t(tile) * S::kABytes, a_smem, S::kABytes);
             bulk_commit();
@@ -223,8 +259,16 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
     const uint32_t dzo_addr = smem_u32(dzo_smem);
     const int C = g.C;
     uint32_t n = 0, nf = 0;
+    // hand-offs: the leader's MMA issuer counts both CTAs' warps, the local barrier feeds this CTA's stash thread
+    auto arrive2 = [&](uint64_t* pair_bar, uint64_t* local_bar) {
+      mbar_arrive(local_bar);
+      if (leader)
+        mbar_arrive(pair_bar);
+      else
+        mbar_arrive_peer(pair_bar, 0);
+    };
     for (int t = 0; t < my_tiles; ++t) {
-      const int tile = int(blockIdx.x) + t * int(gridDim.x);
+      const int tile = tile_of(t);
       const long long row0 = (long long)tile * kTileRows;
 
       // ---- dOut tile -> bf16 [128][64] block
@@ -254,7 +298,7 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dzo_ready);
+        if (lane == 0) arrive2(dzo_ready, dzo_loc);
       }
 
       // ---- dTheta_l = dY_l .* act'(theta_l), l = L .. 0
@@ -321,15 +365,15 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_half[0]);
+            if (lane == 0) arrive2(&a_half[0], &a_loc[0]);
           }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (NH != 2) mbar_arrive(&a_half[0]);
-          mbar_arrive(&a_half[1]);
+          if (NH != 2) arrive2(&a_half[0], &a_loc[0]);
+          arrive2(&a_half[1], &a_loc[1]);
         }
       }
 
@@ -411,8 +455,9 @@ __global__ void __launch_bounds__(kGenBwdThreads, 1) gen_bwd_kernel(const GenBwd
     }
   }
 
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_d);
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still address it
+  if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
 }
 
 template <int H, int ACT>
@@ -420,7 +465,19 @@ static int launch_gen_bwd_t(const GenBwdParams& p, int grid_x, cudaStream_t stre
   const int smem = GenBwdSmem<H>::kBytes + 1024;
   if (cudaFuncSetAttribute(gen_bwd_kernel<H, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
-  gen_bwd_kernel<H, ACT><<<grid_x, kGenBwdThreads, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid_x));
+  cfg.blockDim = dim3(kGenBwdThreads);
+  cfg.dynamicSmemBytes = size_t(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2;
+  at.val.clusterDim.y = 1;
+  at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, gen_bwd_kernel<H, ACT>, p) != cudaSuccess) return B200INR_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? B200INR_OK : B200INR_ERR_CUDA;
 }
 
@@ -457,7 +514,10 @@ int launch_gen_bwd(const b200inr_net* net, const void* packed, void* stash, int6
   p.stash_dz = st + sl.dz;
   p.stash_dzo = st + sl.dzo;
   p.layer_stride = sl.layer_stride;
-  const int grid_x = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  // persistent CTA pairs (clusters of 2) walk tile pairs
+  const int tile_pairs_h = (p.num_tiles + 1) / 2;
+  int grid_x = 2 * (tile_pairs_h < num_sms / 2 ? tile_pairs_h : num_sms / 2);
+  if (grid_x < 2) grid_x = 2;
   const bool sine = net->activation == B200INR_ACT_SINE;
   if (net->activation == B200INR_ACT_TANH) return launch_gen_bwd_t<256, B200INR_ACT_TANH>(p, grid_x, stream);
   if (p.g.H == 256)

@@ -61,13 +61,14 @@ struct GenFwdParams {
   float out_tanh;   // B200INR_NET_TANH_OUT: out = out_tanh * tanh(out) (0: plain linear output)
 };
 
-template <int H>
+template <int H, bool kPair>
 struct GenSmem {
   static constexpr int kKB = H / 64;
   static constexpr int kABlock = kTileRows * 128;
   static constexpr int kABytes = kKB * kABlock;
-  static constexpr int kSlots = 6;                       // weight ring: this CTA's half of a chunk per slot
-  static constexpr int kSlotBytes = kGenChunkBytes / 2;  // [128 rows (its half of N)][64 (K)]
+  // weight ring: a pair member holds ITS half of a chunk per slot ([128 rows][64]); a single CTA whole chunks
+  static constexpr int kSlots = kPair ? 6 : ((H == 512) ? 3 : 4);
+  static constexpr int kSlotBytes = kPair ? kGenChunkBytes / 2 : kGenChunkBytes;
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kABytes;
   static constexpr int kOffBar = kOffW + kSlots * kSlotBytes;
@@ -77,9 +78,13 @@ struct GenSmem {
 constexpr float kGenPhaseScale = 10430.378350470453f;  // 65536 / (2*pi)
 constexpr float kGenPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 
+// kPair = kStash: the training forward runs on CTA pairs (its stash stores and the operand traffic of a lone CTA exceed
+// the shared-memory pipe: 3.10 -> 2.83 ms on cfg4); inference keeps one CTA per tile (the pair's lock step costs it
+// 5-7 %: 2.19 vs 2.35 ms).
 template <int H, int ACT, bool kStash>
 __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdParams p) {
-  using S = GenSmem<H>;
+  constexpr bool kPair = kStash;
+  using S = GenSmem<H, kPair>;
   constexpr int NH = H / 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -104,25 +109,33 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
   const GenDims g = p.g;
   const int L = g.L;
   const int KB0 = g.K0 / 64;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S::kSlots; ++i) {
-      mbar_init(&w_full[i], leader ? 2 : 1);
+      mbar_init(&w_full[i], (kPair && leader) ? 2 : 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_half[0], 2 * kGenEpiWarps);
-    mbar_init(&a_half[1], 2 * kGenEpiWarps);
+    mbar_init(&a_half[0], (kPair ? 2 : 1) * kGenEpiWarps);
+    mbar_init(&a_half[1], (kPair ? 2 : 1) * kGenEpiWarps);
     mbar_init(&a_loc[0], kGenEpiWarps);
     mbar_init(&a_loc[1], kGenEpiWarps);
     mbar_init(d_full, 1);
     mbar_init(a_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  if (warp == 1) {
+    if (kPair)
+      tmem_alloc_2cta<512>(tmem_slot);
+    else
+      tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  if (kPair)
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
@@ -130,8 +143,10 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
   // the last tile (identical values stored twice), so the lock-stepped schedule needs no inactive-tile branches
   const int num_pairs_grid = int(gridDim.x) / 2;
   const int tile_pairs = (p.num_tiles + 1) / 2;
-  const int my_tiles = (tile_pairs - int(blockIdx.x) / 2 + num_pairs_grid - 1) / num_pairs_grid;
+  const int my_tiles = kPair ? (tile_pairs - int(blockIdx.x) / 2 + num_pairs_grid - 1) / num_pairs_grid
+                             : (p.num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   auto tile_of = [&](int t) {
+    if (!kPair) return int(blockIdx.x) + t * int(gridDim.x);
     const int tile = 2 * (int(blockIdx.x) / 2 + t * num_pairs_grid) + int(rank);
     return tile < p.num_tiles ? tile : p.num_tiles - 1;
   };
@@ -148,7 +163,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
           const int nchunks = act_layer ? NH * (l == 0 ? KB0 : S::kKB) : S::kKB;
           const uint8_t* src = act_layer ? p.packed + p.pl.w_layer(g, l) : p.packed + p.pl.wf;
           const uint32_t chunk = act_layer ? uint32_t(kGenChunkBytes) : uint32_t(kOutPad * 128);
-          const uint32_t bytes = chunk / 2;
+          const uint32_t bytes = kPair ? chunk / 2 : chunk;
           for (int j = 0; j < nchunks; ++j, ++c) {
             const uint32_t slot = c % S::kSlots, round = c / S::kSlots;
             if ((B200INR_GKO & 1) && round > 0) continue;
@@ -166,8 +181,9 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
       const uint64_t hi = smem_desc_hi_sw128(0, 1024);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t w_base = smem_u32(w_smem);
-      const uint32_t idesc_h = idesc_bf16(256, 256, false, false);
-      const uint32_t idesc_f = idesc_bf16(256, kOutPad, false, false);
+      constexpr int kM = kPair ? 256 : 128;
+      const uint32_t idesc_h = idesc_bf16(kM, 256, false, false);
+      const uint32_t idesc_f = idesc_bf16(kM, kOutPad, false, false);
       uint32_t c = 0, n = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l <= L + 1; ++l, ++n) {
@@ -190,13 +206,22 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = smem_desc(a_base + kb * S::kABlock + k4 * 32, hi);
                 const uint64_t db = smem_desc(w_base + slot * S::kSlotBytes + k4 * 32, hi);
-                umma_bf16_ss_2cta_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
+                if (kPair)
+                  umma_bf16_ss_2cta_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
+                else
+                  umma_bf16_ss_w(tmem_d + nh * 256, da, db, act_layer ? idesc_h : idesc_f, (kb | k4) != 0);
               }
-              umma_commit_2cta_w(&w_empty[slot]);
+              if (kPair)
+                umma_commit_2cta_w(&w_empty[slot]);
+              else
+                umma_commit_w(&w_empty[slot]);
             }
           }
           if (!second) mbar_wait(&a_half[1], n & 1);  // (every phase of a barrier is consumed by its waiter)
-          umma_commit_2cta_w(d_full);
+          if (kPair)
+            umma_commit_2cta_w(d_full);
+          else
+            umma_commit_w(d_full);
         }
       }
     } else if (lane == 0) {
@@ -427,13 +452,23 @@ __global__ void __launch_bounds__(kGenThreads, 1) gen_fwd_kernel(const GenFwdPar
   }
 
   tc_fence_before();
-  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still address it
-  if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
+  if (kPair) {
+    cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still address it
+    if (warp == 1) tmem_dealloc_2cta<512>(tmem_d);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_d);
+  }
 }
 
 template <int H, int ACT>
-static int launch_gen_fwd_t(const GenFwdParams& p, bool stash, int grid_x, cudaStream_t stream) {
-  const int smem = GenSmem<H>::kBytes + 1024;
+static int launch_gen_fwd_t(const GenFwdParams& p, bool stash, int num_sms, cudaStream_t stream) {
+  const int smem = (stash ? GenSmem<H, true>::kBytes : GenSmem<H, false>::kBytes) + 1024;
+  // training: persistent CTA pairs (clusters of 2) walk tile pairs, an even number of CTAs; inference: one CTA per SM
+  const int tile_pairs = (p.num_tiles + 1) / 2;
+  int grid_x = stash ? 2 * (tile_pairs < num_sms / 2 ? tile_pairs : num_sms / 2)
+                     : (p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  if (stash && grid_x < 2) grid_x = 2;
   void (*kern)(const GenFwdParams) = stash ? gen_fwd_kernel<H, ACT, true> : gen_fwd_kernel<H, ACT, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return B200INR_ERR_CUDA;
@@ -444,7 +479,7 @@ static int launch_gen_fwd_t(const GenFwdParams& p, bool stash, int grid_x, cudaS
   cfg.stream = stream;
   cudaLaunchAttribute at{};
   at.id = cudaLaunchAttributeClusterDimension;
-  at.val.clusterDim.x = 2;
+  at.val.clusterDim.x = stash ? 2 : 1;
   at.val.clusterDim.y = 1;
   at.val.clusterDim.z = 1;
   cfg.attrs = &at;
@@ -486,10 +521,7 @@ int launch_gen_fwd(const b200inr_net* net, const void* packed, const float* coor
   }
   p.lean = (net->flags & B200INR_NET_DGRAD_ONLY) ? 1 : 0;
   p.out_tanh = (net->flags & B200INR_NET_TANH_OUT) ? net->scale_0 : 0.f;
-  // persistent CTA pairs (clusters of 2) walk tile pairs: an even number of CTAs, at most one per SM
-  const int tile_pairs = (p.num_tiles + 1) / 2;
-  int grid_x = 2 * (tile_pairs < num_sms / 2 ? tile_pairs : num_sms / 2);
-  if (grid_x < 2) grid_x = 2;
+  const int grid_x = num_sms;  // (the variant launcher sizes the grid for its schedule)
   const bool sine = net->activation == B200INR_ACT_SINE;
   if (net->activation == B200INR_ACT_TANH)  // the perturbation network: 256-wide operands only
     return launch_gen_fwd_t<256, B200INR_ACT_TANH>(p, stash != nullptr, grid_x, stream);
