@@ -185,13 +185,16 @@ def run_ours(args):
                                       process_group=group)
         return model, sess, lr_host, (r0, r1)
 
-    def timed_steps(sess, steps, warmup):
+    use_graph = os.environ.get("B200INR_BENCH_GRAPH", "1") == "1"
+
+    def timed_steps(sess, steps, warmup, graph=use_graph):
         for _ in range(warmup):
             sess.step()
         sync()
-        # strong-scaled shards are short steps (0.3 ms at N = 8): replay them as CUDA graphs -- possible because the
-        # gradient exchange is inside the optimiser-step kernel, not an NCCL call (one graph per buffer parity)
-        if world > 1 and sess.peer is not None and os.environ.get("B200INR_BENCH_GRAPH", "1") == "1":
+        # the step is replayed as a CUDA graph (FitSession.capture: a step is 4-5 launches whose gaps are 36 us of a
+        # 2.1 ms step on one GPU and a tenth of the 0.3 ms step of a strong-scaled shard at N = 8) -- possible on several
+        # GPUs too because the gradient exchange is inside the optimiser-step kernel, not an NCCL call
+        if graph and sess._graph is None and (world == 1 or sess.peer is not None):
             sess.capture()
             for _ in range(2):
                 sess.step()
@@ -229,8 +232,7 @@ def run_ours(args):
     # ---- per-stage device times (separate pass: an event between two kernels costs a few microseconds of idle GPU)
     rest()
     graphed = sess._graph is not None
-    sess._graph = None  # (eager from here on: stage marks and the staged host targets of the e2e loop)
-    marks = []
+    marks = []  # (a step with marks is issued eagerly: events between the kernels)
     for _ in range(max(5, min(args.steps, 20))):
         marks.append([])
         sess.step(marks[-1])
@@ -278,6 +280,12 @@ def run_ours(args):
     # the device-resident loop once more, AFTER the end-to-end loop: separates what the host copies cost from the drift
     # of a GPU that has been busy for longer (clocks / power state), which both later legs see
     ms_repeat = timed_steps(sess, args.steps, 3) / args.steps if world == 1 else None  # (no rest() before this one)
+    ms_eager = None
+    if world == 1 and graphed:  # the same loop launched kernel by kernel, after a rest like the first leg
+        rest()
+        graphs, sess._graph = sess._graph, None
+        ms_eager = timed_steps(sess, args.steps, 3, graph=False) / args.steps
+        sess._graph = graphs
     sess.finish()
     launches_per_step = sess.kernel_launches_per_step
     piped, n_flat, stash_gb, peer = sess.piped, sess.n_flat, sess.stash.numel() / 1e9, sess.peer is not None
@@ -386,7 +394,9 @@ def run_ours(args):
                    "legs": "value, stage marks, e2e, queries and weak scaling are separate legs (own warm-up + timed "
                            "region) with a 2 s idle gap between them; ms_per_step_after_e2e repeats the first leg "
                            "right after the e2e leg without a gap (power-governor drift)",
-                   "launch": "CUDA-graph replay of the step (one graph per gradient-buffer parity)" if graphed else "eager",
+                   "launch": ("CUDA-graph replay of the step (FitSession.capture(): one graph per gradient-buffer parity "
+                              "and target buffer; ms_per_step_eager = the same loop launched kernel by kernel)")
+                             if graphed else "eager",
                    "e2e": "per step: H2D of this rank's LR slab from pinned host memory (double-buffered, issued on a "
                           "side stream while the previous step computes) + D2H of the loss (read by the host one step "
                           "later, event-synchronised), through FitSession"},
@@ -401,6 +411,7 @@ def run_ours(args):
         "step_frac_of_sustained_peak": step_tflops / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None,
         "stage_ms": stage_ms,
         "ms_per_step_after_e2e": ms_repeat,
+        "ms_per_step_eager": ms_eager,
         "hbm_kernels": hbm,
         "query": query,
         "query_cfg5": query_cfg5,

@@ -97,10 +97,28 @@ constexpr bool kPGroupPh = B200INR_PGPH != 0;
 #define B200INR_PTRACE 0
 #endif
 constexpr bool kPTraceOnly = B200INR_PTRACE != 0;  // tuning build: event trace compiled into the lean kernel
+#ifndef B200INR_PEND
+#define B200INR_PEND 0
+#endif
+constexpr bool kPEndOnly = B200INR_PEND != 0;  // tuning build: the lean kernel records every CTA's total cycle count
 #ifndef B200INR_PPF
 #define B200INR_PPF 0
 #endif
 constexpr int kPPhPrefetch = B200INR_PPF;  // forward tiles of phases pulled into L2 ahead of the bulk copies (0 = off)
+#ifndef B200INR_PADAPT
+#define B200INR_PADAPT 1
+#endif
+// kPAdapt: the pipelines' tile shares follow the speed each pipeline showed in the PREVIOUS launch on the same stash.
+// Pipelines are independent chains with static shares, and they do not run equally fast: with equal shares the
+// per-pipeline finish times of a cfg2 launch spread over 1251 .. 1365 us (the same pipelines slow in every launch -- it
+// follows the SMs a pipeline sits on), so the kernel ran at the pace of its slowest pipeline, 5 % behind the mean.
+// Every pipeline records (tiles, cycles) at its end; the next launch splits the tiles in proportion to tiles / cycles
+// (clamped, validated: anything stale or foreign gives equal shares).  Records live in the unused tail of the stash's
+// profiling area, two banks by launch parity, so a launch never reads what it writes.
+constexpr bool kPAdapt = B200INR_PADAPT != 0;
+constexpr uint32_t kCalMagic = 0xB2001A7Eu;
+constexpr int kCalBankWords = 4 * 32;  // per bank: 32 pipelines x {tiles, cycles, epoch, magic ^ P}
+constexpr int kCalRow = 176;           // first row of the profiling area used (CTAs write rows < grid <= 148)
 #ifndef B200INR_PMC
 #define B200INR_PMC 0
 #endif
@@ -226,6 +244,7 @@ struct PipeParams {
   int dbg;                   // tuning switches (B200INR_BWDP_DBG), 0 in production
   uint32_t* trace;           // nullptr, or the event trace buffer (see TR)
   unsigned long long* prof;  // nullptr, or [grid][kPipeProfSlots] stall-cycle counters (B200INR_BWDP_PROF=1)
+  uint32_t* calib;           // speed records of the previous launch on this stash (see kPAdapt): [epoch, pad x15, 2 banks]
 };
 
 // Stall accounting for pipeline tuning: PW(k, stmt) runs stmt and, when profiling, adds its duration to counter k of
@@ -367,9 +386,9 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
   const int out_edge = edge ? L : layer - 1;  // ring this CTA produces
   const int ph_layer = edge ? L : layer - 1;  // phases needed by the epilogue
 
-  // tiles of this pipeline: forward tiles T = pipe, pipe + P, ...; two 64-row tiles each
-  const int my_fwd = pipe < p.fwd_tiles ? (p.fwd_tiles - pipe + p.pipelines - 1) / p.pipelines : 0;
-  const int n = 2 * my_fwd;
+  uint32_t* share_s = reinterpret_cast<uint32_t*>(smem + S::kBar + 464);  // {first forward tile, count, epoch}
+  static_assert(464 + 12 <= 512, "barrier area layout");
+  const long long t_launch = clock64();
 
   uint8_t* ring_in = p.ring + size_t(pipe * (L + 1) + in_edge) * kPipeRing * kPTile;
   uint8_t* ring_out = p.ring + size_t(pipe * (L + 1) + out_edge) * kPipeRing * kPTile;
@@ -414,11 +433,60 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
     fence_proxy_async_smem();  // one_s is read by the bulk-copy engine
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    // ---- tile shares: pipeline q walks the forward tiles [b_q, b_q+1), b = rounded prefix sums of the pipelines'
+    //      rates.  Every CTA of the grid computes the same boundaries from the same records (same operations in the
+    //      same order), one record per lane.
+    const int P = p.pipelines, N = p.fwd_tiles;
+    uint32_t epoch = 0;
+    bool ok = false;
+    float r = 0.f;
+    if (kPAdapt && p.calib != nullptr && P <= 32) {
+      epoch = __ldcg(p.calib);
+      uint4 e = make_uint4(1u, 1u, epoch, kCalMagic ^ uint32_t(P));
+      if (lane < P) e = __ldcg(reinterpret_cast<const uint4*>(p.calib + 16 + (epoch & 1u) * kCalBankWords) + lane);
+      ok = __all_sync(0xffffffffu, e.w == (kCalMagic ^ uint32_t(P)) && e.z == epoch && e.x > 0u && e.y > 0u);
+      r = float(e.x) / float(e.y);
+    }
+    if (!ok) r = 1.f;
+    if (lane >= P) r = 0.f;
+    auto warp_sum = [](float v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    };
+    const float mean = warp_sum(r) / float(P);
+    if (lane < P) r = fminf(fmaxf(r, 0.8f * mean), 1.25f * mean);  // (a pipeline is never starved or flooded)
+    const float tot = warp_sum(r);
+    float inc = r;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int bnd = (lane >= P - 1) ? N : int(floorf(float(N) * inc / tot + 0.5f));
+    bnd = bnd > N ? N : bnd;
+    int prev = __shfl_up_sync(0xffffffffu, bnd, 1);
+    if (lane == 0) prev = 0;
+    if (P > 32) {  // (more pipelines than lanes: equal contiguous shares)
+      prev = int((long long)N * pipe / P);
+      bnd = int((long long)N * (pipe + 1) / P);
+    }
+    if (lane == (P > 32 ? 0 : pipe)) {
+      share_s[0] = uint32_t(prev);
+      share_s[1] = uint32_t(bnd > prev ? bnd - prev : 0);
+      share_s[2] = epoch;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (kPMc) cluster_sync_all();  // the peer's barriers exist before any multicast copy / remote commit reaches them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // tiles of this pipeline: forward tiles t_first .. t_first + my_fwd - 1; two 64-row tiles each
+  const int t_first = int(share_s[0]);
+  const int my_fwd = int(share_s[1]);
+  const int n = 2 * my_fwd;
   // TMEM columns.  stage: dW^T block [0,256), W'^T half [256,384), chain accumulators 384 + 64 j.
   //               edge : chain accumulators 0 + 64 j, dW_f^T [128,192), dW_0 [192,256).
   const uint32_t t_w = edge ? tmem + 128 : tmem;
@@ -438,7 +506,16 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 
   const bool prof_on = kInstr && p.prof != nullptr;
   const bool trace_on = (kInstr || kPTraceOnly) && p.trace != nullptr && pipe == 0;
-  const long long t_begin = (prof_on || trace_on) ? clock64() : 0;
+  const bool end_on = kPEndOnly && p.prof != nullptr;
+  const long long t_begin = (prof_on || trace_on || end_on) ? clock64() : 0;
+  if (end_on && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[size_t(blockIdx.x) * kPipeProfSlots + 2] = gt;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.prof[size_t(blockIdx.x) * kPipeProfSlots + 4] = smid;
+  }
 
   if (n > 0) {
     if (warp == 0) {
@@ -486,7 +563,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
             // the converter loop is the longest serial loop of the edge CTA)
             const int rs = i % kPRawSlots;
             if (i >= kPRawSlots) mbar_wait(&bars[kBRawEmpty + rs], ((i / kPRawSlots) - 1) & 1);
-            const long long row0 = (long long)(pipe + (i >> 1) * p.pipelines) * 128 + (i & 1) * kPipeTileRows;
+            const long long row0 = (long long)(t_first + (i >> 1)) * 128 + (i & 1) * kPipeTileRows;
             if (row0 + kPipeTileRows <= p.rows) {
               const uint32_t bytes = uint32_t(kPipeTileRows) * p.C * 4;
               mbar_arrive_expect_tx(&bars[kBRawFull + rs], bytes);
@@ -504,9 +581,9 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
           const int round = kPGroupPh ? (i >> 2) : i / nph;
           if (round > 0) PW(0, mbar_wait(&bars[kBPhEmpty + slot], (round - 1) & 1));
           TR(18, i);
-          const int T = pipe + (i >> 1) * p.pipelines;
+          const int T = t_first + (i >> 1);
           if (kPPhPrefetch > 0 && (i & 1) == 0 && (i >> 1) + kPPhPrefetch < my_fwd)
-            bulk_prefetch_l2(p.ph + size_t(ph_layer) * p.layer_stride + size_t(T + kPPhPrefetch * p.pipelines) * kPipePhTile,
+            bulk_prefetch_l2(p.ph + size_t(ph_layer) * p.layer_stride + size_t(T + kPPhPrefetch) * kPipePhTile,
                              kPipePhTile);
           const uint8_t* src = p.ph + size_t(ph_layer) * p.layer_stride + size_t(T) * kPipePhTile +
                                size_t(i & 1) * kPipePhHalf + size_t(h) * kPPhSlot;
@@ -678,7 +755,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       __syncwarp();
       uint32_t k0 = 0;
       auto xa_row = [&](int i, int rr) {  // coordinate record of row lane + 32 rr of tile i
-        const int T = pipe + (i >> 1) * p.pipelines;
+        const int T = t_first + (i >> 1);
         return p.xa + (size_t(T) * 128 + size_t(i & 1) * kPipeTileRows + lane + 32 * rr);
       };
       uint4 xv0 = __ldg(xa_row(0, 0)), xv1 = __ldg(xa_row(0, 1));
@@ -754,7 +831,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
           if (t == 0) TR(20, j);
           if (j >= kPDobSlots) mbar_wait(&bars[kBDobEmpty + bs], ((j / kPDobSlots) - 1) & 1);
           if (t == 0) TR(21, j);
-          const int T = pipe + (j >> 1) * p.pipelines;
+          const int T = t_first + (j >> 1);
           const long long row0 = (long long)T * 128 + (j & 1) * kPipeTileRows;
           float gv[kOutPad];
           if (row0 + kPipeTileRows <= p.rows) {
@@ -821,21 +898,26 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
         // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
         if (cg == 0) {
           const uint8_t* src = p.packed + p.pl.wht + size_t(layer - 1) * 256 * 256 * 2 + size_t(h * 128 + f) * 128;
+          // (two K blocks = 16 independent 16-byte loads per round trip to L2: the pipeline cannot start before this
+          //  operand is in place, and one block at a time was eight serialised L2 latencies)
 #pragma unroll 1
-          for (int kb = 0; kb < 4; ++kb) {
+          for (int kb2 = 0; kb2 < 4; kb2 += 2) {
+            uint4 v[16];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int j = 0; j < 16; ++j)
+              v[j] = __ldg(reinterpret_cast<const uint4*>(src + size_t(kb2 + (j >> 3)) * 256 * 128 +
+                                                          (((j & 7) ^ (f & 7)) << 4)));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {  // q4 = (K block, half) of this round
               uint32_t w[16];
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const int ch = hh * 4 + c;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + size_t(kb) * 256 * 128 + ((ch ^ (f & 7)) << 4)));
-                w[4 * c] = v.x;
-                w[4 * c + 1] = v.y;
-                w[4 * c + 2] = v.z;
-                w[4 * c + 3] = v.w;
+                w[4 * c] = v[4 * q4 + c].x;
+                w[4 * c + 1] = v[4 * q4 + c].y;
+                w[4 * c + 2] = v[4 * q4 + c].z;
+                w[4 * c + 3] = v[4 * q4 + c].w;
               }
-              tmem_st16(t_wt + t_lane + kb * 32 + hh * 16, w);
+              tmem_st16(t_wt + t_lane + (kb2 + (q4 >> 1)) * 32 + (q4 & 1) * 16, w);
             }
           }
           tmem_st_wait();
@@ -942,6 +1024,8 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
         if (tr_me) TR(16, i);
         if (prof_on) pw[8] += (unsigned long long)(clock64() - ts0);
       }
+      if (end_on && threadIdx.x == kPFirstEpiWarp * 32)  // tile loop done, flush not started
+        p.prof[size_t(blockIdx.x) * kPipeProfSlots + 1] = (unsigned long long)(clock64() - t_begin);
       if (threadIdx.x == kPFirstEpiWarp * 32) {
         PW_FLUSH(11, 7);
         if (prof_on) {
@@ -1010,7 +1094,21 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
   __syncthreads();
   if (kPMc) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc<512>(tmem);
-  if (prof_on && threadIdx.x == 0) {
+  if (kPAdapt && p.calib != nullptr && role == 0 && threadIdx.x == 0 && p.pipelines <= 32) {
+    // this pipeline's record for the next launch (the edge CTA holds both ends of the chain: it is the last to finish)
+    const uint32_t epoch = share_s[2] + 1u;
+    const long long cyc = clock64() - t_launch;
+    __stcg(reinterpret_cast<uint4*>(p.calib + 16 + (epoch & 1u) * kCalBankWords) + pipe,
+           make_uint4(uint32_t(my_fwd), uint32_t(cyc > 0xffffffffLL ? 0xffffffffLL : cyc), epoch,
+                      kCalMagic ^ uint32_t(p.pipelines)));
+    if (pipe == 0) __stcg(p.calib, epoch);
+  }
+  if (end_on && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[size_t(blockIdx.x) * kPipeProfSlots + 3] = gt;
+  }
+  if ((prof_on || end_on) && threadIdx.x == 0) {
     p.prof[size_t(blockIdx.x) * kPipeProfSlots + 0] = (unsigned long long)(clock64() - t_begin);
     p.prof[size_t(blockIdx.x) * kPipeProfSlots + 21] = (unsigned long long)n;
   }
@@ -1041,6 +1139,8 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.xa = reinterpret_cast<const uint4*>(st + sl.xa);
   p.ring = st + sl.ring;
   p.flags = reinterpret_cast<uint32_t*>(st + sl.flags);
+  p.calib = reinterpret_cast<uint32_t*>(st + sl.prof + size_t(kCalRow) * kPipeProfSlots * 8);
+  static_assert((kCalRow + 16) <= kPipeProfCtas && (16 + 2 * kCalBankWords) * 4 <= 16 * kPipeProfSlots * 8, "calibration area");
   p.grads = grad_params;
   int64_t off[2 * (kMaxSineLayers + 2)];
   param_offsets(p.d, p.Hr, L, p.C, off);
@@ -1114,7 +1214,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   cfg.numAttrs = 1;
   cudaError_t e;
 #if B200INR_TUNING
-  if (p.prof != nullptr || (p.trace != nullptr && !kPTraceOnly) || p.dbg != 0) {
+  if ((p.prof != nullptr && !kPEndOnly) || (p.trace != nullptr && !kPTraceOnly) || p.dbg != 0) {
     if (cudaFuncSetAttribute(siren_bwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200INR_ERR_CUDA;
     e = cudaLaunchKernelEx(&cfg, siren_bwdp_kernel<true>, p);

@@ -575,8 +575,8 @@ class _FusedMLP(nn.Module):
                              global_count=global_count, process_group=process_group, reset_optimizer=reset_optimizer,
                              weight=weight)
         losses = torch.zeros(steps, dtype=torch.float32, device=session.device)
-        if graph is None:  # small per-step work is launch-latency bound: replay the step as one CUDA graph
-            graph = process_group is None and steps >= 16 and session.rows <= (1 << 18)
+        if graph is None:  # replay the step as one CUDA graph: the launch gaps are a third of a cfg1 step and still
+            graph = process_group is None and steps >= 16  # 1.7 % of a cfg2 step (2.10 -> 2.06 ms)
         done = 0
         if graph:
             losses[0:1].copy_(session.step())  # one eager step (lazy initialisation, allocator warm-up)
@@ -1063,36 +1063,42 @@ class FitSession:
         self._copy_stream = None
 
     def capture(self):
-        """Capture one step (every kernel is stream-ordered, Adam's step counter lives on the device) into a CUDA
-        graph; later step() calls replay it.  Not used with a process group (the all-reduce stays eager)."""
+        """Capture one step (every kernel is stream-ordered, Adam's step counter lives on the device) into CUDA graphs;
+        later step() calls replay them.  One graph per (gradient-buffer parity, target buffer): the multi-GPU step
+        alternates two gradient buffers, and stage_target() / commit_target() alternate two target buffers, so a new
+        combination is captured the first time step() meets it.  Not available when the gradient exchange is an NCCL
+        call or the step exchanges halo planes (both stay eager)."""
         if self.process_group is not None and self.peer is None:
             raise RuntimeError("b200inr: graph capture of a multi-GPU step needs the in-kernel gradient exchange "
                                "(the NCCL all-reduce stays eager)")
         if getattr(self, "halo", None) is not None:
             raise RuntimeError("b200inr: a sharded blur_pool step exchanges halo planes with NCCL send/recv and stays "
                                "eager")
+        self._graph = {}
+        self._capture_current()
+
+    def _capture_current(self):
+        tkey = self.target.data_ptr()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             if self.peer is None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step_eager(None)
-                self._graph = g
+                self._graph[(0, tkey)] = g
             else:
                 # the two gradient buffers alternate: one graph per parity (every rank captures and replays the same
                 # sequence, so the kernels' start barriers keep meeting; the epoch counter lives on the device)
                 start = self._parity
-                graphs = {}
                 for _ in range(2):
                     par = self._parity
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._step_eager(None)  # (toggles self._parity on the host)
-                    graphs[par] = g
+                    self._graph[(par, tkey)] = g
                 self._parity = start
                 self.grads = self.peer.grads[start]
                 self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
-                self._graph = graphs
 
     def set_target(self, target):
         """Replace the target values (same size), e.g. from pinned host memory."""
@@ -1107,8 +1113,6 @@ class FitSession:
                 self._target_back = torch.empty_like(self.target)
                 self._copy_done = torch.cuda.Event()
                 self._steps_done = torch.cuda.Event()
-            if self._graph is not None:
-                raise RuntimeError("b200inr: staged targets cannot be combined with a captured step graph")
             # the back buffer was the target of the step before last: every step issued so far must be done with it
             self._steps_done.record(torch.cuda.current_stream())
             self._copy_stream.wait_event(self._steps_done)
@@ -1124,13 +1128,14 @@ class FitSession:
 
     def step(self, marks=None):
         if self._graph is not None and marks is None:
-            if isinstance(self._graph, dict):  # multi-GPU: one graph per gradient-buffer parity
-                self._graph[self._parity].replay()
+            key = (self._parity if self.peer is not None else 0, self.target.data_ptr())
+            if key not in self._graph:  # a target buffer this session has not stepped on yet
+                self._capture_current()
+            self._graph[key].replay()
+            if self.peer is not None:  # multi-GPU: the gradient buffers alternate
                 self._parity ^= 1
                 self.grads = self.peer.grads[self._parity]
                 self.loss_acc = self.grads[self.n_flat:self.n_flat + 1]
-            else:
-                self._graph.replay()
             return self.loss
         return self._step_eager(marks)
 

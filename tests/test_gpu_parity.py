@@ -924,10 +924,12 @@ def test_staged_host_targets_equal_direct_upload(dev):
     host = [torch.rand(shape[0] // 2 * shape[1] // 2 * shape[2] * C, generator=torch.Generator().manual_seed(k)).pin_memory()
             for k in range(3)]
     res = []
-    for staged in (False, True):
+    for staged, graph in ((False, False), (True, False), (True, True)):
         torch.manual_seed(21)
         m = b200inr.Siren(3, 256, 4, C).to(dev)
         sess = b200inr.FitSession(m, host[0].to(dev), shape, lr=1e-4, degrade="pool")
+        if graph:  # one CUDA graph per target buffer: the second one is captured when step() first meets it
+            sess.capture()
         losses = []
         if staged:
             sess.stage_target(host[0])
@@ -939,8 +941,11 @@ def test_staged_host_targets_equal_direct_upload(dev):
             else:
                 sess.set_target(host[i % 3])
             losses.append(float(sess.step().item()))
+        if graph:
+            assert len(sess._graph) == 2
         res.append(losses)
     np.testing.assert_allclose(res[1], res[0], rtol=2e-3)
+    np.testing.assert_allclose(res[2], res[0], rtol=2e-3)
 
 
 @pytest.mark.parametrize("d,Lh,C,rows", [(3, 1, 4, 1), (3, 3, 31, 65), (2, 7, 3, 129), (3, 5, 32, 1000), (1, 2, 1, 64),

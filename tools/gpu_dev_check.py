@@ -296,12 +296,64 @@ def bwdp_profile():
              12: "ep:ph_full", 13: "ep:y_empty", 14: "ep:acc_full", 15: "ep:stg_empty", 16: "ep:sin", 17: "ep:cos",
              18: "bot:z_empty", 19: "bot:poll", 20: "bot:z_full", 21: "tiles", 22: "ld:fence_proxy", 23: "-",
              24: "-", 25: "mma:credit", 26: "bot:issue", 27: "bot:mma", 28: "ep:dout", 29: "ep:loop", 30: "ep:fence"}
+    # do the pipelines (static tile shares) finish together?  total cycles of every CTA, max over a pipeline's CTAs
+    tot = prof[:P * S2, 0].reshape(P, S2)
+    print("bwdp per-pipeline total kcycles (max over its CTAs): " + " ".join(f"{v / 1e3:.0f}" for v in tot.max(axis=1)))
+    print("bwdp per-role total kcycles (mean over pipelines): " + " ".join(f"{v / 1e3:.0f}" for v in tot.mean(axis=0)))
     print(f"bwdp profile: {P} pipelines x {S2} CTAs; cycles PER TILE, mean over pipelines (role = stage, half)")
     for role in range(S2):
         rowsel = prof[[pp * S2 + role for pp in range(P)]]
         n = rowsel[:, 21].mean()
         txt = " ".join(f"{names[k]}={rowsel[:, k].mean() / max(n, 1):.0f}" for k in list(range(21)) + list(range(22, 31)) if rowsel[:, k].mean() > 0)
         print(f"  role {role} (stage {role // 2}, h {role % 2}) tiles={n:.0f}: {txt}", flush=True)
+
+
+def bwdp_ends(rows_x=128):
+    """Per-CTA start / tile-loop end / kernel end of the LEAN pipelined backward (build with -DB200INR_TUNING=1
+    -DB200INR_PEND=1): do the statically scheduled pipelines finish together, and how long is the gradient flush?"""
+    import numpy as np
+    os.environ["B200INR_BWDP_PROF"] = "1"
+    d, Lh, C, H = 3, 4, 31, 256
+    shape = (rows_x, 128, 64)
+    rows = rows_x * 128 * 64
+    net = L.make_net(d, H, Lh, C, flags=0)
+    m = RefSiren(d, H, Lh, C).to(dev)
+    flat, off = flat_params(net, m)
+    packed = torch.zeros(L.packed_bytes(net) + 1024, dtype=torch.uint8, device=dev)
+    pk = packed[(-packed.data_ptr()) % 1024:]
+    L.check(lib.b200inr_pack_weights(ctypes.byref(net), ptr(flat), ptr(pk), stream()), "pack")
+    grid = L.make_grid(shape)
+    out = torch.zeros(rows, C, device=dev)
+    gout = torch.randn(rows, C, device=dev) * 1e-6
+    gflat = torch.zeros_like(flat)
+    nbytes = L.stash_bytes(net, rows)
+    stash = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
+    st = stash[(-stash.data_ptr()) % 1024:][:nbytes]
+    g, nb = ctypes.byref(grid), ctypes.byref(net)
+    L.check(lib.b200inr_siren_forward(nb, ptr(pk), None, g, rows, ptr(out), 0, 0.0, ptr(st), stream()), "fwd")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(6):
+        e0.record()
+        L.check(lib.b200inr_siren_backward(nb, ptr(pk), ptr(st), None, g, rows, ptr(gout), ptr(gflat), stream()), "bwd")
+        e1.record()
+        torch.cuda.synchronize()
+    os.environ["B200INR_BWDP_PROF"] = "0"
+    prof = st[nbytes - 192 * 32 * 8:].view(torch.int64).reshape(192, 32).cpu().numpy().astype(np.float64)
+    S2 = 2 * (Lh + 1)
+    P = 148 // S2
+    pr = prof[:P * S2].reshape(P, S2, 32)
+    t0 = pr[:, :, 2].min()
+    print(f"bwdp ends ({rows} rows): kernel {e0.elapsed_time(e1) * 1e3:.0f} us by events; CTA start spread "
+          f"{(pr[:, :, 2].max() - t0) / 1e3:.1f} us; last CTA end {(pr[:, :, 3].max() - t0) / 1e3:.1f} us")
+    print("  per pipeline: end of the slowest CTA (us after the first start): " +
+          " ".join(f"{v:.0f}" for v in (pr[:, :, 3].max(axis=1) - t0) / 1e3))
+    print("  per role, mean over pipelines: end (us) " + " ".join(f"{v:.0f}" for v in (pr[:, :, 3].mean(axis=0) - t0) / 1e3))
+    print("  per role: tile loop kcycles " + " ".join(f"{v:.0f}" for v in pr[:, :, 1].mean(axis=0) / 1e3) +
+          " | total kcycles " + " ".join(f"{v:.0f}" for v in pr[:, :, 0].mean(axis=0) / 1e3))
+    print("  per pipeline: 64-row tiles " + " ".join(f"{v:.0f}" for v in pr[:, 0, 21]))
+    print("  SM ids per pipeline: " + " | ".join(",".join(f"{int(v)}" for v in pr[q, :, 4]) for q in range(P)))
+    print("  per pipeline: total kcycles of role 0 " + " ".join(f"{v:.0f}" for v in pr[:, 0, 0] / 1e3))
+    print("  per pipeline: tile-loop kcycles of the last stage (role S2-2) " + " ".join(f"{v:.0f}" for v in pr[:, S2 - 2, 1] / 1e3))
 
 
 def bwdp_trace():
@@ -443,6 +495,10 @@ if __name__ == "__main__":
         piped_vs_staged(3, 0, 5, (16, 16, 8))
     if "prof" in which:
         bwdp_profile()
+    if "ends" in which:
+        bwdp_ends()
+        bwdp_ends(16)
+        bwdp_ends(1)
     if "trace" in which:
         bwdp_trace()
     if "fwd_trace" in which:
