@@ -92,7 +92,12 @@ constexpr int kPipeTileRows = 64;    // rows per pipeline tile (half a forward t
 constexpr int kPipePhChunk = kPipeTileRows * 16 + 32;                 // 1056 bytes
 constexpr int kPipePhHalf = (kSirenWidth / 8) * kPipePhChunk;        // 64 rows x 256 features: 33 792 bytes
 constexpr int kPipePhTile = 2 * kPipePhHalf;                         // one 128-row forward tile: 67 584 bytes
-constexpr int kPipeRing = 8;         // ring depth, in tiles, per layer boundary
+#ifndef B200INR_PRING
+#define B200INR_PRING 10
+#endif
+// ring depth, in tiles, per layer boundary: 4 / 6 / 8 / 10 / 12 / 16 slots give a cfg2 backward of 1.40 / 1.33 / 1.29 /
+// 1.27 / 1.27 / 1.36 ms (a ring has to absorb the jitter of its two ends; 16 costs more L2 than it buys)
+constexpr int kPipeRing = B200INR_PRING;
 constexpr int kPipeMaxEdges = 96;    // pipelines x (L+1) <= #SM / 2
 struct PipeStashLayout {
   size_t ph;            // (L+1) x T x kPipePhTile bytes (see above)
