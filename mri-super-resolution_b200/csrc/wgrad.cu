@@ -255,7 +255,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgParams p) 
 // it to its partner, consumers releasing a slot on the `empty` barriers of all CTAs that copy into it -- bit-identical
 // results, but 5.0 ms on cfg4 (B pairs only: 3.6 ms; the cluster launch alone, without sharing: 3.1 ms, fewer
 // co-resident CTAs): with 32-row stages the cross-CTA release -> copy -> full round trip exceeds the six-stage ring.
+#ifndef B200INR_WG_WAVES
+#define B200INR_WG_WAVES 3
+#endif
 static int launch_items(WgParams& p, const double* weight, const int* group, int num_sms, cudaStream_t stream) {
+  // kWaves > 1: the row range of every item is cut kWaves times finer than the SMs need, and the hardware's block
+  // scheduler hands the next block to whichever SM finishes first (one CTA fits per SM: all 512 TMEM columns).
+  // With one block per SM the SMs were idle for 18 % of the kernel (ncu: active / elapsed cycles 0.82 -- blocks of
+  // different items, and of the same item on different SMs, do not run equally fast); 1 / 2 / 3 / 4 waves:
+  // cfg4 2.61 / 2.50 / 2.37 / 2.38 ms, WIRE 1.36 / 1.25 / 1.19 / 1.20 ms (at 3 the kernel reads its 13.8 GB at 89 % of
+  // the HBM peak).
+  constexpr int kWaves = B200INR_WG_WAVES;
+  num_sms *= kWaves;
   double total = 0.0;
   for (int i = 0; i < p.num_items; ++i) total += weight[i];
   int count[kWgMaxItems];
