@@ -948,6 +948,49 @@ def test_staged_host_targets_equal_direct_upload(dev):
     np.testing.assert_allclose(res[2], res[0], rtol=2e-3)
 
 
+def test_pipelined_backward_adaptive_shares(dev):
+    """The pipelined backward cuts the tile range between its layer pipelines by the speed each one showed in the
+    previous launch on the same stash (records in the tail of the stash's profiling area).  Repeated launches -- every
+    one with different shares -- give the first launch's gradients up to the summation order, and records that are
+    garbage, stale or absurd fall back to equal / clamped shares instead of breaking the kernel."""
+    torch.manual_seed(9)
+    shape = (64, 64, 32)
+    rows = int(np.prod(shape))
+    m = _set_backward_path(b200inr.Siren(3, 256, 4, 31).to(dev), True)
+    grid = L.make_grid(shape)
+    gout = torch.randn(rows, 31, device=dev) / (rows * 31)
+    out, stash = m._forward_rows(None, grid, rows, train=True)
+    nbytes = L.stash_bytes(m._desc, rows)
+    cal = stash[:nbytes][nbytes - 192 * 32 * 8 + 176 * 32 * 8:].view(torch.int32)  # [epoch, pad x15, 2 banks x 32 x 4]
+    cal.zero_()  # (a module-level stash is uninitialised memory; FitSession's is zeroed)
+    ref = m._backward_rows(stash, None, grid, rows, gout).clone()
+    assert int(cal[0].item()) == 1  # the first launch (equal shares) has left its records
+    epochs = [1]
+    for _ in range(4):
+        g = m._backward_rows(stash, None, grid, rows, gout)
+        assert _relerr(g.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+        epochs.append(int(cal[0].item()))
+    assert epochs == [1, 2, 3, 4, 5]
+    bank = cal[16 + (epochs[-1] & 1) * 128:16 + (epochs[-1] & 1) * 128 + 128].view(32, 4)
+    P = 148 // 10 if torch.cuda.get_device_properties(dev).multi_processor_count >= 148 else None
+    if P is not None:
+        tiles = bank[:P, 0].cpu().numpy()
+        assert tiles.sum() == (rows + 127) // 128 and tiles.min() >= 1
+        assert (bank[:P, 2].cpu().numpy() == epochs[-1]).all()
+    # garbage records
+    cal[16:].random_(0, 2 ** 31 - 1)
+    g = m._backward_rows(stash, None, grid, rows, gout)
+    assert _relerr(g.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+    # valid-looking records that claim a 1000 x speed difference: clamped, every pipeline keeps tiles
+    ep = int(cal[0].item())
+    bank = cal[16 + (ep & 1) * 128:16 + (ep & 1) * 128 + 128].view(32, 4)
+    bank[0, 1] = 1
+    bank[1, 1] = 2 ** 30
+    g = m._backward_rows(stash, None, grid, rows, gout)
+    assert _relerr(g.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("d,Lh,C,rows", [(3, 1, 4, 1), (3, 3, 31, 65), (2, 7, 3, 129), (3, 5, 32, 1000), (1, 2, 1, 64),
                                           (4, 4, 17, 20000)])
 def test_pipelined_backward_shapes_vs_oracle(dev, d, Lh, C, rows):
