@@ -396,6 +396,11 @@ def bwdp_trace():
         seg = t[role, 100:200, :]
         line = " ".join(f"{names[e]}={np.mean(seg[:, e] - seg[:, ref]):+.0f}" for e in range(23) if seg[:, e].all())
         print(f"role {role:2d}: period {(t[role, 200, 16] - t[role, 100, 16]) / 100:.0f} clk | {line}")
+    # start-up: absolute times (cycles since the kernel's start) of the first tiles of every stage
+    for role in range(0, S2, 2):
+        for tile in range(0, 3):
+            print(f"  start-up role {role} tile {tile}: " + " ".join(f"{names[e]}={t[role, tile, e]}" for e in range(23)
+                                                                      if t[role, tile, e] != 0))
     for role in (0, 2, 4, 8):
         print(f"role {role}: tile period (ep:arrived, tiles 100..200) = {(t[role, 200, 16] - t[role, 100, 16]) / 100:.0f} clk")
         for tile in range(100, 103):
