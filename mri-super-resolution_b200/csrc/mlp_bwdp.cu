@@ -80,7 +80,7 @@ constexpr int kPWgradWarp = kPFirstCvtWarp + kPCvtWarps;      // 22
 #endif
 // tuning aid, never set in production builds: knock out one resource at a time (results are garbage) to see what the
 // tile period is made of.  1 = no sin / cos, 2 = one chain MMA instead of 16, 4 = one weight-gradient MMA instead of 4,
-// 8 = no phase loads, 16 = ring loads of half a tile.
+// 8 = no phase loads, 16 = ring loads of half a tile, 32 = no dOut conversion.
 constexpr int kPKo = B200INR_PKO;
 #ifndef B200INR_PGPH
 #define B200INR_PGPH 1
@@ -835,7 +835,10 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
           const int T = t_first + (j >> 1);
           const long long row0 = (long long)T * 128 + (j & 1) * kPipeTileRows;
           float gv[kOutPad];
-          if (row0 + kPipeTileRows <= p.rows) {
+          if (kPKo & 32) {  // knock-out: no conversion work (the barriers still cycle)
+#pragma unroll
+            for (int c = 0; c < kOutPad; ++c) gv[c] = 0.f;
+          } else if (row0 + kPipeTileRows <= p.rows) {
             const uint32_t src = sbase + E::kRaw + rs * kPRawSlot + uint32_t(t * C) * 4;
 #pragma unroll
             for (int c = 0; c < kOutPad; ++c) gv[c] = (c < C) ? __uint_as_float(lds32(src + c * 4)) : 0.f;
@@ -848,7 +851,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 #pragma unroll
           for (int c = 0; c < kOutPad; ++c) dbf[c] += gv[c];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
+          for (int ch = 0; ch < ((kPKo & 32) ? 0 : 4); ++ch)
             sts128(sbase + E::kDob + bs * kPBlk + sw128_chunk_off(t, ch),
                    make_uint4(pack_bf16x2(gv[8 * ch], gv[8 * ch + 1]), pack_bf16x2(gv[8 * ch + 2], gv[8 * ch + 3]),
                               pack_bf16x2(gv[8 * ch + 4], gv[8 * ch + 5]), pack_bf16x2(gv[8 * ch + 6], gv[8 * ch + 7])));
