@@ -385,7 +385,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "global_grid": list(gshape), "rows_per_gpu": rows,
                    "parallelism": f"x-plane slabs x{world} of the fixed volume ({gshape[0] // world} planes per GPU), "
                                   f"weights replicated; gradient exchange: {exchange}",
-                   "l2": f"per-step working set (phase stash {stash_gb:.2f} GB/GPU) exceeds the 126 MB L2; no flush needed"
+                   "l2": f"per-step working set (phase stash: {stash_gb:.2f} GB/GPU allocated, 4/5 of it written and read "
+                         "per step) exceeds the 126 MB L2; no flush needed"
                          if stash_gb > 0.2 else
                          f"per-step working set {stash_gb * 1e3:.0f} MB/GPU of phase stash + 2 x {rows * C_OUT * 4 / 1e6:.0f} MB "
                          "of prediction / gradient rows, rewritten every step",

@@ -99,6 +99,13 @@ constexpr int kPipePhTile = 2 * kPipePhHalf;                         // one 128-
 // 1.27 / 1.27 / 1.36 ms (a ring has to absorb the jitter of its two ends; 16 costs more L2 than it buys)
 constexpr int kPipeRing = B200INR_PRING;
 constexpr int kPipeMaxEdges = 96;    // pipelines x (L+1) <= #SM / 2
+// Networks with at least one hidden layer do not stash the phases of layer 0: theta_0 = w' x' + b' is three FMAs per
+// element from the fp32 coordinate records the forward leaves in the first 16 bytes per row of the layer-0 phase region
+// (the other layers' phases would need their whole GEMM again).  A fifth of the stash traffic of both directions.
+#ifndef B200INR_PSKIP0
+#define B200INR_PSKIP0 1
+#endif
+constexpr bool kPipeSkipPh0 = B200INR_PSKIP0 != 0;
 struct PipeStashLayout {
   size_t ph;            // (L+1) x T x kPipePhTile bytes (see above)
   size_t layer_stride;  // bytes per layer inside ph

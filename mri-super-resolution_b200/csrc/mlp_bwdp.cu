@@ -245,6 +245,7 @@ struct PipeParams {
   int dbg;                   // tuning switches (B200INR_BWDP_DBG), 0 in production
   uint32_t* trace;           // nullptr, or the event trace buffer (see TR)
   unsigned long long* prof;  // nullptr, or [grid][kPipeProfSlots] stall-cycle counters (B200INR_BWDP_PROF=1)
+  int skip_ph0;              // kPipeSkipPh0 and L >= 1: layer-0 phases are recomputed from fp32 coordinate records
   uint32_t* calib;           // speed records of the previous launch on this stash (see kPAdapt): [epoch, pad x15, 2 banks]
 };
 
@@ -592,6 +593,14 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
             mbar_arrive(&bars[kBPhFull + slot]);
             continue;
           }
+          if (!edge && ph_layer == 0 && p.skip_ph0) {
+            // layer 0 is not stashed: the tile's 64 coordinate records (fp32 x4, 1 KB) instead of 16.5 KB of phases
+            mbar_arrive_expect_tx(&bars[kBPhFull + slot], kPipeTileRows * 16);
+            bulk_g2s(smem + oPh + slot * kPPhSlot, p.ph + (size_t(T) * 128 + size_t(i & 1) * kPipeTileRows) * 16,
+                     kPipeTileRows * 16, &bars[kBPhFull + slot]);
+            TR(17, i);
+            continue;
+          }
           // one copy: the forward stores the 16 chunks of a feature half contiguously, padding included
           mbar_arrive_expect_tx(&bars[kBPhFull + slot], kPPhSlot);
           bulk_g2s(smem + oPh + slot * kPPhSlot, src, kPPhSlot, &bars[kBPhFull + slot]);
@@ -897,6 +906,23 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       float dbsum = 0.f;
       // ReLU-tail network: the top activated layer (whose stash the edge CTAs read) is Linear + ReLU
       const bool relu_top = kRelu && edge;
+      // layer 0 not stashed (kPipeSkipPh0): the CTAs of layer 1 recompute theta_0[f][row] = w' x' + b' from the row's
+      // coordinate record.  w', b' = bf16 hi + bf16 lo of omega_0 W_0 / omega_0 b_0, the operand pack.cu builds for the
+      // forward's first-layer MMA, so that the angle is the forward's (to fp32 rounding).
+      const bool l0x = !edge && ph_layer == 0 && p.skip_ph0 != 0;
+      float w0x = 0.f, w0y = 0.f, w0z = 0.f, w0w = 0.f, b0x = 0.f;
+      if (l0x) {
+        auto hilo = [](float v) {
+          const float hi = __bfloat162float(__float2bfloat16_rn(v));
+          return hi + __bfloat162float(__float2bfloat16_rn(v - hi));
+        };
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.packed + p.pl.w0) + (h * 128 + f));
+        w0x = hilo(w.x);
+        w0y = hilo(w.y);
+        w0z = hilo(w.z);
+        w0w = hilo(w.w);
+        b0x = hilo(__ldg(reinterpret_cast<const float*>(p.packed + p.pl.bias) + (h * 128 + f)));
+      }
 
       if (!edge) {
         // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
@@ -971,15 +997,29 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 #pragma unroll
         for (int b2 = 0; b2 < 2; ++b2) {
           uint32_t ph[16], ys[8], ds[8];
+          float rd[16];
+          if (l0x) {  // (one uniform branch per batch of 16 rows: every CTA runs one side only)
+            const uint32_t xr = sbase + oPh + ps * kPPhSlot + (rh * 32 + 16 * b2) * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 * b2 + j) * 16);
+            for (int j = 0; j < 16; ++j) {
+              const uint4 x = lds128(xr + j * 16);
+              rd[j] = fmaf(w0w, __uint_as_float(x.w),
+                           fmaf(w0z, __uint_as_float(x.z),
+                                fmaf(w0y, __uint_as_float(x.y), fmaf(w0x, __uint_as_float(x.x), b0x))));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 * b2 + j) * 16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rd[j] = rad_lo16(ph[j]);
+          }
           if (b2 == 1) {  // all phases are in registers: hand the slot back
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kBPhEmpty + ps]);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float r0 = rad_lo16(ph[2 * j]), r1 = rad_lo16(ph[2 * j + 1]);
+            const float r0 = rd[2 * j], r1 = rd[2 * j + 1];
             if (kPKo & 1) {
               const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * r0, d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * r1;
               dbsum += d0 + d1;
@@ -1145,6 +1185,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.flags = reinterpret_cast<uint32_t*>(st + sl.flags);
   p.calib = reinterpret_cast<uint32_t*>(st + sl.prof + size_t(kCalRow) * kPipeProfSlots * 8);
   static_assert((kCalRow + 16) <= kPipeProfCtas && (16 + 2 * kCalBankWords) * 4 <= 16 * kPipeProfSlots * 8, "calibration area");
+  p.skip_ph0 = (kPipeSkipPh0 && L >= 1) ? 1 : 0;
   p.grads = grad_params;
   int64_t off[2 * (kMaxSineLayers + 2)];
   param_offsets(p.d, p.Hr, L, p.C, off);

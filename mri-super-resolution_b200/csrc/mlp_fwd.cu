@@ -73,6 +73,7 @@ struct FwdParams {
   uint8_t* stash_y;   // nullptr => inference
   uint8_t* stash_ph;
   uint8_t* stash_xa;  // coordinate operand of the first-layer weight gradient (wgrad.cu)
+  int skip_ph0;       // pipelined training, L >= 1: layer-0 phases are recomputed by the backward (kPipeSkipPh0)
   size_t stash_layer_stride;
   uint32_t* trace;  // tuning aid (B200INR_FWD_TRACE_PTR): CTA 0 records [phase][8] event times, phase = (pair, layer, tile)
 };
@@ -98,7 +99,8 @@ constexpr float kPhaseMagic = 12582912.0f;          // 1.5 * 2^23
 // holds the bf16 OUTPUT instead of a phase (the backward needs y and the mask y > 0, not an angle).
 template <bool kStash, int kChunkStride = kTileRows * 16, bool kReluNet = false>
 __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_block_addr, int r, int s,
-                                            uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r */,
+                                            uint8_t* ph_chunk0 /* chunk (kb*8 + 2s) of the phase tile, row r; nullptr:
+                                                                  this layer's phases are not stashed */,
                                             bool relu = false) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -118,7 +120,7 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
     for (int j = 0; j < 4; ++j) {
       const float t0 = th[c * 8 + 2 * j], t1 = th[c * 8 + 2 * j + 1];
       yb[j] = (B200INR_FKO & 2) ? pack_bf16x2(t0, t1) : pack_bf16x2(__sinf(t0), __sinf(t1));
-      if (kStash) {
+      if (kStash && ph_chunk0 != nullptr) {
         float p0, p1;
         fma_f32x2(t0, t1, kPhaseScale, kPhaseMagic, p0, p1);
         ph[j] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x5410);
@@ -126,7 +128,7 @@ __device__ __forceinline__ void emit_sine16(const float (&th)[16], uint32_t a_bl
     }
     if (!(B200INR_FKO & 4) || yb[0] == 0x12345678u)
       sts128(a_block_addr + sw128_chunk_off(r, 2 * s + c), make_uint4(yb[0], yb[1], yb[2], yb[3]));
-    if (kStash)
+    if (kStash && ph_chunk0 != nullptr)
       __stcs(reinterpret_cast<uint4*>(ph_chunk0 + size_t(c) * kChunkStride), make_uint4(ph[0], ph[1], ph[2], ph[3]));
   }
 }
@@ -468,8 +470,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         sts128(a_addr + sw128_chunk_off(r, 1), make_uint4(l01, l23, l01, l23));
         sts128(a_addr + sw128_chunk_off(r, 2), make_uint4(0x3F803F80u, 0u, 0u, 0u));  // {1, 1}: the bias columns
         sts128(a_addr + sw128_chunk_off(r, 3), make_uint4(0u, 0u, 0u, 0u));
-        if (kMode == 2)  // pipelined training: compact coordinate record {hi x4, lo x4} per row (operand of dW_0)
+        if (kMode == 2) {  // pipelined training: compact coordinate record {hi x4, lo x4} per row (operand of dW_0)
           reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] = make_uint4(h01, h23, l01, l23);
+          if (p.skip_ph0) {
+            // ... and the same coordinates as fp32 (x' = hi + bf16(lo), what the first layer's MMA multiplies): the
+            // layer-0 phases are NOT stashed (a fifth of the stash traffic); mlp_bwdp.cu recomputes theta_0 = w' x' + b'
+            // from these records, which take the place of the layer-0 phase tiles
+            float xf[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) xf[jj] = hi[jj] + __bfloat162float(__float2bfloat16_rn(lo[jj]));
+            reinterpret_cast<float4*>(p.stash_ph)[size_t(tile) * kTileRows + r] = make_float4(xf[0], xf[1], xf[2], xf[3]);
+          }
+        }
         if (kStashY)  // staged training: coordinate operand of dW_0 as a [128][64] block (cols 0..3 hi, 4..7 lo)
           *reinterpret_cast<uint4*>(p.stash_xa + size_t(tile) * (kTileRows * 128) + sw128_chunk_off(r, 0)) =
               make_uint4(h01, h23, l01, l23);
@@ -500,7 +512,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
           // phase stash: staged layout [H/8 chunks][128 rows][8]; pipelined layout two 64-row halves of padded chunks
           // (common.cuh: kPipePhChunk)
-          uint8_t* ph_l = !kStash ? nullptr
+          uint8_t* ph_l = (!kStash || (kMode == 2 && l == 0 && p.skip_ph0)) ? nullptr
                           : kMode == 2
                               ? p.stash_ph + size_t(l) * p.stash_layer_stride + size_t(tile) * kPipePhTile +
                                     size_t(r >> 6) * kPipePhHalf + size_t(r & 63) * 16
@@ -540,7 +552,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
             }
             constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
             emit_sine16<kStash, kPhStride, kRelu>(th, a_addr + kb * S::kABlock, r, s,
-                                                  kStash ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride : nullptr,
+                                                  (kStash && ph_l != nullptr)
+                                                      ? ph_l + size_t(kb * 8 + 2 * s) * kPhStride
+                                                      : nullptr,
                                                   kRelu && l == L);
           }
           if (trw) p.trace[tph * 8 + 6] = uint32_t(clock64() - t_begin);
@@ -752,6 +766,7 @@ static int launch_siren_fwd_impl(const b200inr_net* net, const void* packed, con
     p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
     p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
+    p.skip_ph0 = (kPipeSkipPh0 && net->hidden_layers >= 1) ? 1 : 0;
   }
   // persistent CTA pairs (clusters of 2) walk tile pairs: an even number of CTAs, at most one per SM, no more than
   // there are tile pairs (a single tile pair still runs on one CTA pair: the peer recomputes the last tile)

@@ -870,8 +870,11 @@ def test_pipelined_backward_vs_oracle_and_staged(dev, d, Lh, C, shape, drop):
 
 
 def test_pipelined_phase_stash_gives_layer_activations(dev, golden_dir):
-    """The pipelined training forward stashes only 16-bit phases: sin(phase) of the first and last sine layer must be
-    the reference's per-layer activations (same bar as the bf16 stash of the staged path)."""
+    """The pipelined training forward stashes only 16-bit phases: sin(phase) of the second and last sine layer must be
+    the reference's per-layer activations (same bar as the bf16 stash of the staged path).  The FIRST layer is not
+    stashed at all when the network has hidden layers: the backward recomputes its angle from the fp32 coordinate
+    records the forward leaves at the start of the layer-0 phase region, so those records must be the grid's coordinates
+    and give the reference's first-layer activations."""
     g, m = _golden_module(golden_dir, "siren_cfg2.npz", dev)
     _set_backward_path(m, True)
     shape = tuple(int(s) for s in g["grid_shape"])
@@ -889,9 +892,18 @@ def test_pipelined_phase_stash_gives_layer_activations(dev, golden_dir):
         a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 1, 3, 2, 4).reshape(tiles * 128, H)
         return a[:rows].astype(np.float32)
 
-    assert _relerr(layer_act(0), g["act_first"]) < BF16_RELERR
+    # layer 0: [tile][128 rows] x {x0, x1, x2, 0} fp32 in place of the phase tiles
+    xrec = stash[:tiles * 128 * 16].view(torch.float32).reshape(tiles * 128, 4)[:rows].cpu().numpy()
+    coords = O.get_mgrid(shape)
+    np.testing.assert_allclose(xrec[:, :3], coords, atol=2e-5)  # hi + lo of two bf16: 16 mantissa bits
+    assert not xrec[:, 3].any()
+    w0 = m.net[0].linear.weight.detach().cpu().numpy().astype(np.float64)
+    b0 = m.net[0].linear.bias.detach().cpu().numpy().astype(np.float64)
+    act0 = np.sin(m.first_omega_0 * (xrec[:, :3].astype(np.float64) @ w0.T + b0))
+    assert _relerr(act0, g["act_first"]) < BF16_RELERR
     assert _relerr(layer_act(nl - 1), g["act_last"]) < BF16_RELERR
     assert _relerr(out.cpu().numpy(), g["out"]) < BF16_RELERR
+    # (what the hidden layers' phases encode is pinned by the gradients: test_pipelined_backward_vs_oracle_and_staged)
 
 
 def test_pipelined_fit_matches_staged_fit(dev):
