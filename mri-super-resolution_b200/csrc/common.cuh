@@ -99,13 +99,20 @@ constexpr int kPipePhTile = 2 * kPipePhHalf;                         // one 128-
 // 1.27 / 1.27 / 1.36 ms (a ring has to absorb the jitter of its two ends; 16 costs more L2 than it buys)
 constexpr int kPipeRing = B200INR_PRING;
 constexpr int kPipeMaxEdges = 96;    // pipelines x (L+1) <= #SM / 2
-// Networks with at least one hidden layer do not stash the phases of layer 0: theta_0 = w' x' + b' is three FMAs per
-// element from the fp32 coordinate records the forward leaves in the first 16 bytes per row of the layer-0 phase region
-// (the other layers' phases would need their whole GEMM again).  A fifth of the stash traffic of both directions.
+// Networks with at least one hidden layer, evaluated on a coordinate GRID whose last axis and first row are multiples of
+// 16, do not stash the phases of layer 0: inside an aligned batch of 16 rows only the last coordinate changes, so
+// theta_0 = base + w_last x_last is ONE FMA and one 4-byte shared-memory read per element, from the fp32 coordinate
+// records (16 bytes per row) the forward leaves at the start of the layer-0 phase region.  (A per-row dot product from
+// the whole record was measured first: the same bytes broadcast to 32 lanes cost four times the shared-memory return
+// bandwidth of a 2-byte phase, the layer-1 CTAs fell behind and every pipeline with them: +7 %.)  A fifth of the stash
+// traffic of both directions.  The forward leaves what it did in word kPipeSkipWord of the calibration area.
 #ifndef B200INR_PSKIP0
 #define B200INR_PSKIP0 1
 #endif
 constexpr bool kPipeSkipPh0 = B200INR_PSKIP0 != 0;
+constexpr int kPipeCalRow = 176;     // first row of the profiling area used for launch-to-launch state (rows < grid <= 148
+                                     // belong to the profiling builds): [epoch, skip word, pad x14, 2 banks of speed records]
+constexpr int kPipeSkipWord = 1;
 struct PipeStashLayout {
   size_t ph;            // (L+1) x T x kPipePhTile bytes (see above)
   size_t layer_stride;  // bytes per layer inside ph

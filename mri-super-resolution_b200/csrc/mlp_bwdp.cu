@@ -53,6 +53,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -118,7 +120,7 @@ constexpr int kPPhPrefetch = B200INR_PPF;  // forward tiles of phases pulled int
 constexpr bool kPAdapt = B200INR_PADAPT != 0;
 constexpr uint32_t kCalMagic = 0xB2001A7Eu;
 constexpr int kCalBankWords = 4 * 32;  // per bank: 32 pipelines x {tiles, cycles, epoch, magic ^ P}
-constexpr int kCalRow = 176;           // first row of the profiling area used (CTAs write rows < grid <= 148)
+constexpr int kCalRow = kPipeCalRow;   // first row of the profiling area used (CTAs write rows < grid <= 148)
 #ifndef B200INR_PMC
 #define B200INR_PMC 0
 #endif
@@ -485,6 +487,8 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
   if (kPMc) cluster_sync_all();  // the peer's barriers exist before any multicast copy / remote commit reaches them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // did the forward leave coordinate records instead of layer-0 phases?  (its word in the stash; see common.cuh)
+  const bool skip0 = p.skip_ph0 != 0 && p.calib != nullptr && __ldcg(p.calib + kPipeSkipWord) != 0u;
   // tiles of this pipeline: forward tiles t_first .. t_first + my_fwd - 1; two 64-row tiles each
   const int t_first = int(share_s[0]);
   const int my_fwd = int(share_s[1]);
@@ -593,7 +597,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
             mbar_arrive(&bars[kBPhFull + slot]);
             continue;
           }
-          if (!edge && ph_layer == 0 && p.skip_ph0) {
+          if (!edge && ph_layer == 0 && skip0) {
             // layer 0 is not stashed: the tile's 64 coordinate records (fp32 x4, 1 KB) instead of 16.5 KB of phases
             mbar_arrive_expect_tx(&bars[kBPhFull + slot], kPipeTileRows * 16);
             bulk_g2s(smem + oPh + slot * kPPhSlot, p.ph + (size_t(T) * 128 + size_t(i & 1) * kPipeTileRows) * 16,
@@ -909,7 +913,7 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       // layer 0 not stashed (kPipeSkipPh0): the CTAs of layer 1 recompute theta_0[f][row] = w' x' + b' from the row's
       // coordinate record.  w', b' = bf16 hi + bf16 lo of omega_0 W_0 / omega_0 b_0, the operand pack.cu builds for the
       // forward's first-layer MMA, so that the angle is the forward's (to fp32 rounding).
-      const bool l0x = !edge && ph_layer == 0 && p.skip_ph0 != 0;
+      const bool l0x = !edge && ph_layer == 0 && skip0;
       float w0x = 0.f, w0y = 0.f, w0z = 0.f, w0w = 0.f, b0x = 0.f;
       if (l0x) {
         auto hilo = [](float v) {
@@ -923,6 +927,9 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
         w0w = hilo(w.w);
         b0x = hilo(__ldg(reinterpret_cast<const float*>(p.packed + p.pl.bias) + (h * 128 + f)));
       }
+      // inside an aligned batch of 16 grid rows only the LAST coordinate changes (the forward's condition for skipping)
+      const float w0l = p.d == 1 ? w0x : (p.d == 2 ? w0y : (p.d == 3 ? w0z : w0w));
+      const uint32_t lastoff = uint32_t(p.d - 1) * 4;
 
       if (!edge) {
         // ---- W'^T half -> TMEM (A operand of the chain MMA): lane = input feature 128 h + f, 2 bf16 per column along K
@@ -958,6 +965,11 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
       }
 
       if (grp == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);  // start the two groups half a cycle apart
+      // The tile loop exists twice in the binary -- with and without the recomputed layer-0 angle -- and a CTA runs one
+      // of them: as a uniform branch INSIDE the one loop the extra 2.5 KB of code cost every CTA 6 % (instruction-cache
+      // stalls 0.22 -> 0.36 per issue; the hot loops of this kernel live on the edge of the instruction cache).
+      auto tile_loop = [&](auto l0c) {
+      constexpr bool kL0 = decltype(l0c)::value;
       for (int i = 0; i < n; ++i) {
         if (kPGroupPh && (i & 1) != grp) continue;  // per-group phase slots: the other group's tiles are not our business
         const int ps = kPGroupPh ? ((i & 1) * 2 + ((i >> 1) & 1)) : i % nph;
@@ -997,21 +1009,20 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
 #pragma unroll
         for (int b2 = 0; b2 < 2; ++b2) {
           uint32_t ph[16], ys[8], ds[8];
-          float rd[16];
-          if (l0x) {  // (one uniform branch per batch of 16 rows: every CTA runs one side only)
+          if (kL0) {  // ph[j] = the bits of the recomputed angle (radians) of row 32 rh + 16 b2 + j:
+                      // base (the batch's first row without its last-axis term) + w_last x_last(row)
             const uint32_t xr = sbase + oPh + ps * kPPhSlot + (rh * 32 + 16 * b2) * 16;
+            const uint4 x0 = lds128(xr);
+            float base = fmaf(w0w, __uint_as_float(x0.w),
+                              fmaf(w0z, __uint_as_float(x0.z),
+                                   fmaf(w0y, __uint_as_float(x0.y), fmaf(w0x, __uint_as_float(x0.x), b0x))));
+            base = fmaf(-w0l, __uint_as_float(lds32(xr + lastoff)), base);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint4 x = lds128(xr + j * 16);
-              rd[j] = fmaf(w0w, __uint_as_float(x.w),
-                           fmaf(w0z, __uint_as_float(x.z),
-                                fmaf(w0y, __uint_as_float(x.y), fmaf(w0x, __uint_as_float(x.x), b0x))));
-            }
+            for (int j = 0; j < 16; ++j)
+              ph[j] = __float_as_uint(fmaf(w0l, __uint_as_float(lds32(xr + j * 16 + lastoff)), base));
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) ph[j] = lds16(ph_f + (16 * b2 + j) * 16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) rd[j] = rad_lo16(ph[j]);
           }
           if (b2 == 1) {  // all phases are in registers: hand the slot back
             __syncwarp();
@@ -1019,7 +1030,8 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float r0 = rd[2 * j], r1 = rd[2 * j + 1];
+            const float r0 = kL0 ? __uint_as_float(ph[2 * j]) : rad_lo16(ph[2 * j]);
+            const float r1 = kL0 ? __uint_as_float(ph[2 * j + 1]) : rad_lo16(ph[2 * j + 1]);
             if (kPKo & 1) {
               const float d0 = __uint_as_float(v[16 * b2 + 2 * j]) * r0, d1 = __uint_as_float(v[16 * b2 + 2 * j + 1]) * r1;
               dbsum += d0 + d1;
@@ -1068,6 +1080,14 @@ __global__ void B200INR_PCLUSTER __launch_bounds__(kPThreads, 1) siren_bwdp_kern
         if (tr_me) TR(16, i);
         if (prof_on) pw[8] += (unsigned long long)(clock64() - ts0);
       }
+      };
+#ifndef B200INR_PL0OFF
+#define B200INR_PL0OFF 0
+#endif
+      if (l0x && !B200INR_PL0OFF)  // (tuning: PL0OFF = 1 times the kernel with the stashed-phase arithmetic everywhere)
+        tile_loop(std::true_type{});
+      else
+        tile_loop(std::false_type{});
       if (end_on && threadIdx.x == kPFirstEpiWarp * 32)  // tile loop done, flush not started
         p.prof[size_t(blockIdx.x) * kPipeProfSlots + 1] = (unsigned long long)(clock64() - t_begin);
       if (threadIdx.x == kPFirstEpiWarp * 32) {
@@ -1185,7 +1205,7 @@ int launch_siren_bwdp(const b200inr_net* net, const void* packed, void* stash, c
   p.flags = reinterpret_cast<uint32_t*>(st + sl.flags);
   p.calib = reinterpret_cast<uint32_t*>(st + sl.prof + size_t(kCalRow) * kPipeProfSlots * 8);
   static_assert((kCalRow + 16) <= kPipeProfCtas && (16 + 2 * kCalBankWords) * 4 <= 16 * kPipeProfSlots * 8, "calibration area");
-  p.skip_ph0 = (kPipeSkipPh0 && L >= 1) ? 1 : 0;
+  p.skip_ph0 = kPipeSkipPh0 ? 1 : 0;  // (and the forward's word in the stash says whether it did skip them)
   p.grads = grad_params;
   int64_t off[2 * (kMaxSineLayers + 2)];
   param_offsets(p.d, p.Hr, L, p.C, off);

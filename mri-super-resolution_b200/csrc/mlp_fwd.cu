@@ -73,7 +73,8 @@ struct FwdParams {
   uint8_t* stash_y;   // nullptr => inference
   uint8_t* stash_ph;
   uint8_t* stash_xa;  // coordinate operand of the first-layer weight gradient (wgrad.cu)
-  int skip_ph0;       // pipelined training, L >= 1: layer-0 phases are recomputed by the backward (kPipeSkipPh0)
+  int skip_ph0;       // pipelined training: layer-0 phases are recomputed by the backward (kPipeSkipPh0)
+  uint32_t* skip_word;  // pipelined training: where the backward reads whether this forward skipped them
   size_t stash_layer_stride;
   uint32_t* trace;  // tuning aid (B200INR_FWD_TRACE_PTR): CTA 0 records [phase][8] event times, phase = (pair, layer, tile)
 };
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
   const int num_pairs = (my_tiles + 1) / 2;
   const bool tr = p.trace != nullptr && blockIdx.x == 0;
   const long long t_begin = tr ? clock64() : 0;
+  if (kMode == 2 && blockIdx.x == 0 && threadIdx.x == 0 && p.skip_word != nullptr) *p.skip_word = uint32_t(p.skip_ph0);
 
   if (warp == 0) {
     // =============================== weight producer ===============================
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
           reinterpret_cast<uint4*>(p.stash_xa)[size_t(tile) * kTileRows + r] = make_uint4(h01, h23, l01, l23);
           if (p.skip_ph0) {
             // ... and the same coordinates as fp32 (x' = hi + bf16(lo), what the first layer's MMA multiplies): the
-            // layer-0 phases are NOT stashed (a fifth of the stash traffic); mlp_bwdp.cu recomputes theta_0 = w' x' + b'
+            // layer-0 phases are NOT stashed (common.cuh: kPipeSkipPh0); mlp_bwdp.cu recomputes theta_0 = w' x' + b'
             // from these records, which take the place of the layer-0 phase tiles
             float xf[4];
 #pragma unroll
@@ -766,7 +768,13 @@ static int launch_siren_fwd_impl(const b200inr_net* net, const void* packed, con
     p.stash_ph = reinterpret_cast<uint8_t*>(stash) + sl.ph;
     p.stash_xa = reinterpret_cast<uint8_t*>(stash) + sl.xa;
     p.stash_layer_stride = sl.layer_stride;
-    p.skip_ph0 = (kPipeSkipPh0 && net->hidden_layers >= 1) ? 1 : 0;
+    // (the rule of common.cuh: a grid whose last axis and first row are multiples of 16)
+    p.skip_ph0 = (kPipeSkipPh0 && net->hidden_layers >= 1 && coords == nullptr && grid != nullptr &&
+                  grid->shape[grid->ndim - 1] % 16 == 0 && grid->row_begin % 16 == 0)
+                     ? 1
+                     : 0;
+    p.skip_word = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stash) + sl.prof +
+                                              size_t(kPipeCalRow) * kPipeProfSlots * 8) + kPipeSkipWord;
   }
   // persistent CTA pairs (clusters of 2) walk tile pairs: an even number of CTAs, at most one per SM, no more than
   // there are tile pairs (a single tile pair still runs on one CTA pair: the peer recomputes the last tile)

@@ -483,6 +483,11 @@ __device__ __forceinline__ unsigned long long f32x2(float a, float b) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
   return r;
 }
+__device__ __forceinline__ unsigned long long u32x2(uint32_t a, uint32_t b) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f32x2(a0, a1)), "l"(f32x2(b0, b1)));

@@ -842,7 +842,8 @@ def _set_backward_path(m, piped):
 
 
 @pytest.mark.parametrize("d,Lh,C,shape,drop", [(2, 2, 1, (64, 48), 0), (3, 4, 31, (32, 32, 16), 77),
-                                                 (3, 0, 5, (16, 16, 8), 0), (3, 4, 31, (64, 64, 32), 0)])
+                                                 (3, 0, 5, (16, 16, 8), 0), (3, 4, 31, (64, 64, 32), 0),
+                                                 (3, 4, 31, (20, 12, 10), 0), (4, 2, 3, (6, 5, 4, 16), 3)])
 def test_pipelined_backward_vs_oracle_and_staged(dev, d, Lh, C, shape, drop):
     """b200inr_siren_backward of a pipelined SIREN (ONE kernel: dgrad chain + all weight / bias gradients from the
     16-bit phase stash) against the NumPy oracle's hand-derived backward and against the staged kernels, incl. a
@@ -870,40 +871,48 @@ def test_pipelined_backward_vs_oracle_and_staged(dev, d, Lh, C, shape, drop):
 
 
 def test_pipelined_phase_stash_gives_layer_activations(dev, golden_dir):
-    """The pipelined training forward stashes only 16-bit phases: sin(phase) of the second and last sine layer must be
-    the reference's per-layer activations (same bar as the bf16 stash of the staged path).  The FIRST layer is not
-    stashed at all when the network has hidden layers: the backward recomputes its angle from the fp32 coordinate
-    records the forward leaves at the start of the layer-0 phase region, so those records must be the grid's coordinates
-    and give the reference's first-layer activations."""
+    """The pipelined training forward stashes only 16-bit phases: sin(phase) of the first and last sine layer must be
+    the reference's per-layer activations (same bar as the bf16 stash of the staged path).  On a grid whose last axis
+    and first row are multiples of 16 the FIRST layer is not stashed at all (csrc/common.cuh, kPipeSkipPh0): the
+    backward recomputes its angle from the fp32 coordinate records the forward leaves at the start of the layer-0 phase
+    region, so those records must be the grid's coordinates and give the first-layer activations; the forward says which
+    of the two it did in its word of the stash."""
     g, m = _golden_module(golden_dir, "siren_cfg2.npz", dev)
     _set_backward_path(m, True)
-    shape = tuple(int(s) for s in g["grid_shape"])
-    rows = int(np.prod(shape))
-    out, stash = m._forward_rows(None, L.make_grid(shape), rows, train=True)
-    torch.cuda.synchronize()
-    tiles = (rows + 127) // 128
     H, nl = 256, m.hidden_layers + 1
-    # layout (csrc/common.cuh, kPipePhTile): [layer][tile][64-row half][chunk of 8 features][64 rows x 8 u16 + 32 B pad]
-    chunk = 64 * 16 + 32
-    raw = stash[:nl * tiles * 2 * (H // 8) * chunk].reshape(nl, tiles, 2, H // 8, chunk)[..., :64 * 16].contiguous()
-    ph = raw.view(torch.int16).reshape(nl, tiles, 2, H // 8, 64, 8).cpu().numpy().astype(np.int64) & 0xFFFF
-
-    def layer_act(layer):  # [tiles][half][chunk][row][8] -> [rows, H]
-        a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 1, 3, 2, 4).reshape(tiles * 128, H)
-        return a[:rows].astype(np.float32)
-
-    # layer 0: [tile][128 rows] x {x0, x1, x2, 0} fp32 in place of the phase tiles
-    xrec = stash[:tiles * 128 * 16].view(torch.float32).reshape(tiles * 128, 4)[:rows].cpu().numpy()
-    coords = O.get_mgrid(shape)
-    np.testing.assert_allclose(xrec[:, :3], coords, atol=2e-5)  # hi + lo of two bf16: 16 mantissa bits
-    assert not xrec[:, 3].any()
+    chunk = 64 * 16 + 32  # layout (csrc/common.cuh, kPipePhTile): [layer][tile][64-row half][chunk of 8 features][64 rows x 8 u16 + 32 B pad]
     w0 = m.net[0].linear.weight.detach().cpu().numpy().astype(np.float64)
     b0 = m.net[0].linear.bias.detach().cpu().numpy().astype(np.float64)
-    act0 = np.sin(m.first_omega_0 * (xrec[:, :3].astype(np.float64) @ w0.T + b0))
-    assert _relerr(act0, g["act_first"]) < BF16_RELERR
-    assert _relerr(layer_act(nl - 1), g["act_last"]) < BF16_RELERR
-    assert _relerr(out.cpu().numpy(), g["out"]) < BF16_RELERR
-    # (what the hidden layers' phases encode is pinned by the gradients: test_pipelined_backward_vs_oracle_and_staged)
+    for shape, skipped in ((tuple(int(s) for s in g["grid_shape"]), 0), ((6, 5, 32), 1)):
+        rows = int(np.prod(shape))
+        out, stash = m._forward_rows(None, L.make_grid(shape), rows, train=True)
+        torch.cuda.synchronize()
+        tiles = (rows + 127) // 128
+        nbytes = L.stash_bytes(m._desc, rows)
+        state = stash[:nbytes][nbytes - 192 * 32 * 8 + 176 * 32 * 8:].view(torch.int32)
+        assert int(state[1].item()) == skipped
+        raw = stash[:nl * tiles * 2 * (H // 8) * chunk].reshape(nl, tiles, 2, H // 8, chunk)[..., :64 * 16].contiguous()
+        ph = raw.view(torch.int16).reshape(nl, tiles, 2, H // 8, 64, 8).cpu().numpy().astype(np.int64) & 0xFFFF
+
+        def layer_act(layer):  # [tiles][half][chunk][row][8] -> [rows, H]
+            a = np.sin(ph[layer] * (2.0 * np.pi / 65536.0)).transpose(0, 1, 3, 2, 4).reshape(tiles * 128, H)
+            return a[:rows].astype(np.float32)
+
+        coords = O.get_mgrid(shape)
+        act_first = np.sin(m.first_omega_0 * (coords.astype(np.float64) @ w0.T + b0))
+        if skipped:  # [tile][128 rows] x {x0, x1, x2, 0} fp32 in place of the layer-0 phase tiles
+            xrec = stash[:tiles * 128 * 16].view(torch.float32).reshape(tiles * 128, 4)[:rows].cpu().numpy()
+            np.testing.assert_allclose(xrec[:, :3], coords, atol=2e-5)  # hi + lo of two bf16: 16 mantissa bits
+            assert not xrec[:, 3].any()
+            act0 = np.sin(m.first_omega_0 * (xrec[:, :3].astype(np.float64) @ w0.T + b0))
+            assert _relerr(act0, act_first) < 1e-3
+        else:
+            assert _relerr(layer_act(0), g["act_first"]) < BF16_RELERR
+            assert _relerr(layer_act(0), act_first) < BF16_RELERR
+            assert _relerr(layer_act(nl - 1), g["act_last"]) < BF16_RELERR
+            assert _relerr(out.cpu().numpy(), g["out"]) < BF16_RELERR
+    # (what the hidden layers' phases encode on the second grid is pinned by the gradients:
+    #  test_pipelined_backward_vs_oracle_and_staged runs grids of both kinds)
 
 
 def test_pipelined_fit_matches_staged_fit(dev):
@@ -974,7 +983,8 @@ def test_pipelined_backward_adaptive_shares(dev):
     out, stash = m._forward_rows(None, grid, rows, train=True)
     nbytes = L.stash_bytes(m._desc, rows)
     cal = stash[:nbytes][nbytes - 192 * 32 * 8 + 176 * 32 * 8:].view(torch.int32)  # [epoch, pad x15, 2 banks x 32 x 4]
-    cal.zero_()  # (a module-level stash is uninitialised memory; FitSession's is zeroed)
+    cal[0] = 0  # (a module-level stash is uninitialised memory; FitSession's is zeroed.  Word 1 is the forward's)
+    cal[16:] = 0
     ref = m._backward_rows(stash, None, grid, rows, gout).clone()
     assert int(cal[0].item()) == 1  # the first launch (equal shares) has left its records
     epochs = [1]
