@@ -24,6 +24,11 @@ struct PackLayout {
   size_t wft;    // [1][H][64]           dgrad   B operand of the final linear (N = in, K = c padded to 64)
   size_t w0p;    // [1][H][64]           forward B operand of the FIRST layer on tensor cores (N = out, K = 32 used):
                  //                      omega0 * W0 and omega0 * b0 split into bf16 hi + lo parts, see pack.cu
+  size_t bias16; // __half[(L+1)*H + 32 + H]  the bias table once more in fp16 (same indices): what the forward's
+                 //                      epilogue adds -- every thread adds the same 64 biases per layer-tile to its row,
+                 //                      and as fp32 those broadcast loads were as many bytes into registers as the
+                 //                      accumulator itself (mlp_fwd.cu).  |omega b| < 4: half an fp16 ulp is < 1e-3 rad,
+                 //                      a third of what the bf16 operands already put into every angle.
   size_t total;
 };
 
@@ -45,6 +50,9 @@ __host__ __device__ inline PackLayout make_pack_layout(int H, int L) {
   o += size_t(H) * 128;
   p.w0p = o;
   o += size_t(H) * 128;
+  p.bias16 = o;
+  o += (size_t(L + 1) * H + 32 + H) * 2;
+  o = (o + 1023) & ~size_t(1023);
   p.total = o;
   return p;
 }

@@ -32,6 +32,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
     const uint32_t t_lane = uint32_t(q * 32) << 16;
     const float4* w0_g = reinterpret_cast<const float4*>(p.packed + p.pl.w0);
     const float* bias_g = reinterpret_cast<const float*>(p.packed + p.pl.bias);
+    const __half* bias16_g = reinterpret_cast<const __half*>(p.packed + p.pl.bias16);
     uint32_t nd[2] = {0, 0}, nf[2] = {0, 0};
     float loss_part = 0.f;  // kLoss: this thread's share of sum((pool(pred) - target)^2)
     // ---- first-layer operand of a tile: row r = [x_hi x_hi x_lo x_lo 1 1 0 ...] (bf16, K = 32 of block 0), so that
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
         for (int j = 0; j < nt; ++j) {
           const int tile = tile_of(pr, j);
           const uint32_t a_addr = smem_u32(a_smem) + j * S::kABytes;
-          const float* bl = (l == 0) ? bias_g + (L + 1) * H + 32 : bias_g + l * H;  // l = 0: H zeros
+          const __half* bl16 = bias16_g + ((l == 0) ? (L + 1) * H + 32 : l * H);  // l = 0: H zeros
           const uint32_t d_addr = tmem_d + t_lane + uint32_t(j) * 256 + s * 16;
           // phase stash: staged layout [H/8 chunks][128 rows][8]; pipelined layout two 64-row halves of padded chunks
           // (common.cuh: kPipePhChunk)
@@ -535,22 +538,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) siren_fwd_kernel(const FwdPara
 #pragma unroll
           for (int kb = 0; kb < S::kKB; ++kb) {
             const int col0 = kb * 64 + s * 16;
-            float4 bq[4];  // (layer 0: its bias is part of the GEMM; bl points at the zero block of the bias table)
+            // the 16 biases of these columns, fp16 (PackLayout::bias16; layer 0: its bias is part of the GEMM, bl16 points
+            // at the zero block): two 16-byte loads instead of four -- the same values go to all 32 lanes, and a
+            // broadcast still costs 32 x 16 bytes of L1 return bandwidth per load
+            uint4 bh[2];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(bl + col0 + j4 * 4));
+            for (int j8 = 0; j8 < 2; ++j8)
+              bh[j8] = (B200INR_FKO & 8) ? make_uint4(0u, 0u, 0u, 0u)
+                                         : __ldg(reinterpret_cast<const uint4*>(bl16 + col0 + j8 * 8));
             tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) v[jj] = vn[jj];
             if (kb + 1 < S::kKB) tmem_ld16(d_addr + (kb + 1) * 64, vn);
             float th[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {  // packed fp32x2 adds: 8 instructions for the 16 biases
-              th[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]);
-              th[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]);
-              th[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]);
-              th[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]);
-              add_f32x2(th[j4 * 4 + 0], th[j4 * 4 + 1], bq[j4].x, bq[j4].y);
-              add_f32x2(th[j4 * 4 + 2], th[j4 * 4 + 3], bq[j4].z, bq[j4].w);
+            for (int j8 = 0; j8 < 2; ++j8) {  // packed fp32x2 adds: 8 instructions for the 16 biases
+              const uint32_t w4[4] = {bh[j8].x, bh[j8].y, bh[j8].z, bh[j8].w};
+#pragma unroll
+              for (int q2 = 0; q2 < 4; ++q2) {
+                const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&w4[q2]));
+                th[j8 * 8 + q2 * 2 + 0] = __uint_as_float(v[j8 * 8 + q2 * 2 + 0]);
+                th[j8 * 8 + q2 * 2 + 1] = __uint_as_float(v[j8 * 8 + q2 * 2 + 1]);
+                add_f32x2(th[j8 * 8 + q2 * 2 + 0], th[j8 * 8 + q2 * 2 + 1], b2.x, b2.y);
+              }
             }
             constexpr int kPhStride = kMode == 2 ? kPipePhChunk : kTileRows * 16;
             emit_sine16<kStash, kPhStride, kRelu>(th, a_addr + kb * S::kABlock, r, s,

@@ -4,6 +4,8 @@
 // linear (INR/SRDWI.py:59).  The fused kernels consume theta = x (omega W)^T + omega b directly, so this kernel
 // folds omega into W and b while it converts to bf16 and lays every matrix out as SWIZZLE_128B tile blocks
 // (see umma.cuh).  It runs once per optimiser step (0.5 MB of output for BASELINE config 2).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
       if (c < C) v = p.params[p.off[2 * (L + 1) + 1] + c];
     }  // else: the zero block (written here once; the fused optimiser step never touches it)
     bias[i] = v;
+    reinterpret_cast<__half*>(p.packed + p.pl.bias16)[i] = __float2half_rn(v);
   }
   // hidden layers, both orientations
   const long long per_layer = (long long)H * H;
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const
     if (k == 0) {
       reinterpret_cast<float4*>(p.packed + p.pl.w0)[o] = make_float4(w0, w1, w2, w3);
       bias[o] = b;
+      reinterpret_cast<__half*>(p.packed + p.pl.bias16)[o] = __float2half_rn(b);
     }
     float v = 0.f;  // columns 4g + j (g = 0..3: hi lo hi lo), 16 = b_hi, 17 = b_lo, the rest zero (32..63 stay zero)
     if (k < 16) {
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(kAdamPackThreads) siren_adam_pack_kernel(const
       if (cc < C) v = adam_apply(a, c, p.off[2 * (L + 1) + 1] + cc);
     }
     bias[H + i] = v;
+    reinterpret_cast<__half*>(p.packed + p.pl.bias16)[H + i] = __float2half_rn(v);
   }
   adam_finish(a);
 }
