@@ -2,6 +2,7 @@
 // 2x2x1 pooling loss), Adam, plus get_mgrid / input_mapping for API parity.  All are coalesced along the fastest
 // axis, 128-bit vectorised where the extent allows, and launched on grids that are multiples of the SM count.
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace b200inr {
 
@@ -230,7 +231,31 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
 //   adjoint : dL/dpred = D^T 2 r / count.  A thread owns 4 zc of one HR column y and marches along x with a 3-deep window
 //             of y-filtered residual rows: 3 loads per LR row, two HR rows written per step.
 // HBM traffic is the algorithmic minimum (pred + target read, residual written and re-read from L2, gradient written).
-constexpr int kBandFwd = 6, kBandAdj = 3, kBlurChunk = 8;
+// A block is a TILE of kEwThreads / TJ zc vectors x TJ neighbouring columns (not kEwThreads consecutive zc of ONE column):
+// neighbouring columns share 4 of their 6 (2 of their 3) y taps, so inside a tile the shared rows are L1 hits and only
+// (2 TJ + 4) / (2 TJ) of the HR rows cross the L2 fabric instead of 3x (residual: 490 MB -> 185 MB at cfg4).
+#ifndef B200INR_BLUR_TILEJ
+#define B200INR_BLUR_TILEJ 16  // 1 = a block is kEwThreads consecutive zc vectors of one column (the first form of these kernels)
+#endif
+#ifndef B200INR_BLUR_CHUNK
+#define B200INR_BLUR_CHUNK 8
+#endif
+constexpr int kBandFwd = 6, kBandAdj = 3, kBlurChunk = B200INR_BLUR_CHUNK, kBlurTileJ = B200INR_BLUR_TILEJ;
+
+// tile t of a [chunks][ncol][zcv] index space -> this thread's (chunk, column, zc vector); false = outside the volume
+__device__ __forceinline__ bool blur_tile_index(long long t, int ncol, long long zcv, int& chunk, int& col, long long& zv) {
+  constexpr int TZ = kEwThreads / kBlurTileJ;
+  const long long tiles_z = (zcv + TZ - 1) / TZ;
+  const int tiles_j = (ncol + kBlurTileJ - 1) / kBlurTileJ;
+  zv = (t % tiles_z) * TZ + threadIdx.x % TZ;
+  col = int((t / tiles_z) % tiles_j) * kBlurTileJ + threadIdx.x / TZ;
+  chunk = int(t / (tiles_z * tiles_j));
+  return zv < zcv && col < ncol;
+}
+__host__ __device__ inline long long blur_tile_count(int chunks, int ncol, long long zcv) {
+  constexpr int TZ = kEwThreads / kBlurTileJ;
+  return (long long)chunks * ((ncol + kBlurTileJ - 1) / kBlurTileJ) * ((zcv + TZ - 1) / TZ);
+}
 
 template <int V>
 struct VecF {
@@ -267,6 +292,10 @@ struct BlurSlab {
   int xa;        // global x of the first plane of grad (adjoint)
 };
 
+// Taps that leave the volume carry ZERO weight in the band tables, so both kernels read them at the clamped position
+// instead of skipping them: without branches around the loads, everything a step needs (12 + 1 vector loads and the x taps
+// in the residual, 3 in the adjoint) is in flight before the first use.  The branchy first form of these kernels went
+// through ~8 serial DRAM round trips per LR row (80 us for the 195 MB of the cfg4 residual pass).
 template <int V>
 __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
     const float* __restrict__ pred, const float* __restrict__ target, int X, int Y, long long ZC,
@@ -275,50 +304,58 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
   const int YL = Y / 2;
   const long long zcv = ZC / V;
   const int chunks = (sb.ie1 - sb.ie0 + kBlurChunk - 1) / kBlurChunk;
-  const long long total = (long long)chunks * YL * zcv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long total = blur_tile_count(chunks, YL, zcv);
   pred -= (long long)sb.px0 * Y * ZC;                 // index with global plane / row numbers below
   target -= (long long)sb.ie0 * YL * ZC;
   resid -= (long long)sb.ie0 * YL * ZC;
+  const int xlo = sb.px0, xhi = min(2 * sb.ie1 + 1, X - 1);  // planes pred holds (clamp range of the x taps)
   float acc = 0.f;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
-    const long long zc = (t % zcv) * V;
-    const int j = int((t / zcv) % YL);
-    const int ic = int(t / (zcv * YL));
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    int ic, j;
+    long long zc;
+    if (!blur_tile_index(t, YL, zcv, ic, j, zc)) continue;
+    zc *= V;
     const int i0 = sb.ie0 + ic * kBlurChunk, i1 = min(i0 + kBlurChunk, sb.ie1);
     float wy[kBandFwd];
+    long long yoff[kBandFwd];
 #pragma unroll
-    for (int b = 0; b < kBandFwd; ++b) wy[b] = __ldg(by6 + j * kBandFwd + b);
-    // y-filtered HR row x of this column: sum_b wy[b] pred[x, 2j-2+b, zc]  (zero weight where the tap leaves the volume)
+    for (int b = 0; b < kBandFwd; ++b) {
+      wy[b] = __ldg(by6 + j * kBandFwd + b);
+      yoff[b] = (long long)min(max(2 * j - 2 + b, 0), Y - 1) * ZC + zc;
+    }
+    // y-filtered HR row x of this column: sum_b wy[b] pred[x, 2j-2+b, zc]
     auto row = [&](int x) {
+      const float* p = pred + (long long)min(max(x, xlo), xhi) * Y * ZC;
+      VecF<V> pv[kBandFwd];
+#pragma unroll
+      for (int b = 0; b < kBandFwd; ++b) pv[b] = ldv<V>(p + yoff[b]);
       VecF<V> s;
 #pragma unroll
       for (int e = 0; e < V; ++e) s.v[e] = 0.f;
-      if (x < 0 || x >= X) return s;
 #pragma unroll
-      for (int b = 0; b < kBandFwd; ++b) {
-        const int y = 2 * j - 2 + b;
-        if (y < 0 || y >= Y) continue;
-        const VecF<V> pv = ldv<V>(pred + ((long long)x * Y + y) * ZC + zc);
+      for (int b = 0; b < kBandFwd; ++b)
 #pragma unroll
-        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], pv.v[e], s.v[e]);
-      }
+        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], pv[b].v[e], s.v[e]);
       return s;
     };
     VecF<V> w[kBandFwd];
 #pragma unroll
     for (int a = 0; a < kBandFwd; ++a) w[a] = row(2 * i0 - 2 + a);
     for (int i = i0; i < i1; ++i) {
+      // this step's loads first: the two HR rows the NEXT LR row adds (past the chunk's end: a harmless clamped
+      // re-read), the target and the x taps
+      const VecF<V> n0 = row(2 * i + 4), n1 = row(2 * i + 5);
       const VecF<V> tg = ldv<V>(target + ((long long)i * YL + j) * ZC + zc);
+      float wx[kBandFwd];
+#pragma unroll
+      for (int a = 0; a < kBandFwd; ++a) wx[a] = __ldg(bx6 + i * kBandFwd + a);
       VecF<V> r;
 #pragma unroll
       for (int e = 0; e < V; ++e) r.v[e] = 0.f;
 #pragma unroll
-      for (int a = 0; a < kBandFwd; ++a) {
-        const float wx = __ldg(bx6 + i * kBandFwd + a);
+      for (int a = 0; a < kBandFwd; ++a)
 #pragma unroll
-        for (int e = 0; e < V; ++e) r.v[e] = fmaf(wx, w[a].v[e], r.v[e]);
-      }
+        for (int e = 0; e < V; ++e) r.v[e] = fmaf(wx[a], w[a].v[e], r.v[e]);
       const bool counts = (i >= sb.il0 && i < sb.il1);
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -326,50 +363,208 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_residual_kernel(
         if (counts) acc = fmaf(r.v[e], r.v[e], acc);
       }
       stv<V>(resid + ((long long)i * YL + j) * ZC + zc, r);
-      if (i + 1 < i1) {
 #pragma unroll
-        for (int a = 0; a < kBandFwd - 2; ++a) w[a] = w[a + 2];
-        w[kBandFwd - 2] = row(2 * i + 4);
-        w[kBandFwd - 1] = row(2 * i + 5);
-      }
+      for (int a = 0; a < kBandFwd - 2; ++a) w[a] = w[a + 2];
+      w[kBandFwd - 2] = n0;
+      w[kBandFwd - 1] = n1;
     }
   }
   if (loss_accum) block_accumulate(acc * inv_count, loss_accum);
+}
+
+// The residual pass as a bulk-copy pipeline (the form the vector path runs; the register-window kernel above stays for
+// ZC % 4 != 0 and as the `-DB200INR_BLUR_RING=0` build).  With per-thread loads a warp goes through one DRAM round trip
+// per LR row (the window march is a dependent chain) and only a third of the bytes in flight are new (neighbouring columns
+// share 4 of their 6 y taps): 2.7 TB/s.  Here a block owns a tile of kRingTJ LR columns x kRingTZ zc vectors x one chunk
+// of LR rows, and ONE producer warp streams everything the tile reads through a kRingStages-deep shared-memory ring:
+// stage k = the HR plane pair (2p, 2p+1), p = i0 - 1 + k -- per plane the 2 kRingTJ + 4 row segments of 16 kRingTZ bytes --
+// plus the target segments of LR row i0 + k - 2, each segment one `cp.async.bulk` (TMA engine, no tensor map) completing
+// on the stage's mbarrier.  Every byte crosses L2 -> SM once per tile and (kRingStages - 1) x 24 KB per block stay in
+// flight whatever the consumers do.  The 8 consumer warps (warp = LR column, lane = zc vector) take their 2 x 6 y taps and
+// their target vector from shared memory (16-byte reads, conflict free), release the stage, and advance the same 6-deep
+// window with the same arithmetic as above: both forms give identical bits.
+#ifndef B200INR_BLUR_RING
+#define B200INR_BLUR_RING 1
+#endif
+#ifndef B200INR_BLUR_RING_STAGES
+#define B200INR_BLUR_RING_STAGES 2
+#endif
+constexpr int kRingTJ = 8, kRingTZ = 32, kRingRows = 2 * kRingTJ + 4, kRingStages = B200INR_BLUR_RING_STAGES;
+constexpr int kRingSegBytes = kRingTZ * 16, kRingSegs = 2 * kRingRows + kRingTJ;  // 2 planes + 1 target row
+constexpr int kRingStageBytes = kRingSegs * kRingSegBytes;
+constexpr int kRingThreads = kRingTJ * 32 + 32;  // consumer warps + the producer warp
+#ifndef B200INR_BLUR_RING_CHUNK
+#define B200INR_BLUR_RING_CHUNK 16  // LR rows per tile when the volume has enough tiles (launch_blurpool_mse)
+#endif
+constexpr int kRingChunkMax = B200INR_BLUR_RING_CHUNK;
+constexpr int kRingSmem = kRingStages * kRingStageBytes + 2 * kRingStages * 8 + 16 + kRingChunkMax * kBandFwd * 4;
+
+__global__ void __launch_bounds__(kRingThreads) blurpool_residual_ring_kernel(
+    const float* __restrict__ pred, const float* __restrict__ target, int X, int Y, long long ZC,
+    const float* __restrict__ bx6, const float* __restrict__ by6, float inv_count, float* __restrict__ resid,
+    float* loss_accum, const BlurSlab sb, int chunk) {
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + kRingStages * kRingStageBytes);
+  uint64_t* empty = full + kRingStages;
+  float* loss_part = reinterpret_cast<float*>(empty + kRingStages);
+  float* wxs = loss_part + 4;  // x taps of the chunk's LR rows
+  const int YL = Y / 2;
+  const long long zcv = ZC / 4;
+  const int tiles_z = int((zcv + kRingTZ - 1) / kRingTZ), tiles_j = (YL + kRingTJ - 1) / kRingTJ;
+  const int tz = blockIdx.x % tiles_z, tj = (blockIdx.x / tiles_z) % tiles_j, ic = blockIdx.x / (tiles_z * tiles_j);
+  const int i0 = sb.ie0 + ic * chunk, i1 = min(i0 + chunk, sb.ie1);
+  const int nstage = (i1 - i0) + 2;  // plane pairs i0 - 1 .. i1
+  const long long zv0 = (long long)tz * kRingTZ;
+  const int nvec = int(min((long long)kRingTZ, zcv - zv0));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pred -= (long long)sb.px0 * Y * ZC;  // index with global plane / row numbers below
+  target -= (long long)sb.ie0 * YL * ZC;
+  resid -= (long long)sb.ie0 * YL * ZC;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kRingTJ);
+    }
+    *loss_part = 0.f;
+    fence_mbar_init();
+  }
+  for (int q = threadIdx.x; q < (i1 - i0) * kBandFwd; q += kRingThreads) wxs[q] = __ldg(bx6 + i0 * kBandFwd + q);
+  __syncthreads();
+  if (warp == kRingTJ) {
+    // ---- producer: segments 0 .. 2 kRingRows - 1 = the two planes' rows, the rest = the target row's columns.  Rows,
+    // planes and columns outside the volume are read at the clamped position (their taps have zero weight; the first two
+    // stages' target segments and those of columns past YL are never used).
+    const int xlo = sb.px0, xhi = min(2 * sb.ie1 + 1, X - 1);
+    const uint32_t bytes = uint32_t(nvec) * 16u;
+    for (int k = 0; k < nstage; ++k) {
+      const int slot = k % kRingStages;
+      if (k >= kRingStages) mbar_wait(&empty[slot], ((k / kRingStages) - 1) & 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full[slot], bytes * kRingSegs);
+      __syncwarp();
+      unsigned char* dst = ring_smem + slot * kRingStageBytes;
+      for (int g = lane; g < kRingSegs; g += 32) {
+        const float* src;
+        if (g < 2 * kRingRows) {
+          const int h = g / kRingRows, b = g % kRingRows;
+          const int x = min(max(2 * (i0 - 1 + k) + h, xlo), xhi);
+          const int y = min(max(2 * tj * kRingTJ - 2 + b, 0), Y - 1);
+          src = pred + ((long long)x * Y + y) * ZC;
+        } else {
+          const int i = min(max(i0 + k - 2, i0), i1 - 1);
+          const int j = min(tj * kRingTJ + (g - 2 * kRingRows), YL - 1);
+          src = target + ((long long)i * YL + j) * ZC;
+        }
+        bulk_g2s(dst + g * kRingSegBytes, src + zv0 * 4, bytes, &full[slot]);
+      }
+    }
+  } else {
+    // ---- consumers
+    const int j = tj * kRingTJ + warp;
+    const bool live = (j < YL) && (lane < nvec);
+    const long long zc = (zv0 + lane) * 4;
+    float wy[kBandFwd];
+#pragma unroll
+    for (int b = 0; b < kBandFwd; ++b) wy[b] = __ldg(by6 + min(j, YL - 1) * kBandFwd + b);
+    const uint32_t my = smem_u32(ring_smem) + uint32_t(lane) * 16;
+    float acc = 0.f;
+    VecF<4> w[kBandFwd];
+#pragma unroll
+    for (int a = 0; a < kBandFwd; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[a].v[e] = 0.f;
+    for (int k = 0; k < nstage; ++k) {
+      const int slot = k % kRingStages;
+      const uint32_t st = my + slot * kRingStageBytes;
+      mbar_wait(&full[slot], (k / kRingStages) & 1);
+      // lanes past nvec read stale shared memory: never stored, never counted
+      VecF<4> nw[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) nw[h].v[e] = 0.f;
+#pragma unroll
+        for (int b = 0; b < kBandFwd; ++b) {
+          const uint4 u = lds128(st + (h * kRingRows + 2 * warp + b) * kRingSegBytes);
+          nw[h].v[0] = fmaf(wy[b], __uint_as_float(u.x), nw[h].v[0]);
+          nw[h].v[1] = fmaf(wy[b], __uint_as_float(u.y), nw[h].v[1]);
+          nw[h].v[2] = fmaf(wy[b], __uint_as_float(u.z), nw[h].v[2]);
+          nw[h].v[3] = fmaf(wy[b], __uint_as_float(u.w), nw[h].v[3]);
+        }
+      }
+      const uint4 tgu = lds128(st + (2 * kRingRows + warp) * kRingSegBytes);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+#pragma unroll
+      for (int a = 0; a < kBandFwd - 2; ++a) w[a] = w[a + 2];
+      w[kBandFwd - 2] = nw[0];
+      w[kBandFwd - 1] = nw[1];
+      if (k >= 2) {
+        const int i = i0 + k - 2;
+        const float tg[4] = {__uint_as_float(tgu.x), __uint_as_float(tgu.y), __uint_as_float(tgu.z),
+                             __uint_as_float(tgu.w)};
+        VecF<4> r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r.v[e] = 0.f;
+#pragma unroll
+        for (int a = 0; a < kBandFwd; ++a) {
+          const float wx = wxs[(k - 2) * kBandFwd + a];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r.v[e] = fmaf(wx, w[a].v[e], r.v[e]);
+        }
+        const bool counts = live && (i >= sb.il0 && i < sb.il1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          r.v[e] -= tg[e];
+          if (counts) acc = fmaf(r.v[e], r.v[e], acc);
+        }
+        if (live) stv<4>(resid + ((long long)i * YL + j) * ZC + zc, r);
+      }
+    }
+    if (loss_accum) {
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(loss_part, acc);
+    }
+  }
+  __syncthreads();
+  if (loss_accum && threadIdx.x == 0) atomicAdd(loss_accum, *loss_part * inv_count);
 }
 
 template <int V>
 __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
     const float* __restrict__ resid, int X, int Y, long long ZC, const float* __restrict__ ax3,
     const float* __restrict__ ay3, float gscale, float* __restrict__ grad, const BlurSlab sb) {
-  const int XL = X / 2, YL = Y / 2;
+  const int YL = Y / 2;
   const long long zcv = ZC / V;
   const int chunks = (sb.il1 - sb.il0 + kBlurChunk - 1) / kBlurChunk;
-  const long long total = (long long)chunks * Y * zcv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long total = blur_tile_count(chunks, Y, zcv);
   resid -= (long long)sb.ie0 * YL * ZC;  // global LR row numbers below
   grad -= (long long)sb.xa * Y * ZC;     // global HR plane numbers below
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
-    const long long zc = (t % zcv) * V;
-    const int y = int((t / zcv) % Y);
-    const int mc = int(t / (zcv * Y));
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    int mc, y;
+    long long zc;
+    if (!blur_tile_index(t, Y, zcv, mc, y, zc)) continue;
+    zc *= V;
     const int m0 = sb.il0 + mc * kBlurChunk, m1 = min(m0 + kBlurChunk, sb.il1);
     const int j0 = (y - 2) >> 1;  // LR columns j0 .. j0+2 read HR column y
     float wy[kBandAdj];
+    long long joff[kBandAdj];
 #pragma unroll
-    for (int b = 0; b < kBandAdj; ++b) wy[b] = __ldg(ay3 + y * kBandAdj + b);
-    auto row = [&](int i) {  // y-filtered residual row i of this HR column
+    for (int b = 0; b < kBandAdj; ++b) {
+      wy[b] = __ldg(ay3 + y * kBandAdj + b);
+      joff[b] = (long long)min(max(j0 + b, 0), YL - 1) * ZC + zc;
+    }
+    auto row = [&](int i) {  // y-filtered residual row i of this HR column (rows resid holds: ie0 .. ie1-1)
+      const float* p = resid + (long long)min(max(i, sb.ie0), sb.ie1 - 1) * YL * ZC;
+      VecF<V> rv[kBandAdj];
+#pragma unroll
+      for (int b = 0; b < kBandAdj; ++b) rv[b] = ldv<V>(p + joff[b]);
       VecF<V> s;
 #pragma unroll
       for (int e = 0; e < V; ++e) s.v[e] = 0.f;
-      if (i < 0 || i >= XL) return s;
 #pragma unroll
-      for (int b = 0; b < kBandAdj; ++b) {
-        const int j = j0 + b;
-        if (j < 0 || j >= YL) continue;
-        const VecF<V> rv = ldv<V>(resid + ((long long)i * YL + j) * ZC + zc);
+      for (int b = 0; b < kBandAdj; ++b)
 #pragma unroll
-        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], rv.v[e], s.v[e]);
-      }
+        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], rv[b].v[e], s.v[e]);
       return s;
     };
     // HR rows 2m and 2m+1 are both read by the LR rows m-1, m, m+1
@@ -377,6 +572,12 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
 #pragma unroll
     for (int a = 0; a < kBandAdj; ++a) w[a] = row(m0 - 1 + a);
     for (int m = m0; m < m1; ++m) {
+      const VecF<V> nx = row(m + 2);  // the next step's row, in flight while this step's two HR rows are formed
+      float wx[2][kBandAdj];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int a = 0; a < kBandAdj; ++a) wx[h][a] = __ldg(ax3 + (2 * m + h) * kBandAdj + a);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int x = 2 * m + h;
@@ -384,20 +585,16 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
 #pragma unroll
         for (int e = 0; e < V; ++e) g.v[e] = 0.f;
 #pragma unroll
-        for (int a = 0; a < kBandAdj; ++a) {
-          const float wx = __ldg(ax3 + x * kBandAdj + a);
+        for (int a = 0; a < kBandAdj; ++a)
 #pragma unroll
-          for (int e = 0; e < V; ++e) g.v[e] = fmaf(wx, w[a].v[e], g.v[e]);
-        }
+          for (int e = 0; e < V; ++e) g.v[e] = fmaf(wx[h][a], w[a].v[e], g.v[e]);
 #pragma unroll
         for (int e = 0; e < V; ++e) g.v[e] *= gscale;
         stv<V>(grad + ((long long)x * Y + y) * ZC + zc, g);
       }
-      if (m + 1 < m1) {
-        w[0] = w[1];
-        w[1] = w[2];
-        w[2] = row(m + 2);
-      }
+      w[0] = w[1];
+      w[1] = w[2];
+      w[2] = nx;
     }
   }
 }
@@ -417,16 +614,33 @@ int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, in
   const bool vec = (ZC % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
                                       reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
   const long long zcv = vec ? ZC / 4 : ZC;
-  auto nblocks = [&](long long total) {
-    long long b = (total + kEwThreads - 1) / kEwThreads;
-    if (b > kSmCount * 16) b = kSmCount * 16;
-    return int(b < 1 ? 1 : b);
+  auto nblocks = [&](long long tiles) {  // one tile per block up to 16 blocks per SM, tile-strided beyond
+    if (tiles > kSmCount * 16) tiles = kSmCount * 16;
+    return int(tiles < 1 ? 1 : tiles);
   };
   const int chunks1 = (sb.ie1 - sb.ie0 + kBlurChunk - 1) / kBlurChunk;
   const int chunks2 = (sb.il1 - sb.il0 + kBlurChunk - 1) / kBlurChunk;
-  const int b1 = nblocks((long long)chunks1 * (Y / 2) * zcv), b2 = nblocks((long long)chunks2 * Y * zcv);
+  const int b1 = nblocks(blur_tile_count(chunks1, Y / 2, zcv)), b2 = nblocks(blur_tile_count(chunks2, Y, zcv));
   const float inv = float(1.0 / count), gsc = float(2.0 / count);
-  if (vec) {
+  if (vec && B200INR_BLUR_RING) {
+    static bool attr_set = false;  // idempotent; a race between host threads sets the same value twice
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(blurpool_residual_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem) !=
+          cudaSuccess)
+        return B200INR_ERR_CUDA;
+      attr_set = true;
+    }
+    // long tiles re-read fewer planes (chunk + 2 plane pairs per chunk rows), short ones keep every SM busy on a thin slab
+    const long long tiles_jz = (long long)((Y / 2 + kRingTJ - 1) / kRingTJ) * ((zcv + kRingTZ - 1) / kRingTZ);
+    const int rows = sb.ie1 - sb.ie0;
+    int chunk = kRingChunkMax;
+    while (chunk > 4 && ((rows + chunk - 1) / chunk) * tiles_jz < 2 * kSmCount) chunk /= 2;
+    const long long tiles = (long long)((rows + chunk - 1) / chunk) * tiles_jz;
+    if (tiles > 0x7fffffffLL) return B200INR_ERR_BAD_SHAPE;
+    blurpool_residual_ring_kernel<<<int(tiles), kRingThreads, kRingSmem, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv,
+                                                                                 resid, loss_accum, sb, chunk);
+    if (grad) blurpool_adjoint_kernel<4><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad, sb);
+  } else if (vec) {
     blurpool_residual_kernel<4><<<b1, kEwThreads, 0, stream>>>(pred, target, X, Y, ZC, bx6, by6, inv, resid, loss_accum, sb);
     if (grad) blurpool_adjoint_kernel<4><<<b2, kEwThreads, 0, stream>>>(resid, X, Y, ZC, ax3, ay3, gsc, grad, sb);
   } else {
