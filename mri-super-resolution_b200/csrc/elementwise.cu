@@ -240,6 +240,10 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
 #ifndef B200INR_BLUR_CHUNK
 #define B200INR_BLUR_CHUNK 8
 #endif
+#ifndef B200INR_BLUR_ADJ_AHEAD
+#define B200INR_BLUR_ADJ_AHEAD 1  // 2: 42 us instead of 40 (80 registers, 3 blocks per SM), 3: 55 us
+#endif
+constexpr int kAdjAhead = B200INR_BLUR_ADJ_AHEAD;  // residual rows in flight ahead of the adjoint's march
 constexpr int kBandFwd = 6, kBandAdj = 3, kBlurChunk = B200INR_BLUR_CHUNK, kBlurTileJ = B200INR_BLUR_TILEJ;
 
 // tile t of a [chunks][ncol][zcv] index space -> this thread's (chunk, column, zc vector); false = outside the volume
@@ -553,26 +557,41 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
       wy[b] = __ldg(ay3 + y * kBandAdj + b);
       joff[b] = (long long)min(max(j0 + b, 0), YL - 1) * ZC + zc;
     }
-    auto row = [&](int i) {  // y-filtered residual row i of this HR column (rows resid holds: ie0 .. ie1-1)
+    struct Raw {
+      VecF<V> t[kBandAdj];
+    };
+    auto load_row = [&](int i) {  // the three y taps of residual row i (rows resid holds: ie0 .. ie1-1), unfiltered
       const float* p = resid + (long long)min(max(i, sb.ie0), sb.ie1 - 1) * YL * ZC;
-      VecF<V> rv[kBandAdj];
+      Raw r;
 #pragma unroll
-      for (int b = 0; b < kBandAdj; ++b) rv[b] = ldv<V>(p + joff[b]);
+      for (int b = 0; b < kBandAdj; ++b) r.t[b] = ldv<V>(p + joff[b]);
+      return r;
+    };
+    auto filt = [&](const Raw& r) {
       VecF<V> s;
 #pragma unroll
       for (int e = 0; e < V; ++e) s.v[e] = 0.f;
 #pragma unroll
       for (int b = 0; b < kBandAdj; ++b)
 #pragma unroll
-        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], rv[b].v[e], s.v[e]);
+        for (int e = 0; e < V; ++e) s.v[e] = fmaf(wy[b], r.t[b].v[e], s.v[e]);
       return s;
     };
-    // HR rows 2m and 2m+1 are both read by the LR rows m-1, m, m+1
+    // HR rows 2m and 2m+1 are both read by the LR rows m-1, m, m+1.  The rows of the next kAdjAhead steps are in flight,
+    // UNFILTERED (the first use of a loaded value is what a warp waits at), while a step forms its two HR rows: a march
+    // with one row in flight waits a whole L2 / DRAM round trip per step.
     VecF<V> w[kBandAdj];
+    Raw q[kAdjAhead];
+    {
+      Raw p[kBandAdj];
 #pragma unroll
-    for (int a = 0; a < kBandAdj; ++a) w[a] = row(m0 - 1 + a);
+      for (int a = 0; a < kBandAdj; ++a) p[a] = load_row(m0 - 1 + a);
+#pragma unroll
+      for (int a = 0; a < kAdjAhead; ++a) q[a] = load_row(m0 + 2 + a);
+#pragma unroll
+      for (int a = 0; a < kBandAdj; ++a) w[a] = filt(p[a]);
+    }
     for (int m = m0; m < m1; ++m) {
-      const VecF<V> nx = row(m + 2);  // the next step's row, in flight while this step's two HR rows are formed
       float wx[2][kBandAdj];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
@@ -594,7 +613,10 @@ __global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
       }
       w[0] = w[1];
       w[1] = w[2];
-      w[2] = nx;
+      w[2] = filt(q[0]);
+#pragma unroll
+      for (int a = 0; a + 1 < kAdjAhead; ++a) q[a] = q[a + 1];
+      q[kAdjAhead - 1] = load_row(m + 2 + kAdjAhead);
     }
   }
 }

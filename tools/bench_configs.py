@@ -117,49 +117,66 @@ def perturb_fused_line(name, shape, steps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma-separated subset of cfg1,cfg2,cfg3,cfg4,cfg5,perturb,wireff")
     a = ap.parse_args()
+    only = set(a.only.split(",")) if a.only else None
+
+    def want(tag):
+        return only is None or tag in only
+
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     lines = []
     # cfg1: SIREN 2D slice fit 256x256, 3x256 hidden (Siren(2,256,2,1)), lr 3e-4
-    m = b200inr.Siren(2, 256, 2, 1).to(dev)
-    tgt = torch.rand(256 * 256, 1, device=dev)
-    lines.append(fit_line("cfg1 SIREN 2->3x256->1, 256x256 slice", m, tgt, (256, 256), None, 3e-4, 790016, a.steps * 5,
-                          graph=True))
+    if want("cfg1"):
+        m = b200inr.Siren(2, 256, 2, 1).to(dev)
+        tgt = torch.rand(256 * 256, 1, device=dev)
+        lines.append(fit_line("cfg1 SIREN 2->3x256->1, 256x256 slice", m, tgt, (256, 256), None, 3e-4, 790016,
+                              a.steps * 5, graph=True))
     # cfg2: SIREN 3D DWI fit with 2x LR-consistency loss
     hr_shape = (128, 128, 64)
     lr_t = torch.rand(64 * 64 * 64, 31, device=dev)
     m2 = b200inr.Siren(3, 256, 4, 31).to(dev)
-    lines.append(fit_line("cfg2 SIREN 3->5x256->31, 128x128x64, pooled loss", m2, lr_t, hr_shape, "pool", 1e-4, 1623552,
-                          a.steps))
+    if want("cfg2"):
+        lines.append(fit_line("cfg2 SIREN 3->5x256->31, 128x128x64, pooled loss", m2, lr_t, hr_shape, "pool", 1e-4,
+                              1623552, a.steps))
     # cfg3: WIRE on the same volume (point-wise loss on the HR grid), omega0 = s0 = 1.2, lr 5e-5
-    m3 = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
-    hr_t = torch.rand(128 * 128 * 64, 31, device=dev)
-    lines.append(fit_line("cfg3 WIRE 3->128c x(1+3)->31, 128x128x64", m3, hr_t, hr_shape, None, 5e-5, 2409984, a.steps))
-    lines.append(query_line("cfg3 WIRE query 128x128x64", m3, hr_shape, 803840, a.steps))
+    if want("cfg3"):
+        m3 = b200inr.Wire(3, 128, 3, 31, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2).to(dev)
+        hr_t = torch.rand(128 * 128 * 64, 31, device=dev)
+        lines.append(fit_line("cfg3 WIRE 3->128c x(1+3)->31, 128x128x64", m3, hr_t, hr_shape, None, 5e-5, 2409984,
+                              a.steps))
+        lines.append(query_line("cfg3 WIRE query 128x128x64", m3, hr_shape, 803840, a.steps))
+        del m3, hr_t
     # cfg4: Fourier-feature ReLU MLP (256 frequencies, 4x512) with the blur+pool degradation operator
-    B = np.random.RandomState(0).normal(size=(256, 3)) * 0.5
-    m4 = b200inr.FourierMLP(3, 256, 512, 3, 31, B).to(dev)
-    lines.append(fit_line("cfg4 FF(256)->ReLU 4x512->31, blur+pool loss", m4, lr_t, hr_shape, "blur_pool", 1e-4, 5863936,
-                          a.steps))
-    lines.append(query_line("cfg4 FF-ReLU query 128x128x64", m4, hr_shape, 2130432, a.steps))
+    if want("cfg4"):
+        B = np.random.RandomState(0).normal(size=(256, 3)) * 0.5
+        m4 = b200inr.FourierMLP(3, 256, 512, 3, 31, B).to(dev)
+        lines.append(fit_line("cfg4 FF(256)->ReLU 4x512->31, blur+pool loss", m4, lr_t, hr_shape, "blur_pool", 1e-4,
+                              5863936, a.steps))
+        lines.append(query_line("cfg4 FF-ReLU query 128x128x64", m4, hr_shape, 2130432, a.steps))
+        del m4
     # cfg5: 4x HR grid inference 512x512x256 x 31 channels with the cfg2 network (one GPU: the whole grid)
-    lines.append(query_line("cfg5 SIREN query 512x512x256 (whole grid on one GPU)", m2, (512, 512, 256), 541696, 3))
-    del m2, m3, m4
+    if want("cfg5"):
+        lines.append(query_line("cfg5 SIREN query 512x512x256 (whole grid on one GPU)", m2, (512, 512, 256), 541696, 3))
+    del m2
     torch.cuda.empty_cache()
-    lines.append(perturb_line("PerturbNet step (INR/inrDWI.py:141-147), Siren(256,512,3,1) + PN(256,128,3), 128x128x64",
-                              hr_shape, max(3, a.steps // 2)))
-    torch.cuda.empty_cache()
-    lines.append(perturb_fused_line("PerturbNet step, fused loop (perturb_fit), same sizes", hr_shape, max(3, a.steps // 2)))
-    torch.cuda.empty_cache()
+    if want("perturb"):
+        lines.append(perturb_line("PerturbNet step (INR/inrDWI.py:141-147), Siren(256,512,3,1) + PN(256,128,3), "
+                                  "128x128x64", hr_shape, max(3, a.steps // 2)))
+        torch.cuda.empty_cache()
+        lines.append(perturb_fused_line("PerturbNet step, fused loop (perturb_fit), same sizes", hr_shape,
+                                        max(3, a.steps // 2)))
+        torch.cuda.empty_cache()
     # WIRE the way the notebook feeds it (wiretest.ipynb cell 7): 512 Fourier features of a 4-D grid -> 128c x (1 + 3) -> 1
-    Bw = np.random.RandomState(2).normal(size=(256, 4)) * 0.5
-    mw = b200inr.Wire(4, 128, 3, 1, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2, B=Bw).to(dev)
-    wshape = (64, 64, 64, 4)
-    wt = torch.rand(int(np.prod(wshape)), 1, device=dev)
-    flop_w = 6 * (512 * 256 + 3 * 256 * 512 + 256) - 2 * 512 * 256
-    lines.append(fit_line("WIRE on 512 Fourier features (wiretest.ipynb cell 7), 64x64x64x4 grid", mw, wt, wshape, None,
-                          5e-5, flop_w, a.steps))
+    if want("wireff"):
+        Bw = np.random.RandomState(2).normal(size=(256, 4)) * 0.5
+        mw = b200inr.Wire(4, 128, 3, 1, first_omega_0=1.2, hidden_omega_0=1.2, scale=1.2, B=Bw).to(dev)
+        wshape = (64, 64, 64, 4)
+        wt = torch.rand(int(np.prod(wshape)), 1, device=dev)
+        flop_w = 6 * (512 * 256 + 3 * 256 * 512 + 256) - 2 * 512 * 256
+        lines.append(fit_line("WIRE on 512 Fourier features (wiretest.ipynb cell 7), 64x64x64x4 grid", mw, wt, wshape,
+                              None, 5e-5, flop_w, a.steps))
     for ln in lines:
         print(json.dumps(ln), flush=True)
 
