@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kRingThreads) blurpool_residual_ring_kernel(
 }
 
 template <int V>
-__global__ void __launch_bounds__(kEwThreads) blurpool_adjoint_kernel(
+__global__ void __launch_bounds__(kEwThreads, 4) blurpool_adjoint_kernel(
     const float* __restrict__ resid, int X, int Y, long long ZC, const float* __restrict__ ax3,
     const float* __restrict__ ay3, float gscale, float* __restrict__ grad, const BlurSlab sb) {
   const int YL = Y / 2;
@@ -645,13 +645,10 @@ int launch_blurpool_mse(const float* pred, const float* target, int X, int Y, in
   const int b1 = nblocks(blur_tile_count(chunks1, Y / 2, zcv)), b2 = nblocks(blur_tile_count(chunks2, Y, zcv));
   const float inv = float(1.0 / count), gsc = float(2.0 / count);
   if (vec && B200INR_BLUR_RING) {
-    static bool attr_set = false;  // idempotent; a race between host threads sets the same value twice
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(blurpool_residual_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem) !=
-          cudaSuccess)
-        return B200INR_ERR_CUDA;
-      attr_set = true;
-    }
+    // per launch, like the other launchers: the attribute belongs to the CURRENT device's copy of the function
+    if (cudaFuncSetAttribute(blurpool_residual_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem) !=
+        cudaSuccess)
+      return B200INR_ERR_CUDA;
     // long tiles re-read fewer planes (chunk + 2 plane pairs per chunk rows), short ones keep every SM busy on a thin slab
     const long long tiles_jz = (long long)((Y / 2 + kRingTJ - 1) / kRingTJ) * ((zcv + kRingTZ - 1) / kRingTZ);
     const int rows = sb.ie1 - sb.ie0;
