@@ -1597,6 +1597,47 @@ def test_blurpool_slabs_equal_whole_volume(dev, shape, C, cuts):
     assert bad != 0  # odd slab bounds are refused
 
 
+def test_blurpool_full_tiles_and_chunking(dev):
+    """The blurred pooling loss where the bulk-copy ring runs with FULL tiles and long chunks (the small cases above
+    always get 4-row chunks and partly filled tiles): 64x64 in-plane, ZC = 4736 (37 tiles of 32 vectors), so the whole
+    volume is cut into 16-row chunks and the two slabs into 8- and 16-row chunks.  D acts on x, y only, so 48 random zc
+    columns are checked against the oracle's dense operator; slabs must reproduce the whole-volume call bit for bit
+    whatever the chunking."""
+    X, Y, Z, C = 64, 64, 148, 32
+    ZC = Z * C
+    gen = torch.Generator(device=dev).manual_seed(5)
+    pred = torch.rand(X, Y, ZC, device=dev, generator=gen)
+    target = torch.rand(X // 2, Y // 2, ZC, device=dev, generator=gen)
+    count = float(target.numel())
+    (bx6, ax3), (by6, ay3) = [tuple(torch.from_numpy(t).to(dev) for t in L.build_band_tables(n, True)) for n in (X, Y)]
+    lib = L.load()
+    resid, grad, loss = torch.empty_like(target), torch.empty_like(pred), torch.zeros(1, device=dev)
+    L.check(lib.b200inr_blurpool_mse(_ptr(pred), _ptr(target), X, Y, ZC, count, _ptr(bx6), _ptr(by6), _ptr(ax3),
+                                     _ptr(ay3), _ptr(resid), _ptr(grad), _ptr(loss), _stream()), "blurpool_mse")
+    torch.cuda.synchronize()
+    cols = torch.from_numpy(np.random.RandomState(3).choice(ZC, 48, replace=False)).to(dev)
+    hr = pred[:, :, cols].cpu().numpy().reshape(X, Y, 48, 1)
+    tg = target[:, :, cols].cpu().numpy().reshape(X // 2, Y // 2, 48, 1)
+    d_ref = O.degrade_forward(hr, True) - tg
+    g_ref = O.degrade_adjoint((2.0 * d_ref / count).astype(np.float32), True)
+    np.testing.assert_allclose(resid[:, :, cols].cpu().numpy().reshape(d_ref.shape), d_ref, atol=3e-6)
+    np.testing.assert_allclose(grad[:, :, cols].cpu().numpy().reshape(g_ref.shape), g_ref, atol=3e-6 / count * 4 + 1e-12)
+    want = float((resid.double() ** 2).mean().item())
+    assert abs(loss.item() - want) <= 1e-4 * want
+    total = 0.0
+    for xa, xb in ((0, 16), (16, 64)):
+        p_ext = pred[max(xa - 4, 0):min(xb + 4, X)].contiguous()
+        t_ext = target[max(xa // 2 - 1, 0):min(xb // 2 + 1, X // 2)].contiguous()
+        r_ext, g_own, l_own = torch.empty_like(t_ext), torch.empty_like(pred[xa:xb]), torch.zeros(1, device=dev)
+        L.check(lib.b200inr_blurpool_mse_slab(_ptr(p_ext), _ptr(t_ext), X, Y, ZC, count, _ptr(bx6), _ptr(by6),
+                                              _ptr(ax3), _ptr(ay3), xa, xb, _ptr(r_ext), _ptr(g_own), _ptr(l_own),
+                                              _stream()), "blurpool_mse_slab")
+        assert torch.equal(g_own, grad[xa:xb]), (xa, xb)
+        assert torch.equal(r_ext, resid[max(xa // 2 - 1, 0):min(xb // 2 + 1, X // 2)])
+        total += l_own.item()
+    assert abs(total - loss.item()) <= 1e-4 * loss.item()
+
+
 # ------------------------------------------------------------------------------------------------ soft-ERD path
 def test_relu_tail_siren_vs_reference_golden(dev, golden_dir):
     """SirenERD (INR/INR_ERD.py:28-67) through the fused kernels against the unmodified reference class: seeded

@@ -441,3 +441,39 @@ def test_nn_mri_surface():
     want = (torch.from_numpy(np.array(imgs[0])).float() / 255.0 - 0.5) / 0.5
     assert torch.allclose(ds.pixels[0].reshape(8, 8), want, atol=1e-6)
     assert ds.mean.shape == (8, 8) and ds.shape == (8, 8)
+
+
+def _run_bench(*args, timeout=300):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    return subprocess.run([sys.executable, os.path.join(root, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=timeout, cwd=root, env=env)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU path of the reference, timed on the host cores through the oracle port):
+    one JSON line with the main arm's metric / unit / workload, `impl`, a `cpu_baseline` describing this run and an
+    `e2e` object without device copies."""
+    import json
+    res = _run_bench("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "inr_train_coord_samples_per_s"
+    assert d["unit"] == "coord-samples/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("cfg2") and "128x128x64x31" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None
+
+
+def test_bench_main_arm_fails_loudly_without_gpu():
+    """The product arm has no CPU fallback: without a CUDA device `bench.py` exits non-zero and prints no result line."""
+    res = _run_bench("--steps", "1", "--warmup", "1", timeout=120)
+    assert res.returncode != 0 and "needs a CUDA device" in res.stderr
+    assert not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
