@@ -477,3 +477,25 @@ def test_bench_main_arm_fails_loudly_without_gpu():
     res = _run_bench("--steps", "1", "--warmup", "1", timeout=120)
     assert res.returncode != 0 and "needs a CUDA device" in res.stderr
     assert not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line():
+    """Launched the way the driver launches N > 1 (torchrun, one process per GPU), only rank 0 times the CPU path and
+    prints the line; the other ranks exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
