@@ -225,15 +225,16 @@ int launch_taps(const float* in, float* out, int in_y, int out_x, int out_y, int
 // D = (2x2x1 average) o (5-tap Gaussian, sigma 0.5, mirror boundary) is separable and BANDED: LR row i reads HR rows
 // 2i-2 .. 2i+3 (6 dense taps per axis, mirror-merged weights; zeros outside the volume), and HR row x is read by the LR
 // rows ((x-2)>>1) .. +2 (3 dense taps).  Two streaming passes replace the three generic tap kernels:
-//   residual: r = D pred - target (+ the loss).  A thread owns 4 consecutive zc of one LR column j and MARCHES along x with
-//             a 6-deep register window of y-filtered rows, so every new LR row costs 12 loads (2 new HR rows x 6 y taps,
-//             float4, coalesced along zc; the y neighbours come from L1) instead of 36;
+//   residual: r = D pred - target (+ the loss).  Vector path: blurpool_residual_ring_kernel (below: a bulk-copy ring feeds
+//             a 6-deep register window of y-filtered planes that marches along x).  Scalar path (ZC % 4 != 0) and
+//             -DB200INR_BLUR_RING=0: blurpool_residual_kernel, the same march with per-thread loads (12 per LR row: 2 new
+//             HR rows x 6 y taps, coalesced along zc);
 //   adjoint : dL/dpred = D^T 2 r / count.  A thread owns 4 zc of one HR column y and marches along x with a 3-deep window
 //             of y-filtered residual rows: 3 loads per LR row, two HR rows written per step.
 // HBM traffic is the algorithmic minimum (pred + target read, residual written and re-read from L2, gradient written).
-// A block is a TILE of kEwThreads / TJ zc vectors x TJ neighbouring columns (not kEwThreads consecutive zc of ONE column):
-// neighbouring columns share 4 of their 6 (2 of their 3) y taps, so inside a tile the shared rows are L1 hits and only
-// (2 TJ + 4) / (2 TJ) of the HR rows cross the L2 fabric instead of 3x (residual: 490 MB -> 185 MB at cfg4).
+// In the per-thread-load kernels a block is a TILE of kEwThreads / TJ zc vectors x TJ neighbouring columns: neighbouring
+// columns share 4 of their 6 (2 of their 3) y taps, so inside a tile the shared rows are L1 hits.  (Measured: no faster
+// than kEwThreads consecutive zc of ONE column, TJ = 1 -- the L2 fabric was not what these kernels wait for; DESIGN.md.)
 #ifndef B200INR_BLUR_TILEJ
 #define B200INR_BLUR_TILEJ 16  // 1 = a block is kEwThreads consecutive zc vectors of one column (the first form of these kernels)
 #endif
